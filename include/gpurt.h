@@ -1,0 +1,249 @@
+/*
+ * gpurt.h — C ABI of libgpurt.so: the B200-native replacement for GPU-RT's ray-tracing hot path.
+ *
+ * Drop-in boundary.  Each entry point names the reference interface it replaces;
+ * citations are relative to the reference root.  The reference calls these interfaces as C++
+ * classes in namespace VK from GPURT (src/gpurt.cpp:39-45, :216-241); the shim that re-creates
+ * VK::Accel / VK::RTPipe on top of this header is gpu-rt_b200/host/rtpipe.h and the maintainer-side
+ * binding is shown in INTEGRATION.md.
+ *
+ * Conventions: every function returns 0 on success and a negative GPURT_E_* code on failure, never
+ * exits (the reference's VK_CHECK -> die() -> exit(), src/vk/vulkan.h:26-33, is replaced by error
+ * codes + gpurt_last_error()).  Handles are opaque.  One gpurt_ctx per GPU, used from one host
+ * thread at a time.  `mem` says where ray/query/result buffers live: GPURT_MEM_HOST buffers are
+ * staged through pinned memory inside the call; GPURT_MEM_DEVICE buffers are used in place and the
+ * call is asynchronous on the context's stream.  There is NO CPU fallback: compute entry points fail
+ * with GPURT_E_NO_DEVICE when no B200 is present.
+ */
+#ifndef GPURT_H
+#define GPURT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPURT_OK 0
+#define GPURT_E_INVALID (-1)   /* bad argument */
+#define GPURT_E_NO_DEVICE (-2) /* CUDA device missing / wrong ordinal */
+#define GPURT_E_CUDA (-3)      /* CUDA runtime error, see gpurt_last_error() */
+#define GPURT_E_IO (-4)        /* scene file could not be read / parsed */
+#define GPURT_E_STATE (-5)     /* call order (e.g. render before accel build) */
+
+#define GPURT_MEM_HOST 0
+#define GPURT_MEM_DEVICE 1
+
+#define GPURT_NO_HIT 0xFFFFFFFFu
+
+typedef struct gpurt_ctx gpurt_ctx;
+typedef struct gpurt_scene gpurt_scene;
+typedef struct gpurt_accel gpurt_accel;
+typedef struct gpurt_pipe gpurt_pipe;
+
+/* ---- POD records ----------------------------------------------------------------------------- */
+
+/* traceRayEXT arguments (src/shaders/rt/rt.rgen:257-270): origin, tmin, direction, tmax. 32 B. */
+typedef struct GpurtRay {
+    float o[3], tmin;
+    float d[3], tmax;
+} GpurtRay;
+
+/* Ray_Payload (src/shaders/rt/rtcommon.glsl:55-60) as written by rt.rchit:11-16 / rt.rmiss:9-11.
+ * barycentrics = (1-u-v, u, v).  prim is the GLOBAL triangle id: objects in Scene order
+ * (Scene::for_objs), triangles in index-buffer order; gpurt_scene_tri_offsets() maps it back to
+ * (gl_InstanceCustomIndexEXT, gl_PrimitiveID).  Miss: t=+inf, prim=GPURT_NO_HIT. 16 B. */
+typedef struct GpurtHit {
+    float t, u, v;
+    uint32_t prim;
+} GpurtHit;
+
+/* Closest-point query (FCPW-GPU branch, README.md:6-8): point + squared search radius. 16 B. */
+typedef struct GpurtQuery {
+    float p[3], r2;
+} GpurtQuery;
+
+/* Closest point, its distance, the triangle (global id, object id) and barycentrics (weights of
+ * vertex 1 and 2).  Nothing within the radius: dist=+inf, prim=GPURT_NO_HIT. 32 B. */
+typedef struct GpurtClosestPoint {
+    float p[3], dist;
+    uint32_t prim, obj;
+    float u, v;
+} GpurtClosestPoint;
+
+/* Material (src/scene/material.h:15-21), packed like Scene_Desc's tail (src/vk/rt.h:70-77). */
+typedef struct GpurtMaterial {
+    float albedo[3];
+    int32_t albedo_tex;
+    float emissive[3];
+    int32_t emissive_tex;
+    float metal_rough[2];
+    int32_t metal_rough_tex;
+    int32_t normal_tex;
+} GpurtMaterial;
+
+/* Scene_Desc (src/vk/rt.h:67-78, GLSL Scene_Obj rtcommon.glsl:10-21). 208 B. */
+typedef struct GpurtSceneDesc {
+    float model[16], modelIT[16]; /* column-major */
+    float albedo[4], emissive[4], metal_rough[4];
+    int32_t albedo_tex, emissive_tex, metal_rough_tex, normal_tex;
+    uint32_t index;
+    uint32_t _pad[3];
+} GpurtSceneDesc;
+
+/* Scene_Light (src/vk/rt.h:79-84). 48 B. */
+typedef struct GpurtSceneLight {
+    float bmin[4], bmax[4];
+    uint32_t index, n_triangles;
+    uint32_t _pad[2];
+} GpurtSceneLight;
+
+/* RTPipe_Constants (src/vk/rt.h:85-102; GLSL push constants rtcommon.glsl:77-95). 88 B.
+ * `frame` is maintained by the pipe exactly like RTPipe::trace (src/vk/rt.cpp:353-368);
+ * n_lights / n_objs are filled from the scene.  `seed` replaces clockARB() in
+ * rt.rgen:569: the per-pixel stream is tea(pixel, seed ^ frame). */
+typedef struct GpurtConstants {
+    float clear_col[4];
+    float env_light[4];
+    int32_t frame, samples, max_frame, qmc, max_depth, use_normal_map, use_metalness, use_temporal,
+        integrator, brdf, debug_view, use_rr, n_lights, n_objs;
+} GpurtConstants;
+
+/* UBO (src/vk/rt.h:104-117): camera matrices + ReSTIR constants, all column-major. */
+typedef struct GpurtCamera {
+    float V[16], P[16], iV[16], iP[16];
+    float prev_PV[16];
+    uint32_t new_samples, temporal_multiplier;
+} GpurtCamera;
+
+/* RTPipe public tunables (src/vk/rt.h:38-53), same defaults. */
+typedef struct GpurtPipeParams {
+    int32_t max_frames, samples_per_frame, max_depth;
+    float clear[3], env[3], env_scale;
+    int32_t use_normal_map, use_rr, use_metalness, use_qmc, use_temporal, integrator,
+        temporal_scale, brdf, debug_view, res_samples;
+    uint32_t seed; /* SURVEY Q1 */
+} GpurtPipeParams;
+
+typedef struct GpurtAccelInfo {
+    uint32_t n_tris, n_objs;
+    uint32_t n_bvh2_nodes;       /* n_tris-1 */
+    uint32_t n_wide_nodes;       /* 80-byte 8-wide nodes */
+    uint32_t wide_depth;         /* levels of the wide tree */
+    float scene_min[3], scene_max[3];
+    float inflation;             /* conservative AABB padding, DESIGN.md §3 N7 */
+    float build_ms;              /* device time of the last build */
+    uint64_t node_bytes, tri_bytes;
+} GpurtAccelInfo;
+
+/* traversal statistics from the instrumented kernel (N_node, N_tri per ray) */
+typedef struct GpurtTraceStats {
+    uint64_t rays, nodes_visited, tris_tested, hits;
+} GpurtTraceStats;
+
+/* ---- errors ---------------------------------------------------------------------------------- */
+const char* gpurt_last_error(void);
+const char* gpurt_version(void);
+
+/* ---- context: replaces the VK::Manager singleton (src/vk/vulkan.cpp:17-20, :1136-1160) -------- */
+int gpurt_ctx_create(int device_ordinal, gpurt_ctx** out);
+int gpurt_ctx_destroy(gpurt_ctx* ctx);
+/* Use a caller-owned cudaStream_t (e.g. torch's current stream); NULL = context's own stream. */
+int gpurt_ctx_set_stream(gpurt_ctx* ctx, void* cuda_stream);
+int gpurt_ctx_synchronize(gpurt_ctx* ctx);
+
+/* ---- scene: replaces Scene (src/scene/scene.h:18-42) + RTPipe::build_desc (src/vk/rt.cpp:26-76) */
+/* ctx may be NULL for host-only use (loading / packing); such a scene cannot be built. */
+int gpurt_scene_create(gpurt_ctx* ctx, gpurt_scene** out);
+int gpurt_scene_destroy(gpurt_scene* scene);
+/* Scene::load (src/scene/scene.cpp:317-391): glTF / GLB -> objects (one per primitive) + textures;
+ * `scale` is Scene::scale (scene.h:42). Object order = Scene::for_objs order. */
+int gpurt_scene_load_gltf(gpurt_scene* scene, const char* path, float scale);
+/* Procedural stand-in for media/sponza (Sponza.bin is missing from the reference snapshot):
+ * same triangle count (262,267), object count (103) and object-space extent. */
+int gpurt_scene_make_sponza_standin(gpurt_scene* scene);
+/* Object(id,pose,mesh,material) (src/scene/object.h:15): verts are Mesh::Vertex, 48-byte stride
+ * (src/vk/mesh.h:16-22); model is scale*pose.transform() column-major (src/gpurt.cpp:228-231). */
+int gpurt_scene_add_object(gpurt_scene* scene, const void* verts48, uint32_t n_verts,
+                           const uint32_t* indices, uint32_t n_indices, const float model[16],
+                           const GpurtMaterial* material, uint32_t* out_obj_index);
+/* RTPipe::build_textures (src/vk/rt.cpp:430-455): RGBA8, sampled as sRGB, linear, repeat. */
+int gpurt_scene_add_texture(gpurt_scene* scene, const uint8_t* rgba8, uint32_t w, uint32_t h,
+                            int32_t* out_tex_index);
+int gpurt_scene_counts(const gpurt_scene* scene, uint32_t* n_objs, uint32_t* n_tris,
+                       uint32_t* n_lights, uint32_t* n_textures);
+/* n_objs+1 prefix offsets: global prim id -> (object, primitive). */
+int gpurt_scene_tri_offsets(const gpurt_scene* scene, uint32_t* out_offsets);
+int gpurt_scene_get_descs(const gpurt_scene* scene, GpurtSceneDesc* out_descs);
+int gpurt_scene_get_lights(const gpurt_scene* scene, GpurtSceneLight* out_lights);
+int gpurt_scene_object_sizes(const gpurt_scene* scene, uint32_t obj, uint32_t* n_verts,
+                             uint32_t* n_indices);
+int gpurt_scene_get_object(const gpurt_scene* scene, uint32_t obj, void* out_verts48,
+                           uint32_t* out_indices);
+
+/* ---- camera: Camera (src/util/camera.cpp:58-71, :150-155) + RTPipe::update_uniforms ------------ */
+/* mode 0: Camera::reset() defaults; mode 1: look_at(center,pos) + vfov. Fills V,P,iV,iP. */
+int gpurt_camera_make(int mode, float width, float height, const float pos[3],
+                      const float center[3], float vfov_deg, GpurtCamera* out);
+
+/* ---- acceleration structure: replaces VK::Accel (src/vk/vulkan.h:256-284) ---------------------- */
+/* = every BLAS build (src/vk/vulkan.cpp:881-936) + the TLAS build (:777-856) of
+ * GPURT::build_accel (src/gpurt.cpp:220-241): LBVH over the world-space triangles of all
+ * instances, collapsed to 80-byte 8-wide compressed nodes. */
+#define GPURT_BUILD_DEFAULT 0u
+#define GPURT_BUILD_KEEP_BVH2 1u /* keep the binary LBVH for gpurt_accel_get_bvh2 / debug trace */
+int gpurt_accel_build(gpurt_scene* scene, uint32_t flags, gpurt_accel** out);
+int gpurt_accel_destroy(gpurt_accel* accel);
+int gpurt_accel_info(const gpurt_accel* accel, GpurtAccelInfo* out);
+/* Canonical primitive order (sorted Morton position -> global prim id), host buffers. */
+int gpurt_accel_get_prim_order(const gpurt_accel* accel, uint32_t* out_order);
+int gpurt_accel_get_morton_keys(const gpurt_accel* accel, uint64_t* out_sorted_keys);
+/* n_tris-1 internal nodes: child >= 0 internal, < 0 leaf ~sorted_position; boxes 6 floats. */
+int gpurt_accel_get_bvh2(const gpurt_accel* accel, int32_t* left, int32_t* right, float* boxes6);
+
+/* ---- queries ---------------------------------------------------------------------------------- */
+/* traceRayEXT closest hit (rt.rgen:257-270 + rt.rchit + rt.rmiss) for a batch of rays. */
+int gpurt_trace_closest(gpurt_accel* accel, const GpurtRay* rays, uint64_t n, GpurtHit* hits, int mem);
+/* `visibility` (rt.rgen:272-291): 1 = occluded. */
+int gpurt_trace_any(gpurt_accel* accel, const GpurtRay* rays, uint64_t n, uint8_t* occluded, int mem);
+/* FCPW closest-point query (README.md:6-8) over the same BVH. */
+int gpurt_closest_points(gpurt_accel* accel, const GpurtQuery* queries, uint64_t n,
+                         GpurtClosestPoint* results, int mem);
+/* Same as gpurt_trace_closest but through the binary LBVH (needs GPURT_BUILD_KEEP_BVH2). */
+int gpurt_trace_closest_bvh2(gpurt_accel* accel, const GpurtRay* rays, uint64_t n, GpurtHit* hits, int mem);
+/* Instrumented closest-hit: same results + visit counters (device buffers only). */
+int gpurt_trace_closest_stats(gpurt_accel* accel, const GpurtRay* rays, uint64_t n, GpurtHit* hits,
+                              GpurtTraceStats* out_host_stats);
+/* Device time (ms) of the last query / render call on this accel's context (CUDA events). */
+int gpurt_last_kernel_ms(gpurt_ctx* ctx, float* out_ms);
+
+/* ---- integrator: replaces VK::RTPipe (src/vk/rt.h:14-142) -------------------------------------- */
+int gpurt_pipe_params_default(GpurtPipeParams* out); /* rt.h:38-53 */
+/* RTPipe::recreate(scene) + use_accel(tlas) (src/vk/rt.cpp:16-24, :159-176) */
+int gpurt_pipe_create(gpurt_scene* scene, gpurt_accel* accel, gpurt_pipe** out);
+int gpurt_pipe_destroy(gpurt_pipe* pipe);
+/* RTPipe::reset_frame (src/vk/rt.cpp:396-398) */
+int gpurt_pipe_reset_frame(gpurt_pipe* pipe);
+/* RTPipe::update_uniforms + RTPipe::trace (src/vk/rt.cpp:121-138, :346-394): renders one
+ * progressive frame of width x height; returns 1 when frame >= max_frames (nothing rendered),
+ * like trace() returning false. cam->prev_PV is filled by the pipe from the previous call. */
+int gpurt_pipe_render_frame(gpurt_pipe* pipe, const GpurtPipeParams* params, const GpurtCamera* cam,
+                            uint32_t width, uint32_t height);
+int gpurt_pipe_frame_index(const gpurt_pipe* pipe, int32_t* out_frame);
+/* rt_target (RGBA32F, src/gpurt.cpp:189-193) -> caller buffer of width*height*4 floats. */
+int gpurt_pipe_read_image(gpurt_pipe* pipe, float* out_rgba, int mem);
+/* which: 0 position, 1 normal, 2 albedo (rt.rgen:674-676) */
+int gpurt_pipe_read_gbuffer(gpurt_pipe* pipe, int which, float* out_rgba, int mem);
+/* rays traced by the last frame: [0] closest-hit, [1] any-hit */
+int gpurt_pipe_ray_counts(const gpurt_pipe* pipe, uint64_t out_counts[2]);
+/* Device pointers of the frame's first-bounce ray buffers, for benchmarking the traversal alone. */
+int gpurt_pipe_device_image(gpurt_pipe* pipe, void** out_dev_rgba);
+
+/* tonemap.frag:17-48 (exposure/Uncharted2 + gamma) -> RGBA8, host or device output */
+int gpurt_tonemap(gpurt_pipe* pipe, int op, float exposure, float gamma, uint8_t* out_rgba8, int mem);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPURT_H */

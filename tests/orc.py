@@ -1,0 +1,161 @@
+"""ctypes binding of oracle/liboracle.so — TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+ORACLE_DIR = os.path.join(os.path.dirname(_HERE), "oracle")
+_LIB = os.path.join(ORACLE_DIR, "liboracle.so")
+
+NONE = 0xFFFFFFFF
+
+_f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+_u32p = np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS")
+_i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+_u64p = np.ctypeslib.ndpointer(np.uint64, flags="C_CONTIGUOUS")
+_u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
+
+
+def _load():
+    if not os.path.exists(_LIB):
+        subprocess.check_call(["make", "-C", ORACLE_DIR, "liboracle.so"])
+    lib = C.CDLL(_LIB)
+    sig = {
+        "orc_tea": (C.c_uint32, [C.c_uint32, C.c_uint32]),
+        "orc_lcg": (C.c_uint32, [C.POINTER(C.c_uint32)]),
+        "orc_randf": (C.c_float, [C.POINTER(C.c_uint32)]),
+        "orc_radical_inverse": (C.c_float, [C.c_uint32]),
+        "orc_flatten_object": (None, [_f32p, _u32p, C.c_uint32, _f32p, _f32p]),
+        "orc_intersect": (C.c_int, [_f32p, _f32p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+        "orc_closest_point_tri": (C.c_float, [_f32p, _f32p, _f32p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+        "orc_closest_hit_brute": (None, [_f32p, C.c_uint32, _f32p, C.c_uint64, _u32p, C.c_int]),
+        "orc_any_hit_brute": (None, [_f32p, C.c_uint32, _f32p, C.c_uint64, _u8p, C.c_int]),
+        "orc_closest_point_brute": (None, [_f32p, C.c_uint32, _f32p, C.c_uint64, _u32p, C.c_int]),
+        "orc_bvh_build": (C.c_void_p, [_f32p, C.c_uint32]),
+        "orc_bvh_free": (None, [C.c_void_p]),
+        "orc_bvh_n_tris": (C.c_uint32, [C.c_void_p]),
+        "orc_bvh_scene_box": (None, [C.c_void_p, _f32p]),
+        "orc_bvh_morton_keys": (None, [C.c_void_p, _u64p]),
+        "orc_bvh_prim_order": (None, [C.c_void_p, _u32p]),
+        "orc_bvh_get_bvh2": (None, [C.c_void_p, _i32p, _i32p, _f32p]),
+        "orc_bvh_inflation": (C.c_float, [C.c_void_p]),
+        "orc_bvh_closest_hit": (None, [C.c_void_p, _f32p, C.c_uint64, _u32p, C.c_int]),
+        "orc_bvh_any_hit": (None, [C.c_void_p, _f32p, C.c_uint64, _u8p, C.c_int]),
+        "orc_bvh_closest_point": (None, [C.c_void_p, _f32p, C.c_uint64, _u32p, C.c_int]),
+        "orc_gen_random_rays": (None, [C.c_uint64, C.c_uint32, _f32p, C.c_float, C.c_float, C.c_float, _f32p]),
+        "orc_gen_random_points": (None, [C.c_uint64, C.c_uint32, _f32p, C.c_float, C.c_float, _f32p]),
+        "orc_hw_threads": (C.c_int, []),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = _load()
+
+HIT_DT = np.dtype([("t", "<f4"), ("u", "<f4"), ("v", "<f4"), ("gid", "<u4")])
+CPQ_DT = np.dtype([("p", "<f4", 3), ("dist", "<f4"), ("gid", "<u4"), ("obj", "<u4"), ("u", "<f4"), ("v", "<f4")])
+
+
+def tea(a, b):
+    return lib.orc_tea(a, b)
+
+
+def flatten(verts48, idx, model16):
+    """verts48: (nv,12) f32, idx: (3*nt,) u32, model16: column-major 16 f32 -> (nt,9) f32"""
+    verts48 = np.ascontiguousarray(verts48, np.float32).reshape(-1, 12)
+    idx = np.ascontiguousarray(idx, np.uint32).reshape(-1)
+    nt = idx.size // 3
+    out = np.empty((nt, 9), np.float32)
+    lib.orc_flatten_object(verts48, idx, nt, np.ascontiguousarray(model16, np.float32).reshape(16), out)
+    return out
+
+
+def closest_hit_brute(tris9, rays, threads=0):
+    hits = np.empty((rays.shape[0], 4), np.uint32)
+    lib.orc_closest_hit_brute(tris9, tris9.shape[0], rays, rays.shape[0], hits, threads)
+    return hits.view(HIT_DT).reshape(-1)
+
+
+def any_hit_brute(tris9, rays, threads=0):
+    occ = np.empty(rays.shape[0], np.uint8)
+    lib.orc_any_hit_brute(tris9, tris9.shape[0], rays, rays.shape[0], occ, threads)
+    return occ
+
+
+def closest_point_brute(tris9, queries, threads=0):
+    res = np.empty((queries.shape[0], 8), np.uint32)
+    lib.orc_closest_point_brute(tris9, tris9.shape[0], queries, queries.shape[0], res, threads)
+    return res.view(CPQ_DT).reshape(-1)
+
+
+class Bvh:
+    def __init__(self, tris9):
+        self.tris9 = np.ascontiguousarray(tris9, np.float32).reshape(-1, 9)
+        self.n = self.tris9.shape[0]
+        self.h = lib.orc_bvh_build(self.tris9, self.n)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib.orc_bvh_free(self.h)
+            self.h = None
+
+    def scene_box(self):
+        b = np.empty(6, np.float32)
+        lib.orc_bvh_scene_box(self.h, b)
+        return b
+
+    def inflation(self):
+        return lib.orc_bvh_inflation(self.h)
+
+    def keys(self):
+        k = np.empty(self.n, np.uint64)
+        lib.orc_bvh_morton_keys(self.h, k)
+        return k
+
+    def prim_order(self):
+        o = np.empty(self.n, np.uint32)
+        lib.orc_bvh_prim_order(self.h, o)
+        return o
+
+    def bvh2(self):
+        m = max(self.n - 1, 0)
+        l = np.empty(m, np.int32)
+        r = np.empty(m, np.int32)
+        b = np.empty((m, 6), np.float32)
+        lib.orc_bvh_get_bvh2(self.h, l, r, b)
+        return l, r, b
+
+    def closest_hit(self, rays, threads=0):
+        hits = np.empty((rays.shape[0], 4), np.uint32)
+        lib.orc_bvh_closest_hit(self.h, rays, rays.shape[0], hits, threads)
+        return hits.view(HIT_DT).reshape(-1)
+
+    def any_hit(self, rays, threads=0):
+        occ = np.empty(rays.shape[0], np.uint8)
+        lib.orc_bvh_any_hit(self.h, rays, rays.shape[0], occ, threads)
+        return occ
+
+    def closest_point(self, queries, threads=0):
+        res = np.empty((queries.shape[0], 8), np.uint32)
+        lib.orc_bvh_closest_point(self.h, queries, queries.shape[0], res, threads)
+        return res.view(CPQ_DT).reshape(-1)
+
+
+def gen_random_rays(n, seed, box6, frac=0.1, tmin=1e-5, tmax=1e7):
+    rays = np.empty((n, 8), np.float32)
+    lib.orc_gen_random_rays(n, seed, np.ascontiguousarray(box6, np.float32), frac, tmin, tmax, rays)
+    return rays
+
+
+def gen_random_points(n, seed, box6, frac=0.25, r2=np.inf):
+    q = np.empty((n, 4), np.float32)
+    lib.orc_gen_random_points(n, seed, np.ascontiguousarray(box6, np.float32), frac, r2, q)
+    return q

@@ -1,0 +1,256 @@
+/*
+ * api.cu — CUDA half of the C ABI (include/gpurt.h): context, scene upload, accel build, queries.
+ * The host-only half (scene loading / packing, camera) is host/host_api.cpp.
+ */
+#include <cstring>
+
+#include "device.cuh"
+
+using namespace gpurt;
+
+namespace gpurt {
+
+template <typename T> static int upload(cudaStream_t st, T*& dst, const std::vector<T>& src) {
+    dst = nullptr;
+    size_t bytes = std::max<size_t>(src.size(), 1) * sizeof(T);
+    GPURT_CUDA(cudaMalloc((void**)&dst, bytes));
+    if(!src.empty())
+        GPURT_CUDA(cudaMemcpyAsync(dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+    return GPURT_OK;
+}
+
+void free_scene(DeviceScene& d) {
+    void* ptrs[] = {d.verts, d.idx, d.tri_off, d.vert_off, d.descs, d.lights, d.texels, d.tex_info};
+    for(void* p : ptrs)
+        if(p) cudaFree(p);
+    d = DeviceScene();
+}
+
+int upload_scene(gpurt_ctx* ctx, gpurt_scene* s, DeviceScene& d) {
+    if(!s->pack()) return GPURT_E_INVALID;
+    free_scene(d);
+    const PackedScene& P = s->packed;
+    cudaStream_t st = ctx->stream;
+    int rc;
+    if((rc = upload(st, d.verts, P.verts))) return rc;
+    if((rc = upload(st, d.idx, P.idx))) return rc;
+    if((rc = upload(st, d.tri_off, P.tri_off))) return rc;
+    if((rc = upload(st, d.vert_off, P.vert_off))) return rc;
+    if((rc = upload(st, d.descs, P.descs))) return rc;
+    if((rc = upload(st, d.lights, P.lights))) return rc;
+    d.n_objs = (uint32_t)P.descs.size();
+    d.n_tris = P.tri_off.back();
+    d.n_lights = (uint32_t)P.lights.size();
+    d.n_verts = (uint32_t)P.verts.size();
+    d.version = s->version;
+    /* textures: RTPipe::build_textures (src/vk/rt.cpp:430-455) */
+    std::vector<uint8_t> texels;
+    std::vector<uint4> info;
+    for(const Texture& t : s->scene.textures) {
+        info.push_back(make_uint4((unsigned)(texels.size() / 4), t.w, t.h, 0));
+        texels.insert(texels.end(), t.rgba.begin(), t.rgba.end());
+    }
+    d.n_textures = (uint32_t)info.size();
+    if((rc = upload(st, d.texels, texels))) return rc;
+    if((rc = upload(st, d.tex_info, info))) return rc;
+    GPURT_CUDA(cudaStreamSynchronize(st));
+    return GPURT_OK;
+}
+
+/* Run `launch(d_in, d_out)` with caller buffers in host or device memory; times the device work. */
+template <typename F>
+static int run_query(gpurt_ctx* ctx, const void* in, size_t in_bytes, void* out, size_t out_bytes,
+                     int mem, F launch) {
+    GPURT_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    if(mem == GPURT_MEM_DEVICE) {
+        GPURT_CUDA(cudaEventRecord(ctx->ev0, st));
+        int rc = launch(in, out);
+        if(rc) return rc;
+        GPURT_CUDA(cudaEventRecord(ctx->ev1, st));
+        return GPURT_OK;
+    }
+    if(mem != GPURT_MEM_HOST) return set_error("mem must be GPURT_MEM_HOST or GPURT_MEM_DEVICE"), GPURT_E_INVALID;
+    int rc;
+    if((rc = ctx->d_in.reserve(in_bytes))) return rc;
+    if((rc = ctx->d_out.reserve(out_bytes))) return rc;
+    /* pageable caller memory: cudaMemcpyAsync stages through the driver's pinned pool */
+    GPURT_CUDA(cudaMemcpyAsync(ctx->d_in.p, in, in_bytes, cudaMemcpyHostToDevice, st));
+    GPURT_CUDA(cudaEventRecord(ctx->ev0, st));
+    if((rc = launch(ctx->d_in.p, ctx->d_out.p))) return rc;
+    GPURT_CUDA(cudaEventRecord(ctx->ev1, st));
+    GPURT_CUDA(cudaMemcpyAsync(out, ctx->d_out.p, out_bytes, cudaMemcpyDeviceToHost, st));
+    GPURT_CUDA(cudaStreamSynchronize(st));
+    return GPURT_OK;
+}
+
+} // namespace gpurt
+
+extern "C" {
+
+int gpurt_ctx_create(int device, gpurt_ctx** out) {
+    if(!out) return set_error("out is NULL"), GPURT_E_INVALID;
+    int count = 0;
+    if(cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+        return set_error("no CUDA device: libgpurt has no CPU fallback"), GPURT_E_NO_DEVICE;
+    if(device < 0 || device >= count) return set_error("device ordinal out of range"), GPURT_E_NO_DEVICE;
+    GPURT_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    GPURT_CUDA(cudaGetDeviceProperties(&prop, device));
+    if(prop.major < 10)
+        return set_error(std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) +
+                         "; libgpurt is built for sm_100a only"),
+               GPURT_E_NO_DEVICE;
+    gpurt_ctx* c = new gpurt_ctx;
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    GPURT_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
+    GPURT_CUDA(cudaEventCreate(&c->ev0));
+    GPURT_CUDA(cudaEventCreate(&c->ev1));
+    *out = c;
+    return GPURT_OK;
+}
+int gpurt_ctx_destroy(gpurt_ctx* c) {
+    if(!c) return GPURT_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    c->d_in.release(), c->d_out.release(), c->scratch.release();
+    c->h_in.release(), c->h_out.release();
+    cudaEventDestroy(c->ev0), cudaEventDestroy(c->ev1);
+    cudaStreamDestroy(c->own_stream);
+    delete c;
+    return GPURT_OK;
+}
+int gpurt_ctx_set_stream(gpurt_ctx* c, void* stream) {
+    if(!c) return set_error("NULL context"), GPURT_E_INVALID;
+    c->stream = stream ? (cudaStream_t)stream : c->own_stream;
+    return GPURT_OK;
+}
+int gpurt_ctx_synchronize(gpurt_ctx* c) {
+    if(!c) return set_error("NULL context"), GPURT_E_INVALID;
+    GPURT_CUDA(cudaSetDevice(c->device));
+    GPURT_CUDA(cudaStreamSynchronize(c->stream));
+    return GPURT_OK;
+}
+int gpurt_last_kernel_ms(gpurt_ctx* c, float* ms) {
+    if(!c || !ms) return set_error("NULL argument"), GPURT_E_INVALID;
+    GPURT_CUDA(cudaEventSynchronize(c->ev1));
+    GPURT_CUDA(cudaEventElapsedTime(ms, c->ev0, c->ev1));
+    return GPURT_OK;
+}
+
+/* ---- accel ------------------------------------------------------------------------------------ */
+int gpurt_accel_build(gpurt_scene* s, uint32_t flags, gpurt_accel** out) {
+    if(!s || !out) return set_error("NULL argument"), GPURT_E_INVALID;
+    if(!s->ctx) return set_error("scene was created without a context: no device to build on"), GPURT_E_NO_DEVICE;
+    gpurt_accel* A = new gpurt_accel;
+    A->ctx = s->ctx;
+    A->scene = s;
+    A->flags = flags;
+    int rc = build_accel_device(A);
+    if(rc == GPURT_OK && A->depth > 60) rc = (set_error("wide BVH deeper than the traversal stack"), GPURT_E_STATE);
+    if(rc) {
+        free_accel_device(A);
+        delete A;
+        return rc;
+    }
+    *out = A;
+    return GPURT_OK;
+}
+int gpurt_accel_destroy(gpurt_accel* A) {
+    if(!A) return GPURT_OK;
+    cudaSetDevice(A->ctx->device);
+    cudaStreamSynchronize(A->ctx->stream);
+    free_accel_device(A);
+    delete A;
+    return GPURT_OK;
+}
+int gpurt_accel_info(const gpurt_accel* A, GpurtAccelInfo* o) {
+    if(!A || !o) return set_error("NULL argument"), GPURT_E_INVALID;
+    std::memset(o, 0, sizeof(*o));
+    o->n_tris = A->n;
+    o->n_objs = A->dscene.n_objs;
+    o->n_bvh2_nodes = A->n > 1 ? A->n - 1 : 0;
+    o->n_wide_nodes = A->n_nodes;
+    o->wide_depth = A->depth;
+    for(int k = 0; k < 3; k++) o->scene_min[k] = A->scene_box[k], o->scene_max[k] = A->scene_box[3 + k];
+    o->inflation = A->inflate;
+    o->build_ms = A->build_ms;
+    o->node_bytes = (uint64_t)A->n_nodes * sizeof(Node8);
+    o->tri_bytes = (uint64_t)A->n * 48;
+    return GPURT_OK;
+}
+static int d2h(const gpurt_accel* A, void* dst, const void* src, size_t bytes) {
+    if(!bytes) return GPURT_OK;
+    GPURT_CUDA(cudaSetDevice(A->ctx->device));
+    GPURT_CUDA(cudaStreamSynchronize(A->ctx->stream));
+    GPURT_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+    return GPURT_OK;
+}
+int gpurt_accel_get_prim_order(const gpurt_accel* A, uint32_t* out) {
+    if(!A || !out) return set_error("NULL argument"), GPURT_E_INVALID;
+    return d2h(A, out, A->order, (size_t)A->n * 4);
+}
+int gpurt_accel_get_morton_keys(const gpurt_accel* A, uint64_t* out) {
+    if(!A || !out) return set_error("NULL argument"), GPURT_E_INVALID;
+    return d2h(A, out, A->keys, (size_t)A->n * 8);
+}
+int gpurt_accel_get_bvh2(const gpurt_accel* A, int32_t* left, int32_t* right, float* boxes6) {
+    if(!A || !left || !right || !boxes6) return set_error("NULL argument"), GPURT_E_INVALID;
+    if(A->n < 2) return GPURT_OK;
+    size_t m = A->n - 1;
+    int rc;
+    if((rc = d2h(A, left, A->left, m * 4))) return rc;
+    if((rc = d2h(A, right, A->right, m * 4))) return rc;
+    std::vector<float4> lo(m), hi(m);
+    if((rc = d2h(A, lo.data(), A->node_lo, m * 16))) return rc;
+    if((rc = d2h(A, hi.data(), A->node_hi, m * 16))) return rc;
+    for(size_t i = 0; i < m; i++) {
+        float* o = boxes6 + 6 * i;
+        o[0] = lo[i].x, o[1] = lo[i].y, o[2] = lo[i].z, o[3] = hi[i].x, o[4] = hi[i].y, o[5] = hi[i].z;
+    }
+    return GPURT_OK;
+}
+
+/* ---- queries ---------------------------------------------------------------------------------- */
+int gpurt_trace_closest(gpurt_accel* A, const GpurtRay* rays, uint64_t n, GpurtHit* hits, int mem) {
+    if(!A || (n && (!rays || !hits))) return set_error("NULL argument"), GPURT_E_INVALID;
+    return run_query(A->ctx, rays, n * sizeof(GpurtRay), hits, n * sizeof(GpurtHit), mem,
+                     [&](const void* i, void* o) { return launch_trace_closest(A, (const float4*)i, n, (float4*)o); });
+}
+int gpurt_trace_closest_bvh2(gpurt_accel* A, const GpurtRay* rays, uint64_t n, GpurtHit* hits, int mem) {
+    if(!A || (n && (!rays || !hits))) return set_error("NULL argument"), GPURT_E_INVALID;
+    return run_query(A->ctx, rays, n * sizeof(GpurtRay), hits, n * sizeof(GpurtHit), mem,
+                     [&](const void* i, void* o) { return launch_trace_closest_bvh2(A, (const float4*)i, n, (float4*)o); });
+}
+int gpurt_trace_any(gpurt_accel* A, const GpurtRay* rays, uint64_t n, uint8_t* occ, int mem) {
+    if(!A || (n && (!rays || !occ))) return set_error("NULL argument"), GPURT_E_INVALID;
+    return run_query(A->ctx, rays, n * sizeof(GpurtRay), occ, n, mem,
+                     [&](const void* i, void* o) { return launch_trace_any(A, (const float4*)i, n, (uint8_t*)o); });
+}
+int gpurt_closest_points(gpurt_accel* A, const GpurtQuery* q, uint64_t n, GpurtClosestPoint* res, int mem) {
+    if(!A || (n && (!q || !res))) return set_error("NULL argument"), GPURT_E_INVALID;
+    return run_query(A->ctx, q, n * sizeof(GpurtQuery), res, n * sizeof(GpurtClosestPoint), mem,
+                     [&](const void* i, void* o) { return launch_closest_points(A, (const float4*)i, n, (float4*)o); });
+}
+int gpurt_trace_closest_stats(gpurt_accel* A, const GpurtRay* rays, uint64_t n, GpurtHit* hits,
+                              GpurtTraceStats* out) {
+    if(!A || !out || (n && (!rays || !hits))) return set_error("NULL argument"), GPURT_E_INVALID;
+    gpurt_ctx* ctx = A->ctx;
+    GPURT_CUDA(cudaSetDevice(ctx->device));
+    int rc = ctx->scratch.reserve(64);
+    if(rc) return rc;
+    unsigned long long* d = ctx->scratch.as<unsigned long long>();
+    GPURT_CUDA(cudaMemsetAsync(d, 0, 32, ctx->stream));
+    rc = run_query(ctx, rays, n * sizeof(GpurtRay), hits, n * sizeof(GpurtHit), GPURT_MEM_DEVICE,
+                   [&](const void* i, void* o) { return launch_trace_closest_stats(A, (const float4*)i, n, (float4*)o, d); });
+    if(rc) return rc;
+    unsigned long long h[4];
+    GPURT_CUDA(cudaMemcpyAsync(h, d, 32, cudaMemcpyDeviceToHost, ctx->stream));
+    GPURT_CUDA(cudaStreamSynchronize(ctx->stream));
+    out->rays = n, out->nodes_visited = h[0], out->tris_tested = h[1], out->hits = h[2];
+    return GPURT_OK;
+}
+
+} /* extern "C" */

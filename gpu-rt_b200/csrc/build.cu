@@ -1,0 +1,609 @@
+/*
+ * build.cu — acceleration-structure build on the GPU.
+ *
+ * Replaces VK::Accel: every per-object BLAS build (src/vk/vulkan.cpp:881-936) plus the TLAS build
+ * over instance transforms (src/vk/vulkan.cpp:777-856) issued by GPURT::build_accel
+ * (src/gpurt.cpp:220-241).  Pipeline (all kernels hand-written, one stream):
+ *
+ *   k_flatten      instances -> world-space triangles (N1), exact AABBs, scene box
+ *   k_morton       63-bit Morton key of the AABB centroid (N6)
+ *   radix sort     stable 8-bit LSD over 64-bit keys (ties keep gid order)
+ *   k_karras       binary radix tree (Karras 2012), one thread per internal node
+ *   k_refit        bottom-up AABB union with arrival counters
+ *   k_collapse_*   level-synchronous greedy-SAH collapse into 80-byte 8-wide nodes (bvh8.cuh),
+ *                  triangles re-laid out in node order
+ */
+#include "device.cuh"
+
+namespace gpurt {
+
+/* ---------------------------------------------------------------------------------------------- */
+int DevBuf::reserve(size_t bytes) {
+    if(bytes <= cap) return GPURT_OK;
+    if(p) cudaFree(p);
+    p = nullptr, cap = 0;
+    GPURT_CUDA(cudaMalloc(&p, bytes));
+    cap = bytes;
+    return GPURT_OK;
+}
+void DevBuf::release() {
+    if(p) cudaFree(p);
+    p = nullptr, cap = 0;
+}
+int PinBuf::reserve(size_t bytes) {
+    if(bytes <= cap) return GPURT_OK;
+    if(p) cudaFreeHost(p);
+    p = nullptr, cap = 0;
+    GPURT_CUDA(cudaMallocHost(&p, bytes));
+    cap = bytes;
+    return GPURT_OK;
+}
+void PinBuf::release() {
+    if(p) cudaFreeHost(p);
+    p = nullptr, cap = 0;
+}
+
+static inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+/* ---- exclusive scan ---------------------------------------------------------------------------- */
+constexpr int SCAN_T = 256, SCAN_I = 8, SCAN_TILE = SCAN_T * SCAN_I;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t& total) {
+    __shared__ uint32_t wsum[SCAN_T / 32];
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for(int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if(lane >= o) inc += t;
+    }
+    if(lane == 31) wsum[w] = inc;
+    __syncthreads();
+    if(w == 0) {
+        uint32_t s = lane < SCAN_T / 32 ? wsum[lane] : 0;
+#pragma unroll
+        for(int o = 1; o < SCAN_T / 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, s, o);
+            if(lane >= o) s += t;
+        }
+        if(lane < SCAN_T / 32) wsum[lane] = s;
+    }
+    __syncthreads();
+    uint32_t base = w ? wsum[w - 1] : 0;
+    total = wsum[SCAN_T / 32 - 1];
+    __syncthreads();
+    return base + inc - v;
+}
+
+__global__ void __launch_bounds__(SCAN_T) k_scan_local(const uint32_t* __restrict__ in,
+                                                       uint32_t* __restrict__ out, size_t n,
+                                                       uint32_t* __restrict__ sums) {
+    size_t base = (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * SCAN_I;
+    uint32_t v[SCAN_I], s = 0;
+#pragma unroll
+    for(int i = 0; i < SCAN_I; i++) {
+        v[i] = base + i < n ? in[base + i] : 0;
+        s += v[i];
+    }
+    uint32_t total;
+    uint32_t ex = block_exclusive_scan(s, total);
+#pragma unroll
+    for(int i = 0; i < SCAN_I; i++) {
+        if(base + i < n) out[base + i] = ex;
+        ex += v[i];
+    }
+    if(threadIdx.x == 0) sums[blockIdx.x] = total;
+}
+__global__ void k_scan_add(uint32_t* __restrict__ out, size_t n, const uint32_t* __restrict__ offs) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if(i < n) out[i] += offs[i / SCAN_TILE];
+}
+
+size_t scan_tmp_bytes(size_t n) {
+    size_t total = 0;
+    while(n > 1) {
+        n = (n + SCAN_TILE - 1) / SCAN_TILE;
+        total += (n + 1) * sizeof(uint32_t);
+    }
+    return total + 64;
+}
+
+static int scan_rec(cudaStream_t st, const uint32_t* in, uint32_t* out, size_t n, uint32_t* tmp) {
+    unsigned nb = cdiv(n, SCAN_TILE);
+    k_scan_local<<<nb, SCAN_T, 0, st>>>(in, out, n, tmp);
+    if(nb > 1) {
+        int rc = scan_rec(st, tmp, tmp, nb, tmp + nb + 1);
+        if(rc) return rc;
+        k_scan_add<<<cdiv(n, 256), 256, 0, st>>>(out, n, tmp);
+    }
+    GPURT_CUDA(cudaGetLastError());
+    return GPURT_OK;
+}
+/* After the call tmp[0] of the top level is NOT the total; callers that need the total append a
+ * zero element and read out[n]. */
+int exclusive_scan_u32(cudaStream_t st, const uint32_t* in, uint32_t* out, size_t n, DevBuf& tmp) {
+    if(n == 0) return GPURT_OK;
+    int rc = tmp.reserve(scan_tmp_bytes(n));
+    if(rc) return rc;
+    return scan_rec(st, in, out, n, tmp.as<uint32_t>());
+}
+
+/* ---- radix sort ------------------------------------------------------------------------------- */
+constexpr int RS_T = 256, RS_I = 16, RS_TILE = RS_T * RS_I, RS_W = RS_T / 32;
+
+__global__ void __launch_bounds__(RS_T) k_rs_hist(const uint64_t* __restrict__ keys, size_t n,
+                                                  int shift, uint32_t* __restrict__ hist, unsigned nb) {
+    __shared__ uint32_t h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    size_t base = (size_t)blockIdx.x * RS_TILE;
+#pragma unroll
+    for(int r = 0; r < RS_I; r++) {
+        size_t i = base + (size_t)r * RS_T + threadIdx.x;
+        if(i < n) atomicAdd(&h[(unsigned)(keys[i] >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    hist[(size_t)threadIdx.x * nb + blockIdx.x] = h[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(RS_T) k_rs_scatter(const uint64_t* __restrict__ kin,
+                                                     const uint32_t* __restrict__ vin,
+                                                     uint64_t* __restrict__ kout,
+                                                     uint32_t* __restrict__ vout, size_t n, int shift,
+                                                     const uint32_t* __restrict__ offs, unsigned nb) {
+    __shared__ uint32_t cnt[RS_W][256];
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    for(int i = threadIdx.x; i < RS_W * 256; i += RS_T) (&cnt[0][0])[i] = 0;
+    __syncthreads();
+    const size_t seg = (size_t)blockIdx.x * RS_TILE + (size_t)w * (32 * RS_I);
+    uint64_t key[RS_I];
+    uint32_t rank[RS_I];
+    const unsigned lt = (1u << l) - 1u;
+#pragma unroll
+    for(int r = 0; r < RS_I; r++) {
+        size_t i = seg + (size_t)r * 32 + l;
+        bool valid = i < n;
+        unsigned vm = __ballot_sync(0xffffffffu, valid);
+        key[r] = 0;
+        rank[r] = 0;
+        if(valid) {
+            key[r] = kin[i];
+            unsigned d = (unsigned)(key[r] >> shift) & 255u;
+            unsigned peers = __match_any_sync(vm, d);
+            uint32_t before = cnt[w][d];
+            rank[r] = before + __popc(peers & lt);
+            __syncwarp(vm);
+            if(l == __ffs(peers) - 1) cnt[w][d] = before + __popc(peers);
+            __syncwarp(vm);
+        }
+    }
+    __syncthreads();
+    {
+        unsigned d = threadIdx.x;
+        uint32_t run = offs[(size_t)d * nb + blockIdx.x];
+#pragma unroll
+        for(int ww = 0; ww < RS_W; ww++) {
+            uint32_t c = cnt[ww][d];
+            cnt[ww][d] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for(int r = 0; r < RS_I; r++) {
+        size_t i = seg + (size_t)r * 32 + l;
+        if(i < n) {
+            unsigned d = (unsigned)(key[r] >> shift) & 255u;
+            uint32_t pos = cnt[w][d] + rank[r];
+            kout[pos] = key[r];
+            vout[pos] = vin[i];
+        }
+    }
+}
+
+int radix_sort_u64(cudaStream_t st, uint64_t* keys, uint32_t* vals, uint64_t* kt, uint32_t* vt,
+                   size_t n, int passes, DevBuf& tmp) {
+    if(n == 0) return GPURT_OK;
+    unsigned nb = cdiv(n, RS_TILE);
+    size_t hist_n = (size_t)256 * nb;
+    size_t hist_bytes = (hist_n * 4 + 255) & ~(size_t)255;
+    int rc = tmp.reserve(hist_bytes + scan_tmp_bytes(hist_n));
+    if(rc) return rc;
+    uint32_t* hist = tmp.as<uint32_t>();
+    uint32_t* stmp = (uint32_t*)((char*)tmp.p + hist_bytes);
+    for(int p = 0; p < passes; p++) {
+        int shift = 8 * p;
+        k_rs_hist<<<nb, RS_T, 0, st>>>(keys, n, shift, hist, nb);
+        rc = scan_rec(st, hist, hist, hist_n, stmp);
+        if(rc) return rc;
+        k_rs_scatter<<<nb, RS_T, 0, st>>>(keys, vals, kt, vt, n, shift, hist, nb);
+        uint64_t* a = keys;
+        keys = kt, kt = a;
+        uint32_t* b = vals;
+        vals = vt, vt = b;
+    }
+    GPURT_CUDA(cudaGetLastError());
+    return GPURT_OK; /* passes even -> result back in the caller's primary buffers */
+}
+
+/* ---- flatten ---------------------------------------------------------------------------------- */
+__device__ __forceinline__ void atomic_min_f(float* a, float v) {
+    if(v >= 0.0f) atomicMin((int*)a, __float_as_int(v));
+    else atomicMax((unsigned*)a, __float_as_uint(v));
+}
+__device__ __forceinline__ void atomic_max_f(float* a, float v) {
+    if(v >= 0.0f) atomicMax((int*)a, __float_as_int(v));
+    else atomicMin((unsigned*)a, __float_as_uint(v));
+}
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+    for(int o = 16; o; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for(int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+/* N1: world = model * vec4(v,1) evaluated as fma(m0,x, fma(m4,y, fma(m8,z, m12))) */
+__global__ void __launch_bounds__(256) k_flatten(DeviceScene S, float4* __restrict__ tri,
+                                                 float4* __restrict__ tlo, float4* __restrict__ thi,
+                                                 float* __restrict__ scene_box) {
+    unsigned gid = blockIdx.x * blockDim.x + threadIdx.x;
+    float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+    if(gid < S.n_tris) {
+        /* object of this triangle: last o with tri_off[o] <= gid */
+        unsigned a = 0, b = S.n_objs;
+        while(b - a > 1) {
+            unsigned m = (a + b) >> 1;
+            if(S.tri_off[m] <= gid) a = m; else b = m;
+        }
+        unsigned obj = a, prim = gid - S.tri_off[obj];
+        const float* m = reinterpret_cast<const float*>(S.descs + obj); /* model is the first member */
+        const Vertex* vb = S.verts + S.vert_off[obj];
+        float w[3][3];
+#pragma unroll
+        for(int k = 0; k < 3; k++) {
+            const Vertex& v = vb[S.idx[3ull * gid + k]];
+            float x = v.pos[0], y = v.pos[1], z = v.pos[2];
+            w[k][0] = fmaf(m[0], x, fmaf(m[4], y, fmaf(m[8], z, m[12])));
+            w[k][1] = fmaf(m[1], x, fmaf(m[5], y, fmaf(m[9], z, m[13])));
+            w[k][2] = fmaf(m[2], x, fmaf(m[6], y, fmaf(m[10], z, m[14])));
+        }
+#pragma unroll
+        for(int c = 0; c < 3; c++) {
+            lo[c] = fminf(fminf(w[0][c], w[1][c]), w[2][c]);
+            hi[c] = fmaxf(fmaxf(w[0][c], w[1][c]), w[2][c]);
+        }
+        tri[3ull * gid + 0] = make_float4(w[0][0], w[0][1], w[0][2], __uint_as_float(gid));
+        tri[3ull * gid + 1] = make_float4(w[1][0] - w[0][0], w[1][1] - w[0][1], w[1][2] - w[0][2],
+                                          __uint_as_float(obj));
+        tri[3ull * gid + 2] = make_float4(w[2][0] - w[0][0], w[2][1] - w[0][1], w[2][2] - w[0][2],
+                                          __uint_as_float(prim));
+        tlo[gid] = make_float4(lo[0], lo[1], lo[2], 0.0f);
+        thi[gid] = make_float4(hi[0], hi[1], hi[2], 0.0f);
+    }
+#pragma unroll
+    for(int c = 0; c < 3; c++) {
+        float l = warp_min(lo[c]), h = warp_max(hi[c]);
+        if((threadIdx.x & 31) == 0) {
+            if(l < 3.0e38f) atomic_min_f(scene_box + c, l);
+            if(h > -3.0e38f) atomic_max_f(scene_box + 3 + c, h);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_morton(const float4* __restrict__ tlo,
+                                                const float4* __restrict__ thi, unsigned n, float lx,
+                                                float ly, float lz, float ix, float iy, float iz,
+                                                uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    unsigned g = blockIdx.x * blockDim.x + threadIdx.x;
+    if(g >= n) return;
+    float4 lo = tlo[g], hi = thi[g];
+    float cx = (lo.x + hi.x) * 0.5f, cy = (lo.y + hi.y) * 0.5f, cz = (lo.z + hi.z) * 0.5f;
+    keys[g] = (expand21(quant21(cx, lx, ix)) << 2) | (expand21(quant21(cy, ly, iy)) << 1) |
+              expand21(quant21(cz, lz, iz));
+    vals[g] = g;
+}
+
+/* ---- Karras 2012 ------------------------------------------------------------------------------ */
+__device__ __forceinline__ int key_delta(const uint64_t* __restrict__ k, int n, int i, int j) {
+    if(j < 0 || j >= n) return -1;
+    uint64_t a = k[i], b = k[j];
+    if(a == b) return 64 + __clz(i ^ j);
+    return __clzll((long long)(a ^ b));
+}
+
+__global__ void __launch_bounds__(256) k_karras(const uint64_t* __restrict__ k, int n,
+                                                int* __restrict__ left, int* __restrict__ right,
+                                                int* __restrict__ parent /* [n-1 internal | n leaves] */,
+                                                int* __restrict__ rf, int* __restrict__ rl) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n - 1) return;
+    int d = (key_delta(k, n, i, i + 1) - key_delta(k, n, i, i - 1)) >= 0 ? 1 : -1;
+    int dmin = key_delta(k, n, i, i - d);
+    int lmax = 2;
+    while(key_delta(k, n, i, i + lmax * d) > dmin) lmax *= 2;
+    int l = 0;
+    for(int t = lmax / 2; t >= 1; t /= 2)
+        if(key_delta(k, n, i, i + (l + t) * d) > dmin) l += t;
+    int j = i + l * d;
+    int dnode = key_delta(k, n, i, j);
+    int s = 0, t = l;
+    do {
+        t = (t + 1) / 2;
+        if(key_delta(k, n, i, i + (s + t) * d) > dnode) s += t;
+    } while(t > 1);
+    int gamma = i + s * d + min(d, 0);
+    int lo = min(i, j), hi = max(i, j);
+    int L = (lo == gamma) ? ~gamma : gamma;
+    int R = (hi == gamma + 1) ? ~(gamma + 1) : gamma + 1;
+    left[i] = L, right[i] = R;
+    rf[i] = lo, rl[i] = hi;
+    if(L < 0) parent[(n - 1) + ~L] = i; else parent[L] = i;
+    if(R < 0) parent[(n - 1) + ~R] = i; else parent[R] = i;
+    if(i == 0) parent[0] = -1;
+}
+
+__global__ void __launch_bounds__(256) k_refit(int n, const int* __restrict__ left,
+                                               const int* __restrict__ right,
+                                               const int* __restrict__ parent,
+                                               const uint32_t* __restrict__ order,
+                                               const float4* __restrict__ tlo,
+                                               const float4* __restrict__ thi, float4* node_lo,
+                                               float4* node_hi, unsigned* __restrict__ arrive) {
+    int leaf = blockIdx.x * blockDim.x + threadIdx.x;
+    if(leaf >= n) return;
+    int p = parent[(n - 1) + leaf];
+    while(p >= 0) {
+        __threadfence();
+        if(atomicAdd(&arrive[p], 1u) == 0u) return;
+        int L = left[p], R = right[p];
+        float4 al, ah, bl, bh;
+        if(L < 0) { unsigned g = order[~L]; al = tlo[g], ah = thi[g]; }
+        else { al = __ldcg(&node_lo[L]), ah = __ldcg(&node_hi[L]); }
+        if(R < 0) { unsigned g = order[~R]; bl = tlo[g], bh = thi[g]; }
+        else { bl = __ldcg(&node_lo[R]), bh = __ldcg(&node_hi[R]); }
+        __stcg(&node_lo[p], make_float4(fminf(al.x, bl.x), fminf(al.y, bl.y), fminf(al.z, bl.z), 0.0f));
+        __stcg(&node_hi[p], make_float4(fmaxf(ah.x, bh.x), fmaxf(ah.y, bh.y), fmaxf(ah.z, bh.z), 0.0f));
+        p = parent[p];
+    }
+}
+
+/* ---- collapse --------------------------------------------------------------------------------- */
+__global__ void __launch_bounds__(128) k_collapse_count(Bvh2View B, const int* __restrict__ items,
+                                                        unsigned n_items, int* __restrict__ children,
+                                                        uint32_t* __restrict__ n_inner,
+                                                        uint32_t* __restrict__ n_tris) {
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n_items) return;
+    int ch[8], nt;
+    int ni = collapse_node(B, items[i], ch, nt);
+#pragma unroll
+    for(int s = 0; s < 8; s++) children[8ull * i + s] = ch[s];
+    n_inner[i] = (uint32_t)ni;
+    n_tris[i] = (uint32_t)nt;
+}
+
+__global__ void __launch_bounds__(128) k_collapse_emit(Bvh2View B, unsigned n_items,
+                                                       const int* __restrict__ children,
+                                                       const uint32_t* __restrict__ off_inner,
+                                                       const uint32_t* __restrict__ off_tris,
+                                                       unsigned level_base, unsigned next_base,
+                                                       unsigned tri_cursor, Node8* __restrict__ nodes,
+                                                       int* __restrict__ next_items,
+                                                       const float4* __restrict__ tri_gid,
+                                                       float4* __restrict__ tri_wide) {
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n_items) return;
+    int ch[8];
+#pragma unroll
+    for(int s = 0; s < 8; s++) ch[s] = children[8ull * i + s];
+    unsigned child_base = next_base + off_inner[i];
+    unsigned tri_base = tri_cursor + off_tris[i];
+    Node8 node;
+    encode_node(B, ch, child_base, tri_base, node);
+    Node8* dst = nodes + (level_base + i);
+#pragma unroll
+    for(int k = 0; k < 5; k++) dst->v[k] = node.v[k];
+    unsigned r = 0, t = 0;
+    for(int s = 0; s < 8; s++) {
+        int c = ch[s];
+        if(c == kEmptyChild) continue;
+        if(c >= 0) next_items[off_inner[i] + r++] = c;
+        else {
+            unsigned first, count;
+            decode_leaf_range(c, first, count);
+            for(unsigned k = 0; k < count; k++, t++) {
+                unsigned g = B.order[first + k];
+#pragma unroll
+                for(int q = 0; q < 3; q++) tri_wide[3ull * (tri_base + t) + q] = tri_gid[3ull * g + q];
+            }
+        }
+    }
+}
+
+/* n <= kMaxLeafTris: a single node whose slot 0 holds every triangle */
+__global__ void k_single_leaf(Bvh2View B, unsigned n, Node8* nodes, const float4* tri_gid, float4* tri_wide) {
+    if(threadIdx.x || blockIdx.x) return;
+    int ch[8];
+    for(int s = 0; s < 8; s++) ch[s] = kEmptyChild;
+    ch[0] = encode_leaf_range(0, n);
+    Node8 node;
+    encode_node(B, ch, 0, 0, node);
+    nodes[0] = node;
+    for(unsigned k = 0; k < n; k++)
+        for(int q = 0; q < 3; q++) tri_wide[3 * k + q] = tri_gid[3 * B.order[k] + q];
+}
+
+/* ---- orchestration ---------------------------------------------------------------------------- */
+template <typename T> static int dmalloc(T*& p, size_t count) {
+    p = nullptr;
+    if(count == 0) count = 1;
+    GPURT_CUDA(cudaMalloc((void**)&p, count * sizeof(T)));
+    return GPURT_OK;
+}
+#define TRY(x)                                                                                     \
+    do {                                                                                           \
+        int rc_ = (x);                                                                             \
+        if(rc_) return rc_;                                                                        \
+    } while(0)
+
+void free_accel_device(gpurt_accel* A) {
+    void* ptrs[] = {A->tri_gid, A->tri_lo, A->tri_hi, A->keys, A->order, A->left, A->right, A->parent,
+                    A->range_first, A->range_last, A->node_lo, A->node_hi, A->nodes, A->tri_wide};
+    for(void* p : ptrs)
+        if(p) cudaFree(p);
+    A->tri_gid = A->tri_lo = A->tri_hi = A->node_lo = A->node_hi = A->tri_wide = nullptr;
+    A->keys = nullptr, A->order = nullptr, A->nodes = nullptr;
+    A->left = A->right = A->parent = A->range_first = A->range_last = nullptr;
+    free_scene(A->dscene);
+}
+
+int build_accel_device(gpurt_accel* A) {
+    gpurt_ctx* ctx = A->ctx;
+    cudaStream_t st = ctx->stream;
+    GPURT_CUDA(cudaSetDevice(ctx->device));
+    TRY(upload_scene(ctx, A->scene, A->dscene));
+    const unsigned n = A->dscene.n_tris;
+    A->n = n;
+    cudaEvent_t e0, e1;
+    GPURT_CUDA(cudaEventCreate(&e0));
+    GPURT_CUDA(cudaEventCreate(&e1));
+    GPURT_CUDA(cudaEventRecord(e0, st));
+
+    TRY(dmalloc(A->tri_gid, 3ull * n));
+    TRY(dmalloc(A->tri_lo, n));
+    TRY(dmalloc(A->tri_hi, n));
+    TRY(dmalloc(A->keys, n));
+    TRY(dmalloc(A->order, n));
+    TRY(dmalloc(A->tri_wide, 3ull * n));
+
+    float* d_box = nullptr;
+    TRY(dmalloc(d_box, 6));
+    float init[6] = {3.0e38f, 3.0e38f, 3.0e38f, -3.0e38f, -3.0e38f, -3.0e38f};
+    GPURT_CUDA(cudaMemcpyAsync(d_box, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    if(n) k_flatten<<<cdiv(n, 256), 256, 0, st>>>(A->dscene, A->tri_gid, A->tri_lo, A->tri_hi, d_box);
+    GPURT_CUDA(cudaMemcpyAsync(A->scene_box, d_box, sizeof(init), cudaMemcpyDeviceToHost, st));
+    GPURT_CUDA(cudaStreamSynchronize(st));
+    cudaFree(d_box);
+    if(n == 0) {
+        for(float& f : A->scene_box) f = 0;
+        A->n_nodes = 0, A->depth = 0;
+        TRY(dmalloc(A->nodes, 1));
+        cudaEventDestroy(e0), cudaEventDestroy(e1);
+        return GPURT_OK;
+    }
+    const float* sb = A->scene_box;
+    float maxabs = 0;
+    for(int k = 0; k < 6; k++) maxabs = fmaxf(maxabs, fabsf(sb[k]));
+    A->inflate = fmaxf(maxabs, 1e-30f) * 1.9073486328125e-06f; /* N7: 2^-19 * max|coord| */
+    float ext[3] = {sb[3] - sb[0], sb[4] - sb[1], sb[5] - sb[2]}, inv[3];
+    for(int k = 0; k < 3; k++) inv[k] = ext[k] > 0 ? 1.0f / ext[k] : 0.0f;
+
+    /* keys + sort */
+    uint64_t* keys_tmp = nullptr;
+    uint32_t* vals_tmp = nullptr;
+    TRY(dmalloc(keys_tmp, n));
+    TRY(dmalloc(vals_tmp, n));
+    k_morton<<<cdiv(n, 256), 256, 0, st>>>(A->tri_lo, A->tri_hi, n, sb[0], sb[1], sb[2], inv[0], inv[1],
+                                          inv[2], A->keys, A->order);
+    TRY(radix_sort_u64(st, A->keys, A->order, keys_tmp, vals_tmp, n, 8, ctx->scratch));
+
+    /* binary tree */
+    const unsigned ni = n > 1 ? n - 1 : 0;
+    TRY(dmalloc(A->left, ni));
+    TRY(dmalloc(A->right, ni));
+    TRY(dmalloc(A->parent, (size_t)ni + n));
+    TRY(dmalloc(A->range_first, ni));
+    TRY(dmalloc(A->range_last, ni));
+    TRY(dmalloc(A->node_lo, ni));
+    TRY(dmalloc(A->node_hi, ni));
+    unsigned* arrive = (unsigned*)vals_tmp; /* reuse */
+    if(ni) {
+        GPURT_CUDA(cudaMemsetAsync(arrive, 0, (size_t)ni * 4, st));
+        k_karras<<<cdiv(ni, 256), 256, 0, st>>>(A->keys, (int)n, A->left, A->right, A->parent,
+                                               A->range_first, A->range_last);
+        k_refit<<<cdiv(n, 256), 256, 0, st>>>((int)n, A->left, A->right, A->parent, A->order, A->tri_lo,
+                                             A->tri_hi, A->node_lo, A->node_hi, arrive);
+    }
+    GPURT_CUDA(cudaGetLastError());
+
+    Bvh2View B;
+    B.left = A->left, B.right = A->right, B.range_first = A->range_first, B.range_last = A->range_last;
+    B.node_lo = A->node_lo, B.node_hi = A->node_hi, B.tri_lo = A->tri_lo, B.tri_hi = A->tri_hi;
+    B.order = A->order, B.inflate = A->inflate;
+
+    /* wide collapse. Upper bound on wide nodes: every inner node owns > kMaxLeafTris triangles and
+     * has >= 2 children, so there are fewer than n/2 of them. */
+    size_t max_nodes = (size_t)n / 2 + 2;
+    TRY(dmalloc(A->nodes, max_nodes));
+    if(n <= (unsigned)kMaxLeafTris) {
+        k_single_leaf<<<1, 32, 0, st>>>(B, n, A->nodes, A->tri_gid, A->tri_wide);
+        A->n_nodes = 1, A->depth = 1;
+    } else {
+        size_t max_items = max_nodes;
+        int *items_a = nullptr, *items_b = nullptr, *children = nullptr;
+        uint32_t *cnt_i = nullptr, *cnt_t = nullptr;
+        TRY(dmalloc(items_a, max_items));
+        TRY(dmalloc(items_b, max_items));
+        TRY(dmalloc(children, 8 * max_items));
+        TRY(dmalloc(cnt_i, max_items + 1));
+        TRY(dmalloc(cnt_t, max_items + 1));
+        int root = 0;
+        GPURT_CUDA(cudaMemcpyAsync(items_a, &root, 4, cudaMemcpyHostToDevice, st));
+        unsigned n_items = 1, level_base = 0, tri_cursor = 0, depth = 0;
+        DevBuf scan_tmp;
+        TRY(scan_tmp.reserve(scan_tmp_bytes(max_items + 1)));
+        while(n_items) {
+            k_collapse_count<<<cdiv(n_items, 128), 128, 0, st>>>(B, items_a, n_items, children, cnt_i, cnt_t);
+            GPURT_CUDA(cudaMemsetAsync(cnt_i + n_items, 0, 4, st));
+            GPURT_CUDA(cudaMemsetAsync(cnt_t + n_items, 0, 4, st));
+            TRY(scan_rec(st, cnt_i, cnt_i, n_items + 1, scan_tmp.as<uint32_t>()));
+            TRY(scan_rec(st, cnt_t, cnt_t, n_items + 1, scan_tmp.as<uint32_t>()));
+            unsigned next_base = level_base + n_items;
+            k_collapse_emit<<<cdiv(n_items, 128), 128, 0, st>>>(B, n_items, children, cnt_i, cnt_t,
+                                                               level_base, next_base, tri_cursor,
+                                                               A->nodes, items_b, A->tri_gid, A->tri_wide);
+            uint32_t tot[2];
+            GPURT_CUDA(cudaMemcpyAsync(&tot[0], cnt_i + n_items, 4, cudaMemcpyDeviceToHost, st));
+            GPURT_CUDA(cudaMemcpyAsync(&tot[1], cnt_t + n_items, 4, cudaMemcpyDeviceToHost, st));
+            GPURT_CUDA(cudaStreamSynchronize(st));
+            level_base = next_base;
+            tri_cursor += tot[1];
+            n_items = tot[0];
+            int* sw = items_a;
+            items_a = items_b, items_b = sw;
+            depth++;
+            if((size_t)level_base + n_items > max_nodes) {
+                set_error("wide node bound exceeded");
+                return GPURT_E_STATE;
+            }
+        }
+        A->n_nodes = level_base;
+        A->depth = depth;
+        scan_tmp.release();
+        cudaFree(items_a), cudaFree(items_b), cudaFree(children), cudaFree(cnt_i), cudaFree(cnt_t);
+        if(tri_cursor != n) {
+            set_error("collapse lost triangles: " + std::to_string(tri_cursor) + " of " + std::to_string(n));
+            return GPURT_E_STATE;
+        }
+    }
+    GPURT_CUDA(cudaEventRecord(e1, st));
+    GPURT_CUDA(cudaStreamSynchronize(st));
+    cudaEventElapsedTime(&A->build_ms, e0, e1);
+    cudaEventDestroy(e0), cudaEventDestroy(e1);
+    cudaFree(keys_tmp), cudaFree(vals_tmp);
+    A->has_bvh2 = true;
+    if(!(A->flags & GPURT_BUILD_KEEP_BVH2)) {
+        /* the binary tree is only needed for get_bvh2 / the bvh2 debug trace */
+        void* drop[] = {A->parent, A->range_first, A->range_last};
+        for(void* p : drop) cudaFree(p);
+        A->parent = A->range_first = A->range_last = nullptr;
+    }
+    GPURT_CUDA(cudaGetLastError());
+    return GPURT_OK;
+}
+
+} // namespace gpurt

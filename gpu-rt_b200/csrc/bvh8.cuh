@@ -1,0 +1,317 @@
+/*
+ * bvh8.cuh — the compressed 8-wide BVH node: layout, collapse from the binary LBVH, child tests.
+ *
+ * Replaces the opaque NVIDIA acceleration structure built at src/vk/vulkan.cpp:877 and walked by
+ * traceRayEXT (src/shaders/rt/rt.rgen:258).  Layout follows the compressed-wide-BVH idea
+ * (Ylitie, Karras, Laine 2017): 80 bytes = 5 x 16-byte loads per 8 children.
+ *
+ *   vec0: p.x p.y p.z | ex ey ez imask          quantisation origin, per-axis exponents, inner mask
+ *   vec1: child_base | tri_base | meta[0..3] | meta[4..7]
+ *   vec2: qlo_x[0..7] | qlo_y[0..7]             8-bit child boxes on the grid p + q * 2^(e-127)
+ *   vec3: qlo_z[0..7] | qhi_x[0..7]
+ *   vec4: qhi_y[0..7] | qhi_z[0..7]
+ *
+ *   meta[i] == 0            empty slot
+ *   inner child  (imask i)  meta = 0x20 | (24 + i); the child node is child_base + popc(imask & ((1<<i)-1))
+ *   leaf child              meta = unary(count) << 5 | first triangle offset from tri_base (count<=3,
+ *                           at most 24 triangles per node, stored contiguously in wide order)
+ *
+ * Slot i encodes the octant of the child relative to the node centre (bit0:+x bit1:+y bit2:+z), so a
+ * ray visits hit children in front-to-back order by popping the highest bit of
+ * (24 + (i ^ octinv)) without sorting distances.
+ */
+#pragma once
+#include "common.cuh"
+
+namespace gpurt {
+
+struct Node8 {
+    float4 v[5];
+};
+
+/* children produced by the collapse, before encoding */
+constexpr int kEmptyChild = (int)0x80000000;
+/* >= 0: BVH2 internal node that becomes an inner child; < 0 (and != empty): leaf range */
+GPURT_HD int encode_leaf_range(unsigned first, unsigned count) { return ~(int)((first << 2) | count); }
+GPURT_HD void decode_leaf_range(int c, unsigned& first, unsigned& count) {
+    unsigned u = (unsigned)~c;
+    first = u >> 2;
+    count = u & 3u;
+}
+
+/* Read-only view of the binary LBVH (Karras 2012) the collapse consumes. */
+struct Bvh2View {
+    const int* left;        /* >=0 internal, <0 leaf ~sorted_pos */
+    const int* right;
+    const int* range_first; /* per internal node: first sorted position covered */
+    const int* range_last;
+    const float4* node_lo;  /* exact boxes of internal nodes */
+    const float4* node_hi;
+    const float4* tri_lo;   /* exact boxes of triangles, gid order */
+    const float4* tri_hi;
+    const unsigned* order;  /* sorted position -> gid */
+    float inflate;
+};
+
+GPURT_HD Box3 bvh2_child_box(const Bvh2View& B, int c) {
+    Box3 b;
+    if(c >= 0) {
+        float4 lo = B.node_lo[c], hi = B.node_hi[c];
+        b.lo = f3(lo.x, lo.y, lo.z), b.hi = f3(hi.x, hi.y, hi.z);
+    } else {
+        unsigned g = B.order[~c];
+        float4 lo = B.tri_lo[g], hi = B.tri_hi[g];
+        b.lo = f3(lo.x, lo.y, lo.z), b.hi = f3(hi.x, hi.y, hi.z);
+    }
+    return b;
+}
+GPURT_HD int bvh2_count(const Bvh2View& B, int c) {
+    return c < 0 ? 1 : B.range_last[c] - B.range_first[c] + 1;
+}
+/* leaf-like: at most kMaxLeafTris triangles, contiguous in sorted order */
+GPURT_HD int bvh2_to_child(const Bvh2View& B, int c) {
+    if(c < 0) return encode_leaf_range((unsigned)~c, 1);
+    int n = bvh2_count(B, c);
+    if(n <= kMaxLeafTris) return encode_leaf_range((unsigned)B.range_first[c], (unsigned)n);
+    return c;
+}
+
+/* Greedy surface-area collapse: start from the two children of BVH2 node `root`, repeatedly open
+ * the inner candidate with the largest area until 8 children.  Then assign children to octant
+ * slots (greedy on the signed centroid projection).  out_child[8] is indexed by slot. Returns the
+ * number of inner children; n_leaf_tris gets the triangles referenced by leaf slots. */
+GPURT_HD int collapse_node(const Bvh2View& B, int root, int out_child[8], int& n_leaf_tris) {
+    int cand[8]; /* raw BVH2 refs */
+    int n = 2;
+    cand[0] = B.left[root];
+    cand[1] = B.right[root];
+    while(n < 8) {
+        int best = -1;
+        float best_area = -1.0f;
+        for(int i = 0; i < n; i++) {
+            int c = cand[i];
+            if(c < 0 || bvh2_count(B, c) <= kMaxLeafTris) continue;
+            float a = box_area(bvh2_child_box(B, c));
+            if(a > best_area) best_area = a, best = i;
+        }
+        if(best < 0) break;
+        int c = cand[best];
+        cand[best] = B.left[c];
+        cand[n++] = B.right[c];
+    }
+    /* node centre from the union of candidate boxes */
+    Box3 nb = bvh2_child_box(B, cand[0]);
+    F3 cen[8];
+    for(int i = 0; i < n; i++) {
+        Box3 b = bvh2_child_box(B, cand[i]);
+        cen[i] = (b.lo + b.hi) * 0.5f;
+        nb.lo = f3(fminf(nb.lo.x, b.lo.x), fminf(nb.lo.y, b.lo.y), fminf(nb.lo.z, b.lo.z));
+        nb.hi = f3(fmaxf(nb.hi.x, b.hi.x), fmaxf(nb.hi.y, b.hi.y), fmaxf(nb.hi.z, b.hi.z));
+    }
+    F3 nc = (nb.lo + nb.hi) * 0.5f;
+    for(int s = 0; s < 8; s++) out_child[s] = kEmptyChild;
+    unsigned used_child = 0, used_slot = 0;
+    for(int round = 0; round < n; round++) {
+        float best = -3.0e38f;
+        int bc = -1, bs = -1;
+        for(int i = 0; i < n; i++) {
+            if(used_child & (1u << i)) continue;
+            F3 dlt = cen[i] - nc;
+            for(int s = 0; s < 8; s++) {
+                if(used_slot & (1u << s)) continue;
+                float cost = ((s & 1) ? dlt.x : -dlt.x) + ((s & 2) ? dlt.y : -dlt.y) +
+                             ((s & 4) ? dlt.z : -dlt.z);
+                if(cost > best) best = cost, bc = i, bs = s;
+            }
+        }
+        used_child |= 1u << bc;
+        used_slot |= 1u << bs;
+        out_child[bs] = bvh2_to_child(B, cand[bc]);
+    }
+    int n_inner = 0;
+    n_leaf_tris = 0;
+    for(int s = 0; s < 8; s++) {
+        int c = out_child[s];
+        if(c == kEmptyChild) continue;
+        if(c >= 0) n_inner++;
+        else {
+            unsigned f, k;
+            decode_leaf_range(c, f, k);
+            n_leaf_tris += (int)k;
+        }
+    }
+    return n_inner;
+}
+
+/* box of a collapsed child (exact), from the BVH2 */
+GPURT_HD Box3 collapsed_child_box(const Bvh2View& B, int c) {
+    if(c >= 0) return bvh2_child_box(B, c);
+    unsigned first, count;
+    decode_leaf_range(c, first, count);
+    Box3 b = bvh2_child_box(B, ~(int)first);
+    for(unsigned k = 1; k < count; k++) {
+        Box3 t = bvh2_child_box(B, ~(int)(first + k));
+        b.lo = f3(fminf(b.lo.x, t.lo.x), fminf(b.lo.y, t.lo.y), fminf(b.lo.z, t.lo.z));
+        b.hi = f3(fmaxf(b.hi.x, t.hi.x), fmaxf(b.hi.y, t.hi.y), fmaxf(b.hi.z, t.hi.z));
+    }
+    return b;
+}
+
+GPURT_HD unsigned pick_exponent(float extent) {
+    /* smallest e with extent <= 255 * 2^(e-127); extent >= 0 */
+    if(!(extent > 0.0f)) return 1u;
+    unsigned e = (f2u(extent) >> 23) & 0xffu; /* 2^(e-127) <= extent < 2^(e-126) */
+    e = e > 7u ? e - 7u : 1u;                 /* extent/2^(e-7-127) < 256 */
+    while(extent > 255.0f * u2f(e << 23)) e++;
+    if(e < 1u) e = 1u;
+    if(e > 254u) e = 254u;
+    return e;
+}
+
+/* Encode one node. child[8] by slot; child boxes are inflated by B.inflate (N7) and quantised
+ * outward.  child_base / tri_base are absolute indices. */
+GPURT_HD void encode_node(const Bvh2View& B, const int child[8], unsigned child_base,
+                          unsigned tri_base, Node8& out) {
+    Box3 cb[8];
+    Box3 nb;
+    nb.lo = f3(3.0e38f, 3.0e38f, 3.0e38f);
+    nb.hi = f3(-3.0e38f, -3.0e38f, -3.0e38f);
+    float e = B.inflate;
+    for(int s = 0; s < 8; s++) {
+        if(child[s] == kEmptyChild) continue;
+        Box3 b = collapsed_child_box(B, child[s]);
+        b.lo = f3(b.lo.x - e, b.lo.y - e, b.lo.z - e);
+        b.hi = f3(b.hi.x + e, b.hi.y + e, b.hi.z + e);
+        cb[s] = b;
+        nb.lo = f3(fminf(nb.lo.x, b.lo.x), fminf(nb.lo.y, b.lo.y), fminf(nb.lo.z, b.lo.z));
+        nb.hi = f3(fmaxf(nb.hi.x, b.hi.x), fmaxf(nb.hi.y, b.hi.y), fmaxf(nb.hi.z, b.hi.z));
+    }
+    unsigned ex = pick_exponent(nb.hi.x - nb.lo.x), ey = pick_exponent(nb.hi.y - nb.lo.y),
+             ez = pick_exponent(nb.hi.z - nb.lo.z);
+    float sx = u2f(ex << 23), sy = u2f(ey << 23), sz = u2f(ez << 23);
+    float ix = u2f((254u - ex) << 23), iy = u2f((254u - ey) << 23), iz = u2f((254u - ez) << 23);
+    unsigned imask = 0, meta[8], q[6][8];
+    unsigned tri_off = 0;
+    for(int s = 0; s < 8; s++) {
+        meta[s] = 0;
+        for(int k = 0; k < 6; k++) q[k][s] = k < 3 ? 255u : 0u;
+        int c = child[s];
+        if(c == kEmptyChild) continue;
+        if(c >= 0) {
+            imask |= 1u << s;
+            meta[s] = 0x20u | (24u + (unsigned)s);
+        } else {
+            unsigned first, count;
+            decode_leaf_range(c, first, count);
+            unsigned unary = count == 1 ? 1u : count == 2 ? 3u : 7u;
+            meta[s] = (unary << 5) | tri_off;
+            tri_off += count;
+        }
+        const Box3& b = cb[s];
+        float lo[3] = {b.lo.x, b.lo.y, b.lo.z}, hi[3] = {b.hi.x, b.hi.y, b.hi.z};
+        float p[3] = {nb.lo.x, nb.lo.y, nb.lo.z}, sc[3] = {sx, sy, sz}, isc[3] = {ix, iy, iz};
+        for(int a = 0; a < 3; a++) {
+            float fl = floorf((lo[a] - p[a]) * isc[a]);
+            float fh = ceilf((hi[a] - p[a]) * isc[a]);
+            fl = fminf(fmaxf(fl, 0.0f), 255.0f);
+            fh = fminf(fmaxf(fh, 0.0f), 255.0f);
+            /* keep the decoded box a superset under fp32 rounding of (x - p) */
+            if(fl > 0.0f && p[a] + fl * sc[a] > lo[a]) fl -= 1.0f;
+            if(fh < 255.0f && p[a] + fh * sc[a] < hi[a]) fh += 1.0f;
+            q[a][s] = (unsigned)fl;
+            q[3 + a][s] = (unsigned)fh;
+        }
+    }
+    auto pack4 = [](const unsigned* b) { return b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24); };
+    out.v[0].x = nb.lo.x, out.v[0].y = nb.lo.y, out.v[0].z = nb.lo.z;
+    out.v[0].w = u2f(ex | (ey << 8) | (ez << 16) | (imask << 24));
+    out.v[1].x = u2f(child_base), out.v[1].y = u2f(tri_base);
+    out.v[1].z = u2f(pack4(meta)), out.v[1].w = u2f(pack4(meta + 4));
+    out.v[2].x = u2f(pack4(q[0])), out.v[2].y = u2f(pack4(q[0] + 4));
+    out.v[2].z = u2f(pack4(q[1])), out.v[2].w = u2f(pack4(q[1] + 4));
+    out.v[3].x = u2f(pack4(q[2])), out.v[3].y = u2f(pack4(q[2] + 4));
+    out.v[3].z = u2f(pack4(q[3])), out.v[3].w = u2f(pack4(q[3] + 4));
+    out.v[4].x = u2f(pack4(q[4])), out.v[4].y = u2f(pack4(q[4] + 4));
+    out.v[4].z = u2f(pack4(q[5])), out.v[4].w = u2f(pack4(q[5] + 4));
+}
+
+/* ---- traversal-side decoding ------------------------------------------------------------------- */
+struct RaySetup {
+    F3 o, d, idir;
+    float tmin;
+    unsigned octinv; /* bit set where the ray travels towards + */
+};
+GPURT_HD float safe_rcp_dir(float d) {
+    float a = fabsf(d) > 1e-20f ? d : copysignf(1e-20f, d);
+    return 1.0f / a;
+}
+GPURT_HD RaySetup make_ray_setup(F3 o, F3 d, float tmin) {
+    RaySetup r;
+    r.o = o, r.d = d, r.tmin = tmin;
+    r.idir = f3(safe_rcp_dir(d.x), safe_rcp_dir(d.y), safe_rcp_dir(d.z));
+    r.octinv = (r.idir.x < 0.0f ? 0u : 1u) | (r.idir.y < 0.0f ? 0u : 2u) | (r.idir.z < 0.0f ? 0u : 4u);
+    return r;
+}
+GPURT_HD unsigned byte_of(unsigned lo4, unsigned hi4, int i) {
+    return ((i < 4 ? lo4 : hi4) >> (8 * (i & 3))) & 0xffu;
+}
+
+/* Test the 8 children of `n` against the ray interval [tmin, tmax]; returns the hit mask:
+ * bits 24..31 inner children in traversal priority, bits 0..23 triangles relative to tri_base. */
+GPURT_HD unsigned node_hitmask(const Node8& n, const RaySetup& r, float tmax) {
+    unsigned eb = f2u(n.v[0].w);
+    unsigned imask = eb >> 24;
+    float sx = u2f((eb & 0xffu) << 23) * r.idir.x;
+    float sy = u2f(((eb >> 8) & 0xffu) << 23) * r.idir.y;
+    float sz = u2f(((eb >> 16) & 0xffu) << 23) * r.idir.z;
+    float ox = (n.v[0].x - r.o.x) * r.idir.x;
+    float oy = (n.v[0].y - r.o.y) * r.idir.y;
+    float oz = (n.v[0].z - r.o.z) * r.idir.z;
+    unsigned m_lo = f2u(n.v[1].z), m_hi = f2u(n.v[1].w);
+    /* near / far byte planes per axis according to the ray octant */
+    bool px = r.idir.x >= 0.0f, py = r.idir.y >= 0.0f, pz = r.idir.z >= 0.0f;
+    unsigned nx0 = f2u(px ? n.v[2].x : n.v[3].z), nx1 = f2u(px ? n.v[2].y : n.v[3].w);
+    unsigned fx0 = f2u(px ? n.v[3].z : n.v[2].x), fx1 = f2u(px ? n.v[3].w : n.v[2].y);
+    unsigned ny0 = f2u(py ? n.v[2].z : n.v[4].x), ny1 = f2u(py ? n.v[2].w : n.v[4].y);
+    unsigned fy0 = f2u(py ? n.v[4].x : n.v[2].z), fy1 = f2u(py ? n.v[4].y : n.v[2].w);
+    unsigned nz0 = f2u(pz ? n.v[3].x : n.v[4].z), nz1 = f2u(pz ? n.v[3].y : n.v[4].w);
+    unsigned fz0 = f2u(pz ? n.v[4].z : n.v[3].x), fz1 = f2u(pz ? n.v[4].w : n.v[3].y);
+    unsigned mask = 0;
+#pragma unroll
+    for(int i = 0; i < 8; i++) {
+        unsigned meta = byte_of(m_lo, m_hi, i);
+        if(meta == 0) continue;
+        float tnx = fmaf((float)byte_of(nx0, nx1, i), sx, ox);
+        float tny = fmaf((float)byte_of(ny0, ny1, i), sy, oy);
+        float tnz = fmaf((float)byte_of(nz0, nz1, i), sz, oz);
+        float tfx = fmaf((float)byte_of(fx0, fx1, i), sx, ox);
+        float tfy = fmaf((float)byte_of(fy0, fy1, i), sy, oy);
+        float tfz = fmaf((float)byte_of(fz0, fz1, i), sz, oz);
+        float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, r.tmin));
+        float tf = fminf(fminf(tfx, tfy), fminf(tfz, tmax));
+        if(tn <= tf) {
+            if((imask >> i) & 1u) mask |= 1u << (24u + ((unsigned)i ^ r.octinv));
+            else mask |= (meta >> 5) << (meta & 31u);
+        }
+    }
+    return mask;
+}
+
+/* squared distance from p to child i's decoded box (for the closest-point descent) */
+GPURT_HD float node_child_dist2(const Node8& n, int i, F3 p) {
+    unsigned eb = f2u(n.v[0].w);
+    float sx = u2f((eb & 0xffu) << 23), sy = u2f(((eb >> 8) & 0xffu) << 23),
+          sz = u2f(((eb >> 16) & 0xffu) << 23);
+    float lox = fmaf((float)byte_of(f2u(n.v[2].x), f2u(n.v[2].y), i), sx, n.v[0].x);
+    float loy = fmaf((float)byte_of(f2u(n.v[2].z), f2u(n.v[2].w), i), sy, n.v[0].y);
+    float loz = fmaf((float)byte_of(f2u(n.v[3].x), f2u(n.v[3].y), i), sz, n.v[0].z);
+    float hix = fmaf((float)byte_of(f2u(n.v[3].z), f2u(n.v[3].w), i), sx, n.v[0].x);
+    float hiy = fmaf((float)byte_of(f2u(n.v[4].x), f2u(n.v[4].y), i), sy, n.v[0].y);
+    float hiz = fmaf((float)byte_of(f2u(n.v[4].z), f2u(n.v[4].w), i), sz, n.v[0].z);
+    float dx = fmaxf(fmaxf(lox - p.x, p.x - hix), 0.0f);
+    float dy = fmaxf(fmaxf(loy - p.y, p.y - hiy), 0.0f);
+    float dz = fmaxf(fmaxf(loz - p.z, p.z - hiz), 0.0f);
+    return fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+}
+
+} // namespace gpurt

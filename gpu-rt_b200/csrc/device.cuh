@@ -1,0 +1,123 @@
+/*
+ * device.cuh — CUDA-side internals of libgpurt.so: context, device scene, acceleration structure.
+ */
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "../host/internal.h"
+#include "bvh8.cuh"
+
+namespace gpurt {
+
+#define GPURT_CUDA(call)                                                                           \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if(e_ != cudaSuccess) {                                                                    \
+            gpurt::set_error(std::string(#call) + ": " + cudaGetErrorString(e_));                  \
+            return GPURT_E_CUDA;                                                                   \
+        }                                                                                          \
+    } while(0)
+
+/* grow-only device / pinned buffers */
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes);
+    void release();
+    template <typename T> T* as() const { return (T*)p; }
+};
+struct PinBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes);
+    void release();
+};
+
+} // namespace gpurt
+
+struct gpurt_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    cudaStream_t own_stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float last_ms = 0;
+    /* staging for GPURT_MEM_HOST calls */
+    gpurt::DevBuf d_in, d_out;
+    gpurt::PinBuf h_in, h_out;
+    gpurt::DevBuf scratch;
+};
+
+namespace gpurt {
+
+/* Device copy of PackedScene: the descriptor arrays of src/vk/rt.cpp:529-741 as plain pointers. */
+struct DeviceScene {
+    Vertex* verts = nullptr;
+    uint32_t* idx = nullptr;
+    uint32_t* tri_off = nullptr;
+    uint32_t* vert_off = nullptr;
+    SceneDesc* descs = nullptr;
+    SceneLight* lights = nullptr;
+    uint32_t n_objs = 0, n_tris = 0, n_lights = 0, n_verts = 0;
+    uint64_t version = 0;
+    /* textures: RGBA8 texels, one allocation, per-texture (offset,w,h) table */
+    uint8_t* texels = nullptr;
+    uint4* tex_info = nullptr; /* x: texel offset, y: w, z: h */
+    uint32_t n_textures = 0;
+};
+
+int upload_scene(gpurt_ctx* ctx, gpurt_scene* s, DeviceScene& out);
+void free_scene(DeviceScene& d);
+
+/* exclusive prefix sum of n u32 values (in place allowed), returns total via d_total (device) */
+int exclusive_scan_u32(cudaStream_t st, const uint32_t* in, uint32_t* out, size_t n, DevBuf& tmp);
+size_t scan_tmp_bytes(size_t n);
+
+/* stable LSD radix sort of 64-bit keys with 32-bit payload, 8 bits per pass */
+int radix_sort_u64(cudaStream_t st, uint64_t* keys, uint32_t* vals, uint64_t* keys_tmp,
+                   uint32_t* vals_tmp, size_t n, int passes, DevBuf& tmp);
+
+} // namespace gpurt
+
+struct gpurt_accel {
+    gpurt_ctx* ctx = nullptr;
+    gpurt_scene* scene = nullptr;
+    gpurt::DeviceScene dscene;
+    uint32_t n = 0;
+    uint32_t flags = 0;
+    /* gid order */
+    float4* tri_gid = nullptr; /* 3 x float4 per triangle */
+    float4* tri_lo = nullptr;
+    float4* tri_hi = nullptr;
+    /* canonical order */
+    uint64_t* keys = nullptr;
+    uint32_t* order = nullptr;
+    /* binary LBVH */
+    int *left = nullptr, *right = nullptr, *parent = nullptr, *range_first = nullptr,
+        *range_last = nullptr;
+    float4 *node_lo = nullptr, *node_hi = nullptr;
+    /* wide BVH */
+    gpurt::Node8* nodes = nullptr;
+    float4* tri_wide = nullptr;
+    uint32_t n_nodes = 0, depth = 0;
+    float scene_box[6] = {0, 0, 0, 0, 0, 0};
+    float inflate = 0;
+    float build_ms = 0;
+    bool has_bvh2 = false;
+};
+
+namespace gpurt {
+int build_accel_device(gpurt_accel* A);
+void free_accel_device(gpurt_accel* A);
+
+/* query launchers (device pointers, async on ctx->stream) */
+int launch_trace_closest(gpurt_accel* A, const float4* rays, uint64_t n, float4* hits);
+int launch_trace_any(gpurt_accel* A, const float4* rays, uint64_t n, uint8_t* occ);
+int launch_trace_closest_bvh2(gpurt_accel* A, const float4* rays, uint64_t n, float4* hits);
+int launch_trace_closest_stats(gpurt_accel* A, const float4* rays, uint64_t n, float4* hits,
+                               unsigned long long* d_counters);
+int launch_closest_points(gpurt_accel* A, const float4* queries, uint64_t n, float4* results);
+} // namespace gpurt

@@ -1,0 +1,164 @@
+"""GPU parity tests proper: CUDA path (through the C ABI) vs the CPU oracle, bit-exact."""
+import numpy as np
+import pytest
+
+from scenes import load_scene, same_bits, soup, world_tris
+
+pytestmark = pytest.mark.gpu
+
+
+def _check_build(gpurt, orc, accel, tris):
+    ob = orc.Bvh(tris)
+    info = accel.info()
+    assert info.n_tris == tris.shape[0]
+    if tris.shape[0]:
+        assert same_bits(np.array(list(info.scene_min) + list(info.scene_max), np.float32), ob.scene_box())
+        assert info.inflation == ob.inflation()
+    assert (accel.morton_keys() == ob.keys()).all(), "sorted Morton keys differ"
+    assert (accel.prim_order() == ob.prim_order()).all(), "canonical primitive order differs"
+    l, r, b = accel.bvh2()
+    ol, orr, obx = ob.bvh2()
+    assert (l == ol).all() and (r == orr).all(), "Karras topology differs"
+    assert same_bits(b, obx), "refit boxes differ"
+    return ob
+
+
+def _check_queries(gpurt, orc, accel, ob, tris, n_rays, brute_n, box=None):
+    if box is None:
+        box = ob.scene_box() if tris.shape[0] else np.array([0, 0, 0, 1, 1, 1], np.float32)
+    rays = orc.gen_random_rays(n_rays, 0xC0FFEE, box)
+    hits = accel.trace_closest(rays)
+    ref = ob.closest_hit(rays)
+    assert same_bits(hits, ref), f"closest hit: {(hits.view(np.uint32).reshape(-1,4) != ref.view(np.uint32).reshape(-1,4)).any(axis=1).sum()} rays differ"
+    if tris.shape[0] > 1:
+        assert same_bits(accel.trace_closest(rays, bvh2=True), ref), "binary-LBVH trace differs"
+    occ = accel.trace_any(rays)
+    assert (occ == ob.any_hit(rays)).all()
+    assert ((hits["prim"] != gpurt.NO_HIT) == (occ != 0)).all()
+    # brute force on a subset pins the oracle BVH itself
+    sub = rays[:brute_n]
+    assert same_bits(orc.closest_hit_brute(tris, sub), ref[:brute_n])
+    # shadow-style rays: short segments (rt.rgen:272-291)
+    seg = rays.copy()
+    seg[:, 7] = np.linspace(0.01, 3.0, n_rays, dtype=np.float32)
+    assert (accel.trace_any(seg) == ob.any_hit(seg)).all()
+    for r2 in (np.inf, 0.05):
+        q = orc.gen_random_points(n_rays, 0xFACADE, box, r2=r2)
+        cp = accel.closest_points(q)
+        cref = ob.closest_point(q)
+        for f in ("p", "dist", "u", "v"):
+            assert same_bits(cp[f], cref[f]), f"closest point field {f} (r2={r2})"
+        assert (cp["prim"] == cref["gid"]).all()
+        cb = orc.closest_point_brute(tris, q[:brute_n])
+        assert same_bits(cb, cref[:brute_n])
+    return hits
+
+
+@pytest.mark.parametrize("name", ["cube", "mis_test", "cbox"])
+def test_reference_scenes(gpurt, orc, ctx, name):
+    scene = load_scene(gpurt, ctx, name)
+    tris = world_tris(orc, scene)
+    accel = gpurt.Accel(scene, gpurt.BUILD_KEEP_BVH2)
+    ob = _check_build(gpurt, orc, accel, tris)
+    n = 1 << 20 if name == "cbox" else 1 << 17   # 1,048,576 rays / queries
+    hits = _check_queries(gpurt, orc, accel, ob, tris, n, 1 << 15)
+    # hit ids map back to (gl_InstanceCustomIndexEXT, gl_PrimitiveID)
+    offs = scene.tri_offsets()
+    h = hits["prim"][hits["prim"] != gpurt.NO_HIT]
+    obj = np.searchsorted(offs, h, side="right") - 1
+    assert (obj >= 0).all() and (obj < len(offs) - 1).all() and (h - offs[obj] < offs[obj + 1] - offs[obj]).all()
+    accel.close(), scene.close()
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 4, 5, 9, 33, 1000, 100000])
+def test_soups_and_edge_sizes(gpurt, orc, ctx, n):
+    tris = soup(n, seed=n + 7)
+    if n >= 33:
+        tris[10:20] = tris[10]          # duplicate triangles -> equal Morton keys, equal t ties
+    scene = gpurt.Scene(ctx)
+    if n:
+        scene.add_triangles(tris)
+    accel = gpurt.Accel(scene, gpurt.BUILD_KEEP_BVH2)
+    if n == 0:
+        rays = orc.gen_random_rays(1000, 1, np.array([0, 0, 0, 1, 1, 1], np.float32))
+        assert (accel.trace_closest(rays)["prim"] == gpurt.NO_HIT).all()
+        assert (accel.trace_any(rays) == 0).all()
+        assert (accel.closest_points(orc.gen_random_points(1000, 2, np.array([0, 0, 0, 1, 1, 1], np.float32)))["prim"] == gpurt.NO_HIT).all()
+    else:
+        ob = _check_build(gpurt, orc, accel, tris)
+        _check_queries(gpurt, orc, accel, ob, tris, 1 << 15, 1 << 12)
+    accel.close(), scene.close()
+
+
+def test_coplanar_grid_ties(gpurt, orc, ctx):
+    """axis-aligned quads sharing edges and exactly duplicated layers: equal-t ties -> lowest id"""
+    g = []
+    for layer in range(2):
+        for i in range(24):
+            for j in range(24):
+                x0, x1, y0, y1 = i / 24, (i + 1) / 24, j / 24, (j + 1) / 24
+                g.append([x0, y0, 0.5, x1, y0, 0.5, x1, y1, 0.5])
+                g.append([x0, y0, 0.5, x1, y1, 0.5, x0, y1, 0.5])
+    tris = np.array(g, np.float32)
+    scene = gpurt.Scene(ctx)
+    scene.add_triangles(tris)
+    accel = gpurt.Accel(scene, gpurt.BUILD_KEEP_BVH2)
+    ob = _check_build(gpurt, orc, accel, tris)
+    hits = _check_queries(gpurt, orc, accel, ob, tris, 1 << 16, 1 << 12, box=np.array([0, 0, 0, 1, 1, 1], np.float32))
+    hit = hits["prim"] != gpurt.NO_HIT
+    assert hit.any() and (hits["prim"][hit] < len(g) // 2).all(), "ties must resolve to the lower (first-layer) id"
+    accel.close(), scene.close()
+
+
+def test_device_buffers_match_host_buffers(gpurt, orc, ctx):
+    import torch
+    scene = load_scene(gpurt, ctx, "cbox")
+    accel = gpurt.Accel(scene)
+    box = np.array(list(accel.info().scene_min) + list(accel.info().scene_max), np.float32)
+    rays = orc.gen_random_rays(200000, 5, box)
+    host = accel.trace_closest(rays)
+    d_rays = torch.from_numpy(rays).cuda()
+    d_hits = accel.trace_closest(d_rays)
+    torch.cuda.synchronize()
+    assert same_bits(d_hits.cpu().numpy(), host)
+    st = accel.trace_stats(d_rays, d_hits)
+    assert st.rays == 200000 and st.hits == int((host["prim"] != gpurt.NO_HIT).sum())
+    assert st.nodes_visited > st.rays
+    accel.close(), scene.close()
+
+
+def test_sponza_standin_properties(gpurt, orc, ctx):
+    """full-size stand-in (262,267 tris): oracle BVH agreement + size-independent properties"""
+    scene = load_scene(gpurt, ctx, "sponza_standin")
+    c = scene.counts()
+    assert c["tris"] == 262267 and c["objs"] == 103 and c["lights"] == 0
+    tris = world_tris(orc, scene)
+    accel = gpurt.Accel(scene, gpurt.BUILD_KEEP_BVH2)
+    ob = _check_build(gpurt, orc, accel, tris)
+    info = accel.info()
+    assert np.allclose(list(info.scene_min), [-1921, -126, -1183]) and np.allclose(list(info.scene_max), [1800, 1429, 1105])
+    rays = orc.gen_random_rays(1 << 19, 11, ob.scene_box(), frac=-0.05)
+    hits = accel.trace_closest(rays)
+    assert same_bits(hits, ob.closest_hit(rays))
+    # property: the reported hit point re-derived from barycentrics lies on the ray at t
+    h = hits["prim"] != gpurt.NO_HIT
+    assert h.mean() > 0.99  # origins inside a closed atrium
+    t9 = tris[hits["prim"][h]].reshape(-1, 3, 3).astype(np.float64)
+    u, v = hits["u"][h].astype(np.float64)[:, None], hits["v"][h].astype(np.float64)[:, None]
+    p_tri = t9[:, 0] * (1 - u - v) + t9[:, 1] * u + t9[:, 2] * v
+    p_ray = rays[h, 0:3].astype(np.float64) + hits["t"][h].astype(np.float64)[:, None] * rays[h, 4:7].astype(np.float64)
+    assert np.abs(p_tri - p_ray).max() < 0.5  # scene extent ~3700 units, fp32
+    # property: shortening the ray to just before / after the hit flips visibility
+    seg = rays[h].copy()
+    seg[:, 7] = hits["t"][h] * 0.999
+    assert (accel.trace_any(seg) == 0).all()
+    seg[:, 7] = hits["t"][h] * 1.001 + 1e-3
+    assert (accel.trace_any(seg) == 1).all()
+    # property: a closest point is never farther than any triangle vertex; distance is idempotent
+    q = orc.gen_random_points(1 << 18, 13, ob.scene_box(), frac=0.1)
+    cp = accel.closest_points(q)
+    assert same_bits(cp["dist"], ob.closest_point(q)["dist"])
+    q2 = q.copy()
+    q2[:, 0:3] = cp["p"]
+    assert (accel.closest_points(q2)["dist"] <= 1e-3 * 3700).all()
+    accel.close(), scene.close()

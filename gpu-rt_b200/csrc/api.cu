@@ -124,7 +124,7 @@ int gpurt_ctx_destroy(gpurt_ctx* c) {
 }
 int gpurt_ctx_set_stream(gpurt_ctx* c, void* stream) {
     if(!c) return set_error("NULL context"), GPURT_E_INVALID;
-    c->stream = stream ? (cudaStream_t)stream : c->own_stream;
+    c->stream = stream == GPURT_STREAM_OWN ? c->own_stream : (cudaStream_t)stream;
     return GPURT_OK;
 }
 int gpurt_ctx_synchronize(gpurt_ctx* c) {

@@ -179,8 +179,16 @@ void make_sponza_standin(Scene& sc) {
     /* 1 floor mosaic: a fan that brings the total to exactly 262,267 triangles */
     {
         const size_t target = 262267;
-        int rest = (int)(target - tris);
-        b.fan(Vec3{-60.0f, Y0 + 0.5f, -40.0f}, Vec3{0, 1, 0}, 380.0f, rest, Vec3{1, 0, 0}, Vec3{0, 0, 1});
+        int rest = (int)(target - tris); /* 17,243 = 401 * 43: 401 segments x (21 rings of quads + centre fan) */
+        const int ns = 401, nr = (rest / ns - 1) / 2;
+        const Vec3 c{-60.0f, Y0 + 0.5f, -40.0f};
+        const float R = 380.0f, r0 = R / (float)(nr + 1);
+        b.fan(c, Vec3{0, 1, 0}, r0, ns, Vec3{1, 0, 0}, Vec3{0, 0, 1});
+        b.grid(ns, nr, [&](float s, float t, Vec3& p, Vec3& n) {
+            float a = TWO_PI * s, r = r0 + (R - r0) * t;
+            p = Vec3{c.x + r * std::cos(a), c.y, c.z + r * std::sin(a)};
+            n = Vec3{0, 1, 0};
+        });
         done();
     }
     (void)objs;

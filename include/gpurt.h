@@ -149,7 +149,9 @@ const char* gpurt_version(void);
 /* ---- context: replaces the VK::Manager singleton (src/vk/vulkan.cpp:17-20, :1136-1160) -------- */
 int gpurt_ctx_create(int device_ordinal, gpurt_ctx** out);
 int gpurt_ctx_destroy(gpurt_ctx* ctx);
-/* Use a caller-owned cudaStream_t (e.g. torch's current stream); NULL = context's own stream. */
+/* Launch on a caller-owned cudaStream_t (e.g. torch's current stream). NULL is CUDA's legacy default
+ * stream (what torch uses unless told otherwise); GPURT_STREAM_OWN goes back to the context's own. */
+#define GPURT_STREAM_OWN ((void*)(intptr_t)-1)
 int gpurt_ctx_set_stream(gpurt_ctx* ctx, void* cuda_stream);
 int gpurt_ctx_synchronize(gpurt_ctx* ctx);
 

@@ -34,4 +34,6 @@ def soup(n, seed=1, ext=0.05):
 
 
 def same_bits(a, b):
-    return (np.ascontiguousarray(a).view(np.uint32) == np.ascontiguousarray(b).view(np.uint32)).all()
+    a = np.ascontiguousarray(a).reshape(-1).view(np.uint8)
+    b = np.ascontiguousarray(b).reshape(-1).view(np.uint8)
+    return a.size == b.size and bool((a == b).all())

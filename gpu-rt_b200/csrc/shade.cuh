@@ -1,0 +1,720 @@
+/*
+ * shade.cuh — device-side shading library of the wavefront integrator: everything rt.rgen does
+ * between two traceRayEXT calls (src/shaders/rt/rt.rgen:62-549, rtcommon.glsl:99-369,
+ * restir.glsl:2-35), as __device__ functions over the flat scene arrays.
+ *
+ * fp32 contract N8: component-wise single-rounded ops in GLSL source order, fma only
+ * inside dot3 / cross3 / mat*vec, normalize(v) = v / sqrt(dot3(v,v)), sin/cos/pow from
+ * gpurt_detmath.h; compiled with -fmad=false.  Shadow / light rays inside an integrator are traced
+ * inline with the same traverse8 core as the batch kernels.
+ */
+#pragma once
+#include "../../include/gpurt_detmath.h"
+#include "device.cuh"
+#include "traverse.cuh"
+
+namespace gpurt {
+
+#define SH_D __device__ __forceinline__
+
+constexpr float kPiGlsl = 3.141592f;       /* rtcommon.glsl:6 */
+constexpr float kLargeDist = 10000000.0f;  /* rtcommon.glsl:7 */
+constexpr float kEps = 0.00001f;           /* rtcommon.glsl:8 */
+
+SH_D F3 f3s(float s) { return F3{s, s, s}; }
+SH_D F3 operator-(F3 a) { return F3{-a.x, -a.y, -a.z}; }
+SH_D F3 operator*(F3 a, F3 b) { return F3{a.x * b.x, a.y * b.y, a.z * b.z}; }
+SH_D F3 operator*(float s, F3 a) { return F3{s * a.x, s * a.y, s * a.z}; }
+SH_D F3 operator/(F3 a, float s) { return F3{a.x / s, a.y / s, a.z / s}; }
+SH_D F3 operator/(F3 a, F3 b) { return F3{a.x / b.x, a.y / b.y, a.z / b.z}; }
+SH_D float length3(F3 a) { return sqrtf(dot3(a, a)); }
+SH_D F3 normalize3(F3 a) { return a / length3(a); }
+SH_D F3 reflect3(F3 I, F3 N) { return I - (2.0f * dot3(N, I)) * N; }
+SH_D F3 mix3(F3 a, F3 b, float t) { return a * (1.0f - t) + b * t; }
+SH_D bool any_gt0(F3 a) { return a.x > 0 || a.y > 0 || a.z > 0; }
+
+struct F4 {
+    float x, y, z, w;
+};
+/* column-major mat4 * vec4 */
+SH_D F4 mul4(const float* m, float x, float y, float z, float w) {
+    F4 r;
+    r.x = fmaf(m[0], x, fmaf(m[4], y, fmaf(m[8], z, m[12] * w)));
+    r.y = fmaf(m[1], x, fmaf(m[5], y, fmaf(m[9], z, m[13] * w)));
+    r.z = fmaf(m[2], x, fmaf(m[6], y, fmaf(m[10], z, m[14] * w)));
+    r.w = fmaf(m[3], x, fmaf(m[7], y, fmaf(m[11], z, m[15] * w)));
+    return r;
+}
+SH_D F3 xform_point(const float* m, F3 p) {
+    return F3{fmaf(m[0], p.x, fmaf(m[4], p.y, fmaf(m[8], p.z, m[12]))),
+              fmaf(m[1], p.x, fmaf(m[5], p.y, fmaf(m[9], p.z, m[13]))),
+              fmaf(m[2], p.x, fmaf(m[6], p.y, fmaf(m[10], p.z, m[14])))};
+}
+SH_D F3 xform_dir(const float* m, F3 p) {
+    return F3{fmaf(m[0], p.x, fmaf(m[4], p.y, m[8] * p.z)), fmaf(m[1], p.x, fmaf(m[5], p.y, m[9] * p.z)),
+              fmaf(m[2], p.x, fmaf(m[6], p.y, m[10] * p.z))};
+}
+
+/* push constants + UBO of one frame (rt.h:85-117) */
+struct FrameParams {
+    GpurtConstants c;
+    GpurtCamera cam;
+    uint32_t W, H, seed_val;
+};
+
+struct Reservoir { /* restir.glsl:2-9; stored as 3 float4: pos|w_sum, normal|w, emissive|n_seen */
+    F3 pos, normal, emissive;
+    float w_sum, w;
+    uint32_t n_seen;
+};
+struct TraceInfo {
+    F3 o, d, acc;
+    uint32_t depth;
+    F3 throughput;
+    float mis;
+};
+struct Payload {
+    F3 bary;
+    uint32_t obj_id, prim_id;
+    bool hit;
+};
+struct HitInfo {
+    F3 pos, normal, tangent;
+    float tc[2];
+};
+struct MatInfo {
+    F3 albedo, emissive, tanspaceNormal;
+    float roughness;
+    bool use_tanspace;
+};
+struct ShadeInfo {
+    F3 wo, T, B, N;
+};
+struct LightSample {
+    F3 pos, normal, emissive;
+    float pdf;
+};
+
+__constant__ float c_srgb_lut[256];
+
+/* everything a shading thread can see */
+struct ShadeCtx {
+    DeviceScene S;
+    const float4* nodes;
+    const float4* tris;
+    unsigned n_nodes;
+    const float4* prev_res;  /* previous frame reservoirs */
+    const float4* ppos;      /* previous frame G-buffers */
+    const float4* pnorm;
+    const float4* palb;
+    unsigned long long* ray_counts; /* [0] closest, [1] any */
+};
+
+struct Shader {
+    const ShadeCtx& X;
+    const FrameParams& P;
+    uint32_t seed;
+    Reservoir prev_res;
+    unsigned n_closest, n_any;
+
+    SH_D Shader(const ShadeCtx& x, const FrameParams& p) : X(x), P(p), seed(0), n_closest(0), n_any(0) {}
+
+    /* rtcommon.glsl:111-124 */
+    SH_D uint32_t lcg() {
+        seed = 1664525u * seed + 1013904223u;
+        return seed & 0x00FFFFFFu;
+    }
+    SH_D float randf() { return (float)lcg() / (float)0x01000000; }
+    SH_D uint32_t randu(uint32_t a, uint32_t b) { return lcg() % (b - a) + a; }
+
+    SH_D const float* model(uint32_t o) const { return reinterpret_cast<const float*>(X.S.descs + o); }
+    SH_D const float* modelIT(uint32_t o) const { return reinterpret_cast<const float*>(X.S.descs + o) + 16; }
+    SH_D F3 desc_vec(uint32_t o, int word) const {
+        const float* f = reinterpret_cast<const float*>(X.S.descs + o) + word;
+        return F3{f[0], f[1], f[2]};
+    }
+    SH_D int desc_int(uint32_t o, int word) const {
+        return reinterpret_cast<const int*>(X.S.descs + o)[word];
+    }
+    SH_D const float* vertex(uint32_t obj, uint32_t i) const {
+        return reinterpret_cast<const float*>(X.S.verts + (X.S.vert_off[obj] + i));
+    }
+    SH_D void tri_indices(uint32_t obj, uint32_t prim, uint32_t ind[3]) const {
+        const uint32_t* p = X.S.idx + 3ull * (X.S.tri_off[obj] + prim);
+        ind[0] = p[0], ind[1] = p[1], ind[2] = p[2];
+    }
+    SH_D void payload_from_hit(float u, float v, uint32_t gid, Payload& pl) const {
+        uint32_t a = 0, b = X.S.n_objs;
+        while(b - a > 1) {
+            uint32_t m = (a + b) >> 1;
+            if(X.S.tri_off[m] <= gid) a = m; else b = m;
+        }
+        pl.hit = true;
+        pl.bary = F3{1.0f - u - v, u, v}; /* rt.rchit:13 */
+        pl.obj_id = a;
+        pl.prim_id = gid - X.S.tri_off[a];
+    }
+
+    /* texture(): R8G8B8A8_SRGB, linear, REPEAT, one mip (rt.cpp:439-446, vulkan.cpp:515-537) */
+    SH_D F3 texture(int t, const float tc[2]) const {
+        uint4 info = X.S.tex_info[t];
+        int w = (int)info.y, h = (int)info.z;
+        const uint8_t* base = X.S.texels + 4ull * info.x;
+        float x = tc[0] * (float)w - 0.5f, y = tc[1] * (float)h - 0.5f;
+        float fx0 = floorf(x), fy0 = floorf(y);
+        float ax = x - fx0, ay = y - fy0;
+        int x0 = (int)fx0, y0 = (int)fy0;
+        int xa = x0 % w, xb = (x0 + 1) % w, ya = y0 % h, yb = (y0 + 1) % h;
+        xa = xa < 0 ? xa + w : xa, xb = xb < 0 ? xb + w : xb, ya = ya < 0 ? ya + h : ya, yb = yb < 0 ? yb + h : yb;
+        auto tex = [&](int xx, int yy) {
+            const uint8_t* p = base + 4ull * ((size_t)yy * w + xx);
+            return F3{c_srgb_lut[p[0]], c_srgb_lut[p[1]], c_srgb_lut[p[2]]};
+        };
+        F3 top = tex(xa, ya) * (1.0f - ax) + tex(xb, ya) * ax;
+        F3 bot = tex(xa, yb) * (1.0f - ax) + tex(xb, yb) * ax;
+        return top * (1.0f - ay) + bot * ay;
+    }
+    /* NEAREST fetch of a previous-frame G-buffer (rt.cpp:449-450) */
+    SH_D F3 gbuf_fetch(const float4* img, float u, float v) const {
+        int W = (int)P.W, H = (int)P.H;
+        int x = (int)floorf(u * (float)W), y = (int)floorf(v * (float)H);
+        x = ((x % W) + W) % W, y = ((y % H) + H) % H;
+        float4 p = img[(size_t)y * W + x];
+        return F3{p.x, p.y, p.z};
+    }
+
+    /* traceRayEXT closest, inline (rt.rgen:257-270) */
+    SH_D void trace_ray(F3 o, F3 d, Payload& pl) {
+        HitRec h;
+        h.gid = kNoHit;
+        n_closest++;
+        if(X.n_nodes && traverse8<false, false>(X.nodes, X.tris, o, d, kEps, kLargeDist, h, nullptr))
+            payload_from_hit(h.u, h.v, h.gid, pl);
+        else
+            pl.hit = false;
+    }
+    /* rt.rgen:272-291 */
+    SH_D bool visibility(F3 a, F3 b) {
+        F3 dir = b - a;
+        float d = length3(dir);
+        HitRec h;
+        n_any++;
+        return X.n_nodes && traverse8<true, false>(X.nodes, X.tris, a, dir / d, kEps, d - kEps, h, nullptr);
+    }
+
+    /* rt.rgen:62-95 */
+    SH_D HitInfo hit_info(const Payload& pl) const {
+        uint32_t obj = pl.obj_id;
+        const float *mIT = modelIT(obj), *m = model(obj);
+        F3 bary = pl.bary;
+        uint32_t ind[3];
+        tri_indices(obj, pl.prim_id, ind);
+        const float *v0 = vertex(obj, ind[0]), *v1 = vertex(obj, ind[1]), *v2 = vertex(obj, ind[2]);
+        HitInfo hit;
+        F3 n = F3{v0[4], v0[5], v0[6]} * bary.x + F3{v1[4], v1[5], v1[6]} * bary.y + F3{v2[4], v2[5], v2[6]} * bary.z;
+        hit.normal = normalize3(xform_dir(mIT, n));
+        F3 t0 = F3{v0[8], v0[9], v0[10]} * v0[11], t1 = F3{v1[8], v1[9], v1[10]} * v1[11],
+           t2 = F3{v2[8], v2[9], v2[10]} * v2[11];
+        F3 t = t0 * bary.x + t1 * bary.y + t2 * bary.z;
+        hit.tangent = normalize3(xform_dir(mIT, t));
+        F3 p = F3{v0[0], v0[1], v0[2]} * bary.x + F3{v1[0], v1[1], v1[2]} * bary.y + F3{v2[0], v2[1], v2[2]} * bary.z;
+        hit.pos = xform_point(m, p);
+        hit.tc[0] = v0[3] * bary.x + v1[3] * bary.y + v2[3] * bary.z;
+        hit.tc[1] = v0[7] * bary.x + v1[7] * bary.y + v2[7] * bary.z;
+        return hit;
+    }
+    /* rt.rgen:97-130; Scene_Desc words: albedo 32, emissive 36, metal_rough 40, textures 44..47 */
+    SH_D MatInfo mat_info(const Payload& pl, const HitInfo& hit) const {
+        uint32_t obj = pl.obj_id;
+        MatInfo mat;
+        int albedoIdx = desc_int(obj, 44);
+        mat.albedo = desc_vec(obj, 32);
+        if(albedoIdx >= 0) mat.albedo = texture(albedoIdx, hit.tc);
+        int emissiveIdx = desc_int(obj, 45);
+        mat.emissive = desc_vec(obj, 36);
+        if(emissiveIdx >= 0) mat.emissive = texture(emissiveIdx, hit.tc);
+        int mrIdx = desc_int(obj, 46);
+        F3 mr = desc_vec(obj, 40);
+        if(mrIdx >= 0) mr = texture(mrIdx, hit.tc);
+        mat.roughness = mr.y;
+        if(P.c.use_metalness == 1) mat.albedo = mix3(f3s(0.04f), mat.albedo, mr.x);
+        int nIdx = desc_int(obj, 47);
+        mat.use_tanspace = nIdx >= 0;
+        mat.tanspaceNormal = f3s(0.0f);
+        if(mat.use_tanspace) mat.tanspaceNormal = texture(nIdx, hit.tc) * 2.0f - f3s(1.0f);
+        return mat;
+    }
+    /* rtcommon.glsl:218-224 */
+    SH_D static void make_tanspace(F3 N, F3& Nt, F3& Nb) {
+        if(fabsf(N.x) > fabsf(N.y)) Nt = F3{N.z, 0.0f, -N.x} / sqrtf(N.x * N.x + N.z * N.z);
+        else Nt = F3{0.0f, -N.z, N.y} / sqrtf(N.y * N.y + N.z * N.z);
+        Nb = cross3(N, Nt);
+    }
+    /* rt.rgen:132-149 */
+    SH_D ShadeInfo shade_info(F3 wo, HitInfo hit, const MatInfo& mat) const {
+        ShadeInfo shade;
+        shade.wo = wo;
+        if(dot3(shade.wo, hit.normal) > 0) hit.normal = -hit.normal;
+        shade.T = hit.tangent;
+        shade.N = hit.normal;
+        if(mat.use_tanspace && P.c.use_normal_map == 1) {
+            shade.B = cross3(shade.N, shade.T);
+            F3 tn = mat.tanspaceNormal;
+            shade.N = normalize3(shade.T * tn.x + shade.B * tn.y + shade.N * tn.z);
+        }
+        make_tanspace(shade.N, shade.T, shade.B);
+        return shade;
+    }
+
+    /* rtcommon.glsl:160-179 */
+    SH_D F3 cospow_hemisphere(float exponent, F3 x, F3 y, F3 z) {
+        float phi = (2 * kPiGlsl) * randf();
+        float cosT = dm_pow(randf(), 1.0f / (exponent + 1.0f));
+        float sinT = sqrtf(1.0f - cosT * cosT);
+        F3 dir = F3{dm_cos(phi) * sinT, dm_sin(phi) * sinT, cosT};
+        return dir.x * x + dir.y * y + dir.z * z;
+    }
+    SH_D F3 triangle_sample() {
+        float u = sqrtf(randf());
+        float v = randf();
+        float a = u * (1 - v);
+        float b = u * v;
+        return F3{a, b, 1 - a - b};
+    }
+
+    /* rtcommon.glsl:255-369 */
+    SH_D float bp_pdf(const MatInfo& mat, const ShadeInfo& sh, F3 wi) const {
+        float oDn = dot3(-sh.wo, sh.N), iDn = dot3(wi, sh.N);
+        if(oDn <= 0 || iDn <= 0) return 0;
+        float ex = 1 / mat.roughness;
+        F3 Hh = normalize3(wi - sh.wo);
+        float cosine = fmaxf(dot3(Hh, sh.N), 0.0f);
+        float N_pdf = (ex + 1) / (2 * kPiGlsl) * dm_pow(cosine, ex);
+        return N_pdf / (4 * dot3(-sh.wo, Hh));
+    }
+    SH_D static F3 GGX_F(F3 r0, float iDn) {
+        float cos5 = dm_pow(1 - iDn, 5.0f);
+        return r0 + (f3s(1.0f) - r0) * cos5;
+    }
+    SH_D static float GGX_G(float oDn, float iDn, float a2) {
+        float sqr0 = sqrtf(a2 + (1 - a2) * iDn * iDn);
+        float sqr1 = sqrtf(a2 + (1 - a2) * oDn * oDn);
+        return 2 * oDn * iDn / (oDn * sqr0 + iDn * sqr1);
+    }
+    SH_D static float GGX_D(float nDh, float a2) {
+        float b = nDh * nDh * (a2 - 1) + 1;
+        return a2 / (kPiGlsl * b * b);
+    }
+    SH_D float GGX_pdf(const MatInfo& mat, const ShadeInfo& sh, F3 wi) const {
+        float oDn = dot3(-sh.wo, sh.N), iDn = dot3(wi, sh.N);
+        if(oDn <= 0 || iDn <= 0) return 0;
+        F3 Hh = normalize3(wi - sh.wo);
+        float nDh = fmaxf(dot3(Hh, sh.N), 0.0f);
+        float oDh = fmaxf(dot3(wi, Hh), 0.0f);
+        float a2 = mat.roughness * mat.roughness;
+        return GGX_D(nDh, a2) * nDh / (4 * oDh);
+    }
+    SH_D F3 GGX_eval(const MatInfo& mat, const ShadeInfo& sh, F3 wi) const {
+        float oDn = dot3(-sh.wo, sh.N), iDn = dot3(wi, sh.N);
+        if(oDn <= 0 || iDn <= 0) return f3s(0.0f);
+        F3 Hh = normalize3(wi - sh.wo);
+        float nDh = fmaxf(dot3(Hh, sh.N), 0.0f);
+        float a2 = mat.roughness * mat.roughness;
+        return GGX_F(mat.albedo, iDn) * GGX_D(nDh, a2) * GGX_G(oDn, iDn, a2) / (4 * oDn);
+    }
+    SH_D float MAT_pdf(const MatInfo& mat, const ShadeInfo& sh, F3 wi) const {
+        if(P.c.brdf == 0) return bp_pdf(mat, sh, wi);
+        if(P.c.brdf == 1) return GGX_pdf(mat, sh, wi);
+        return 0;
+    }
+    SH_D F3 MAT_eval(const MatInfo& mat, const ShadeInfo& sh, F3 wi) const {
+        if(P.c.brdf == 0) return mat.albedo * bp_pdf(mat, sh, wi);
+        if(P.c.brdf == 1) return GGX_eval(mat, sh, wi);
+        return f3s(0.0f);
+    }
+    SH_D bool MAT_sample(const MatInfo& mat, const ShadeInfo& sh, F3& wi) {
+        if(P.c.brdf == 0) {
+            float ex = 1 / mat.roughness;
+            F3 Hh = cospow_hemisphere(ex, sh.T, sh.B, sh.N);
+            wi = reflect3(sh.wo, Hh);
+            return dot3(wi, sh.N) > 0;
+        }
+        if(P.c.brdf == 1) {
+            float a2 = mat.roughness * mat.roughness;
+            float Xi_x = randf(), Xi_y = randf();
+            float phi = (2.0f * kPiGlsl) * Xi_x;
+            float cosTheta = sqrtf((1.0f - Xi_y) / (1.0f + (a2 - 1.0f) * Xi_y));
+            float sinTheta = sqrtf(1.0f - cosTheta * cosTheta);
+            F3 dir = F3{dm_cos(phi) * sinTheta, dm_sin(phi) * sinTheta, cosTheta};
+            F3 Hh = sh.T * dir.x + sh.B * dir.y + sh.N * dir.z;
+            wi = reflect3(sh.wo, Hh);
+            return dot3(wi, sh.N) > 0;
+        }
+        wi = f3s(0.0f);
+        return false;
+    }
+
+    /* ---- lights ---- */
+    /* rt.rgen:151-198 (Q4: no lights -> pdf 0, nothing drawn; Q5 texcoord quirk kept) */
+    SH_D LightSample light_sample(F3 p) {
+        LightSample s;
+        if(P.c.n_lights <= 0) {
+            s.pos = s.normal = s.emissive = f3s(0.0f);
+            s.pdf = 0;
+            return s;
+        }
+        uint32_t l_idx = randu(0, (uint32_t)P.c.n_lights);
+        uint32_t o_idx = X.S.lights[l_idx].index, n_tris = X.S.lights[l_idx].n_triangles;
+        uint32_t t_idx = randu(0, n_tris);
+        uint32_t ind[3];
+        tri_indices(o_idx, t_idx, ind);
+        const float *v0 = vertex(o_idx, ind[0]), *v1 = vertex(o_idx, ind[1]), *v2 = vertex(o_idx, ind[2]);
+        const float* m = model(o_idx);
+        F3 _v0 = xform_point(m, F3{v0[0], v0[1], v0[2]}), _v1 = xform_point(m, F3{v1[0], v1[1], v1[2]}),
+           _v2 = xform_point(m, F3{v2[0], v2[1], v2[2]});
+        F3 bary = triangle_sample();
+        float tc[2] = {v0[3] * bary.x + v1[3] * bary.y + v2[3] * bary.z, v1[7] * bary.x + v1[7] * bary.y + v1[7] * bary.z};
+        s.pos = _v0 * bary.x + _v1 * bary.y + _v2 * bary.z;
+        int emissiveIdx = desc_int(o_idx, 45);
+        s.emissive = desc_vec(o_idx, 36);
+        if(emissiveIdx >= 0) s.emissive = texture(emissiveIdx, tc);
+        F3 Narea = cross3(_v1 - _v0, _v2 - _v0);
+        float a = 2 / length3(Narea);
+        F3 dist = s.pos - p;
+        F3 N = normalize3(Narea);
+        F3 d = normalize3(dist);
+        float g = dot3(dist, dist) / fabsf(dot3(N, d));
+        s.normal = N;
+        s.pdf = a * g / (float)(n_tris * (uint32_t)P.c.n_lights);
+        return s;
+    }
+    /* rt.rgen:200-220 */
+    SH_D F3 light_sample_dir(F3 p) {
+        uint32_t l_idx = randu(0, (uint32_t)P.c.n_lights);
+        uint32_t o_idx = X.S.lights[l_idx].index, n_tris = X.S.lights[l_idx].n_triangles;
+        uint32_t t_idx = randu(0, n_tris);
+        uint32_t ind[3];
+        tri_indices(o_idx, t_idx, ind);
+        const float *v0 = vertex(o_idx, ind[0]), *v1 = vertex(o_idx, ind[1]), *v2 = vertex(o_idx, ind[2]);
+        F3 bary = triangle_sample();
+        F3 point = F3{v0[0], v0[1], v0[2]} * bary.x + F3{v1[0], v1[1], v1[2]} * bary.y + F3{v2[0], v2[1], v2[2]} * bary.z;
+        point = xform_point(model(o_idx), point);
+        return normalize3(point - p);
+    }
+    /* rtcommon.glsl:181-214 */
+    SH_D static bool triangle_hit(F3 o, F3 d, F3 pa, F3 pb, F3 pc, F3& hitp) {
+        F3 v1 = pb - pa, v2 = pc - pa;
+        F3 p = cross3(d, v2);
+        float det = dot3(v1, p);
+        if(fabsf(det) < kEps) return false;
+        float invDet = 1 / det;
+        F3 s = o - pa;
+        float u = dot3(s, p) * invDet;
+        if(u < 0 || u > 1) return false;
+        F3 q = cross3(s, v1);
+        float v = dot3(d, q) * invDet;
+        if(v < 0 || u + v > 1) return false;
+        float t = dot3(v2, q) * invDet;
+        hitp = o + t * d;
+        return t >= 0;
+    }
+    SH_D static float triangle_pdf(F3 o, F3 d, F3 v0, F3 v1, F3 v2) {
+        F3 hitp;
+        if(triangle_hit(o, d, v0, v1, v2, hitp)) {
+            float a = 2 / length3(cross3(v1 - v0, v2 - v0));
+            F3 dist = hitp - o;
+            F3 N = normalize3(cross3(v1 - v0, v2 - v0));
+            float g = dot3(dist, dist) / fabsf(dot3(N, d));
+            return a * g;
+        }
+        return 0;
+    }
+    /* rtcommon.glsl:242-251 */
+    SH_D static bool hit_bbox(F3 o, F3 d, F3 bmin, F3 bmax) {
+        F3 invD = f3s(1.0f) / d;
+        F3 t0 = (bmin - o) * invD, t1 = (bmax - o) * invD;
+        F3 tNear = F3{fminf(t0.x, t1.x), fminf(t0.y, t1.y), fminf(t0.z, t1.z)};
+        F3 tFar = F3{fmaxf(t0.x, t1.x), fmaxf(t0.y, t1.y), fmaxf(t0.z, t1.z)};
+        float tNearMax = fmaxf(fmaxf(tNear.x, tNear.y), fmaxf(tNear.z, 0.0f));
+        float tFarMin = fminf(fminf(tFar.x, tFar.y), tFar.z);
+        return tNearMax <= tFarMin;
+    }
+    /* rt.rgen:222-255: every triangle of every light whose bbox the ray hits */
+    SH_D float light_pdf(F3 p, F3 d) const {
+        if(P.c.n_lights <= 0) return 0;
+        float oacc = 0;
+        for(uint32_t l = 0; l < (uint32_t)P.c.n_lights; l++) {
+            float tacc = 0;
+            const SceneLight& L = X.S.lights[l];
+            uint32_t o_idx = L.index, n_tris = L.n_triangles;
+            if(!hit_bbox(p, d, F3{L.bmin[0], L.bmin[1], L.bmin[2]}, F3{L.bmax[0], L.bmax[1], L.bmax[2]})) continue;
+            const float* m = model(o_idx);
+            for(uint32_t t = 0; t < n_tris; t++) {
+                uint32_t ind[3];
+                tri_indices(o_idx, t, ind);
+                const float *a = vertex(o_idx, ind[0]), *b = vertex(o_idx, ind[1]), *cc = vertex(o_idx, ind[2]);
+                F3 v0 = xform_point(m, F3{a[0], a[1], a[2]}), v1 = xform_point(m, F3{b[0], b[1], b[2]}),
+                   v2 = xform_point(m, F3{cc[0], cc[1], cc[2]});
+                tacc += triangle_pdf(p, d, v0, v1, v2);
+            }
+            oacc += tacc / (float)n_tris;
+        }
+        return oacc / (float)P.c.n_lights;
+    }
+    /* rt.rgen:293-301 */
+    SH_D F3 direct_light(F3 o, F3 d) {
+        Payload pl;
+        trace_ray(o, d, pl);
+        if(!pl.hit) return F3{P.c.env_light[0], P.c.env_light[1], P.c.env_light[2]};
+        HitInfo hit = hit_info(pl);
+        MatInfo mat = mat_info(pl, hit);
+        return mat.emissive;
+    }
+    SH_D static float power_heuristic(float a, float b) { return a * a / (a * a + b * b); }
+    SH_D static float luma(F3 rgb) { return 0.299f * rgb.x + 0.587f * rgb.y + 0.114f * rgb.z; }
+
+    /* ---- integrators ---- */
+    /* rt.rgen:303-353 */
+    SH_D void integrate_mis(TraceInfo& trace, const HitInfo& hit, const MatInfo& mat, const ShadeInfo& shade) {
+        if(any_gt0(mat.emissive)) {
+            trace.acc = trace.acc + trace.throughput * trace.mis * mat.emissive;
+            trace.depth = P.c.max_depth;
+            return;
+        }
+        trace.o = hit.pos;
+        if(mat.roughness == 0) {
+            trace.d = reflect3(shade.wo, shade.N);
+            trace.throughput = trace.throughput * mat.albedo;
+            trace.mis = 1;
+        } else {
+            if(P.c.n_lights > 0) {
+                F3 wi_light = light_sample_dir(hit.pos);
+                float light_pdf_l = light_pdf(hit.pos, wi_light);
+                if(light_pdf_l != 0) {
+                    float light_pdf_m = MAT_pdf(mat, shade, wi_light);
+                    F3 light_atten = MAT_eval(mat, shade, wi_light);
+                    F3 weight = light_atten / light_pdf_l * power_heuristic(light_pdf_l, light_pdf_m);
+                    trace.acc = trace.acc + trace.throughput * weight * direct_light(hit.pos, wi_light);
+                }
+            }
+            F3 wi_brdf;
+            if(!MAT_sample(mat, shade, wi_brdf)) {
+                trace.depth = P.c.max_depth;
+                return;
+            }
+            float brdf_pdf_m = MAT_pdf(mat, shade, wi_brdf);
+            if(brdf_pdf_m != 0) {
+                float brdf_pdf_l = light_pdf(hit.pos, wi_brdf);
+                F3 brdf_atten = MAT_eval(mat, shade, wi_brdf);
+                trace.throughput = trace.throughput * (brdf_atten / brdf_pdf_m);
+                trace.mis = power_heuristic(brdf_pdf_m, brdf_pdf_l);
+            } else {
+                trace.depth = P.c.max_depth;
+                return;
+            }
+            trace.d = wi_brdf;
+        }
+    }
+    /* rt.rgen:355-389 */
+    SH_D void integrate_mats(TraceInfo& trace, const HitInfo& hit, const MatInfo& mat, const ShadeInfo& shade) {
+        if(any_gt0(mat.emissive)) {
+            trace.acc = trace.acc + mat.emissive * trace.throughput;
+            trace.depth = P.c.max_depth;
+            return;
+        }
+        trace.o = hit.pos;
+        if(mat.roughness == 0) {
+            trace.d = reflect3(shade.wo, shade.N);
+            trace.throughput = trace.throughput * mat.albedo;
+        } else {
+            F3 wi;
+            if(!MAT_sample(mat, shade, wi)) {
+                trace.depth = P.c.max_depth;
+                return;
+            }
+            float pdf = MAT_pdf(mat, shade, wi);
+            F3 atten = MAT_eval(mat, shade, wi);
+            if(pdf != 0) trace.throughput = trace.throughput * (atten / pdf);
+            else {
+                trace.depth = P.c.max_depth;
+                return;
+            }
+            trace.d = wi;
+        }
+    }
+    /* rt.rgen:391-411 */
+    SH_D void integrate_direct(TraceInfo& trace, const HitInfo& hit, const MatInfo& mat, const ShadeInfo& shade) {
+        trace.depth = P.c.max_depth;
+        if(any_gt0(mat.emissive)) {
+            trace.acc = trace.acc + mat.emissive;
+            return;
+        }
+        if(mat.roughness != 0) {
+            LightSample light = light_sample(hit.pos);
+            F3 wi = normalize3(light.pos - hit.pos);
+            F3 light_atten = MAT_eval(mat, shade, wi);
+            if(light.pdf != 0) {
+                float shadow = visibility(hit.pos, light.pos) ? 0.0f : 1.0f;
+                trace.acc = trace.acc + light_atten / light.pdf * light.emissive * shadow;
+            }
+        }
+    }
+
+    /* restir.glsl:17-35 */
+    SH_D void res_update(Reservoir& res, float weight, F3 pos, F3 normal, F3 emissive) {
+        res.n_seen++;
+        res.w_sum += weight;
+        if(randf() < weight / res.w_sum) {
+            res.pos = pos;
+            res.normal = normal;
+            res.emissive = emissive;
+        }
+    }
+    SH_D static Reservoir res_new() {
+        Reservoir r;
+        r.pos = r.normal = r.emissive = F3{0.0f, 0.0f, 0.0f};
+        r.w_sum = 0, r.w = 0, r.n_seen = 0;
+        return r;
+    }
+    SH_D static Reservoir res_load(const float4* p) {
+        float4 a = p[0], b = p[1], c = p[2];
+        Reservoir r;
+        r.pos = F3{a.x, a.y, a.z}, r.w_sum = a.w;
+        r.normal = F3{b.x, b.y, b.z}, r.w = b.w;
+        r.emissive = F3{c.x, c.y, c.z}, r.n_seen = __float_as_uint(c.w);
+        return r;
+    }
+    SH_D static void res_store(float4* p, const Reservoir& r) {
+        p[0] = make_float4(r.pos.x, r.pos.y, r.pos.z, r.w_sum);
+        p[1] = make_float4(r.normal.x, r.normal.y, r.normal.z, r.w);
+        p[2] = make_float4(r.emissive.x, r.emissive.y, r.emissive.z, __uint_as_float(r.n_seen));
+    }
+    /* rt.rgen:415-433 */
+    SH_D float update_weight(Reservoir& res, const HitInfo& hit, const MatInfo& mat, const ShadeInfo& shade) const {
+        if(res.n_seen == 0) {
+            res.w = 0;
+            return 0;
+        }
+        F3 dir = res.pos - hit.pos;
+        F3 wi = normalize3(dir);
+        F3 light_atten = MAT_eval(mat, shade, wi);
+        float g = fabsf(dot3(res.normal, wi)) / dot3(dir, dir);
+        F3 contrib = g * light_atten * res.emissive;
+        float pHat = luma(contrib);
+        res.w = (1 / pHat) * (res.w_sum / (float)res.n_seen);
+        if(pHat == 0) res.w = 0;
+        return pHat;
+    }
+    /* rt.rgen:435-505 */
+    SH_D void reservoir_sample(TraceInfo& trace, const HitInfo& hit, const MatInfo& mat, const ShadeInfo& shade, bool first) {
+        Reservoir new_res = res_new();
+        if(P.c.n_lights > 0)
+            for(uint32_t i = 0; i < P.cam.new_samples; i++) {
+                LightSample light = light_sample(hit.pos);
+                F3 wi = normalize3(light.pos - hit.pos);
+                F3 light_atten = MAT_eval(mat, shade, wi);
+                F3 contrib = light_atten * light.emissive / light.pdf;
+                res_update(new_res, luma(contrib), light.pos, light.normal, light.emissive);
+            }
+        float new_pHat = update_weight(new_res, hit, mat, shade);
+        if(new_pHat != 0 && visibility(hit.pos, new_res.pos)) new_res.w = 0;
+        for(;;) {
+            if(first && P.c.use_temporal == 1) {
+                F4 pp = mul4(P.cam.prev_PV, hit.pos.x, hit.pos.y, hit.pos.z, 1.0f);
+                pp.x /= pp.w, pp.y /= pp.w, pp.z /= pp.w;
+                pp.x = (pp.x + 1.0f) * 0.5f, pp.y = (pp.y + 1.0f) * 0.5f;
+                if(!((pp.x > 0 && pp.y > 0) && (pp.x < 1 && pp.y < 1))) break;
+                F3 old_pos = gbuf_fetch(X.ppos, pp.x, pp.y);
+                F3 old_norm = gbuf_fetch(X.pnorm, pp.x, pp.y);
+                F3 old_alb = gbuf_fetch(X.palb, pp.x, pp.y);
+                F3 posdiff = old_pos - hit.pos;
+                if(dot3(posdiff, posdiff) > 0.01f) break;
+                F3 albdiff = old_alb - mat.albedo;
+                if(dot3(albdiff, albdiff) > 0.01f) break;
+                if(dot3(old_norm, shade.N) < 0.5f) break;
+                int fx = (int)(pp.x * (float)P.W), fy = (int)(pp.y * (float)P.H);
+                prev_res = res_load(X.prev_res + 3ull * ((size_t)fy * P.W + fx));
+            }
+            Reservoir temporal_res = res_new();
+            res_update(temporal_res, new_pHat * new_res.w * (float)new_res.n_seen, new_res.pos, new_res.normal, new_res.emissive);
+            float old_pHat = update_weight(prev_res, hit, mat, shade);
+            uint32_t cap = P.cam.temporal_multiplier * new_res.n_seen;
+            prev_res.n_seen = cap < prev_res.n_seen ? cap : prev_res.n_seen;
+            res_update(temporal_res, old_pHat * prev_res.w * (float)prev_res.n_seen, prev_res.pos, prev_res.normal, prev_res.emissive);
+            temporal_res.n_seen = new_res.n_seen + prev_res.n_seen;
+            update_weight(temporal_res, hit, mat, shade);
+            new_res = temporal_res;
+            break;
+        }
+        if(new_res.w != 0) {
+            F3 dir = new_res.pos - hit.pos;
+            F3 wi = normalize3(dir);
+            F3 light_atten = MAT_eval(mat, shade, wi);
+            F3 contrib = light_atten * new_res.emissive;
+            float g = fabsf(dot3(new_res.normal, wi)) / dot3(dir, dir);
+            trace.acc = trace.acc + new_res.w * contrib * g;
+        }
+        prev_res = new_res;
+    }
+    /* rt.rgen:507-549 */
+    SH_D void integrate_restir(TraceInfo& trace, const HitInfo& hit, const MatInfo& mat, const ShadeInfo& shade, bool d_only, bool first) {
+        if(any_gt0(mat.emissive)) {
+            trace.acc = trace.acc + mat.emissive * trace.throughput * trace.mis;
+            trace.depth = P.c.max_depth;
+            return;
+        }
+        trace.o = hit.pos;
+        if(mat.roughness == 0) {
+            trace.d = reflect3(shade.wo, shade.N);
+            trace.throughput = trace.throughput * mat.albedo;
+            trace.mis = 1;
+        } else {
+            if(trace.depth == 0) reservoir_sample(trace, hit, mat, shade, first);
+            F3 wi_brdf;
+            if(!MAT_sample(mat, shade, wi_brdf)) {
+                trace.depth = P.c.max_depth;
+                return;
+            }
+            float brdf_pdf = MAT_pdf(mat, shade, wi_brdf);
+            if(brdf_pdf != 0) {
+                F3 brdf_atten = MAT_eval(mat, shade, wi_brdf);
+                trace.throughput = trace.throughput * (brdf_atten / brdf_pdf);
+                trace.mis = trace.depth == 0 ? 0.0f : 1.0f;
+            } else {
+                trace.depth = P.c.max_depth;
+                return;
+            }
+            trace.d = wi_brdf;
+        }
+        if(d_only) trace.depth = P.c.max_depth;
+    }
+
+    /* rt.rgen:551-565 */
+    SH_D F3 make_camera_ray(uint32_t s, uint32_t px, uint32_t py) {
+        float jx, jy;
+        if(P.c.qmc == 0) {
+            if(P.c.frame == 0) jx = jy = 0.5f;
+            else {
+                jx = randf();
+                jy = randf();
+            }
+        } else {
+            uint32_t i = s + (uint32_t)(P.c.samples * P.c.frame), N = (uint32_t)(P.c.samples * P.c.max_frame);
+            jx = (float)i / (float)N;
+            uint32_t bits = i; /* rtcommon.glsl:128-135 */
+            bits = (bits << 16u) | (bits >> 16u);
+            bits = ((bits & 0x55555555u) << 1u) | ((bits & 0xAAAAAAAAu) >> 1u);
+            bits = ((bits & 0x33333333u) << 2u) | ((bits & 0xCCCCCCCCu) >> 2u);
+            bits = ((bits & 0x0F0F0F0Fu) << 4u) | ((bits & 0xF0F0F0F0u) >> 4u);
+            bits = ((bits & 0x00FF00FFu) << 8u) | ((bits & 0xFF00FF00u) >> 8u);
+            jy = (float)bits * 2.3283064365386963e-10f;
+        }
+        float pcx = (float)px + jx, pcy = (float)py + jy;
+        float ux = pcx / (float)P.W, uy = pcy / (float)P.H;
+        F4 target = mul4(P.cam.iP, ux * 2.0f - 1.0f, uy * 2.0f - 1.0f, 0.0f, 1.0f);
+        F4 direction = mul4(P.cam.iV, target.x, target.y, target.z, 0.0f);
+        return normalize3(F3{direction.x, direction.y, direction.z});
+    }
+};
+
+} // namespace gpurt

@@ -88,8 +88,16 @@ SYMBOLS = [
     "gpurt_trace_closest_bvh2", "gpurt_trace_closest_stats", "gpurt_last_kernel_ms",
     "gpurt_pipe_params_default", "gpurt_pipe_create", "gpurt_pipe_destroy", "gpurt_pipe_reset_frame",
     "gpurt_pipe_render_frame", "gpurt_pipe_frame_index", "gpurt_pipe_read_image", "gpurt_pipe_read_gbuffer",
-    "gpurt_pipe_ray_counts", "gpurt_pipe_device_image", "gpurt_tonemap",
+    "gpurt_pipe_ray_counts", "gpurt_pipe_device_image", "gpurt_tonemap", "gpurt_pipe_last_uniforms",
+    "gpurt_pipe_read_reservoirs", "gpurt_pipe_bounce_rays",
 ]
+
+
+class Constants(C.Structure):
+    _fields_ = [("clear_col", C.c_float * 4), ("env_light", C.c_float * 4)] + [
+        (n, C.c_int32) for n in ("frame", "samples", "max_frame", "qmc", "max_depth", "use_normal_map",
+                                 "use_metalness", "use_temporal", "integrator", "brdf", "debug_view", "use_rr",
+                                 "n_lights", "n_objs")]
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
@@ -370,6 +378,35 @@ class RTPipe:
         c = (C.c_uint64 * 2)()
         _check(lib.gpurt_pipe_ray_counts(self.h, c))
         return int(c[0]), int(c[1])
+
+    def last_uniforms(self):
+        """(consts words, ubo words, seed word) of the last frame, as uint32 arrays"""
+        c, u, s = Constants(), Camera(), C.c_uint32()
+        _check(lib.gpurt_pipe_last_uniforms(self.h, C.byref(c), C.byref(u), C.byref(s)))
+        return (np.frombuffer(bytes(c), np.uint32).copy(), np.frombuffer(bytes(u), np.uint32).copy(), s.value)
+
+    def read_reservoirs(self):
+        out = np.zeros((self.h_px * self.w, 12), np.uint32)
+        _check(lib.gpurt_pipe_read_reservoirs(self.h, C.c_void_p(out.ctypes.data), MEM_HOST))
+        return out
+
+    def bounce_rays(self, bounce):
+        """torch view (n,8) of the device ray queue traced at `bounce` in the last frame"""
+        import torch
+        ptr, n = C.c_void_p(), C.c_uint32()
+        _check(lib.gpurt_pipe_bounce_rays(self.h, bounce, C.byref(ptr), C.byref(n)))
+        if n.value == 0:
+            return torch.empty((0, 8), dtype=torch.float32, device=f"cuda:{self.ctx.device}")
+
+        class _Arr:  # __cuda_array_interface__ wrapper, memory stays owned by the pipe
+            pass
+
+        a = _Arr()
+        a.__cuda_array_interface__ = {"shape": (n.value, 8), "typestr": "<f4", "data": (ptr.value, False), "version": 2}
+        return torch.as_tensor(a, device=f"cuda:{self.ctx.device}")
+
+    def time_ms(self):
+        return self.ctx.last_kernel_ms()
 
     def tonemap(self, op=0, exposure=1.0, gamma=2.2):
         out = np.zeros((self.h_px, self.w, 4), np.uint8)

@@ -239,8 +239,18 @@ int gpurt_pipe_read_image(gpurt_pipe* pipe, float* out_rgba, int mem);
 int gpurt_pipe_read_gbuffer(gpurt_pipe* pipe, int which, float* out_rgba, int mem);
 /* rays traced by the last frame: [0] closest-hit, [1] any-hit */
 int gpurt_pipe_ray_counts(const gpurt_pipe* pipe, uint64_t out_counts[2]);
-/* Device pointers of the frame's first-bounce ray buffers, for benchmarking the traversal alone. */
+/* Device pointer of rt_target (RGBA32F) for zero-copy consumers (e.g. an NCCL gather of tiles). */
 int gpurt_pipe_device_image(gpurt_pipe* pipe, void** out_dev_rgba);
+/* Push constants (rt.h:85-102) and UBO (rt.h:104-117) exactly as used by the last rendered frame,
+ * plus the per-frame seed word that replaces clockARB(). For parity tests / debugging. */
+int gpurt_pipe_last_uniforms(const gpurt_pipe* pipe, GpurtConstants* out_consts, GpurtCamera* out_ubo,
+                             uint32_t* out_seed_word);
+/* The reservoir buffer written by the last frame (rt.rgen:633-636): 12 words per pixel
+ * {pos.xyz, w_sum, normal.xyz, w, emissive.xyz, n_seen}. */
+int gpurt_pipe_read_reservoirs(gpurt_pipe* pipe, float* out_words, int mem);
+/* Device pointer + count of the ray queue (GpurtRay) traced at `bounce` in the last sample of the
+ * last frame; lets a benchmark re-trace exactly the rays the integrator produced. */
+int gpurt_pipe_bounce_rays(gpurt_pipe* pipe, uint32_t bounce, void** out_dev_rays, uint32_t* out_count);
 
 /* tonemap.frag:17-48 (exposure/Uncharted2 + gamma) -> RGBA8, host or device output */
 int gpurt_tonemap(gpurt_pipe* pipe, int op, float exposure, float gamma, uint8_t* out_rgba8, int mem);

@@ -485,7 +485,7 @@ static void bvh_trace(const orc_bvh* B, const float* rays, uint64_t n, uint32_t*
             int32_t node;
             float tn;
         };
-        std::vector<Ent> stack(256);
+        static thread_local std::vector<Ent> stack(256);
         for(uint64_t i = b; i < e; i++) {
             const float* r = rays + 8 * i;
             V3 o{r[0], r[1], r[2]}, d{r[4], r[5], r[6]};
@@ -534,6 +534,17 @@ void orc_bvh_closest_hit(const orc_bvh* B, const float* rays, uint64_t n, uint32
 }
 void orc_bvh_any_hit(const orc_bvh* B, const float* rays, uint64_t n, uint8_t* occ, int th) {
     bvh_trace<true>(B, rays, n, nullptr, occ, th);
+}
+
+/* single-ray versions for the CPU integrator (oracle_render.cpp); hit4 = t,u,v,gid */
+int orc_bvh_trace_one(const orc_bvh* B, const float* ray8, uint32_t* hit4) {
+    bvh_trace<false>(B, ray8, 1, hit4, nullptr, 1);
+    return hit4[3] != NONE;
+}
+int orc_bvh_occluded_one(const orc_bvh* B, const float* ray8) {
+    uint8_t o = 0;
+    bvh_trace<true>(B, ray8, 1, nullptr, &o, 1);
+    return o;
 }
 
 static inline float box_d2(const Box& b, V3 p) {

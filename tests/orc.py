@@ -159,3 +159,94 @@ def gen_random_points(n, seed, box6, frac=0.25, r2=np.inf):
     q = np.empty((n, 4), np.float32)
     lib.orc_gen_random_points(n, seed, np.ascontiguousarray(box6, np.float32), frac, r2, q)
     return q
+
+
+# ---- integrator oracle (oracle_render.cpp) ---------------------------------------------------
+_vp = C.c_void_p
+lib.orc_scene_create.restype = _vp
+lib.orc_scene_create.argtypes = [C.c_uint32, _vp, _vp, _vp, _vp, _vp, C.c_uint32, _vp, C.c_uint32, _vp, _vp, _vp]
+lib.orc_scene_free.argtypes = [_vp]
+lib.orc_render_frame.restype = None
+lib.orc_render_frame.argtypes = [_vp, _vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32, _vp, _vp, _vp, _vp, _vp, _vp,
+                                 _vp, _vp, _vp, _vp, C.c_int]
+lib.orc_camera_ray.restype = None
+lib.orc_camera_ray.argtypes = [_vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                               C.POINTER(C.c_uint32), _f32p, _f32p]
+lib.orc_mat_pdf.restype = C.c_float
+lib.orc_mat_pdf.argtypes = [C.c_int, C.c_float, _f32p, _f32p, _f32p]
+lib.orc_mat_eval.restype = None
+lib.orc_mat_eval.argtypes = [C.c_int, _f32p, C.c_float, _f32p, _f32p, _f32p, _f32p]
+lib.orc_tonemap.restype = None
+lib.orc_tonemap.argtypes = [_f32p, C.c_uint64, C.c_int, C.c_float, C.c_float, _u8p]
+
+
+def _p(a):
+    return C.c_void_p(a.ctypes.data)
+
+
+class RenderScene:
+    """Oracle-side scene built from the packed arrays a gpurt.Scene exposes (host-only calls)."""
+
+    def __init__(self, gscene, textures=()):
+        descs = gscene.descs()
+        self.n_objs = len(descs)
+        self.descs = np.frombuffer(b"".join(bytes(d) for d in descs), np.uint32).copy() if descs else np.zeros(52, np.uint32)
+        self.tri_off = gscene.tri_offsets().astype(np.uint32)
+        objs = [gscene.object(i) for i in range(self.n_objs)]
+        self.vert_off = np.concatenate([[0], np.cumsum([o[0].shape[0] for o in objs])]).astype(np.uint32)
+        self.verts = np.concatenate([o[0] for o in objs]).astype(np.float32) if objs else np.zeros((1, 12), np.float32)
+        self.idx = np.concatenate([o[1] for o in objs]).astype(np.uint32) if objs else np.zeros(3, np.uint32)
+        lights = gscene.lights()
+        self.n_lights = len(lights)
+        self.lights = np.frombuffer(b"".join(bytes(l) for l in lights), np.uint32).copy() if lights else np.zeros(12, np.uint32)
+        info, tex = [], []
+        off = 0
+        for t in textures:
+            t = np.ascontiguousarray(t, np.uint8)
+            info.append([off, t.shape[1], t.shape[0], 0])
+            tex.append(t.reshape(-1))
+            off += t.shape[0] * t.shape[1]
+        self.tex_info = np.array(info, np.uint32).reshape(-1) if info else np.zeros(4, np.uint32)
+        self.texels = np.concatenate(tex) if tex else np.zeros(4, np.uint8)
+        self.tris = np.concatenate([flatten(objs[i][0], objs[i][1], np.array(descs[i].model, np.float32))
+                                    for i in range(self.n_objs)]) if objs else np.zeros((0, 9), np.float32)
+        self.bvh = Bvh(self.tris)
+        self.h = lib.orc_scene_create(self.n_objs, _p(self.descs), _p(self.tri_off), _p(self.vert_off), _p(self.verts),
+                                      _p(self.idx), self.n_lights, _p(self.lights), len(info), _p(self.tex_info),
+                                      _p(self.texels), self.bvh.h)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib.orc_scene_free(self.h)
+            self.h = None
+
+
+class FrameState:
+    """rt_target, ping-pong reservoirs and G-buffers (rt.cpp:178-220), oracle side"""
+
+    def __init__(self, w, h):
+        self.w, self.h = w, h
+        self.image = np.zeros((h, w, 4), np.float32)
+        self.res = [np.zeros((h * w, 12), np.uint32) for _ in range(2)]
+        self.gb = [[np.zeros((h, w, 4), np.float32) for _ in range(3)] for _ in range(2)]
+        self.parity = 0
+
+
+def render_frame(rs, st, consts_words, camera_words, seed, threads=0):
+    """one rt.rgen dispatch; consts/camera are the exact words the product used for the frame"""
+    cur, prev = st.parity, st.parity ^ 1
+    counts = np.zeros(2, np.uint64)
+    consts_words = np.ascontiguousarray(consts_words, np.uint32)
+    camera_words = np.ascontiguousarray(camera_words, np.uint32)
+    lib.orc_render_frame(rs.h, _p(consts_words), _p(camera_words), st.w, st.h, seed, _p(st.image), _p(st.res[prev]),
+                         _p(st.res[cur]), _p(st.gb[prev][0]), _p(st.gb[prev][1]), _p(st.gb[prev][2]),
+                         _p(st.gb[cur][0]), _p(st.gb[cur][1]), _p(st.gb[cur][2]), _p(counts), threads)
+    st.parity ^= 1
+    return counts
+
+
+def tonemap(rgba, op=1, exposure=1.0, gamma=2.2):
+    rgba = np.ascontiguousarray(rgba, np.float32)
+    out = np.zeros(rgba.shape, np.uint8)
+    lib.orc_tonemap(rgba.reshape(-1), rgba.size // 4, op, exposure, gamma, out.reshape(-1))
+    return out

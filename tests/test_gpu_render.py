@@ -1,0 +1,181 @@
+"""Integrator parity: the wavefront CUDA integrator (through the C ABI) vs the CPU restatement of
+rt.rgen, frame by frame, at equal seed and spp.
+
+The oracle is fed the exact push constants / UBO words the product used for each frame
+(gpurt_pipe_last_uniforms), so this checks the device code; the host-side frame logic
+(RTPipe::update_uniforms / trace) is checked separately below.
+
+Stated tolerance: images must agree to per-pixel RMSE <= 1e-6 relative to the mean radiance and at
+most 1e-4 of the pixels may differ at all.  (With the shared deterministic sin/cos/pow and the fp32
+contract N8 the expectation is bit-exact; the tolerance only leaves room for fp ties in the
+traversal)
+"""
+import numpy as np
+import pytest
+
+from scenes import load_scene
+
+pytestmark = pytest.mark.gpu
+
+MAX_DIFF_FRAC = 1e-4
+MAX_REL_RMSE = 1e-6
+
+
+def _compare(name, got, ref):
+    got, ref = np.asarray(got, np.float32), np.asarray(ref, np.float32)
+    same = (got.view(np.uint32) == ref.view(np.uint32)) | (np.isnan(got) & np.isnan(ref))
+    diff_px = (~same.reshape(-1, got.shape[-1]).all(axis=1)).mean()
+    d = np.nan_to_num(got.astype(np.float64) - ref.astype(np.float64))
+    rmse = np.sqrt((d ** 2).mean()) / max(1e-12, np.abs(np.nan_to_num(ref)).mean())
+    assert diff_px <= MAX_DIFF_FRAC and rmse <= MAX_REL_RMSE, f"{name}: {diff_px:.2e} of pixels differ, rel RMSE {rmse:.2e}"
+    return diff_px
+
+
+def _run(gpurt, orc, ctx, scene_name, w, h, frames, cam=None, textures=(), scene=None, **params):
+    scene = scene or load_scene(gpurt, ctx, scene_name)
+    accel = gpurt.Accel(scene)
+    pipe = gpurt.RTPipe(scene, accel)
+    rs = orc.RenderScene(scene, textures)
+    st = orc.FrameState(w, h)
+    prm = gpurt.pipe_params(**params)
+    cam = cam or gpurt.camera(0, w, h)
+    worst = 0.0
+    for f in range(frames):
+        assert pipe.render_frame(prm, cam, w, h) == 0
+        consts, ubo, seed_word = pipe.last_uniforms()
+        # frame counter: 0, 0, 1, 2, ... (the second call resets: old_cam was never assigned, rt.cpp:132-135)
+        assert consts[8] == max(0, f - 1)
+        counts = orc.render_frame(rs, st, consts, ubo, seed_word ^ int(consts[8]))  # oracle xors the frame itself
+        worst = max(worst, _compare(f"{scene_name} frame {f} image", pipe.read_image(), st.image))
+        for g in range(3):
+            _compare(f"{scene_name} frame {f} gbuffer {g}", pipe.read_gbuffer(g), st.gb[st.parity ^ 1][g])
+        if params.get("integrator", 0) in (3, 4):
+            _compare(f"{scene_name} frame {f} reservoirs", pipe.read_reservoirs().view(np.float32),
+                     st.res[st.parity ^ 1].view(np.float32))
+        assert pipe.ray_counts() == (int(counts[0]), int(counts[1])), "ray counts differ from the oracle"
+    img = pipe.read_image()
+    assert np.isfinite(img[..., :3]).mean() > 0.999
+    pipe.close(), accel.close()
+    return img
+
+
+@pytest.mark.parametrize("integrator", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("brdf", [0, 1])
+def test_cbox_all_integrators(gpurt, orc, ctx, integrator, brdf):
+    img = _run(gpurt, orc, ctx, "cbox", 192, 108, 3, integrator=integrator, brdf=brdf, samples_per_frame=2,
+               max_depth=4, seed=1234 + integrator)
+    assert img[..., :3].mean() > 0.01
+
+
+def test_mis_test_scene_mis_and_restir(gpurt, orc, ctx):
+    # scene spans x[-0.14,1.10] y[0,1.16] z[-1,1]
+    cam = gpurt.camera(1, 160, 90, (0.5, 0.6, 2.6), (0.5, 0.45, 0.0), 50.0)
+    _run(gpurt, orc, ctx, "mis_test", 160, 90, 2, cam=cam, integrator=2, brdf=1, samples_per_frame=1, max_depth=4, seed=7)
+    _run(gpurt, orc, ctx, "mis_test", 160, 90, 8, cam=cam, integrator=3, brdf=0, samples_per_frame=1, max_depth=4,
+         res_samples=4, use_temporal=1, temporal_scale=16, seed=8)
+    _run(gpurt, orc, ctx, "mis_test", 160, 90, 4, cam=cam, integrator=4, brdf=1, samples_per_frame=2, max_depth=4, seed=9)
+
+
+def test_sponza_standin_config2(gpurt, orc, ctx):
+    """BASELINE config 2 at reduced resolution: integrator 1, GGX, depth 2, 1 spp, env light, no RR"""
+    cam = gpurt.camera(1, 320, 180, (-1000.0, 200.0, 0.0), (0.0, 200.0, 0.0), 90.0)
+    _run(gpurt, orc, ctx, "sponza_standin", 320, 180, 2, cam=cam, integrator=1, brdf=1, samples_per_frame=1,
+         max_depth=2, use_rr=0, env_scale=1.0, seed=3)
+
+
+def test_options_qmc_metalness_rr_off_depth1(gpurt, orc, ctx):
+    _run(gpurt, orc, ctx, "cbox", 128, 72, 3, integrator=1, brdf=1, samples_per_frame=3, max_depth=5, use_qmc=1,
+         use_metalness=1, seed=11)
+    _run(gpurt, orc, ctx, "cbox", 128, 72, 2, integrator=0, brdf=0, samples_per_frame=1, max_depth=1, use_rr=0, seed=12)
+    _run(gpurt, orc, ctx, "cbox", 128, 72, 3, integrator=4, brdf=0, samples_per_frame=2, max_depth=3, debug_view=2, seed=13)
+    _run(gpurt, orc, ctx, "cbox", 128, 72, 2, integrator=3, brdf=1, samples_per_frame=2, max_depth=3, use_temporal=0, seed=14)
+
+
+def test_textured_scene(gpurt, orc, ctx):
+    """albedo / emissive / metal-rough / normal textures, sRGB decode, bilinear + repeat"""
+    rng = np.random.default_rng(5)
+    texs = [rng.integers(0, 256, (16, 16, 4), dtype=np.uint8), rng.integers(0, 256, (8, 32, 4), dtype=np.uint8),
+            rng.integers(64, 256, (4, 4, 4), dtype=np.uint8), rng.integers(100, 156, (32, 32, 4), dtype=np.uint8)]
+    texs[3][..., 2] = 250  # normals mostly +z
+    scene = gpurt.Scene(ctx)
+    for t in texs:
+        scene.add_texture(t)
+
+    def quad(z, size, mat, uvscale=3.0):
+        v = np.zeros((4, 12), np.float32)
+        v[:, 0:3] = [[-size, -size, z], [size, -size, z], [size, size, z], [-size, size, z]]
+        v[:, 3] = np.array([0, 1, 1, 0]) * uvscale - 0.7   # u (exercises REPEAT with negatives)
+        v[:, 7] = np.array([0, 0, 1, 1]) * uvscale - 0.3   # v
+        v[:, 4:7] = [0, 0, 1]
+        v[:, 8:12] = [1, 0, 0, 1]
+        scene.add_object(v, np.array([0, 1, 2, 0, 2, 3], np.uint32), None, mat)
+
+    m = gpurt.Material()
+    m.albedo[:] = (1, 1, 1)
+    m.albedo_tex, m.emissive_tex, m.metal_rough_tex, m.normal_tex = 0, -1, 2, 3
+    m.metal_rough[:] = (0.5, 0.5)
+    quad(0.0, 2.0, m)
+    e = gpurt.Material()
+    e.albedo[:] = (1, 1, 1)
+    e.emissive[:] = (4, 4, 4)
+    e.albedo_tex, e.emissive_tex, e.metal_rough_tex, e.normal_tex = -1, 1, -1, -1
+    e.metal_rough[:] = (0, 1)
+    quad(3.0, 0.8, e, uvscale=1.0)
+    cam = gpurt.camera(1, 128, 96, (1.5, 1.0, 2.5), (0.0, 0.0, 0.5), 70.0)
+    for integ in (0, 1, 2, 4):
+        _run(gpurt, orc, ctx, "textured", 128, 96, 2, cam=cam, textures=texs, scene=scene, integrator=integ, brdf=1,
+             samples_per_frame=2, max_depth=3, use_normal_map=1, use_metalness=1, seed=20 + integ)
+    scene.close()
+
+
+def test_rtpipe_frame_logic(gpurt, ctx):
+    """RTPipe::update_uniforms / trace host semantics (rt.cpp:121-138, :346-398)"""
+    scene = load_scene(gpurt, ctx, "cube")
+    accel = gpurt.Accel(scene)
+    pipe = gpurt.RTPipe(scene, accel)
+    w, h = 64, 48
+    prm = gpurt.pipe_params(max_frames=3, samples_per_frame=1, max_depth=2, integrator=1, env_scale=1.0)
+    cam = gpurt.camera(1, w, h, (3, 2, 4), (0, 0, 0), 60.0)
+    assert pipe.frame_index() == -1
+    assert pipe.render_frame(prm, cam, w, h) == 0 and pipe.frame_index() == 0
+    c, ubo, _ = pipe.last_uniforms()
+    ident = np.eye(4, dtype=np.float32).reshape(-1)
+    assert (ubo[64:80].view(np.float32) == ident).all(), "prev_PV is identity until old_cam is first assigned"
+    # second call: camera differs from old_cam (never assigned) -> reset_frame, frame 0 again (rt.cpp:132-135)
+    assert pipe.render_frame(prm, cam, w, h) == 0 and pipe.frame_index() == 0
+    assert pipe.render_frame(prm, cam, w, h) == 0 and pipe.frame_index() == 1
+    _, ubo, _ = pipe.last_uniforms()
+    P, V = np.array(cam.P, np.float64).reshape(4, 4).T, np.array(cam.V, np.float64).reshape(4, 4).T
+    assert np.allclose(ubo[64:80].view(np.float32).reshape(4, 4).T, P @ V, rtol=1e-5, atol=1e-5)
+    assert pipe.render_frame(prm, cam, w, h) == 0 and pipe.frame_index() == 2
+    assert pipe.render_frame(prm, cam, w, h) == 0 and pipe.frame_index() == 3
+    before = pipe.read_image().copy()
+    assert pipe.render_frame(prm, cam, w, h) == 1, "frame >= max_frames: trace() returns false, nothing rendered"
+    assert (pipe.read_image() == before).all()
+    cam2 = gpurt.camera(1, w, h, (3, 2.5, 4), (0, 0, 0), 60.0)
+    assert pipe.render_frame(prm, cam2, w, h) == 0 and pipe.frame_index() == 0, "camera change resets accumulation"
+    pipe.reset_frame()
+    assert pipe.frame_index() == -1
+    # progressive accumulation converges: mean of frames == running mix (rt.rgen:638-645)
+    prm2 = gpurt.pipe_params(max_frames=64, samples_per_frame=1, max_depth=2, integrator=1, env_scale=1.0)
+    pipe.render_frame(prm2, cam2, w, h)
+    imgs = []
+    for _ in range(4):
+        pipe.render_frame(prm2, cam2, w, h)
+        imgs.append(pipe.read_image().copy())
+    assert np.isfinite(imgs[-1]).all()
+    rgba8 = pipe.tonemap(1, 1.0, 2.2)
+    assert rgba8.shape == (h, w, 4) and rgba8[..., 3].min() == 255
+    pipe.close(), accel.close(), scene.close()
+
+
+def test_tonemap_matches_oracle(gpurt, orc, ctx):
+    scene = load_scene(gpurt, ctx, "cbox")
+    accel = gpurt.Accel(scene)
+    pipe = gpurt.RTPipe(scene, accel)
+    w, h = 96, 54
+    pipe.render_frame(gpurt.pipe_params(samples_per_frame=2, max_depth=3, integrator=0), gpurt.camera(0, w, h), w, h)
+    img = pipe.read_image()
+    for op, exposure, gamma in [(0, 1.0, 2.2), (1, 1.0, 2.2), (1, 2.5, 1.8), (2, 1.0, 1.0)]:
+        assert (pipe.tonemap(op, exposure, gamma) == orc.tonemap(img, op, exposure, gamma)).all(), (op, exposure, gamma)
+    pipe.close(), accel.close(), scene.close()

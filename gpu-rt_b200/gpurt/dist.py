@@ -1,0 +1,39 @@
+"""Data-parallel plumbing for the sharded workloads: rays, query points and image rows
+are independent, the scene + BVH are replicated on every GPU, and the only collective is the gather
+of result arrays / image tiles to rank 0.  torch.distributed is plumbing only (NCCL over NVLink on
+the GPU box, gloo in the CPU tests); all compute goes through libgpurt.
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n, rank, world):
+    """contiguous range [r*n/R, (r+1)*n/R) of rank r"""
+    return (n * rank) // world, (n * (rank + 1)) // world
+
+
+def row_bands(height, rank, world):
+    """interleaved 16-row bands of an image for load balance: list of (y0, y1)"""
+    band = 16
+    return [(y, min(height, y + band)) for i, y in enumerate(range(0, height, band)) if i % world == rank]
+
+
+def gather_to_rank0(local, counts=None):
+    """Gather variable-length first-dimension shards to rank 0 (returns the concatenation on rank 0,
+    None elsewhere).  Uses all_gather of the lengths + gather / point-to-point of the payload."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return local
+    world, rank = dist.get_world_size(), dist.get_rank()
+    n = torch.tensor([local.shape[0]], dtype=torch.int64, device=local.device)
+    ns = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(ns, n)
+    ns = [int(x.item()) for x in ns]
+    if rank == 0:
+        parts = [local] + [torch.empty((m,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device) for m in ns[1:]]
+        reqs = [dist.irecv(parts[r], src=r) for r in range(1, world) if ns[r]]
+        for q in reqs:
+            q.wait()
+        return torch.cat(parts)
+    if local.shape[0]:
+        dist.send(local.contiguous(), dst=0)
+    return None

@@ -1,0 +1,71 @@
+"""CPU replay of the product's host+device BVH8 code (collapse, node encoding, octant-ordered
+traversal, closest-point descent) against the oracle — catches logic errors without a GPU.
+tests/emu/libemu.so is test-only; the product never links it."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from conftest import MEDIA, ROOT
+from scenes import soup, world_tris
+
+
+@pytest.fixture(scope="module")
+def emu(built):
+    lib = C.CDLL(os.path.join(ROOT, "tests", "emu", "libemu.so"))
+    lib.emu_build.restype = C.c_void_p
+    return lib
+
+
+def _vp(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _check(emu, orc, tris, n=20000, box=None):
+    b = orc.Bvh(tris)
+    order = b.prim_order()
+    l, r, bx = b.bvh2()
+    h = C.c_void_p(emu.emu_build(_vp(tris), len(tris), _vp(order), _vp(l), _vp(r), _vp(bx), C.c_float(b.inflation())))
+    assert emu.emu_depth(h) < 60
+    box = b.scene_box() if box is None else box
+    rays = orc.gen_random_rays(n, 0xC0FFEE, box)
+    hits, occ, cnt = np.zeros((n, 4), np.uint32), np.zeros(n, np.uint8), np.zeros(4, np.uint64)
+    emu.emu_trace(h, _vp(rays), C.c_ulonglong(n), _vp(hits), _vp(occ), _vp(cnt))
+    assert (hits == b.closest_hit(rays).view(np.uint32).reshape(-1, 4)).all()
+    assert (occ == b.any_hit(rays)).all()
+    for r2 in (np.inf, 0.003):
+        q = orc.gen_random_points(n, 0xFACADE, box, r2=r2)
+        res = np.zeros((n, 8), np.uint32)
+        emu.emu_cpq(h, _vp(q), C.c_ulonglong(n), _vp(res))
+        assert (res == b.closest_point(q).view(np.uint32).reshape(-1, 8)).all()
+    nodes = emu.emu_n_nodes(h)
+    emu.emu_free(h)
+    return nodes, cnt[0] / n, cnt[1] / n
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 9, 100, 5000, 60000])
+def test_soups(emu, orc, n):
+    tris = soup(n, seed=n + 1)
+    if n >= 100:
+        tris[10:14] = tris[10]
+    _check(emu, orc, tris, 8000)
+
+
+@pytest.mark.parametrize("name", ["cube", "mis_test", "cbox"])
+def test_reference_scenes(emu, orc, gpurt, name):
+    s = gpurt.Scene(None)
+    s.load(os.path.join(MEDIA, {"cube": "cube.gltf", "mis_test": "mis_test/mis_test.gltf", "cbox": "cbox/cbox.gltf"}[name]))
+    tris = world_tris(orc, s)
+    nodes, npr, tpr = _check(emu, orc, tris, 20000)
+    assert nodes <= len(tris) // 2 + 2 and npr < 64
+
+
+def test_flat_grid_with_duplicate_layer(emu, orc):
+    g = []
+    for _ in range(2):
+        for i in range(20):
+            for j in range(20):
+                x0, x1, y0, y1 = i / 20, (i + 1) / 20, j / 20, (j + 1) / 20
+                g += [[x0, y0, 0.5, x1, y0, 0.5, x1, y1, 0.5], [x0, y0, 0.5, x1, y1, 0.5, x0, y1, 0.5]]
+    _check(emu, orc, np.array(g, np.float32), 20000, box=np.array([0, 0, 0, 1, 1, 1], np.float32))

@@ -1,0 +1,188 @@
+"""CPU tests of the host front end and the C ABI surface (no GPU needed)."""
+import base64
+import ctypes as C
+import hashlib
+import io
+import json
+import os
+import re
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import MEDIA, ROOT
+
+GOLDEN = json.load(open(os.path.join(ROOT, "tests", "golden", "ref_host_golden.json")))
+
+
+def _words(a):
+    return [int(x) for x in np.ascontiguousarray(a).view(np.uint32).reshape(-1)]
+
+
+@pytest.mark.parametrize("g", GOLDEN["scenes"], ids=lambda g: f"{g['file']}@{g['scale']}")
+def test_loader_matches_reference_loader(gpurt, g):
+    """glTF loader + Mat4/Pose/BBox math + Scene_Desc/Scene_Light packing == the reference's own
+    Scene::load / RTPipe::build_desc, bit for bit (fixture from oracle/_ref, tests/golden/make_golden.py)"""
+    s = gpurt.Scene(None).load(os.path.join(MEDIA, g["file"]), g["scale"])
+    descs, lights = s.descs(), s.lights()
+    assert len(descs) == len(g["objects"]) and len(lights) == len(g["lights"])
+    assert s.counts()["textures"] == g["n_textures"]
+    for i, (d, o) in enumerate(zip(descs, g["objects"])):
+        v, ix = s.object(i)
+        assert (v.shape[0], ix.size) == (o["n_verts"], o["n_indices"])
+        assert hashlib.sha256(v.tobytes()).hexdigest() == o["verts_sha256"]
+        assert hashlib.sha256(ix.tobytes()).hexdigest() == o["indices_sha256"]
+        assert _words(np.array(d.model, np.float32)) == o["model"], f"object {i} model matrix"
+        assert _words(np.array(d.modelIT, np.float32)) == o["modelIT"], f"object {i} modelIT"
+        mat = list(d.albedo[:3]) + list(d.emissive[:3]) + list(d.metal_rough[:2])
+        assert _words(np.array(mat, np.float32)) == o["material"]
+        assert [d.albedo_tex, d.emissive_tex, d.metal_rough_tex, d.normal_tex] == o["textures"]
+        assert d.index == i
+    for l, o in zip(lights, g["lights"]):
+        assert _words(np.array(l.bmin, np.float32)) == o["bmin"] and _words(np.array(l.bmax, np.float32)) == o["bmax"]
+        assert (l.index, l.n_triangles) == (o["index"], o["n_triangles"])
+    # unordered_map iteration order -> descending ids for these scenes
+    assert [o["id"] for o in g["objects"]] == sorted([o["id"] for o in g["objects"]], reverse=True)
+    offs = s.tri_offsets()
+    assert offs[0] == 0 and (np.diff(offs) == [o["n_indices"] // 3 for o in g["objects"]]).all()
+
+
+@pytest.mark.parametrize("c", GOLDEN["cameras"], ids=lambda c: f"cam{c['mode']}_{c['w']}x{c['h']}")
+def test_camera_matches_reference_camera(gpurt, c):
+    cam = gpurt.camera(c["mode"], c["w"], c["h"], c["pos"], c["center"], c["vfov"])
+    got = _words(np.array(list(cam.V) + list(cam.P) + list(cam.iV) + list(cam.iP), np.float32))
+    assert got == c["V_P_iV_iP"]
+
+
+def test_scene_counts_of_the_named_configs(gpurt):
+    assert gpurt.Scene(None).load(os.path.join(MEDIA, "cbox", "cbox.gltf")).counts() == \
+        {"objs": 10, "tris": 16732, "lights": 1, "textures": 0}
+    assert gpurt.Scene(None).load(os.path.join(MEDIA, "mis_test", "mis_test.gltf")).counts() == \
+        {"objs": 7, "tris": 1544, "lights": 3, "textures": 0}
+    assert gpurt.Scene(None).load(os.path.join(MEDIA, "cube.gltf")).counts()["tris"] == 12
+
+
+def test_sponza_standin_is_deterministic_and_sized_like_sponza(gpurt):
+    a, b = gpurt.Scene(None).make_sponza_standin(), gpurt.Scene(None).make_sponza_standin()
+    assert a.counts() == {"objs": 103, "tris": 262267, "lights": 0, "textures": 0}
+    lo, hi = np.full(3, np.inf), np.full(3, -np.inf)
+    for i in range(103):
+        va, ia = a.object(i)
+        vb, ib = b.object(i)
+        assert (va == vb).all() and (ia == ib).all()
+        lo, hi = np.minimum(lo, va[:, :3].min(0)), np.maximum(hi, va[:, :3].max(0))
+        assert ia.max() < va.shape[0]
+    assert np.allclose(lo, [-1921, -126, -1183]) and np.allclose(hi, [1800, 1429, 1105])
+
+
+def test_errors_are_codes_not_exits(gpurt, tmp_path):
+    with pytest.raises(gpurt.GpurtError) as e:
+        gpurt.Scene(None).load(str(tmp_path / "missing.gltf"))
+    assert e.value.code == -4
+    bad = tmp_path / "bad.gltf"
+    bad.write_text("{ not json")
+    with pytest.raises(gpurt.GpurtError):
+        gpurt.Scene(None).load(str(bad))
+    s = gpurt.Scene(None)
+    v = np.zeros((3, 12), np.float32)
+    with pytest.raises(gpurt.GpurtError):
+        s.add_object(v, np.array([0, 1, 3], np.uint32))      # index out of range
+    s.add_object(v, np.array([0, 1, 2], np.uint32))
+    # no CPU fallback: a scene without a context cannot be built, and without a GPU no context exists
+    with pytest.raises(gpurt.GpurtError) as e:
+        gpurt.Accel(s)
+    assert e.value.code == -2
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises(gpurt.GpurtError) as e:
+            gpurt.Context(0)
+        assert e.value.code == -2 and "no CPU fallback" in str(e.value)
+
+
+def test_library_exports_every_declared_symbol(gpurt):
+    header = open(os.path.join(ROOT, "include", "gpurt.h")).read()
+    declared = set(re.findall(r"\b(gpurt_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(gpurt.SYMBOLS), declared ^ set(gpurt.SYMBOLS)
+    nm = subprocess.run(["nm", "-D", "--defined-only", gpurt.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (gpurt_[a-z0-9_]+)", nm))
+    assert declared <= exported, declared - exported
+    for name in declared:
+        assert hasattr(gpurt.lib, name)
+    assert gpurt.lib.gpurt_version().startswith(b"gpurt-b200")
+    # POD layouts promised by the header
+    assert C.sizeof(gpurt.SceneDesc) == 208 and C.sizeof(gpurt.SceneLight) == 48 and C.sizeof(gpurt.Constants) == 88
+    assert C.sizeof(gpurt.Camera) == 328 and gpurt.RAY_DT.itemsize == 32 and gpurt.HIT_DT.itemsize == 16
+    assert gpurt.QUERY_DT.itemsize == 16 and gpurt.CPQ_DT.itemsize == 32
+
+
+def test_product_does_not_link_or_load_the_oracle(gpurt):
+    ldd = subprocess.run(["ldd", gpurt.LIB_PATH], capture_output=True, text=True).stdout
+    assert "oracle" not in ldd and "emu" not in ldd
+    for root, _, files in os.walk(os.path.join(ROOT, "gpu-rt_b200")):
+        if "build" in root:
+            continue
+        for f in files:
+            if f.endswith((".cu", ".cuh", ".cpp", ".h", ".py")):
+                src = open(os.path.join(root, f)).read()
+                assert "liboracle" not in src and "orc_" not in src and "import orc" not in src, f
+
+
+def _png(arr):
+    from PIL import Image
+    buf = io.BytesIO()
+    Image.fromarray(arr).save(buf, format="PNG")
+    return buf.getvalue()
+
+
+def test_gltf_features_embedded_buffers_png_textures_glb_strip_fan(gpurt, tmp_path):
+    """data: URIs, PNG decode, byteStride, u8/u16 indices, strip/fan conversion (scene.cpp:71-143), GLB"""
+    rng = np.random.default_rng(3)
+    rgba = rng.integers(0, 256, (5, 7, 4), dtype=np.uint8)
+    rgb = rng.integers(0, 256, (4, 4, 3), dtype=np.uint8)
+    pos = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0], [0.5, 2, 0]], np.float32)
+    inter = np.zeros((5, 5), np.float32)          # interleaved pos + uv, stride 20
+    inter[:, :3] = pos
+    inter[:, 3:] = rng.random((5, 2), dtype=np.float32)
+    idx8 = np.array([0, 1, 2, 3, 4], np.uint8)     # strip: 3 triangles, fan: 3 triangles
+    blob = inter.tobytes() + idx8.tobytes() + b"\0" * 3
+    uri = "data:application/octet-stream;base64," + base64.b64encode(blob).decode()
+    def gltf(mode, buffers):
+        return {"asset": {"version": "2.0"}, "scene": 0, "scenes": [{"nodes": [0]}],
+                "nodes": [{"mesh": 0, "matrix": [2, 0, 0, 0, 0, 2, 0, 0, 0, 0, 2, 0, 1, 2, 3, 1]}],
+                "meshes": [{"primitives": [{"attributes": {"POSITION": 0, "TEXCOORD_0": 1}, "indices": 2, "material": 0, "mode": mode}]}],
+                "materials": [{"pbrMetallicRoughness": {"baseColorTexture": {"index": 0}, "roughnessFactor": 0.25},
+                               "emissiveTexture": {"index": 1}, "emissiveFactor": [1, 2, 3]}],
+                "textures": [{"source": 0}, {"source": 1}],
+                "images": [{"uri": "data:image/png;base64," + base64.b64encode(_png(rgba)).decode()},
+                           {"uri": "data:image/png;base64," + base64.b64encode(_png(rgb)).decode()}],
+                "buffers": buffers,
+                "bufferViews": [{"buffer": 0, "byteOffset": 0, "byteLength": 100, "byteStride": 20},
+                                {"buffer": 0, "byteOffset": 100, "byteLength": 5}],
+                "accessors": [{"bufferView": 0, "componentType": 5126, "count": 5, "type": "VEC3"},
+                              {"bufferView": 0, "byteOffset": 12, "componentType": 5126, "count": 5, "type": "VEC2"},
+                              {"bufferView": 1, "componentType": 5121, "count": 5, "type": "SCALAR"}]}
+    expect = {5: [0, 1, 2, 1, 2, 3, 2, 3, 4], 6: [0, 1, 2, 0, 2, 3, 0, 3, 4], 4: [0, 1, 2]}
+    for mode in (5, 6):
+        p = tmp_path / f"m{mode}.gltf"
+        p.write_text(json.dumps(gltf(mode, [{"byteLength": len(blob), "uri": uri}])))
+        s = gpurt.Scene(None).load(str(p))
+        v, ix = s.object(0)
+        assert list(ix) == expect[mode]
+        assert (v[:, :3] == pos).all() and (v[:, 3] == inter[:, 3]).all() and (v[:, 7] == inter[:, 4]).all()
+        d = s.descs()[0]
+        assert s.counts()["textures"] == 2 and (d.albedo_tex, d.emissive_tex, d.normal_tex) == (0, 1, -1)
+        assert list(d.emissive[:3]) == [1, 2, 3] and d.metal_rough[1] == 0.25 and len(s.lights()) == 1
+        m = np.array(d.model, np.float32).reshape(4, 4).T
+        assert np.allclose(m[:3, 3], [1, 2, 3], atol=1e-5) and np.allclose(np.diag(m)[:3], 2, atol=1e-5)
+    # GLB container with the binary chunk as buffer 0
+    js = json.dumps(gltf(5, [{"byteLength": len(blob)}])).encode()
+    js += b" " * (-len(js) % 4)
+    bin_chunk = blob + b"\0" * (-len(blob) % 4)
+    glb = b"glTF" + struct.pack("<II", 2, 12 + 8 + len(js) + 8 + len(bin_chunk)) + struct.pack("<II", len(js), 0x4E4F534A) + js \
+        + struct.pack("<II", len(bin_chunk), 0x004E4942) + bin_chunk
+    p = tmp_path / "m.glb"
+    p.write_bytes(glb)
+    s = gpurt.Scene(None).load(str(p))
+    assert list(s.object(0)[1]) == expect[5] and s.counts()["textures"] == 2

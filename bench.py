@@ -117,33 +117,6 @@ def primary_rays(gpurt, rank):
     return rays, cam
 
 
-def bounce_rays(rays, hits, tris_fn, rank):
-    """1-bounce ray set of integrate_mats (rt.rgen:355-389) in shape: origin = hit point, direction =
-    cosine-ish lobe around the geometric normal from the reference RNG stream.  Generated on the host
-    from the traced primary hits until the wavefront integrator exports its own bounce buffer."""
-    ok = hits["prim"] != 0xFFFFFFFF
-    idx = np.nonzero(ok)[0]
-    t9 = tris_fn(hits["prim"][idx])
-    e1, e2 = t9[:, 3:6] - t9[:, 0:3], t9[:, 6:9] - t9[:, 0:3]
-    n = np.cross(e1, e2)
-    n /= np.maximum(np.linalg.norm(n, axis=1, keepdims=True), 1e-20)
-    d0 = rays[idx, 4:7]
-    n = np.where((np.sum(n * d0, 1) > 0)[:, None], -n, n).astype(np.float32)
-    s = tea(idx.astype(np.uint32), np.uint32(0x5EED + rank))
-    phi = np.float32(2 * np.pi) * lcg_randf(s)
-    c2 = lcg_randf(s)
-    sin_t = np.sqrt(1 - c2)
-    a = np.where(np.abs(n[:, :1]) > 0.9, np.array([[0, 1, 0]], np.float32), np.array([[1, 0, 0]], np.float32))
-    tx = np.cross(n, a)
-    tx /= np.linalg.norm(tx, axis=1, keepdims=True)
-    ty = np.cross(n, tx)
-    d = tx * (np.cos(phi) * sin_t)[:, None] + ty * (np.sin(phi) * sin_t)[:, None] + n * np.sqrt(c2)[:, None]
-    out = np.zeros((idx.size, 8), np.float32)
-    out[:, 0:3] = rays[idx, 0:3] + hits["t"][idx, None] * d0
-    out[:, 3], out[:, 4:7], out[:, 7] = 1e-5, d.astype(np.float32), 1e7
-    return out
-
-
 def build_scene(gpurt, ctx):
     scene = gpurt.Scene(ctx)
     path = os.environ.get("GPURT_SPONZA_GLTF")
@@ -154,15 +127,10 @@ def build_scene(gpurt, ctx):
     return scene, "sponza_standin (Sponza.bin missing from the reference snapshot)"
 
 
-def scene_world_tris(scene):
-    """bench-side flattening for the bounce-ray generator / CPU arm input (numpy, fp32)"""
-    parts = []
-    for i, d in enumerate(scene.descs()):
-        v, ix = scene.object(i)
-        m = np.array(d.model, np.float32).reshape(4, 4).T
-        p = v[:, :3] @ m[:3, :3].T + m[:3, 3]
-        parts.append(p[ix].reshape(-1, 9).astype(np.float32))
-    return np.concatenate(parts)
+def scene_world_tris(scene, orc):
+    """world-space triangles for the CPU arm (the oracle's own flattening, contract N1)"""
+    return np.concatenate([orc.flatten(*scene.object(i), np.array(d.model, np.float32))
+                           for i, d in enumerate(scene.descs())])
 
 
 def reference_arm(args, rank, world):
@@ -174,7 +142,7 @@ def reference_arm(args, rank, world):
     import gpurt
     import orc
     scene, label = build_scene(gpurt, None)
-    tris = scene_world_tris(scene)
+    tris = scene_world_tris(scene, orc)
     rays, _ = primary_rays(gpurt, 0)
     t0 = time.time()
     bvh = orc.Bvh(tris)
@@ -229,15 +197,24 @@ def main():
     info = accel.info()
 
     # ---- the frame's ray set, resident in HBM ------------------------------------------------
-    prim, _cam = primary_rays(gpurt, rank)
-    d_prim = torch.from_numpy(prim).cuda()
-    d_hits_p = accel.trace_closest(d_prim)
-    torch.cuda.synchronize()
-    tris = scene_world_tris(scene)
-    bnc = bounce_rays(prim, d_hits_p.cpu().numpy().view(gpurt.HIT_DT).reshape(-1), lambda g: tris[g], rank)
-    rays_np = np.concatenate([prim, bnc])
+    # Rendered by the wavefront integrator itself (config 2: integrator 1 = Material, GGX, depth 2,
+    # 1 spp, frame 0, no RR, env light on); the closest-hit rays it traced are re-used as the step.
+    pos = (CAM_POS[0] + 40.0 * rank, CAM_POS[1], CAM_POS[2] + 25.0 * rank)   # weak scaling: one view per rank
+    cam = gpurt.camera(1, W, H, pos, CAM_AT, VFOV)
+    pipe = gpurt.RTPipe(scene, accel)
+    prm = gpurt.pipe_params(integrator=1, brdf=1, max_depth=2, samples_per_frame=1, max_frames=1, use_rr=0,
+                            env_scale=1.0, seed=rank)
+    ctx.use_torch_stream()
+    frame_ms = []
+    for _ in range(4):
+        pipe.reset_frame()
+        assert pipe.render_frame(prm, cam, W, H) == 0
+        frame_ms.append(pipe.time_ms())
+    frame_rays = pipe.ray_counts()
+    d_rays = torch.cat([pipe.bounce_rays(0), pipe.bounce_rays(1)]).clone()
+    rays_np = d_rays.cpu().numpy()
+    prim = rays_np[: W * H]
     n_rays = rays_np.shape[0]
-    d_rays = torch.from_numpy(rays_np).cuda()
     d_hits = torch.empty((n_rays, 4), dtype=torch.float32, device="cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
@@ -334,7 +311,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         import orc
-        ob = orc.Bvh(tris)
+        ob = orc.Bvh(scene_world_tris(scene, orc))
         cores = orc.lib.orc_hw_threads()
         stride = max(1, n_rays // 600000)
         sample = rays_np[::stride].copy()
@@ -366,6 +343,10 @@ def main():
             "primary_only": {"value": n_p / (float(np.median(prim_ms)) * 1e-3) / 1e6, "unit": "Mrays/s", "rays": n_p},
             "cpq": {"value": n_p / (float(np.median(cpq_ms)) * 1e-3) / 1e6, "unit": "Mqueries/s", "queries": n_p,
                     "what": "closest-point queries near the primary hit points"},
+            "render": {"what": "whole config-2 frame through gpurt_pipe_render_frame (gen + trace + shade + accumulate)",
+                       "ms_per_frame": float(np.median(frame_ms)), "closest_rays": frame_rays[0], "any_rays": frame_rays[1],
+                       "mrays_s": frame_rays[0] / (float(np.median(frame_ms)) * 1e-3) / 1e6,
+                       "mpaths_s": W * H / (float(np.median(frame_ms)) * 1e-3) / 1e6},
             "clocks": clocks, "wall_s": wall,
         }
         print(json.dumps(line), flush=True)

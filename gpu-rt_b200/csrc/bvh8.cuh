@@ -236,10 +236,15 @@ GPURT_HD void encode_node(const Bvh2View& B, const int child[8], unsigned child_
 }
 
 /* ---- traversal-side decoding ------------------------------------------------------------------- */
+#if defined(__CUDACC__)
+static __constant__ unsigned c_one_bits = 0x3f800000u;
+#endif
+
 struct RaySetup {
     F3 o, d, idir;
     float tmin;
     unsigned octinv; /* bit set where the ray travels towards + */
+    unsigned one;    /* 0x3f800000 held in a register for byte_as_unit_float */
 };
 GPURT_HD float safe_rcp_dir(float d) {
     float a = fabsf(d) > 1e-20f ? d : copysignf(1e-20f, d);
@@ -250,24 +255,51 @@ GPURT_HD RaySetup make_ray_setup(F3 o, F3 d, float tmin) {
     r.o = o, r.d = d, r.tmin = tmin;
     r.idir = f3(safe_rcp_dir(d.x), safe_rcp_dir(d.y), safe_rcp_dir(d.z));
     r.octinv = (r.idir.x < 0.0f ? 0u : 1u) | (r.idir.y < 0.0f ? 0u : 2u) | (r.idir.z < 0.0f ? 0u : 4u);
+#if defined(__CUDA_ARCH__)
+    r.one = c_one_bits; /* read from the constant bank so ptxas cannot fold it into PRMT's immediate slot */
+#else
+    r.one = 0x3f800000u;
+#endif
     return r;
 }
 GPURT_HD unsigned byte_of(unsigned lo4, unsigned hi4, int i) {
     return ((i < 4 ? lo4 : hi4) >> (8 * (i & 3))) & 0xffu;
 }
 
-/* Test the 8 children of `n` against the ray interval [tmin, tmax]; returns the hit mask:
- * bits 24..31 inner children in traversal priority, bits 0..23 triangles relative to tri_base. */
-GPURT_HD unsigned node_hitmask(const Node8& n, const RaySetup& r, float tmax) {
+/* 1 + q * 2^-15 for byte `i` (0..3) of `word`, exactly, with one byte-permute: the byte lands in
+ * mantissa bits 8..15 of 1.0f.  fma(that, 2^15*s, o - 2^15*s) == o + q*s up to one rounding of
+ * (o - 2^15*s), i.e. <= 2^-24 * 128.5 * node extent in position units — covered by the N7
+ * inflation (2^-15 * max|coord|).  Replaces shift + mask + I2F (a quarter-rate conversion). */
+GPURT_HD float byte_as_unit_float(unsigned word, unsigned one, int i) {
+#if defined(__CUDA_ARCH__)
+    /* `one` (0x3f800000) is kept in a register so the selector can be an immediate: one PRMT, no
+     * selector materialisation per use */
+    unsigned d;
+    switch(i) {
+    case 0: asm("prmt.b32 %0, %1, %2, 0x7604;" : "=r"(d) : "r"(word), "r"(one)); break;
+    case 1: asm("prmt.b32 %0, %1, %2, 0x7614;" : "=r"(d) : "r"(word), "r"(one)); break;
+    case 2: asm("prmt.b32 %0, %1, %2, 0x7624;" : "=r"(d) : "r"(word), "r"(one)); break;
+    default: asm("prmt.b32 %0, %1, %2, 0x7634;" : "=r"(d) : "r"(word), "r"(one)); break;
+    }
+    return __uint_as_float(d);
+#else
+    return u2f(one | (((word >> (8 * i)) & 0xffu) << 8));
+#endif
+}
+
+/* Test the 8 children of `n` against the ray interval [tmin, tmax]; returns one bit per SLOT
+ * (bit i = child i hit).  Empty slots hold an inverted box (lo=255, hi=0) and always fail.
+ * Cost per child: 4 PRMT + 2 I2F.U8 conversions, 6 FFMA, 4 FMNMX, 1 FSETP, 1 predicated OR. */
+GPURT_HD unsigned node_hits8(const Node8& n, const RaySetup& r, float tmax) {
     unsigned eb = f2u(n.v[0].w);
-    unsigned imask = eb >> 24;
-    float sx = u2f((eb & 0xffu) << 23) * r.idir.x;
-    float sy = u2f(((eb >> 8) & 0xffu) << 23) * r.idir.y;
+    /* x,y: scale = 2^(e-127) * 2^15 * idir (exponent byte moved up by 15), PRMT conversion */
+    float sx = u2f(((eb & 0xffu) + 15u) << 23) * r.idir.x;
+    float sy = u2f((((eb >> 8) & 0xffu) + 15u) << 23) * r.idir.y;
+    /* z planes go through I2F.U8 (XU pipe) to take load off the ALU pipe, which bounds this loop */
     float sz = u2f(((eb >> 16) & 0xffu) << 23) * r.idir.z;
-    float ox = (n.v[0].x - r.o.x) * r.idir.x;
-    float oy = (n.v[0].y - r.o.y) * r.idir.y;
+    float ox = (n.v[0].x - r.o.x) * r.idir.x - sx;
+    float oy = (n.v[0].y - r.o.y) * r.idir.y - sy;
     float oz = (n.v[0].z - r.o.z) * r.idir.z;
-    unsigned m_lo = f2u(n.v[1].z), m_hi = f2u(n.v[1].w);
     /* near / far byte planes per axis according to the ray octant */
     bool px = r.idir.x >= 0.0f, py = r.idir.y >= 0.0f, pz = r.idir.z >= 0.0f;
     unsigned nx0 = f2u(px ? n.v[2].x : n.v[3].z), nx1 = f2u(px ? n.v[2].y : n.v[3].w);
@@ -276,25 +308,31 @@ GPURT_HD unsigned node_hitmask(const Node8& n, const RaySetup& r, float tmax) {
     unsigned fy0 = f2u(py ? n.v[4].x : n.v[2].z), fy1 = f2u(py ? n.v[4].y : n.v[2].w);
     unsigned nz0 = f2u(pz ? n.v[3].x : n.v[4].z), nz1 = f2u(pz ? n.v[3].y : n.v[4].w);
     unsigned fz0 = f2u(pz ? n.v[4].z : n.v[3].x), fz1 = f2u(pz ? n.v[4].w : n.v[3].y);
-    unsigned mask = 0;
+    unsigned one = r.one;
+    unsigned hits = 0;
 #pragma unroll
     for(int i = 0; i < 8; i++) {
-        unsigned meta = byte_of(m_lo, m_hi, i);
-        if(meta == 0) continue;
-        float tnx = fmaf((float)byte_of(nx0, nx1, i), sx, ox);
-        float tny = fmaf((float)byte_of(ny0, ny1, i), sy, oy);
-        float tnz = fmaf((float)byte_of(nz0, nz1, i), sz, oz);
-        float tfx = fmaf((float)byte_of(fx0, fx1, i), sx, ox);
-        float tfy = fmaf((float)byte_of(fy0, fy1, i), sy, oy);
-        float tfz = fmaf((float)byte_of(fz0, fz1, i), sz, oz);
+        const int b = i & 3;
+        float tnx = fmaf(byte_as_unit_float(i < 4 ? nx0 : nx1, one, b), sx, ox);
+        float tny = fmaf(byte_as_unit_float(i < 4 ? ny0 : ny1, one, b), sy, oy);
+        float tnz = fmaf((float)(((i < 4 ? nz0 : nz1) >> (8 * b)) & 0xffu), sz, oz);
+        float tfx = fmaf(byte_as_unit_float(i < 4 ? fx0 : fx1, one, b), sx, ox);
+        float tfy = fmaf(byte_as_unit_float(i < 4 ? fy0 : fy1, one, b), sy, oy);
+        float tfz = fmaf((float)(((i < 4 ? fz0 : fz1) >> (8 * b)) & 0xffu), sz, oz);
         float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, r.tmin));
         float tf = fminf(fminf(tfx, tfy), fminf(tfz, tmax));
-        if(tn <= tf) {
-            if((imask >> i) & 1u) mask |= 1u << (24u + ((unsigned)i ^ r.octinv));
-            else mask |= (meta >> 5) << (meta & 31u);
-        }
+        if(tn <= tf) hits |= 1u << i;
     }
-    return mask;
+    return hits;
+}
+
+/* slot i -> traversal priority i ^ octinv (three conditional bit-swap stages on a byte), so that
+ * the highest set bit is the nearest child */
+GPURT_HD unsigned octant_permute8(unsigned x, unsigned octinv) {
+    if(octinv & 1u) x = ((x & 0x55u) << 1) | ((x & 0xaau) >> 1);
+    if(octinv & 2u) x = ((x & 0x33u) << 2) | ((x & 0xccu) >> 2);
+    if(octinv & 4u) x = ((x & 0x0fu) << 4) | ((x & 0xf0u) >> 4);
+    return x;
 }
 
 /* squared distance from p to child i's decoded box (for the closest-point descent) */

@@ -73,22 +73,29 @@ GPURT_HD bool traverse8(const float4* __restrict__ nodes,
 #pragma unroll
         for(int k = 0; k < 5; k++) node.v[k] = GPURT_LDG(np + k);
         if(STATS) n_nodes++;
-        unsigned mask = node_hitmask(node, rs, best.t);
+        unsigned hit8 = node_hits8(node, rs, best.t);
+        unsigned imask = f2u(node.v[0].w) >> 24;
         ng.x = f2u(node.v[1].x);
-        ng.y = (mask & 0xff000000u) | (f2u(node.v[0].w) >> 24);
-        unsigned tg = mask & 0x00ffffffu;
+        ng.y = (octant_permute8(hit8 & imask, rs.octinv) << 24) | imask;
+        /* hit leaf slots: meta byte = unary(count) << 5 | first triangle offset */
+        unsigned leaf = hit8 & ~imask;
         const float4* tp = tris + (size_t)f2u(node.v[1].y) * kTriVec4;
-        while(tg) {
-            unsigned k = gpurt_ctz(tg);
-            tg &= tg - 1u;
-            float4 r0 = GPURT_LDG(tp + 3 * k), r1 = GPURT_LDG(tp + 3 * k + 1), r2 = GPURT_LDG(tp + 3 * k + 2);
-            if(STATS) n_tris++;
-            float t, u, v;
-            if(intersect_tri(o, d, tmin, tmax, f3(r0.x, r0.y, r0.z), f3(r1.x, r1.y, r1.z),
-                             f3(r2.x, r2.y, r2.z), t, u, v)) {
-                if(ANY) return true;
-                unsigned gid = f2u(r0.w);
-                if(t < best.t || (t == best.t && gid < best.gid)) best.t = t, best.u = u, best.v = v, best.gid = gid;
+        unsigned m_lo = f2u(node.v[1].z), m_hi = f2u(node.v[1].w);
+        while(leaf) {
+            unsigned slot = gpurt_ctz(leaf);
+            leaf &= leaf - 1u;
+            unsigned meta = ((slot & 4u ? m_hi : m_lo) >> (8u * (slot & 3u))) & 0xffu;
+            unsigned k = meta & 31u, kend = k + gpurt_popc(meta >> 5);
+            for(; k < kend; k++) {
+                float4 r0 = GPURT_LDG(tp + 3 * k), r1 = GPURT_LDG(tp + 3 * k + 1), r2 = GPURT_LDG(tp + 3 * k + 2);
+                if(STATS) n_tris++;
+                float t, u, v;
+                if(intersect_tri(o, d, tmin, tmax, f3(r0.x, r0.y, r0.z), f3(r1.x, r1.y, r1.z),
+                                 f3(r2.x, r2.y, r2.z), t, u, v)) {
+                    if(ANY) return true;
+                    unsigned gid = f2u(r0.w);
+                    if(t < best.t || (t == best.t && gid < best.gid)) best.t = t, best.u = u, best.v = v, best.gid = gid;
+                }
             }
         }
     }

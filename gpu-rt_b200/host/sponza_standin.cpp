@@ -91,10 +91,14 @@ void make_sponza_standin(Scene& sc) {
             n = Vec3{0, ny, 0};
         });
     };
-    /* 1 floor, 1 ceiling: 60x40 quads each = 4,800 tris */
+    /* 1 floor: 60x40 quads = 4,800 tris; 1 roof of the same count, open over the light-well like the
+     * real atrium (4 strips of 50x12 quads), so environment light reaches the nave */
     plane_y(Y0, 1.0f, 60, 40, X0, X1, Z0, Z1);
     done();
-    plane_y(Y1, -1.0f, 60, 40, X0, X1, Z0, Z1);
+    plane_y(Y1, -1.0f, 50, 12, X0, X1, Z0, -420.0f);
+    plane_y(Y1, -1.0f, 50, 12, X0, X1, 420.0f, Z1);
+    plane_y(Y1, -1.0f, 50, 12, X0, -1300.0f, -420.0f, 420.0f);
+    plane_y(Y1, -1.0f, 50, 12, 1180.0f, X1, -420.0f, 420.0f);
     done();
     /* 4 outer walls: 40x20 quads = 1,600 tris each */
     for(int w = 0; w < 4; w++) {

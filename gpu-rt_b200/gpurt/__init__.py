@@ -14,7 +14,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "libgpurt.so")
+LIB_PATH = os.environ.get("GPURT_LIB") or os.path.join(os.path.dirname(_HERE), "libgpurt.so")  # GPURT_LIB: tuning builds
 
 MEM_HOST, MEM_DEVICE = 0, 1
 NO_HIT = 0xFFFFFFFF

@@ -498,10 +498,9 @@ int build_accel_device(gpurt_accel* A) {
     const float* sb = A->scene_box;
     float maxabs = 0;
     for(int k = 0; k < 6; k++) maxabs = fmaxf(maxabs, fabsf(sb[k]));
-    /* N7: 2^-15 * max|coord|. Covers fp32 rounding of the primitive tests (a few ulp of the largest
-     * coordinate) plus the 2^-17 * node-extent error of the I2F-free child-plane evaluation
-     * (bvh8.cuh: byte_as_unit_float). */
-    A->inflate = fmaxf(maxabs, 1e-30f) * 3.0517578125e-05f;
+    /* N7, global part: 2^-19 * max|coord| (32 ulp of the largest coordinate) covers fp32 rounding of the
+     * primitive tests; the node-relative part is added in encode_node (bvh8.cuh). */
+    A->inflate = fmaxf(maxabs, 1e-30f) * 1.9073486328125e-06f;
     float ext[3] = {sb[3] - sb[0], sb[4] - sb[1], sb[5] - sb[2]}, inv[3];
     for(int k = 0; k < 3; k++) inv[k] = ext[k] > 0 ? 1.0f / ext[k] : 0.0f;
 

@@ -186,6 +186,20 @@ GPURT_HD void encode_node(const Bvh2View& B, const int child[8], unsigned child_
         nb.lo = f3(fminf(nb.lo.x, b.lo.x), fminf(nb.lo.y, b.lo.y), fminf(nb.lo.z, b.lo.z));
         nb.hi = f3(fmaxf(nb.hi.x, b.hi.x), fmaxf(nb.hi.y, b.hi.y), fmaxf(nb.hi.z, b.hi.z));
     }
+    /* N7, node-relative part: the conversion-free plane evaluation (byte_as_unit_float) rounds
+     * (origin - 2^15*scale) once, an error of at most 2^-24 * 257 * node extent per axis; pad every child
+     * by 2^-14 * node extent (4x that bound).  Small nodes get a negligible pad, only the few large ones
+     * near the root a visible one. */
+    {
+        F3 pad = (nb.hi - nb.lo) * 6.103515625e-05f;
+        for(int s = 0; s < 8; s++) {
+            if(child[s] == kEmptyChild) continue;
+            cb[s].lo = cb[s].lo - pad;
+            cb[s].hi = cb[s].hi + pad;
+        }
+        nb.lo = nb.lo - pad;
+        nb.hi = nb.hi + pad;
+    }
     unsigned ex = pick_exponent(nb.hi.x - nb.lo.x), ey = pick_exponent(nb.hi.y - nb.lo.y),
              ez = pick_exponent(nb.hi.z - nb.lo.z);
     float sx = u2f(ex << 23), sy = u2f(ey << 23), sz = u2f(ez << 23);
@@ -268,8 +282,8 @@ GPURT_HD unsigned byte_of(unsigned lo4, unsigned hi4, int i) {
 
 /* 1 + q * 2^-15 for byte `i` (0..3) of `word`, exactly, with one byte-permute: the byte lands in
  * mantissa bits 8..15 of 1.0f.  fma(that, 2^15*s, o - 2^15*s) == o + q*s up to one rounding of
- * (o - 2^15*s), i.e. <= 2^-24 * 128.5 * node extent in position units — covered by the N7
- * inflation (2^-15 * max|coord|).  Replaces shift + mask + I2F (a quarter-rate conversion). */
+ * (o - 2^15*s), i.e. <= 2^-24 * 257 * node extent in position units — covered by the node-relative
+ * N7 padding (2^-14 * node extent, encode_node).  Replaces shift + mask + I2F (quarter-rate). */
 GPURT_HD float byte_as_unit_float(unsigned word, unsigned one, int i) {
 #if defined(__CUDA_ARCH__)
     /* `one` (0x3f800000) is kept in a register so the selector can be an immediate: one PRMT, no
@@ -335,7 +349,39 @@ GPURT_HD unsigned octant_permute8(unsigned x, unsigned octinv) {
     return x;
 }
 
-/* squared distance from p to child i's decoded box (for the closest-point descent) */
+/* Per-node constants of the closest-point child test.  With u = 1 + q*2^-15 (byte_as_unit_float) and
+ * S = 2^(e-127+15):  lo - p = fma(u_lo, S, a)   and   p - hi = fma(u_hi, -S, -a),  a = origin - S - p,
+ * so each signed plane distance is one PRMT + one FFMA (no I2F, no extra subtraction). */
+struct ChildDist {
+    float sx, sy, sz, ax, ay, az;
+};
+GPURT_HD ChildDist make_child_dist(const Node8& n, F3 p, unsigned one) {
+    (void)one;
+    unsigned eb = f2u(n.v[0].w);
+    ChildDist c;
+    c.sx = u2f(((eb & 0xffu) + 15u) << 23);
+    c.sy = u2f((((eb >> 8) & 0xffu) + 15u) << 23);
+    c.sz = u2f((((eb >> 16) & 0xffu) + 15u) << 23);
+    c.ax = (n.v[0].x - c.sx) - p.x;
+    c.ay = (n.v[0].y - c.sy) - p.y;
+    c.az = (n.v[0].z - c.sz) - p.z;
+    return c;
+}
+GPURT_HD float child_dist2(const Node8& n, const ChildDist& c, int i, unsigned one) {
+    const int b = i & 3;
+    float lx = fmaf(byte_as_unit_float(f2u(i < 4 ? n.v[2].x : n.v[2].y), one, b), c.sx, c.ax);
+    float ly = fmaf(byte_as_unit_float(f2u(i < 4 ? n.v[2].z : n.v[2].w), one, b), c.sy, c.ay);
+    float lz = fmaf(byte_as_unit_float(f2u(i < 4 ? n.v[3].x : n.v[3].y), one, b), c.sz, c.az);
+    float hx = fmaf(byte_as_unit_float(f2u(i < 4 ? n.v[3].z : n.v[3].w), one, b), -c.sx, -c.ax);
+    float hy = fmaf(byte_as_unit_float(f2u(i < 4 ? n.v[4].x : n.v[4].y), one, b), -c.sy, -c.ay);
+    float hz = fmaf(byte_as_unit_float(f2u(i < 4 ? n.v[4].z : n.v[4].w), one, b), -c.sz, -c.az);
+    float dx = fmaxf(fmaxf(lx, hx), 0.0f);
+    float dy = fmaxf(fmaxf(ly, hy), 0.0f);
+    float dz = fmaxf(fmaxf(lz, hz), 0.0f);
+    return fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+}
+
+/* squared distance from p to child i's decoded box (reference form of the above) */
 GPURT_HD float node_child_dist2(const Node8& n, int i, F3 p) {
     unsigned eb = f2u(n.v[0].w);
     float sx = u2f((eb & 0xffu) << 23), sy = u2f(((eb >> 8) & 0xffu) << 23),

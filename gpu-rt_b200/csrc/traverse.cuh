@@ -122,6 +122,11 @@ template <int STACK>
 GPURT_HD void closest_point8(const float4* __restrict__ nodes, const float4* __restrict__ tris, F3 p,
                              float r2, CpRec& best) {
     best.d2 = r2, best.v = 0.0f, best.w = 0.0f, best.gid = kNoHit, best.idx = 0;
+#if defined(__CUDA_ARCH__)
+    const unsigned one = c_one_bits; /* see byte_as_unit_float */
+#else
+    const unsigned one = 0x3f800000u;
+#endif
     uint2 stack[STACK];
     int sp = 0;
     unsigned cur = 0;
@@ -159,11 +164,12 @@ GPURT_HD void closest_point8(const float4* __restrict__ nodes, const float4* __r
         unsigned near_ref = 0;
         float near_d2 = 0.0f;
         bool near_ok = false;
+        ChildDist cd = make_child_dist(node, p, one);
 #pragma unroll
         for(int s = 0; s < 8; s++) {
             unsigned meta = byte_of(m_lo, m_hi, s);
             if(meta == 0) continue;
-            float d2 = node_child_dist2(node, s, p);
+            float d2 = child_dist2(node, cd, s, one);
             if(d2 > best.d2) continue;
             unsigned ref;
             if((imask >> s) & 1u) ref = child_base + gpurt_popc(imask & ((1u << s) - 1u));

@@ -26,7 +26,7 @@ def _check(emu, orc, tris, n=20000, box=None):
     b = orc.Bvh(tris)
     order = b.prim_order()
     l, r, bx = b.bvh2()
-    inflate = np.float32(max(1e-30, np.abs(b.scene_box()).max()) * 2.0 ** -15)   # N7, as csrc/build.cu
+    inflate = np.float32(max(1e-30, np.abs(b.scene_box()).max()) * 2.0 ** -19)   # N7 global part, as csrc/build.cu
     h = C.c_void_p(emu.emu_build(_vp(tris), len(tris), _vp(order), _vp(l), _vp(r), _vp(bx), C.c_float(inflate)))
     assert emu.emu_depth(h) < 60
     box = b.scene_box() if box is None else box

@@ -120,7 +120,7 @@ struct CpRec {
  * shrinking radius when popped.  At most 7 pushes per level: STACK >= 7*depth+1. */
 template <int STACK>
 GPURT_HD void closest_point8(const float4* __restrict__ nodes, const float4* __restrict__ tris, F3 p,
-                             float r2, CpRec& best) {
+                             float r2, CpRec& best, unsigned* visit_counts = nullptr) {
     best.d2 = r2, best.v = 0.0f, best.w = 0.0f, best.gid = kNoHit, best.idx = 0;
 #if defined(__CUDA_ARCH__)
     const unsigned one = c_one_bits; /* see byte_as_unit_float */
@@ -142,6 +142,7 @@ GPURT_HD void closest_point8(const float4* __restrict__ nodes, const float4* __r
         if(cur_d2 > best.d2) continue;
         if(cur & kLeafBit) {
             unsigned first = (cur & ~kLeafBit) >> 2, count = cur & 3u;
+            if(visit_counts) visit_counts[1] += count;
             for(unsigned k = 0; k < count; k++) {
                 const float4* tp = tris + (size_t)(first + k) * kTriVec4;
                 float4 r0 = GPURT_LDG(tp), r1 = GPURT_LDG(tp + 1), r2v = GPURT_LDG(tp + 2);
@@ -158,9 +159,13 @@ GPURT_HD void closest_point8(const float4* __restrict__ nodes, const float4* __r
         Node8 node;
 #pragma unroll
         for(int k = 0; k < 5; k++) node.v[k] = GPURT_LDG(np + k);
+        if(visit_counts) visit_counts[0]++;
         unsigned imask = f2u(node.v[0].w) >> 24;
         unsigned child_base = f2u(node.v[1].x), tri_base = f2u(node.v[1].y);
         unsigned m_lo = f2u(node.v[1].z), m_hi = f2u(node.v[1].w);
+        /* Nearest child continues immediately; the others are pushed (unsorted) with their box distance.
+         * A full distance sort (19-comparator network) was measured: same visit counts on surface-near
+         * queries (17.5 nodes / 21 triangles per query either way) and 10 % slower, so it is not used. */
         unsigned near_ref = 0;
         float near_d2 = 0.0f;
         bool near_ok = false;
@@ -173,11 +178,7 @@ GPURT_HD void closest_point8(const float4* __restrict__ nodes, const float4* __r
             if(d2 > best.d2) continue;
             unsigned ref;
             if((imask >> s) & 1u) ref = child_base + gpurt_popc(imask & ((1u << s) - 1u));
-            else {
-                unsigned unary = meta >> 5;
-                unsigned count = unary == 1u ? 1u : unary == 3u ? 2u : 3u;
-                ref = kLeafBit | ((tri_base + (meta & 31u)) << 2) | count;
-            }
+            else ref = kLeafBit | ((tri_base + (meta & 31u)) << 2) | gpurt_popc(meta >> 5);
             uint2 e;
             if(!near_ok) {
                 near_ref = ref, near_d2 = d2, near_ok = true;

@@ -133,6 +133,8 @@ void emu_trace(void* h, const float* rays, unsigned long long n, unsigned* hits4
     }
 }
 
+unsigned g_cpq_counts[2] = {0, 0};
+void emu_cpq_counts(unsigned long long* out) { out[0] = g_cpq_counts[0], out[1] = g_cpq_counts[1], g_cpq_counts[0] = g_cpq_counts[1] = 0; }
 void emu_cpq(void* h, const float* q, unsigned long long n, unsigned* res8) {
     Emu* E = (Emu*)h;
     for(unsigned long long i = 0; i < n; i++) {
@@ -140,7 +142,7 @@ void emu_cpq(void* h, const float* q, unsigned long long n, unsigned* res8) {
         b.gid = kNoHit;
         if(!E->nodes.empty())
             closest_point8<512>((const float4*)E->nodes.data(), E->tri_wide.data(), f3(q[4 * i], q[4 * i + 1], q[4 * i + 2]),
-                                q[4 * i + 3], b);
+                                q[4 * i + 3], b, g_cpq_counts);
         unsigned* o = res8 + 8 * i;
         if(b.gid == kNoHit) {
             o[0] = o[1] = o[2] = 0, o[3] = f2u(GPURT_INF), o[4] = kNoHit, o[5] = 0, o[6] = o[7] = 0;

@@ -45,19 +45,21 @@ struct gpurt_pipe {
     FrameParams last;                       /* uniforms of the last rendered frame */
     uint64_t last_counts[2] = {0, 0};
     uint32_t max_counts = 0;
+    uint32_t band_rows = 0, n_shards = 1, shard = 0; /* gpurt_pipe_set_shard; 0 = whole frame */
 };
 
 namespace gpurt {
 
 static inline unsigned cdivu(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
 
-__global__ void __launch_bounds__(256) k_frame_begin(uint32_t n, uint32_t seed_val, int restir, float4* acc,
+__global__ void __launch_bounds__(256) k_frame_begin(const __grid_constant__ FrameParams P, int restir, float4* acc,
                                                      float4* pathB, float4* gpos, float4* gnorm, float4* galb,
                                                      float4* res_out) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if(i >= n) return;
+    uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
+    if(li >= P.n_local) return;
+    const uint32_t i = shard_pixel(P, li);
     /* tea(pixel, seed) — rtcommon.glsl:99-109; Q1: seed = user seed ^ frame replaces clockARB() */
-    uint32_t v0 = i, v1 = seed_val, s0 = 0;
+    uint32_t v0 = i, v1 = P.seed_val, s0 = 0;
     for(uint32_t k = 0; k < 16; k++) {
         s0 += 0x9e3779b9u;
         v0 += ((v1 << 4) + 0xa341316cu) ^ (v1 + s0) ^ ((v1 >> 5) + 0xc8013ea4u);
@@ -75,19 +77,19 @@ __global__ void __launch_bounds__(256) k_frame_begin(uint32_t n, uint32_t seed_v
 __global__ void __launch_bounds__(256) k_gen_camera(const __grid_constant__ FrameParams P, uint32_t s,
                                                     float4* pathA, float4* pathB, float4* rays,
                                                     uint32_t* queue, uint32_t* count) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t n = P.W * P.H;
-    if(i == 0) *count = n;
-    if(i >= n) return;
+    uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
+    if(li == 0) *count = P.n_local;
+    if(li >= P.n_local) return;
+    const uint32_t i = shard_pixel(P, li);
     ShadeCtx dummy{};
     Shader sh(dummy, P);
     float4 B = pathB[i];
     sh.seed = __float_as_uint(B.w);
     F3 d = sh.make_camera_ray(s, i % P.W, i / P.W);
     F4 co = mul4(P.cam.iV, 0.0f, 0.0f, 0.0f, 1.0f); /* rt.rgen:572 */
-    rays[2ull * i] = make_float4(co.x, co.y, co.z, kEps);
-    rays[2ull * i + 1] = make_float4(d.x, d.y, d.z, kLargeDist);
-    queue[i] = i;
+    rays[2ull * li] = make_float4(co.x, co.y, co.z, kEps);
+    rays[2ull * li + 1] = make_float4(d.x, d.y, d.z, kLargeDist);
+    queue[li] = i;
     pathA[i] = make_float4(0, 0, 0, 1.0f);                           /* trace.acc, trace.mis */
     pathB[i] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(sh.seed)); /* trace.throughput, rng */
 }
@@ -194,8 +196,9 @@ __global__ void __launch_bounds__(128) k_shade(const __grid_constant__ FramePara
 __global__ void __launch_bounds__(256) k_frame_end(const __grid_constant__ FrameParams P, const float4* acc,
                                                    float4* image, const float4* gpos, const float4* gnorm,
                                                    const float4* ppos, const float4* pnorm, const float4* palb) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if(i >= P.W * P.H) return;
+    uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
+    if(li >= P.n_local) return;
+    const uint32_t i = shard_pixel(P, li);
     float4 a = acc[i];
     F3 avg = F3{a.x, a.y, a.z} / (float)P.c.samples; /* rt.rgen:638 */
     float4 out;
@@ -342,6 +345,12 @@ int gpurt_pipe_reset_frame(gpurt_pipe* p) { /* rt.cpp:396-398 */
     p->frame = -1;
     return GPURT_OK;
 }
+/* Multi-GPU sharding (no reference counterpart: the reference is single-GPU). */
+int gpurt_pipe_set_shard(gpurt_pipe* p, uint32_t band_rows, uint32_t n_shards, uint32_t shard) {
+    if(!p || (band_rows && (!n_shards || shard >= n_shards))) return set_error("bad shard arguments"), GPURT_E_INVALID;
+    p->band_rows = band_rows, p->n_shards = band_rows ? n_shards : 1, p->shard = band_rows ? shard : 0;
+    return GPURT_OK;
+}
 int gpurt_pipe_frame_index(const gpurt_pipe* p, int32_t* f) {
     if(!p || !f) return set_error("NULL argument"), GPURT_E_INVALID;
     *f = p->frame;
@@ -392,7 +401,18 @@ int gpurt_pipe_render_frame(gpurt_pipe* p, const GpurtPipeParams* prm, const Gpu
     F.W = w, F.H = h;
     F.seed_val = prm->seed ^ (uint32_t)c.frame;
 
-    const uint32_t n = w * h;
+    F.band_rows = p->band_rows ? p->band_rows : h, F.n_shards = p->band_rows ? p->n_shards : 1, F.shard = p->band_rows ? p->shard : 0;
+    {
+        uint32_t n_local = 0, bands = (h + F.band_rows - 1) / F.band_rows;
+        for(uint32_t g = F.shard; g < bands; g += F.n_shards) n_local += std::min(F.band_rows, h - g * F.band_rows) * w;
+        F.n_local = n_local;
+    }
+    const uint32_t n = F.n_local; /* pixels rendered by this pipe */
+    if(n == 0) { /* more shards than bands: nothing to do on this rank */
+        p->parity ^= 1;
+        p->last = F;
+        return GPURT_OK;
+    }
     const int cur = p->parity, prev = cur ^ 1; /* bind_temporal_stuff ping-pong (rt.cpp:222-344) */
     const bool restir = c.integrator == 3 || c.integrator == 4;
     ShadeCtx X;
@@ -403,7 +423,7 @@ int gpurt_pipe_render_frame(gpurt_pipe* p, const GpurtPipeParams* prm, const Gpu
 
     GPURT_CUDA(cudaEventRecord(ctx->ev0, st));
     GPURT_CUDA(cudaMemsetAsync(p->ray_counts, 0, 16, st));
-    k_frame_begin<<<cdivu(n, 256), 256, 0, st>>>(n, F.seed_val, restir ? 1 : 0, p->acc, p->pathB, p->gbuf[cur][0],
+    k_frame_begin<<<cdivu(n, 256), 256, 0, st>>>(F, restir ? 1 : 0, p->acc, p->pathB, p->gbuf[cur][0],
                                                 p->gbuf[cur][1], p->gbuf[cur][2], p->res[cur]);
     const uint32_t D = (uint32_t)c.max_depth;
     for(uint32_t s = 0; s < (uint32_t)c.samples && D > 0; s++) {

@@ -60,7 +60,18 @@ struct FrameParams {
     GpurtConstants c;
     GpurtCamera cam;
     uint32_t W, H, seed_val;
+    /* multi-GPU sharding of the frame: this pipe renders the bands of `band_rows` rows whose
+     * band index is congruent to `shard` modulo `n_shards`; (H, 1, 0) = the whole frame */
+    uint32_t band_rows, n_shards, shard, n_local;
 };
+
+/* i-th locally rendered pixel -> global pixel index y*W + x (RNG, image and G-buffers are indexed by
+ * the global pixel, so results do not depend on how the frame is sharded) */
+__device__ __forceinline__ uint32_t shard_pixel(const FrameParams& P, uint32_t i) {
+    uint32_t per_band = P.band_rows * P.W;
+    uint32_t band = i / per_band, in_band = i - band * per_band;
+    return (band * P.n_shards + P.shard) * per_band + in_band;
+}
 
 struct Reservoir { /* restir.glsl:2-9; stored as 3 float4: pos|w_sum, normal|w, emissive|n_seen */
     F3 pos, normal, emissive;

@@ -89,7 +89,7 @@ SYMBOLS = [
     "gpurt_pipe_params_default", "gpurt_pipe_create", "gpurt_pipe_destroy", "gpurt_pipe_reset_frame",
     "gpurt_pipe_render_frame", "gpurt_pipe_frame_index", "gpurt_pipe_read_image", "gpurt_pipe_read_gbuffer",
     "gpurt_pipe_ray_counts", "gpurt_pipe_device_image", "gpurt_tonemap", "gpurt_pipe_last_uniforms",
-    "gpurt_pipe_read_reservoirs", "gpurt_pipe_bounce_rays",
+    "gpurt_pipe_read_reservoirs", "gpurt_pipe_bounce_rays", "gpurt_pipe_set_shard",
 ]
 
 
@@ -350,6 +350,23 @@ class RTPipe:
 
     def reset_frame(self):
         _check(lib.gpurt_pipe_reset_frame(self.h))
+
+    def set_shard(self, band_rows, n_shards, shard):
+        """render only row bands with (band index % n_shards) == shard; band_rows=0: whole frame"""
+        _check(lib.gpurt_pipe_set_shard(self.h, band_rows, n_shards, shard))
+
+    def device_image(self):
+        """torch view (H,W,4) of rt_target in device memory (no copy)"""
+        import torch
+        ptr = C.c_void_p()
+        _check(lib.gpurt_pipe_device_image(self.h, C.byref(ptr)))
+
+        class _Arr:
+            pass
+
+        a = _Arr()
+        a.__cuda_array_interface__ = {"shape": (self.h_px, self.w, 4), "typestr": "<f4", "data": (ptr.value, False), "version": 2}
+        return torch.as_tensor(a, device=f"cuda:{self.ctx.device}")
 
     def render_frame(self, params, cam, width, height):
         self.w, self.h_px = width, height

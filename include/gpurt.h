@@ -233,6 +233,12 @@ int gpurt_pipe_reset_frame(gpurt_pipe* pipe);
 int gpurt_pipe_render_frame(gpurt_pipe* pipe, const GpurtPipeParams* params, const GpurtCamera* cam,
                             uint32_t width, uint32_t height);
 int gpurt_pipe_frame_index(const gpurt_pipe* pipe, int32_t* out_frame);
+/* Multi-GPU sharding of a frame (the reference is single-GPU): this pipe renders only the
+ * bands of `band_rows` rows whose band index is congruent to `shard` modulo `n_shards`.  RNG streams,
+ * image and G-buffers stay indexed by the global pixel, so the union of all shards is bit-identical to
+ * an unsharded frame (integrators 0-2; ReSTIR's temporal pass reads neighbouring pixels of the previous
+ * frame and needs the whole previous frame on the rank).  band_rows = 0 restores whole-frame rendering. */
+int gpurt_pipe_set_shard(gpurt_pipe* pipe, uint32_t band_rows, uint32_t n_shards, uint32_t shard);
 /* rt_target (RGBA32F, src/gpurt.cpp:189-193) -> caller buffer of width*height*4 floats. */
 int gpurt_pipe_read_image(gpurt_pipe* pipe, float* out_rgba, int mem);
 /* which: 0 position, 1 normal, 2 albedo (rt.rgen:674-676) */

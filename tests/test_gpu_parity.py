@@ -162,3 +162,20 @@ def test_sponza_standin_properties(gpurt, orc, ctx):
     q2[:, 0:3] = cp["p"]
     assert (accel.closest_points(q2)["dist"] <= 1e-3 * 3700).all()
     accel.close(), scene.close()
+
+
+def test_config4_full_size_soup(gpurt, built):
+    """BASELINE config 4 at full mesh size: 10,000,000-triangle soup, 20 M sharded queries on this GPU;
+    primitive order and a 100 k-query subsample are compared with the CPU oracle bit for bit."""
+    import json
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "config4_cpq.py"), "--tris", "10000000",
+                          "--queries", "20000000", "--check", "100000"], capture_output=True, text=True, timeout=1500)
+    assert out.returncode == 0, out.stderr[-2000:]
+    res = json.loads(out.stdout.strip().splitlines()[-1])
+    assert res["tris"] == 10_000_000 and res["queries"] == 20_000_000
+    assert res["check"]["bit_exact_vs_oracle"] and res["check"]["prim_order_equals_oracle"]
+    assert res["mqueries_s"] > 50

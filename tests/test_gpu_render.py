@@ -169,6 +169,42 @@ def test_rtpipe_frame_logic(gpurt, ctx):
     pipe.close(), accel.close(), scene.close()
 
 
+def test_sharded_frames_compose_to_the_unsharded_frame(gpurt, ctx):
+    """interleaved row bands per rank; RNG keyed by the global pixel -> rank-count invariant"""
+    scene = load_scene(gpurt, ctx, "cbox")
+    accel = gpurt.Accel(scene)
+    w, h = 160, 100   # 100 rows: the last 16-row band is partial
+    cam = gpurt.camera(0, w, h)
+    prm = gpurt.pipe_params(integrator=2, brdf=1, samples_per_frame=2, max_depth=4, seed=5)
+
+    def frames(pipe, n=3):
+        for _ in range(n):
+            pipe.render_frame(prm, cam, w, h)
+        return pipe.read_image(), [pipe.read_gbuffer(g) for g in range(3)]
+
+    whole = gpurt.RTPipe(scene, accel)
+    ref_img, ref_gb = frames(whole)
+    for world in (2, 3, 8):
+        img = np.zeros_like(ref_img)
+        gb = [np.zeros_like(g) for g in ref_gb]
+        rows = np.arange(h)
+        for rank in range(world):
+            p = gpurt.RTPipe(scene, accel)
+            p.set_shard(16, world, rank)
+            i, g = frames(p)
+            mine = (rows // 16) % world == rank
+            img[mine] = i[mine]
+            for k in range(3):
+                gb[k][mine] = g[k][mine]
+            assert (i[~mine] == 0).all(), "a shard must not touch other ranks' rows"
+            p.close()
+        assert (img.view(np.uint32) == ref_img.view(np.uint32)).all(), f"{world} shards"
+        for k in range(3):
+            assert (gb[k].view(np.uint32) == ref_gb[k].view(np.uint32)).all()
+    whole.set_shard(0, 1, 0)
+    whole.close(), accel.close(), scene.close()
+
+
 def test_tonemap_matches_oracle(gpurt, orc, ctx):
     scene = load_scene(gpurt, ctx, "cbox")
     accel = gpurt.Accel(scene)

@@ -18,6 +18,13 @@ def row_bands(height, rank, world):
     return [(y, min(height, y + band)) for i, y in enumerate(range(0, height, band)) if i % world == rank]
 
 
+def warmup(device):
+    """create the NCCL communicators (collective + point-to-point) before anything is timed"""
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        gather_to_rank0(torch.zeros((1 + dist.get_rank(), 4), device=device))
+        torch.cuda.synchronize() if device.type == "cuda" else None
+
+
 def gather_to_rank0(local, counts=None):
     """Gather variable-length first-dimension shards to rank 0 (returns the concatenation on rank 0,
     None elsewhere).  Uses all_gather of the lengths + gather / point-to-point of the payload."""

@@ -22,7 +22,7 @@ import torch.distributed as dist
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "gpu-rt_b200"))
 import gpurt  # noqa: E402
-from gpurt.dist import gather_to_rank0, shard_range  # noqa: E402
+from gpurt.dist import gather_to_rank0, shard_range, warmup  # noqa: E402
 
 M32 = 0xFFFFFFFF
 
@@ -82,6 +82,7 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        warmup(dev)
     ctx = gpurt.Context(local)
     ctx.use_torch_stream()
 

@@ -24,6 +24,7 @@ sys.path.insert(0, os.path.join(ROOT, "gpu-rt_b200"))
 sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 import gpurt  # noqa: E402
+from gpurt.dist import gather_to_rank0, warmup  # noqa: E402
 
 BAND = 16
 
@@ -53,6 +54,7 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        warmup(dev)
     w, h = args.size
     ctx = gpurt.Context(local)
     ctx.use_torch_stream()
@@ -75,9 +77,7 @@ def main():
     mine = img.view(nb, BAND, w, 4)[rank::world].contiguous()
     torch.cuda.synchronize()
     g0 = time.time()
-    if world > 1:
-        parts = [torch.empty_like(img.view(nb, BAND, w, 4)[r::world].contiguous()) for r in range(world)] if rank == 0 else None
-        dist.gather(mine, parts, dst=0)
+    gathered = gather_to_rank0(mine) if world > 1 else None   # ranks own different band counts
     torch.cuda.synchronize()
     gather_ms = (time.time() - g0) * 1e3
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -86,8 +86,11 @@ def main():
     if rank == 0:
         full = torch.empty((nb, BAND, w, 4), dtype=torch.float32, device=dev)
         if world > 1:
+            off = 0
             for r in range(world):
-                full[r::world] = parts[r]
+                cnt = len(range(r, nb, world))
+                full[r::world] = gathered[off:off + cnt]
+                off += cnt
         else:
             full.copy_(img.view(nb, BAND, w, 4))
         full = full.view(h, w, 4)
@@ -103,7 +106,7 @@ def main():
             "spp_total": args.spp * args.frames, "frames_rendered": frames, "depth": args.depth,
             "s_total_max_rank": t.item() * 1e-3, "mpaths_s": paths / (t.item() * 1e-3) / 1e6,
             "gather_ms": gather_ms, "gather_bytes": int(w * h * 16 * (world - 1) / world),
-            "bit_identical_to_unsharded": identical, "mean_radiance": float(full[..., :3].mean())}), flush=True)
+            "bit_identical_to_unsharded": identical, "mean_radiance": float(torch.nanmean(full[..., :3]))}), flush=True)
         if args.out:
             from PIL import Image
             x = 1.0 - torch.exp(-full[..., :3])

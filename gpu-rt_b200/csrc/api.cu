@@ -57,29 +57,45 @@ int upload_scene(gpurt_ctx* ctx, gpurt_scene* s, DeviceScene& d) {
     return GPURT_OK;
 }
 
-/* Run `launch(d_in, d_out)` with caller buffers in host or device memory; times the device work. */
+/* Run `launch(d_in, d_out, count)` over n elements with caller buffers in host or device memory.
+ * Device buffers: one launch, asynchronous on the context's stream.  Host buffers: the batch is cut
+ * into chunks and pipelined over three streams (H2D copy -> kernel -> D2H copy), so that PCIe traffic
+ * in both directions overlaps the traversal; with pinned caller memory the call approaches
+ * max(H2D, kernel, D2H) instead of their sum.  ev0/ev1 bracket the device work for gpurt_last_kernel_ms. */
 template <typename F>
-static int run_query(gpurt_ctx* ctx, const void* in, size_t in_bytes, void* out, size_t out_bytes,
+static int run_query(gpurt_ctx* ctx, const void* in, size_t in_stride, void* out, size_t out_stride, uint64_t n,
                      int mem, F launch) {
     GPURT_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     if(mem == GPURT_MEM_DEVICE) {
         GPURT_CUDA(cudaEventRecord(ctx->ev0, st));
-        int rc = launch(in, out);
+        int rc = launch(in, out, n);
         if(rc) return rc;
         GPURT_CUDA(cudaEventRecord(ctx->ev1, st));
         return GPURT_OK;
     }
     if(mem != GPURT_MEM_HOST) return set_error("mem must be GPURT_MEM_HOST or GPURT_MEM_DEVICE"), GPURT_E_INVALID;
     int rc;
-    if((rc = ctx->d_in.reserve(in_bytes))) return rc;
-    if((rc = ctx->d_out.reserve(out_bytes))) return rc;
-    /* pageable caller memory: cudaMemcpyAsync stages through the driver's pinned pool */
-    GPURT_CUDA(cudaMemcpyAsync(ctx->d_in.p, in, in_bytes, cudaMemcpyHostToDevice, st));
+    if((rc = ctx->d_in.reserve(n * in_stride))) return rc;
+    if((rc = ctx->d_out.reserve(n * out_stride))) return rc;
+    const uint64_t chunk = 1u << 18; /* 256 Ki elements: 8 MB of rays per copy */
     GPURT_CUDA(cudaEventRecord(ctx->ev0, st));
-    if((rc = launch(ctx->d_in.p, ctx->d_out.p))) return rc;
+    GPURT_CUDA(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev0, 0)); /* staging buffers may still be in use on st */
+    GPURT_CUDA(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev0, 0));
+    for(uint64_t off = 0; off < n; off += chunk) {
+        uint64_t cnt = std::min<uint64_t>(chunk, n - off);
+        char* di = (char*)ctx->d_in.p + off * in_stride;
+        char* dout = (char*)ctx->d_out.p + off * out_stride;
+        GPURT_CUDA(cudaMemcpyAsync(di, (const char*)in + off * in_stride, cnt * in_stride, cudaMemcpyHostToDevice, ctx->s_h2d));
+        GPURT_CUDA(cudaEventRecord(ctx->ev_copy, ctx->s_h2d));
+        GPURT_CUDA(cudaStreamWaitEvent(st, ctx->ev_copy, 0));
+        if((rc = launch(di, dout, cnt))) return rc;
+        GPURT_CUDA(cudaEventRecord(ctx->ev_kernel, st));
+        GPURT_CUDA(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_kernel, 0));
+        GPURT_CUDA(cudaMemcpyAsync((char*)out + off * out_stride, dout, cnt * out_stride, cudaMemcpyDeviceToHost, ctx->s_d2h));
+    }
     GPURT_CUDA(cudaEventRecord(ctx->ev1, st));
-    GPURT_CUDA(cudaMemcpyAsync(out, ctx->d_out.p, out_bytes, cudaMemcpyDeviceToHost, st));
+    GPURT_CUDA(cudaStreamSynchronize(ctx->s_d2h));
     GPURT_CUDA(cudaStreamSynchronize(st));
     return GPURT_OK;
 }
@@ -108,6 +124,10 @@ int gpurt_ctx_create(int device, gpurt_ctx** out) {
     c->stream = c->own_stream;
     GPURT_CUDA(cudaEventCreate(&c->ev0));
     GPURT_CUDA(cudaEventCreate(&c->ev1));
+    GPURT_CUDA(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
+    GPURT_CUDA(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
+    GPURT_CUDA(cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming));
+    GPURT_CUDA(cudaEventCreateWithFlags(&c->ev_kernel, cudaEventDisableTiming));
     *out = c;
     return GPURT_OK;
 }
@@ -117,7 +137,8 @@ int gpurt_ctx_destroy(gpurt_ctx* c) {
     cudaStreamSynchronize(c->stream);
     c->d_in.release(), c->d_out.release(), c->scratch.release();
     c->h_in.release(), c->h_out.release();
-    cudaEventDestroy(c->ev0), cudaEventDestroy(c->ev1);
+    cudaEventDestroy(c->ev0), cudaEventDestroy(c->ev1), cudaEventDestroy(c->ev_copy), cudaEventDestroy(c->ev_kernel);
+    cudaStreamDestroy(c->s_h2d), cudaStreamDestroy(c->s_d2h);
     cudaStreamDestroy(c->own_stream);
     delete c;
     return GPURT_OK;
@@ -216,23 +237,23 @@ int gpurt_accel_get_bvh2(const gpurt_accel* A, int32_t* left, int32_t* right, fl
 /* ---- queries ---------------------------------------------------------------------------------- */
 int gpurt_trace_closest(gpurt_accel* A, const GpurtRay* rays, uint64_t n, GpurtHit* hits, int mem) {
     if(!A || (n && (!rays || !hits))) return set_error("NULL argument"), GPURT_E_INVALID;
-    return run_query(A->ctx, rays, n * sizeof(GpurtRay), hits, n * sizeof(GpurtHit), mem,
-                     [&](const void* i, void* o) { return launch_trace_closest(A, (const float4*)i, n, (float4*)o); });
+    return run_query(A->ctx, rays, sizeof(GpurtRay), hits, sizeof(GpurtHit), n, mem,
+                     [&](const void* i, void* o, uint64_t c) { return launch_trace_closest(A, (const float4*)i, c, (float4*)o); });
 }
 int gpurt_trace_closest_bvh2(gpurt_accel* A, const GpurtRay* rays, uint64_t n, GpurtHit* hits, int mem) {
     if(!A || (n && (!rays || !hits))) return set_error("NULL argument"), GPURT_E_INVALID;
-    return run_query(A->ctx, rays, n * sizeof(GpurtRay), hits, n * sizeof(GpurtHit), mem,
-                     [&](const void* i, void* o) { return launch_trace_closest_bvh2(A, (const float4*)i, n, (float4*)o); });
+    return run_query(A->ctx, rays, sizeof(GpurtRay), hits, sizeof(GpurtHit), n, mem,
+                     [&](const void* i, void* o, uint64_t c) { return launch_trace_closest_bvh2(A, (const float4*)i, c, (float4*)o); });
 }
 int gpurt_trace_any(gpurt_accel* A, const GpurtRay* rays, uint64_t n, uint8_t* occ, int mem) {
     if(!A || (n && (!rays || !occ))) return set_error("NULL argument"), GPURT_E_INVALID;
-    return run_query(A->ctx, rays, n * sizeof(GpurtRay), occ, n, mem,
-                     [&](const void* i, void* o) { return launch_trace_any(A, (const float4*)i, n, (uint8_t*)o); });
+    return run_query(A->ctx, rays, sizeof(GpurtRay), occ, 1, n, mem,
+                     [&](const void* i, void* o, uint64_t c) { return launch_trace_any(A, (const float4*)i, c, (uint8_t*)o); });
 }
 int gpurt_closest_points(gpurt_accel* A, const GpurtQuery* q, uint64_t n, GpurtClosestPoint* res, int mem) {
     if(!A || (n && (!q || !res))) return set_error("NULL argument"), GPURT_E_INVALID;
-    return run_query(A->ctx, q, n * sizeof(GpurtQuery), res, n * sizeof(GpurtClosestPoint), mem,
-                     [&](const void* i, void* o) { return launch_closest_points(A, (const float4*)i, n, (float4*)o); });
+    return run_query(A->ctx, q, sizeof(GpurtQuery), res, sizeof(GpurtClosestPoint), n, mem,
+                     [&](const void* i, void* o, uint64_t c) { return launch_closest_points(A, (const float4*)i, c, (float4*)o); });
 }
 int gpurt_trace_closest_stats(gpurt_accel* A, const GpurtRay* rays, uint64_t n, GpurtHit* hits,
                               GpurtTraceStats* out) {
@@ -243,8 +264,8 @@ int gpurt_trace_closest_stats(gpurt_accel* A, const GpurtRay* rays, uint64_t n, 
     if(rc) return rc;
     unsigned long long* d = ctx->scratch.as<unsigned long long>();
     GPURT_CUDA(cudaMemsetAsync(d, 0, 32, ctx->stream));
-    rc = run_query(ctx, rays, n * sizeof(GpurtRay), hits, n * sizeof(GpurtHit), GPURT_MEM_DEVICE,
-                   [&](const void* i, void* o) { return launch_trace_closest_stats(A, (const float4*)i, n, (float4*)o, d); });
+    rc = run_query(ctx, rays, sizeof(GpurtRay), hits, sizeof(GpurtHit), n, GPURT_MEM_DEVICE,
+                   [&](const void* i, void* o, uint64_t c) { return launch_trace_closest_stats(A, (const float4*)i, c, (float4*)o, d); });
     if(rc) return rc;
     unsigned long long h[4];
     GPURT_CUDA(cudaMemcpyAsync(h, d, 32, cudaMemcpyDeviceToHost, ctx->stream));

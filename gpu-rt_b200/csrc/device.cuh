@@ -44,6 +44,9 @@ struct gpurt_ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t own_stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    /* host-buffer calls: copy streams and hand-over events of the H2D -> kernel -> D2H pipeline */
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    cudaEvent_t ev_copy = nullptr, ev_kernel = nullptr;
     float last_ms = 0;
     /* staging for GPURT_MEM_HOST calls */
     gpurt::DevBuf d_in, d_out;

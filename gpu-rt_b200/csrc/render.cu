@@ -6,11 +6,12 @@
  *   k_frame_begin                      per pixel: RNG seed, zero accumulators / G-buffer / reservoir
  *   for s < samples:
  *     k_gen_camera                     make_camera_ray (rt.rgen:551-565) -> ray queue 0 (all pixels)
- *     for depth < max_depth:
+ *     for depth < wave:                (wave = max_depth, or 4 for small shards)
  *       k_trace_closest_indirect       the batch closest-hit kernel over the compacted queue
  *       k_shade                        miss / hit_info / mat_info / shade_info / integrator / Russian
  *                                      roulette; surviving paths are compacted into the next queue
  *                                      with a warp ballot + one atomicAdd per warp
+ *     k_tail                           remaining bounces of the surviving paths, one thread per path
  *   k_frame_end                        reservoir / progressive accumulation / debug view
  *
  * Per-pixel state (RNG, throughput, radiance, mis weight) lives in two float4 arrays indexed by
@@ -19,6 +20,7 @@
  * integrator are traced inline by the shading thread.
  */
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "../host/camera.h"
@@ -46,6 +48,7 @@ struct gpurt_pipe {
     uint64_t last_counts[2] = {0, 0};
     uint32_t max_counts = 0;
     uint32_t band_rows = 0, n_shards = 1, shard = 0; /* gpurt_pipe_set_shard; 0 = whole frame */
+    uint32_t wave_depth = 0;                          /* bounces run as wavefronts before k_tail; 0 = by size */
 };
 
 namespace gpurt {
@@ -108,6 +111,45 @@ __global__ void __launch_bounds__(128) k_trace_closest_indirect(const float4* __
     hits[i] = make_float4(h.gid == kNoHit ? GPURT_INF : h.t, h.u, h.v, u2f(h.gid));
 }
 
+/* One iteration of rt.rgen's bounce loop body after traceRayEXT (rt.rgen:591-627) for the path of pixel
+ * `pix`: miss handling, hit_info / mat_info / shade_info, G-buffer capture, the selected integrator and
+ * Russian roulette.  Returns true when the path ends here (`break` in the shader). */
+__device__ __forceinline__ bool shade_step(const FrameParams& P, Shader& sh, TraceInfo& trace, uint32_t s, uint32_t depth,
+                                           uint32_t pix, float4 h, float4* gpos, float4* gnorm, float4* galb,
+                                           float4* res_cur) {
+    const bool restir = P.c.integrator == 3 || P.c.integrator == 4;
+    bool broke = false;
+    uint32_t gid = f2u(h.w);
+    if(gid == kNoHit) { /* rt.rgen:591-598 */
+        if(depth == 0) trace.acc = F3{P.c.clear_col[0], P.c.clear_col[1], P.c.clear_col[2]};
+        else trace.acc = trace.acc + F3{P.c.env_light[0], P.c.env_light[1], P.c.env_light[2]} * trace.throughput;
+        return true;
+    }
+    Payload pl;
+    sh.payload_from_hit(h.y, h.z, gid, pl);
+    HitInfo hit = sh.hit_info(pl);
+    MatInfo mat = sh.mat_info(pl, hit);
+    ShadeInfo shade = sh.shade_info(trace.d, hit, mat);
+    if(s == 0 && depth == 0) { /* rt.rgen:604-608 */
+        gpos[pix] = make_float4(hit.pos.x, hit.pos.y, hit.pos.z, 1.0f);
+        gnorm[pix] = make_float4(shade.N.x, shade.N.y, shade.N.z, 1.0f);
+        galb[pix] = make_float4(mat.albedo.x, mat.albedo.y, mat.albedo.z, 1.0f);
+    }
+    if(restir && depth == 0) sh.prev_res = Shader::res_load(res_cur + 3ull * pix);
+    if(P.c.integrator == 0) sh.integrate_direct(trace, hit, mat, shade);
+    else if(P.c.integrator == 1) sh.integrate_mats(trace, hit, mat, shade);
+    else if(P.c.integrator == 2) sh.integrate_mis(trace, hit, mat, shade);
+    else if(P.c.integrator == 3) sh.integrate_restir(trace, hit, mat, shade, true, s == 0);
+    else if(P.c.integrator == 4) sh.integrate_restir(trace, hit, mat, shade, false, s == 0);
+    if(restir && depth == 0) Shader::res_store(res_cur + 3ull * pix, sh.prev_res);
+    if(P.c.use_rr == 1) { /* rt.rgen:622-627 */
+        float pcont = fminf(fmaxf(trace.throughput.x, fmaxf(trace.throughput.y, trace.throughput.z)) + 0.001f, 0.95f);
+        if(sh.randf() >= pcont) broke = true;
+        else trace.throughput = trace.throughput / pcont;
+    }
+    return broke;
+}
+
 __global__ void __launch_bounds__(128) k_shade(const __grid_constant__ FrameParams P,
                                                const __grid_constant__ ShadeCtx X, uint32_t s, uint32_t depth,
                                                const uint32_t* __restrict__ count_in, const uint32_t* __restrict__ queue_in,
@@ -129,37 +171,7 @@ __global__ void __launch_bounds__(128) k_shade(const __grid_constant__ FramePara
         trace.acc = F3{A.x, A.y, A.z}, trace.mis = A.w;
         trace.throughput = F3{B.x, B.y, B.z}, trace.depth = depth;
         sh.seed = __float_as_uint(B.w);
-        const bool restir = P.c.integrator == 3 || P.c.integrator == 4;
-        bool broke = false;
-        uint32_t gid = f2u(h.w);
-        if(gid == kNoHit) { /* rt.rgen:591-598 */
-            if(depth == 0) trace.acc = F3{P.c.clear_col[0], P.c.clear_col[1], P.c.clear_col[2]};
-            else trace.acc = trace.acc + F3{P.c.env_light[0], P.c.env_light[1], P.c.env_light[2]} * trace.throughput;
-            broke = true;
-        } else {
-            Payload pl;
-            sh.payload_from_hit(h.y, h.z, gid, pl);
-            HitInfo hit = sh.hit_info(pl);
-            MatInfo mat = sh.mat_info(pl, hit);
-            ShadeInfo shade = sh.shade_info(trace.d, hit, mat);
-            if(s == 0 && depth == 0) { /* rt.rgen:604-608 */
-                gpos[pix] = make_float4(hit.pos.x, hit.pos.y, hit.pos.z, 1.0f);
-                gnorm[pix] = make_float4(shade.N.x, shade.N.y, shade.N.z, 1.0f);
-                galb[pix] = make_float4(mat.albedo.x, mat.albedo.y, mat.albedo.z, 1.0f);
-            }
-            if(restir && depth == 0) sh.prev_res = Shader::res_load(res_cur + 3ull * pix);
-            if(P.c.integrator == 0) sh.integrate_direct(trace, hit, mat, shade);
-            else if(P.c.integrator == 1) sh.integrate_mats(trace, hit, mat, shade);
-            else if(P.c.integrator == 2) sh.integrate_mis(trace, hit, mat, shade);
-            else if(P.c.integrator == 3) sh.integrate_restir(trace, hit, mat, shade, true, s == 0);
-            else if(P.c.integrator == 4) sh.integrate_restir(trace, hit, mat, shade, false, s == 0);
-            if(restir && depth == 0) Shader::res_store(res_cur + 3ull * pix, sh.prev_res);
-            if(P.c.use_rr == 1) { /* rt.rgen:622-627 */
-                float pcont = fminf(fmaxf(trace.throughput.x, fmaxf(trace.throughput.y, trace.throughput.z)) + 0.001f, 0.95f);
-                if(sh.randf() >= pcont) broke = true;
-                else trace.throughput = trace.throughput / pcont;
-            }
-        }
+        bool broke = shade_step(P, sh, trace, s, depth, pix, h, gpos, gnorm, galb, res_cur);
         cont = !broke && trace.depth + 1 < (uint32_t)P.c.max_depth;
         if(cont) {
             pathA[pix] = make_float4(trace.acc.x, trace.acc.y, trace.acc.z, trace.mis);
@@ -188,6 +200,50 @@ __global__ void __launch_bounds__(128) k_shade(const __grid_constant__ FramePara
     unsigned nc = __reduce_add_sync(0xffffffffu, live ? 1u + sh.n_closest : 0u);
     unsigned na = __reduce_add_sync(0xffffffffu, live ? sh.n_any : 0u);
     if(lane == 0) {
+        if(nc) atomicAdd(X.ray_counts + 0, (unsigned long long)nc);
+        if(na) atomicAdd(X.ray_counts + 1, (unsigned long long)na);
+    }
+}
+
+/* Tail of the wavefront: after the first bounces only a fraction of the paths is alive and one
+ * trace + one shade launch per bounce become latency-bound (worst when a frame is sharded over 8 GPUs).
+ * Here every remaining path runs its bounce loop to the end in one thread: same shade_step, same
+ * traverse8, same per-pixel RNG stream, so the image does not change — only the launch count does. */
+__global__ void __launch_bounds__(128) k_tail(const __grid_constant__ FrameParams P, const __grid_constant__ ShadeCtx X,
+                                              uint32_t s, uint32_t depth0, const uint32_t* __restrict__ count_in,
+                                              const uint32_t* __restrict__ queue_in, const float4* __restrict__ rays_in,
+                                              float4* pathA, float4* pathB, float4* acc, float4* gpos, float4* gnorm,
+                                              float4* galb, float4* res_cur) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    bool live = k < *count_in;
+    Shader sh(X, P);
+    unsigned n_wave = 0;
+    if(live) {
+        uint32_t pix = queue_in[k];
+        float4 r0 = rays_in[2ull * k], r1 = rays_in[2ull * k + 1];
+        float4 A = pathA[pix], B = pathB[pix];
+        TraceInfo trace;
+        trace.o = F3{r0.x, r0.y, r0.z}, trace.d = F3{r1.x, r1.y, r1.z};
+        trace.acc = F3{A.x, A.y, A.z}, trace.mis = A.w;
+        trace.throughput = F3{B.x, B.y, B.z};
+        sh.seed = __float_as_uint(B.w);
+        for(uint32_t depth = depth0;; depth++) {
+            trace.depth = depth;
+            HitRec hr;
+            hr.gid = kNoHit, hr.t = 0, hr.u = hr.v = 0;
+            n_wave++;
+            if(X.n_nodes) traverse8<false, false>(X.nodes, X.tris, trace.o, trace.d, kEps, kLargeDist, hr, nullptr);
+            float4 h = make_float4(hr.t, hr.u, hr.v, u2f(hr.gid));
+            bool broke = shade_step(P, sh, trace, s, depth, pix, h, gpos, gnorm, galb, res_cur);
+            if(broke || trace.depth + 1 >= (uint32_t)P.c.max_depth) break;
+        }
+        float4 a = acc[pix];
+        acc[pix] = make_float4(a.x + trace.acc.x, a.y + trace.acc.y, a.z + trace.acc.z, 0.0f);
+        pathB[pix] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(sh.seed));
+    }
+    unsigned nc = __reduce_add_sync(0xffffffffu, live ? n_wave + sh.n_closest : 0u);
+    unsigned na = __reduce_add_sync(0xffffffffu, live ? sh.n_any : 0u);
+    if((threadIdx.x & 31) == 0) {
         if(nc) atomicAdd(X.ray_counts + 0, (unsigned long long)nc);
         if(na) atomicAdd(X.ray_counts + 1, (unsigned long long)na);
     }
@@ -329,6 +385,7 @@ int gpurt_pipe_create(gpurt_scene* scene, gpurt_accel* accel, gpurt_pipe** out) 
     std::memset(&p->last, 0, sizeof(p->last));
     GPURT_CUDA(cudaSetDevice(p->ctx->device));
     upload_lut_once();
+    if(const char* e = getenv("GPURT_WAVE_DEPTH")) p->wave_depth = (uint32_t)std::max(1, atoi(e)); /* tuning knob */
     *out = p;
     return GPURT_OK;
 }
@@ -429,7 +486,12 @@ int gpurt_pipe_render_frame(gpurt_pipe* p, const GpurtPipeParams* prm, const Gpu
     for(uint32_t s = 0; s < (uint32_t)c.samples && D > 0; s++) {
         GPURT_CUDA(cudaMemsetAsync(p->counts, 0, (size_t)p->max_counts * 4, st));
         k_gen_camera<<<cdivu(n, 256), 256, 0, st>>>(F, s, p->pathA, p->pathB, p->rays[0], p->queue[0], p->counts + 0);
-        for(uint32_t d = 0; d < D; d++) {
+        /* wavefront for the first `wave` bounces, then one tail kernel for whatever is still alive */
+        /* measured (profiles/r01_tuning.md): with >= ~2.5 M paths per launch the full wavefront is fastest
+         * (tail after 3 bounces: -9 %, mega-kernel: -73 %); for small shards (4K frame over 8 GPUs) every
+         * launch is latency-bound and a tail after 4 bounces is 10 % faster */
+        const uint32_t wave = p->wave_depth ? std::min(D, p->wave_depth) : (n > 2500000u ? D : std::min(D, 4u));
+        for(uint32_t d = 0; d < wave; d++) {
             int qi = d & 1, qo = qi ^ 1;
             k_trace_closest_indirect<<<cdivu(n, 128), 128, 0, st>>>(X.nodes, X.tris, p->rays[qi], p->counts + d, p->hits,
                                                                    X.n_nodes);
@@ -437,6 +499,10 @@ int gpurt_pipe_render_frame(gpurt_pipe* p, const GpurtPipeParams* prm, const Gpu
                                                   p->pathB, p->acc, p->gbuf[cur][0], p->gbuf[cur][1], p->gbuf[cur][2],
                                                   p->res[cur], p->counts + d + 1, p->queue[qo], p->rays[qo]);
         }
+        if(wave < D)
+            k_tail<<<cdivu(n, 128), 128, 0, st>>>(F, X, s, wave, p->counts + wave, p->queue[wave & 1], p->rays[wave & 1],
+                                                 p->pathA, p->pathB, p->acc, p->gbuf[cur][0], p->gbuf[cur][1],
+                                                 p->gbuf[cur][2], p->res[cur]);
         /* closest-hit rays of the wavefront = sum of queue sizes */
     }
     k_frame_end<<<cdivu(n, 256), 256, 0, st>>>(F, p->acc, p->image, p->gbuf[cur][0], p->gbuf[cur][1], p->gbuf[prev][0],

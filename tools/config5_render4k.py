@@ -48,6 +48,7 @@ def main():
     ap.add_argument("--depth", type=int, default=8)
     ap.add_argument("--verify", action="store_true")
     ap.add_argument("--out", default="")
+    ap.add_argument("--emulate-shards", type=int, default=0, help="single process: render only shard 0 of N (per-rank cost probe)")
     args = ap.parse_args()
     rank, local, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     torch.cuda.set_device(local)
@@ -65,7 +66,7 @@ def main():
     # max_frames-1 because frames are numbered from 0 and trace() stops when frame >= max_frames
     prm = gpurt.pipe_params(integrator=1, brdf=1, max_depth=args.depth, samples_per_frame=args.spp,
                             max_frames=args.frames - 1, use_rr=1, env_scale=1.0, seed=7)
-    pipe.set_shard(BAND, world, rank)
+    pipe.set_shard(BAND, args.emulate_shards or world, rank)
     render(pipe, prm, cam, w, h, ctx)                      # warm-up (allocations, L2)
     torch.cuda.synchronize()
     if world > 1:

@@ -193,6 +193,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = gpurt.Context(local)
     scene, label = build_scene(gpurt, ctx)
+    gpurt.Accel(scene).close()      # first build warms the allocation pool
     accel = gpurt.Accel(scene)
     info = accel.info()
 
@@ -332,6 +333,7 @@ def main():
             "config": {"workload": "sponza 1080p config-2 ray set (2,073,600 primary + 1-bounce rays), closest-hit",
                        "scene": label, "rays_per_gpu": n_rays, "tris": info.n_tris, "wide_nodes": info.n_wide_nodes,
                        "wide_depth": info.wide_depth, "bvh_build_ms": info.build_ms,
+                       "bvh_build_mtris_s": info.n_tris / (info.build_ms * 1e-3) / 1e6,
                        "l2": "flushed between timed steps (256 MiB memset)", "sharding": "rays sharded per rank, scene replicated, no collective in the timed region"},
             "e2e": {"value": e2e_val, "unit": "Mrays/s", "h2d_bytes_per_step": int(n_rays * 32), "d2h_bytes_per_step": int(n_rays * 16)},
             "gpu_launches": args.steps,

@@ -120,6 +120,13 @@ int gpurt_ctx_create(int device, gpurt_ctx** out) {
     gpurt_ctx* c = new gpurt_ctx;
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
+    { /* keep freed build temporaries cached in the stream-ordered pool instead of returning them to the OS */
+        cudaMemPool_t pool;
+        if(cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     GPURT_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
     GPURT_CUDA(cudaEventCreate(&c->ev0));

@@ -70,6 +70,22 @@ struct FrameParams {
 __device__ __forceinline__ uint32_t shard_pixel(const FrameParams& P, uint32_t i) {
     uint32_t per_band = P.band_rows * P.W;
     uint32_t band = i / per_band, in_band = i - band * per_band;
+    /* inside a band pixels are enumerated in 8x4 tiles, so the 32 camera rays a warp traces together
+     * cover a compact screen region (better node / triangle sharing than a 32x1 scanline segment);
+     * only the ORDER of the ray queue changes, never a pixel's result */
+    if((P.W & 15u) == 0u && (P.band_rows & 7u) == 0u && (P.H & 7u) == 0u) {
+        /* 128 consecutive paths (one CTA of the trace kernel) = a 16x8 pixel block of 2x2 warp tiles */
+        uint32_t blk = in_band >> 7, t = in_band & 127u;
+        uint32_t blocks_x = P.W >> 4;
+        uint32_t by = blk / blocks_x, bx = blk - by * blocks_x;
+        uint32_t w = t >> 5, l = t & 31u;
+        in_band = (by * 8u + (w >> 1) * 4u + (l >> 3)) * P.W + bx * 16u + (w & 1u) * 8u + (l & 7u);
+    } else if((P.W & 7u) == 0u && (P.band_rows & 3u) == 0u && (P.H & 3u) == 0u) {
+        uint32_t tile = in_band >> 5, t = in_band & 31u;
+        uint32_t tiles_x = P.W >> 3;
+        uint32_t ty = tile / tiles_x, tx = tile - ty * tiles_x;
+        in_band = (ty * 4u + (t >> 3)) * P.W + tx * 8u + (t & 7u);
+    }
     return (band * P.n_shards + P.shard) * per_band + in_band;
 }
 

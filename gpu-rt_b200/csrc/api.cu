@@ -168,6 +168,45 @@ int gpurt_last_kernel_ms(gpurt_ctx* c, float* ms) {
     return GPURT_OK;
 }
 
+/* ---- cross-process result buffers (multi-GPU sharding, include/gpurt.h) ----------------------- */
+static_assert(sizeof(cudaIpcMemHandle_t) == GPURT_IPC_HANDLE_BYTES, "handle size");
+int gpurt_shared_alloc(gpurt_ctx* c, uint64_t bytes, void** out, uint8_t* handle) {
+    if(!c || !out || !handle || !bytes) return set_error("NULL argument"), GPURT_E_INVALID;
+    GPURT_CUDA(cudaSetDevice(c->device));
+    void* p = nullptr;
+    GPURT_CUDA(cudaMalloc(&p, bytes)); /* a dedicated allocation: the handle names its base address */
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if(e != cudaSuccess) {
+        cudaFree(p);
+        return set_error(std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e)), GPURT_E_CUDA;
+    }
+    memcpy(handle, &h, sizeof h);
+    *out = p;
+    return GPURT_OK;
+}
+int gpurt_shared_free(gpurt_ctx* c, void* p) {
+    if(!c) return set_error("NULL context"), GPURT_E_INVALID;
+    GPURT_CUDA(cudaSetDevice(c->device));
+    GPURT_CUDA(cudaFree(p));
+    return GPURT_OK;
+}
+int gpurt_shared_open(gpurt_ctx* c, const uint8_t* handle, void** out) {
+    if(!c || !handle || !out) return set_error("NULL argument"), GPURT_E_INVALID;
+    GPURT_CUDA(cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof h);
+    GPURT_CUDA(cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
+    return GPURT_OK;
+}
+int gpurt_shared_close(gpurt_ctx* c, void* p) {
+    if(!c) return set_error("NULL context"), GPURT_E_INVALID;
+    GPURT_CUDA(cudaSetDevice(c->device));
+    GPURT_CUDA(cudaStreamSynchronize(c->stream));
+    GPURT_CUDA(cudaIpcCloseMemHandle(p));
+    return GPURT_OK;
+}
+
 /* ---- accel ------------------------------------------------------------------------------------ */
 int gpurt_accel_build(gpurt_scene* s, uint32_t flags, gpurt_accel** out) {
     if(!s || !out) return set_error("NULL argument"), GPURT_E_INVALID;

@@ -90,6 +90,7 @@ SYMBOLS = [
     "gpurt_pipe_render_frame", "gpurt_pipe_frame_index", "gpurt_pipe_read_image", "gpurt_pipe_read_gbuffer",
     "gpurt_pipe_ray_counts", "gpurt_pipe_device_image", "gpurt_tonemap", "gpurt_pipe_last_uniforms",
     "gpurt_pipe_read_reservoirs", "gpurt_pipe_bounce_rays", "gpurt_pipe_set_shard",
+    "gpurt_shared_alloc", "gpurt_shared_free", "gpurt_shared_open", "gpurt_shared_close",
 ]
 
 
@@ -121,8 +122,42 @@ def _is_torch(x):
     return type(x).__module__.startswith("torch")
 
 
+class SharedBuffer:
+    """A device allocation that other ranks' kernels write into directly (gpurt_shared_*): rank 0 owns
+    it, the other ranks map it over NVLink and pass `buf.at(byte_offset)` as the result pointer of
+    their query call.  `.tensor()` views the owner's copy as a torch uint8 tensor without copying."""
+
+    def __init__(self, ctx, ptr, nbytes, handle, owner):
+        self.ctx, self.ptr, self.nbytes, self.handle, self.owner = ctx, ptr, nbytes, handle, owner
+
+    def at(self, byte_offset):
+        assert 0 <= byte_offset <= self.nbytes
+        return _RawDevicePtr(self.ptr + byte_offset, self)
+
+    def tensor(self):
+        import torch
+        return torch.as_tensor(self, device=f"cuda:{self.ctx.device}")
+
+    @property
+    def __cuda_array_interface__(self):
+        return {"shape": (self.nbytes,), "typestr": "|u1", "data": (self.ptr, False), "version": 2}
+
+    def close(self):
+        if self.ptr:
+            fn = lib.gpurt_shared_free if self.owner else lib.gpurt_shared_close
+            _check(fn(self.ctx.h, C.c_void_p(self.ptr)))
+            self.ptr = 0
+
+
+class _RawDevicePtr:
+    def __init__(self, ptr, keep):
+        self.ptr, self.keep = ptr, keep
+
+
 def _ptr(x, nbytes_min=0):
-    """(void* pointer, mem flag, keepalive) of a numpy array or torch tensor"""
+    """(void* pointer, mem flag, keepalive) of a numpy array, torch tensor or SharedBuffer offset"""
+    if isinstance(x, _RawDevicePtr):
+        return C.c_void_p(x.ptr), MEM_DEVICE, x
     if _is_torch(x):
         assert x.is_contiguous()
         if x.is_cuda:
@@ -151,6 +186,17 @@ class Context:
         ms = C.c_float()
         _check(lib.gpurt_last_kernel_ms(self.h, C.byref(ms)))
         return ms.value
+
+    def shared_alloc(self, nbytes):
+        """owner side of a cross-process result buffer (include/gpurt.h, multi-GPU result placement)"""
+        p, h = C.c_void_p(), (C.c_uint8 * 64)()
+        _check(lib.gpurt_shared_alloc(self.h, C.c_uint64(nbytes), C.byref(p), h))
+        return SharedBuffer(self, p.value, nbytes, bytes(h), True)
+
+    def shared_open(self, handle, nbytes):
+        p, h = C.c_void_p(), (C.c_uint8 * 64).from_buffer_copy(handle)
+        _check(lib.gpurt_shared_open(self.h, h, C.byref(p)))
+        return SharedBuffer(self, p.value, nbytes, bytes(handle), False)
 
     def close(self):
         if self.h:

@@ -25,6 +25,24 @@ def warmup(device):
         torch.cuda.synchronize() if device.type == "cuda" else None
 
 
+def shared_result_buffer(ctx, nbytes):
+    """Rank 0 allocates `nbytes` of result storage, every other rank maps it over NVLink
+    (gpurt_shared_alloc / gpurt_shared_open).  A rank then passes `buf.at(first_element * stride)` as
+    the result pointer of its query call: the traversal kernel stores straight into rank 0's HBM and
+    no gather collective follows.  Call `dist.barrier()` after the ranks' streams are synchronised and
+    before rank 0 reads `buf.tensor()`."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return ctx.shared_alloc(nbytes)
+    box = [None]
+    if dist.get_rank() == 0:
+        buf = ctx.shared_alloc(nbytes)
+        box[0] = buf.handle
+    dist.broadcast_object_list(box, src=0)
+    if dist.get_rank() != 0:
+        buf = ctx.shared_open(box[0], nbytes)
+    return buf
+
+
 def gather_to_rank0(local, counts=None):
     """Gather variable-length first-dimension shards to rank 0 (returns the concatenation on rank 0,
     None elsewhere).  Uses all_gather of the lengths + gather / point-to-point of the payload."""

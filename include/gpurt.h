@@ -220,6 +220,21 @@ int gpurt_trace_closest_stats(gpurt_accel* accel, const GpurtRay* rays, uint64_t
 /* Device time (ms) of the last query / render call on this accel's context (CUDA events). */
 int gpurt_last_kernel_ms(gpurt_ctx* ctx, float* out_ms);
 
+/* ---- multi-GPU result placement (no reference counterpart — GPU-RT is single-GPU) --- */
+/* One process per GPU, scene replicated, queries sharded.  Instead of a gather collective after the
+ * query, the rank that owns the full result array exports it once; every other rank maps it over
+ * NVLink and passes `mapped + first_element` as the device `hits` / `results` pointer of its query
+ * call, so the traversal kernel's own result stores land in the owner's HBM while it computes.
+ * The handle is 64 opaque bytes (cudaIpcMemHandle_t); ship it with any byte transport. */
+#define GPURT_IPC_HANDLE_BYTES 64
+/* owner rank: a dedicated device allocation + its handle */
+int gpurt_shared_alloc(gpurt_ctx* ctx, uint64_t bytes, void** out_device_ptr,
+                       uint8_t handle_out[GPURT_IPC_HANDLE_BYTES]);
+int gpurt_shared_free(gpurt_ctx* ctx, void* device_ptr);
+/* other ranks (other processes): map / unmap the owner's allocation */
+int gpurt_shared_open(gpurt_ctx* ctx, const uint8_t handle[GPURT_IPC_HANDLE_BYTES], void** out_device_ptr);
+int gpurt_shared_close(gpurt_ctx* ctx, void* mapped_device_ptr);
+
 /* ---- integrator: replaces VK::RTPipe (src/vk/rt.h:14-142) -------------------------------------- */
 int gpurt_pipe_params_default(GpurtPipeParams* out); /* rt.h:38-53 */
 /* RTPipe::recreate(scene) + use_accel(tlas) (src/vk/rt.cpp:16-24, :159-176) */

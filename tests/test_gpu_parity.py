@@ -179,3 +179,41 @@ def test_config4_full_size_soup(gpurt, built):
     assert res["tris"] == 10_000_000 and res["queries"] == 20_000_000
     assert res["check"]["bit_exact_vs_oracle"] and res["check"]["prim_order_equals_oracle"]
     assert res["mqueries_s"] > 50
+
+
+def test_shared_result_buffer_single_process(gpurt, orc, ctx):
+    """gpurt_shared_alloc: a query writes through `buf.at(offset)`; the owner's view holds the same bytes"""
+    import torch
+    scene = load_scene(gpurt, ctx, "cbox")
+    accel = gpurt.Accel(scene)
+    box = np.array(list(accel.info().scene_min) + list(accel.info().scene_max), np.float32)
+    rays = orc.gen_random_rays(50000, 21, box)
+    want = accel.trace_closest(rays)
+    buf = ctx.shared_alloc(2 * 50000 * 16)
+    assert len(buf.handle) == 64
+    d_rays = torch.from_numpy(rays).cuda()
+    accel.trace_closest(d_rays, buf.at(50000 * 16))   # second half of the buffer
+    torch.cuda.synchronize()
+    got = buf.tensor()[50000 * 16:].cpu().numpy().view(gpurt.HIT_DT)
+    assert same_bits(got, want)
+    buf.close(), accel.close(), scene.close()
+
+
+def test_p2p_result_placement_two_gpus(gpurt, built):
+    """config 4 on two ranks with the kernels storing into rank 0's buffer over NVLink; rank 0 checks
+    the half written by rank 1 against the oracle (needs 2 GPUs)"""
+    import json
+    import os
+    import subprocess
+    import sys
+    import torch
+    from conftest import ROOT
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29731",
+                          os.path.join(ROOT, "tools", "config4_cpq.py"), "--tris", "1000000", "--queries", "4000000",
+                          "--chunk", "1000000", "--check", "50000", "--p2p"], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr[-2000:]
+    res = json.loads(out.stdout.strip().splitlines()[-1])
+    assert res["n_gpus"] == 2 and res["queries"] == 4_000_000 and res["check"]["bit_exact_vs_oracle"]

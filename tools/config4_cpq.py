@@ -22,7 +22,7 @@ import torch.distributed as dist
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "gpu-rt_b200"))
 import gpurt  # noqa: E402
-from gpurt.dist import gather_to_rank0, shard_range, warmup  # noqa: E402
+from gpurt.dist import gather_to_rank0, shard_range, shared_result_buffer, warmup  # noqa: E402
 
 M32 = 0xFFFFFFFF
 
@@ -75,7 +75,9 @@ def main():
     ap.add_argument("--queries", type=int, default=100_000_000)
     ap.add_argument("--chunk", type=int, default=12_500_000)
     ap.add_argument("--check", type=int, default=200_000)
-    ap.add_argument("--gather", action="store_true")
+    ap.add_argument("--gather", action="store_true", help="NCCL gather of the results to rank 0 after the queries")
+    ap.add_argument("--p2p", action="store_true",
+                    help="kernels store their results straight into rank 0's buffer over NVLink (no gather)")
     args = ap.parse_args()
     rank, local, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     torch.cuda.set_device(local)
@@ -97,6 +99,7 @@ def main():
     info = accel.info()
 
     a, b = shard_range(args.queries, rank, world)
+    shared = shared_result_buffer(ctx, args.queries * 32) if args.p2p else None
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -106,12 +109,12 @@ def main():
     for c0 in range(a, b, args.chunk):
         c1 = min(b, c0 + args.chunk)
         q = make_queries(c0, c1, dev)          # generated on the device, not timed
-        out = torch.empty((c1 - c0, 8), dtype=torch.float32, device=dev)
+        out = shared.at(c0 * 32) if args.p2p else torch.empty((c1 - c0, 8), dtype=torch.float32, device=dev)
         torch.cuda.synchronize()
         accel.closest_points(q, out)
         ms += ctx.last_kernel_ms()
         n_done += c1 - c0
-        if args.gather or (rank == 0 and c0 == a):
+        if args.gather or (rank == 0 and c0 == a and not args.p2p):
             results.append(out if args.gather else out[: args.check].clone())
         del q
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -130,12 +133,21 @@ def main():
         if rank == 0:
             assert full.shape[0] == args.queries
 
+    chk0 = a
+    if args.p2p:
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        if rank == 0:   # check the part of the array the LAST rank wrote over NVLink
+            chk0 = shard_range(args.queries, world - 1, world)[0]
+            full = shared.tensor().view(torch.float32).view(-1, 8)
+            results = [full[chk0:chk0 + args.check].clone()]
     check = None
     if rank == 0 and args.check:
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         import orc
         n_chk = min(args.check, b - a)
-        q = make_queries(a, a + n_chk, dev).cpu().numpy()
+        q = make_queries(chk0, chk0 + n_chk, dev).cpu().numpy()
         got = results[0][:n_chk].cpu().numpy().view(np.uint32)
         t1 = time.time()
         ob = orc.Bvh(tris_h)
@@ -150,7 +162,12 @@ def main():
             "mqueries_s": tot.item() / (t.item() * 1e-3) / 1e6, "kernel_ms_max_rank": t.item(),
             "bvh_build_ms_device": info.build_ms, "bvh_build_s_wall_incl_upload": round(t_build_wall, 2),
             "build_mtris_s": info.n_tris / (info.build_ms * 1e-3) / 1e6, "wide_nodes": info.n_wide_nodes,
-            "wide_depth": info.wide_depth, "gather_ms": gather_ms, "check": check}), flush=True)
+            "wide_depth": info.wide_depth, "gather_ms": gather_ms, "results": "p2p stores into rank 0" if args.p2p else
+            ("nccl gather" if args.gather else "left on each rank"), "check": check}), flush=True)
+    if shared is not None:
+        if world > 1:
+            dist.barrier()
+        shared.close()
     if world > 1:
         dist.destroy_process_group()
 

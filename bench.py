@@ -196,6 +196,10 @@ def main():
     gpurt.Accel(scene).close()      # first build warms the allocation pool
     accel = gpurt.Accel(scene)
     info = accel.info()
+    # pose edit + in-place rebuild (GPURT::build_accel after edit_scene): same matrix, so the scene is unchanged
+    scene.set_transform(0, np.array(list(scene.descs()[0].model), np.float32))
+    accel.update()
+    update_ms = accel.info().build_ms
 
     # ---- the frame's ray set, resident in HBM ------------------------------------------------
     # Rendered by the wavefront integrator itself (config 2: integrator 1 = Material, GGX, depth 2,
@@ -332,7 +336,7 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "sponza 1080p config-2 ray set (2,073,600 primary + 1-bounce rays), closest-hit",
                        "scene": label, "rays_per_gpu": n_rays, "tris": info.n_tris, "wide_nodes": info.n_wide_nodes,
-                       "wide_depth": info.wide_depth, "bvh_build_ms": info.build_ms,
+                       "wide_depth": info.wide_depth, "bvh_build_ms": info.build_ms, "bvh_update_ms": update_ms,
                        "bvh_build_mtris_s": info.n_tris / (info.build_ms * 1e-3) / 1e6,
                        "l2": "flushed between timed steps (256 MiB memset)", "sharding": "rays sharded per rank, scene replicated, no collective in the timed region"},
             "e2e": {"value": e2e_val, "unit": "Mrays/s", "h2d_bytes_per_step": int(n_rays * 32), "d2h_bytes_per_step": int(n_rays * 16)},

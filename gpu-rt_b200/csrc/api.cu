@@ -28,9 +28,20 @@ void free_scene(DeviceScene& d) {
 
 int upload_scene(gpurt_ctx* ctx, gpurt_scene* s, DeviceScene& d) {
     if(!s->pack()) return GPURT_E_INVALID;
-    free_scene(d);
     const PackedScene& P = s->packed;
     cudaStream_t st = ctx->stream;
+    if(d.verts && d.geom_version == s->geom_version && d.n_objs == P.descs.size() && d.n_lights == P.lights.size()) {
+        /* pose-only edit: geometry stays resident, Scene_Desc / Scene_Light are rewritten in place */
+        if(d.version == s->version) return GPURT_OK;
+        if(!P.descs.empty())
+            GPURT_CUDA(cudaMemcpyAsync(d.descs, P.descs.data(), P.descs.size() * sizeof(SceneDesc), cudaMemcpyHostToDevice, st));
+        if(!P.lights.empty())
+            GPURT_CUDA(cudaMemcpyAsync(d.lights, P.lights.data(), P.lights.size() * sizeof(SceneLight), cudaMemcpyHostToDevice, st));
+        d.version = s->version;
+        GPURT_CUDA(cudaStreamSynchronize(st)); /* P.descs may be rebuilt by the next edit */
+        return GPURT_OK;
+    }
+    free_scene(d);
     int rc;
     if((rc = upload(st, d.verts, P.verts))) return rc;
     if((rc = upload(st, d.idx, P.idx))) return rc;
@@ -42,7 +53,7 @@ int upload_scene(gpurt_ctx* ctx, gpurt_scene* s, DeviceScene& d) {
     d.n_tris = P.tri_off.back();
     d.n_lights = (uint32_t)P.lights.size();
     d.n_verts = (uint32_t)P.verts.size();
-    d.version = s->version;
+    d.version = s->version, d.geom_version = s->geom_version;
     /* textures: RTPipe::build_textures (src/vk/rt.cpp:430-455) */
     std::vector<uint8_t> texels;
     std::vector<uint4> info;
@@ -224,6 +235,18 @@ int gpurt_accel_build(gpurt_scene* s, uint32_t flags, gpurt_accel** out) {
     }
     *out = A;
     return GPURT_OK;
+}
+int gpurt_accel_update(gpurt_accel* A) {
+    if(!A) return set_error("NULL argument"), GPURT_E_INVALID;
+    GPURT_CUDA(cudaSetDevice(A->ctx->device));
+    if(!A->scene->pack()) return GPURT_E_INVALID;
+    if(A->scene->geom_version != A->dscene.geom_version) { /* geometry changed: buffer sizes change too */
+        GPURT_CUDA(cudaStreamSynchronize(A->ctx->stream));
+        free_accel_device(A);
+    }
+    int rc = build_accel_device(A);
+    if(rc == GPURT_OK && A->depth > 60) rc = (set_error("wide BVH deeper than the traversal stack"), GPURT_E_STATE);
+    return rc;
 }
 int gpurt_accel_destroy(gpurt_accel* A) {
     if(!A) return GPURT_OK;

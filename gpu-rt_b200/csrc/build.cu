@@ -48,45 +48,46 @@ static inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) 
 /* ---- exclusive scan ---------------------------------------------------------------------------- */
 constexpr int SCAN_T = 256, SCAN_I = 8, SCAN_TILE = SCAN_T * SCAN_I;
 
-__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t& total) {
-    __shared__ uint32_t wsum[SCAN_T / 32];
+/* T = uint32_t, or uint64_t holding two 32-bit counters that are scanned together */
+template <typename T> __device__ __forceinline__ T block_exclusive_scan(T v, T& total) {
+    __shared__ T wsum[SCAN_T / 32];
     int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    uint32_t inc = v;
+    T inc = v;
 #pragma unroll
     for(int o = 1; o < 32; o <<= 1) {
-        uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        T t = __shfl_up_sync(0xffffffffu, inc, o);
         if(lane >= o) inc += t;
     }
     if(lane == 31) wsum[w] = inc;
     __syncthreads();
     if(w == 0) {
-        uint32_t s = lane < SCAN_T / 32 ? wsum[lane] : 0;
+        T s = lane < SCAN_T / 32 ? wsum[lane] : 0;
 #pragma unroll
         for(int o = 1; o < SCAN_T / 32; o <<= 1) {
-            uint32_t t = __shfl_up_sync(0xffffffffu, s, o);
+            T t = __shfl_up_sync(0xffffffffu, s, o);
             if(lane >= o) s += t;
         }
         if(lane < SCAN_T / 32) wsum[lane] = s;
     }
     __syncthreads();
-    uint32_t base = w ? wsum[w - 1] : 0;
+    T base = w ? wsum[w - 1] : 0;
     total = wsum[SCAN_T / 32 - 1];
     __syncthreads();
     return base + inc - v;
 }
 
-__global__ void __launch_bounds__(SCAN_T) k_scan_local(const uint32_t* __restrict__ in,
-                                                       uint32_t* __restrict__ out, size_t n,
-                                                       uint32_t* __restrict__ sums) {
+template <typename T>
+__global__ void __launch_bounds__(SCAN_T) k_scan_local(const T* __restrict__ in, T* __restrict__ out, size_t n,
+                                                       T* __restrict__ sums) {
     size_t base = (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * SCAN_I;
-    uint32_t v[SCAN_I], s = 0;
+    T v[SCAN_I], s = 0;
 #pragma unroll
     for(int i = 0; i < SCAN_I; i++) {
         v[i] = base + i < n ? in[base + i] : 0;
         s += v[i];
     }
-    uint32_t total;
-    uint32_t ex = block_exclusive_scan(s, total);
+    T total;
+    T ex = block_exclusive_scan<T>(s, total);
 #pragma unroll
     for(int i = 0; i < SCAN_I; i++) {
         if(base + i < n) out[base + i] = ex;
@@ -94,7 +95,7 @@ __global__ void __launch_bounds__(SCAN_T) k_scan_local(const uint32_t* __restric
     }
     if(threadIdx.x == 0) sums[blockIdx.x] = total;
 }
-__global__ void k_scan_add(uint32_t* __restrict__ out, size_t n, const uint32_t* __restrict__ offs) {
+template <typename T> __global__ void k_scan_add(T* __restrict__ out, size_t n, const T* __restrict__ offs) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if(i < n) out[i] += offs[i / SCAN_TILE];
 }
@@ -103,18 +104,18 @@ size_t scan_tmp_bytes(size_t n) {
     size_t total = 0;
     while(n > 1) {
         n = (n + SCAN_TILE - 1) / SCAN_TILE;
-        total += (n + 1) * sizeof(uint32_t);
+        total += (n + 1) * sizeof(uint64_t);
     }
     return total + 64;
 }
 
-static int scan_rec(cudaStream_t st, const uint32_t* in, uint32_t* out, size_t n, uint32_t* tmp) {
+template <typename T> static int scan_rec(cudaStream_t st, const T* in, T* out, size_t n, T* tmp) {
     unsigned nb = cdiv(n, SCAN_TILE);
-    k_scan_local<<<nb, SCAN_T, 0, st>>>(in, out, n, tmp);
+    k_scan_local<T><<<nb, SCAN_T, 0, st>>>(in, out, n, tmp);
     if(nb > 1) {
-        int rc = scan_rec(st, tmp, tmp, nb, tmp + nb + 1);
+        int rc = scan_rec<T>(st, tmp, tmp, nb, tmp + nb + 1);
         if(rc) return rc;
-        k_scan_add<<<cdiv(n, 256), 256, 0, st>>>(out, n, tmp);
+        k_scan_add<T><<<cdiv(n, 256), 256, 0, st>>>(out, n, tmp);
     }
     GPURT_CUDA(cudaGetLastError());
     return GPURT_OK;
@@ -125,7 +126,7 @@ int exclusive_scan_u32(cudaStream_t st, const uint32_t* in, uint32_t* out, size_
     if(n == 0) return GPURT_OK;
     int rc = tmp.reserve(scan_tmp_bytes(n));
     if(rc) return rc;
-    return scan_rec(st, in, out, n, tmp.as<uint32_t>());
+    return scan_rec<uint32_t>(st, in, out, n, tmp.as<uint32_t>());
 }
 
 /* ---- radix sort ------------------------------------------------------------------------------- */
@@ -214,7 +215,7 @@ int radix_sort_u64(cudaStream_t st, uint64_t* keys, uint32_t* vals, uint64_t* kt
     for(int p = 0; p < passes; p++) {
         int shift = 8 * p;
         k_rs_hist<<<nb, RS_T, 0, st>>>(keys, n, shift, hist, nb);
-        rc = scan_rec(st, hist, hist, hist_n, stmp);
+        rc = scan_rec<uint32_t>(st, hist, hist, hist_n, stmp);
         if(rc) return rc;
         k_rs_scatter<<<nb, RS_T, 0, st>>>(keys, vals, kt, vt, n, shift, hist, nb);
         uint64_t* a = keys;
@@ -246,13 +247,15 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
-/* N1: world = model * vec4(v,1) evaluated as fma(m0,x, fma(m4,y, fma(m8,z, m12))) */
+/* N1: world = model * vec4(v,1) evaluated as fma(m0,x, fma(m4,y, fma(m8,z, m12))).
+ * Grid-stride over the triangles; the scene box is reduced per thread, per warp, per block and only then
+ * with 6 atomics per block (the first version issued 6 same-address atomics per warp: 1.9 ms of the
+ * 10 M-triangle build). */
 __global__ void __launch_bounds__(256) k_flatten(DeviceScene S, float4* __restrict__ tri,
                                                  float4* __restrict__ tlo, float4* __restrict__ thi,
                                                  float* __restrict__ scene_box) {
-    unsigned gid = blockIdx.x * blockDim.x + threadIdx.x;
     float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
-    if(gid < S.n_tris) {
+    for(unsigned gid = blockIdx.x * blockDim.x + threadIdx.x; gid < S.n_tris; gid += gridDim.x * blockDim.x) {
         /* object of this triangle: last o with tri_off[o] <= gid */
         unsigned a = 0, b = S.n_objs;
         while(b - a > 1) {
@@ -261,36 +264,44 @@ __global__ void __launch_bounds__(256) k_flatten(DeviceScene S, float4* __restri
         }
         unsigned obj = a, prim = gid - S.tri_off[obj];
         const float* m = reinterpret_cast<const float*>(S.descs + obj); /* model is the first member */
-        const Vertex* vb = S.verts + S.vert_off[obj];
-        float w[3][3];
+        const float4* vb = reinterpret_cast<const float4*>(S.verts + S.vert_off[obj]); /* 3 x float4 per vertex */
+        float w[3][3], tl[3], th[3];
 #pragma unroll
         for(int k = 0; k < 3; k++) {
-            const Vertex& v = vb[S.idx[3ull * gid + k]];
-            float x = v.pos[0], y = v.pos[1], z = v.pos[2];
+            float4 v = vb[3ull * S.idx[3ull * gid + k]]; /* pos.xyz | u */
+            float x = v.x, y = v.y, z = v.z;
             w[k][0] = fmaf(m[0], x, fmaf(m[4], y, fmaf(m[8], z, m[12])));
             w[k][1] = fmaf(m[1], x, fmaf(m[5], y, fmaf(m[9], z, m[13])));
             w[k][2] = fmaf(m[2], x, fmaf(m[6], y, fmaf(m[10], z, m[14])));
         }
 #pragma unroll
         for(int c = 0; c < 3; c++) {
-            lo[c] = fminf(fminf(w[0][c], w[1][c]), w[2][c]);
-            hi[c] = fmaxf(fmaxf(w[0][c], w[1][c]), w[2][c]);
+            tl[c] = fminf(fminf(w[0][c], w[1][c]), w[2][c]);
+            th[c] = fmaxf(fmaxf(w[0][c], w[1][c]), w[2][c]);
+            lo[c] = fminf(lo[c], tl[c]);
+            hi[c] = fmaxf(hi[c], th[c]);
         }
         tri[3ull * gid + 0] = make_float4(w[0][0], w[0][1], w[0][2], __uint_as_float(gid));
         tri[3ull * gid + 1] = make_float4(w[1][0] - w[0][0], w[1][1] - w[0][1], w[1][2] - w[0][2],
                                           __uint_as_float(obj));
         tri[3ull * gid + 2] = make_float4(w[2][0] - w[0][0], w[2][1] - w[0][1], w[2][2] - w[0][2],
                                           __uint_as_float(prim));
-        tlo[gid] = make_float4(lo[0], lo[1], lo[2], 0.0f);
-        thi[gid] = make_float4(hi[0], hi[1], hi[2], 0.0f);
+        tlo[gid] = make_float4(tl[0], tl[1], tl[2], 0.0f);
+        thi[gid] = make_float4(th[0], th[1], th[2], 0.0f);
     }
+    __shared__ float red[6][8];
 #pragma unroll
     for(int c = 0; c < 3; c++) {
         float l = warp_min(lo[c]), h = warp_max(hi[c]);
-        if((threadIdx.x & 31) == 0) {
-            if(l < 3.0e38f) atomic_min_f(scene_box + c, l);
-            if(h > -3.0e38f) atomic_max_f(scene_box + 3 + c, h);
-        }
+        if((threadIdx.x & 31) == 0) red[c][threadIdx.x >> 5] = l, red[3 + c][threadIdx.x >> 5] = h;
+    }
+    __syncthreads();
+    if(threadIdx.x < 6) {
+        const int c = threadIdx.x;
+        float v = red[c][0];
+        for(int k = 1; k < 8; k++) v = c < 3 ? fminf(v, red[c][k]) : fmaxf(v, red[c][k]);
+        if(c < 3) { if(v < 3.0e38f) atomic_min_f(scene_box + c, v); }
+        else if(v > -3.0e38f) atomic_max_f(scene_box + c, v);
     }
 }
 
@@ -374,22 +385,20 @@ __global__ void __launch_bounds__(256) k_refit(int n, const int* __restrict__ le
 /* ---- collapse --------------------------------------------------------------------------------- */
 __global__ void __launch_bounds__(128) k_collapse_count(Bvh2View B, const int* __restrict__ items,
                                                         unsigned n_items, int* __restrict__ children,
-                                                        uint32_t* __restrict__ n_inner,
-                                                        uint32_t* __restrict__ n_tris) {
+                                                        uint64_t* __restrict__ counts /* inner | tris << 32 */) {
     unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i == 0) counts[n_items] = 0; /* the exclusive scan leaves the level totals here */
     if(i >= n_items) return;
     int ch[8], nt;
     int ni = collapse_node(B, items[i], ch, nt);
 #pragma unroll
     for(int s = 0; s < 8; s++) children[8ull * i + s] = ch[s];
-    n_inner[i] = (uint32_t)ni;
-    n_tris[i] = (uint32_t)nt;
+    counts[i] = (uint64_t)(uint32_t)ni | ((uint64_t)(uint32_t)nt << 32);
 }
 
 __global__ void __launch_bounds__(128) k_collapse_emit(Bvh2View B, unsigned n_items,
                                                        const int* __restrict__ children,
-                                                       const uint32_t* __restrict__ off_inner,
-                                                       const uint32_t* __restrict__ off_tris,
+                                                       const uint64_t* __restrict__ offsets,
                                                        unsigned level_base, unsigned next_base,
                                                        unsigned tri_cursor, Node8* __restrict__ nodes,
                                                        int* __restrict__ next_items,
@@ -400,8 +409,10 @@ __global__ void __launch_bounds__(128) k_collapse_emit(Bvh2View B, unsigned n_it
     int ch[8];
 #pragma unroll
     for(int s = 0; s < 8; s++) ch[s] = children[8ull * i + s];
-    unsigned child_base = next_base + off_inner[i];
-    unsigned tri_base = tri_cursor + off_tris[i];
+    const uint64_t off = offsets[i];
+    const unsigned off_inner = (unsigned)off;
+    unsigned child_base = next_base + off_inner;
+    unsigned tri_base = tri_cursor + (unsigned)(off >> 32);
     Node8 node;
     encode_node(B, ch, child_base, tri_base, node);
     Node8* dst = nodes + (level_base + i);
@@ -411,7 +422,7 @@ __global__ void __launch_bounds__(128) k_collapse_emit(Bvh2View B, unsigned n_it
     for(int s = 0; s < 8; s++) {
         int c = ch[s];
         if(c == kEmptyChild) continue;
-        if(c >= 0) next_items[off_inner[i] + r++] = c;
+        if(c >= 0) next_items[off_inner + r++] = c;
         else {
             unsigned first, count;
             decode_leaf_range(c, first, count);
@@ -455,6 +466,8 @@ template <typename T> static int dmalloc(T*& p, size_t count) {
         GPURT_CUDA(cudaMallocAsync((void**)&p, bytes, t_alloc_stream));
     return GPURT_OK;
 }
+/* buffers the accel keeps: allocated on the first build, reused by gpurt_accel_update */
+template <typename T> static int dkeep(T*& p, size_t count) { return p ? GPURT_OK : dmalloc(p, count); }
 static inline void dfree(void* p) {
     if(!p) return;
     for(size_t i = 0; i < t_big_allocs.size(); i++)
@@ -496,25 +509,25 @@ int build_accel_device(gpurt_accel* A) {
     GPURT_CUDA(cudaEventCreate(&e1));
     GPURT_CUDA(cudaEventRecord(e0, st));
 
-    TRY(dmalloc(A->tri_gid, 3ull * n));
-    TRY(dmalloc(A->tri_lo, n));
-    TRY(dmalloc(A->tri_hi, n));
-    TRY(dmalloc(A->keys, n));
-    TRY(dmalloc(A->order, n));
-    TRY(dmalloc(A->tri_wide, 3ull * n));
+    TRY(dkeep(A->tri_gid, 3ull * n));
+    TRY(dkeep(A->tri_lo, n));
+    TRY(dkeep(A->tri_hi, n));
+    TRY(dkeep(A->keys, n));
+    TRY(dkeep(A->order, n));
+    TRY(dkeep(A->tri_wide, 3ull * n));
 
     float* d_box = nullptr;
     TRY(dmalloc(d_box, 6));
     float init[6] = {3.0e38f, 3.0e38f, 3.0e38f, -3.0e38f, -3.0e38f, -3.0e38f};
     GPURT_CUDA(cudaMemcpyAsync(d_box, init, sizeof(init), cudaMemcpyHostToDevice, st));
-    if(n) k_flatten<<<cdiv(n, 256), 256, 0, st>>>(A->dscene, A->tri_gid, A->tri_lo, A->tri_hi, d_box);
+    if(n) k_flatten<<<std::min(cdiv(n, 256), (unsigned)ctx->sm_count * 16u), 256, 0, st>>>(A->dscene, A->tri_gid, A->tri_lo, A->tri_hi, d_box);
     GPURT_CUDA(cudaMemcpyAsync(A->scene_box, d_box, sizeof(init), cudaMemcpyDeviceToHost, st));
     GPURT_CUDA(cudaStreamSynchronize(st));
     dfree(d_box);
     if(n == 0) {
         for(float& f : A->scene_box) f = 0;
         A->n_nodes = 0, A->depth = 0;
-        TRY(dmalloc(A->nodes, 1));
+        TRY(dkeep(A->nodes, 1));
         cudaEventDestroy(e0), cudaEventDestroy(e1);
         return GPURT_OK;
     }
@@ -538,13 +551,13 @@ int build_accel_device(gpurt_accel* A) {
 
     /* binary tree */
     const unsigned ni = n > 1 ? n - 1 : 0;
-    TRY(dmalloc(A->left, ni));
-    TRY(dmalloc(A->right, ni));
-    TRY(dmalloc(A->parent, (size_t)ni + n));
-    TRY(dmalloc(A->range_first, ni));
-    TRY(dmalloc(A->range_last, ni));
-    TRY(dmalloc(A->node_lo, ni));
-    TRY(dmalloc(A->node_hi, ni));
+    TRY(dkeep(A->left, ni));
+    TRY(dkeep(A->right, ni));
+    TRY(dkeep(A->parent, (size_t)ni + n));
+    TRY(dkeep(A->range_first, ni));
+    TRY(dkeep(A->range_last, ni));
+    TRY(dkeep(A->node_lo, ni));
+    TRY(dkeep(A->node_hi, ni));
     unsigned* arrive = (unsigned*)vals_tmp; /* reuse */
     if(ni) {
         GPURT_CUDA(cudaMemsetAsync(arrive, 0, (size_t)ni * 4, st));
@@ -563,37 +576,31 @@ int build_accel_device(gpurt_accel* A) {
     /* wide collapse. Upper bound on wide nodes: every inner node owns > kMaxLeafTris triangles and
      * has >= 2 children, so there are fewer than n/2 of them. */
     size_t max_nodes = (size_t)n / 2 + 2;
-    TRY(dmalloc(A->nodes, max_nodes));
+    TRY(dkeep(A->nodes, max_nodes));
     if(n <= (unsigned)kMaxLeafTris) {
         k_single_leaf<<<1, 32, 0, st>>>(B, n, A->nodes, A->tri_gid, A->tri_wide);
         A->n_nodes = 1, A->depth = 1;
     } else {
         size_t max_items = max_nodes;
         int *items_a = nullptr, *items_b = nullptr, *children = nullptr;
-        uint32_t *cnt_i = nullptr, *cnt_t = nullptr;
+        uint64_t* cnt = nullptr;
         TRY(dmalloc(items_a, max_items));
         TRY(dmalloc(items_b, max_items));
         TRY(dmalloc(children, 8 * max_items));
-        TRY(dmalloc(cnt_i, max_items + 1));
-        TRY(dmalloc(cnt_t, max_items + 1));
+        TRY(dmalloc(cnt, max_items + 1));
         int root = 0;
         GPURT_CUDA(cudaMemcpyAsync(items_a, &root, 4, cudaMemcpyHostToDevice, st));
         unsigned n_items = 1, level_base = 0, tri_cursor = 0, depth = 0;
         DevBuf scan_tmp;
         TRY(scan_tmp.reserve(scan_tmp_bytes(max_items + 1)));
         while(n_items) {
-            k_collapse_count<<<cdiv(n_items, 128), 128, 0, st>>>(B, items_a, n_items, children, cnt_i, cnt_t);
-            GPURT_CUDA(cudaMemsetAsync(cnt_i + n_items, 0, 4, st));
-            GPURT_CUDA(cudaMemsetAsync(cnt_t + n_items, 0, 4, st));
-            TRY(scan_rec(st, cnt_i, cnt_i, n_items + 1, scan_tmp.as<uint32_t>()));
-            TRY(scan_rec(st, cnt_t, cnt_t, n_items + 1, scan_tmp.as<uint32_t>()));
+            k_collapse_count<<<cdiv(n_items, 128), 128, 0, st>>>(B, items_a, n_items, children, cnt);
+            TRY(scan_rec<uint64_t>(st, cnt, cnt, n_items + 1, scan_tmp.as<uint64_t>()));
             unsigned next_base = level_base + n_items;
-            k_collapse_emit<<<cdiv(n_items, 128), 128, 0, st>>>(B, n_items, children, cnt_i, cnt_t,
-                                                               level_base, next_base, tri_cursor,
-                                                               A->nodes, items_b, A->tri_gid, A->tri_wide);
-            uint32_t tot[2];
-            GPURT_CUDA(cudaMemcpyAsync(&tot[0], cnt_i + n_items, 4, cudaMemcpyDeviceToHost, st));
-            GPURT_CUDA(cudaMemcpyAsync(&tot[1], cnt_t + n_items, 4, cudaMemcpyDeviceToHost, st));
+            k_collapse_emit<<<cdiv(n_items, 128), 128, 0, st>>>(B, n_items, children, cnt, level_base, next_base,
+                                                               tri_cursor, A->nodes, items_b, A->tri_gid, A->tri_wide);
+            uint32_t tot[2]; /* {inner children, triangles} emitted by this level */
+            GPURT_CUDA(cudaMemcpyAsync(tot, cnt + n_items, 8, cudaMemcpyDeviceToHost, st));
             GPURT_CUDA(cudaStreamSynchronize(st));
             level_base = next_base;
             tri_cursor += tot[1];
@@ -609,7 +616,7 @@ int build_accel_device(gpurt_accel* A) {
         A->n_nodes = level_base;
         A->depth = depth;
         scan_tmp.release();
-        dfree(items_a), dfree(items_b), dfree(children), dfree(cnt_i), dfree(cnt_t);
+        dfree(items_a), dfree(items_b), dfree(children), dfree(cnt);
         if(tri_cursor != n) {
             set_error("collapse lost triangles: " + std::to_string(tri_cursor) + " of " + std::to_string(n));
             return GPURT_E_STATE;

@@ -65,7 +65,7 @@ struct DeviceScene {
     SceneDesc* descs = nullptr;
     SceneLight* lights = nullptr;
     uint32_t n_objs = 0, n_tris = 0, n_lights = 0, n_verts = 0;
-    uint64_t version = 0;
+    uint64_t version = 0, geom_version = 0;
     /* textures: RGBA8 texels, one allocation, per-texture (offset,w,h) table */
     uint8_t* texels = nullptr;
     uint4* tex_info = nullptr; /* x: texel offset, y: w, z: h */

@@ -90,7 +90,7 @@ SYMBOLS = [
     "gpurt_pipe_render_frame", "gpurt_pipe_frame_index", "gpurt_pipe_read_image", "gpurt_pipe_read_gbuffer",
     "gpurt_pipe_ray_counts", "gpurt_pipe_device_image", "gpurt_tonemap", "gpurt_pipe_last_uniforms",
     "gpurt_pipe_read_reservoirs", "gpurt_pipe_bounce_rays", "gpurt_pipe_set_shard",
-    "gpurt_shared_alloc", "gpurt_shared_free", "gpurt_shared_open", "gpurt_shared_close",
+    "gpurt_scene_set_transform", "gpurt_accel_update", "gpurt_shared_alloc", "gpurt_shared_free", "gpurt_shared_open", "gpurt_shared_close",
 ]
 
 
@@ -232,6 +232,11 @@ class Scene:
                                           C.byref(material) if material is not None else None, C.byref(out)))
         return out.value
 
+    def set_transform(self, obj, model16):
+        """pose edit of object `obj` (for_objs index); follow with Accel.update()"""
+        model = np.ascontiguousarray(model16, np.float32).reshape(16)
+        _check(lib.gpurt_scene_set_transform(self.h, int(obj), C.c_void_p(model.ctypes.data)))
+
     def add_triangles(self, tris9, material=None):
         """convenience: (n,9) world-space triangle soup as one object with identity model"""
         tris9 = np.ascontiguousarray(tris9, np.float32).reshape(-1, 3, 3)
@@ -310,6 +315,10 @@ class Accel:
         self.ctx = scene.ctx
         self.h = C.c_void_p()
         _check(lib.gpurt_accel_build(scene.h, flags, C.byref(self.h)))
+
+    def update(self):
+        """rebuild after scene edits (GPURT::build_accel, src/gpurt.cpp:220-241)"""
+        _check(lib.gpurt_accel_update(self.h))
 
     def info(self):
         i = AccelInfo()

@@ -37,6 +37,7 @@ bool gpurt_scene::pack() {
     }
     dirty = false;
     version++;
+    geom_version++;
     return true;
 }
 
@@ -108,6 +109,18 @@ int gpurt_scene_add_object(gpurt_scene* s, const void* verts48, uint32_t nv, con
             k++;
         });
         *out = found;
+    }
+    return GPURT_OK;
+}
+int gpurt_scene_set_transform(gpurt_scene* s, uint32_t obj, const float model[16]) {
+    if(!s || !model) return set_error("NULL argument"), GPURT_E_INVALID;
+    Object* o = s->scene.at_index(obj);
+    if(!o) return set_error("object index out of range"), GPURT_E_INVALID;
+    o->has_model = true;
+    std::memcpy(o->model.data(), model, 64);
+    if(!s->dirty) { /* geometry already packed: only Scene_Desc / Scene_Light change (rt.cpp:26-76) */
+        s->scene.build_desc(s->packed.descs, s->packed.lights);
+        s->version++;
     }
     return GPURT_OK;
 }

@@ -30,7 +30,8 @@ struct gpurt_scene {
     gpurt::Scene scene;
     gpurt::PackedScene packed;
     bool dirty = true;
-    uint64_t version = 0;
+    uint64_t version = 0;      /* bumps on every change of `packed` */
+    uint64_t geom_version = 0; /* bumps only when geometry / textures were repacked (not on pose changes) */
     std::string label = "custom";
     /* (re)build `packed` from `scene`; returns false (with error set) on invalid indices */
     bool pack();

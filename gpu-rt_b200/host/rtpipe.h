@@ -57,6 +57,8 @@ public:
     ~Accel() { gpurt_accel_destroy(h); }
     Accel(const Accel&) = delete;
     Accel& operator=(const Accel&) = delete;
+    /* GPURT::build_accel after edit_scene (src/gpurt.cpp:220-241, :378-385) */
+    void update() { check(gpurt_accel_update(h)); }
     GpurtAccelInfo info() const {
         GpurtAccelInfo i;
         check(gpurt_accel_info(h, &i));

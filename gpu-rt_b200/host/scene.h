@@ -87,6 +87,13 @@ public:
         for(auto& o : objs) f(o.second);
     }
 
+    /* k-th object in for_objs order (the obj_id the shaders see), or nullptr */
+    Object* at_index(size_t k) {
+        for(auto& o : objs)
+            if(k-- == 0) return &o.second;
+        return nullptr;
+    }
+
     /* RTPipe::build_desc, src/vk/rt.cpp:26-76 */
     void build_desc(std::vector<SceneDesc>& descs, std::vector<SceneLight>& lights) const;
 

@@ -170,6 +170,9 @@ int gpurt_scene_make_sponza_standin(gpurt_scene* scene);
 int gpurt_scene_add_object(gpurt_scene* scene, const void* verts48, uint32_t n_verts,
                            const uint32_t* indices, uint32_t n_indices, const float model[16],
                            const GpurtMaterial* material, uint32_t* out_obj_index);
+/* Pose edit (GPURT::edit_scene -> rebuild_tlas, src/gpurt.cpp:286-289, :378-385): replaces the model
+ * matrix of object `obj` (index in Scene::for_objs order).  Follow with gpurt_accel_update(). */
+int gpurt_scene_set_transform(gpurt_scene* scene, uint32_t obj, const float model[16]);
 /* RTPipe::build_textures (src/vk/rt.cpp:430-455): RGBA8, sampled as sRGB, linear, repeat. */
 int gpurt_scene_add_texture(gpurt_scene* scene, const uint8_t* rgba8, uint32_t w, uint32_t h,
                             int32_t* out_tex_index);
@@ -196,6 +199,11 @@ int gpurt_camera_make(int mode, float width, float height, const float pos[3],
 #define GPURT_BUILD_DEFAULT 0u
 #define GPURT_BUILD_KEEP_BVH2 1u /* keep the binary LBVH for gpurt_accel_get_bvh2 / debug trace */
 int gpurt_accel_build(gpurt_scene* scene, uint32_t flags, gpurt_accel** out);
+/* Rebuild after scene edits (GPURT::build_accel with rebuild_tlas / rebuild_blas, src/gpurt.cpp:220-241).
+ * Pose-only edits re-upload the 208-byte Scene_Desc records and rebuild on the device in the buffers
+ * the accel already owns (no geometry upload, no allocation); geometry edits fall back to a full build.
+ * Pipes created on this accel stay valid (call gpurt_pipe_reset_frame, like GPURT::build_accel does). */
+int gpurt_accel_update(gpurt_accel* accel);
 int gpurt_accel_destroy(gpurt_accel* accel);
 int gpurt_accel_info(const gpurt_accel* accel, GpurtAccelInfo* out);
 /* Canonical primitive order (sorted Morton position -> global prim id), host buffers. */

@@ -57,6 +57,18 @@ def make_soup(n, device):
     return torch.stack([c, c + e1, c + e2], 1).reshape(n, 9).contiguous()
 
 
+def make_grid(side, device):
+    """coherent variant: height field over side x side vertices, z = 0.05 sin(8 pi x) cos(8 pi y);
+    side 2237 gives 9,999,392 triangles"""
+    u = torch.arange(side, dtype=torch.float32, device=device) / (side - 1)
+    x, y = torch.meshgrid(u, u, indexing="ij")
+    z = 0.05 * torch.sin(8 * torch.pi * x) * torch.cos(8 * torch.pi * y)
+    v = torch.stack([x, y, z], -1)
+    a, b, c, d = v[:-1, :-1], v[1:, :-1], v[:-1, 1:], v[1:, 1:]
+    t = torch.stack([torch.stack([a, b, c], -2), torch.stack([b, d, c], -2)], 2)   # (s-1, s-1, 2, 3, 3)
+    return t.reshape(-1, 9).contiguous()
+
+
 def make_queries(a, b, device):
     """query i: s = tea(i, 0xD00D); uniform in [-0.25,1.25]^3, r2 = +inf"""
     i = torch.arange(a, b, dtype=torch.int64, device=device)
@@ -73,6 +85,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--tris", type=int, default=10_000_000)
     ap.add_argument("--queries", type=int, default=100_000_000)
+    ap.add_argument("--mesh", choices=["soup", "grid"], default="soup", help="grid = coherent height field (2237^2 vertices)")
     ap.add_argument("--chunk", type=int, default=12_500_000)
     ap.add_argument("--check", type=int, default=200_000)
     ap.add_argument("--gather", action="store_true", help="NCCL gather of the results to rank 0 after the queries")
@@ -88,7 +101,7 @@ def main():
     ctx = gpurt.Context(local)
     ctx.use_torch_stream()
 
-    tris = make_soup(args.tris, dev)
+    tris = make_soup(args.tris, dev) if args.mesh == "soup" else make_grid(int(round((args.tris / 2) ** 0.5)) + 1, dev)
     tris_h = tris.cpu().numpy()
     del tris
     scene = gpurt.Scene(ctx)
@@ -158,7 +171,7 @@ def main():
                  "oracle_s": round(time.time() - t1, 1)}
     if rank == 0:
         print(json.dumps({
-            "config": "synthetic CPQ (SURVEY config 4)", "n_gpus": world, "tris": info.n_tris, "queries": int(tot.item()),
+            "config": f"synthetic CPQ (SURVEY config 4, {args.mesh})", "n_gpus": world, "tris": info.n_tris, "queries": int(tot.item()),
             "mqueries_s": tot.item() / (t.item() * 1e-3) / 1e6, "kernel_ms_max_rank": t.item(),
             "bvh_build_ms_device": info.build_ms, "bvh_build_s_wall_incl_upload": round(t_build_wall, 2),
             "build_mtris_s": info.n_tris / (info.build_ms * 1e-3) / 1e6, "wide_nodes": info.n_wide_nodes,

@@ -153,8 +153,7 @@ int gpurt_ctx_destroy(gpurt_ctx* c) {
     if(!c) return GPURT_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    c->d_in.release(), c->d_out.release(), c->scratch.release();
-    c->h_in.release(), c->h_out.release();
+    c->d_in.release(), c->d_out.release(), c->scratch.release(), c->build_arena.release();
     cudaEventDestroy(c->ev0), cudaEventDestroy(c->ev1), cudaEventDestroy(c->ev_copy), cudaEventDestroy(c->ev_kernel);
     cudaStreamDestroy(c->s_h2d), cudaStreamDestroy(c->s_d2h);
     cudaStreamDestroy(c->own_stream);

@@ -30,19 +30,6 @@ void DevBuf::release() {
     if(p) cudaFree(p);
     p = nullptr, cap = 0;
 }
-int PinBuf::reserve(size_t bytes) {
-    if(bytes <= cap) return GPURT_OK;
-    if(p) cudaFreeHost(p);
-    p = nullptr, cap = 0;
-    GPURT_CUDA(cudaMallocHost(&p, bytes));
-    cap = bytes;
-    return GPURT_OK;
-}
-void PinBuf::release() {
-    if(p) cudaFreeHost(p);
-    p = nullptr, cap = 0;
-}
-
 static inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
 
 /* ---- exclusive scan ---------------------------------------------------------------------------- */
@@ -449,35 +436,29 @@ __global__ void k_single_leaf(Bvh2View B, unsigned n, Node8* nodes, const float4
 }
 
 /* ---- orchestration ---------------------------------------------------------------------------- */
-/* Small buffers come from the device's stream-ordered pool (no device-wide synchronisation per buffer,
- * memory of a previous build is reused: 262 k triangles build in 1.4 ms instead of 7 ms); buffers of
- * 32 MB and more use plain cudaMalloc, which is faster than growing the pool for a one-off 10 M-triangle
- * build (15 ms vs 325 ms). */
+/* Buffers the accel keeps (allocated by the first build, reused by gpurt_accel_update): small ones come
+ * from the device's stream-ordered pool, which keeps freed memory cached (a second build of a 262 k-triangle
+ * scene finds all of them there), buffers of 32 MB and more use plain cudaMalloc, which is faster than
+ * growing the pool for a one-off 10 M-triangle build.  Build temporaries are carved from one arena
+ * owned by the context (grown on demand, never shrunk): no allocation call at all in a rebuild. */
 static thread_local cudaStream_t t_alloc_stream = nullptr;
-static thread_local std::vector<void*> t_big_allocs;
-template <typename T> static int dmalloc(T*& p, size_t count) {
-    p = nullptr;
-    if(count == 0) count = 1;
-    size_t bytes = count * sizeof(T);
-    if(bytes >= (32u << 20)) {
-        GPURT_CUDA(cudaMalloc((void**)&p, bytes));
-        t_big_allocs.push_back(p);
-    } else
-        GPURT_CUDA(cudaMallocAsync((void**)&p, bytes, t_alloc_stream));
+template <typename T> static int dkeep(T*& p, size_t count) {
+    if(p) return GPURT_OK;
+    size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+    if(bytes >= (32u << 20)) GPURT_CUDA(cudaMalloc((void**)&p, bytes));
+    else GPURT_CUDA(cudaMallocAsync((void**)&p, bytes, t_alloc_stream));
     return GPURT_OK;
 }
-/* buffers the accel keeps: allocated on the first build, reused by gpurt_accel_update */
-template <typename T> static int dkeep(T*& p, size_t count) { return p ? GPURT_OK : dmalloc(p, count); }
-static inline void dfree(void* p) {
-    if(!p) return;
-    for(size_t i = 0; i < t_big_allocs.size(); i++)
-        if(t_big_allocs[i] == p) {
-            t_big_allocs.erase(t_big_allocs.begin() + i);
-            cudaFree(p);
-            return;
-        }
-    cudaFreeAsync(p, t_alloc_stream);
-}
+struct Arena {
+    char* base = nullptr;
+    size_t used = 0, cap = 0;
+    template <typename T> T* take(size_t count) {
+        size_t bytes = (std::max<size_t>(count, 1) * sizeof(T) + 255) & ~(size_t)255;
+        T* p = (T*)(base + used);
+        used += bytes;
+        return used <= cap ? p : nullptr;
+    }
+};
 #define TRY(x)                                                                                     \
     do {                                                                                           \
         int rc_ = (x);                                                                             \
@@ -485,13 +466,13 @@ static inline void dfree(void* p) {
     } while(0)
 
 void free_accel_device(gpurt_accel* A) {
-    void* ptrs[] = {A->tri_gid, A->tri_lo, A->tri_hi, A->keys, A->order, A->left, A->right, A->parent,
-                    A->range_first, A->range_last, A->node_lo, A->node_hi, A->nodes, A->tri_wide};
+    void* ptrs[] = {A->tri_gid, A->tri_lo, A->tri_hi, A->keys, A->order, A->left, A->right,
+                    A->node_lo, A->node_hi, A->nodes, A->tri_wide};
     for(void* p : ptrs)
         if(p) cudaFree(p);
     A->tri_gid = A->tri_lo = A->tri_hi = A->node_lo = A->node_hi = A->tri_wide = nullptr;
     A->keys = nullptr, A->order = nullptr, A->nodes = nullptr;
-    A->left = A->right = A->parent = A->range_first = A->range_last = nullptr;
+    A->left = A->right = nullptr;
     free_scene(A->dscene);
 }
 
@@ -500,14 +481,11 @@ int build_accel_device(gpurt_accel* A) {
     cudaStream_t st = ctx->stream;
     GPURT_CUDA(cudaSetDevice(ctx->device));
     t_alloc_stream = st;
-    t_big_allocs.clear();
     TRY(upload_scene(ctx, A->scene, A->dscene));
     const unsigned n = A->dscene.n_tris;
+    const unsigned ni = n > 1 ? n - 1 : 0;
+    const size_t max_nodes = (size_t)n / 2 + 2; /* every inner wide node owns > kMaxLeafTris triangles, >= 2 children */
     A->n = n;
-    cudaEvent_t e0, e1;
-    GPURT_CUDA(cudaEventCreate(&e0));
-    GPURT_CUDA(cudaEventCreate(&e1));
-    GPURT_CUDA(cudaEventRecord(e0, st));
 
     TRY(dkeep(A->tri_gid, 3ull * n));
     TRY(dkeep(A->tri_lo, n));
@@ -515,19 +493,44 @@ int build_accel_device(gpurt_accel* A) {
     TRY(dkeep(A->keys, n));
     TRY(dkeep(A->order, n));
     TRY(dkeep(A->tri_wide, 3ull * n));
+    TRY(dkeep(A->left, ni));
+    TRY(dkeep(A->right, ni));
+    TRY(dkeep(A->node_lo, ni));
+    TRY(dkeep(A->node_hi, ni));
+    TRY(dkeep(A->nodes, max_nodes));
 
-    float* d_box = nullptr;
-    TRY(dmalloc(d_box, 6));
+    /* temporaries: [box | range_first | range_last] live through the whole build; behind them phase 1
+     * (sort + tree: keys_tmp, vals_tmp / arrival counters, parent) and phase 2 (collapse: item lists,
+     * child lists, counters, scan scratch) share the same bytes */
+    const size_t pad = 256;
+    size_t fixed = 3 * pad + 2 * ((size_t)ni * 4 + pad);
+    size_t phase1 = (size_t)n * 8 + (size_t)n * 4 + ((size_t)ni + n) * 4 + 4 * pad;
+    size_t phase2 = 2 * max_nodes * 4 + 8 * max_nodes * 4 + (max_nodes + 1) * 8 + scan_tmp_bytes(max_nodes + 1) + 6 * pad;
+    TRY(ctx->build_arena.reserve(fixed + std::max(phase1, phase2)));
+    Arena ar;
+    ar.base = (char*)ctx->build_arena.p, ar.cap = ctx->build_arena.cap;
+    float* d_box = ar.take<float>(8);
+    int* range_first = ar.take<int>(ni);
+    int* range_last = ar.take<int>(ni);
+    const size_t phase_mark = ar.used;
+    uint64_t* keys_tmp = ar.take<uint64_t>(n);
+    uint32_t* vals_tmp = ar.take<uint32_t>(n);
+    int* parent = ar.take<int>((size_t)ni + n);
+    if(!parent) return set_error("build arena layout"), GPURT_E_STATE;
+
+    cudaEvent_t e0, e1;
+    GPURT_CUDA(cudaEventCreate(&e0));
+    GPURT_CUDA(cudaEventCreate(&e1));
+    GPURT_CUDA(cudaEventRecord(e0, st));
+
     float init[6] = {3.0e38f, 3.0e38f, 3.0e38f, -3.0e38f, -3.0e38f, -3.0e38f};
     GPURT_CUDA(cudaMemcpyAsync(d_box, init, sizeof(init), cudaMemcpyHostToDevice, st));
     if(n) k_flatten<<<std::min(cdiv(n, 256), (unsigned)ctx->sm_count * 16u), 256, 0, st>>>(A->dscene, A->tri_gid, A->tri_lo, A->tri_hi, d_box);
     GPURT_CUDA(cudaMemcpyAsync(A->scene_box, d_box, sizeof(init), cudaMemcpyDeviceToHost, st));
     GPURT_CUDA(cudaStreamSynchronize(st));
-    dfree(d_box);
     if(n == 0) {
         for(float& f : A->scene_box) f = 0;
-        A->n_nodes = 0, A->depth = 0;
-        TRY(dkeep(A->nodes, 1));
+        A->n_nodes = 0, A->depth = 0, A->build_ms = 0;
         cudaEventDestroy(e0), cudaEventDestroy(e1);
         return GPURT_OK;
     }
@@ -541,61 +544,43 @@ int build_accel_device(gpurt_accel* A) {
     for(int k = 0; k < 3; k++) inv[k] = ext[k] > 0 ? 1.0f / ext[k] : 0.0f;
 
     /* keys + sort */
-    uint64_t* keys_tmp = nullptr;
-    uint32_t* vals_tmp = nullptr;
-    TRY(dmalloc(keys_tmp, n));
-    TRY(dmalloc(vals_tmp, n));
     k_morton<<<cdiv(n, 256), 256, 0, st>>>(A->tri_lo, A->tri_hi, n, sb[0], sb[1], sb[2], inv[0], inv[1],
                                           inv[2], A->keys, A->order);
     TRY(radix_sort_u64(st, A->keys, A->order, keys_tmp, vals_tmp, n, 8, ctx->scratch));
 
     /* binary tree */
-    const unsigned ni = n > 1 ? n - 1 : 0;
-    TRY(dkeep(A->left, ni));
-    TRY(dkeep(A->right, ni));
-    TRY(dkeep(A->parent, (size_t)ni + n));
-    TRY(dkeep(A->range_first, ni));
-    TRY(dkeep(A->range_last, ni));
-    TRY(dkeep(A->node_lo, ni));
-    TRY(dkeep(A->node_hi, ni));
-    unsigned* arrive = (unsigned*)vals_tmp; /* reuse */
+    unsigned* arrive = (unsigned*)vals_tmp; /* the sort is done with it */
     if(ni) {
         GPURT_CUDA(cudaMemsetAsync(arrive, 0, (size_t)ni * 4, st));
-        k_karras<<<cdiv(ni, 256), 256, 0, st>>>(A->keys, (int)n, A->left, A->right, A->parent,
-                                               A->range_first, A->range_last);
-        k_refit<<<cdiv(n, 256), 256, 0, st>>>((int)n, A->left, A->right, A->parent, A->order, A->tri_lo,
+        k_karras<<<cdiv(ni, 256), 256, 0, st>>>(A->keys, (int)n, A->left, A->right, parent, range_first, range_last);
+        k_refit<<<cdiv(n, 256), 256, 0, st>>>((int)n, A->left, A->right, parent, A->order, A->tri_lo,
                                              A->tri_hi, A->node_lo, A->node_hi, arrive);
     }
     GPURT_CUDA(cudaGetLastError());
 
     Bvh2View B;
-    B.left = A->left, B.right = A->right, B.range_first = A->range_first, B.range_last = A->range_last;
+    B.left = A->left, B.right = A->right, B.range_first = range_first, B.range_last = range_last;
     B.node_lo = A->node_lo, B.node_hi = A->node_hi, B.tri_lo = A->tri_lo, B.tri_hi = A->tri_hi;
     B.order = A->order, B.inflate = A->inflate;
 
-    /* wide collapse. Upper bound on wide nodes: every inner node owns > kMaxLeafTris triangles and
-     * has >= 2 children, so there are fewer than n/2 of them. */
-    size_t max_nodes = (size_t)n / 2 + 2;
-    TRY(dkeep(A->nodes, max_nodes));
+    /* wide collapse, one level of the wide tree per iteration */
     if(n <= (unsigned)kMaxLeafTris) {
         k_single_leaf<<<1, 32, 0, st>>>(B, n, A->nodes, A->tri_gid, A->tri_wide);
         A->n_nodes = 1, A->depth = 1;
     } else {
-        size_t max_items = max_nodes;
-        int *items_a = nullptr, *items_b = nullptr, *children = nullptr;
-        uint64_t* cnt = nullptr;
-        TRY(dmalloc(items_a, max_items));
-        TRY(dmalloc(items_b, max_items));
-        TRY(dmalloc(children, 8 * max_items));
-        TRY(dmalloc(cnt, max_items + 1));
+        ar.used = phase_mark; /* phase 2 reuses the bytes of phase 1 (stream order makes that safe) */
+        int* items_a = ar.take<int>(max_nodes);
+        int* items_b = ar.take<int>(max_nodes);
+        int* children = ar.take<int>(8 * max_nodes);
+        uint64_t* cnt = ar.take<uint64_t>(max_nodes + 1);
+        uint64_t* scan_tmp = ar.take<uint64_t>(scan_tmp_bytes(max_nodes + 1) / 8 + 1);
+        if(!scan_tmp) return set_error("build arena layout"), GPURT_E_STATE;
         int root = 0;
         GPURT_CUDA(cudaMemcpyAsync(items_a, &root, 4, cudaMemcpyHostToDevice, st));
         unsigned n_items = 1, level_base = 0, tri_cursor = 0, depth = 0;
-        DevBuf scan_tmp;
-        TRY(scan_tmp.reserve(scan_tmp_bytes(max_items + 1)));
         while(n_items) {
             k_collapse_count<<<cdiv(n_items, 128), 128, 0, st>>>(B, items_a, n_items, children, cnt);
-            TRY(scan_rec<uint64_t>(st, cnt, cnt, n_items + 1, scan_tmp.as<uint64_t>()));
+            TRY(scan_rec<uint64_t>(st, cnt, cnt, n_items + 1, scan_tmp));
             unsigned next_base = level_base + n_items;
             k_collapse_emit<<<cdiv(n_items, 128), 128, 0, st>>>(B, n_items, children, cnt, level_base, next_base,
                                                                tri_cursor, A->nodes, items_b, A->tri_gid, A->tri_wide);
@@ -608,32 +593,17 @@ int build_accel_device(gpurt_accel* A) {
             int* sw = items_a;
             items_a = items_b, items_b = sw;
             depth++;
-            if((size_t)level_base + n_items > max_nodes) {
-                set_error("wide node bound exceeded");
-                return GPURT_E_STATE;
-            }
+            if((size_t)level_base + n_items > max_nodes) return set_error("wide node bound exceeded"), GPURT_E_STATE;
         }
         A->n_nodes = level_base;
         A->depth = depth;
-        scan_tmp.release();
-        dfree(items_a), dfree(items_b), dfree(children), dfree(cnt);
-        if(tri_cursor != n) {
-            set_error("collapse lost triangles: " + std::to_string(tri_cursor) + " of " + std::to_string(n));
-            return GPURT_E_STATE;
-        }
+        if(tri_cursor != n)
+            return set_error("collapse lost triangles: " + std::to_string(tri_cursor) + " of " + std::to_string(n)), GPURT_E_STATE;
     }
     GPURT_CUDA(cudaEventRecord(e1, st));
     GPURT_CUDA(cudaStreamSynchronize(st));
     cudaEventElapsedTime(&A->build_ms, e0, e1);
     cudaEventDestroy(e0), cudaEventDestroy(e1);
-    dfree(keys_tmp), dfree(vals_tmp);
-    A->has_bvh2 = true;
-    if(!(A->flags & GPURT_BUILD_KEEP_BVH2)) {
-        /* the binary tree is only needed for get_bvh2 / the bvh2 debug trace */
-        void* drop[] = {A->parent, A->range_first, A->range_last};
-        for(void* p : drop) dfree(p);
-        A->parent = A->range_first = A->range_last = nullptr;
-    }
     GPURT_CUDA(cudaGetLastError());
     return GPURT_OK;
 }

@@ -29,12 +29,6 @@ struct DevBuf {
     void release();
     template <typename T> T* as() const { return (T*)p; }
 };
-struct PinBuf {
-    void* p = nullptr;
-    size_t cap = 0;
-    int reserve(size_t bytes);
-    void release();
-};
 
 } // namespace gpurt
 
@@ -50,8 +44,8 @@ struct gpurt_ctx {
     float last_ms = 0;
     /* staging for GPURT_MEM_HOST calls */
     gpurt::DevBuf d_in, d_out;
-    gpurt::PinBuf h_in, h_out;
     gpurt::DevBuf scratch;
+    gpurt::DevBuf build_arena; /* temporaries of gpurt_accel_build / gpurt_accel_update */
 };
 
 namespace gpurt {
@@ -99,8 +93,7 @@ struct gpurt_accel {
     uint64_t* keys = nullptr;
     uint32_t* order = nullptr;
     /* binary LBVH */
-    int *left = nullptr, *right = nullptr, *parent = nullptr, *range_first = nullptr,
-        *range_last = nullptr;
+    int *left = nullptr, *right = nullptr;
     float4 *node_lo = nullptr, *node_hi = nullptr;
     /* wide BVH */
     gpurt::Node8* nodes = nullptr;
@@ -109,7 +102,6 @@ struct gpurt_accel {
     float scene_box[6] = {0, 0, 0, 0, 0, 0};
     float inflate = 0;
     float build_ms = 0;
-    bool has_bvh2 = false;
 };
 
 namespace gpurt {

@@ -197,7 +197,7 @@ int gpurt_camera_make(int mode, float width, float height, const float pos[3],
  * GPURT::build_accel (src/gpurt.cpp:220-241): LBVH over the world-space triangles of all
  * instances, collapsed to 80-byte 8-wide compressed nodes. */
 #define GPURT_BUILD_DEFAULT 0u
-#define GPURT_BUILD_KEEP_BVH2 1u /* keep the binary LBVH for gpurt_accel_get_bvh2 / debug trace */
+#define GPURT_BUILD_KEEP_BVH2 1u /* accepted; the binary LBVH is always kept (gpurt_accel_update rebuilds into it) */
 int gpurt_accel_build(gpurt_scene* scene, uint32_t flags, gpurt_accel** out);
 /* Rebuild after scene edits (GPURT::build_accel with rebuild_tlas / rebuild_blas, src/gpurt.cpp:220-241).
  * Pose-only edits re-upload the 208-byte Scene_Desc records and rebuild on the device in the buffers
@@ -220,7 +220,7 @@ int gpurt_trace_any(gpurt_accel* accel, const GpurtRay* rays, uint64_t n, uint8_
 /* FCPW closest-point query (README.md:6-8) over the same BVH. */
 int gpurt_closest_points(gpurt_accel* accel, const GpurtQuery* queries, uint64_t n,
                          GpurtClosestPoint* results, int mem);
-/* Same as gpurt_trace_closest but through the binary LBVH (needs GPURT_BUILD_KEEP_BVH2). */
+/* Same as gpurt_trace_closest but through the binary LBVH (debug / cross-check path). */
 int gpurt_trace_closest_bvh2(gpurt_accel* accel, const GpurtRay* rays, uint64_t n, GpurtHit* hits, int mem);
 /* Instrumented closest-hit: same results + visit counters (device buffers only). */
 int gpurt_trace_closest_stats(gpurt_accel* accel, const GpurtRay* rays, uint64_t n, GpurtHit* hits,

@@ -117,33 +117,43 @@ int exclusive_scan_u32(cudaStream_t st, const uint32_t* in, uint32_t* out, size_
 }
 
 /* ---- radix sort ------------------------------------------------------------------------------- */
+/* Stable LSD radix sort of 64-bit keys with a 32-bit payload, 8 bits per pass, "onesweep" style:
+ * one kernel histograms all 8 digits of every key, then each pass is ONE kernel that ranks a tile of
+ * 4096 keys, obtains the tile's per-digit base with a decoupled look-back over the tiles before it
+ * (tiles are numbered by an atomic ticket, so every predecessor is already running) and scatters.
+ * Per pass every key and payload is read once and written once. */
 constexpr int RS_T = 256, RS_I = 16, RS_TILE = RS_T * RS_I, RS_W = RS_T / 32;
+constexpr uint32_t RS_FLAG_AGG = 1u << 30, RS_FLAG_PREFIX = 2u << 30, RS_VALUE = (1u << 30) - 1u;
 
-__global__ void __launch_bounds__(RS_T) k_rs_hist(const uint64_t* __restrict__ keys, size_t n,
-                                                  int shift, uint32_t* __restrict__ hist, unsigned nb) {
-    __shared__ uint32_t h[256];
-    h[threadIdx.x] = 0;
+__global__ void __launch_bounds__(RS_T) k_rs_digit_hist(const uint64_t* __restrict__ keys, size_t n, int passes,
+                                                        uint32_t* __restrict__ ghist /* [passes][256] */) {
+    __shared__ uint32_t h[8][256];
+    for(int i = threadIdx.x; i < 8 * 256; i += RS_T) (&h[0][0])[i] = 0;
     __syncthreads();
-    size_t base = (size_t)blockIdx.x * RS_TILE;
-#pragma unroll
-    for(int r = 0; r < RS_I; r++) {
-        size_t i = base + (size_t)r * RS_T + threadIdx.x;
-        if(i < n) atomicAdd(&h[(unsigned)(keys[i] >> shift) & 255u], 1u);
+    for(size_t i = (size_t)blockIdx.x * RS_T + threadIdx.x; i < n; i += (size_t)gridDim.x * RS_T) {
+        uint64_t k = keys[i];
+        for(int p = 0; p < passes; p++) atomicAdd(&h[p][(unsigned)(k >> (8 * p)) & 255u], 1u);
     }
     __syncthreads();
-    hist[(size_t)threadIdx.x * nb + blockIdx.x] = h[threadIdx.x];
+    for(int p = 0; p < passes; p++) {
+        uint32_t c = h[p][threadIdx.x];
+        if(c) atomicAdd(&ghist[p * 256 + threadIdx.x], c);
+    }
 }
 
-__global__ void __launch_bounds__(RS_T) k_rs_scatter(const uint64_t* __restrict__ kin,
-                                                     const uint32_t* __restrict__ vin,
-                                                     uint64_t* __restrict__ kout,
-                                                     uint32_t* __restrict__ vout, size_t n, int shift,
-                                                     const uint32_t* __restrict__ offs, unsigned nb) {
+__global__ void __launch_bounds__(RS_T) k_rs_onesweep(const uint64_t* __restrict__ kin, const uint32_t* __restrict__ vin,
+                                                      uint64_t* __restrict__ kout, uint32_t* __restrict__ vout,
+                                                      size_t n, int shift, const uint32_t* __restrict__ ghist,
+                                                      uint32_t* __restrict__ desc /* [tiles][256], zeroed */,
+                                                      unsigned* __restrict__ ticket) {
     __shared__ uint32_t cnt[RS_W][256];
+    __shared__ unsigned s_tile;
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if(threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
     for(int i = threadIdx.x; i < RS_W * 256; i += RS_T) (&cnt[0][0])[i] = 0;
     __syncthreads();
-    const size_t seg = (size_t)blockIdx.x * RS_TILE + (size_t)w * (32 * RS_I);
+    const unsigned tile = s_tile;
+    const size_t seg = (size_t)tile * RS_TILE + (size_t)w * (32 * RS_I);
     uint64_t key[RS_I];
     uint32_t rank[RS_I];
     const unsigned lt = (1u << l) - 1u;
@@ -167,8 +177,25 @@ __global__ void __launch_bounds__(RS_T) k_rs_scatter(const uint64_t* __restrict_
     }
     __syncthreads();
     {
-        unsigned d = threadIdx.x;
-        uint32_t run = offs[(size_t)d * nb + blockIdx.x];
+        /* thread d owns digit d: tile total, publish, look back, turn the per-warp counts into bases */
+        const unsigned d = threadIdx.x;
+        uint32_t total = 0;
+#pragma unroll
+        for(int ww = 0; ww < RS_W; ww++) total += cnt[ww][d];
+        volatile uint32_t* vd = desc;
+        if(tile > 0) atomicExch(&desc[(size_t)tile * 256 + d], total | RS_FLAG_AGG);
+        uint32_t excl = 0;
+        for(int t = (int)tile - 1; t >= 0; t--) {
+            uint32_t v;
+            do { v = vd[(size_t)t * 256 + d]; } while((v >> 30) == 0u);
+            excl += v & RS_VALUE;
+            if(v & RS_FLAG_PREFIX) break;
+        }
+        atomicExch(&desc[(size_t)tile * 256 + d], (excl + total) | RS_FLAG_PREFIX);
+        /* exclusive prefix of the global digit histogram = start of digit d in the output */
+        uint32_t gtot;
+        uint32_t gbase = block_exclusive_scan<uint32_t>(ghist[d], gtot);
+        uint32_t run = gbase + excl;
 #pragma unroll
         for(int ww = 0; ww < RS_W; ww++) {
             uint32_t c = cnt[ww][d];
@@ -189,22 +216,27 @@ __global__ void __launch_bounds__(RS_T) k_rs_scatter(const uint64_t* __restrict_
     }
 }
 
+size_t radix_sort_tmp_bytes(size_t n, int passes) {
+    size_t nb = (n + RS_TILE - 1) / RS_TILE;
+    return (size_t)passes * (256 + 64) * 4 + (size_t)passes * nb * 256 * 4;
+}
+
 int radix_sort_u64(cudaStream_t st, uint64_t* keys, uint32_t* vals, uint64_t* kt, uint32_t* vt,
-                   size_t n, int passes, DevBuf& tmp) {
+                   size_t n, int passes, DevBuf& tmp, int sm_count) {
     if(n == 0) return GPURT_OK;
+    if(n > RS_VALUE || passes > 8) return set_error("radix sort: more than 2^30-1 keys"), GPURT_E_INVALID;
     unsigned nb = cdiv(n, RS_TILE);
-    size_t hist_n = (size_t)256 * nb;
-    size_t hist_bytes = (hist_n * 4 + 255) & ~(size_t)255;
-    int rc = tmp.reserve(hist_bytes + scan_tmp_bytes(hist_n));
+    size_t bytes = radix_sort_tmp_bytes(n, passes);
+    int rc = tmp.reserve(bytes);
     if(rc) return rc;
-    uint32_t* hist = tmp.as<uint32_t>();
-    uint32_t* stmp = (uint32_t*)((char*)tmp.p + hist_bytes);
+    uint32_t* ghist = tmp.as<uint32_t>();                 /* [passes][256] */
+    unsigned* tickets = ghist + (size_t)passes * 256;      /* [passes] (64 reserved) */
+    uint32_t* desc = ghist + (size_t)passes * (256 + 64);  /* [passes][nb][256] */
+    GPURT_CUDA(cudaMemsetAsync(tmp.p, 0, bytes, st));
+    k_rs_digit_hist<<<std::min(nb * (unsigned)RS_I, (unsigned)sm_count * 8u), RS_T, 0, st>>>(keys, n, passes, ghist);
     for(int p = 0; p < passes; p++) {
-        int shift = 8 * p;
-        k_rs_hist<<<nb, RS_T, 0, st>>>(keys, n, shift, hist, nb);
-        rc = scan_rec<uint32_t>(st, hist, hist, hist_n, stmp);
-        if(rc) return rc;
-        k_rs_scatter<<<nb, RS_T, 0, st>>>(keys, vals, kt, vt, n, shift, hist, nb);
+        k_rs_onesweep<<<nb, RS_T, 0, st>>>(keys, vals, kt, vt, n, 8 * p, ghist + p * 256,
+                                          desc + (size_t)p * nb * 256, tickets + p);
         uint64_t* a = keys;
         keys = kt, kt = a;
         uint32_t* b = vals;
@@ -546,7 +578,7 @@ int build_accel_device(gpurt_accel* A) {
     /* keys + sort */
     k_morton<<<cdiv(n, 256), 256, 0, st>>>(A->tri_lo, A->tri_hi, n, sb[0], sb[1], sb[2], inv[0], inv[1],
                                           inv[2], A->keys, A->order);
-    TRY(radix_sort_u64(st, A->keys, A->order, keys_tmp, vals_tmp, n, 8, ctx->scratch));
+    TRY(radix_sort_u64(st, A->keys, A->order, keys_tmp, vals_tmp, n, 8, ctx->scratch, ctx->sm_count));
 
     /* binary tree */
     unsigned* arrive = (unsigned*)vals_tmp; /* the sort is done with it */

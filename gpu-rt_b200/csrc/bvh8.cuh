@@ -81,29 +81,32 @@ GPURT_HD int bvh2_to_child(const Bvh2View& B, int c) {
  * slots (greedy on the signed centroid projection).  out_child[8] is indexed by slot. Returns the
  * number of inner children; n_leaf_tris gets the triangles referenced by leaf slots. */
 GPURT_HD int collapse_node(const Bvh2View& B, int root, int out_child[8], int& n_leaf_tris) {
-    int cand[8]; /* raw BVH2 refs */
+    int cand[8];    /* raw BVH2 refs */
+    Box3 box[8];    /* their boxes, loaded once */
+    float area[8];  /* surface area, or -1 when the candidate cannot be opened (leaf / small subtree) */
+    auto load = [&](int i, int c) {
+        cand[i] = c;
+        box[i] = bvh2_child_box(B, c);
+        area[i] = (c < 0 || bvh2_count(B, c) <= kMaxLeafTris) ? -1.0f : box_area(box[i]);
+    };
     int n = 2;
-    cand[0] = B.left[root];
-    cand[1] = B.right[root];
+    load(0, B.left[root]);
+    load(1, B.right[root]);
     while(n < 8) {
         int best = -1;
         float best_area = -1.0f;
-        for(int i = 0; i < n; i++) {
-            int c = cand[i];
-            if(c < 0 || bvh2_count(B, c) <= kMaxLeafTris) continue;
-            float a = box_area(bvh2_child_box(B, c));
-            if(a > best_area) best_area = a, best = i;
-        }
+        for(int i = 0; i < n; i++)
+            if(area[i] > best_area) best_area = area[i], best = i;
         if(best < 0) break;
         int c = cand[best];
-        cand[best] = B.left[c];
-        cand[n++] = B.right[c];
+        load(best, B.left[c]);
+        load(n++, B.right[c]);
     }
     /* node centre from the union of candidate boxes */
-    Box3 nb = bvh2_child_box(B, cand[0]);
+    Box3 nb = box[0];
     F3 cen[8];
     for(int i = 0; i < n; i++) {
-        Box3 b = bvh2_child_box(B, cand[i]);
+        const Box3& b = box[i];
         cen[i] = (b.lo + b.hi) * 0.5f;
         nb.lo = f3(fminf(nb.lo.x, b.lo.x), fminf(nb.lo.y, b.lo.y), fminf(nb.lo.z, b.lo.z));
         nb.hi = f3(fmaxf(nb.hi.x, b.hi.x), fmaxf(nb.hi.y, b.hi.y), fmaxf(nb.hi.z, b.hi.z));

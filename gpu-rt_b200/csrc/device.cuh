@@ -75,7 +75,7 @@ size_t scan_tmp_bytes(size_t n);
 
 /* stable LSD radix sort of 64-bit keys with 32-bit payload, 8 bits per pass */
 int radix_sort_u64(cudaStream_t st, uint64_t* keys, uint32_t* vals, uint64_t* keys_tmp,
-                   uint32_t* vals_tmp, size_t n, int passes, DevBuf& tmp);
+                   uint32_t* vals_tmp, size_t n, int passes, DevBuf& tmp, int sm_count);
 
 } // namespace gpurt
 

@@ -141,19 +141,28 @@ __global__ void __launch_bounds__(RS_T) k_rs_digit_hist(const uint64_t* __restri
     }
 }
 
+constexpr size_t RS_SMEM = (size_t)RS_TILE * 12 + (size_t)RS_W * 256 * 4 + 2 * 256 * 4 + 16;
+
 __global__ void __launch_bounds__(RS_T) k_rs_onesweep(const uint64_t* __restrict__ kin, const uint32_t* __restrict__ vin,
                                                       uint64_t* __restrict__ kout, uint32_t* __restrict__ vout,
                                                       size_t n, int shift, const uint32_t* __restrict__ ghist,
                                                       uint32_t* __restrict__ desc /* [tiles][256], zeroed */,
                                                       unsigned* __restrict__ ticket) {
-    __shared__ uint32_t cnt[RS_W][256];
-    __shared__ unsigned s_tile;
+    extern __shared__ __align__(16) unsigned char rs_smem[];
+    uint64_t* s_key = reinterpret_cast<uint64_t*>(rs_smem);                       /* [RS_TILE] tile in digit order */
+    uint32_t* s_val = reinterpret_cast<uint32_t*>(rs_smem + (size_t)RS_TILE * 8);  /* [RS_TILE] */
+    uint32_t(*cnt)[256] = reinterpret_cast<uint32_t(*)[256]>(rs_smem + (size_t)RS_TILE * 12); /* [RS_W][256] */
+    uint32_t* s_lstart = &cnt[RS_W][0];  /* [256] start of digit d inside the tile */
+    uint32_t* s_gbase = s_lstart + 256;  /* [256] start of this tile's digit d in the output */
+    unsigned* s_tile = s_gbase + 256;
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-    if(threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    if(threadIdx.x == 0) *s_tile = atomicAdd(ticket, 1u);
     for(int i = threadIdx.x; i < RS_W * 256; i += RS_T) (&cnt[0][0])[i] = 0;
     __syncthreads();
-    const unsigned tile = s_tile;
-    const size_t seg = (size_t)tile * RS_TILE + (size_t)w * (32 * RS_I);
+    const unsigned tile = *s_tile;
+    const size_t tile0 = (size_t)tile * RS_TILE;
+    const size_t seg = tile0 + (size_t)w * (32 * RS_I);
+    const unsigned tile_n = (unsigned)min((size_t)RS_TILE, n - tile0);
     uint64_t key[RS_I];
     uint32_t rank[RS_I];
     const unsigned lt = (1u << l) - 1u;
@@ -177,7 +186,7 @@ __global__ void __launch_bounds__(RS_T) k_rs_onesweep(const uint64_t* __restrict
     }
     __syncthreads();
     {
-        /* thread d owns digit d: tile total, publish, look back, turn the per-warp counts into bases */
+        /* thread d owns digit d: tile total, publish, look back, turn the per-warp counts into offsets */
         const unsigned d = threadIdx.x;
         uint32_t total = 0;
 #pragma unroll
@@ -192,10 +201,12 @@ __global__ void __launch_bounds__(RS_T) k_rs_onesweep(const uint64_t* __restrict
             if(v & RS_FLAG_PREFIX) break;
         }
         atomicExch(&desc[(size_t)tile * 256 + d], (excl + total) | RS_FLAG_PREFIX);
-        /* exclusive prefix of the global digit histogram = start of digit d in the output */
-        uint32_t gtot;
-        uint32_t gbase = block_exclusive_scan<uint32_t>(ghist[d], gtot);
-        uint32_t run = gbase + excl;
+        uint32_t gtot, ltot;
+        uint32_t gbase = block_exclusive_scan<uint32_t>(ghist[d], gtot); /* start of digit d in the output */
+        uint32_t lstart = block_exclusive_scan<uint32_t>(total, ltot);   /* start of digit d in the tile */
+        s_gbase[d] = gbase + excl;
+        s_lstart[d] = lstart;
+        uint32_t run = lstart;
 #pragma unroll
         for(int ww = 0; ww < RS_W; ww++) {
             uint32_t c = cnt[ww][d];
@@ -204,14 +215,27 @@ __global__ void __launch_bounds__(RS_T) k_rs_onesweep(const uint64_t* __restrict
         }
     }
     __syncthreads();
+    /* stage the tile in digit order, then write runs of equal digits with consecutive threads */
 #pragma unroll
     for(int r = 0; r < RS_I; r++) {
         size_t i = seg + (size_t)r * 32 + l;
         if(i < n) {
             unsigned d = (unsigned)(key[r] >> shift) & 255u;
-            uint32_t pos = cnt[w][d] + rank[r];
-            kout[pos] = key[r];
-            vout[pos] = vin[i];
+            uint32_t lp = cnt[w][d] + rank[r];
+            s_key[lp] = key[r];
+            s_val[lp] = vin[i];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for(int r = 0; r < RS_I; r++) {
+        unsigned j = (unsigned)r * RS_T + threadIdx.x;
+        if(j < tile_n) {
+            uint64_t k = s_key[j];
+            unsigned d = (unsigned)(k >> shift) & 255u;
+            uint32_t pos = s_gbase[d] + (j - s_lstart[d]);
+            kout[pos] = k;
+            vout[pos] = s_val[j];
         }
     }
 }
@@ -233,9 +257,10 @@ int radix_sort_u64(cudaStream_t st, uint64_t* keys, uint32_t* vals, uint64_t* kt
     unsigned* tickets = ghist + (size_t)passes * 256;      /* [passes] (64 reserved) */
     uint32_t* desc = ghist + (size_t)passes * (256 + 64);  /* [passes][nb][256] */
     GPURT_CUDA(cudaMemsetAsync(tmp.p, 0, bytes, st));
+    GPURT_CUDA(cudaFuncSetAttribute(k_rs_onesweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM));
     k_rs_digit_hist<<<std::min(nb * (unsigned)RS_I, (unsigned)sm_count * 8u), RS_T, 0, st>>>(keys, n, passes, ghist);
     for(int p = 0; p < passes; p++) {
-        k_rs_onesweep<<<nb, RS_T, 0, st>>>(keys, vals, kt, vt, n, 8 * p, ghist + p * 256,
+        k_rs_onesweep<<<nb, RS_T, RS_SMEM, st>>>(keys, vals, kt, vt, n, 8 * p, ghist + p * 256,
                                           desc + (size_t)p * nb * 256, tickets + p);
         uint64_t* a = keys;
         keys = kt, kt = a;
@@ -421,8 +446,7 @@ __global__ void __launch_bounds__(128) k_collapse_emit(Bvh2View B, unsigned n_it
                                                        unsigned level_base, unsigned next_base,
                                                        unsigned tri_cursor, Node8* __restrict__ nodes,
                                                        int* __restrict__ next_items,
-                                                       const float4* __restrict__ tri_gid,
-                                                       float4* __restrict__ tri_wide) {
+                                                       uint32_t* __restrict__ wide_order) {
     unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if(i >= n_items) return;
     int ch[8];
@@ -445,13 +469,19 @@ __global__ void __launch_bounds__(128) k_collapse_emit(Bvh2View B, unsigned n_it
         else {
             unsigned first, count;
             decode_leaf_range(c, first, count);
-            for(unsigned k = 0; k < count; k++, t++) {
-                unsigned g = B.order[first + k];
-#pragma unroll
-                for(int q = 0; q < 3; q++) tri_wide[3ull * (tri_base + t) + q] = tri_gid[3ull * g + q];
-            }
+            for(unsigned k = 0; k < count; k++, t++) wide_order[tri_base + t] = B.order[first + k];
         }
     }
+}
+
+/* triangles into node order: slot j of the wide layout holds triangle wide_order[j]; one thread per float4 */
+__global__ void __launch_bounds__(256) k_tri_reorder(const uint32_t* __restrict__ wide_order, size_t n,
+                                                     const float4* __restrict__ tri_gid, float4* __restrict__ tri_wide) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= 3 * n) return;
+    size_t j = i / 3;
+    unsigned q = (unsigned)(i - 3 * j);
+    tri_wide[i] = tri_gid[3ull * wide_order[j] + q];
 }
 
 /* n <= kMaxLeafTris: a single node whose slot 0 holds every triangle */
@@ -537,7 +567,8 @@ int build_accel_device(gpurt_accel* A) {
     const size_t pad = 256;
     size_t fixed = 3 * pad + 2 * ((size_t)ni * 4 + pad);
     size_t phase1 = (size_t)n * 8 + (size_t)n * 4 + ((size_t)ni + n) * 4 + 4 * pad;
-    size_t phase2 = 2 * max_nodes * 4 + 8 * max_nodes * 4 + (max_nodes + 1) * 8 + scan_tmp_bytes(max_nodes + 1) + 6 * pad;
+    size_t phase2 = 2 * max_nodes * 4 + 8 * max_nodes * 4 + (max_nodes + 1) * 8 + scan_tmp_bytes(max_nodes + 1) +
+                    (size_t)n * 4 + 7 * pad;
     TRY(ctx->build_arena.reserve(fixed + std::max(phase1, phase2)));
     Arena ar;
     ar.base = (char*)ctx->build_arena.p, ar.cap = ctx->build_arena.cap;
@@ -606,7 +637,8 @@ int build_accel_device(gpurt_accel* A) {
         int* children = ar.take<int>(8 * max_nodes);
         uint64_t* cnt = ar.take<uint64_t>(max_nodes + 1);
         uint64_t* scan_tmp = ar.take<uint64_t>(scan_tmp_bytes(max_nodes + 1) / 8 + 1);
-        if(!scan_tmp) return set_error("build arena layout"), GPURT_E_STATE;
+        uint32_t* wide_order = ar.take<uint32_t>(n);
+        if(!wide_order) return set_error("build arena layout"), GPURT_E_STATE;
         int root = 0;
         GPURT_CUDA(cudaMemcpyAsync(items_a, &root, 4, cudaMemcpyHostToDevice, st));
         unsigned n_items = 1, level_base = 0, tri_cursor = 0, depth = 0;
@@ -615,7 +647,7 @@ int build_accel_device(gpurt_accel* A) {
             TRY(scan_rec<uint64_t>(st, cnt, cnt, n_items + 1, scan_tmp));
             unsigned next_base = level_base + n_items;
             k_collapse_emit<<<cdiv(n_items, 128), 128, 0, st>>>(B, n_items, children, cnt, level_base, next_base,
-                                                               tri_cursor, A->nodes, items_b, A->tri_gid, A->tri_wide);
+                                                               tri_cursor, A->nodes, items_b, wide_order);
             uint32_t tot[2]; /* {inner children, triangles} emitted by this level */
             GPURT_CUDA(cudaMemcpyAsync(tot, cnt + n_items, 8, cudaMemcpyDeviceToHost, st));
             GPURT_CUDA(cudaStreamSynchronize(st));
@@ -631,6 +663,7 @@ int build_accel_device(gpurt_accel* A) {
         A->depth = depth;
         if(tri_cursor != n)
             return set_error("collapse lost triangles: " + std::to_string(tri_cursor) + " of " + std::to_string(n)), GPURT_E_STATE;
+        k_tri_reorder<<<cdiv(3ull * n, 256), 256, 0, st>>>(wide_order, n, A->tri_gid, A->tri_wide);
     }
     GPURT_CUDA(cudaEventRecord(e1, st));
     GPURT_CUDA(cudaStreamSynchronize(st));

@@ -135,35 +135,44 @@ def scene_world_tris(scene, orc):
 
 def reference_arm(args, rank, world):
     """--impl reference: CPU traversal (oracle restatement of the reference semantics) on all host
-    cores, on a bounded sample of the same workload."""
+    cores, on a bounded sample of the same workload: the config-2 frame is rendered once on the CPU
+    (untimed) with the oracle's restatement of rt.rgen, the closest-hit rays it traces (primary + bounce)
+    are recorded, and every step traces a 1-in-8 sample of them through the CPU BVH."""
     if rank != 0:
         return
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import gpurt
     import orc
     scene, label = build_scene(gpurt, None)
-    tris = scene_world_tris(scene, orc)
-    rays, _ = primary_rays(gpurt, 0)
     t0 = time.time()
-    bvh = orc.Bvh(tris)
+    rs = orc.RenderScene(scene)            # flattens the scene and builds the CPU LBVH
     build_s = time.time() - t0
-    sample = rays[:: max(1, rays.shape[0] // 400000)][:400000].copy()
+    cam = gpurt.camera(1, W, H, CAM_POS, CAM_AT, VFOV)
+    c = gpurt.Constants()
+    c.clear_col[:] = [0.3, 0.3, 0.3, 1.0]
+    c.env_light[:] = [1.0, 1.0, 1.0, 1.0]
+    c.frame, c.samples, c.max_frame, c.max_depth, c.integrator, c.brdf, c.use_rr = 0, 1, 1, 2, 1, 1, 0
+    c.use_temporal, c.n_lights, c.n_objs = 1, scene.counts()["lights"], scene.counts()["objs"]
+    rays = orc.frame_rays(rs, W, H, np.frombuffer(bytes(c), np.uint32), np.frombuffer(bytes(cam), np.uint32), 0, 2 * W * H)
+    stride = 8
+    sample = rays[::stride].copy()
     cores = orc.lib.orc_hw_threads()
     times = []
     for i in range(args.warmup + args.steps):
         t0 = time.time()
-        bvh.closest_hit(sample, threads=cores)
+        rs.bvh.closest_hit(sample, threads=cores)
         if i >= args.warmup:
             times.append(time.time() - t0)
     dt = float(np.mean(times))
     val = sample.shape[0] / dt / 1e6
+    what = f"every {stride}th of the {rays.shape[0]} closest-hit rays of the frame ({sample.shape[0]} rays per step)"
     line = {"impl": "reference", "metric": "Mrays/s closest-hit on Sponza", "value": val, "unit": "Mrays/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "sponza 1080p config-2 ray set (primary+1 bounce)", "scene": label,
-                       "sample": f"{sample.shape[0]} primary rays (every {max(1, rays.shape[0] // 400000)}th pixel)"},
+            "config": {"workload": "sponza 1080p config-2 ray set (2,073,600 primary + 1-bounce rays), closest-hit",
+                       "scene": label, "sample": what},
             "cpu_baseline": {"value": val, "unit": "Mrays/s", "cores": cores, "kind": "port",
-                             "sample": f"{sample.shape[0]} primary rays per step; CPU LBVH build {build_s:.2f} s not included"},
+                             "sample": what + f"; CPU LBVH build {build_s:.2f} s not included"},
             "e2e": {"value": val, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -318,7 +327,7 @@ def main():
         import orc
         ob = orc.Bvh(scene_world_tris(scene, orc))
         cores = orc.lib.orc_hw_threads()
-        stride = max(1, n_rays // 600000)
+        stride = 1   # the whole step: ~13 core-seconds of CPU traversal
         sample = rays_np[::stride].copy()
         t0 = time.time()
         ref = ob.closest_hit(sample, threads=cores)
@@ -326,9 +335,16 @@ def main():
         got = np.ascontiguousarray(d_hits.cpu().numpy()[::stride])
         assert np.array_equal(ref.view(np.uint32).reshape(-1, 4), got.view(np.uint32)), "GPU result differs from the CPU oracle"
         cpu = {"value": sample.shape[0] / dt / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
-               "sample": f"every {stride}th ray of the step's ray set ({sample.shape[0]} rays, {dt:.1f} s); "
+               "sample": f"all {sample.shape[0]} rays of one step ({dt:.1f} s wall on {cores} threads); "
                          "results compared bit-exactly with the GPU's"}
 
+    # physical DRAM bytes of one launch: dram__bytes_read.sum + dram__bytes_write.sum of k_trace_closest from the
+    # committed ncu capture of this same workload, scaled per ray (never measured under the profiler here)
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        traffic, traffic_src = tj["dram_bytes_per_ray"] * n_rays, tj["source"]
     if rank == 0:
         line = {
             "metric": "Mrays/s closest-hit on Sponza", "value": value, "unit": "Mrays/s", "n_gpus": world,
@@ -342,7 +358,7 @@ def main():
             "e2e": {"value": e2e_val, "unit": "Mrays/s", "h2d_bytes_per_step": int(n_rays * 32), "d2h_bytes_per_step": int(n_rays * 16)},
             "gpu_launches": args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "k_trace_closest<false>",
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel": "k_trace_closest<false>",
                          "bytes_per_ray": bytes_per_ray, "nodes_per_ray": nodes_per_ray, "tris_per_ray": tris_per_ray,
                          "stream_floor_bytes_per_ray": BYTES_STREAM, "kernel_ms": kernel_ms},
             "cpu_baseline": cpu,

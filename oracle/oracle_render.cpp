@@ -15,6 +15,7 @@
 
 #include <cmath>
 #include <cstring>
+#include <atomic>
 #include <thread>
 #include <vector>
 
@@ -153,6 +154,11 @@ struct orc_scene {
 namespace {
 
 /* per-invocation state of rt.rgen (its globals: seed, payload, prev_res) */
+/* optional recorder of every closest-hit ray a frame traces (bench.py's CPU arm replays them) */
+static float* g_rec_buf = nullptr;
+static uint64_t g_rec_cap = 0;
+static std::atomic<uint64_t> g_rec_count{0};
+
 struct Invocation {
     const orc_scene* S;
     const Consts* c;
@@ -221,6 +227,10 @@ struct Invocation {
         float ray[8] = {o.x, o.y, o.z, EPS, d.x, d.y, d.z, LARGE_DIST};
         uint32_t hit[4];
         n_closest++;
+        if(g_rec_buf) {
+            uint64_t k = g_rec_count.fetch_add(1);
+            if(k < g_rec_cap) memcpy(g_rec_buf + 8 * k, ray, sizeof(ray));
+        }
         if(orc_bvh_trace_one(S->bvh, ray, hit)) {
             float u = u2f(hit[1]), v = u2f(hit[2]);
             uint32_t gid = hit[3];
@@ -843,6 +853,12 @@ orc_scene* orc_scene_create(uint32_t n_objs, const uint32_t* descs, const uint32
     return s;
 }
 void orc_scene_free(orc_scene* s) { delete s; }
+
+void orc_record_rays(float* rays8, uint64_t capacity) {
+    g_rec_buf = rays8, g_rec_cap = capacity;
+    g_rec_count = 0;
+}
+uint64_t orc_recorded_rays(void) { return std::min<uint64_t>(g_rec_count.load(), g_rec_cap); }
 
 void orc_render_frame(const orc_scene* S, const uint32_t* consts, const uint32_t* camera, uint32_t w,
                       uint32_t h, uint32_t seed, float* image, const uint32_t* prev_res,

@@ -35,6 +35,11 @@ void orc_render_frame(const orc_scene* S, const uint32_t* consts, const uint32_t
                       uint32_t* out_res, const float* ppos, const float* pnorm, const float* palb,
                       float* pos, float* norm, float* alb, uint64_t* ray_counts2, int threads);
 
+/* Record the closest-hit rays (8 floats each, traversal order of the worker threads) traced by the
+ * following orc_render_frame calls into rays8[capacity]; NULL stops recording. */
+void orc_record_rays(float* rays8, uint64_t capacity);
+uint64_t orc_recorded_rays(void);
+
 /* unit-level entry points for tests (each restates one GLSL function) */
 void orc_camera_ray(const uint32_t* consts, const uint32_t* camera, uint32_t w, uint32_t h, uint32_t px,
                     uint32_t py, uint32_t s, uint32_t* rng, float* o3, float* d3);

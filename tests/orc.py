@@ -169,6 +169,10 @@ lib.orc_scene_free.argtypes = [_vp]
 lib.orc_render_frame.restype = None
 lib.orc_render_frame.argtypes = [_vp, _vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32, _vp, _vp, _vp, _vp, _vp, _vp,
                                  _vp, _vp, _vp, _vp, C.c_int]
+lib.orc_record_rays.restype = None
+lib.orc_record_rays.argtypes = [_vp, C.c_uint64]
+lib.orc_recorded_rays.restype = C.c_uint64
+lib.orc_recorded_rays.argtypes = []
 lib.orc_camera_ray.restype = None
 lib.orc_camera_ray.argtypes = [_vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                C.POINTER(C.c_uint32), _f32p, _f32p]
@@ -243,6 +247,18 @@ def render_frame(rs, st, consts_words, camera_words, seed, threads=0):
                          _p(st.gb[cur][0]), _p(st.gb[cur][1]), _p(st.gb[cur][2]), _p(counts), threads)
     st.parity ^= 1
     return counts
+
+
+def frame_rays(rs, w, h, consts_words, camera_words, seed, capacity, threads=0):
+    """render one frame on the CPU and return the closest-hit rays it traced, (n,8) f32 (thread order)"""
+    buf = np.zeros((capacity, 8), np.float32)
+    lib.orc_record_rays(_p(buf), capacity)
+    try:
+        render_frame(rs, FrameState(w, h), consts_words, camera_words, seed, threads)
+        n = int(lib.orc_recorded_rays())
+    finally:
+        lib.orc_record_rays(None, 0)
+    return buf[:n]
 
 
 def tonemap(rgba, op=1, exposure=1.0, gamma=2.2):

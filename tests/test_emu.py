@@ -70,3 +70,32 @@ def test_flat_grid_with_duplicate_layer(emu, orc):
                 x0, x1, y0, y1 = i / 20, (i + 1) / 20, j / 20, (j + 1) / 20
                 g += [[x0, y0, 0.5, x1, y0, 0.5, x1, y1, 0.5], [x0, y0, 0.5, x1, y1, 0.5, x0, y1, 0.5]]
     _check(emu, orc, np.array(g, np.float32), 20000, box=np.array([0, 0, 0, 1, 1, 1], np.float32))
+
+
+def test_adversarial_inputs(emu, orc):
+    """degenerate triangles, axis-aligned / in-plane / zero / NaN rays, on-surface and NaN queries:
+    the BVH8 code, the oracle BVH and brute force agree bit for bit"""
+    from scenes import adversarial_points, adversarial_rays, adversarial_scene
+    tris = adversarial_scene()
+    b = orc.Bvh(tris)
+    order = b.prim_order()
+    l, r, bx = b.bvh2()
+    inflate = np.float32(max(1e-30, np.abs(b.scene_box()).max()) * 2.0 ** -19)
+    h = C.c_void_p(emu.emu_build(_vp(tris), len(tris), _vp(order), _vp(l), _vp(r), _vp(bx), C.c_float(inflate)))
+    rays = adversarial_rays(tris)
+    n = len(rays)
+    hits, occ, cnt = np.zeros((n, 4), np.uint32), np.zeros(n, np.uint8), np.zeros(4, np.uint64)
+    emu.emu_trace(h, _vp(rays), C.c_ulonglong(n), _vp(hits), _vp(occ), _vp(cnt))
+    ref = b.closest_hit(rays).view(np.uint32).reshape(-1, 4)
+    brute = orc.closest_hit_brute(tris, rays).view(np.uint32).reshape(-1, 4)
+    assert (ref == brute).all(), f"oracle BVH vs brute force: rays {np.nonzero((ref != brute).any(1))[0][:10]}"
+    assert (hits == ref).all(), f"BVH8 vs oracle: rays {np.nonzero((hits != ref).any(1))[0][:10]}"
+    assert (occ == b.any_hit(rays)).all()
+    q = adversarial_points(tris)
+    res = np.zeros((len(q), 8), np.uint32)
+    emu.emu_cpq(h, _vp(q), C.c_ulonglong(len(q)), _vp(res))
+    cref = b.closest_point(q).view(np.uint32).reshape(-1, 8)
+    cbrute = orc.closest_point_brute(tris, q).view(np.uint32).reshape(-1, 8)
+    assert (cref == cbrute).all(), f"oracle BVH vs brute force: queries {np.nonzero((cref != cbrute).any(1))[0][:10]}"
+    assert (res == cref).all(), f"BVH8 vs oracle: queries {np.nonzero((res != cref).any(1))[0][:10]}"
+    emu.emu_free(h)

@@ -263,3 +263,31 @@ def test_pose_edit_update_equals_fresh_build(gpurt, orc, ctx):
     assert same_bits(pipe.read_image(), fresh_pipe.read_image())
     for o in (pipe, fresh_pipe, accel, fresh, scene, fresh_scene):
         o.close()
+
+
+def test_adversarial_inputs(gpurt, orc, ctx):
+    """degenerate triangles, coplanar axis-aligned quads, slivers, 1e-6 and 4096-offset clusters; rays that
+    are axis-aligned, aimed exactly at vertices / edges, lie inside triangle planes, have zero / denormal /
+    NaN / inf components or odd [tmin,tmax]; queries on vertices / edges / faces with r2 = 0, NaN, negative"""
+    from scenes import adversarial_points, adversarial_rays, adversarial_scene
+    tris = adversarial_scene()
+    scene = gpurt.Scene(ctx)
+    scene.add_triangles(tris)
+    accel = gpurt.Accel(scene)
+    ob = _check_build(gpurt, orc, accel, tris)
+    rays = adversarial_rays(tris)
+    ref = ob.closest_hit(rays)
+    assert same_bits(ref, orc.closest_hit_brute(tris, rays))
+    hits = accel.trace_closest(rays)
+    bad = np.nonzero((hits.view(np.uint32).reshape(-1, 4) != ref.view(np.uint32).reshape(-1, 4)).any(1))[0]
+    assert bad.size == 0, f"rays {bad[:10]}: {rays[bad[:3]]} gpu {hits[bad[:3]]} oracle {ref[bad[:3]]}"
+    assert same_bits(accel.trace_closest(rays, bvh2=True), ref)
+    assert (accel.trace_any(rays) == ob.any_hit(rays)).all()
+    q = adversarial_points(tris)
+    cref = ob.closest_point(q)
+    assert same_bits(cref, orc.closest_point_brute(tris, q))
+    cp = accel.closest_points(q)
+    for f in ("p", "dist", "u", "v"):
+        assert same_bits(cp[f], cref[f]), f"closest point field {f}"
+    assert (cp["prim"] == cref["gid"]).all()
+    accel.close(), scene.close()

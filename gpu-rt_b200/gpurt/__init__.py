@@ -90,7 +90,7 @@ SYMBOLS = [
     "gpurt_pipe_render_frame", "gpurt_pipe_frame_index", "gpurt_pipe_read_image", "gpurt_pipe_read_gbuffer",
     "gpurt_pipe_ray_counts", "gpurt_pipe_device_image", "gpurt_tonemap", "gpurt_pipe_last_uniforms",
     "gpurt_pipe_read_reservoirs", "gpurt_pipe_bounce_rays", "gpurt_pipe_set_shard",
-    "gpurt_scene_set_transform", "gpurt_accel_update", "gpurt_shared_alloc", "gpurt_shared_free", "gpurt_shared_open", "gpurt_shared_close",
+    "gpurt_scene_set_transform", "gpurt_accel_update", "gpurt_scene_get_texture", "gpurt_shared_alloc", "gpurt_shared_free", "gpurt_shared_open", "gpurt_shared_close",
 ]
 
 
@@ -250,6 +250,14 @@ class Scene:
         out = C.c_int32()
         _check(lib.gpurt_scene_add_texture(self.h, C.c_void_p(rgba8.ctypes.data), w, h, C.byref(out)))
         return out.value
+
+    def texture(self, i):
+        """decoded RGBA8 texels of texture i as an (h, w, 4) uint8 array"""
+        w, h = C.c_uint32(), C.c_uint32()
+        _check(lib.gpurt_scene_get_texture(self.h, int(i), C.byref(w), C.byref(h), None))
+        out = np.zeros((h.value, w.value, 4), np.uint8)
+        _check(lib.gpurt_scene_get_texture(self.h, int(i), None, None, C.c_void_p(out.ctypes.data)))
+        return out
 
     def counts(self):
         a, b, c, d = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint32()

@@ -112,6 +112,14 @@ int gpurt_scene_add_object(gpurt_scene* s, const void* verts48, uint32_t nv, con
     }
     return GPURT_OK;
 }
+int gpurt_scene_get_texture(const gpurt_scene* s, uint32_t tex, uint32_t* w, uint32_t* h, uint8_t* out) {
+    if(!s || tex >= s->scene.textures.size()) return set_error("texture index out of range"), GPURT_E_INVALID;
+    const Texture& t = s->scene.textures[tex];
+    if(w) *w = t.w;
+    if(h) *h = t.h;
+    if(out) std::memcpy(out, t.rgba.data(), t.rgba.size());
+    return GPURT_OK;
+}
 int gpurt_scene_set_transform(gpurt_scene* s, uint32_t obj, const float model[16]) {
     if(!s || !model) return set_error("NULL argument"), GPURT_E_INVALID;
     Object* o = s->scene.at_index(obj);

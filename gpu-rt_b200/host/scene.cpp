@@ -206,8 +206,9 @@ bool read_vec(const Accessor& a, int want, std::vector<float>& out) {
 /* ---- PNG (8-bit, non-interlaced) via zlib ---------------------------------------------------- */
 bool decode_image(const std::vector<uint8_t>& f, Texture& out, std::string& err) {
     static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0D, 0x0A, 0x1A, 0x0A};
+    if(f.size() >= 3 && f[0] == 0xFF && f[1] == 0xD8 && f[2] == 0xFF) return decode_jpeg(f, out, err);
     if(f.size() < 8 || std::memcmp(f.data(), sig, 8) != 0) {
-        err = "unsupported image format (only PNG is decoded in this build)";
+        err = "unsupported image format (PNG and baseline JPEG are decoded)";
         return false;
     }
     auto be32 = [&](size_t o) {

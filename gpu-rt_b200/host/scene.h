@@ -108,7 +108,9 @@ private:
 /* Procedural stand-in for media/sponza (geometry blob missing from the snapshot). */
 void make_sponza_standin(Scene& scene);
 
-/* PNG (zlib) decode for glTF textures; returns false for formats not supported yet (JPEG). */
+/* glTF texture decode to RGBA8 with the reference's (tinygltf -> stb_image, 4 channels requested)
+ * results: PNG (zlib; 8-bit, non-interlaced) and baseline JPEG (jpeg.cpp). */
 bool decode_image(const std::vector<uint8_t>& file, Texture& out, std::string& err);
+bool decode_jpeg(const std::vector<uint8_t>& file, Texture& out, std::string& err);
 
 } // namespace gpurt

@@ -176,6 +176,8 @@ int gpurt_scene_set_transform(gpurt_scene* scene, uint32_t obj, const float mode
 /* RTPipe::build_textures (src/vk/rt.cpp:430-455): RGBA8, sampled as sRGB, linear, repeat. */
 int gpurt_scene_add_texture(gpurt_scene* scene, const uint8_t* rgba8, uint32_t w, uint32_t h,
                             int32_t* out_tex_index);
+/* Texture `tex` as uploaded (RGBA8, row-major): sizes first (rgba8_out may be NULL), then the texels. */
+int gpurt_scene_get_texture(const gpurt_scene* scene, uint32_t tex, uint32_t* w, uint32_t* h, uint8_t* rgba8_out);
 int gpurt_scene_counts(const gpurt_scene* scene, uint32_t* n_objs, uint32_t* n_tris,
                        uint32_t* n_lights, uint32_t* n_textures);
 /* n_objs+1 prefix offsets: global prim id -> (object, primitive). */

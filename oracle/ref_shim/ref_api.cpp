@@ -66,6 +66,12 @@ void ref_scene_free(void* h) { delete(RefScene*)h; }
 int ref_scene_n_objs(void* h) { return (int)((RefScene*)h)->objs.size(); }
 int ref_scene_n_lights(void* h) { return (int)((RefScene*)h)->lights.size(); }
 int ref_scene_n_textures(void* h) { return (int)((RefScene*)h)->scene.n_textures(); }
+/* decoded texture i (tinygltf -> stb_image, RGBA8): sizes, then texels when rgba != NULL */
+void ref_texture_get(void* h, int i, unsigned* w, unsigned* ht, unsigned char* rgba) {
+    const Util::Image& im = ((RefScene*)h)->scene.images()[i];
+    *w = im.w(), *ht = im.h();
+    if(rgba) std::memcpy(rgba, im.data(), im.bytes());
+}
 void ref_obj_counts(void* h, int i, unsigned* nv, unsigned* ni, unsigned* id) {
     RefObj& o = ((RefScene*)h)->objs[i];
     *nv = o.mesh->verts().size();

@@ -8,6 +8,7 @@ Scene_Desc / Scene_Light packing) bit for bit: floats are stored as uint32 words
 
     make -C oracle ref && python tests/golden/make_golden.py
 """
+import base64
 import ctypes as C
 import hashlib
 import json
@@ -59,6 +60,40 @@ def dump_scene(rel, scale):
     return out
 
 
+def dump_textures(gltf_path, names):
+    """SHA-256 of every texture of `gltf_path` as decoded by the reference (tinygltf -> stb_image, RGBA8)"""
+    h = C.c_void_p(ref.ref_scene_load(gltf_path.encode(), 1.0))
+    out = []
+    for i in range(ref.ref_scene_n_textures(h)):
+        w, ht = C.c_uint(), C.c_uint()
+        ref.ref_texture_get(h, i, C.byref(w), C.byref(ht), None)
+        px = np.zeros((ht.value, w.value, 4), np.uint8)
+        ref.ref_texture_get(h, i, C.byref(w), C.byref(ht), vp(px))
+        out.append({"file": names[i], "w": w.value, "h": ht.value, "sha256": hashlib.sha256(px.tobytes()).hexdigest()})
+    ref.ref_scene_free(h)
+    return out
+
+
+def texture_gltf(directory, files, out_path):
+    """one-triangle glTF (the reference's parse_mesh needs a material) whose textures are `files`,
+    symlinked next to it (tinygltf resolves image URIs relative to the glTF)"""
+    for f in files:
+        os.symlink(os.path.join(directory, f), os.path.join(os.path.dirname(out_path), f))
+    pos = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32)
+    blob = pos.tobytes() + np.array([0, 1, 2], np.uint16).tobytes() + b"\0\0"
+    g = {"asset": {"version": "2.0"}, "scene": 0, "scenes": [{"nodes": [0]}], "nodes": [{"mesh": 0}],
+         "meshes": [{"primitives": [{"attributes": {"POSITION": 0}, "indices": 1, "material": 0}]}],
+         "materials": [{"pbrMetallicRoughness": {"baseColorTexture": {"index": 0}}}],
+         "textures": [{"source": i} for i in range(len(files))],
+         "images": [{"uri": f} for f in files],
+         "buffers": [{"byteLength": len(blob), "uri": "data:application/octet-stream;base64," + base64.b64encode(blob).decode()}],
+         "bufferViews": [{"buffer": 0, "byteOffset": 0, "byteLength": 36}, {"buffer": 0, "byteOffset": 36, "byteLength": 6}],
+         "accessors": [{"bufferView": 0, "componentType": 5126, "count": 3, "type": "VEC3", "min": [0, 0, 0], "max": [1, 1, 0]},
+                       {"bufferView": 1, "componentType": 5123, "count": 3, "type": "SCALAR"}]}
+    with open(out_path, "w") as f:
+        json.dump(g, f)
+
+
 def dump_camera(mode, w, h, pos, center, fov):
     o = np.zeros(64, np.float32)
     p = np.array(pos or (0, 0, 0), np.float32)
@@ -76,6 +111,17 @@ def main():
                      dump_camera(1, 1920, 1080, [0.5, 0.6, 2.6], [0.5, 0.45, 0.0], 50.0),
                      dump_camera(1, 800, 600, [0.0, 10.0, 0.0], [0.0, 0.0, 0.0], 70.0),
                      dump_camera(1, 640, 480, [3.0, 2.0, 4.0], [0.0, 0.0, 0.0], 60.0)]}
+    # textures: the committed synthetic set, and every texture of media/sponza (the .jpg / .png files are in
+    # the reference snapshot even though Sponza.bin is not) through a scratch glTF with absolute image paths
+    synth = os.path.join(ROOT, "tests", "data", "synth")
+    names = [im["uri"] for im in json.load(open(os.path.join(synth, "textures.gltf")))["images"]]
+    g["synth_textures"] = dump_textures(os.path.join(synth, "textures.gltf"), names)
+    sponza = os.path.join(REF_MEDIA, "sponza")
+    files = sorted(f for f in os.listdir(sponza) if f.endswith((".jpg", ".png")))
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        texture_gltf(sponza, files, os.path.join(tmp, "sponza_textures.gltf"))
+        g["sponza_textures"] = dump_textures(os.path.join(tmp, "sponza_textures.gltf"), files)
     with open(os.path.join(HERE, "ref_host_golden.json"), "w") as f:
         json.dump(g, f, indent=0, separators=(",", ":"))
     print("wrote", os.path.join(HERE, "ref_host_golden.json"))

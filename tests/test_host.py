@@ -186,3 +186,79 @@ def test_gltf_features_embedded_buffers_png_textures_glb_strip_fan(gpurt, tmp_pa
     p.write_bytes(glb)
     s = gpurt.Scene(None).load(str(p))
     assert list(s.object(0)[1]) == expect[5] and s.counts()["textures"] == 2
+
+
+def _texture_hashes(scene):
+    return [(t.shape[1], t.shape[0], hashlib.sha256(t.tobytes()).hexdigest())
+            for t in (scene.texture(i) for i in range(scene.counts()["textures"]))]
+
+
+def test_texture_decode_matches_reference_decoder(gpurt):
+    """JPEG (baseline + progressive, 4:4:4 / 4:2:2 / 4:2:0 / 4:1:1, gray, restart intervals, optimised tables) and
+    PNG (RGB, RGBA, gray, gray+alpha, palette) decode to the bytes the reference's tinygltf -> stb_image path
+    produced for the same files (tests/golden/make_golden.py)"""
+    s = gpurt.Scene(None).load(os.path.join(ROOT, "tests", "data", "synth", "textures.gltf"))
+    assert "[warn]" not in gpurt.last_error()
+    got = _texture_hashes(s)
+    assert len(got) == len(GOLDEN["synth_textures"]) == 22
+    for g, (w, h, sha) in zip(GOLDEN["synth_textures"], got):
+        assert (g["w"], g["h"], g["sha256"]) == (w, h, sha), g["file"]
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/media/sponza"), reason="reference media not present")
+def test_sponza_textures_match_reference_decoder(gpurt, tmp_path):
+    """all 69 textures of media/sponza (65 baseline JPEG, 4 PNG; up to 2048^2) decode bit-identically to the reference"""
+    src = "/root/reference/media/sponza"
+    files = [g["file"] for g in GOLDEN["sponza_textures"]]
+    for f in files:
+        os.symlink(os.path.join(src, f), tmp_path / f)
+    pos = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32)
+    blob = pos.tobytes() + np.array([0, 1, 2], np.uint16).tobytes() + b"\0\0"
+    g = {"asset": {"version": "2.0"}, "scene": 0, "scenes": [{"nodes": [0]}], "nodes": [{"mesh": 0}],
+         "meshes": [{"primitives": [{"attributes": {"POSITION": 0}, "indices": 1}]}],
+         "textures": [{"source": i} for i in range(len(files))], "images": [{"uri": f} for f in files],
+         "buffers": [{"byteLength": len(blob), "uri": "data:application/octet-stream;base64," + base64.b64encode(blob).decode()}],
+         "bufferViews": [{"buffer": 0, "byteOffset": 0, "byteLength": 36}, {"buffer": 0, "byteOffset": 36, "byteLength": 6}],
+         "accessors": [{"bufferView": 0, "componentType": 5126, "count": 3, "type": "VEC3"},
+                       {"bufferView": 1, "componentType": 5123, "count": 3, "type": "SCALAR"}]}
+    (tmp_path / "t.gltf").write_text(json.dumps(g))
+    s = gpurt.Scene(None).load(str(tmp_path / "t.gltf"))
+    got = _texture_hashes(s)
+    assert len(got) == 69
+    for gt, (w, h, sha) in zip(GOLDEN["sponza_textures"], got):
+        assert (gt["w"], gt["h"], gt["sha256"]) == (w, h, sha), gt["file"]
+
+
+def test_corrupt_images_fall_back_to_a_placeholder_with_a_warning(gpurt, tmp_path):
+    """truncated / garbage JPEG and PNG never crash the loader: 1x1 white placeholder + [warn] in last_error"""
+    good = open(os.path.join(ROOT, "tests", "data", "synth", "j420_37x23_q92.jpg"), "rb").read()
+    variants = {"trunc.jpg": good[: len(good) // 2], "head.jpg": good[:40], "noise.jpg": good[:200] + bytes(range(256)) * 4,
+                "soi_only.jpg": b"\xff\xd8\xff", "bad.png": b"\x89PNG\r\n\x1a\n" + b"\0" * 30}
+    rng = np.random.default_rng(5)
+    for k in range(12):      # random byte corruption inside the entropy-coded data
+        b = bytearray(good)
+        for p in rng.integers(300, len(b) - 2, 6):
+            b[p] = int(rng.integers(0, 256))
+        variants[f"fuzz{k}.jpg"] = bytes(b)
+    files = sorted(variants)
+    for f in files:
+        (tmp_path / f).write_bytes(variants[f])
+    pos = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32)
+    blob = pos.tobytes() + np.array([0, 1, 2], np.uint16).tobytes() + b"\0\0"
+    g = {"asset": {"version": "2.0"}, "scene": 0, "scenes": [{"nodes": [0]}], "nodes": [{"mesh": 0}],
+         "meshes": [{"primitives": [{"attributes": {"POSITION": 0}, "indices": 1}]}],
+         "textures": [{"source": i} for i in range(len(files))], "images": [{"uri": f} for f in files],
+         "buffers": [{"byteLength": len(blob), "uri": "data:application/octet-stream;base64," + base64.b64encode(blob).decode()}],
+         "bufferViews": [{"buffer": 0, "byteOffset": 0, "byteLength": 36}, {"buffer": 0, "byteOffset": 36, "byteLength": 6}],
+         "accessors": [{"bufferView": 0, "componentType": 5126, "count": 3, "type": "VEC3"},
+                       {"bufferView": 1, "componentType": 5123, "count": 3, "type": "SCALAR"}]}
+    (tmp_path / "t.gltf").write_text(json.dumps(g))
+    s = gpurt.Scene(None).load(str(tmp_path / "t.gltf"))
+    assert s.counts()["textures"] == len(files)
+    assert "[warn]" in gpurt.last_error()
+    for i, f in enumerate(files):
+        t = s.texture(i)
+        if f in ("head.jpg", "soi_only.jpg", "bad.png"):    # no image data at all
+            assert t.shape == (1, 1, 4) and (t == 255).all(), f
+        else:                                                # damaged data decodes to something of the right size, or not at all
+            assert t.shape in ((1, 1, 4), (23, 37, 4)), f

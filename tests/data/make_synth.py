@@ -66,6 +66,102 @@ def main():
     with open(j("textures.gltf"), "w") as f:
         json.dump(g, f, indent=1)
     print(len(files), "images ->", OUT)
+    features()
+
+
+def features():
+    """features.gltf: nested node matrices (the reference composes them as T * M.T(), scene.cpp:355), a TRS node
+    (ignored), one mesh instanced twice, several primitives per mesh, triangle list / strip / fan,
+    u8 / u16 / u32 indices, interleaved (byteStride) and tightly packed attributes, NORMAL / TANGENT / TEXCOORD_0
+    present or missing, emissive materials (lights), texture references"""
+    r = np.random.default_rng(21)
+    chunks, views, accs = [], [], []
+
+    def add(arr, ctype, atype, stride=None, target_off=0):
+        raw = arr.tobytes()
+        off = sum(len(c) for c in chunks)
+        pad = (-len(raw)) % 4
+        chunks.append(raw + b"\0" * pad)
+        v = {"buffer": 0, "byteOffset": off, "byteLength": len(raw)}
+        if stride:
+            v["byteStride"] = stride
+        views.append(v)
+        return len(views) - 1
+
+    def acc(view, ctype, count, atype, off=0):
+        accs.append({"bufferView": view, "byteOffset": off, "componentType": ctype, "count": count, "type": atype})
+        return len(accs) - 1
+
+    def grid(n):   # (n+1)^2 vertices, triangle list
+        u = np.linspace(0, 1, n + 1, dtype=np.float32)
+        x, y = np.meshgrid(u, u, indexing="ij")
+        p = np.stack([x, y, 0.2 * np.sin(5 * x) * np.cos(3 * y)], -1).reshape(-1, 3).astype(np.float32)
+        ix = []
+        for i in range(n):
+            for j in range(n):
+                a = i * (n + 1) + j
+                ix += [a, a + n + 1, a + 1, a + 1, a + n + 1, a + n + 2]
+        return p, np.array(ix)
+
+    # mesh 0 / primitive 0: tightly packed POSITION NORMAL TANGENT TEXCOORD_0, u16 triangle list
+    p, ix = grid(6)
+    nrm = r.standard_normal((len(p), 3)).astype(np.float32)
+    tan = r.standard_normal((len(p), 4)).astype(np.float32)
+    uv = r.random((len(p), 2), dtype=np.float32)
+    a_p = acc(add(p, 0, 0), 5126, len(p), "VEC3")
+    a_n = acc(add(nrm, 0, 0), 5126, len(p), "VEC3")
+    a_t = acc(add(tan, 0, 0), 5126, len(p), "VEC4")
+    a_uv = acc(add(uv, 0, 0), 5126, len(p), "VEC2")
+    a_i = acc(add(ix.astype(np.uint16), 0, 0), 5123, len(ix), "SCALAR")
+    prim0 = {"attributes": {"POSITION": a_p, "NORMAL": a_n, "TANGENT": a_t, "TEXCOORD_0": a_uv}, "indices": a_i, "material": 0}
+    # mesh 0 / primitive 1: triangle strip, u8 indices, POSITION only
+    sp = r.random((9, 3), dtype=np.float32)
+    prim1 = {"attributes": {"POSITION": acc(add(sp, 0, 0), 5126, 9, "VEC3")},
+             "indices": acc(add(np.arange(9, dtype=np.uint8), 0, 0), 5121, 9, "SCALAR"), "material": 1, "mode": 5}
+    # mesh 1: triangle fan, u32 indices, interleaved POSITION + TEXCOORD_0 (stride 20)
+    inter = np.zeros((8, 5), np.float32)
+    inter[:, :3] = r.random((8, 3), dtype=np.float32) * 2 - 1
+    inter[:, 3:] = r.random((8, 2), dtype=np.float32)
+    vi = add(inter, 0, 0, stride=20)
+    prim2 = {"attributes": {"POSITION": acc(vi, 5126, 8, "VEC3"), "TEXCOORD_0": acc(vi, 5126, 8, "VEC2", off=12)},
+             "indices": acc(add(np.array([0, 1, 2, 3, 4, 5, 6, 7], np.uint32), 0, 0), 5125, 8, "SCALAR"), "material": 2, "mode": 6}
+    # mesh 2: emissive triangle list with u32 indices and normals only
+    p2, ix2 = grid(3)
+    prim3 = {"attributes": {"POSITION": acc(add(p2 * np.float32(0.5), 0, 0), 5126, len(p2), "VEC3"),
+                            "NORMAL": acc(add(r.standard_normal((len(p2), 3)).astype(np.float32), 0, 0), 5126, len(p2), "VEC3")},
+             "indices": acc(add(ix2.astype(np.uint32), 0, 0), 5125, len(ix2), "SCALAR"), "material": 3}
+
+    def mat(angle, axis, scale, t):
+        c, s_ = np.cos(angle), np.sin(angle)
+        R = np.eye(3)
+        i, j = [(1, 2), (0, 2), (0, 1)][axis]
+        R[i, i], R[i, j], R[j, i], R[j, j] = c, -s_, s_, c
+        M = np.eye(4)
+        M[:3, :3] = R * np.array(scale)
+        M[:3, 3] = t
+        return [float(x) for x in M.T.reshape(-1)]     # glTF stores column-major
+
+    blob = b"".join(chunks)
+    g = {"asset": {"version": "2.0"}, "scene": 0, "scenes": [{"nodes": [0, 2, 3]}],
+         "nodes": [{"mesh": 0, "matrix": mat(0.4, 1, (1.5, 1.5, 1.5), (1, 2, 3)), "children": [1]},
+                   {"mesh": 1, "matrix": mat(-0.9, 2, (0.5, 2.0, 1.0), (-1, 0.5, 0.25))},
+                   {"mesh": 2, "translation": [5, 5, 5], "rotation": [0, 0.7071068, 0, 0.7071068], "scale": [2, 2, 2]},
+                   {"mesh": 0, "matrix": mat(1.2, 0, (1, 1, 1), (0, -3, 0.5))}],
+         "meshes": [{"primitives": [prim0, prim1]}, {"primitives": [prim2]}, {"primitives": [prim3]}],
+         "materials": [{"pbrMetallicRoughness": {"baseColorFactor": [0.8, 0.6, 0.4, 1], "metallicFactor": 0.25, "roughnessFactor": 0.6,
+                                                 "baseColorTexture": {"index": 0}, "metallicRoughnessTexture": {"index": 1}},
+                        "normalTexture": {"index": 2}},
+                       {"pbrMetallicRoughness": {"baseColorFactor": [0.1, 0.9, 0.2, 1], "roughnessFactor": 0.0}},
+                       {"pbrMetallicRoughness": {}, "emissiveTexture": {"index": 1}},
+                       {"pbrMetallicRoughness": {"baseColorFactor": [1, 1, 1, 1]}, "emissiveFactor": [4.0, 3.0, 2.5]}],
+         "textures": [{"source": 0}, {"source": 1}, {"source": 0}],
+         "images": [{"uri": "p_rgb.png"}, {"uri": "j420_37x23_q92.jpg"}],
+         "buffers": [{"byteLength": len(blob), "uri": "features.bin"}], "bufferViews": views, "accessors": accs}
+    with open(os.path.join(OUT, "features.bin"), "wb") as f:
+        f.write(blob)
+    with open(os.path.join(OUT, "features.gltf"), "w") as f:
+        json.dump(g, f, indent=1)
+    print("features.gltf:", len(accs), "accessors,", len(blob), "bytes")
 
 
 if __name__ == "__main__":

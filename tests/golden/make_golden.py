@@ -33,8 +33,8 @@ def words(a):
     return [int(x) for x in np.ascontiguousarray(a).view(np.uint32).reshape(-1)]
 
 
-def dump_scene(rel, scale):
-    h = C.c_void_p(ref.ref_scene_load(os.path.join(REF_MEDIA, rel).encode(), scale))
+def dump_scene(rel, scale, base=REF_MEDIA):
+    h = C.c_void_p(ref.ref_scene_load(os.path.join(base, rel).encode(), scale))
     n = ref.ref_scene_n_objs(h)
     out = {"file": rel, "scale": scale, "n_textures": ref.ref_scene_n_textures(h), "objects": [], "lights": []}
     for i in range(n):
@@ -105,7 +105,9 @@ def dump_camera(mode, w, h, pos, center, fov):
 def main():
     g = {"about": "generated by tests/golden/make_golden.py from the reference's own host sources (oracle/_ref)",
          "scenes": [dump_scene("cbox/cbox.gltf", 1.0), dump_scene("cbox/cbox.gltf", 0.37),
-                    dump_scene("mis_test/mis_test.gltf", 1.0), dump_scene("cube.gltf", 1.0)],
+                    dump_scene("mis_test/mis_test.gltf", 1.0), dump_scene("cube.gltf", 1.0),
+                    dump_scene("synth/features.gltf", 1.0, os.path.join(ROOT, "tests", "data")),
+                    dump_scene("synth/features.gltf", 2.5, os.path.join(ROOT, "tests", "data"))],
          "cameras": [dump_camera(0, 1280, 720, None, None, 0.0), dump_camera(0, 1024, 1024, None, None, 0.0),
                      dump_camera(1, 1920, 1080, [-1000.0, 200.0, 0.0], [0.0, 200.0, 0.0], 90.0),
                      dump_camera(1, 1920, 1080, [0.5, 0.6, 2.6], [0.5, 0.45, 0.0], 50.0),

@@ -25,7 +25,8 @@ def _words(a):
 def test_loader_matches_reference_loader(gpurt, g):
     """glTF loader + Mat4/Pose/BBox math + Scene_Desc/Scene_Light packing == the reference's own
     Scene::load / RTPipe::build_desc, bit for bit (fixture from oracle/_ref, tests/golden/make_golden.py)"""
-    s = gpurt.Scene(None).load(os.path.join(MEDIA, g["file"]), g["scale"])
+    base = os.path.join(ROOT, "tests", "data") if g["file"].startswith("synth/") else MEDIA
+    s = gpurt.Scene(None).load(os.path.join(base, g["file"]), g["scale"])
     descs, lights = s.descs(), s.lights()
     assert len(descs) == len(g["objects"]) and len(lights) == len(g["lights"])
     assert s.counts()["textures"] == g["n_textures"]

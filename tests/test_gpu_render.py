@@ -215,3 +215,23 @@ def test_tonemap_matches_oracle(gpurt, orc, ctx):
     for op, exposure, gamma in [(0, 1.0, 2.2), (1, 1.0, 2.2), (1, 2.5, 1.8), (2, 1.0, 1.0)]:
         assert (pipe.tonemap(op, exposure, gamma) == orc.tonemap(img, op, exposure, gamma)).all(), (op, exposure, gamma)
     pipe.close(), accel.close(), scene.close()
+
+
+def test_gltf_feature_scene_with_decoded_textures(gpurt, orc, ctx):
+    """tests/data/synth/features.gltf end to end: loader (nested matrices, strip / fan, instancing), PNG + JPEG
+    texture decode, albedo / metal-rough / normal / emissive textures, an emissive light — rendered by every
+    integrator and compared with the oracle, which is given the decoded texels of the product's loader
+    (those are pinned against the reference's decoder in tests/test_host.py)"""
+    import os
+    from conftest import ROOT
+    path = os.path.join(ROOT, "tests", "data", "synth", "features.gltf")
+    cam = gpurt.camera(1, 160, 120, (4.0, 3.0, 6.0), (1.0, 1.0, 2.0), 60.0)
+    for integ in (0, 1, 2, 4):
+        scene = gpurt.Scene(ctx).load(path)
+        texs = [scene.texture(i) for i in range(scene.counts()["textures"])]
+        assert len(texs) == 3 and scene.counts()["lights"] == 2
+        img = _run(gpurt, orc, ctx, "features", 160, 120, 2, cam=cam, textures=texs, scene=scene, integrator=integ,
+                   brdf=integ % 2, samples_per_frame=2, max_depth=3, use_normal_map=1, use_metalness=1, env_scale=0.5,
+                   seed=77 + integ)
+        assert img[..., :3].mean() > 0.001
+        scene.close()

@@ -235,3 +235,38 @@ def test_gltf_feature_scene_with_decoded_textures(gpurt, orc, ctx):
                    seed=77 + integ)
         assert img[..., :3].mean() > 0.001
         scene.close()
+
+
+def test_headless_cli_writes_the_same_image_as_the_api(gpurt, orc, ctx, tmp_path):
+    """gpurt_render (the headless replacement of GPURT::loop + save_rt, src/gpurt.cpp:258-262) renders cbox until
+    trace() reports convergence and writes a PNG; its pixels equal the tonemapped image of the same sequence of
+    frames driven through the Python binding, which equals the oracle's tonemap of the oracle's image"""
+    import os
+    import subprocess
+    from conftest import MEDIA, ROOT
+    Image = pytest.importorskip("PIL.Image")
+    exe = os.path.join(ROOT, "gpu-rt_b200", "gpurt_render")
+    out = str(tmp_path / "cli.png")
+    w, h, frames, spp = 160, 96, 3, 2
+    r = subprocess.run([exe, "-s", os.path.join(MEDIA, "cbox", "cbox.gltf"), "-o", out, "--size", str(w), str(h), "--frames", str(frames),
+                        "--spp", str(spp), "--depth", "4", "--integrator", "2", "--brdf", "1", "--seed", "9", "--tonemap", "1",
+                        "--exposure", "1.5"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert "16732 tris" in r.stdout
+    cli = np.array(Image.open(out).convert("RGBA"))
+    scene = load_scene(gpurt, ctx, "cbox")
+    accel = gpurt.Accel(scene)
+    pipe = gpurt.RTPipe(scene, accel)
+    rs, st = orc.RenderScene(scene), orc.FrameState(w, h)
+    prm = gpurt.pipe_params(max_frames=frames, samples_per_frame=spp, max_depth=4, integrator=2, brdf=1, seed=9)
+    cam = gpurt.camera(0, w, h)
+    n = 0
+    while pipe.render_frame(prm, cam, w, h) == 0:
+        consts, ubo, seed_word = pipe.last_uniforms()
+        orc.render_frame(rs, st, consts, ubo, seed_word ^ int(consts[8]))
+        n += 1
+    assert n == frames + 2                 # frames 0, 0, 1, ..., max_frames
+    api = pipe.tonemap(1, 1.5, 2.2)
+    assert cli.shape == api.shape and (cli == api).all()
+    assert (api == orc.tonemap(st.image, 1, 1.5, 2.2)).all()
+    pipe.close(), accel.close(), scene.close()

@@ -107,15 +107,6 @@ template <typename T> static int scan_rec(cudaStream_t st, const T* in, T* out, 
     GPURT_CUDA(cudaGetLastError());
     return GPURT_OK;
 }
-/* After the call tmp[0] of the top level is NOT the total; callers that need the total append a
- * zero element and read out[n]. */
-int exclusive_scan_u32(cudaStream_t st, const uint32_t* in, uint32_t* out, size_t n, DevBuf& tmp) {
-    if(n == 0) return GPURT_OK;
-    int rc = tmp.reserve(scan_tmp_bytes(n));
-    if(rc) return rc;
-    return scan_rec<uint32_t>(st, in, out, n, tmp.as<uint32_t>());
-}
-
 /* ---- radix sort ------------------------------------------------------------------------------- */
 /* Stable LSD radix sort of 64-bit keys with a 32-bit payload, 8 bits per pass, "onesweep" style:
  * one kernel histograms all 8 digits of every key, then each pass is ONE kernel that ranks a tile of

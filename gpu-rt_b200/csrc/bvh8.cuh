@@ -384,21 +384,4 @@ GPURT_HD float child_dist2(const Node8& n, const ChildDist& c, int i, unsigned o
     return fmaf(dx, dx, fmaf(dy, dy, dz * dz));
 }
 
-/* squared distance from p to child i's decoded box (reference form of the above) */
-GPURT_HD float node_child_dist2(const Node8& n, int i, F3 p) {
-    unsigned eb = f2u(n.v[0].w);
-    float sx = u2f((eb & 0xffu) << 23), sy = u2f(((eb >> 8) & 0xffu) << 23),
-          sz = u2f(((eb >> 16) & 0xffu) << 23);
-    float lox = fmaf((float)byte_of(f2u(n.v[2].x), f2u(n.v[2].y), i), sx, n.v[0].x);
-    float loy = fmaf((float)byte_of(f2u(n.v[2].z), f2u(n.v[2].w), i), sy, n.v[0].y);
-    float loz = fmaf((float)byte_of(f2u(n.v[3].x), f2u(n.v[3].y), i), sz, n.v[0].z);
-    float hix = fmaf((float)byte_of(f2u(n.v[3].z), f2u(n.v[3].w), i), sx, n.v[0].x);
-    float hiy = fmaf((float)byte_of(f2u(n.v[4].x), f2u(n.v[4].y), i), sy, n.v[0].y);
-    float hiz = fmaf((float)byte_of(f2u(n.v[4].z), f2u(n.v[4].w), i), sz, n.v[0].z);
-    float dx = fmaxf(fmaxf(lox - p.x, p.x - hix), 0.0f);
-    float dy = fmaxf(fmaxf(loy - p.y, p.y - hiy), 0.0f);
-    float dz = fmaxf(fmaxf(loz - p.z, p.z - hiz), 0.0f);
-    return fmaf(dx, dx, fmaf(dy, dy, dz * dz));
-}
-
 } // namespace gpurt

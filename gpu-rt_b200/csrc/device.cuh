@@ -41,7 +41,6 @@ struct gpurt_ctx {
     /* host-buffer calls: copy streams and hand-over events of the H2D -> kernel -> D2H pipeline */
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
     cudaEvent_t ev_copy = nullptr, ev_kernel = nullptr;
-    float last_ms = 0;
     /* staging for GPURT_MEM_HOST calls */
     gpurt::DevBuf d_in, d_out;
     gpurt::DevBuf scratch;
@@ -69,8 +68,6 @@ struct DeviceScene {
 int upload_scene(gpurt_ctx* ctx, gpurt_scene* s, DeviceScene& out);
 void free_scene(DeviceScene& d);
 
-/* exclusive prefix sum of n u32 values (in place allowed), returns total via d_total (device) */
-int exclusive_scan_u32(cudaStream_t st, const uint32_t* in, uint32_t* out, size_t n, DevBuf& tmp);
 size_t scan_tmp_bytes(size_t n);
 
 /* stable LSD radix sort of 64-bit keys with 32-bit payload, 8 bits per pass */

@@ -249,22 +249,39 @@ __global__ void __launch_bounds__(128) k_tail(const __grid_constant__ FrameParam
     }
 }
 
+/* rt.rgen:640-645: progressive mean over frames */
+__device__ __forceinline__ float4 accumulate_frame(float4 old, F3 avg, int frame) {
+    if(frame > 0) {
+        F3 m = mix3(F3{old.x, old.y, old.z}, avg, 1.0f / (float)(frame + 1));
+        return make_float4(m.x, m.y, m.z, 1.0f);
+    }
+    return make_float4(avg.x, avg.y, avg.z, 1.0f);
+}
+
+/* frame-parallel sharding: fold the frame mean another GPU rendered into this pipe's image */
+__global__ void __launch_bounds__(256) k_accumulate_mean(float4* __restrict__ image, const float4* __restrict__ mean,
+                                                         uint32_t n, int frame) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) return;
+    float4 m = mean[i];
+    image[i] = accumulate_frame(frame > 0 ? image[i] : m, F3{m.x, m.y, m.z}, frame);
+}
+
 __global__ void __launch_bounds__(256) k_frame_end(const __grid_constant__ FrameParams P, const float4* acc,
                                                    float4* image, const float4* gpos, const float4* gnorm,
-                                                   const float4* ppos, const float4* pnorm, const float4* palb) {
+                                                   const float4* ppos, const float4* pnorm, const float4* palb,
+                                                   float4* mean_out) {
     uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
     if(li >= P.n_local) return;
     const uint32_t i = shard_pixel(P, li);
     float4 a = acc[i];
     F3 avg = F3{a.x, a.y, a.z} / (float)P.c.samples; /* rt.rgen:638 */
+    if(mean_out) { /* frame-parallel sharding: hand the frame mean to the accumulating rank, leave the image alone */
+        mean_out[i] = make_float4(avg.x, avg.y, avg.z, 1.0f);
+        return;
+    }
     float4 out;
-    if(P.c.frame > 0) {
-        float t = 1.0f / (float)(P.c.frame + 1);
-        float4 o = image[i];
-        F3 m = mix3(F3{o.x, o.y, o.z}, avg, t);
-        out = make_float4(m.x, m.y, m.z, 1.0f);
-    } else
-        out = make_float4(avg.x, avg.y, avg.z, 1.0f);
+    out = accumulate_frame(P.c.frame > 0 ? image[i] : make_float4(0, 0, 0, 0), avg, P.c.frame);
     if(P.c.debug_view > 0) { /* rt.rgen:647-672 */
         float4 gp = gpos[i], gn = gnorm[i];
         F4 pp = mul4(P.cam.prev_PV, gp.x, gp.y, gp.z, 1.0f);
@@ -414,7 +431,10 @@ int gpurt_pipe_frame_index(const gpurt_pipe* p, int32_t* f) {
     return GPURT_OK;
 }
 
-int gpurt_pipe_render_frame(gpurt_pipe* p, const GpurtPipeParams* prm, const GpurtCamera* cam, uint32_t w, uint32_t h) {
+/* forced_frame < 0: the reference's frame logic (update_uniforms + trace).  forced_frame >= 0: render exactly that
+ * frame of the progressive sequence and write its per-pixel mean to mean_out instead of accumulating. */
+static int render_core(gpurt_pipe* p, const GpurtPipeParams* prm, const GpurtCamera* cam, uint32_t w, uint32_t h,
+                       int forced_frame, float4* mean_out) {
     if(!p || !prm || !cam || !w || !h) return set_error("bad argument"), GPURT_E_INVALID;
     if(prm->samples_per_frame < 1 || prm->max_depth < 0) return set_error("bad sample / depth count"), GPURT_E_INVALID;
     gpurt_ctx* ctx = p->ctx;
@@ -436,7 +456,7 @@ int gpurt_pipe_render_frame(gpurt_pipe* p, const GpurtPipeParams* prm, const Gpu
         Mat4 pv = oP * oV;
         std::memcpy(F.cam.prev_PV, pv.data(), 64);
     }
-    if(p->frame >= 0 && (!p->old_cam_init || std::memcmp(cam->V, p->old_cam.V, 64 * 4) != 0)) {
+    if(forced_frame < 0 && p->frame >= 0 && (!p->old_cam_init || std::memcmp(cam->V, p->old_cam.V, 64 * 4) != 0)) {
         p->frame = -1; /* reset_frame() */
         std::memcpy(p->old_cam.V, cam->V, 64 * 4);
         p->old_cam_init = true;
@@ -445,7 +465,7 @@ int gpurt_pipe_render_frame(gpurt_pipe* p, const GpurtPipeParams* prm, const Gpu
     /* ---- RTPipe::trace (rt.cpp:346-394) ---- */
     int rc = pipe_resize(p, w, h, (uint32_t)prm->max_depth);
     if(rc) return rc;
-    if(p->frame >= prm->max_frames) return 1;
+    if(forced_frame < 0 && p->frame >= prm->max_frames) return 1;
     GpurtConstants& c = F.c;
     c.clear_col[0] = prm->clear[0], c.clear_col[1] = prm->clear[1], c.clear_col[2] = prm->clear[2], c.clear_col[3] = 1.0f;
     c.env_light[0] = prm->env_scale * prm->env[0], c.env_light[1] = prm->env_scale * prm->env[1];
@@ -454,7 +474,7 @@ int gpurt_pipe_render_frame(gpurt_pipe* p, const GpurtPipeParams* prm, const Gpu
     c.use_metalness = prm->use_metalness, c.integrator = prm->integrator, c.brdf = prm->brdf, c.use_rr = prm->use_rr;
     c.max_frame = prm->max_frames, c.qmc = prm->use_qmc, c.use_temporal = prm->use_temporal, c.debug_view = prm->debug_view;
     c.n_lights = (int)p->accel->dscene.n_lights, c.n_objs = (int)p->accel->dscene.n_objs;
-    c.frame = ++p->frame;
+    c.frame = forced_frame < 0 ? ++p->frame : forced_frame;
     F.W = w, F.H = h;
     F.seed_val = prm->seed ^ (uint32_t)c.frame;
 
@@ -506,11 +526,33 @@ int gpurt_pipe_render_frame(gpurt_pipe* p, const GpurtPipeParams* prm, const Gpu
         /* closest-hit rays of the wavefront = sum of queue sizes */
     }
     k_frame_end<<<cdivu(n, 256), 256, 0, st>>>(F, p->acc, p->image, p->gbuf[cur][0], p->gbuf[cur][1], p->gbuf[prev][0],
-                                              p->gbuf[prev][1], p->gbuf[prev][2]);
+                                              p->gbuf[prev][1], p->gbuf[prev][2], mean_out);
     GPURT_CUDA(cudaEventRecord(ctx->ev1, st));
     GPURT_CUDA(cudaGetLastError());
     p->parity ^= 1;
     p->last = F;
+    return GPURT_OK;
+}
+
+int gpurt_pipe_render_frame(gpurt_pipe* p, const GpurtPipeParams* prm, const GpurtCamera* cam, uint32_t w, uint32_t h) {
+    return render_core(p, prm, cam, w, h, -1, nullptr);
+}
+int gpurt_pipe_render_frame_mean(gpurt_pipe* p, const GpurtPipeParams* prm, const GpurtCamera* cam, uint32_t w, uint32_t h,
+                                 int32_t frame, void* mean_out_device) {
+    if(!prm || frame < 0 || !mean_out_device) return set_error("bad argument"), GPURT_E_INVALID;
+    if(prm->integrator > 2) return set_error("frame-parallel rendering needs an integrator without temporal reuse (0-2)"), GPURT_E_INVALID;
+    return render_core(p, prm, cam, w, h, frame, (float4*)mean_out_device);
+}
+int gpurt_pipe_accumulate_mean(gpurt_pipe* p, const void* mean_device, int32_t frame, uint32_t w, uint32_t h) {
+    if(!p || !mean_device || frame < 0 || !w || !h) return set_error("bad argument"), GPURT_E_INVALID;
+    GPURT_CUDA(cudaSetDevice(p->ctx->device));
+    if(!p->image || p->w != w || p->h != h) return set_error("accumulate: the pipe has no image of this size (render or resize first)"), GPURT_E_STATE;
+    cudaStream_t st = p->ctx->stream;
+    GPURT_CUDA(cudaEventRecord(p->ctx->ev0, st));
+    k_accumulate_mean<<<cdivu(w * h, 256), 256, 0, st>>>(p->image, (const float4*)mean_device, w * h, frame);
+    GPURT_CUDA(cudaEventRecord(p->ctx->ev1, st));
+    GPURT_CUDA(cudaGetLastError());
+    p->frame = frame;
     return GPURT_OK;
 }
 

@@ -90,7 +90,7 @@ SYMBOLS = [
     "gpurt_pipe_render_frame", "gpurt_pipe_frame_index", "gpurt_pipe_read_image", "gpurt_pipe_read_gbuffer",
     "gpurt_pipe_ray_counts", "gpurt_pipe_device_image", "gpurt_tonemap", "gpurt_pipe_last_uniforms",
     "gpurt_pipe_read_reservoirs", "gpurt_pipe_bounce_rays", "gpurt_pipe_set_shard",
-    "gpurt_scene_set_transform", "gpurt_accel_update", "gpurt_scene_get_texture", "gpurt_shared_alloc", "gpurt_shared_free", "gpurt_shared_open", "gpurt_shared_close",
+    "gpurt_pipe_render_frame_mean", "gpurt_pipe_accumulate_mean", "gpurt_scene_set_transform", "gpurt_accel_update", "gpurt_scene_get_texture", "gpurt_shared_alloc", "gpurt_shared_free", "gpurt_shared_open", "gpurt_shared_close",
 ]
 
 
@@ -439,6 +439,21 @@ class RTPipe:
         f = C.c_int32()
         _check(lib.gpurt_pipe_frame_index(self.h, C.byref(f)))
         return f.value
+
+    def render_frame_mean(self, params, cam, width, height, frame, mean_out):
+        """frame-parallel sharding: render frame `frame`, write its per-pixel mean to mean_out (device tensor of
+        w*h*4 f32 or SharedBuffer.at(offset))"""
+        self.ctx.use_torch_stream()
+        self.w, self.h_px = width, height
+        ptr, mem, _keep = _ptr(mean_out)
+        assert mem == MEM_DEVICE
+        return _check(lib.gpurt_pipe_render_frame_mean(self.h, C.byref(params), C.byref(cam), width, height, int(frame), ptr))
+
+    def accumulate_mean(self, mean, frame, width, height):
+        self.ctx.use_torch_stream()
+        ptr, mem, _keep = _ptr(mean)
+        assert mem == MEM_DEVICE
+        _check(lib.gpurt_pipe_accumulate_mean(self.h, ptr, int(frame), width, height))
 
     def read_image(self, out=None):
         if out is None:

@@ -264,6 +264,16 @@ int gpurt_pipe_frame_index(const gpurt_pipe* pipe, int32_t* out_frame);
  * an unsharded frame (integrators 0-2; ReSTIR's temporal pass reads neighbouring pixels of the previous
  * frame and needs the whole previous frame on the rank).  band_rows = 0 restores whole-frame rendering. */
 int gpurt_pipe_set_shard(gpurt_pipe* pipe, uint32_t band_rows, uint32_t n_shards, uint32_t shard);
+/* Frame-parallel sharding (integrators 0-2, whose frames are independent given the frame index): render frame
+ * `frame` of the progressive sequence — same RNG streams as RTPipe::trace would use for it — and write the
+ * per-pixel mean of its samples (rt.rgen:638) to mean_out_device (w*h RGBA32F, may be a gpurt_shared_open
+ * mapping of another GPU's memory) without touching this pipe's accumulated image or frame counter. */
+int gpurt_pipe_render_frame_mean(gpurt_pipe* pipe, const GpurtPipeParams* params, const GpurtCamera* cam,
+                                 uint32_t width, uint32_t height, int32_t frame, void* mean_out_device);
+/* image = frame == 0 ? mean : mix(image, mean, 1/(frame+1)) (rt.rgen:640-645); call for frame = 0, 1, 2, ...
+ * in order: the result is bit-identical to rendering the frames one after the other on one GPU. */
+int gpurt_pipe_accumulate_mean(gpurt_pipe* pipe, const void* mean_device, int32_t frame, uint32_t width,
+                               uint32_t height);
 /* rt_target (RGBA32F, src/gpurt.cpp:189-193) -> caller buffer of width*height*4 floats. */
 int gpurt_pipe_read_image(gpurt_pipe* pipe, float* out_rgba, int mem);
 /* which: 0 position, 1 normal, 2 albedo (rt.rgen:674-676) */

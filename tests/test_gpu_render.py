@@ -270,3 +270,35 @@ def test_headless_cli_writes_the_same_image_as_the_api(gpurt, orc, ctx, tmp_path
     assert cli.shape == api.shape and (cli == api).all()
     assert (api == orc.tonemap(st.image, 1, 1.5, 2.2)).all()
     pipe.close(), accel.close(), scene.close()
+
+
+def test_frame_parallel_equals_sequential(gpurt, ctx):
+    """gpurt_pipe_render_frame_mean + gpurt_pipe_accumulate_mean (frame-parallel multi-GPU sharding): frames rendered
+    out of order into separate buffers and folded in order give the bits of the ordinary progressive loop"""
+    import torch
+    w, h, frames = 200, 120, 5
+    scene = load_scene(gpurt, ctx, "cbox")
+    accel = gpurt.Accel(scene)
+    prm = gpurt.pipe_params(max_frames=frames - 1, samples_per_frame=3, max_depth=4, integrator=2, brdf=1, seed=21)
+    cam = gpurt.camera(0, w, h)
+    seq = gpurt.RTPipe(scene, accel)
+    n = 0
+    while seq.render_frame(prm, cam, w, h) == 0:
+        n += 1
+    assert n == frames + 1                      # 0, 0, 1, ..., frames-1
+    want = seq.read_image()
+    par = gpurt.RTPipe(scene, accel)
+    other = gpurt.RTPipe(scene, accel)          # stands in for another GPU
+    means = torch.zeros((frames, h, w, 4), dtype=torch.float32, device="cuda")
+    for f in (3, 0, 4, 2, 1):                   # any order, any pipe
+        (par if f % 2 else other).render_frame_mean(prm, cam, w, h, f, means[f])
+    for f in range(frames):
+        par.accumulate_mean(means[f], f, w, h)
+    torch.cuda.synchronize()
+    got = par.read_image()
+    assert (got.view(np.uint32) == want.view(np.uint32)).all()
+    assert par.frame_index() == frames - 1
+    with pytest.raises(gpurt.GpurtError):       # ReSTIR frames depend on the previous frame
+        par.render_frame_mean(gpurt.pipe_params(integrator=3), cam, w, h, 0, means[0])
+    for o in (seq, par, other, accel, scene):
+        o.close()

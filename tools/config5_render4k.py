@@ -24,7 +24,7 @@ sys.path.insert(0, os.path.join(ROOT, "gpu-rt_b200"))
 sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 import gpurt  # noqa: E402
-from gpurt.dist import gather_to_rank0, warmup  # noqa: E402
+from gpurt.dist import gather_to_rank0, shared_result_buffer, warmup  # noqa: E402
 
 BAND = 16
 
@@ -40,6 +40,59 @@ def render(pipe, prm, cam, w, h, ctx):
     return ms, frames
 
 
+def frame_parallel(args, ctx, scene, accel, pipe, prm, cam, w, h, rank, world, dev, label):
+    F = args.frames
+    img_bytes = w * h * 16
+    means = shared_result_buffer(ctx, F * img_bytes)      # rank 0 owns it, the others map it over NVLink
+    mine = list(range(rank, F, world))
+
+    def run():
+        ms = 0.0
+        for f in mine:
+            pipe.render_frame_mean(prm, cam, w, h, f, means.at(f * img_bytes))
+            ms += pipe.time_ms()
+        torch.cuda.synchronize()
+        return ms
+
+    run()                                                  # warm-up
+    if world > 1:
+        dist.barrier()
+    t0 = time.time()
+    ms = run()
+    if world > 1:
+        dist.barrier()                                     # every mean is in rank 0's memory
+    fold_ms = 0.0
+    if rank == 0:
+        for f in range(F):
+            pipe.accumulate_mean(means.at(f * img_bytes), f, w, h)
+            fold_ms += pipe.time_ms()
+        torch.cuda.synchronize()
+    wall = time.time() - t0
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        full = pipe.device_image()
+        identical = None
+        if args.verify:
+            ref_pipe = gpurt.RTPipe(scene, accel)
+            render(ref_pipe, prm, cam, w, h, ctx)
+            identical = bool(torch.equal(ref_pipe.device_image().view(torch.int32), full.view(torch.int32)))
+        total_s = (t.item() + fold_ms) * 1e-3
+        print(json.dumps({
+            "config": "Sponza 4K progressive path tracing (SURVEY config 5), frame-parallel sharding", "scene": label,
+            "n_gpus": world, "size": [w, h], "spp_total": args.spp * F, "frames_rendered": F, "depth": args.depth,
+            "s_total_max_rank": total_s, "render_s_max_rank": t.item() * 1e-3, "fold_ms_rank0": fold_ms, "wall_s": wall,
+            "mpaths_s": w * h * args.spp * F / total_s / 1e6, "gather_ms": 0.0,
+            "results": "frame means stored into rank 0's buffer by the frame-end kernel (gpurt_shared_*), no collective",
+            "bit_identical_to_unsharded": identical, "mean_radiance": float(torch.nanmean(full[..., :3]))}), flush=True)
+    if world > 1:
+        dist.barrier()
+    means.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--size", type=int, nargs=2, default=[3840, 2160])
@@ -48,6 +101,9 @@ def main():
     ap.add_argument("--depth", type=int, default=8)
     ap.add_argument("--verify", action="store_true")
     ap.add_argument("--out", default="")
+    ap.add_argument("--frame-parallel", action="store_true",
+                    help="shard by progressive frame instead of by row band: rank r renders frames r, r+N, ... at full "
+                         "resolution and stores their means straight into rank 0's buffer over NVLink; rank 0 folds them in order")
     ap.add_argument("--emulate-shards", type=int, default=0, help="single process: render only shard 0 of N (per-rank cost probe)")
     args = ap.parse_args()
     rank, local, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
@@ -66,6 +122,8 @@ def main():
     # max_frames-1 because frames are numbered from 0 and trace() stops when frame >= max_frames
     prm = gpurt.pipe_params(integrator=1, brdf=1, max_depth=args.depth, samples_per_frame=args.spp,
                             max_frames=args.frames - 1, use_rr=1, env_scale=1.0, seed=7)
+    if args.frame_parallel:
+        return frame_parallel(args, ctx, scene, accel, pipe, prm, cam, w, h, rank, world, dev, label)
     pipe.set_shard(BAND, args.emulate_shards or world, rank)
     render(pipe, prm, cam, w, h, ctx)                      # warm-up (allocations, L2)
     torch.cuda.synchronize()

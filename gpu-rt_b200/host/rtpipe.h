@@ -98,8 +98,7 @@ public:
 
     void reset_frame() { check(gpurt_pipe_reset_frame(h)); }
 
-    /* update_uniforms(cam) + trace(cam, cmds, ext): false when frame >= max_frames (rt.cpp:353) */
-    bool trace(const GpurtCamera& cam, unsigned width, unsigned height) {
+    GpurtPipeParams params() const {
         GpurtPipeParams p;
         gpurt_pipe_params_default(&p);
         p.max_frames = max_frames, p.samples_per_frame = samples_per_frame, p.max_depth = max_depth;
@@ -108,6 +107,19 @@ public:
         p.use_normal_map = use_normal_map, p.use_rr = use_rr, p.use_metalness = use_metalness, p.use_qmc = use_qmc;
         p.use_temporal = use_temporal, p.integrator = integrator, p.temporal_scale = temporal_scale, p.brdf = brdf;
         p.debug_view = debug_view, p.res_samples = res_samples, p.seed = seed;
+        return p;
+    }
+    /* multi-GPU, frame-parallel: render frame f into a device buffer / fold a frame mean (include/gpurt.h) */
+    void render_frame_mean(const GpurtCamera& cam, unsigned width, unsigned height, int frame, void* mean_out_device) {
+        GpurtPipeParams p = params();
+        check(gpurt_pipe_render_frame_mean(h, &p, &cam, width, height, frame, mean_out_device));
+        w_ = width, h_ = height;
+    }
+    void accumulate_mean(const void* mean_device, int frame) { check(gpurt_pipe_accumulate_mean(h, mean_device, frame, w_, h_)); }
+
+    /* update_uniforms(cam) + trace(cam, cmds, ext): false when frame >= max_frames (rt.cpp:353) */
+    bool trace(const GpurtCamera& cam, unsigned width, unsigned height) {
+        GpurtPipeParams p = params();
         int rc = gpurt_pipe_render_frame(h, &p, &cam, width, height);
         check(rc);
         w_ = width, h_ = height;

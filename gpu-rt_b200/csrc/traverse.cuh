@@ -129,69 +129,82 @@ GPURT_HD void closest_point8(const float4* __restrict__ nodes, const float4* __r
 #endif
     uint2 stack[STACK];
     int sp = 0;
-    unsigned cur = 0;
+    unsigned cur = 0;      /* entry in hand: node index, or kLeafBit | first triangle << 2 | count */
     float cur_d2 = 0.0f;
     bool have = true;
+    /* One iteration = (pop if nothing is in hand) + (expand the node in hand) + (test the leaf in hand).  A lane
+     * whose nearest child is a leaf does node and leaf work in the same iteration, so a warp with a mix of
+     * node and leaf entries keeps more lanes busy per pass (ncu: 9 of 32 lanes with one entry per iteration). */
     for(;;) {
         if(!have) {
-            if(sp == 0) break;
-            uint2 e = stack[--sp];
-            cur = e.x, cur_d2 = u2f(e.y);
-        }
-        have = false;
-        if(cur_d2 > best.d2) continue;
-        if(cur & kLeafBit) {
-            unsigned first = (cur & ~kLeafBit) >> 2, count = cur & 3u;
-            if(visit_counts) visit_counts[1] += count;
-            for(unsigned k = 0; k < count; k++) {
-                const float4* tp = tris + (size_t)(first + k) * kTriVec4;
-                float4 r0 = GPURT_LDG(tp), r1 = GPURT_LDG(tp + 1), r2v = GPURT_LDG(tp + 2);
-                float v, w;
-                float d2 = closest_point_tri(p, f3(r0.x, r0.y, r0.z), f3(r1.x, r1.y, r1.z),
-                                             f3(r2v.x, r2v.y, r2v.z), v, w);
-                unsigned gid = f2u(r0.w);
-                if(d2 < best.d2 || (d2 == best.d2 && gid < best.gid))
-                    best.d2 = d2, best.v = v, best.w = w, best.gid = gid, best.idx = first + k;
+            while(sp > 0) { /* entries pushed earlier may have fallen outside the shrinking radius */
+                uint2 e = stack[--sp];
+                if(u2f(e.y) <= best.d2) {
+                    cur = e.x, cur_d2 = u2f(e.y), have = true;
+                    break;
+                }
             }
-            continue;
+            if(!have) break;
         }
-        const float4* np = nodes + (size_t)cur * kNodeVec4;
-        Node8 node;
+        if(!(cur & kLeafBit)) {
+            have = false;
+            if(cur_d2 <= best.d2) {
+                const float4* np = nodes + (size_t)cur * kNodeVec4;
+                Node8 node;
 #pragma unroll
-        for(int k = 0; k < 5; k++) node.v[k] = GPURT_LDG(np + k);
-        if(visit_counts) visit_counts[0]++;
-        unsigned imask = f2u(node.v[0].w) >> 24;
-        unsigned child_base = f2u(node.v[1].x), tri_base = f2u(node.v[1].y);
-        unsigned m_lo = f2u(node.v[1].z), m_hi = f2u(node.v[1].w);
-        /* Nearest child continues immediately; the others are pushed (unsorted) with their box distance.
-         * A full distance sort (19-comparator network) was measured: same visit counts on surface-near
-         * queries (17.5 nodes / 21 triangles per query either way) and 10 % slower, so it is not used. */
-        unsigned near_ref = 0;
-        float near_d2 = 0.0f;
-        bool near_ok = false;
-        ChildDist cd = make_child_dist(node, p, one);
+                for(int k = 0; k < 5; k++) node.v[k] = GPURT_LDG(np + k);
+                if(visit_counts) visit_counts[0]++;
+                unsigned imask = f2u(node.v[0].w) >> 24;
+                unsigned child_base = f2u(node.v[1].x), tri_base = f2u(node.v[1].y);
+                unsigned m_lo = f2u(node.v[1].z), m_hi = f2u(node.v[1].w);
+                /* Nearest child continues immediately; the others are pushed (unsorted) with their box distance.
+                 * A full distance sort (19-comparator network) was measured: same visit counts on surface-near
+                 * queries (17.5 nodes / 21 triangles per query either way) and 10 % slower, so it is not used. */
+                unsigned near_ref = 0;
+                float near_d2 = 0.0f;
+                bool near_ok = false;
+                ChildDist cd = make_child_dist(node, p, one);
 #pragma unroll
-        for(int s = 0; s < 8; s++) {
-            unsigned meta = byte_of(m_lo, m_hi, s);
-            if(meta == 0) continue;
-            float d2 = child_dist2(node, cd, s, one);
-            if(d2 > best.d2) continue;
-            unsigned ref;
-            if((imask >> s) & 1u) ref = child_base + gpurt_popc(imask & ((1u << s) - 1u));
-            else ref = kLeafBit | ((tri_base + (meta & 31u)) << 2) | gpurt_popc(meta >> 5);
-            uint2 e;
-            if(!near_ok) {
-                near_ref = ref, near_d2 = d2, near_ok = true;
-                continue;
+                for(int s = 0; s < 8; s++) {
+                    unsigned meta = byte_of(m_lo, m_hi, s);
+                    if(meta == 0) continue;
+                    float d2 = child_dist2(node, cd, s, one);
+                    if(d2 > best.d2) continue;
+                    unsigned ref;
+                    if((imask >> s) & 1u) ref = child_base + gpurt_popc(imask & ((1u << s) - 1u));
+                    else ref = kLeafBit | ((tri_base + (meta & 31u)) << 2) | gpurt_popc(meta >> 5);
+                    uint2 e;
+                    if(!near_ok) {
+                        near_ref = ref, near_d2 = d2, near_ok = true;
+                        continue;
+                    }
+                    if(d2 < near_d2) {
+                        e.x = near_ref, e.y = f2u(near_d2);
+                        near_ref = ref, near_d2 = d2;
+                    } else
+                        e.x = ref, e.y = f2u(d2);
+                    stack[sp++] = e;
+                }
+                if(near_ok) cur = near_ref, cur_d2 = near_d2, have = true;
             }
-            if(d2 < near_d2) {
-                e.x = near_ref, e.y = f2u(near_d2);
-                near_ref = ref, near_d2 = d2;
-            } else
-                e.x = ref, e.y = f2u(d2);
-            stack[sp++] = e;
         }
-        if(near_ok) cur = near_ref, cur_d2 = near_d2, have = true;
+        if(have && (cur & kLeafBit)) {
+            have = false;
+            if(cur_d2 <= best.d2) {
+                unsigned first = (cur & ~kLeafBit) >> 2, count = cur & 3u;
+                if(visit_counts) visit_counts[1] += count;
+                for(unsigned k = 0; k < count; k++) {
+                    const float4* tp = tris + (size_t)(first + k) * kTriVec4;
+                    float4 r0 = GPURT_LDG(tp), r1 = GPURT_LDG(tp + 1), r2v = GPURT_LDG(tp + 2);
+                    float v, w;
+                    float d2 = closest_point_tri(p, f3(r0.x, r0.y, r0.z), f3(r1.x, r1.y, r1.z),
+                                                 f3(r2v.x, r2v.y, r2v.z), v, w);
+                    unsigned gid = f2u(r0.w);
+                    if(d2 < best.d2 || (d2 == best.d2 && gid < best.gid))
+                        best.d2 = d2, best.v = v, best.w = w, best.gid = gid, best.idx = first + k;
+                }
+            }
+        }
     }
 }
 

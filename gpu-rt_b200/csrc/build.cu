@@ -465,6 +465,75 @@ __global__ void __launch_bounds__(128) k_collapse_emit(Bvh2View B, unsigned n_it
     }
 }
 
+/* Levels with few items (the top of the tree, and its last levels) are launch-latency bound when every level costs
+ * three kernels and a host read-back: one CTA walks them instead — count, block scan, emit and the level switch all
+ * inside the kernel — and stops at the first level with more than COLLAPSE_SMALL items (or none).  Same node and
+ * triangle layout as the level-per-launch path. */
+constexpr int COLLAPSE_SMALL = 512;
+struct CollapseState {
+    unsigned n_items, level_base, tri_cursor, depth;
+};
+__global__ void __launch_bounds__(COLLAPSE_SMALL) k_collapse_small(Bvh2View B, int* items_a, int* items_b,
+                                                                   CollapseState* __restrict__ state,
+                                                                   Node8* __restrict__ nodes,
+                                                                   uint32_t* __restrict__ wide_order) {
+    __shared__ unsigned long long wsum[COLLAPSE_SMALL / 32];
+    __shared__ unsigned long long s_total;
+    CollapseState S = *state;
+    const unsigned i = threadIdx.x, lane = i & 31u, w = i >> 5;
+    while(S.n_items > 0 && S.n_items <= (unsigned)COLLAPSE_SMALL && S.depth < 64u) {
+        int ch[8], nt = 0, ni = 0;
+        const bool valid = i < S.n_items;
+        if(valid) ni = collapse_node(B, items_a[i], ch, nt);
+        unsigned long long v = valid ? ((unsigned long long)(unsigned)ni | ((unsigned long long)(unsigned)nt << 32)) : 0ull;
+        unsigned long long inc = v;
+#pragma unroll
+        for(int o = 1; o < 32; o <<= 1) {
+            unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
+            if(lane >= (unsigned)o) inc += t;
+        }
+        if(lane == 31) wsum[w] = inc;
+        __syncthreads();
+        if(w == 0) {
+            unsigned long long x = lane < COLLAPSE_SMALL / 32 ? wsum[lane] : 0ull;
+#pragma unroll
+            for(int o = 1; o < COLLAPSE_SMALL / 32; o <<= 1) {
+                unsigned long long t = __shfl_up_sync(0xffffffffu, x, o);
+                if(lane >= (unsigned)o) x += t;
+            }
+            if(lane < COLLAPSE_SMALL / 32) wsum[lane] = x;
+            if(lane == COLLAPSE_SMALL / 32 - 1) s_total = x;
+        }
+        __syncthreads();
+        const unsigned long long off = (w ? wsum[w - 1] : 0ull) + inc - v, total = s_total;
+        const unsigned next_base = S.level_base + S.n_items;
+        if(valid) {
+            const unsigned off_inner = (unsigned)off, tri_base = S.tri_cursor + (unsigned)(off >> 32);
+            Node8 node;
+            encode_node(B, ch, next_base + off_inner, tri_base, node);
+            Node8* dst = nodes + (S.level_base + i);
+#pragma unroll
+            for(int k = 0; k < 5; k++) dst->v[k] = node.v[k];
+            unsigned r = 0, t = 0;
+            for(int s = 0; s < 8; s++) {
+                int c = ch[s];
+                if(c == kEmptyChild) continue;
+                if(c >= 0) items_b[off_inner + r++] = c;
+                else {
+                    unsigned first, count;
+                    decode_leaf_range(c, first, count);
+                    for(unsigned k = 0; k < count; k++, t++) wide_order[tri_base + t] = B.order[first + k];
+                }
+            }
+        }
+        S.level_base = next_base, S.n_items = (unsigned)total, S.tri_cursor += (unsigned)(total >> 32), S.depth++;
+        int* sw = items_a;
+        items_a = items_b, items_b = sw;
+        __syncthreads(); /* next level reads what this one wrote; wsum / s_total are reused */
+    }
+    if(i == 0) *state = S;
+}
+
 /* triangles into node order: slot j of the wide layout holds triangle wide_order[j]; one thread per float4 */
 __global__ void __launch_bounds__(256) k_tri_reorder(const uint32_t* __restrict__ wide_order, size_t n,
                                                      const float4* __restrict__ tri_gid, float4* __restrict__ tri_wide) {
@@ -559,7 +628,7 @@ int build_accel_device(gpurt_accel* A) {
     size_t fixed = 3 * pad + 2 * ((size_t)ni * 4 + pad);
     size_t phase1 = (size_t)n * 8 + (size_t)n * 4 + ((size_t)ni + n) * 4 + 4 * pad;
     size_t phase2 = 2 * max_nodes * 4 + 8 * max_nodes * 4 + (max_nodes + 1) * 8 + scan_tmp_bytes(max_nodes + 1) +
-                    (size_t)n * 4 + 7 * pad;
+                    (size_t)n * 4 + 8 * pad;
     TRY(ctx->build_arena.reserve(fixed + std::max(phase1, phase2)));
     Arena ar;
     ar.base = (char*)ctx->build_arena.p, ar.cap = ctx->build_arena.cap;
@@ -630,10 +699,26 @@ int build_accel_device(gpurt_accel* A) {
         uint64_t* scan_tmp = ar.take<uint64_t>(scan_tmp_bytes(max_nodes + 1) / 8 + 1);
         uint32_t* wide_order = ar.take<uint32_t>(n);
         if(!wide_order) return set_error("build arena layout"), GPURT_E_STATE;
+        CollapseState* d_state = ar.take<CollapseState>(1);
+        if(!d_state) return set_error("build arena layout"), GPURT_E_STATE;
         int root = 0;
         GPURT_CUDA(cudaMemcpyAsync(items_a, &root, 4, cudaMemcpyHostToDevice, st));
         unsigned n_items = 1, level_base = 0, tri_cursor = 0, depth = 0;
         while(n_items) {
+            if(n_items <= (unsigned)COLLAPSE_SMALL) { /* a run of small levels in one launch */
+                CollapseState hs = {n_items, level_base, tri_cursor, depth};
+                GPURT_CUDA(cudaMemcpyAsync(d_state, &hs, sizeof(hs), cudaMemcpyHostToDevice, st));
+                k_collapse_small<<<1, COLLAPSE_SMALL, 0, st>>>(B, items_a, items_b, d_state, A->nodes, wide_order);
+                GPURT_CUDA(cudaMemcpyAsync(&hs, d_state, sizeof(hs), cudaMemcpyDeviceToHost, st));
+                GPURT_CUDA(cudaStreamSynchronize(st));
+                if((hs.depth - depth) & 1u) { /* an odd number of levels swapped the item lists once more */
+                    int* sw = items_a;
+                    items_a = items_b, items_b = sw;
+                }
+                n_items = hs.n_items, level_base = hs.level_base, tri_cursor = hs.tri_cursor, depth = hs.depth;
+                if(depth >= 64u || (size_t)level_base + n_items > max_nodes) return set_error("wide node bound exceeded"), GPURT_E_STATE;
+                continue;
+            }
             k_collapse_count<<<cdiv(n_items, 128), 128, 0, st>>>(B, items_a, n_items, children, cnt);
             TRY(scan_rec<uint64_t>(st, cnt, cnt, n_items + 1, scan_tmp));
             unsigned next_base = level_base + n_items;

@@ -263,3 +263,38 @@ def test_corrupt_images_fall_back_to_a_placeholder_with_a_warning(gpurt, tmp_pat
             assert t.shape == (1, 1, 4) and (t == 255).all(), f
         else:                                                # damaged data decodes to something of the right size, or not at all
             assert t.shape in ((1, 1, 4), (23, 37, 4)), f
+
+
+def test_header_is_plain_c_and_links(gpurt, tmp_path):
+    """include/gpurt.h compiles as C99 with -pedantic, and a C program linked against libgpurt.so can call the
+    host-only entry points (what a cgo / JNI / ctypes binding of the reference's maintainers would do)"""
+    src = tmp_path / "abi.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "gpurt.h"
+int main(void) {
+    GpurtPipeParams p;
+    GpurtCamera cam;
+    float pos[3] = {0, 0, 5}, at[3] = {0, 0, 0};
+    gpurt_scene* s = 0;
+    unsigned int no = 9, nt = 9, nl = 9, nx = 9;
+    if(sizeof(GpurtRay) != 32 || sizeof(GpurtHit) != 16 || sizeof(GpurtQuery) != 16 || sizeof(GpurtClosestPoint) != 32) return 2;
+    if(sizeof(GpurtSceneDesc) != 208 || sizeof(GpurtSceneLight) != 48 || sizeof(GpurtConstants) != 88 || sizeof(GpurtCamera) != 328) return 3;
+    if(gpurt_pipe_params_default(&p) != GPURT_OK || p.max_frames != 256 || p.samples_per_frame != 8) return 4;
+    if(gpurt_camera_make(1, 640.0f, 480.0f, pos, at, 60.0f, &cam) != GPURT_OK) return 5;
+    if(gpurt_scene_create(0, &s) != GPURT_OK || gpurt_scene_make_sponza_standin(s) != GPURT_OK) return 6;
+    if(gpurt_scene_counts(s, &no, &nt, &nl, &nx) != GPURT_OK || no != 103 || nt != 262267) return 7;
+    if(gpurt_trace_closest(0, 0, 0, 0, GPURT_MEM_HOST) != GPURT_E_INVALID || !strlen(gpurt_last_error())) return 8;
+    gpurt_scene_destroy(s);
+    printf("%s\n", gpurt_version());
+    return 0;
+}
+''')
+    exe = tmp_path / "abi"
+    lib_dir = os.path.join(ROOT, "gpu-rt_b200")
+    r = subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                        "-L", lib_dir, "-lgpurt", f"-Wl,-rpath,{lib_dir}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and "gpurt-b200" in r.stdout, (r.returncode, r.stdout, r.stderr)

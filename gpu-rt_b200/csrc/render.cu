@@ -495,6 +495,7 @@ static int render_core(gpurt_pipe* p, const GpurtPipeParams* prm, const GpurtCam
     ShadeCtx X;
     X.S = p->accel->dscene;
     X.nodes = (const float4*)p->accel->nodes, X.tris = p->accel->tri_wide, X.n_nodes = p->accel->n_nodes;
+    X.tri_world = p->accel->tri_gid;
     X.prev_res = p->res[prev], X.ppos = p->gbuf[prev][0], X.pnorm = p->gbuf[prev][1], X.palb = p->gbuf[prev][2];
     X.ray_counts = p->ray_counts;
 

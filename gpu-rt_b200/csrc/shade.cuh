@@ -129,6 +129,7 @@ struct ShadeCtx {
     DeviceScene S;
     const float4* nodes;
     const float4* tris;
+    const float4* tri_world; /* world-space triangles in global primitive order: v0 | e1 = v1-v0 | e2 = v2-v0 (k_flatten, N1) */
     unsigned n_nodes;
     const float4* prev_res;  /* previous frame reservoirs */
     const float4* ppos;      /* previous frame G-buffers */
@@ -445,6 +446,30 @@ struct Shader {
         hitp = o + t * d;
         return t >= 0;
     }
+    /* triangle_hit / triangle_pdf on a pre-flattened triangle (pa, e1 = pb - pa, e2 = pc - pa).  k_flatten evaluates
+     * model * vec4(v, 1) and the two edge subtractions with exactly the operations of the GLSL (xform_point, then
+     * `pb - pa`), so these return the same bits as the vertex forms below. */
+    SH_D static float triangle_pdf_flat(F3 o, F3 d, F3 pa, F3 v1, F3 v2) {
+        F3 p = cross3(d, v2);
+        float det = dot3(v1, p);
+        if(fabsf(det) < kEps) return 0;
+        float invDet = 1 / det;
+        F3 s = o - pa;
+        float u = dot3(s, p) * invDet;
+        if(u < 0 || u > 1) return 0;
+        F3 q = cross3(s, v1);
+        float v = dot3(d, q) * invDet;
+        if(v < 0 || u + v > 1) return 0;
+        float t = dot3(v2, q) * invDet;
+        if(!(t >= 0)) return 0;
+        F3 hitp = o + t * d;
+        F3 c = cross3(v1, v2);
+        float a = 2 / length3(c);
+        F3 dist = hitp - o;
+        F3 N = normalize3(c);
+        float g = dot3(dist, dist) / fabsf(dot3(N, d));
+        return a * g;
+    }
     SH_D static float triangle_pdf(F3 o, F3 d, F3 v0, F3 v1, F3 v2) {
         F3 hitp;
         if(triangle_hit(o, d, v0, v1, v2, hitp)) {
@@ -475,14 +500,12 @@ struct Shader {
             const SceneLight& L = X.S.lights[l];
             uint32_t o_idx = L.index, n_tris = L.n_triangles;
             if(!hit_bbox(p, d, F3{L.bmin[0], L.bmin[1], L.bmin[2]}, F3{L.bmax[0], L.bmax[1], L.bmax[2]})) continue;
-            const float* m = model(o_idx);
-            for(uint32_t t = 0; t < n_tris; t++) {
-                uint32_t ind[3];
-                tri_indices(o_idx, t, ind);
-                const float *a = vertex(o_idx, ind[0]), *b = vertex(o_idx, ind[1]), *cc = vertex(o_idx, ind[2]);
-                F3 v0 = xform_point(m, F3{a[0], a[1], a[2]}), v1 = xform_point(m, F3{b[0], b[1], b[2]}),
-                   v2 = xform_point(m, F3{cc[0], cc[1], cc[2]});
-                tacc += triangle_pdf(p, d, v0, v1, v2);
+            /* the GLSL re-fetches 3 indices + 3 vertices and re-transforms them for every triangle of every call; the
+             * build already holds the same world-space triangles, contiguous per object */
+            const float4* tp = X.tri_world + 3ull * X.S.tri_off[o_idx];
+            for(uint32_t t = 0; t < n_tris; t++, tp += 3) {
+                float4 r0 = __ldg(tp), r1 = __ldg(tp + 1), r2 = __ldg(tp + 2);
+                tacc += triangle_pdf_flat(p, d, F3{r0.x, r0.y, r0.z}, F3{r1.x, r1.y, r1.z}, F3{r2.x, r2.y, r2.z});
             }
             oacc += tacc / (float)n_tris;
         }

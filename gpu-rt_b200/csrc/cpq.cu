@@ -6,44 +6,12 @@
  * Priority-ordered descent (traverse.cuh: closest_point8).  N5 tie rule: smallest d^2 wins, equal
  * d^2 -> lowest global primitive id; the radius is inclusive.
  */
-#include <cstdlib>
-
 #include "device.cuh"
 #include "traverse.cuh"
 
 namespace gpurt {
 
-/* ---- query re-ordering ------------------------------------------------------------------------ */
-/* Unlike rays, closest-point descents of neighbouring points visit the same nodes and shrink their radius at the
- * same pace; a warp of 32 unrelated points runs at ~9 of 32 lanes.  Large device batches whose points arrive in
- * no spatial order (config 4: 100 M uniform random points) are therefore processed in Morton order of the query
- * position — a key per query, one 4-pass radix sort of (key, index) pairs, and the descent kernel reads its
- * query and writes its result through the sorted index — which is 1.5x faster end to end on that workload.
- * Batches that are already coherent (measured: neighbours fall into the same 16^3 cell) skip the sort, and so do
- * scenes whose BVH fits in L2 with room to spare (< 64 MB), where order hardly matters.
- * Results do not depend on the processing order. */
-__global__ void __launch_bounds__(256) k_cpq_keys(const float4* __restrict__ queries, uint64_t n, float lx, float ly,
-                                                  float lz, float ix, float iy, float iz, uint64_t* __restrict__ keys,
-                                                  uint32_t* __restrict__ vals, unsigned* __restrict__ same_cell) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned key = 0xffffffffu;
-    if(i < n) {
-        float4 q = __ldg(queries + i);
-        unsigned x = (unsigned)fminf(fmaxf((q.x - lx) * ix * 1024.0f, 0.0f), 1023.0f);
-        unsigned y = (unsigned)fminf(fmaxf((q.y - ly) * iy * 1024.0f, 0.0f), 1023.0f);
-        unsigned z = (unsigned)fminf(fmaxf((q.z - lz) * iz * 1024.0f, 0.0f), 1023.0f);
-        key = (unsigned)((expand21(x) << 2) | (expand21(y) << 1) | expand21(z));
-        keys[i] = key;
-        vals[i] = (uint32_t)i;
-    }
-    /* coherence probe: does the next query fall into the same cell of a 16^3 grid (top 12 key bits)? */
-    unsigned next = __shfl_down_sync(0xffffffffu, key, 1);
-    bool same = (threadIdx.x & 31) != 31 && i + 1 < n && (key >> 18) == (next >> 18);
-    unsigned cnt = __popc(__ballot_sync(0xffffffffu, same));
-    if((threadIdx.x & 31) == 0 && cnt) atomicAdd(same_cell, cnt);
-}
-
-template <int STACK>
+template <int STACK, bool ORDERED>
 __global__ void __launch_bounds__(128) k_closest_points(const float4* __restrict__ nodes,
                                                         const float4* __restrict__ tris,
                                                         const float4* __restrict__ queries, uint64_t n,
@@ -68,84 +36,33 @@ __global__ void __launch_bounds__(128) k_closest_points(const float4* __restrict
         o0 = make_float4(c.x, c.y, c.z, sqrtf(best.d2));
         o1 = make_float4(u2f(best.gid), r1.w, best.v, best.w);
     }
-    if(staged) i = slot; /* results go to a local staging array in processing order, k_cpq_unpermute moves them */
+    if(ORDERED && staged) i = slot; /* results go to a local staging array in processing order (order.cu) */
     results[2 * i] = o0;
     results[2 * i + 1] = o1;
 }
-
-/* Sorted batches whose result array lives on another GPU (gpurt_shared_open mapping): 32-byte stores scattered over
- * NVLink are slow (config 4 on 8 GPUs: 16.8 ms vs 10.0 ms with local results), so the descent writes a local
- * staging array in processing order and this kernel writes the caller's array front to back, fully coalesced. */
-__global__ void __launch_bounds__(256) k_cpq_invert(const uint32_t* __restrict__ order, uint64_t n, uint32_t* __restrict__ inv) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if(i < n) inv[order[i]] = (uint32_t)i;
-}
-__global__ void __launch_bounds__(256) k_cpq_unpermute(const float4* __restrict__ staged, const uint32_t* __restrict__ inv,
-                                                       uint64_t n, float4* __restrict__ results) {
-    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; /* one thread per float4 */
-    if(t >= 2 * n) return;
-    results[t] = staged[2ull * inv[t >> 1] + (t & 1)];
-}
-
-constexpr uint64_t kCpqSortMin = 1u << 20; /* smaller batches are not worth a sort */
 
 int launch_closest_points(gpurt_accel* A, const float4* queries, uint64_t n, float4* results) {
     if(!n) return GPURT_OK;
     unsigned nb = (unsigned)((n + 127) / 128);
     const float4* nodes = (const float4*)A->nodes;
-    gpurt_ctx* ctx = A->ctx;
-    cudaStream_t st = ctx->stream;
-    const uint32_t* order = nullptr;
-    float4* out = results;
-    const uint32_t* unperm = nullptr; /* storage position -> processing position, when results are staged */
-    static const bool allow_sort = !(getenv("GPURT_CPQ_SORT") && atoi(getenv("GPURT_CPQ_SORT")) == 0);
-    /* only when the BVH does not sit in L2 anyway: on the 16 k-triangle Cornell box the sort costs 8 % and gains nothing */
-    const size_t bvh_bytes = (size_t)A->n_nodes * sizeof(Node8) + (size_t)A->n * 48;
-    if(allow_sort && n >= kCpqSortMin && n < (1ull << 30) && bvh_bytes > (64u << 20)) {
-        /* scratch: keys | vals | keys_tmp | vals_tmp | counter, in the build arena (no build runs concurrently on this stream) */
-        size_t kb = ((size_t)n * 8 + 255) & ~(size_t)255, vb = ((size_t)n * 4 + 255) & ~(size_t)255;
-        /* is the result array on another GPU (a gpurt_shared_open mapping)?  then the results are staged, see below */
-        cudaPointerAttributes pa;
-        const bool remote = cudaPointerGetAttributes(&pa, results) == cudaSuccess && pa.type == cudaMemoryTypeDevice &&
-                            pa.device != ctx->device;
-        (void)cudaGetLastError();
-        const size_t used = 2 * kb + 2 * vb + 256, stage_bytes = remote ? (((size_t)n * 32 + 255) & ~(size_t)255) : 0;
-        int rc = ctx->build_arena.reserve(used + stage_bytes);
-        if(rc) return rc;
-        char* base = (char*)ctx->build_arena.p;
-        uint64_t *keys = (uint64_t*)base, *keys_tmp = (uint64_t*)(base + kb);
-        uint32_t *vals = (uint32_t*)(base + 2 * kb), *vals_tmp = (uint32_t*)(base + 2 * kb + vb);
-        unsigned* counter = (unsigned*)(base + 2 * kb + 2 * vb);
-        const float* sb = A->scene_box;
-        float inv[3];
-        for(int k = 0; k < 3; k++) inv[k] = sb[3 + k] > sb[k] ? 1.0f / (sb[3 + k] - sb[k]) : 0.0f;
-        GPURT_CUDA(cudaMemsetAsync(counter, 0, 4, st));
-        k_cpq_keys<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(queries, n, sb[0], sb[1], sb[2], inv[0], inv[1], inv[2], keys,
-                                                                 vals, counter);
-        unsigned same = 0;
-        GPURT_CUDA(cudaMemcpyAsync(&same, counter, 4, cudaMemcpyDeviceToHost, st));
-        GPURT_CUDA(cudaStreamSynchronize(st));
-        if((double)same < 0.5 * (double)n) { /* incoherent batch */
-            rc = radix_sort_u64(st, keys, vals, keys_tmp, vals_tmp, n, 4, ctx->scratch, ctx->sm_count);
-            if(rc) return rc;
-            order = vals; /* 4 passes: the result is back in the primary buffers */
-            if(remote) { /* stage locally, write the remote array coalesced afterwards */
-                out = (float4*)(base + used);
-                uint32_t* invw = (uint32_t*)keys_tmp; /* the sort is finished with its key scratch */
-                k_cpq_invert<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(order, n, invw);
-                unperm = invw;
-            }
-        }
-    }
+    cudaStream_t st = A->ctx->stream;
+    OrderPlan P; /* large incoherent batches on large scenes are processed in Morton order of the query point (order.cu) */
+    int rc = plan_spatial_order(A, queries, 1, n, results, 32, P);
+    if(rc) return rc;
+    float4* out = (float4*)P.out;
+    const int staged = P.unperm ? 1 : 0;
     unsigned need = 7u * A->depth + 1u;
-    if(need <= 64) k_closest_points<64><<<nb, 128, 0, st>>>(nodes, A->tri_wide, queries, n, out, A->n_nodes, order, unperm ? 1 : 0);
-    else if(need <= 128) k_closest_points<128><<<nb, 128, 0, st>>>(nodes, A->tri_wide, queries, n, out, A->n_nodes, order, unperm ? 1 : 0);
-    else if(need <= 256) k_closest_points<256><<<nb, 128, 0, st>>>(nodes, A->tri_wide, queries, n, out, A->n_nodes, order, unperm ? 1 : 0);
-    else if(need <= 512) k_closest_points<512><<<nb, 128, 0, st>>>(nodes, A->tri_wide, queries, n, out, A->n_nodes, order, unperm ? 1 : 0);
+#define GPURT_CPQ_LAUNCH(S)                                                                                                  \
+    (P.order ? k_closest_points<S, true><<<nb, 128, 0, st>>>(nodes, A->tri_wide, queries, n, out, A->n_nodes, P.order, staged) \
+             : k_closest_points<S, false><<<nb, 128, 0, st>>>(nodes, A->tri_wide, queries, n, out, A->n_nodes, nullptr, 0))
+    if(need <= 64) GPURT_CPQ_LAUNCH(64);
+    else if(need <= 128) GPURT_CPQ_LAUNCH(128);
+    else if(need <= 256) GPURT_CPQ_LAUNCH(256);
+    else if(need <= 512) GPURT_CPQ_LAUNCH(512);
     else return set_error("wide BVH too deep for the closest-point stack"), GPURT_E_STATE;
-    if(unperm) k_cpq_unpermute<<<(unsigned)((2 * n + 255) / 256), 256, 0, st>>>(out, unperm, n, results);
+#undef GPURT_CPQ_LAUNCH
     GPURT_CUDA(cudaGetLastError());
-    return GPURT_OK;
+    return finish_spatial_order(A, P, n, results, 32);
 }
 
 } // namespace gpurt

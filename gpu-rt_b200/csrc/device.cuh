@@ -105,6 +105,18 @@ namespace gpurt {
 int build_accel_device(gpurt_accel* A);
 void free_accel_device(gpurt_accel* A);
 
+/* order.cu: processing order for large incoherent device batches.  `order` (may be NULL) maps processing slot ->
+ * storage index; when `unperm` is set the kernel writes slot-indexed records to `out` (local staging) and
+ * finish_spatial_order() moves them to the caller's (remote) array. */
+struct OrderPlan {
+    const uint32_t* order = nullptr;
+    const uint32_t* unperm = nullptr;
+    void* out = nullptr;
+};
+int plan_spatial_order(gpurt_accel* A, const float4* pos, unsigned stride_vec4, uint64_t n, void* results,
+                       size_t result_bytes, OrderPlan& P);
+int finish_spatial_order(gpurt_accel* A, const OrderPlan& P, uint64_t n, void* results, size_t result_bytes);
+
 /* query launchers (device pointers, async on ctx->stream) */
 int launch_trace_closest(gpurt_accel* A, const float4* rays, uint64_t n, float4* hits);
 int launch_trace_any(gpurt_accel* A, const float4* rays, uint64_t n, uint8_t* occ);

@@ -1,0 +1,128 @@
+/*
+ * order.cu — spatial processing order for large, incoherent device batches of rays / query points.
+ *
+ * One thread per ray or point walks the BVH.  When the BVH is much larger than L2 and the batch arrives in no
+ * spatial order, the 32 lanes of a warp touch unrelated nodes: every fetch misses L1, and for closest-point
+ * descents the lanes also shrink their radius at different paces (9 of 32 lanes busy).  Measured on the
+ * 10 M-triangle config-4 soup (tools/cpq_sort_probe.py, tools/ray_sort_probe.py): uniform random points
+ * 807 -> 1355 Mq/s and uniform random rays 676 -> 970 Mrays/s when processed in Morton order of the position.
+ * So such batches get a 30-bit Morton key per element, a 4-pass radix sort of (key, index) pairs, and the
+ * traversal kernel reads its element and writes its result through the sorted index.  Skipped when the scene is
+ * small (BVH < 64 MB: order hardly matters once the tree sits in L2), when the batch is small (< 2^20), or when
+ * neighbouring elements already share a cell of a 16^3 grid (e.g. rays and points generated per pixel).
+ * Results never depend on the processing order (contracts N4 / N5).
+ *
+ * If the result array lives on another GPU (gpurt_shared_open mapping), scattered 16/32-byte stores over NVLink
+ * would cost ~70 % more than the traversal itself, so results are staged locally in processing order and a second
+ * kernel writes the caller's array front to back.
+ */
+#include <cstdlib>
+
+#include "device.cuh"
+#include "traverse.cuh"
+
+namespace gpurt {
+
+__global__ void __launch_bounds__(256) k_order_keys(const float4* __restrict__ pos, unsigned stride, uint64_t n, float lx,
+                                                    float ly, float lz, float ix, float iy, float iz,
+                                                    uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
+                                                    unsigned* __restrict__ same_cell) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned key = 0xffffffffu;
+    if(i < n) {
+        float4 q = __ldg(pos + (size_t)stride * i);
+        unsigned x = (unsigned)fminf(fmaxf((q.x - lx) * ix * 1024.0f, 0.0f), 1023.0f);
+        unsigned y = (unsigned)fminf(fmaxf((q.y - ly) * iy * 1024.0f, 0.0f), 1023.0f);
+        unsigned z = (unsigned)fminf(fmaxf((q.z - lz) * iz * 1024.0f, 0.0f), 1023.0f);
+        key = (unsigned)((expand21(x) << 2) | (expand21(y) << 1) | expand21(z));
+        keys[i] = key;
+        vals[i] = (uint32_t)i;
+    }
+    /* coherence probe: does the next element fall into the same cell of a 16^3 grid (top 12 key bits)? */
+    unsigned next = __shfl_down_sync(0xffffffffu, key, 1);
+    bool same = (threadIdx.x & 31) != 31 && i + 1 < n && (key >> 18) == (next >> 18);
+    unsigned cnt = __popc(__ballot_sync(0xffffffffu, same));
+    if((threadIdx.x & 31) == 0 && cnt) atomicAdd(same_cell, cnt);
+}
+
+__global__ void __launch_bounds__(256) k_order_invert(const uint32_t* __restrict__ order, uint64_t n, uint32_t* __restrict__ inv) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if(i < n) inv[order[i]] = (uint32_t)i;
+}
+/* results[j] = staged[inv[j]] for records of VEC4 float4s; one thread per float4 */
+template <int VEC4>
+__global__ void __launch_bounds__(256) k_order_unpermute(const float4* __restrict__ staged, const uint32_t* __restrict__ inv,
+                                                         uint64_t n, float4* __restrict__ results) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if(t >= (uint64_t)VEC4 * n) return;
+    results[t] = staged[(uint64_t)VEC4 * inv[t / VEC4] + (t % VEC4)];
+}
+__global__ void __launch_bounds__(256) k_order_unpermute_u8(const uint8_t* __restrict__ staged, const uint32_t* __restrict__ inv,
+                                                            uint64_t n, uint8_t* __restrict__ results) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if(t < n) results[t] = staged[inv[t]];
+}
+
+constexpr uint64_t kOrderMinBatch = 1u << 20;
+constexpr size_t kOrderMinBvhBytes = 64u << 20;
+
+int plan_spatial_order(gpurt_accel* A, const float4* pos, unsigned stride_vec4, uint64_t n, void* results,
+                       size_t result_bytes, OrderPlan& P) {
+    P = OrderPlan();
+    P.out = results;
+    gpurt_ctx* ctx = A->ctx;
+    cudaStream_t st = ctx->stream;
+    static const bool allow = !(getenv("GPURT_SPATIAL_ORDER") && atoi(getenv("GPURT_SPATIAL_ORDER")) == 0);
+    const size_t bvh_bytes = (size_t)A->n_nodes * sizeof(Node8) + (size_t)A->n * 48;
+    if(!allow || n < kOrderMinBatch || n >= (1ull << 30) || bvh_bytes <= kOrderMinBvhBytes) return GPURT_OK;
+    /* scratch in the build arena (no build runs concurrently on this stream): keys | keys_tmp | vals | vals_tmp | counter | staging */
+    const size_t kb = ((size_t)n * 8 + 255) & ~(size_t)255, vb = ((size_t)n * 4 + 255) & ~(size_t)255;
+    cudaPointerAttributes pa;
+    const bool remote = cudaPointerGetAttributes(&pa, results) == cudaSuccess && pa.type == cudaMemoryTypeDevice &&
+                        pa.device != ctx->device;
+    (void)cudaGetLastError();
+    const size_t used = 2 * kb + 2 * vb + 256, stage_bytes = remote ? (((size_t)n * result_bytes + 255) & ~(size_t)255) : 0;
+    int rc = ctx->build_arena.reserve(used + stage_bytes);
+    if(rc) return rc;
+    char* base = (char*)ctx->build_arena.p;
+    uint64_t *keys = (uint64_t*)base, *keys_tmp = (uint64_t*)(base + kb);
+    uint32_t *vals = (uint32_t*)(base + 2 * kb), *vals_tmp = (uint32_t*)(base + 2 * kb + vb);
+    unsigned* counter = (unsigned*)(base + 2 * kb + 2 * vb);
+    const float* sb = A->scene_box;
+    float inv[3];
+    for(int k = 0; k < 3; k++) inv[k] = sb[3 + k] > sb[k] ? 1.0f / (sb[3 + k] - sb[k]) : 0.0f;
+    GPURT_CUDA(cudaMemsetAsync(counter, 0, 4, st));
+    k_order_keys<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(pos, stride_vec4, n, sb[0], sb[1], sb[2], inv[0], inv[1], inv[2],
+                                                               keys, vals, counter);
+    unsigned same = 0;
+    GPURT_CUDA(cudaMemcpyAsync(&same, counter, 4, cudaMemcpyDeviceToHost, st));
+    GPURT_CUDA(cudaStreamSynchronize(st));
+    if((double)same >= 0.5 * (double)n) return GPURT_OK; /* already coherent */
+    rc = radix_sort_u64(st, keys, vals, keys_tmp, vals_tmp, n, 4, ctx->scratch, ctx->sm_count);
+    if(rc) return rc;
+    P.order = vals; /* 4 passes: the result is back in the primary buffers */
+    if(remote) {
+        P.out = base + used;
+        uint32_t* invw = (uint32_t*)keys_tmp; /* the sort is finished with its key scratch */
+        k_order_invert<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(P.order, n, invw);
+        P.unperm = invw;
+    }
+    GPURT_CUDA(cudaGetLastError());
+    return GPURT_OK;
+}
+
+int finish_spatial_order(gpurt_accel* A, const OrderPlan& P, uint64_t n, void* results, size_t result_bytes) {
+    if(!P.unperm) return GPURT_OK;
+    cudaStream_t st = A->ctx->stream;
+    if(result_bytes == 32)
+        k_order_unpermute<2><<<(unsigned)((2 * n + 255) / 256), 256, 0, st>>>((const float4*)P.out, P.unperm, n, (float4*)results);
+    else if(result_bytes == 16)
+        k_order_unpermute<1><<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const float4*)P.out, P.unperm, n, (float4*)results);
+    else if(result_bytes == 1)
+        k_order_unpermute_u8<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const uint8_t*)P.out, P.unperm, n, (uint8_t*)results);
+    else return set_error("finish_spatial_order: record size"), GPURT_E_STATE;
+    GPURT_CUDA(cudaGetLastError());
+    return GPURT_OK;
+}
+
+} // namespace gpurt

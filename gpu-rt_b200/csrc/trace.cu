@@ -16,14 +16,18 @@
 
 namespace gpurt {
 
-template <bool STATS>
+/* ORDERED: the batch is processed through a sorted index (order.cu); the plain instantiation is the headline kernel */
+template <bool STATS, bool ORDERED>
 __global__ void __launch_bounds__(128) k_trace_closest(const float4* __restrict__ nodes,
                                                        const float4* __restrict__ tris,
                                                        const float4* __restrict__ rays, uint64_t n,
                                                        float4* __restrict__ hits, unsigned n_nodes,
-                                                       unsigned long long* counters) {
+                                                       unsigned long long* counters,
+                                                       const uint32_t* __restrict__ order, int staged) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if(i >= n) return;
+    const uint64_t slot = i;        /* processing position */
+    if(ORDERED) i = order[i];       /* storage position */
     float4 a = __ldg(rays + 2 * i), b = __ldg(rays + 2 * i + 1);
     HitRec h;
     h.t = a.w, h.u = h.v = 0, h.gid = kNoHit;
@@ -32,20 +36,24 @@ __global__ void __launch_bounds__(128) k_trace_closest(const float4* __restrict_
     float4 out;
     out.x = h.gid == kNoHit ? GPURT_INF : h.t;
     out.y = h.u, out.z = h.v, out.w = u2f(h.gid);
-    hits[i] = out;
+    hits[ORDERED && staged ? slot : i] = out;
 }
 
+template <bool ORDERED>
 __global__ void __launch_bounds__(128) k_trace_any(const float4* __restrict__ nodes,
                                                    const float4* __restrict__ tris,
                                                    const float4* __restrict__ rays, uint64_t n,
-                                                   uint8_t* __restrict__ occ, unsigned n_nodes) {
+                                                   uint8_t* __restrict__ occ, unsigned n_nodes,
+                                                   const uint32_t* __restrict__ order, int staged) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if(i >= n) return;
+    const uint64_t slot = i;
+    if(ORDERED) i = order[i];
     float4 a = __ldg(rays + 2 * i), b = __ldg(rays + 2 * i + 1);
     HitRec h;
     bool hit = n_nodes && traverse8<true, false>(nodes, tris, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), a.w,
                                                   b.w, h, nullptr);
-    occ[i] = hit ? 1 : 0;
+    occ[ORDERED && staged ? slot : i] = hit ? 1 : 0;
 }
 
 /* ---- binary-LBVH traversal (debug / baseline for the wide path) ------------------------------- */
@@ -116,25 +124,39 @@ static inline unsigned blocks_for(uint64_t n, unsigned t) { return (unsigned)((n
 
 int launch_trace_closest(gpurt_accel* A, const float4* rays, uint64_t n, float4* hits) {
     if(!n) return GPURT_OK;
-    k_trace_closest<false><<<blocks_for(n, 128), 128, 0, A->ctx->stream>>>(
-        (const float4*)A->nodes, A->tri_wide, rays, n, hits, A->n_nodes, nullptr);
+    OrderPlan P; /* large incoherent batches on large scenes are processed in Morton order of the ray origin (order.cu) */
+    int rc = plan_spatial_order(A, rays, 2, n, hits, 16, P);
+    if(rc) return rc;
+    if(P.order)
+        k_trace_closest<false, true><<<blocks_for(n, 128), 128, 0, A->ctx->stream>>>(
+            (const float4*)A->nodes, A->tri_wide, rays, n, (float4*)P.out, A->n_nodes, nullptr, P.order, P.unperm ? 1 : 0);
+    else
+        k_trace_closest<false, false><<<blocks_for(n, 128), 128, 0, A->ctx->stream>>>(
+            (const float4*)A->nodes, A->tri_wide, rays, n, hits, A->n_nodes, nullptr, nullptr, 0);
     GPURT_CUDA(cudaGetLastError());
-    return GPURT_OK;
+    return finish_spatial_order(A, P, n, hits, 16);
 }
 int launch_trace_closest_stats(gpurt_accel* A, const float4* rays, uint64_t n, float4* hits,
                                unsigned long long* d_counters) {
     if(!n) return GPURT_OK;
-    k_trace_closest<true><<<blocks_for(n, 128), 128, 0, A->ctx->stream>>>(
-        (const float4*)A->nodes, A->tri_wide, rays, n, hits, A->n_nodes, d_counters);
+    k_trace_closest<true, false><<<blocks_for(n, 128), 128, 0, A->ctx->stream>>>(
+        (const float4*)A->nodes, A->tri_wide, rays, n, hits, A->n_nodes, d_counters, nullptr, 0);
     GPURT_CUDA(cudaGetLastError());
     return GPURT_OK;
 }
 int launch_trace_any(gpurt_accel* A, const float4* rays, uint64_t n, uint8_t* occ) {
     if(!n) return GPURT_OK;
-    k_trace_any<<<blocks_for(n, 128), 128, 0, A->ctx->stream>>>((const float4*)A->nodes, A->tri_wide, rays,
-                                                              n, occ, A->n_nodes);
+    OrderPlan P;
+    int rc = plan_spatial_order(A, rays, 2, n, occ, 1, P);
+    if(rc) return rc;
+    if(P.order)
+        k_trace_any<true><<<blocks_for(n, 128), 128, 0, A->ctx->stream>>>((const float4*)A->nodes, A->tri_wide, rays, n,
+                                                                        (uint8_t*)P.out, A->n_nodes, P.order, P.unperm ? 1 : 0);
+    else
+        k_trace_any<false><<<blocks_for(n, 128), 128, 0, A->ctx->stream>>>((const float4*)A->nodes, A->tri_wide, rays, n, occ,
+                                                                         A->n_nodes, nullptr, 0);
     GPURT_CUDA(cudaGetLastError());
-    return GPURT_OK;
+    return finish_spatial_order(A, P, n, occ, 1);
 }
 int launch_trace_closest_bvh2(gpurt_accel* A, const float4* rays, uint64_t n, float4* hits) {
     if(!n) return GPURT_OK;

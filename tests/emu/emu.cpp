@@ -36,6 +36,9 @@ static void fill_ranges(const int* left, const int* right, int node, std::vector
 
 extern "C" {
 
+int g_greedy = 1; /* 1: the greedy largest-area collapse (the default); 0: SAH-optimal collapse (GPURT_BUILD_SAH_COLLAPSE) */
+void emu_set_greedy(int g) { g_greedy = g; }
+
 void* emu_build(const float* tris9, unsigned n, const unsigned* order, const int* left, const int* right,
                 const float* boxes6, float inflate) {
     Emu* E = new Emu;
@@ -55,6 +58,23 @@ void* emu_build(const float* tris9, unsigned n, const unsigned* order, const int
     std::vector<int> rf(n ? n - 1 : 0), rl(n ? n - 1 : 0);
     if(n > 1) fill_ranges(left, right, 0, rf, rl);
     Bvh2View B{left, right, rf.data(), rl.data(), nlo.data(), nhi.data(), tlo.data(), thi.data(), order, inflate};
+    /* SAH-optimal collapse tables, children before parents (the GPU computes them in the refit kernel) */
+    std::vector<float> dp_cost(n > 1 ? 7ull * (n - 1) : 0);
+    std::vector<unsigned char> dp_dec(n > 1 ? 8ull * (n - 1) : 0);
+    if(n > 1 && !g_greedy) {
+        std::vector<std::pair<int, int>> st{{0, 0}};
+        while(!st.empty()) {
+            auto [c, phase] = st.back();
+            st.pop_back();
+            if(phase == 0) {
+                st.push_back({c, 1});
+                if(left[c] >= 0) st.push_back({left[c], 0});
+                if(right[c] >= 0) st.push_back({right[c], 0});
+            } else
+                dp_node(B, dp_cost.data(), dp_dec.data(), c, bvh2_child_box(B, c));
+        }
+        B.dp_dec = dp_dec.data();
+    }
     E->tri_wide.resize(3ull * n);
     if(n == 0) return E;
     if(n <= (unsigned)kMaxLeafTris) {

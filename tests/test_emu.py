@@ -53,6 +53,22 @@ def test_soups(emu, orc, n):
     _check(emu, orc, tris, 8000)
 
 
+def test_sah_optimal_collapse_same_results_fewer_nodes(emu, orc, gpurt):
+    """GPURT_BUILD_SAH_COLLAPSE (dp_node / collapse_node_dp): identical hits and closest points, fewer wide nodes"""
+    s = gpurt.Scene(None)
+    s.load(os.path.join(MEDIA, "cbox/cbox.gltf"))
+    tris = world_tris(orc, s)
+    try:
+        emu.emu_set_greedy(1)
+        greedy_nodes, g_npr, _ = _check(emu, orc, tris, 20000)
+        emu.emu_set_greedy(0)
+        sah_nodes, s_npr, _ = _check(emu, orc, tris, 20000)
+        _check(emu, orc, soup(5000, seed=3), 8000)
+    finally:
+        emu.emu_set_greedy(1)
+    assert sah_nodes < greedy_nodes and s_npr < g_npr * 1.02
+
+
 @pytest.mark.parametrize("name", ["cube", "mis_test", "cbox"])
 def test_reference_scenes(emu, orc, gpurt, name):
     s = gpurt.Scene(None)

@@ -325,3 +325,20 @@ def test_large_scene_batches_in_spatial_order(gpurt, orc, ctx):
     torch.cuda.synchronize()
     assert same_bits(hits2.cpu().numpy(), hits.cpu().numpy()[order])
     accel.close(), scene.close()
+
+
+def test_sah_optimal_collapse_flag(gpurt, orc, ctx):
+    """GPURT_BUILD_SAH_COLLAPSE: same primitive order and query results as the default build, fewer wide nodes"""
+    scene = load_scene(gpurt, ctx, "sponza_standin")
+    tris = world_tris(orc, scene)
+    base = gpurt.Accel(scene)
+    sah = gpurt.Accel(scene, gpurt.BUILD_SAH_COLLAPSE)
+    ob = _check_build(gpurt, orc, sah, tris)
+    assert sah.info().n_wide_nodes < 0.8 * base.info().n_wide_nodes
+    hits = _check_queries(gpurt, orc, sah, ob, tris, 1 << 18, 1 << 10)
+    rays = orc.gen_random_rays(1 << 18, 0xC0FFEE, ob.scene_box())
+    assert same_bits(hits, base.trace_closest(rays))
+    scene.set_transform(5, np.eye(4, dtype=np.float32).reshape(16) * np.float32(1.0))
+    sah.update()                                       # the in-place rebuild keeps the flag
+    assert sah.info().n_wide_nodes < 0.8 * base.info().n_wide_nodes
+    sah.close(), base.close(), scene.close()

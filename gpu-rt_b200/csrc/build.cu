@@ -691,6 +691,7 @@ int build_accel_device(gpurt_accel* A) {
     B.left = A->left, B.right = A->right, B.range_first = range_first, B.range_last = range_last;
     B.node_lo = A->node_lo, B.node_hi = A->node_hi, B.tri_lo = A->tri_lo, B.tri_hi = A->tri_hi;
     B.order = A->order, B.inflate = A->inflate;
+    if(const char* e = getenv("GPURT_SAH_CPRIM")) B.dp_cprim = (float)atof(e);
     unsigned* arrive = (unsigned*)vals_tmp; /* the sort is done with it */
     if(ni) {
         GPURT_CUDA(cudaMemsetAsync(arrive, 0, (size_t)ni * 4, st));

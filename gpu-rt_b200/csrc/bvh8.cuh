@@ -53,6 +53,7 @@ struct Bvh2View {
     float inflate;
     /* SAH-optimal collapse decisions (dp_node), 8 bytes per internal node; nullptr = greedy collapse */
     const unsigned char* dp_dec = nullptr;
+    float dp_cprim = 0.3f; /* cost of a triangle test relative to a node visit */
 };
 
 GPURT_HD Box3 bvh2_child_box(const Bvh2View& B, int c) {
@@ -168,14 +169,14 @@ GPURT_HD int collapse_node_greedy(const Bvh2View& B, int root, int out_child[8],
  * from the refit kernel when both children are final) stores the costs and the 8 decision bytes per node; the
  * collapse then follows the decisions instead of the greedy largest-area rule.  Against the greedy rule on the
  * Sponza stand-in: 32 % fewer wide nodes, 5 % / 2 % / 4 % fewer node visits for primary / bounce / random rays. */
-constexpr float kDpCostNode = 1.0f, kDpCostPrim = 0.3f;
+constexpr float kDpCostNode = 1.0f;
 #if defined(__CUDA_ARCH__)
 #define GPURT_LDCG_F(p) __ldcg(p)
 #else
 #define GPURT_LDCG_F(p) (*(p))
 #endif
 GPURT_HD float dp_ref_cost(const Bvh2View& B, const float* cost, int c, int i) { /* C(c, i), i = 1..7 */
-    if(c < 0) return box_area(bvh2_child_box(B, c)) * kDpCostPrim;
+    if(c < 0) return box_area(bvh2_child_box(B, c)) * B.dp_cprim;
     return GPURT_LDCG_F(cost + 7ull * c + (i - 1));
 }
 /* dec[0] = split of D(n,8); dec[1] = 1 leaf / 2 inner; dec[i], i = 2..7: 0 = same as i-1, else the split k */
@@ -196,7 +197,7 @@ GPURT_HD void dp_node(const Bvh2View& B, float* cost, unsigned char* dec, int n,
         }
         d[0] = (unsigned char)kb;
         float c_int = A * kDpCostNode + best;
-        float c_leaf = P <= kMaxLeafTris ? A * (float)P * kDpCostPrim : 3.0e38f;
+        float c_leaf = P <= kMaxLeafTris ? A * (float)P * B.dp_cprim : 3.0e38f;
         out[0] = fminf(c_leaf, c_int);
         d[1] = c_leaf <= c_int ? 1 : 2;
     }

@@ -212,11 +212,13 @@ def test_p2p_result_placement_two_gpus(gpurt, built):
         pytest.skip("needs 2 GPUs")
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
                           "--master-addr", "127.0.0.1", "--master-port", "29731",
-                          os.path.join(ROOT, "tools", "config4_cpq.py"), "--tris", "1000000", "--queries", "4000000",
-                          "--chunk", "1000000", "--check", "50000", "--p2p"], capture_output=True, text=True, timeout=900)
+                          os.path.join(ROOT, "tools", "config4_cpq.py"), "--tris", "1600000", "--queries", "4400000",
+                          "--chunk", "1100000", "--check", "50000", "--p2p"], capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stderr[-2000:]
     res = json.loads(out.stdout.strip().splitlines()[-1])
-    assert res["n_gpus"] == 2 and res["queries"] == 4_000_000 and res["check"]["bit_exact_vs_oracle"]
+    # 1.6 M triangles (BVH > 64 MB) and chunks of 1.1 M queries: the batches are Morton-ordered, staged locally and
+    # written to rank 0 coalesced (order.cu)
+    assert res["n_gpus"] == 2 and res["queries"] == 4_400_000 and res["check"]["bit_exact_vs_oracle"]
 
 
 def test_pose_edit_update_equals_fresh_build(gpurt, orc, ctx):

@@ -5,13 +5,18 @@
  * over instance transforms (src/vk/vulkan.cpp:777-856) issued by GPURT::build_accel
  * (src/gpurt.cpp:220-241).  Pipeline (all kernels hand-written, one stream):
  *
- *   k_flatten      instances -> world-space triangles (N1), exact AABBs, scene box
- *   k_morton       63-bit Morton key of the AABB centroid (N6)
- *   radix sort     stable 8-bit LSD over 64-bit keys (ties keep gid order)
- *   k_karras       binary radix tree (Karras 2012), one thread per internal node
- *   k_refit        bottom-up AABB union with arrival counters
- *   k_collapse_*   level-synchronous greedy-SAH collapse into 80-byte 8-wide nodes (bvh8.cuh),
- *                  triangles re-laid out in node order
+ *   k_flatten        instances -> world-space triangles (N1), exact AABBs, scene box (block-reduced)
+ *   k_morton         63-bit Morton key of the AABB centroid (N6)
+ *   k_rs_digit_hist, stable 8-bit LSD radix sort over 64-bit keys, "onesweep": one kernel per pass with
+ *   k_rs_onesweep    decoupled look-back between tiles (ties keep gid order)
+ *   k_karras         binary radix tree (Karras 2012), one thread per internal node
+ *   k_refit          bottom-up AABB union with arrival counters (+ SAH-optimal collapse tables when asked for)
+ *   k_collapse_*     level-synchronous collapse into 80-byte 8-wide nodes (bvh8.cuh): greedy largest-area
+ *                    opening by default, runs of small levels inside one CTA
+ *   k_tri_reorder    triangles re-laid out in node order
+ *
+ * Temporaries live in one arena owned by the context; gpurt_accel_update re-runs the pipeline in the buffers
+ * the accel already owns.
  */
 #include <cstdlib>
 #include <cstring>

@@ -344,3 +344,33 @@ def test_sah_optimal_collapse_flag(gpurt, orc, ctx):
     sah.update()                                       # the in-place rebuild keeps the flag
     assert sah.info().n_wide_nodes < 0.8 * base.info().n_wide_nodes
     sah.close(), base.close(), scene.close()
+
+
+def test_no_device_memory_growth_over_create_destroy_cycles(gpurt, ctx):
+    """scene / accel / pipe / update cycles return their device memory (cudaMemGetInfo stays flat)"""
+    import torch
+    w, h = 128, 72
+    cam = gpurt.camera(0, w, h)
+    prm = gpurt.pipe_params(max_frames=1, samples_per_frame=1, max_depth=2, integrator=2)
+
+    def cycle():
+        scene = load_scene(gpurt, ctx, "cbox")
+        accel = gpurt.Accel(scene)
+        pipe = gpurt.RTPipe(scene, accel)
+        pipe.render_frame(prm, cam, w, h)
+        scene.set_transform(2, np.eye(4, dtype=np.float32).reshape(16))
+        accel.update()
+        pipe.reset_frame()
+        pipe.render_frame(prm, cam, w, h)
+        pipe.read_image()
+        pipe.close(), accel.close(), scene.close()
+
+    for _ in range(5):
+        cycle()                      # pools and arenas reach their steady size
+    torch.cuda.synchronize()
+    free0 = torch.cuda.mem_get_info()[0]
+    for _ in range(40):
+        cycle()
+    torch.cuda.synchronize()
+    free1 = torch.cuda.mem_get_info()[0]
+    assert free0 - free1 < (8 << 20), f"device memory shrank by {(free0 - free1) >> 20} MiB over 40 cycles"

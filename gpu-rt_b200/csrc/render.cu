@@ -114,10 +114,13 @@ __global__ void __launch_bounds__(128) k_trace_closest_indirect(const float4* __
 /* One iteration of rt.rgen's bounce loop body after traceRayEXT (rt.rgen:591-627) for the path of pixel
  * `pix`: miss handling, hit_info / mat_info / shade_info, G-buffer capture, the selected integrator and
  * Russian roulette.  Returns true when the path ends here (`break` in the shader). */
+/* INTEG = the integrator, fixed at compile time: one kernel per integrator instead of one kernel carrying all five
+ * (the five-way kernel needs 128 registers -> 23 % occupancy; ncu capture prof_frame_r1k) */
+template <int INTEG>
 __device__ __forceinline__ bool shade_step(const FrameParams& P, Shader& sh, TraceInfo& trace, uint32_t s, uint32_t depth,
                                            uint32_t pix, float4 h, float4* gpos, float4* gnorm, float4* galb,
                                            float4* res_cur) {
-    const bool restir = P.c.integrator == 3 || P.c.integrator == 4;
+    const bool restir = INTEG == 3 || INTEG == 4;
     bool broke = false;
     uint32_t gid = f2u(h.w);
     if(gid == kNoHit) { /* rt.rgen:591-598 */
@@ -136,11 +139,11 @@ __device__ __forceinline__ bool shade_step(const FrameParams& P, Shader& sh, Tra
         galb[pix] = make_float4(mat.albedo.x, mat.albedo.y, mat.albedo.z, 1.0f);
     }
     if(restir && depth == 0) sh.prev_res = Shader::res_load(res_cur + 3ull * pix);
-    if(P.c.integrator == 0) sh.integrate_direct(trace, hit, mat, shade);
-    else if(P.c.integrator == 1) sh.integrate_mats(trace, hit, mat, shade);
-    else if(P.c.integrator == 2) sh.integrate_mis(trace, hit, mat, shade);
-    else if(P.c.integrator == 3) sh.integrate_restir(trace, hit, mat, shade, true, s == 0);
-    else if(P.c.integrator == 4) sh.integrate_restir(trace, hit, mat, shade, false, s == 0);
+    if(INTEG == 0) sh.integrate_direct(trace, hit, mat, shade);
+    else if(INTEG == 1) sh.integrate_mats(trace, hit, mat, shade);
+    else if(INTEG == 2) sh.integrate_mis(trace, hit, mat, shade);
+    else if(INTEG == 3) sh.integrate_restir(trace, hit, mat, shade, true, s == 0);
+    else if(INTEG == 4) sh.integrate_restir(trace, hit, mat, shade, false, s == 0);
     if(restir && depth == 0) Shader::res_store(res_cur + 3ull * pix, sh.prev_res);
     if(P.c.use_rr == 1) { /* rt.rgen:622-627 */
         float pcont = fminf(fmaxf(trace.throughput.x, fmaxf(trace.throughput.y, trace.throughput.z)) + 0.001f, 0.95f);
@@ -150,6 +153,7 @@ __device__ __forceinline__ bool shade_step(const FrameParams& P, Shader& sh, Tra
     return broke;
 }
 
+template <int INTEG>
 __global__ void __launch_bounds__(128) k_shade(const __grid_constant__ FrameParams P,
                                                const __grid_constant__ ShadeCtx X, uint32_t s, uint32_t depth,
                                                const uint32_t* __restrict__ count_in, const uint32_t* __restrict__ queue_in,
@@ -171,7 +175,7 @@ __global__ void __launch_bounds__(128) k_shade(const __grid_constant__ FramePara
         trace.acc = F3{A.x, A.y, A.z}, trace.mis = A.w;
         trace.throughput = F3{B.x, B.y, B.z}, trace.depth = depth;
         sh.seed = __float_as_uint(B.w);
-        bool broke = shade_step(P, sh, trace, s, depth, pix, h, gpos, gnorm, galb, res_cur);
+        bool broke = shade_step<INTEG>(P, sh, trace, s, depth, pix, h, gpos, gnorm, galb, res_cur);
         cont = !broke && trace.depth + 1 < (uint32_t)P.c.max_depth;
         if(cont) {
             pathA[pix] = make_float4(trace.acc.x, trace.acc.y, trace.acc.z, trace.mis);
@@ -209,6 +213,7 @@ __global__ void __launch_bounds__(128) k_shade(const __grid_constant__ FramePara
  * trace + one shade launch per bounce become latency-bound (worst when a frame is sharded over 8 GPUs).
  * Here every remaining path runs its bounce loop to the end in one thread: same shade_step, same
  * traverse8, same per-pixel RNG stream, so the image does not change — only the launch count does. */
+template <int INTEG>
 __global__ void __launch_bounds__(128) k_tail(const __grid_constant__ FrameParams P, const __grid_constant__ ShadeCtx X,
                                               uint32_t s, uint32_t depth0, const uint32_t* __restrict__ count_in,
                                               const uint32_t* __restrict__ queue_in, const float4* __restrict__ rays_in,
@@ -234,7 +239,7 @@ __global__ void __launch_bounds__(128) k_tail(const __grid_constant__ FrameParam
             n_wave++;
             if(X.n_nodes) traverse8<false, false>(X.nodes, X.tris, trace.o, trace.d, kEps, kLargeDist, hr, nullptr);
             float4 h = make_float4(hr.t, hr.u, hr.v, u2f(hr.gid));
-            bool broke = shade_step(P, sh, trace, s, depth, pix, h, gpos, gnorm, galb, res_cur);
+            bool broke = shade_step<INTEG>(P, sh, trace, s, depth, pix, h, gpos, gnorm, galb, res_cur);
             if(broke || trace.depth + 1 >= (uint32_t)P.c.max_depth) break;
         }
         float4 a = acc[pix];
@@ -516,14 +521,33 @@ static int render_core(gpurt_pipe* p, const GpurtPipeParams* prm, const GpurtCam
             int qi = d & 1, qo = qi ^ 1;
             k_trace_closest_indirect<<<cdivu(n, 128), 128, 0, st>>>(X.nodes, X.tris, p->rays[qi], p->counts + d, p->hits,
                                                                    X.n_nodes);
-            k_shade<<<cdivu(n, 128), 128, 0, st>>>(F, X, s, d, p->counts + d, p->queue[qi], p->rays[qi], p->hits, p->pathA,
-                                                  p->pathB, p->acc, p->gbuf[cur][0], p->gbuf[cur][1], p->gbuf[cur][2],
-                                                  p->res[cur], p->counts + d + 1, p->queue[qo], p->rays[qo]);
+#define GPURT_SHADE(I)                                                                                                   \
+    k_shade<I><<<cdivu(n, 128), 128, 0, st>>>(F, X, s, d, p->counts + d, p->queue[qi], p->rays[qi], p->hits, p->pathA,  \
+                                              p->pathB, p->acc, p->gbuf[cur][0], p->gbuf[cur][1], p->gbuf[cur][2],      \
+                                              p->res[cur], p->counts + d + 1, p->queue[qo], p->rays[qo])
+            switch(c.integrator) {
+            case 0: GPURT_SHADE(0); break;
+            case 1: GPURT_SHADE(1); break;
+            case 2: GPURT_SHADE(2); break;
+            case 3: GPURT_SHADE(3); break;
+            default: GPURT_SHADE(4); break;
+            }
+#undef GPURT_SHADE
         }
-        if(wave < D)
-            k_tail<<<cdivu(n, 128), 128, 0, st>>>(F, X, s, wave, p->counts + wave, p->queue[wave & 1], p->rays[wave & 1],
-                                                 p->pathA, p->pathB, p->acc, p->gbuf[cur][0], p->gbuf[cur][1],
-                                                 p->gbuf[cur][2], p->res[cur]);
+        if(wave < D) {
+#define GPURT_TAIL(I)                                                                                                    \
+    k_tail<I><<<cdivu(n, 128), 128, 0, st>>>(F, X, s, wave, p->counts + wave, p->queue[wave & 1], p->rays[wave & 1],     \
+                                             p->pathA, p->pathB, p->acc, p->gbuf[cur][0], p->gbuf[cur][1],              \
+                                             p->gbuf[cur][2], p->res[cur])
+            switch(c.integrator) {
+            case 0: GPURT_TAIL(0); break;
+            case 1: GPURT_TAIL(1); break;
+            case 2: GPURT_TAIL(2); break;
+            case 3: GPURT_TAIL(3); break;
+            default: GPURT_TAIL(4); break;
+            }
+#undef GPURT_TAIL
+        }
         /* closest-hit rays of the wavefront = sum of queue sizes */
     }
     k_frame_end<<<cdivu(n, 256), 256, 0, st>>>(F, p->acc, p->image, p->gbuf[cur][0], p->gbuf[cur][1], p->gbuf[prev][0],

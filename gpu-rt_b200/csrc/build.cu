@@ -661,9 +661,16 @@ int build_accel_device(gpurt_accel* A) {
     float* dp_cost = ar.take<float>(sah ? (size_t)ni * 7 : 1);
     if(!dp_cost) return set_error("build arena layout"), GPURT_E_STATE;
 
-    cudaEvent_t e0, e1;
-    GPURT_CUDA(cudaEventCreate(&e0));
-    GPURT_CUDA(cudaEventCreate(&e1));
+    struct EventPair { /* destroyed on every return path */
+        cudaEvent_t a = nullptr, b = nullptr;
+        ~EventPair() {
+            if(a) cudaEventDestroy(a);
+            if(b) cudaEventDestroy(b);
+        }
+    } ev;
+    GPURT_CUDA(cudaEventCreate(&ev.a));
+    GPURT_CUDA(cudaEventCreate(&ev.b));
+    cudaEvent_t e0 = ev.a, e1 = ev.b;
     GPURT_CUDA(cudaEventRecord(e0, st));
 
     float init[6] = {3.0e38f, 3.0e38f, 3.0e38f, -3.0e38f, -3.0e38f, -3.0e38f};
@@ -674,7 +681,6 @@ int build_accel_device(gpurt_accel* A) {
     if(n == 0) {
         for(float& f : A->scene_box) f = 0;
         A->n_nodes = 0, A->depth = 0, A->build_ms = 0;
-        cudaEventDestroy(e0), cudaEventDestroy(e1);
         return GPURT_OK;
     }
     const float* sb = A->scene_box;
@@ -769,7 +775,6 @@ int build_accel_device(gpurt_accel* A) {
     GPURT_CUDA(cudaEventRecord(e1, st));
     GPURT_CUDA(cudaStreamSynchronize(st));
     cudaEventElapsedTime(&A->build_ms, e0, e1);
-    cudaEventDestroy(e0), cudaEventDestroy(e1);
     GPURT_CUDA(cudaGetLastError());
     return GPURT_OK;
 }

@@ -67,6 +67,42 @@ def main():
         json.dump(g, f, indent=1)
     print(len(files), "images ->", OUT)
     features()
+    embedded_glb()
+
+
+def embedded_glb():
+    """embedded.glb: binary glTF whose geometry and two images (a progressive JPEG and a palette PNG) all live in
+    the BIN chunk and are referenced through bufferViews (image.bufferView + mimeType)"""
+    import struct
+    pos = np.array([[0, 0, 0], [2, 0, 0], [0, 2, 0], [2, 2, 1]], np.float32)
+    uv = np.array([[0, 0], [1, 0], [0, 1], [1, 1]], np.float32)
+    idx = np.array([0, 1, 2, 2, 1, 3], np.uint16)
+    jpg = open(os.path.join(OUT, "jprog_420.jpg"), "rb").read()
+    png = open(os.path.join(OUT, "p_pal.png"), "rb").read()
+    chunks, views = [], []
+    for raw in (pos.tobytes(), uv.tobytes(), idx.tobytes(), jpg, png):
+        off = sum(len(c) for c in chunks)
+        views.append({"buffer": 0, "byteOffset": off, "byteLength": len(raw)})
+        chunks.append(raw + b"\0" * ((-len(raw)) % 4))
+    blob = b"".join(chunks)
+    g = {"asset": {"version": "2.0"}, "scene": 0, "scenes": [{"nodes": [0]}],
+         "nodes": [{"mesh": 0, "matrix": [1, 0, 0, 0, 0, 0, 1, 0, 0, -1, 0, 0, 0.5, 0.25, -1, 1]}],
+         "meshes": [{"primitives": [{"attributes": {"POSITION": 0, "TEXCOORD_0": 1}, "indices": 2, "material": 0}]}],
+         "materials": [{"pbrMetallicRoughness": {"baseColorTexture": {"index": 0}, "metallicRoughnessTexture": {"index": 1}},
+                        "emissiveFactor": [0.5, 0.25, 0.125]}],
+         "textures": [{"source": 0}, {"source": 1}],
+         "images": [{"bufferView": 3, "mimeType": "image/jpeg"}, {"bufferView": 4, "mimeType": "image/png"}],
+         "buffers": [{"byteLength": len(blob)}], "bufferViews": views,
+         "accessors": [{"bufferView": 0, "componentType": 5126, "count": 4, "type": "VEC3", "min": [0, 0, 0], "max": [2, 2, 1]},
+                       {"bufferView": 1, "componentType": 5126, "count": 4, "type": "VEC2"},
+                       {"bufferView": 2, "componentType": 5123, "count": 6, "type": "SCALAR"}]}
+    js = json.dumps(g).encode()
+    js += b" " * ((-len(js)) % 4)
+    glb = b"glTF" + struct.pack("<II", 2, 12 + 8 + len(js) + 8 + len(blob)) + struct.pack("<II", len(js), 0x4E4F534A) + js \
+        + struct.pack("<II", len(blob), 0x004E4942) + blob
+    with open(os.path.join(OUT, "embedded.glb"), "wb") as f:
+        f.write(glb)
+    print("embedded.glb:", len(glb), "bytes")
 
 
 def features():

@@ -107,7 +107,8 @@ def main():
          "scenes": [dump_scene("cbox/cbox.gltf", 1.0), dump_scene("cbox/cbox.gltf", 0.37),
                     dump_scene("mis_test/mis_test.gltf", 1.0), dump_scene("cube.gltf", 1.0),
                     dump_scene("synth/features.gltf", 1.0, os.path.join(ROOT, "tests", "data")),
-                    dump_scene("synth/features.gltf", 2.5, os.path.join(ROOT, "tests", "data"))],
+                    dump_scene("synth/features.gltf", 2.5, os.path.join(ROOT, "tests", "data")),
+                    dump_scene("synth/embedded.glb", 1.0, os.path.join(ROOT, "tests", "data"))],
          "cameras": [dump_camera(0, 1280, 720, None, None, 0.0), dump_camera(0, 1024, 1024, None, None, 0.0),
                      dump_camera(1, 1920, 1080, [-1000.0, 200.0, 0.0], [0.0, 200.0, 0.0], 90.0),
                      dump_camera(1, 1920, 1080, [0.5, 0.6, 2.6], [0.5, 0.45, 0.0], 50.0),
@@ -118,6 +119,7 @@ def main():
     synth = os.path.join(ROOT, "tests", "data", "synth")
     names = [im["uri"] for im in json.load(open(os.path.join(synth, "textures.gltf")))["images"]]
     g["synth_textures"] = dump_textures(os.path.join(synth, "textures.gltf"), names)
+    g["glb_textures"] = dump_textures(os.path.join(synth, "embedded.glb"), ["jprog_420.jpg (bufferView)", "p_pal.png (bufferView)"])
     sponza = os.path.join(REF_MEDIA, "sponza")
     files = sorted(f for f in os.listdir(sponza) if f.endswith((".jpg", ".png")))
     import tempfile

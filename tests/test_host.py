@@ -206,6 +206,14 @@ def test_texture_decode_matches_reference_decoder(gpurt):
         assert (g["w"], g["h"], g["sha256"]) == (w, h, sha), g["file"]
 
 
+def test_glb_embedded_images_match_reference_decoder(gpurt):
+    """binary glTF with geometry and images (JPEG + PNG) in the BIN chunk, referenced through bufferViews"""
+    s = gpurt.Scene(None).load(os.path.join(ROOT, "tests", "data", "synth", "embedded.glb"))
+    assert "[warn]" not in gpurt.last_error()
+    got = _texture_hashes(s)
+    assert [(g["w"], g["h"], g["sha256"]) for g in GOLDEN["glb_textures"]] == got
+
+
 @pytest.mark.skipif(not os.path.isdir("/root/reference/media/sponza"), reason="reference media not present")
 def test_sponza_textures_match_reference_decoder(gpurt, tmp_path):
     """all 69 textures of media/sponza (65 baseline JPEG, 4 PNG; up to 2048^2) decode bit-identically to the reference"""

@@ -393,6 +393,13 @@ bool Scene::load(const std::string& file, std::string& err) {
                     else if(kv.first == "TEXCOORD_0") read_vec(a, 2, uv);
                 }
             }
+            if(!(mode == 4 || mode == 5 || mode == 6)) {
+                /* points / lines: the reference keeps the index list next to an empty vertex array (scene.cpp:278-283)
+                 * and dies in the Vulkan upload; here the object stays (ids and object order as in the reference)
+                 * but holds no triangles */
+                indices.clear();
+                err += "[warn] primitive with mode " + std::to_string(mode) + " is not triangle based, ignored; ";
+            }
             /* scene.cpp:286-302; tinygltf defaults: baseColor 1, metallic 1, roughness 1 */
             Material mat;
             const Json& gm = materials[(size_t)prim["material"].integer(-1)];

@@ -306,3 +306,23 @@ int main(void) {
     assert r.returncode == 0, r.stderr
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0 and "gpurt-b200" in r.stdout, (r.returncode, r.stdout, r.stderr)
+
+
+def test_non_triangle_primitives_keep_their_slot_but_no_triangles(gpurt, tmp_path):
+    """points / lines primitives: the object (and with it ids and object order) stays, with zero triangles and a
+    warning — the reference keeps indices next to an empty vertex array and dies in the Vulkan upload"""
+    pos = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [1, 1, 0], [2, 1, 0], [2, 2, 0]], np.float32)
+    blob = pos.tobytes() + np.arange(6, dtype=np.uint16).tobytes()
+    prim = lambda mode: {"attributes": {"POSITION": 0}, "indices": 1, "material": 0, "mode": mode}
+    g = {"asset": {"version": "2.0"}, "scene": 0, "scenes": [{"nodes": [0]}], "nodes": [{"mesh": 0}],
+         "meshes": [{"primitives": [prim(0), prim(1), prim(4)]}], "materials": [{"pbrMetallicRoughness": {}}],
+         "buffers": [{"byteLength": len(blob), "uri": "data:application/octet-stream;base64," + base64.b64encode(blob).decode()}],
+         "bufferViews": [{"buffer": 0, "byteOffset": 0, "byteLength": 72}, {"buffer": 0, "byteOffset": 72, "byteLength": 12}],
+         "accessors": [{"bufferView": 0, "componentType": 5126, "count": 6, "type": "VEC3"},
+                       {"bufferView": 1, "componentType": 5123, "count": 6, "type": "SCALAR"}]}
+    p = tmp_path / "pl.gltf"
+    p.write_text(json.dumps(g))
+    s = gpurt.Scene(None).load(str(p))
+    assert s.counts()["objs"] == 3 and s.counts()["tris"] == 2 and "[warn]" in gpurt.last_error()
+    assert sorted(s.object(i)[1].size for i in range(3)) == [0, 0, 6]
+    assert list(s.tri_offsets()) in ([0, 2, 2, 2], [0, 0, 2, 2], [0, 0, 0, 2])

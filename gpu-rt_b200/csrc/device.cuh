@@ -9,6 +9,7 @@
 
 #include "../host/internal.h"
 #include "bvh8.cuh"
+#include "scene_view.cuh"
 
 namespace gpurt {
 
@@ -48,22 +49,6 @@ struct gpurt_ctx {
 };
 
 namespace gpurt {
-
-/* Device copy of PackedScene: the descriptor arrays of src/vk/rt.cpp:529-741 as plain pointers. */
-struct DeviceScene {
-    Vertex* verts = nullptr;
-    uint32_t* idx = nullptr;
-    uint32_t* tri_off = nullptr;
-    uint32_t* vert_off = nullptr;
-    SceneDesc* descs = nullptr;
-    SceneLight* lights = nullptr;
-    uint32_t n_objs = 0, n_tris = 0, n_lights = 0, n_verts = 0;
-    uint64_t version = 0, geom_version = 0;
-    /* textures: RGBA8 texels, one allocation, per-texture (offset,w,h) table */
-    uint8_t* texels = nullptr;
-    uint4* tex_info = nullptr; /* x: texel offset, y: w, z: h */
-    uint32_t n_textures = 0;
-};
 
 int upload_scene(gpurt_ctx* ctx, gpurt_scene* s, DeviceScene& out);
 void free_scene(DeviceScene& d);

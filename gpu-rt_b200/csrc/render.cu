@@ -24,6 +24,7 @@
 #include <cstring>
 
 #include "../host/camera.h"
+#include "device.cuh"
 #include "shade.cuh"
 
 using namespace gpurt;
@@ -60,21 +61,7 @@ __global__ void __launch_bounds__(256) k_frame_begin(const __grid_constant__ Fra
                                                      float4* res_out) {
     uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
     if(li >= P.n_local) return;
-    const uint32_t i = shard_pixel(P, li);
-    /* tea(pixel, seed) — rtcommon.glsl:99-109; Q1: seed = user seed ^ frame replaces clockARB() */
-    uint32_t v0 = i, v1 = P.seed_val, s0 = 0;
-    for(uint32_t k = 0; k < 16; k++) {
-        s0 += 0x9e3779b9u;
-        v0 += ((v1 << 4) + 0xa341316cu) ^ (v1 + s0) ^ ((v1 >> 5) + 0xc8013ea4u);
-        v1 += ((v0 << 4) + 0xad90777du) ^ (v0 + s0) ^ ((v0 >> 5) + 0x7e95761eu);
-    }
-    acc[i] = make_float4(0, 0, 0, 0);
-    pathB[i] = make_float4(1, 1, 1, __uint_as_float(v0));
-    gpos[i] = gnorm[i] = galb[i] = make_float4(0, 0, 0, 1); /* rt.rgen:573, :674-676 */
-    if(restir) {
-        res_out[3ull * i] = res_out[3ull * i + 1] = make_float4(0, 0, 0, 0);
-        res_out[3ull * i + 2] = make_float4(0, 0, 0, __uint_as_float(0u));
-    }
+    pixel_begin(P, restir, shard_pixel(P, li), acc, pathB, gpos, gnorm, galb, res_out);
 }
 
 __global__ void __launch_bounds__(256) k_gen_camera(const __grid_constant__ FrameParams P, uint32_t s,
@@ -83,18 +70,7 @@ __global__ void __launch_bounds__(256) k_gen_camera(const __grid_constant__ Fram
     uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
     if(li == 0) *count = P.n_local;
     if(li >= P.n_local) return;
-    const uint32_t i = shard_pixel(P, li);
-    ShadeCtx dummy{};
-    Shader sh(dummy, P);
-    float4 B = pathB[i];
-    sh.seed = __float_as_uint(B.w);
-    F3 d = sh.make_camera_ray(s, i % P.W, i / P.W);
-    F4 co = mul4(P.cam.iV, 0.0f, 0.0f, 0.0f, 1.0f); /* rt.rgen:572 */
-    rays[2ull * li] = make_float4(co.x, co.y, co.z, kEps);
-    rays[2ull * li + 1] = make_float4(d.x, d.y, d.z, kLargeDist);
-    queue[li] = i;
-    pathA[i] = make_float4(0, 0, 0, 1.0f);                           /* trace.acc, trace.mis */
-    pathB[i] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(sh.seed)); /* trace.throughput, rng */
+    pixel_gen_camera(P, s, shard_pixel(P, li), li, pathA, pathB, rays, queue);
 }
 
 __global__ void __launch_bounds__(128) k_trace_closest_indirect(const float4* __restrict__ nodes,
@@ -109,48 +85,6 @@ __global__ void __launch_bounds__(128) k_trace_closest_indirect(const float4* __
     h.t = a.w, h.u = h.v = 0, h.gid = kNoHit;
     if(n_nodes) traverse8<false, false>(nodes, tris, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), a.w, b.w, h, nullptr);
     hits[i] = make_float4(h.gid == kNoHit ? GPURT_INF : h.t, h.u, h.v, u2f(h.gid));
-}
-
-/* One iteration of rt.rgen's bounce loop body after traceRayEXT (rt.rgen:591-627) for the path of pixel
- * `pix`: miss handling, hit_info / mat_info / shade_info, G-buffer capture, the selected integrator and
- * Russian roulette.  Returns true when the path ends here (`break` in the shader). */
-/* INTEG = the integrator, fixed at compile time: one kernel per integrator instead of one kernel carrying all five
- * (the five-way kernel needs 128 registers -> 23 % occupancy; ncu capture prof_frame_r1k) */
-template <int INTEG>
-__device__ __forceinline__ bool shade_step(const FrameParams& P, Shader& sh, TraceInfo& trace, uint32_t s, uint32_t depth,
-                                           uint32_t pix, float4 h, float4* gpos, float4* gnorm, float4* galb,
-                                           float4* res_cur) {
-    const bool restir = INTEG == 3 || INTEG == 4;
-    bool broke = false;
-    uint32_t gid = f2u(h.w);
-    if(gid == kNoHit) { /* rt.rgen:591-598 */
-        if(depth == 0) trace.acc = F3{P.c.clear_col[0], P.c.clear_col[1], P.c.clear_col[2]};
-        else trace.acc = trace.acc + F3{P.c.env_light[0], P.c.env_light[1], P.c.env_light[2]} * trace.throughput;
-        return true;
-    }
-    Payload pl;
-    sh.payload_from_hit(h.y, h.z, gid, pl);
-    HitInfo hit = sh.hit_info(pl);
-    MatInfo mat = sh.mat_info(pl, hit);
-    ShadeInfo shade = sh.shade_info(trace.d, hit, mat);
-    if(s == 0 && depth == 0) { /* rt.rgen:604-608 */
-        gpos[pix] = make_float4(hit.pos.x, hit.pos.y, hit.pos.z, 1.0f);
-        gnorm[pix] = make_float4(shade.N.x, shade.N.y, shade.N.z, 1.0f);
-        galb[pix] = make_float4(mat.albedo.x, mat.albedo.y, mat.albedo.z, 1.0f);
-    }
-    if(restir && depth == 0) sh.prev_res = Shader::res_load(res_cur + 3ull * pix);
-    if(INTEG == 0) sh.integrate_direct(trace, hit, mat, shade);
-    else if(INTEG == 1) sh.integrate_mats(trace, hit, mat, shade);
-    else if(INTEG == 2) sh.integrate_mis(trace, hit, mat, shade);
-    else if(INTEG == 3) sh.integrate_restir(trace, hit, mat, shade, true, s == 0);
-    else if(INTEG == 4) sh.integrate_restir(trace, hit, mat, shade, false, s == 0);
-    if(restir && depth == 0) Shader::res_store(res_cur + 3ull * pix, sh.prev_res);
-    if(P.c.use_rr == 1) { /* rt.rgen:622-627 */
-        float pcont = fminf(fmaxf(trace.throughput.x, fmaxf(trace.throughput.y, trace.throughput.z)) + 0.001f, 0.95f);
-        if(sh.randf() >= pcont) broke = true;
-        else trace.throughput = trace.throughput / pcont;
-    }
-    return broke;
 }
 
 template <int INTEG>
@@ -174,7 +108,7 @@ __global__ void __launch_bounds__(128) k_shade(const __grid_constant__ FramePara
         trace.o = F3{r0.x, r0.y, r0.z}, trace.d = F3{r1.x, r1.y, r1.z};
         trace.acc = F3{A.x, A.y, A.z}, trace.mis = A.w;
         trace.throughput = F3{B.x, B.y, B.z}, trace.depth = depth;
-        sh.seed = __float_as_uint(B.w);
+        sh.seed = f2u(B.w);
         bool broke = shade_step<INTEG>(P, sh, trace, s, depth, pix, h, gpos, gnorm, galb, res_cur);
         cont = !broke && trace.depth + 1 < (uint32_t)P.c.max_depth;
         if(cont) {
@@ -223,44 +157,15 @@ __global__ void __launch_bounds__(128) k_tail(const __grid_constant__ FrameParam
     bool live = k < *count_in;
     Shader sh(X, P);
     unsigned n_wave = 0;
-    if(live) {
-        uint32_t pix = queue_in[k];
-        float4 r0 = rays_in[2ull * k], r1 = rays_in[2ull * k + 1];
-        float4 A = pathA[pix], B = pathB[pix];
-        TraceInfo trace;
-        trace.o = F3{r0.x, r0.y, r0.z}, trace.d = F3{r1.x, r1.y, r1.z};
-        trace.acc = F3{A.x, A.y, A.z}, trace.mis = A.w;
-        trace.throughput = F3{B.x, B.y, B.z};
-        sh.seed = __float_as_uint(B.w);
-        for(uint32_t depth = depth0;; depth++) {
-            trace.depth = depth;
-            HitRec hr;
-            hr.gid = kNoHit, hr.t = 0, hr.u = hr.v = 0;
-            n_wave++;
-            if(X.n_nodes) traverse8<false, false>(X.nodes, X.tris, trace.o, trace.d, kEps, kLargeDist, hr, nullptr);
-            float4 h = make_float4(hr.t, hr.u, hr.v, u2f(hr.gid));
-            bool broke = shade_step<INTEG>(P, sh, trace, s, depth, pix, h, gpos, gnorm, galb, res_cur);
-            if(broke || trace.depth + 1 >= (uint32_t)P.c.max_depth) break;
-        }
-        float4 a = acc[pix];
-        acc[pix] = make_float4(a.x + trace.acc.x, a.y + trace.acc.y, a.z + trace.acc.z, 0.0f);
-        pathB[pix] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(sh.seed));
-    }
+    if(live)
+        n_wave = path_tail<INTEG>(P, X, sh, s, depth0, queue_in[k], rays_in[2ull * k], rays_in[2ull * k + 1], pathA, pathB,
+                                  acc, gpos, gnorm, galb, res_cur);
     unsigned nc = __reduce_add_sync(0xffffffffu, live ? n_wave + sh.n_closest : 0u);
     unsigned na = __reduce_add_sync(0xffffffffu, live ? sh.n_any : 0u);
     if((threadIdx.x & 31) == 0) {
         if(nc) atomicAdd(X.ray_counts + 0, (unsigned long long)nc);
         if(na) atomicAdd(X.ray_counts + 1, (unsigned long long)na);
     }
-}
-
-/* rt.rgen:640-645: progressive mean over frames */
-__device__ __forceinline__ float4 accumulate_frame(float4 old, F3 avg, int frame) {
-    if(frame > 0) {
-        F3 m = mix3(F3{old.x, old.y, old.z}, avg, 1.0f / (float)(frame + 1));
-        return make_float4(m.x, m.y, m.z, 1.0f);
-    }
-    return make_float4(avg.x, avg.y, avg.z, 1.0f);
 }
 
 /* frame-parallel sharding: fold the frame mean another GPU rendered into this pipe's image */
@@ -278,32 +183,7 @@ __global__ void __launch_bounds__(256) k_frame_end(const __grid_constant__ Frame
                                                    float4* mean_out) {
     uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
     if(li >= P.n_local) return;
-    const uint32_t i = shard_pixel(P, li);
-    float4 a = acc[i];
-    F3 avg = F3{a.x, a.y, a.z} / (float)P.c.samples; /* rt.rgen:638 */
-    if(mean_out) { /* frame-parallel sharding: hand the frame mean to the accumulating rank, leave the image alone */
-        mean_out[i] = make_float4(avg.x, avg.y, avg.z, 1.0f);
-        return;
-    }
-    float4 out;
-    out = accumulate_frame(P.c.frame > 0 ? image[i] : make_float4(0, 0, 0, 0), avg, P.c.frame);
-    if(P.c.debug_view > 0) { /* rt.rgen:647-672 */
-        float4 gp = gpos[i], gn = gnorm[i];
-        F4 pp = mul4(P.cam.prev_PV, gp.x, gp.y, gp.z, 1.0f);
-        pp.x /= pp.w, pp.y /= pp.w, pp.z /= pp.w;
-        pp.x = (pp.x + 1.0f) * 0.5f, pp.y = (pp.y + 1.0f) * 0.5f;
-        F3 n = F3{gn.x, gn.y, gn.z};
-        if(dot3(n, n) > 0.5f && (pp.x > 0 && pp.y > 0) && (pp.x < 1 && pp.y < 1)) {
-            int W = (int)P.W, H = (int)P.H;
-            int x = (int)floorf(pp.x * (float)W), y = (int)floorf(pp.y * (float)H);
-            x = ((x % W) + W) % W, y = ((y % H) + H) % H;
-            const float4* img = P.c.debug_view == 1 ? ppos : P.c.debug_view == 2 ? pnorm : palb;
-            float4 v = img[(size_t)y * W + x];
-            if(P.c.debug_view <= 3) out = make_float4(v.x, v.y, v.z, 1.0f);
-        } else
-            out = make_float4(0, 0, 0, 1.0f);
-    }
-    image[i] = out;
+    pixel_end(P, shard_pixel(P, li), acc, image, gpos, gnorm, ppos, pnorm, palb, mean_out);
 }
 
 /* tonemap.frag:17-48 followed by the R8G8B8A8_SRGB framebuffer encode (gpurt.cpp:176) */

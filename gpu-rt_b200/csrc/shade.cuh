@@ -10,12 +10,21 @@
  */
 #pragma once
 #include "../../include/gpurt_detmath.h"
-#include "device.cuh"
+#include "scene_view.cuh"
 #include "traverse.cuh"
 
 namespace gpurt {
 
+/* Like traverse.cuh this file also compiles for the host: tests/emu replays the per-pixel functions
+ * below on the CPU against the oracle (test-only; the product launches them from render.cu). */
+#if defined(__CUDACC__)
 #define SH_D __device__ __forceinline__
+#define SH_CONST __constant__
+#else
+#define SH_D inline
+#define SH_CONST static
+inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+#endif
 
 constexpr float kPiGlsl = 3.141592f;       /* rtcommon.glsl:6 */
 constexpr float kLargeDist = 10000000.0f;  /* rtcommon.glsl:7 */
@@ -67,7 +76,7 @@ struct FrameParams {
 
 /* i-th locally rendered pixel -> global pixel index y*W + x (RNG, image and G-buffers are indexed by
  * the global pixel, so results do not depend on how the frame is sharded) */
-__device__ __forceinline__ uint32_t shard_pixel(const FrameParams& P, uint32_t i) {
+SH_D uint32_t shard_pixel(const FrameParams& P, uint32_t i) {
     uint32_t per_band = P.band_rows * P.W;
     uint32_t band = i / per_band, in_band = i - band * per_band;
     /* inside a band pixels are enumerated in 8x4 tiles, so the 32 camera rays a warp traces together
@@ -122,7 +131,7 @@ struct LightSample {
     float pdf;
 };
 
-__constant__ float c_srgb_lut[256];
+SH_CONST float c_srgb_lut[256];
 
 /* everything a shading thread can see */
 struct ShadeCtx {
@@ -504,7 +513,7 @@ struct Shader {
              * build already holds the same world-space triangles, contiguous per object */
             const float4* tp = X.tri_world + 3ull * X.S.tri_off[o_idx];
             for(uint32_t t = 0; t < n_tris; t++, tp += 3) {
-                float4 r0 = __ldg(tp), r1 = __ldg(tp + 1), r2 = __ldg(tp + 2);
+                float4 r0 = GPURT_LDG(tp), r1 = GPURT_LDG(tp + 1), r2 = GPURT_LDG(tp + 2);
                 tacc += triangle_pdf_flat(p, d, F3{r0.x, r0.y, r0.z}, F3{r1.x, r1.y, r1.z}, F3{r2.x, r2.y, r2.z});
             }
             oacc += tacc / (float)n_tris;
@@ -631,13 +640,13 @@ struct Shader {
         Reservoir r;
         r.pos = F3{a.x, a.y, a.z}, r.w_sum = a.w;
         r.normal = F3{b.x, b.y, b.z}, r.w = b.w;
-        r.emissive = F3{c.x, c.y, c.z}, r.n_seen = __float_as_uint(c.w);
+        r.emissive = F3{c.x, c.y, c.z}, r.n_seen = f2u(c.w);
         return r;
     }
     SH_D static void res_store(float4* p, const Reservoir& r) {
         p[0] = make_float4(r.pos.x, r.pos.y, r.pos.z, r.w_sum);
         p[1] = make_float4(r.normal.x, r.normal.y, r.normal.z, r.w);
-        p[2] = make_float4(r.emissive.x, r.emissive.y, r.emissive.z, __uint_as_float(r.n_seen));
+        p[2] = make_float4(r.emissive.x, r.emissive.y, r.emissive.z, u2f(r.n_seen));
     }
     /* rt.rgen:415-433 */
     SH_D float update_weight(Reservoir& res, const HitInfo& hit, const MatInfo& mat, const ShadeInfo& shade) const {
@@ -766,5 +775,150 @@ struct Shader {
         return normalize3(F3{direction.x, direction.y, direction.z});
     }
 };
+
+/* ---- per-pixel bodies of the frame kernels (render.cu launches them; tests/emu replays them) ---------------- */
+
+/* k_frame_begin: tea(pixel, seed) — rtcommon.glsl:99-109; Q1: seed = user seed ^ frame replaces clockARB() */
+SH_D void pixel_begin(const FrameParams& P, int restir, uint32_t i, float4* acc, float4* pathB, float4* gpos,
+                      float4* gnorm, float4* galb, float4* res_out) {
+    uint32_t v0 = i, v1 = P.seed_val, s0 = 0;
+    for(uint32_t k = 0; k < 16; k++) {
+        s0 += 0x9e3779b9u;
+        v0 += ((v1 << 4) + 0xa341316cu) ^ (v1 + s0) ^ ((v1 >> 5) + 0xc8013ea4u);
+        v1 += ((v0 << 4) + 0xad90777du) ^ (v0 + s0) ^ ((v0 >> 5) + 0x7e95761eu);
+    }
+    acc[i] = make_float4(0, 0, 0, 0);
+    pathB[i] = make_float4(1, 1, 1, u2f(v0));
+    gpos[i] = gnorm[i] = galb[i] = make_float4(0, 0, 0, 1); /* rt.rgen:573, :674-676 */
+    if(restir) {
+        res_out[3ull * i] = res_out[3ull * i + 1] = make_float4(0, 0, 0, 0);
+        res_out[3ull * i + 2] = make_float4(0, 0, 0, u2f(0u));
+    }
+}
+
+/* k_gen_camera: sample s of pixel i -> ray slot li of queue 0 (rt.rgen:551-565, :572, :579-585) */
+SH_D void pixel_gen_camera(const FrameParams& P, uint32_t s, uint32_t i, uint32_t li, float4* pathA, float4* pathB,
+                           float4* rays, uint32_t* queue) {
+    ShadeCtx dummy{};
+    Shader sh(dummy, P);
+    float4 B = pathB[i];
+    sh.seed = f2u(B.w);
+    F3 d = sh.make_camera_ray(s, i % P.W, i / P.W);
+    F4 co = mul4(P.cam.iV, 0.0f, 0.0f, 0.0f, 1.0f); /* rt.rgen:572 */
+    rays[2ull * li] = make_float4(co.x, co.y, co.z, kEps);
+    rays[2ull * li + 1] = make_float4(d.x, d.y, d.z, kLargeDist);
+    queue[li] = i;
+    pathA[i] = make_float4(0, 0, 0, 1.0f);                /* trace.acc, trace.mis */
+    pathB[i] = make_float4(1.0f, 1.0f, 1.0f, u2f(sh.seed)); /* trace.throughput, rng */
+}
+
+/* One iteration of rt.rgen's bounce loop body after traceRayEXT (rt.rgen:591-627) for the path of pixel
+ * `pix`: miss handling, hit_info / mat_info / shade_info, G-buffer capture, the selected integrator and
+ * Russian roulette.  Returns true when the path ends here (`break` in the shader). */
+/* INTEG = the integrator, fixed at compile time: one kernel per integrator instead of one kernel carrying all five
+ * (the five-way kernel needs 128 registers -> 23 % occupancy; ncu capture prof_frame_r1k) */
+template <int INTEG>
+SH_D bool shade_step(const FrameParams& P, Shader& sh, TraceInfo& trace, uint32_t s, uint32_t depth, uint32_t pix,
+                     float4 h, float4* gpos, float4* gnorm, float4* galb, float4* res_cur) {
+    const bool restir = INTEG == 3 || INTEG == 4;
+    bool broke = false;
+    uint32_t gid = f2u(h.w);
+    if(gid == kNoHit) { /* rt.rgen:591-598 */
+        if(depth == 0) trace.acc = F3{P.c.clear_col[0], P.c.clear_col[1], P.c.clear_col[2]};
+        else trace.acc = trace.acc + F3{P.c.env_light[0], P.c.env_light[1], P.c.env_light[2]} * trace.throughput;
+        return true;
+    }
+    Payload pl;
+    sh.payload_from_hit(h.y, h.z, gid, pl);
+    HitInfo hit = sh.hit_info(pl);
+    MatInfo mat = sh.mat_info(pl, hit);
+    ShadeInfo shade = sh.shade_info(trace.d, hit, mat);
+    if(s == 0 && depth == 0) { /* rt.rgen:604-608 */
+        gpos[pix] = make_float4(hit.pos.x, hit.pos.y, hit.pos.z, 1.0f);
+        gnorm[pix] = make_float4(shade.N.x, shade.N.y, shade.N.z, 1.0f);
+        galb[pix] = make_float4(mat.albedo.x, mat.albedo.y, mat.albedo.z, 1.0f);
+    }
+    if(restir && depth == 0) sh.prev_res = Shader::res_load(res_cur + 3ull * pix);
+    if(INTEG == 0) sh.integrate_direct(trace, hit, mat, shade);
+    else if(INTEG == 1) sh.integrate_mats(trace, hit, mat, shade);
+    else if(INTEG == 2) sh.integrate_mis(trace, hit, mat, shade);
+    else if(INTEG == 3) sh.integrate_restir(trace, hit, mat, shade, true, s == 0);
+    else if(INTEG == 4) sh.integrate_restir(trace, hit, mat, shade, false, s == 0);
+    if(restir && depth == 0) Shader::res_store(res_cur + 3ull * pix, sh.prev_res);
+    if(P.c.use_rr == 1) { /* rt.rgen:622-627 */
+        float pcont = fminf(fmaxf(trace.throughput.x, fmaxf(trace.throughput.y, trace.throughput.z)) + 0.001f, 0.95f);
+        if(sh.randf() >= pcont) broke = true;
+        else trace.throughput = trace.throughput / pcont;
+    }
+    return broke;
+}
+
+/* k_tail's per-path loop: the remaining bounces of pixel `pix` from depth0 on, traced inline; returns the number of
+ * closest-hit rays it traced for the bounces themselves (shadow / light rays are counted inside `sh`) */
+template <int INTEG>
+SH_D unsigned path_tail(const FrameParams& P, const ShadeCtx& X, Shader& sh, uint32_t s, uint32_t depth0, uint32_t pix,
+                        float4 r0, float4 r1, float4* pathA, float4* pathB, float4* acc, float4* gpos, float4* gnorm,
+                        float4* galb, float4* res_cur) {
+    unsigned n_wave = 0;
+    float4 A = pathA[pix], B = pathB[pix];
+    TraceInfo trace;
+    trace.o = F3{r0.x, r0.y, r0.z}, trace.d = F3{r1.x, r1.y, r1.z};
+    trace.acc = F3{A.x, A.y, A.z}, trace.mis = A.w;
+    trace.throughput = F3{B.x, B.y, B.z};
+    sh.seed = f2u(B.w);
+    for(uint32_t depth = depth0;; depth++) {
+        trace.depth = depth;
+        HitRec hr;
+        hr.gid = kNoHit, hr.t = 0, hr.u = hr.v = 0;
+        n_wave++;
+        if(X.n_nodes) traverse8<false, false>(X.nodes, X.tris, trace.o, trace.d, kEps, kLargeDist, hr, nullptr);
+        float4 h = make_float4(hr.t, hr.u, hr.v, u2f(hr.gid));
+        bool broke = shade_step<INTEG>(P, sh, trace, s, depth, pix, h, gpos, gnorm, galb, res_cur);
+        if(broke || trace.depth + 1 >= (uint32_t)P.c.max_depth) break;
+    }
+    float4 a = acc[pix]; /* rt.rgen:630: acc += trace.acc; the RNG stream continues into the next sample */
+    acc[pix] = make_float4(a.x + trace.acc.x, a.y + trace.acc.y, a.z + trace.acc.z, 0.0f);
+    pathB[pix] = make_float4(1.0f, 1.0f, 1.0f, u2f(sh.seed));
+    return n_wave;
+}
+
+/* rt.rgen:640-645: progressive mean over frames */
+SH_D float4 accumulate_frame(float4 old, F3 avg, int frame) {
+    if(frame > 0) {
+        F3 m = mix3(F3{old.x, old.y, old.z}, avg, 1.0f / (float)(frame + 1));
+        return make_float4(m.x, m.y, m.z, 1.0f);
+    }
+    return make_float4(avg.x, avg.y, avg.z, 1.0f);
+}
+
+/* k_frame_end: per-frame mean, progressive accumulation, debug views (rt.rgen:638-672) */
+SH_D void pixel_end(const FrameParams& P, uint32_t i, const float4* acc, float4* image, const float4* gpos,
+                    const float4* gnorm, const float4* ppos, const float4* pnorm, const float4* palb, float4* mean_out) {
+    float4 a = acc[i];
+    F3 avg = F3{a.x, a.y, a.z} / (float)P.c.samples; /* rt.rgen:638 */
+    if(mean_out) { /* frame-parallel sharding: hand the frame mean to the accumulating rank, leave the image alone */
+        mean_out[i] = make_float4(avg.x, avg.y, avg.z, 1.0f);
+        return;
+    }
+    float4 out;
+    out = accumulate_frame(P.c.frame > 0 ? image[i] : make_float4(0, 0, 0, 0), avg, P.c.frame);
+    if(P.c.debug_view > 0) { /* rt.rgen:647-672 */
+        float4 gp = gpos[i], gn = gnorm[i];
+        F4 pp = mul4(P.cam.prev_PV, gp.x, gp.y, gp.z, 1.0f);
+        pp.x /= pp.w, pp.y /= pp.w, pp.z /= pp.w;
+        pp.x = (pp.x + 1.0f) * 0.5f, pp.y = (pp.y + 1.0f) * 0.5f;
+        F3 n = F3{gn.x, gn.y, gn.z};
+        if(dot3(n, n) > 0.5f && (pp.x > 0 && pp.y > 0) && (pp.x < 1 && pp.y < 1)) {
+            int W = (int)P.W, H = (int)P.H;
+            int x = (int)floorf(pp.x * (float)W), y = (int)floorf(pp.y * (float)H);
+            x = ((x % W) + W) % W, y = ((y % H) + H) % H;
+            const float4* img = P.c.debug_view == 1 ? ppos : P.c.debug_view == 2 ? pnorm : palb;
+            float4 v = img[(size_t)y * W + x];
+            if(P.c.debug_view <= 3) out = make_float4(v.x, v.y, v.z, 1.0f);
+        } else
+            out = make_float4(0, 0, 0, 1.0f);
+    }
+    image[i] = out;
+}
 
 } // namespace gpurt

@@ -1,19 +1,23 @@
 /*
  * emu.cpp — CPU replay of the product's host+device traversal/collapse code (csrc/bvh8.cuh,
- * csrc/traverse.cuh) for debugging without a GPU.  TEST-ONLY: built by tests/test_emu.py into
+ * csrc/traverse.cuh) and of the wavefront integrator's per-pixel shading code (csrc/shade.cuh) for debugging without a GPU.  TEST-ONLY: built by tests/test_emu.py into
  * tests/emu/libemu.so, never linked into libgpurt.so and never used as a fallback.
  * The binary LBVH it collapses comes from the oracle (tests pass it in).
  */
 #include <cstring>
 #include <vector>
 
-#include "../../gpu-rt_b200/csrc/traverse.cuh"
+#include <cmath>
+#include <thread>
+
+#include "../../gpu-rt_b200/csrc/shade.cuh"
 
 using namespace gpurt;
 
 struct Emu {
     std::vector<Node8> nodes;
     std::vector<float4> tri_wide;
+    std::vector<float4> tri_gid; /* world-space triangles in global primitive order (k_flatten's output) */
     unsigned depth = 0;
 };
 
@@ -76,6 +80,7 @@ void* emu_build(const float* tris9, unsigned n, const unsigned* order, const int
         B.dp_dec = dp_dec.data();
     }
     E->tri_wide.resize(3ull * n);
+    E->tri_gid = tri_gid;
     if(n == 0) return E;
     if(n <= (unsigned)kMaxLeafTris) {
         int ch[8];
@@ -172,6 +177,99 @@ void emu_cpq(void* h, const float* q, unsigned long long n, unsigned* res8) {
             o[0] = f2u(c.x), o[1] = f2u(c.y), o[2] = f2u(c.z), o[3] = f2u(sqrtf(b.d2));
             o[4] = b.gid, o[5] = 0, o[6] = f2u(b.v), o[7] = f2u(b.w);
         }
+    }
+}
+} /* extern "C" */
+
+/* ---- replay of render.cu's frame: k_frame_begin, then per sample k_gen_camera + the bounce loop (k_tail's per-path
+ * loop from depth 0 — the same shade_step / traverse8 calls the k_trace_closest_indirect + k_shade wavefront makes, in
+ * the same per-pixel order), then k_frame_end.  Pixels only interact through the previous frame's buffers. ---- */
+struct EmuFrameArgs {
+    const uint32_t *descs, *tri_off, *vert_off;
+    const float* verts;
+    const uint32_t* idx;
+    const uint32_t* lights;
+    const uint32_t* tex_info;
+    const uint8_t* texels;
+    uint32_t n_objs, n_lights, n_tex;
+};
+
+template <int I>
+static void render_rows(const FrameParams& P, const ShadeCtx& X, uint32_t i0, uint32_t i1, float4* image, float4* res_cur,
+                        float4* gpos, float4* gnorm, float4* galb, float4* acc, float4* pathA, float4* pathB,
+                        unsigned long long* counts) {
+    const bool restir = I == 3 || I == 4;
+    unsigned long long nc = 0, na = 0;
+    for(uint32_t i = i0; i < i1; i++) {
+        pixel_begin(P, restir ? 1 : 0, i, acc, pathB, gpos, gnorm, galb, res_cur);
+        for(uint32_t s = 0; s < (uint32_t)P.c.samples && P.c.max_depth > 0; s++) {
+            float4 ray[2];
+            uint32_t q;
+            pixel_gen_camera(P, s, i, 0, pathA, pathB, ray, &q);
+            Shader sh(X, P);
+            nc += path_tail<I>(P, X, sh, s, 0, i, ray[0], ray[1], pathA, pathB, acc, gpos, gnorm, galb, res_cur);
+            nc += sh.n_closest, na += sh.n_any;
+        }
+        pixel_end(P, i, acc, image, gpos, gnorm, X.ppos, X.pnorm, X.palb, nullptr);
+    }
+    counts[0] = nc, counts[1] = na;
+}
+
+extern "C" {
+void emu_render_frame(void* bvh, const EmuFrameArgs* A, const uint32_t* consts, const uint32_t* camera, uint32_t w, uint32_t h,
+                      uint32_t seed_val, float* image, const uint32_t* prev_res, uint32_t* out_res, const float* ppos,
+                      const float* pnorm, const float* palb, float* pos, float* norm, float* alb,
+                      unsigned long long* ray_counts2, int threads) {
+    Emu* E = (Emu*)bvh;
+    static bool lut_done = false;
+    if(!lut_done) { /* upload_lut_once() of render.cu */
+        for(int i = 0; i < 256; i++) {
+            double c = i / 255.0;
+            c_srgb_lut[i] = (float)(c <= 0.04045 ? c / 12.92 : std::pow((c + 0.055) / 1.055, 2.4));
+        }
+        lut_done = true;
+    }
+    FrameParams P;
+    std::memset(&P, 0, sizeof(P));
+    std::memcpy(&P.c, consts, sizeof(P.c));
+    std::memcpy(&P.cam, camera, sizeof(P.cam));
+    P.W = w, P.H = h, P.seed_val = seed_val;
+    P.band_rows = h, P.n_shards = 1, P.shard = 0, P.n_local = w * h;
+    ShadeCtx X{};
+    X.S.verts = (Vertex*)A->verts, X.S.idx = (uint32_t*)A->idx, X.S.tri_off = (uint32_t*)A->tri_off;
+    X.S.vert_off = (uint32_t*)A->vert_off, X.S.descs = (SceneDesc*)A->descs, X.S.lights = (SceneLight*)A->lights;
+    X.S.n_objs = A->n_objs, X.S.n_lights = A->n_lights, X.S.n_tris = A->tri_off[A->n_objs];
+    X.S.texels = (uint8_t*)A->texels, X.S.tex_info = (uint4*)A->tex_info, X.S.n_textures = A->n_tex;
+    X.nodes = (const float4*)E->nodes.data(), X.tris = E->tri_wide.data(), X.tri_world = E->tri_gid.data();
+    X.n_nodes = (unsigned)E->nodes.size();
+    X.prev_res = (const float4*)prev_res, X.ppos = (const float4*)ppos, X.pnorm = (const float4*)pnorm, X.palb = (const float4*)palb;
+    const uint32_t n = w * h;
+    std::vector<float4> acc(n), pathA(n), pathB(n);
+    int T = threads > 0 ? threads : (int)std::max(1u, std::thread::hardware_concurrency());
+    T = std::min<int>(T, (int)std::max(1u, n / 64));
+    std::vector<unsigned long long> cnt(2 * T, 0);
+    std::vector<std::thread> pool;
+    for(int t = 0; t < T; t++) {
+        uint32_t i0 = (uint32_t)((unsigned long long)n * t / T), i1 = (uint32_t)((unsigned long long)n * (t + 1) / T);
+        auto run = [&, i0, i1, t] {
+#define EMU_ROWS(I)                                                                                                      \
+    render_rows<I>(P, X, i0, i1, (float4*)image, (float4*)out_res, (float4*)pos, (float4*)norm, (float4*)alb, acc.data(), \
+                   pathA.data(), pathB.data(), &cnt[2 * t])
+            switch(P.c.integrator) {
+            case 0: EMU_ROWS(0); break;
+            case 1: EMU_ROWS(1); break;
+            case 2: EMU_ROWS(2); break;
+            case 3: EMU_ROWS(3); break;
+            default: EMU_ROWS(4); break;
+            }
+#undef EMU_ROWS
+        };
+        pool.emplace_back(run);
+    }
+    for(auto& th : pool) th.join();
+    if(ray_counts2) {
+        ray_counts2[0] = ray_counts2[1] = 0;
+        for(int t = 0; t < T; t++) ray_counts2[0] += cnt[2 * t], ray_counts2[1] += cnt[2 * t + 1];
     }
 }
 }

@@ -1,0 +1,145 @@
+"""CPU replay of the product's integrator code (csrc/shade.cuh: the per-pixel functions render.cu's kernels call)
+against the oracle's restatement of rt.rgen — bit for bit, without a GPU.
+
+The replay (tests/emu/libemu.so) compiles shade.cuh / traverse.cuh / bvh8.cuh for the host and runs, per pixel,
+k_frame_begin -> k_gen_camera -> the bounce loop -> k_frame_end over the emu's own wide BVH.  It is test-only:
+the product never links it, and the GPU parity tests (test_gpu_render.py) remain the proof for the CUDA build."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from conftest import MEDIA, ROOT
+
+
+class FrameArgs(C.Structure):
+    _fields_ = [("descs", C.c_void_p), ("tri_off", C.c_void_p), ("vert_off", C.c_void_p), ("verts", C.c_void_p),
+                ("idx", C.c_void_p), ("lights", C.c_void_p), ("tex_info", C.c_void_p), ("texels", C.c_void_p),
+                ("n_objs", C.c_uint32), ("n_lights", C.c_uint32), ("n_tex", C.c_uint32)]
+
+
+def _vp(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+@pytest.fixture(scope="module")
+def emu(built):
+    lib = C.CDLL(os.path.join(ROOT, "tests", "emu", "libemu.so"))
+    lib.emu_build.restype = C.c_void_p
+    lib.emu_render_frame.restype = None
+    return lib
+
+
+class EmuScene:
+    """the arrays of orc.RenderScene + the emu's wide BVH over the same world triangles"""
+
+    def __init__(self, emu, orc, gscene, textures=()):
+        self.emu, self.rs = emu, orc.RenderScene(gscene, textures)
+        rs, b = self.rs, self.rs.bvh
+        self.order = b.prim_order()
+        l, r, bx = b.bvh2()
+        inflate = np.float32(max(1e-30, np.abs(b.scene_box()).max()) * 2.0 ** -19)
+        self.h = C.c_void_p(emu.emu_build(_vp(rs.tris), len(rs.tris), _vp(self.order), _vp(l), _vp(r), _vp(bx),
+                                          C.c_float(inflate)))
+        self.args = FrameArgs(rs.descs.ctypes.data, rs.tri_off.ctypes.data, rs.vert_off.ctypes.data, rs.verts.ctypes.data,
+                              rs.idx.ctypes.data, rs.lights.ctypes.data, rs.tex_info.ctypes.data, rs.texels.ctypes.data,
+                              rs.n_objs, rs.n_lights, len(textures))
+
+    def render_frame(self, st, consts, cam, seed_val):
+        cur, prev = st.parity, st.parity ^ 1
+        counts = np.zeros(2, np.uint64)
+        self.emu.emu_render_frame(self.h, C.byref(self.args), _vp(consts), _vp(cam), st.w, st.h, C.c_uint32(seed_val),
+                                  _vp(st.image), _vp(st.res[prev]), _vp(st.res[cur]), _vp(st.gb[prev][0]),
+                                  _vp(st.gb[prev][1]), _vp(st.gb[prev][2]), _vp(st.gb[cur][0]), _vp(st.gb[cur][1]),
+                                  _vp(st.gb[cur][2]), _vp(counts), 0)
+        st.parity ^= 1
+        return counts
+
+    def close(self):
+        self.emu.emu_free(self.h)
+
+
+def _uniforms(gpurt, rs, cam, frame, **kw):
+    """the words RTPipe::trace / update_uniforms would push (rt.cpp:121-138, :355-368) for these tunables"""
+    p = gpurt.pipe_params(**kw)
+    c = gpurt.Constants()
+    c.clear_col = (C.c_float * 4)(p.clear[0], p.clear[1], p.clear[2], 1.0)
+    e = [np.float32(p.env_scale) * np.float32(p.env[k]) for k in range(3)]
+    c.env_light = (C.c_float * 4)(e[0], e[1], e[2], 1.0)
+    c.frame, c.samples, c.max_frame, c.qmc, c.max_depth = frame, p.samples_per_frame, p.max_frames, p.use_qmc, p.max_depth
+    c.use_normal_map, c.use_metalness, c.use_temporal, c.integrator = p.use_normal_map, p.use_metalness, p.use_temporal, p.integrator
+    c.brdf, c.debug_view, c.use_rr, c.n_lights, c.n_objs = p.brdf, p.debug_view, p.use_rr, rs.n_lights, rs.n_objs
+    cam = type(cam).from_buffer_copy(bytes(cam))
+    cam.new_samples, cam.temporal_multiplier = p.res_samples, p.temporal_scale
+    V = np.array(cam.V, np.float32).reshape(4, 4).T
+    P = np.array(cam.P, np.float32).reshape(4, 4).T
+    cam.prev_PV = (C.c_float * 16)(*(P @ V).T.reshape(-1))   # static camera: prev_PV = P * V
+    return np.frombuffer(bytes(c), np.uint32).copy(), np.frombuffer(bytes(cam), np.uint32).copy(), p.seed
+
+
+def _run(emu, orc, gpurt, gscene, w, h, frames, cam=None, textures=(), **kw):
+    es = EmuScene(emu, orc, gscene, textures)
+    a, b = orc.FrameState(w, h), orc.FrameState(w, h)
+    cam = cam or gpurt.camera(0, w, h)
+    for f in range(frames):
+        consts, ubo, seed = _uniforms(gpurt, es.rs, cam, f, **kw)
+        ce = es.render_frame(a, consts, ubo, seed ^ f)
+        co = orc.render_frame(es.rs, b, consts, ubo, seed)
+        assert (a.image.view(np.uint32) == b.image.view(np.uint32)).all(), f"frame {f}: image differs"
+        cur = a.parity ^ 1
+        for g in range(3):
+            assert (a.gb[cur][g].view(np.uint32) == b.gb[cur][g].view(np.uint32)).all(), f"frame {f}: G-buffer {g} differs"
+        if kw.get("integrator", 0) in (3, 4):
+            assert (a.res[cur] == b.res[cur]).all(), f"frame {f}: reservoirs differ"
+        assert tuple(int(x) for x in ce) == tuple(int(x) for x in co), "ray counts differ"
+    img = a.image.copy()
+    es.close()
+    return img
+
+
+@pytest.mark.parametrize("integrator", [0, 1, 2, 3, 4])
+def test_cbox_all_integrators(emu, orc, gpurt, integrator):
+    s = gpurt.Scene(None).load(os.path.join(MEDIA, "cbox", "cbox.gltf"))
+    for brdf in (0, 1):
+        img = _run(emu, orc, gpurt, s, 64, 36, 3, integrator=integrator, brdf=brdf, samples_per_frame=2, max_depth=4,
+                   seed=1234 + integrator)
+        assert img[..., :3].mean() > 0.01
+
+
+def test_mis_test_scene(emu, orc, gpurt):
+    s = gpurt.Scene(None).load(os.path.join(MEDIA, "mis_test", "mis_test.gltf"))
+    cam = gpurt.camera(1, 80, 45, (0.5, 0.6, 2.6), (0.5, 0.45, 0.0), 50.0)
+    _run(emu, orc, gpurt, s, 80, 45, 2, cam=cam, integrator=2, brdf=1, samples_per_frame=1, max_depth=4, seed=7)
+    _run(emu, orc, gpurt, s, 80, 45, 4, cam=cam, integrator=3, brdf=0, samples_per_frame=1, max_depth=4, res_samples=4,
+         use_temporal=1, temporal_scale=16, seed=8)
+
+
+def test_options(emu, orc, gpurt):
+    s = gpurt.Scene(None).load(os.path.join(MEDIA, "cbox", "cbox.gltf"))
+    _run(emu, orc, gpurt, s, 48, 27, 2, integrator=1, brdf=1, use_qmc=1, use_metalness=1, use_rr=0, max_depth=3,
+         samples_per_frame=2, env_scale=1.0, seed=3)
+    _run(emu, orc, gpurt, s, 48, 27, 2, integrator=2, brdf=0, max_depth=1, samples_per_frame=1, seed=4)
+    for dv in (1, 2, 3):
+        _run(emu, orc, gpurt, s, 48, 27, 2, integrator=0, debug_view=dv, samples_per_frame=1, seed=5)
+
+
+def test_gltf_feature_scene_with_textures(emu, orc, gpurt):
+    """tests/data/synth/features.gltf: albedo / metal-rough / normal / emissive textures, two lights"""
+    path = os.path.join(ROOT, "tests", "data", "synth", "features.gltf")
+    cam = gpurt.camera(1, 80, 60, (4.0, 3.0, 6.0), (1.0, 1.0, 2.0), 60.0)
+    for integ in (0, 1, 2, 4):
+        scene = gpurt.Scene(None).load(path)
+        texs = [scene.texture(i) for i in range(scene.counts()["textures"])]
+        img = _run(emu, orc, gpurt, scene, 80, 60, 2, cam=cam, textures=texs, integrator=integ, brdf=integ % 2,
+                   samples_per_frame=2, max_depth=3, use_normal_map=1, use_metalness=1, env_scale=0.5, seed=77 + integ)
+        assert img[..., :3].mean() > 0.001
+        scene.close()
+
+
+def test_sponza_standin_config2(emu, orc, gpurt):
+    s = gpurt.Scene(None)
+    s.make_sponza_standin()
+    cam = gpurt.camera(1, 96, 54, (-1000.0, 200.0, 0.0), (0.0, 200.0, 0.0), 90.0)
+    _run(emu, orc, gpurt, s, 96, 54, 2, cam=cam, integrator=1, brdf=1, samples_per_frame=1, max_depth=2, use_rr=0,
+         env_scale=1.0, seed=3)

@@ -50,6 +50,13 @@ struct gpurt_pipe {
     uint32_t max_counts = 0;
     uint32_t band_rows = 0, n_shards = 1, shard = 0; /* gpurt_pipe_set_shard; 0 = whole frame */
     uint32_t wave_depth = 0;                          /* bounces run as wavefronts before k_tail; 0 = by size */
+    /* light groups for light_pdf (shade.cuh light_run_box), rebuilt when the accel's triangles change */
+    float4* lgrp = nullptr;
+    uint2* lgrp_off = nullptr;
+    size_t lgrp_cap = 0, lgrp_off_cap = 0;
+    uint64_t lgrp_version = ~0ull;
+    const float4* lgrp_tris = nullptr;
+    bool use_lgrp = true;                             /* GPURT_LIGHT_GROUPS=0: every light triangle, like the GLSL */
 };
 
 namespace gpurt {
@@ -62,6 +69,16 @@ __global__ void __launch_bounds__(256) k_frame_begin(const __grid_constant__ Fra
     uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
     if(li >= P.n_local) return;
     pixel_begin(P, restir, shard_pixel(P, li), acc, pathB, gpos, gnorm, galb, res_out);
+}
+
+/* padded boxes over runs of 8 / 64 consecutive triangles of every light (blockIdx.y = light) */
+__global__ void __launch_bounds__(128) k_light_groups(const float4* __restrict__ tri_world, const uint32_t* __restrict__ tri_off,
+                                                      const SceneLight* __restrict__ lights, const uint2* __restrict__ off,
+                                                      float pad, float4* __restrict__ out) {
+    const uint32_t l = blockIdx.y, r = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n_tris = lights[l].n_triangles;
+    if(r >= light_box_records(n_tris)) return;
+    light_box_record(tri_world + 3ull * tri_off[lights[l].index], n_tris, r, pad, out + 2ull * (off[l].x + r));
 }
 
 __global__ void __launch_bounds__(256) k_gen_camera(const __grid_constant__ FrameParams P, uint32_t s,
@@ -217,7 +234,7 @@ __global__ void __launch_bounds__(256) k_tonemap(const float4* __restrict__ img,
 static int pipe_free(gpurt_pipe* p) {
     void* ptrs[] = {p->image, p->res[0], p->res[1], p->gbuf[0][0], p->gbuf[0][1], p->gbuf[0][2], p->gbuf[1][0],
                     p->gbuf[1][1], p->gbuf[1][2], p->acc, p->pathA, p->pathB, p->rays[0], p->rays[1], p->hits,
-                    p->queue[0], p->queue[1], p->counts, p->ray_counts};
+                    p->queue[0], p->queue[1], p->counts, p->ray_counts, p->lgrp, p->lgrp_off};
     for(void* q : ptrs)
         if(q) cudaFree(q);
     return GPURT_OK;
@@ -262,6 +279,43 @@ static int pipe_resize(gpurt_pipe* p, uint32_t w, uint32_t h, uint32_t max_depth
     return GPURT_OK;
 }
 
+/* (re)build the light groups when the accel's world-space triangles changed (build / update) */
+static int pipe_light_groups(gpurt_pipe* p) {
+    const gpurt_accel* A = p->accel;
+    const std::vector<SceneLight>& L = p->scene->packed.lights;
+    if(!p->use_lgrp || L.empty() || !A->tri_gid || L.size() != A->dscene.n_lights) {
+        p->lgrp_tris = nullptr;
+        return GPURT_OK;
+    }
+    if(p->lgrp_tris == A->tri_gid && p->lgrp_version == A->dscene.version) return GPURT_OK;
+    cudaStream_t st = p->ctx->stream;
+    std::vector<uint2> off(L.size());
+    uint32_t total = 0, most = 0;
+    for(size_t l = 0; l < L.size(); l++) {
+        uint32_t ng = (L[l].n_triangles + kLightRun - 1) / kLightRun, nsg = (ng + kLightRun - 1) / kLightRun;
+        off[l] = make_uint2(total, total + nsg);
+        total += nsg + ng;
+        most = std::max(most, nsg + ng);
+    }
+    if(p->lgrp_cap < total || p->lgrp_off_cap < L.size()) {
+        GPURT_CUDA(cudaStreamSynchronize(st));
+        if(p->lgrp) cudaFree(p->lgrp);
+        if(p->lgrp_off) cudaFree(p->lgrp_off);
+        p->lgrp = nullptr, p->lgrp_off = nullptr, p->lgrp_cap = p->lgrp_off_cap = 0;
+        GPURT_CUDA(cudaMalloc((void**)&p->lgrp, (size_t)std::max(total, 1u) * 32));
+        GPURT_CUDA(cudaMalloc((void**)&p->lgrp_off, L.size() * sizeof(uint2)));
+        p->lgrp_cap = total, p->lgrp_off_cap = L.size();
+    }
+    /* pageable source: the copy is staged before the call returns, so `off` may go out of scope */
+    GPURT_CUDA(cudaMemcpyAsync(p->lgrp_off, off.data(), L.size() * sizeof(uint2), cudaMemcpyHostToDevice, st));
+    if(most)
+        k_light_groups<<<dim3(cdivu(most, 128), (unsigned)L.size()), 128, 0, st>>>(
+            A->tri_gid, A->dscene.tri_off, A->dscene.lights, p->lgrp_off, A->inflate * kLightPadScale, p->lgrp);
+    GPURT_CUDA(cudaGetLastError());
+    p->lgrp_tris = A->tri_gid, p->lgrp_version = A->dscene.version;
+    return GPURT_OK;
+}
+
 static void upload_lut_once() {
     static bool done = false;
     if(done) return;
@@ -288,6 +342,7 @@ int gpurt_pipe_create(gpurt_scene* scene, gpurt_accel* accel, gpurt_pipe** out) 
     GPURT_CUDA(cudaSetDevice(p->ctx->device));
     upload_lut_once();
     if(const char* e = getenv("GPURT_WAVE_DEPTH")) p->wave_depth = (uint32_t)std::max(1, atoi(e)); /* tuning knob */
+    if(const char* e = getenv("GPURT_LIGHT_GROUPS")) p->use_lgrp = atoi(e) != 0;                   /* A/B knob */
     *out = p;
     return GPURT_OK;
 }
@@ -381,6 +436,8 @@ static int render_core(gpurt_pipe* p, const GpurtPipeParams* prm, const GpurtCam
     X.S = p->accel->dscene;
     X.nodes = (const float4*)p->accel->nodes, X.tris = p->accel->tri_wide, X.n_nodes = p->accel->n_nodes;
     X.tri_world = p->accel->tri_gid;
+    if((rc = pipe_light_groups(p))) return rc;
+    X.lgrp = p->lgrp_tris ? p->lgrp : nullptr, X.lgrp_off = p->lgrp_off;
     X.prev_res = p->res[prev], X.ppos = p->gbuf[prev][0], X.pnorm = p->gbuf[prev][1], X.palb = p->gbuf[prev][2];
     X.ray_counts = p->ray_counts;
 

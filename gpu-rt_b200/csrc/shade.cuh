@@ -133,6 +133,55 @@ struct LightSample {
 
 SH_CONST float c_srgb_lut[256];
 
+/* ---- light groups: an implicit two-level hierarchy over each light's triangles in index order ----------------
+ * light_pdf (rt.rgen:222-255) sums triangle_pdf over EVERY triangle of every light whose box the ray hits; all but
+ * the one or two triangles the ray actually crosses contribute +0.  The boxes below let it skip runs of 8 / 64
+ * triangles the ray cannot touch.  The tests that remain run in the same ascending order and x + 0 == x for the
+ * non-negative partial sums, so the result has the same bits as the full loop.  The boxes only have to be
+ * conservative for the fp32 triangle test: they are padded by 2^-12 of the largest scene coordinate (128 x the BVH's
+ * own N7 margin; the rounding of (lo - o) * (1/d) over a scene-sized distance is ~2^-21 of it). */
+constexpr uint32_t kLightRun = 8;
+constexpr float kLightPadScale = 128.0f; /* x accel inflation (= 2^-19 max|coord|) */
+
+SH_D void light_run_box(const float4* tp, uint32_t count, float pad, float4& lo, float4& hi) {
+    const float inf = GPURT_INF;
+    F3 a = F3{inf, inf, inf}, b = F3{-inf, -inf, -inf};
+    for(uint32_t t = 0; t < count; t++, tp += 3) {
+        float4 r0 = tp[0], r1 = tp[1], r2 = tp[2];
+        F3 p0 = F3{r0.x, r0.y, r0.z}, p1 = p0 + F3{r1.x, r1.y, r1.z}, p2 = p0 + F3{r2.x, r2.y, r2.z};
+        a = F3{fminf(a.x, fminf(p0.x, fminf(p1.x, p2.x))), fminf(a.y, fminf(p0.y, fminf(p1.y, p2.y))),
+               fminf(a.z, fminf(p0.z, fminf(p1.z, p2.z)))};
+        b = F3{fmaxf(b.x, fmaxf(p0.x, fmaxf(p1.x, p2.x))), fmaxf(b.y, fmaxf(p0.y, fmaxf(p1.y, p2.y))),
+               fmaxf(b.z, fmaxf(p0.z, fmaxf(p1.z, p2.z)))};
+    }
+    lo = make_float4(a.x - pad, a.y - pad, a.z - pad, 0.0f);
+    hi = make_float4(b.x + pad, b.y + pad, b.z + pad, 0.0f);
+}
+/* box r of one light: r < n_runs64 -> triangles [64 r, 64 r + 64), else run g = r - n_runs64 -> [8 g, 8 g + 8) */
+SH_D void light_box_record(const float4* light_tris, uint32_t n_tris, uint32_t r, float pad, float4* out2) {
+    uint32_t ng = (n_tris + kLightRun - 1) / kLightRun, nsg = (ng + kLightRun - 1) / kLightRun;
+    uint32_t span = r < nsg ? kLightRun * kLightRun : kLightRun, first = r < nsg ? r * span : (r - nsg) * span;
+    uint32_t count = n_tris - first < span ? n_tris - first : span;
+    light_run_box(light_tris + 3ull * first, count, pad, out2[0], out2[1]);
+}
+SH_D uint32_t light_box_records(uint32_t n_tris) {
+    uint32_t ng = (n_tris + kLightRun - 1) / kLightRun;
+    return ng + (ng + kLightRun - 1) / kLightRun;
+}
+/* does the ray o + t d, t >= 0, touch the (padded) box?  axes the ray is parallel to are decided by the origin */
+SH_D bool ray_touches_box(F3 o, F3 d, F3 inv, float4 lo, float4 hi) {
+    const float inf = GPURT_INF;
+    bool px = fabsf(d.x) < 1e-20f, py = fabsf(d.y) < 1e-20f, pz = fabsf(d.z) < 1e-20f;
+    float ax = px ? -inf : (lo.x - o.x) * inv.x, bx = px ? inf : (hi.x - o.x) * inv.x;
+    float ay = py ? -inf : (lo.y - o.y) * inv.y, by = py ? inf : (hi.y - o.y) * inv.y;
+    float az = pz ? -inf : (lo.z - o.z) * inv.z, bz = pz ? inf : (hi.z - o.z) * inv.z;
+    float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f));
+    float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
+    bool inside = (!px || (o.x >= lo.x && o.x <= hi.x)) && (!py || (o.y >= lo.y && o.y <= hi.y)) &&
+                  (!pz || (o.z >= lo.z && o.z <= hi.z));
+    return inside && tn <= tf;
+}
+
 /* everything a shading thread can see */
 struct ShadeCtx {
     DeviceScene S;
@@ -140,6 +189,11 @@ struct ShadeCtx {
     const float4* tris;
     const float4* tri_world; /* world-space triangles in global primitive order: v0 | e1 = v1-v0 | e2 = v2-v0 (k_flatten, N1) */
     unsigned n_nodes;
+    /* light groups (render.cu k_light_groups): padded boxes over runs of 8 and 64 consecutive triangles of every
+     * light, 2 float4 (lo, hi) per box; lgrp_off[l] = {first 64-run box, first 8-run box} of light l.  NULL: light_pdf
+     * tests every triangle like the GLSL */
+    const float4* lgrp;
+    const uint2* lgrp_off;
     const float4* prev_res;  /* previous frame reservoirs */
     const float4* ppos;      /* previous frame G-buffers */
     const float4* pnorm;
@@ -504,6 +558,7 @@ struct Shader {
     SH_D float light_pdf(F3 p, F3 d) const {
         if(P.c.n_lights <= 0) return 0;
         float oacc = 0;
+        const F3 inv = f3s(1.0f) / d;
         for(uint32_t l = 0; l < (uint32_t)P.c.n_lights; l++) {
             float tacc = 0;
             const SceneLight& L = X.S.lights[l];
@@ -512,10 +567,28 @@ struct Shader {
             /* the GLSL re-fetches 3 indices + 3 vertices and re-transforms them for every triangle of every call; the
              * build already holds the same world-space triangles, contiguous per object */
             const float4* tp = X.tri_world + 3ull * X.S.tri_off[o_idx];
-            for(uint32_t t = 0; t < n_tris; t++, tp += 3) {
-                float4 r0 = GPURT_LDG(tp), r1 = GPURT_LDG(tp + 1), r2 = GPURT_LDG(tp + 2);
-                tacc += triangle_pdf_flat(p, d, F3{r0.x, r0.y, r0.z}, F3{r1.x, r1.y, r1.z}, F3{r2.x, r2.y, r2.z});
-            }
+            if(X.lgrp) { /* same sum, skipping the runs of triangles whose box the ray misses (see light_run_box) */
+                const uint2 off = X.lgrp_off[l];
+                const float4 *b64 = X.lgrp + 2ull * off.x, *b8 = X.lgrp + 2ull * off.y;
+                const uint32_t ng = (n_tris + kLightRun - 1) / kLightRun, nsg = (ng + kLightRun - 1) / kLightRun;
+                for(uint32_t sg = 0; sg < nsg; sg++) {
+                    if(!ray_touches_box(p, d, inv, GPURT_LDG(b64 + 2 * sg), GPURT_LDG(b64 + 2 * sg + 1))) continue;
+                    const uint32_t g1 = sg * kLightRun + kLightRun < ng ? sg * kLightRun + kLightRun : ng;
+                    for(uint32_t g = sg * kLightRun; g < g1; g++) {
+                        if(!ray_touches_box(p, d, inv, GPURT_LDG(b8 + 2 * g), GPURT_LDG(b8 + 2 * g + 1))) continue;
+                        const uint32_t t1 = g * kLightRun + kLightRun < n_tris ? g * kLightRun + kLightRun : n_tris;
+                        const float4* q = tp + 3ull * g * kLightRun;
+                        for(uint32_t t = g * kLightRun; t < t1; t++, q += 3) {
+                            float4 r0 = GPURT_LDG(q), r1 = GPURT_LDG(q + 1), r2 = GPURT_LDG(q + 2);
+                            tacc += triangle_pdf_flat(p, d, F3{r0.x, r0.y, r0.z}, F3{r1.x, r1.y, r1.z}, F3{r2.x, r2.y, r2.z});
+                        }
+                    }
+                }
+            } else
+                for(uint32_t t = 0; t < n_tris; t++, tp += 3) {
+                    float4 r0 = GPURT_LDG(tp), r1 = GPURT_LDG(tp + 1), r2 = GPURT_LDG(tp + 2);
+                    tacc += triangle_pdf_flat(p, d, F3{r0.x, r0.y, r0.z}, F3{r1.x, r1.y, r1.z}, F3{r2.x, r2.y, r2.z});
+                }
             oacc += tacc / (float)n_tris;
         }
         return oacc / (float)P.c.n_lights;

@@ -19,6 +19,7 @@ struct Emu {
     std::vector<float4> tri_wide;
     std::vector<float4> tri_gid; /* world-space triangles in global primitive order (k_flatten's output) */
     unsigned depth = 0;
+    float inflate = 0;
 };
 
 static void fill_ranges(const int* left, const int* right, int node, std::vector<int>& rf, std::vector<int>& rl) {
@@ -81,6 +82,7 @@ void* emu_build(const float* tris9, unsigned n, const unsigned* order, const int
     }
     E->tri_wide.resize(3ull * n);
     E->tri_gid = tri_gid;
+    E->inflate = inflate;
     if(n == 0) return E;
     if(n <= (unsigned)kMaxLeafTris) {
         int ch[8];
@@ -194,6 +196,32 @@ struct EmuFrameArgs {
     uint32_t n_objs, n_lights, n_tex;
 };
 
+/* pipe_light_groups() + k_light_groups of render.cu */
+static int g_light_groups = 1;
+static void build_light_groups(const Emu* E, const EmuFrameArgs* A, std::vector<float4>& boxes, std::vector<uint2>& off) {
+    const SceneLight* L = (const SceneLight*)A->lights;
+    off.resize(A->n_lights);
+    uint32_t total = 0;
+    for(uint32_t l = 0; l < A->n_lights; l++) {
+        uint32_t ng = (L[l].n_triangles + kLightRun - 1) / kLightRun, nsg = (ng + kLightRun - 1) / kLightRun;
+        off[l] = uint2{total, total + nsg};
+        total += nsg + ng;
+    }
+    boxes.resize(2ull * total);
+    for(uint32_t l = 0; l < A->n_lights; l++)
+        for(uint32_t r = 0; r < light_box_records(L[l].n_triangles); r++)
+            light_box_record(E->tri_gid.data() + 3ull * A->tri_off[L[l].index], L[l].n_triangles, r, E->inflate * kLightPadScale,
+                             boxes.data() + 2ull * (off[l].x + r));
+}
+static void fill_ctx(const Emu* E, const EmuFrameArgs* A, ShadeCtx& X) {
+    X.S.verts = (Vertex*)A->verts, X.S.idx = (uint32_t*)A->idx, X.S.tri_off = (uint32_t*)A->tri_off;
+    X.S.vert_off = (uint32_t*)A->vert_off, X.S.descs = (SceneDesc*)A->descs, X.S.lights = (SceneLight*)A->lights;
+    X.S.n_objs = A->n_objs, X.S.n_lights = A->n_lights, X.S.n_tris = A->tri_off[A->n_objs];
+    X.S.texels = (uint8_t*)A->texels, X.S.tex_info = (uint4*)A->tex_info, X.S.n_textures = A->n_tex;
+    X.nodes = (const float4*)E->nodes.data(), X.tris = E->tri_wide.data(), X.tri_world = E->tri_gid.data();
+    X.n_nodes = (unsigned)E->nodes.size();
+}
+
 template <int I>
 static void render_rows(const FrameParams& P, const ShadeCtx& X, uint32_t i0, uint32_t i1, float4* image, float4* res_cur,
                         float4* gpos, float4* gnorm, float4* galb, float4* acc, float4* pathA, float4* pathB,
@@ -216,6 +244,29 @@ static void render_rows(const FrameParams& P, const ShadeCtx& X, uint32_t i0, ui
 }
 
 extern "C" {
+void emu_set_light_groups(int on) { g_light_groups = on; }
+
+/* light_pdf(p, d) for n rays (6 floats each): with the light groups and testing every triangle, out2[2 i], out2[2 i + 1] */
+void emu_light_pdf(void* bvh, const EmuFrameArgs* A, const float* rays6, unsigned long long n, float* out2) {
+    Emu* E = (Emu*)bvh;
+    FrameParams P;
+    std::memset(&P, 0, sizeof(P));
+    P.c.n_lights = (int)A->n_lights, P.c.n_objs = (int)A->n_objs;
+    ShadeCtx X{};
+    fill_ctx(E, A, X);
+    std::vector<float4> lboxes;
+    std::vector<uint2> loff;
+    build_light_groups(E, A, lboxes, loff);
+    for(int mode = 0; mode < 2; mode++) {
+        X.lgrp = mode == 0 ? lboxes.data() : nullptr, X.lgrp_off = loff.data();
+        Shader sh(X, P);
+        for(unsigned long long i = 0; i < n; i++) {
+            const float* r = rays6 + 6 * i;
+            out2[2 * i + mode] = sh.light_pdf(F3{r[0], r[1], r[2]}, F3{r[3], r[4], r[5]});
+        }
+    }
+}
+
 void emu_render_frame(void* bvh, const EmuFrameArgs* A, const uint32_t* consts, const uint32_t* camera, uint32_t w, uint32_t h,
                       uint32_t seed_val, float* image, const uint32_t* prev_res, uint32_t* out_res, const float* ppos,
                       const float* pnorm, const float* palb, float* pos, float* norm, float* alb,
@@ -236,12 +287,13 @@ void emu_render_frame(void* bvh, const EmuFrameArgs* A, const uint32_t* consts, 
     P.W = w, P.H = h, P.seed_val = seed_val;
     P.band_rows = h, P.n_shards = 1, P.shard = 0, P.n_local = w * h;
     ShadeCtx X{};
-    X.S.verts = (Vertex*)A->verts, X.S.idx = (uint32_t*)A->idx, X.S.tri_off = (uint32_t*)A->tri_off;
-    X.S.vert_off = (uint32_t*)A->vert_off, X.S.descs = (SceneDesc*)A->descs, X.S.lights = (SceneLight*)A->lights;
-    X.S.n_objs = A->n_objs, X.S.n_lights = A->n_lights, X.S.n_tris = A->tri_off[A->n_objs];
-    X.S.texels = (uint8_t*)A->texels, X.S.tex_info = (uint4*)A->tex_info, X.S.n_textures = A->n_tex;
-    X.nodes = (const float4*)E->nodes.data(), X.tris = E->tri_wide.data(), X.tri_world = E->tri_gid.data();
-    X.n_nodes = (unsigned)E->nodes.size();
+    fill_ctx(E, A, X);
+    std::vector<float4> lboxes;
+    std::vector<uint2> loff;
+    if(g_light_groups && A->n_lights) {
+        build_light_groups(E, A, lboxes, loff);
+        X.lgrp = lboxes.data(), X.lgrp_off = loff.data();
+    }
     X.prev_res = (const float4*)prev_res, X.ppos = (const float4*)ppos, X.pnorm = (const float4*)pnorm, X.palb = (const float4*)palb;
     const uint32_t n = w * h;
     std::vector<float4> acc(n), pathA(n), pathB(n);

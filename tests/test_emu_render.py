@@ -143,3 +143,89 @@ def test_sponza_standin_config2(emu, orc, gpurt):
     cam = gpurt.camera(1, 96, 54, (-1000.0, 200.0, 0.0), (0.0, 200.0, 0.0), 90.0)
     _run(emu, orc, gpurt, s, 96, 54, 2, cam=cam, integrator=1, brdf=1, samples_per_frame=1, max_depth=2, use_rr=0,
          env_scale=1.0, seed=3)
+
+
+def _light_rays(rs, rng, n):
+    """rays that stress light_pdf: towards points on light triangles (most hit), from light surfaces, axis-parallel,
+    grazing, random"""
+    lights = rs.lights.reshape(-1, 12)
+    tris = []
+    for l in lights:
+        obj, nt = int(l[8]), int(l[9])
+        t0 = int(rs.tri_off[obj])
+        tris.append(rs.tris[t0:t0 + nt])
+    tris = np.concatenate(tris).reshape(-1, 3, 3)
+    box = rs.bvh.scene_box()
+    lo, hi = box[:3], box[3:]
+    o = (lo + (hi - lo) * rng.random((n, 3), dtype=np.float32)).astype(np.float32)
+    pick = tris[rng.integers(0, len(tris), n)]
+    b = rng.random((n, 3), dtype=np.float32)
+    kind = rng.integers(0, 8, n)
+    b[kind == 1] = [1, 0, 0]                      # exactly at a vertex
+    b[kind == 2, 2] = 0                           # on an edge
+    b /= b.sum(axis=1, keepdims=True)
+    target = (pick * b[:, :, None]).sum(axis=1).astype(np.float32)
+    d = target - o
+    on_light = kind == 3                          # origin on a light triangle, random direction
+    o[on_light] = target[on_light]
+    d[on_light] = rng.standard_normal((int(on_light.sum()), 3)).astype(np.float32)
+    rnd = kind == 4
+    d[rnd] = rng.standard_normal((int(rnd.sum()), 3)).astype(np.float32)
+    ax = kind == 5                                # axis-parallel through the target
+    k = rng.integers(0, 3, n)
+    for a in range(3):
+        m = ax & (k == a)
+        o[m] = target[m]
+        o[m, a] = lo[a] - 0.1 * (hi[a] - lo[a])
+        d[m] = 0
+        d[m, a] = 1
+    d /= np.maximum(np.linalg.norm(d, axis=1, keepdims=True), 1e-30).astype(np.float32)
+    return np.concatenate([o, d.astype(np.float32)], axis=1).astype(np.float32)
+
+
+def _sliver_light_scene(gpurt, scale, seed):
+    """emissive meshes with slivers, tiny and huge triangles at a Sponza-like coordinate scale"""
+    rng = np.random.default_rng(seed)
+    s = gpurt.Scene(None)
+    e = gpurt.Material()
+    e.albedo[:] = (1, 1, 1)
+    e.emissive[:] = (3, 3, 3)
+    e.albedo_tex = e.emissive_tex = e.metal_rough_tex = e.normal_tex = -1
+    e.metal_rough[:] = (0, 1)
+    for n_tris in (1, 7, 8, 9, 63, 64, 65, 130, 700):
+        c = (rng.random(3) * scale).astype(np.float32)
+        tris = c + (rng.random((n_tris, 3, 3)) - 0.5) * scale * 0.05
+        thin = rng.random(n_tris) < 0.4           # slivers: third vertex almost on the first edge
+        w = rng.random(n_tris)[:, None]
+        tris[thin, 2] = tris[thin, 0] * (1 - w[thin]) + tris[thin, 1] * w[thin] + (rng.random((int(thin.sum()), 3)) - 0.5) * scale * 1e-5
+        tiny = rng.random(n_tris) < 0.1
+        tris[tiny] = tris[tiny, :1] + (tris[tiny] - tris[tiny, :1]) * 1e-3
+        s.add_triangles(tris.reshape(-1, 9).astype(np.float32), e)
+    d = gpurt.Material()
+    d.albedo[:] = (0.5, 0.5, 0.5)
+    d.albedo_tex = d.emissive_tex = d.metal_rough_tex = d.normal_tex = -1
+    d.metal_rough[:] = (0, 0.5)
+    floor = np.array([[0, 0, 0, 1, 0, 0, 0, 0, 1], [1, 0, 0, 1, 0, 1, 0, 0, 1]], np.float32) * scale
+    s.add_triangles(floor, d)
+    return s
+
+
+@pytest.mark.parametrize("name", ["mis_test", "cbox", "features", "slivers_1", "slivers_2000"])
+def test_light_groups_do_not_change_light_pdf(emu, orc, gpurt, name):
+    """light_pdf through the light-run boxes == light_pdf over every triangle, bit for bit"""
+    if name.startswith("slivers"):
+        s = _sliver_light_scene(gpurt, float(name.split("_")[1]), 11)
+    elif name == "features":
+        s = gpurt.Scene(None).load(os.path.join(ROOT, "tests", "data", "synth", "features.gltf"))
+    else:
+        s = gpurt.Scene(None).load(os.path.join(MEDIA, name, name + ".gltf"))
+    es = EmuScene(emu, orc, s)
+    assert es.rs.n_lights > 0
+    n = 300000
+    rays = _light_rays(es.rs, np.random.default_rng(3), n)
+    out = np.zeros((n, 2), np.float32)
+    emu.emu_light_pdf(es.h, C.byref(es.args), _vp(rays), C.c_ulonglong(n), _vp(out))
+    a, b = out[:, 0].view(np.uint32), out[:, 1].view(np.uint32)
+    assert (a == b).all(), f"{(a != b).sum()} of {n} light_pdf values differ"
+    assert (out[:, 1] > 0).mean() > 0.2
+    es.close()

@@ -99,21 +99,28 @@ static int run_query(gpurt_ctx* ctx, const void* in, size_t in_stride, void* out
     GPURT_CUDA(cudaEventRecord(ctx->ev0, st));
     GPURT_CUDA(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev0, 0)); /* staging buffers may still be in use on st */
     GPURT_CUDA(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev0, 0));
-    for(uint64_t off = 0; off < n; off += chunk) {
-        uint64_t cnt = std::min<uint64_t>(chunk, n - off);
-        char* di = (char*)ctx->d_in.p + off * in_stride;
-        char* dout = (char*)ctx->d_out.p + off * out_stride;
-        GPURT_CUDA(cudaMemcpyAsync(di, (const char*)in + off * in_stride, cnt * in_stride, cudaMemcpyHostToDevice, ctx->s_h2d));
-        GPURT_CUDA(cudaEventRecord(ctx->ev_copy, ctx->s_h2d));
-        GPURT_CUDA(cudaStreamWaitEvent(st, ctx->ev_copy, 0));
-        if((rc = launch(di, dout, cnt))) return rc;
-        GPURT_CUDA(cudaEventRecord(ctx->ev_kernel, st));
-        GPURT_CUDA(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_kernel, 0));
-        GPURT_CUDA(cudaMemcpyAsync((char*)out + off * out_stride, dout, cnt * out_stride, cudaMemcpyDeviceToHost, ctx->s_d2h));
-    }
-    GPURT_CUDA(cudaEventRecord(ctx->ev1, st));
-    GPURT_CUDA(cudaStreamSynchronize(ctx->s_d2h));
-    GPURT_CUDA(cudaStreamSynchronize(st));
+    /* after the first copy is queued the caller's buffers are in flight: every exit drains the three streams */
+    auto body = [&]() -> int {
+        for(uint64_t off = 0; off < n; off += chunk) {
+            uint64_t cnt = std::min<uint64_t>(chunk, n - off);
+            char* di = (char*)ctx->d_in.p + off * in_stride;
+            char* dout = (char*)ctx->d_out.p + off * out_stride;
+            GPURT_CUDA(cudaMemcpyAsync(di, (const char*)in + off * in_stride, cnt * in_stride, cudaMemcpyHostToDevice, ctx->s_h2d));
+            GPURT_CUDA(cudaEventRecord(ctx->ev_copy, ctx->s_h2d));
+            GPURT_CUDA(cudaStreamWaitEvent(st, ctx->ev_copy, 0));
+            if(int lrc = launch(di, dout, cnt)) return lrc;
+            GPURT_CUDA(cudaEventRecord(ctx->ev_kernel, st));
+            GPURT_CUDA(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_kernel, 0));
+            GPURT_CUDA(cudaMemcpyAsync((char*)out + off * out_stride, dout, cnt * out_stride, cudaMemcpyDeviceToHost, ctx->s_d2h));
+        }
+        GPURT_CUDA(cudaEventRecord(ctx->ev1, st));
+        return GPURT_OK;
+    };
+    rc = body();
+    cudaError_t e0 = cudaStreamSynchronize(ctx->s_h2d), e1 = cudaStreamSynchronize(st), e2 = cudaStreamSynchronize(ctx->s_d2h);
+    if(rc) return rc;
+    for(cudaError_t e : {e0, e1, e2})
+        if(e != cudaSuccess) return set_error(std::string("host-buffer query: ") + cudaGetErrorString(e)), GPURT_E_CUDA;
     return GPURT_OK;
 }
 
@@ -144,25 +151,31 @@ int gpurt_ctx_create(int device, gpurt_ctx** out) {
             cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
         }
     }
-    GPURT_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    cudaError_t e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
     c->stream = c->own_stream;
-    GPURT_CUDA(cudaEventCreate(&c->ev0));
-    GPURT_CUDA(cudaEventCreate(&c->ev1));
-    GPURT_CUDA(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
-    GPURT_CUDA(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
-    GPURT_CUDA(cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming));
-    GPURT_CUDA(cudaEventCreateWithFlags(&c->ev_kernel, cudaEventDisableTiming));
+    if(e == cudaSuccess) e = cudaEventCreate(&c->ev0);
+    if(e == cudaSuccess) e = cudaEventCreate(&c->ev1);
+    if(e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking);
+    if(e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking);
+    if(e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming);
+    if(e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_kernel, cudaEventDisableTiming);
+    if(e != cudaSuccess) { /* release whatever was created before the failure */
+        set_error(std::string("gpurt_ctx_create: ") + cudaGetErrorString(e));
+        gpurt_ctx_destroy(c);
+        return GPURT_E_CUDA;
+    }
     *out = c;
     return GPURT_OK;
 }
 int gpurt_ctx_destroy(gpurt_ctx* c) {
     if(!c) return GPURT_OK;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
+    if(c->stream) cudaStreamSynchronize(c->stream);
     c->d_in.release(), c->d_out.release(), c->scratch.release(), c->build_arena.release();
-    cudaEventDestroy(c->ev0), cudaEventDestroy(c->ev1), cudaEventDestroy(c->ev_copy), cudaEventDestroy(c->ev_kernel);
-    cudaStreamDestroy(c->s_h2d), cudaStreamDestroy(c->s_d2h);
-    cudaStreamDestroy(c->own_stream);
+    for(cudaEvent_t ev : {c->ev0, c->ev1, c->ev_copy, c->ev_kernel})
+        if(ev) cudaEventDestroy(ev);
+    for(cudaStream_t st : {c->s_h2d, c->s_d2h, c->own_stream})
+        if(st) cudaStreamDestroy(st);
     delete c;
     return GPURT_OK;
 }

@@ -236,13 +236,25 @@ def test_pose_edit_update_equals_fresh_build(gpurt, orc, ctx):
     pipe = gpurt.RTPipe(scene, accel)
     before = accel.prim_order().copy()
     n_nodes_before = accel.info().n_wide_nodes
+    cam = gpurt.camera(0, 256, 256)
+    params = gpurt.pipe_params(max_frames=1, samples_per_frame=2, max_depth=3, integrator=2, seed=5)
+    pipe.render_frame(params, cam, 256, 256)   # builds the pipe's light-run boxes for the OLD pose of the light
+    light = scene.lights()[0].index
+
+    def light_model(k):
+        m = np.array(list(scene.descs()[light].model), np.float32).reshape(4, 4).T.copy()
+        m[:3, 3] += np.float32(0.05 * k) * np.array([1, -1, 0.5], np.float32)
+        return m.T.reshape(16).copy()
+    light_models = [light_model(k) for k in (1, 2)]
     for k in (1, 2):                       # two successive edits reuse the same buffers
         scene.set_transform(3, model(k))
         scene.set_transform(7, model(k + 2))
+        scene.set_transform(light, light_models[k - 1])
         accel.update()
     fresh_scene = load_scene(gpurt, ctx, "cbox")
     fresh_scene.set_transform(3, model(2))
     fresh_scene.set_transform(7, model(4))
+    fresh_scene.set_transform(light, light_models[1])
     fresh = gpurt.Accel(fresh_scene)
     assert (accel.prim_order() == fresh.prim_order()).all() and (accel.morton_keys() == fresh.morton_keys()).all()
     assert not (accel.prim_order() == before).all() or accel.info().n_wide_nodes != n_nodes_before
@@ -255,9 +267,7 @@ def test_pose_edit_update_equals_fresh_build(gpurt, orc, ctx):
     q = orc.gen_random_points(50000, 32, ob.scene_box())
     cp, cref = accel.closest_points(q), ob.closest_point(q)
     assert same_bits(cp["dist"], cref["dist"]) and (cp["prim"] == cref["gid"]).all()
-    # the pipe created before the edit keeps working on the updated accel and matches a fresh pipe
-    cam = gpurt.camera(0, 256, 256)
-    params = gpurt.pipe_params(max_frames=1, samples_per_frame=2, max_depth=3, integrator=2, seed=5)
+    # the pipe created (and used) before the edit keeps working on the updated accel and matches a fresh pipe
     pipe.reset_frame()
     pipe.render_frame(params, cam, 256, 256)
     fresh_pipe = gpurt.RTPipe(fresh_scene, fresh)

@@ -688,7 +688,7 @@ int build_accel_device(gpurt_accel* A) {
     for(int k = 0; k < 6; k++) maxabs = fmaxf(maxabs, fabsf(sb[k]));
     /* N7, global part: 2^-19 * max|coord| (32 ulp of the largest coordinate) covers fp32 rounding of the
      * primitive tests; the node-relative part is added in encode_node (bvh8.cuh). */
-    A->inflate = fmaxf(maxabs, 1e-30f) * 1.9073486328125e-06f;
+    A->inflate = fmaxf(fmaxf(maxabs, 1e-30f) * 1.9073486328125e-06f, A->min_inflate);
     float ext[3] = {sb[3] - sb[0], sb[4] - sb[1], sb[5] - sb[2]}, inv[3];
     for(int k = 0; k < 3; k++) inv[k] = ext[k] > 0 ? 1.0f / ext[k] : 0.0f;
 

@@ -83,6 +83,7 @@ struct gpurt_accel {
     uint32_t n_nodes = 0, depth = 0;
     float scene_box[6] = {0, 0, 0, 0, 0, 0};
     float inflate = 0;
+    float min_inflate = 0; /* lower bound for `inflate` (a light BVH is queried from anywhere in the main scene) */
     float build_ms = 0;
 };
 

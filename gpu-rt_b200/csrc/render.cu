@@ -57,6 +57,11 @@ struct gpurt_pipe {
     uint64_t lgrp_version = ~0ull;
     const float4* lgrp_tris = nullptr;
     bool use_lgrp = true;                             /* GPURT_LIGHT_GROUPS=0: every light triangle, like the GLSL */
+    /* light BVH for light_pdf (shade.cuh light_pdf_bvh): a second accel over the lights' triangles only */
+    gpurt_scene* lscene = nullptr;
+    gpurt_accel* laccel = nullptr;
+    uint64_t laccel_version = ~0ull, laccel_geom = ~0ull;
+    bool use_lbvh = true;                             /* GPURT_LIGHT_BVH=0: light-run boxes only */
 };
 
 namespace gpurt {
@@ -105,7 +110,7 @@ __global__ void __launch_bounds__(128) k_trace_closest_indirect(const float4* __
 }
 
 template <int INTEG>
-__global__ void __launch_bounds__(128) k_shade(const __grid_constant__ FrameParams P,
+__global__ void __launch_bounds__(128, INTEG == 2 ? 5 : 0) k_shade(const __grid_constant__ FrameParams P,
                                                const __grid_constant__ ShadeCtx X, uint32_t s, uint32_t depth,
                                                const uint32_t* __restrict__ count_in, const uint32_t* __restrict__ queue_in,
                                                const float4* __restrict__ rays_in, const float4* __restrict__ hits,
@@ -165,7 +170,7 @@ __global__ void __launch_bounds__(128) k_shade(const __grid_constant__ FramePara
  * Here every remaining path runs its bounce loop to the end in one thread: same shade_step, same
  * traverse8, same per-pixel RNG stream, so the image does not change — only the launch count does. */
 template <int INTEG>
-__global__ void __launch_bounds__(128) k_tail(const __grid_constant__ FrameParams P, const __grid_constant__ ShadeCtx X,
+__global__ void __launch_bounds__(128, INTEG == 2 ? 5 : 0) k_tail(const __grid_constant__ FrameParams P, const __grid_constant__ ShadeCtx X,
                                               uint32_t s, uint32_t depth0, const uint32_t* __restrict__ count_in,
                                               const uint32_t* __restrict__ queue_in, const float4* __restrict__ rays_in,
                                               float4* pathA, float4* pathB, float4* acc, float4* gpos, float4* gnorm,
@@ -316,6 +321,60 @@ static int pipe_light_groups(gpurt_pipe* p) {
     return GPURT_OK;
 }
 
+static void pipe_drop_light_accel(gpurt_pipe* p) {
+    if(p->laccel) gpurt_accel_destroy(p->laccel);
+    delete p->lscene;
+    p->laccel = nullptr, p->lscene = nullptr;
+}
+
+/* (re)build the light BVH: the emissive objects of the scene, in light order, as a scene of their own (same vertices,
+ * indices and model matrices -> k_flatten produces the same world-space triangles), built by the ordinary pipeline.
+ * Its culling boxes are padded for ray origins anywhere in the MAIN scene (min_inflate). */
+static int pipe_light_accel(gpurt_pipe* p) {
+    const gpurt_accel* A = p->accel;
+    const PackedScene& M = p->scene->packed;
+    bool usable = p->use_lbvh && !M.lights.empty() && M.lights.size() == A->dscene.n_lights && A->n > 0;
+    for(const SceneLight& L : M.lights) usable = usable && L.n_triangles > 0 && L.index < M.descs.size();
+    if(!usable) { /* a light without triangles makes the GLSL's 0/0: leave that to the scan, which reproduces it */
+        pipe_drop_light_accel(p);
+        return GPURT_OK;
+    }
+    const bool same_geom = p->laccel && p->laccel_geom == A->dscene.geom_version && p->lscene->packed.descs.size() == M.lights.size();
+    if(same_geom && p->laccel_version == A->dscene.version) return GPURT_OK;
+    int rc;
+    if(!same_geom) {
+        pipe_drop_light_accel(p);
+        p->lscene = new gpurt_scene;
+        p->lscene->ctx = p->ctx;
+        p->lscene->label = "lights";
+        PackedScene& S = p->lscene->packed;
+        S.tri_off.push_back(0), S.vert_off.push_back(0);
+        for(const SceneLight& L : M.lights) {
+            const uint32_t o = L.index;
+            S.descs.push_back(M.descs[o]);
+            S.verts.insert(S.verts.end(), M.verts.begin() + M.vert_off[o], M.verts.begin() + M.vert_off[o + 1]);
+            S.idx.insert(S.idx.end(), M.idx.begin() + 3ull * M.tri_off[o], M.idx.begin() + 3ull * M.tri_off[o + 1]);
+            S.tri_off.push_back((uint32_t)(S.idx.size() / 3)), S.vert_off.push_back((uint32_t)S.verts.size());
+        }
+        p->lscene->dirty = false; /* `packed` is authoritative: there is no host Scene behind it */
+        p->lscene->version = p->lscene->geom_version = 1;
+        p->laccel = new gpurt_accel;
+        p->laccel->ctx = p->ctx, p->laccel->scene = p->lscene, p->laccel->flags = 0;
+    } else { /* pose edit: same geometry, new model matrices */
+        for(size_t l = 0; l < M.lights.size(); l++) p->lscene->packed.descs[l] = M.descs[M.lights[l].index];
+        p->lscene->version++;
+    }
+    p->laccel->min_inflate = A->inflate * kLightPadScale;
+    rc = build_accel_device(p->laccel);
+    if(rc == GPURT_OK && p->laccel->depth > 60) rc = GPURT_E_STATE;
+    if(rc) {
+        pipe_drop_light_accel(p);
+        return rc == GPURT_E_STATE ? GPURT_OK : rc; /* too deep for the stack: scan instead */
+    }
+    p->laccel_version = A->dscene.version, p->laccel_geom = A->dscene.geom_version;
+    return GPURT_OK;
+}
+
 static void upload_lut_once() {
     static bool done = false;
     if(done) return;
@@ -343,6 +402,7 @@ int gpurt_pipe_create(gpurt_scene* scene, gpurt_accel* accel, gpurt_pipe** out) 
     upload_lut_once();
     if(const char* e = getenv("GPURT_WAVE_DEPTH")) p->wave_depth = (uint32_t)std::max(1, atoi(e)); /* tuning knob */
     if(const char* e = getenv("GPURT_LIGHT_GROUPS")) p->use_lgrp = atoi(e) != 0;                   /* A/B knob */
+    if(const char* e = getenv("GPURT_LIGHT_BVH")) p->use_lbvh = atoi(e) != 0;                      /* A/B knob */
     *out = p;
     return GPURT_OK;
 }
@@ -351,6 +411,7 @@ int gpurt_pipe_destroy(gpurt_pipe* p) {
     cudaSetDevice(p->ctx->device);
     cudaStreamSynchronize(p->ctx->stream);
     pipe_free(p);
+    pipe_drop_light_accel(p);
     delete p;
     return GPURT_OK;
 }
@@ -438,6 +499,13 @@ static int render_core(gpurt_pipe* p, const GpurtPipeParams* prm, const GpurtCam
     X.tri_world = p->accel->tri_gid;
     if((rc = pipe_light_groups(p))) return rc;
     X.lgrp = p->lgrp_tris ? p->lgrp : nullptr, X.lgrp_off = p->lgrp_off;
+    X.lnodes = nullptr, X.ltris = nullptr, X.ltri_off = nullptr, X.n_lnodes = 0;
+    if(c.integrator == 2) { /* only MIS evaluates light_pdf */
+        if((rc = pipe_light_accel(p))) return rc;
+        if(p->laccel && p->laccel->n_nodes)
+            X.lnodes = (const float4*)p->laccel->nodes, X.ltris = p->laccel->tri_wide, X.ltri_off = p->laccel->dscene.tri_off,
+            X.n_lnodes = p->laccel->n_nodes;
+    }
     X.prev_res = p->res[prev], X.ppos = p->gbuf[prev][0], X.pnorm = p->gbuf[prev][1], X.palb = p->gbuf[prev][2];
     X.ray_counts = p->ray_counts;
 

@@ -19,9 +19,11 @@ namespace gpurt {
  * below on the CPU against the oracle (test-only; the product launches them from render.cu). */
 #if defined(__CUDACC__)
 #define SH_D __device__ __forceinline__
+#define SH_D_CALL __device__ __noinline__ /* large bodies with more than one call site: one copy, called */
 #define SH_CONST __constant__
 #else
 #define SH_D inline
+#define SH_D_CALL inline
 #define SH_CONST static
 inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
 #endif
@@ -194,6 +196,12 @@ struct ShadeCtx {
      * tests every triangle like the GLSL */
     const float4* lgrp;
     const uint2* lgrp_off;
+    /* light BVH (render.cu pipe_light_accel): a second wide BVH over the triangles of the lights only, primitive id =
+     * ltri_off[light] + triangle; n_lnodes == 0: light_pdf scans the light-run boxes instead */
+    const float4* lnodes;
+    const float4* ltris;
+    const uint32_t* ltri_off;
+    unsigned n_lnodes;
     const float4* prev_res;  /* previous frame reservoirs */
     const float4* ppos;      /* previous frame G-buffers */
     const float4* pnorm;
@@ -560,7 +568,7 @@ struct Shader {
      * nest: in a nest, a warp whose lanes look at different runs executes every run's triangle loop with one or two
      * live lanes (ncu r01n: 70 % of the MIS shade kernel's instructions at 2.8 of 32 lanes); here the lanes that have a
      * triangle to test all test it in the same instruction stream.  Same tests, same order, same sums per lane. */
-    SH_D float light_pdf(F3 p, F3 d) const {
+    SH_D float light_pdf_scan(F3 p, F3 d) const {
         const uint32_t n_lights = P.c.n_lights > 0 ? (uint32_t)P.c.n_lights : 0u;
         if(n_lights == 0) return 0;
         const F3 inv = f3s(1.0f) / d;
@@ -606,6 +614,88 @@ struct Shader {
             }
         }
         return oacc / (float)n_lights;
+    }
+    /* light_pdf through the light BVH.  Only the triangles the ray actually crosses contribute a non-zero term to the
+     * GLSL's sums, and index-order runs make poor boxes (64 consecutive triangles of a sphere are one latitude ring: its
+     * box is the whole disc).  So: collect every light triangle with a non-zero triangle_pdf along the ray [0, inf) with
+     * the wide-BVH traversal core — any order —, sort the handful of hits by (light, triangle) and add them the way the
+     * GLSL loop does: per light in ascending triangle order from 0, `oacc += tacc / n` only for lights whose hit_bbox
+     * test passes.  Zero terms and lights without a hit add +0 to non-negative sums, so the bits are the GLSL's.  More
+     * than kLightHits hits (a ray through a stack of lights): fall back to the scan. */
+    static constexpr int kLightHits = 8;
+    SH_D float light_pdf_bvh(F3 p, F3 d) const {
+        unsigned hg[kLightHits];
+        float hp[kLightHits];
+        int nh = 0;
+        {
+            const RaySetup rs = make_ray_setup(p, d, 0.0f);
+            const float tmax = GPURT_INF;
+            uint2 stack[kStack];
+            int sp = 0;
+            uint2 ng;
+            ng.x = 0u, ng.y = 0x80000000u;
+            for(;;) { /* traverse8's node loop without a shrinking interval */
+                if(ng.y <= 0x00ffffffu) {
+                    if(sp == 0) break;
+                    ng = stack[--sp];
+                }
+                unsigned hits = ng.y;
+                unsigned bit = 31u - gpurt_clz(hits);
+                ng.y &= ~(1u << bit);
+                if(ng.y > 0x00ffffffu) stack[sp++] = ng;
+                unsigned slot = (bit - 24u) ^ rs.octinv;
+                unsigned rel = gpurt_popc(hits & 0xffu & ((1u << slot) - 1u));
+                const float4* np = X.lnodes + (size_t)(ng.x + rel) * kNodeVec4;
+                Node8 node;
+#pragma unroll
+                for(int k = 0; k < 5; k++) node.v[k] = GPURT_LDG(np + k);
+                unsigned hit8 = node_hits8(node, rs, tmax);
+                unsigned imask = f2u(node.v[0].w) >> 24;
+                ng.x = f2u(node.v[1].x);
+                ng.y = (octant_permute8(hit8 & imask, rs.octinv) << 24) | imask;
+                unsigned leaf = hit8 & ~imask;
+                const float4* tp = X.ltris + (size_t)f2u(node.v[1].y) * kTriVec4;
+                unsigned m_lo = f2u(node.v[1].z), m_hi = f2u(node.v[1].w);
+                while(leaf) {
+                    unsigned ls = gpurt_ctz(leaf);
+                    leaf &= leaf - 1u;
+                    unsigned meta = ((ls & 4u ? m_hi : m_lo) >> (8u * (ls & 3u))) & 0xffu;
+                    unsigned k = meta & 31u, kend = k + gpurt_popc(meta >> 5);
+                    for(; k < kend; k++) {
+                        float4 r0 = GPURT_LDG(tp + 3 * k), r1 = GPURT_LDG(tp + 3 * k + 1), r2 = GPURT_LDG(tp + 3 * k + 2);
+                        float pdf = triangle_pdf_flat(p, d, F3{r0.x, r0.y, r0.z}, F3{r1.x, r1.y, r1.z}, F3{r2.x, r2.y, r2.z});
+                        if(pdf != 0) {
+                            if(nh == kLightHits) return light_pdf_scan(p, d);
+                            unsigned gid = f2u(r0.w);
+                            int i = nh++;
+                            for(; i > 0 && hg[i - 1] > gid; i--) hg[i] = hg[i - 1], hp[i] = hp[i - 1];
+                            hg[i] = gid, hp[i] = pdf;
+                        }
+                    }
+                }
+            }
+        }
+        float oacc = 0;
+        uint32_t l = 0;
+        for(int i = 0; i < nh;) {
+            while(X.ltri_off[l + 1] <= hg[i]) l++;
+            const SceneLight& L = X.S.lights[l];
+            const uint32_t end = X.ltri_off[l + 1];
+            float tacc = 0;
+            for(; i < nh && hg[i] < end; i++) tacc += hp[i];
+            if(hit_bbox(p, d, F3{L.bmin[0], L.bmin[1], L.bmin[2]}, F3{L.bmax[0], L.bmax[1], L.bmax[2]}))
+                oacc += tacc / (float)L.n_triangles;
+        }
+        return oacc / (float)P.c.n_lights;
+    }
+#if defined(GPURT_LIGHT_PDF_INLINE) /* A/B build: both call sites of integrate_mis get their own copy */
+    SH_D
+#else
+    SH_D_CALL
+#endif
+    float light_pdf(F3 p, F3 d) const {
+        if(P.c.n_lights <= 0) return 0;
+        return X.n_lnodes ? light_pdf_bvh(p, d) : light_pdf_scan(p, d);
     }
     /* rt.rgen:293-301 */
     SH_D F3 direct_light(F3 o, F3 d) {

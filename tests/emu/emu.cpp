@@ -194,10 +194,13 @@ struct EmuFrameArgs {
     const uint32_t* tex_info;
     const uint8_t* texels;
     uint32_t n_objs, n_lights, n_tex;
+    /* light BVH (render.cu pipe_light_accel): an Emu built over the lights' triangles, and their prefix offsets */
+    void* light_bvh;
+    const uint32_t* ltri_off;
 };
 
 /* pipe_light_groups() + k_light_groups of render.cu */
-static int g_light_groups = 1;
+static int g_light_groups = 1, g_light_bvh = 1;
 static void build_light_groups(const Emu* E, const EmuFrameArgs* A, std::vector<float4>& boxes, std::vector<uint2>& off) {
     const SceneLight* L = (const SceneLight*)A->lights;
     off.resize(A->n_lights);
@@ -220,6 +223,11 @@ static void fill_ctx(const Emu* E, const EmuFrameArgs* A, ShadeCtx& X) {
     X.S.texels = (uint8_t*)A->texels, X.S.tex_info = (uint4*)A->tex_info, X.S.n_textures = A->n_tex;
     X.nodes = (const float4*)E->nodes.data(), X.tris = E->tri_wide.data(), X.tri_world = E->tri_gid.data();
     X.n_nodes = (unsigned)E->nodes.size();
+    if(g_light_bvh && A->light_bvh) {
+        const Emu* LB = (const Emu*)A->light_bvh;
+        X.lnodes = (const float4*)LB->nodes.data(), X.ltris = LB->tri_wide.data(), X.ltri_off = A->ltri_off;
+        X.n_lnodes = (unsigned)LB->nodes.size();
+    }
 }
 
 template <int I>
@@ -245,9 +253,11 @@ static void render_rows(const FrameParams& P, const ShadeCtx& X, uint32_t i0, ui
 
 extern "C" {
 void emu_set_light_groups(int on) { g_light_groups = on; }
+void emu_set_light_bvh(int on) { g_light_bvh = on; }
 
-/* light_pdf(p, d) for n rays (6 floats each): with the light groups and testing every triangle, out2[2 i], out2[2 i + 1] */
-void emu_light_pdf(void* bvh, const EmuFrameArgs* A, const float* rays6, unsigned long long n, float* out2) {
+/* light_pdf(p, d) for n rays (6 floats each): through the light-run boxes, testing every triangle, through the light
+ * BVH -> out3[3 i .. 3 i + 2] */
+void emu_light_pdf(void* bvh, const EmuFrameArgs* A, const float* rays6, unsigned long long n, float* out3) {
     Emu* E = (Emu*)bvh;
     FrameParams P;
     std::memset(&P, 0, sizeof(P));
@@ -257,12 +267,14 @@ void emu_light_pdf(void* bvh, const EmuFrameArgs* A, const float* rays6, unsigne
     std::vector<float4> lboxes;
     std::vector<uint2> loff;
     build_light_groups(E, A, lboxes, loff);
-    for(int mode = 0; mode < 2; mode++) {
-        X.lgrp = mode == 0 ? lboxes.data() : nullptr, X.lgrp_off = loff.data();
+    const unsigned n_lnodes = X.n_lnodes;
+    for(int mode = 0; mode < 3; mode++) {
+        X.lgrp = mode != 1 ? lboxes.data() : nullptr, X.lgrp_off = loff.data();
+        X.n_lnodes = mode == 2 ? n_lnodes : 0;
         Shader sh(X, P);
         for(unsigned long long i = 0; i < n; i++) {
             const float* r = rays6 + 6 * i;
-            out2[2 * i + mode] = sh.light_pdf(F3{r[0], r[1], r[2]}, F3{r[3], r[4], r[5]});
+            out3[3 * i + mode] = sh.light_pdf(F3{r[0], r[1], r[2]}, F3{r[3], r[4], r[5]});
         }
     }
 }

@@ -16,7 +16,8 @@ from conftest import MEDIA, ROOT
 class FrameArgs(C.Structure):
     _fields_ = [("descs", C.c_void_p), ("tri_off", C.c_void_p), ("vert_off", C.c_void_p), ("verts", C.c_void_p),
                 ("idx", C.c_void_p), ("lights", C.c_void_p), ("tex_info", C.c_void_p), ("texels", C.c_void_p),
-                ("n_objs", C.c_uint32), ("n_lights", C.c_uint32), ("n_tex", C.c_uint32)]
+                ("n_objs", C.c_uint32), ("n_lights", C.c_uint32), ("n_tex", C.c_uint32),
+                ("light_bvh", C.c_void_p), ("ltri_off", C.c_void_p)]
 
 
 def _vp(a):
@@ -42,9 +43,23 @@ class EmuScene:
         inflate = np.float32(max(1e-30, np.abs(b.scene_box()).max()) * 2.0 ** -19)
         self.h = C.c_void_p(emu.emu_build(_vp(rs.tris), len(rs.tris), _vp(self.order), _vp(l), _vp(r), _vp(bx),
                                           C.c_float(inflate)))
+        # light BVH: the lights' triangles in light order, built like any other scene (render.cu pipe_light_accel);
+        # its boxes are padded for ray origins anywhere in the MAIN scene: 128 x the main inflation
+        self.lh, self.ltri_off = None, np.zeros(rs.n_lights + 1, np.uint32)
+        lights = rs.lights.reshape(-1, 12)[:rs.n_lights]
+        if rs.n_lights and all(int(l[9]) > 0 for l in lights):
+            parts = [rs.tris[int(rs.tri_off[int(l[8])]):int(rs.tri_off[int(l[8])]) + int(l[9])] for l in lights]
+            self.ltris = np.ascontiguousarray(np.concatenate(parts), np.float32)
+            self.ltri_off[1:] = np.cumsum([len(q) for q in parts])
+            lb = orc.Bvh(self.ltris)
+            ll, lr, lbx = lb.bvh2()
+            self.lorder = lb.prim_order()
+            self.lh = C.c_void_p(emu.emu_build(_vp(self.ltris), len(self.ltris), _vp(self.lorder), _vp(ll), _vp(lr), _vp(lbx),
+                                               C.c_float(np.float32(inflate) * np.float32(128.0))))
+            self.lb = lb
         self.args = FrameArgs(rs.descs.ctypes.data, rs.tri_off.ctypes.data, rs.vert_off.ctypes.data, rs.verts.ctypes.data,
                               rs.idx.ctypes.data, rs.lights.ctypes.data, rs.tex_info.ctypes.data, rs.texels.ctypes.data,
-                              rs.n_objs, rs.n_lights, len(textures))
+                              rs.n_objs, rs.n_lights, len(textures), self.lh, self.ltri_off.ctypes.data)
 
     def render_frame(self, st, consts, cam, seed_val):
         cur, prev = st.parity, st.parity ^ 1
@@ -58,6 +73,8 @@ class EmuScene:
 
     def close(self):
         self.emu.emu_free(self.h)
+        if self.lh:
+            self.emu.emu_free(self.lh)
 
 
 def _uniforms(gpurt, rs, cam, frame, **kw):
@@ -212,7 +229,7 @@ def _sliver_light_scene(gpurt, scale, seed):
 
 @pytest.mark.parametrize("name", ["mis_test", "cbox", "features", "slivers_1", "slivers_2000"])
 def test_light_groups_do_not_change_light_pdf(emu, orc, gpurt, name):
-    """light_pdf through the light-run boxes == light_pdf over every triangle, bit for bit"""
+    """light_pdf through the light-run boxes and through the light BVH == light_pdf over every triangle, bit for bit"""
     if name.startswith("slivers"):
         s = _sliver_light_scene(gpurt, float(name.split("_")[1]), 11)
     elif name == "features":
@@ -223,9 +240,10 @@ def test_light_groups_do_not_change_light_pdf(emu, orc, gpurt, name):
     assert es.rs.n_lights > 0
     n = 300000
     rays = _light_rays(es.rs, np.random.default_rng(3), n)
-    out = np.zeros((n, 2), np.float32)
+    out = np.zeros((n, 3), np.float32)
     emu.emu_light_pdf(es.h, C.byref(es.args), _vp(rays), C.c_ulonglong(n), _vp(out))
-    a, b = out[:, 0].view(np.uint32), out[:, 1].view(np.uint32)
-    assert (a == b).all(), f"{(a != b).sum()} of {n} light_pdf values differ"
+    a, b, c = (out[:, k].view(np.uint32) for k in range(3))
+    assert (a == b).all(), f"{(a != b).sum()} of {n} light_pdf values differ (light-run boxes)"
+    assert es.lh and (c == b).all(), f"{(c != b).sum()} of {n} light_pdf values differ (light BVH)"
     assert (out[:, 1] > 0).mean() > 0.2
     es.close()

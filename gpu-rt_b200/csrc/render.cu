@@ -50,6 +50,12 @@ struct gpurt_pipe {
     uint32_t max_counts = 0;
     uint32_t band_rows = 0, n_shards = 1, shard = 0; /* gpurt_pipe_set_shard; 0 = whole frame */
     uint32_t wave_depth = 0;                          /* bounces run as wavefronts before k_tail; 0 = by size */
+    /* queue sizes of the previous frame, copied back without a sync and used to size this frame's launches */
+    uint32_t* h_counts = nullptr;                     /* pinned */
+    cudaEvent_t ev_counts = nullptr;
+    bool counts_pending = false;
+    std::vector<uint32_t> est_counts;
+    bool use_est = true;                              /* GPURT_WAVE_ESTIMATE=0: one thread per pixel for every launch */
     /* light groups for light_pdf (shade.cuh light_run_box), rebuilt when the accel's triangles change */
     float4* lgrp = nullptr;
     uint2* lgrp_off = nullptr;
@@ -100,13 +106,15 @@ __global__ void __launch_bounds__(128) k_trace_closest_indirect(const float4* __
                                                                 const float4* __restrict__ rays,
                                                                 const uint32_t* __restrict__ count,
                                                                 float4* __restrict__ hits, unsigned n_nodes) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if(i >= *count) return;
-    float4 a = __ldg(rays + 2ull * i), b = __ldg(rays + 2ull * i + 1);
-    HitRec h;
-    h.t = a.w, h.u = h.v = 0, h.gid = kNoHit;
-    if(n_nodes) traverse8<false, false>(nodes, tris, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), a.w, b.w, h, nullptr);
-    hits[i] = make_float4(h.gid == kNoHit ? GPURT_INF : h.t, h.u, h.v, u2f(h.gid));
+    /* grid-stride: queues after the first bounce are launched with a capped grid (see render_core) */
+    const uint32_t cnt = *count;
+    for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
+        float4 a = __ldg(rays + 2ull * i), b = __ldg(rays + 2ull * i + 1);
+        HitRec h;
+        h.t = a.w, h.u = h.v = 0, h.gid = kNoHit;
+        if(n_nodes) traverse8<false, false>(nodes, tris, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), a.w, b.w, h, nullptr);
+        hits[i] = make_float4(h.gid == kNoHit ? GPURT_INF : h.t, h.u, h.v, u2f(h.gid));
+    }
 }
 
 template <int INTEG>
@@ -117,48 +125,54 @@ __global__ void __launch_bounds__(128, INTEG == 2 ? 5 : 0) k_shade(const __grid_
                                                float4* pathA, float4* pathB, float4* acc, float4* gpos, float4* gnorm,
                                                float4* galb, float4* res_cur, uint32_t* count_out, uint32_t* queue_out,
                                                float4* rays_out) {
-    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    bool live = k < *count_in;
-    bool cont = false;
-    uint32_t pix = 0;
-    TraceInfo trace;
-    Shader sh(X, P);
-    if(live) {
-        pix = queue_in[k];
-        float4 r0 = rays_in[2ull * k], r1 = rays_in[2ull * k + 1], h = hits[k];
-        float4 A = pathA[pix], B = pathB[pix];
-        trace.o = F3{r0.x, r0.y, r0.z}, trace.d = F3{r1.x, r1.y, r1.z};
-        trace.acc = F3{A.x, A.y, A.z}, trace.mis = A.w;
-        trace.throughput = F3{B.x, B.y, B.z}, trace.depth = depth;
-        sh.seed = f2u(B.w);
-        bool broke = shade_step<INTEG>(P, sh, trace, s, depth, pix, h, gpos, gnorm, galb, res_cur);
-        cont = !broke && trace.depth + 1 < (uint32_t)P.c.max_depth;
+    /* grid-stride over the queue, one warp-aligned slice of 32 paths per iteration (the trip count is the same for the
+     * lanes of a warp, so the full-mask ballot / reduce below are safe) */
+    const uint32_t cnt = *count_in, lane = threadIdx.x & 31u;
+    unsigned nc = 0, na = 0;
+    for(uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < cnt; base += gridDim.x * blockDim.x) {
+        const uint32_t k = base + lane;
+        const bool live = k < cnt;
+        bool cont = false;
+        uint32_t pix = 0;
+        TraceInfo trace;
+        Shader sh(X, P);
+        if(live) {
+            pix = queue_in[k];
+            float4 r0 = rays_in[2ull * k], r1 = rays_in[2ull * k + 1], h = hits[k];
+            float4 A = pathA[pix], B = pathB[pix];
+            trace.o = F3{r0.x, r0.y, r0.z}, trace.d = F3{r1.x, r1.y, r1.z};
+            trace.acc = F3{A.x, A.y, A.z}, trace.mis = A.w;
+            trace.throughput = F3{B.x, B.y, B.z}, trace.depth = depth;
+            sh.seed = f2u(B.w);
+            bool broke = shade_step<INTEG>(P, sh, trace, s, depth, pix, h, gpos, gnorm, galb, res_cur);
+            cont = !broke && trace.depth + 1 < (uint32_t)P.c.max_depth;
+            if(cont) {
+                pathA[pix] = make_float4(trace.acc.x, trace.acc.y, trace.acc.z, trace.mis);
+                pathB[pix] = make_float4(trace.throughput.x, trace.throughput.y, trace.throughput.z, u2f(sh.seed));
+            } else { /* rt.rgen:630: acc += trace.acc; the RNG stream continues into the next sample */
+                float4 a = acc[pix];
+                acc[pix] = make_float4(a.x + trace.acc.x, a.y + trace.acc.y, a.z + trace.acc.z, 0.0f);
+                pathB[pix] = make_float4(1.0f, 1.0f, 1.0f, u2f(sh.seed));
+            }
+            nc += 1u + sh.n_closest, na += sh.n_any; /* this thread's wavefront ray + its inline rays */
+        }
+        /* warp-aggregated compaction of the surviving paths */
+        unsigned m = __ballot_sync(0xffffffffu, cont);
+        uint32_t slot0 = 0;
+        if(m) {
+            if(lane == (unsigned)__ffs(m) - 1) slot0 = atomicAdd(count_out, (uint32_t)__popc(m));
+            slot0 = __shfl_sync(0xffffffffu, slot0, __ffs(m) - 1);
+        }
         if(cont) {
-            pathA[pix] = make_float4(trace.acc.x, trace.acc.y, trace.acc.z, trace.mis);
-            pathB[pix] = make_float4(trace.throughput.x, trace.throughput.y, trace.throughput.z, __uint_as_float(sh.seed));
-        } else { /* rt.rgen:630: acc += trace.acc; the RNG stream continues into the next sample */
-            float4 a = acc[pix];
-            acc[pix] = make_float4(a.x + trace.acc.x, a.y + trace.acc.y, a.z + trace.acc.z, 0.0f);
-            pathB[pix] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(sh.seed));
+            uint32_t slot = slot0 + __popc(m & ((1u << lane) - 1u));
+            queue_out[slot] = pix;
+            rays_out[2ull * slot] = make_float4(trace.o.x, trace.o.y, trace.o.z, kEps);
+            rays_out[2ull * slot + 1] = make_float4(trace.d.x, trace.d.y, trace.d.z, kLargeDist);
         }
     }
-    /* warp-aggregated compaction of the surviving paths */
-    unsigned m = __ballot_sync(0xffffffffu, cont);
-    unsigned lane = threadIdx.x & 31;
-    uint32_t base = 0;
-    if(m) {
-        if(lane == (unsigned)__ffs(m) - 1) base = atomicAdd(count_out, (uint32_t)__popc(m));
-        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-    }
-    if(cont) {
-        uint32_t slot = base + __popc(m & ((1u << lane) - 1u));
-        queue_out[slot] = pix;
-        rays_out[2ull * slot] = make_float4(trace.o.x, trace.o.y, trace.o.z, kEps);
-        rays_out[2ull * slot + 1] = make_float4(trace.d.x, trace.d.y, trace.d.z, kLargeDist);
-    }
-    /* ray accounting: this thread's wavefront ray + its inline rays, one atomic per warp */
-    unsigned nc = __reduce_add_sync(0xffffffffu, live ? 1u + sh.n_closest : 0u);
-    unsigned na = __reduce_add_sync(0xffffffffu, live ? sh.n_any : 0u);
+    /* ray accounting, one atomic per warp */
+    nc = __reduce_add_sync(0xffffffffu, nc);
+    na = __reduce_add_sync(0xffffffffu, na);
     if(lane == 0) {
         if(nc) atomicAdd(X.ray_counts + 0, (unsigned long long)nc);
         if(na) atomicAdd(X.ray_counts + 1, (unsigned long long)na);
@@ -175,15 +189,16 @@ __global__ void __launch_bounds__(128, INTEG == 2 ? 5 : 0) k_tail(const __grid_c
                                               const uint32_t* __restrict__ queue_in, const float4* __restrict__ rays_in,
                                               float4* pathA, float4* pathB, float4* acc, float4* gpos, float4* gnorm,
                                               float4* galb, float4* res_cur) {
-    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    bool live = k < *count_in;
-    Shader sh(X, P);
-    unsigned n_wave = 0;
-    if(live)
-        n_wave = path_tail<INTEG>(P, X, sh, s, depth0, queue_in[k], rays_in[2ull * k], rays_in[2ull * k + 1], pathA, pathB,
-                                  acc, gpos, gnorm, galb, res_cur);
-    unsigned nc = __reduce_add_sync(0xffffffffu, live ? n_wave + sh.n_closest : 0u);
-    unsigned na = __reduce_add_sync(0xffffffffu, live ? sh.n_any : 0u);
+    const uint32_t cnt = *count_in;
+    unsigned nc = 0, na = 0;
+    for(uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < cnt; k += gridDim.x * blockDim.x) {
+        Shader sh(X, P);
+        nc += path_tail<INTEG>(P, X, sh, s, depth0, queue_in[k], rays_in[2ull * k], rays_in[2ull * k + 1], pathA, pathB, acc,
+                               gpos, gnorm, galb, res_cur);
+        nc += sh.n_closest, na += sh.n_any;
+    }
+    nc = __reduce_add_sync(0xffffffffu, nc); /* every lane gets here, whatever its trip count was */
+    na = __reduce_add_sync(0xffffffffu, na);
     if((threadIdx.x & 31) == 0) {
         if(nc) atomicAdd(X.ray_counts + 0, (unsigned long long)nc);
         if(na) atomicAdd(X.ray_counts + 1, (unsigned long long)na);
@@ -278,8 +293,14 @@ static int pipe_resize(gpurt_pipe* p, uint32_t w, uint32_t h, uint32_t max_depth
     }
     if(p->max_counts < need_counts) {
         if((rc = alloc(p->counts, need_counts * 4))) return rc;
+        GPURT_CUDA(cudaStreamSynchronize(st)); /* a copy into the old pinned block may be in flight */
+        if(p->h_counts) cudaFreeHost(p->h_counts);
+        p->h_counts = nullptr, p->counts_pending = false;
+        GPURT_CUDA(cudaMallocHost((void**)&p->h_counts, need_counts * 4));
+        if(!p->ev_counts) GPURT_CUDA(cudaEventCreateWithFlags(&p->ev_counts, cudaEventDisableTiming));
         p->max_counts = need_counts;
     }
+    if(dims) p->est_counts.clear();
     p->w = w, p->h = h;
     return GPURT_OK;
 }
@@ -401,6 +422,7 @@ int gpurt_pipe_create(gpurt_scene* scene, gpurt_accel* accel, gpurt_pipe** out) 
     GPURT_CUDA(cudaSetDevice(p->ctx->device));
     upload_lut_once();
     if(const char* e = getenv("GPURT_WAVE_DEPTH")) p->wave_depth = (uint32_t)std::max(1, atoi(e)); /* tuning knob */
+    if(const char* e = getenv("GPURT_WAVE_ESTIMATE")) p->use_est = atoi(e) != 0;                   /* A/B knob */
     if(const char* e = getenv("GPURT_LIGHT_GROUPS")) p->use_lgrp = atoi(e) != 0;                   /* A/B knob */
     if(const char* e = getenv("GPURT_LIGHT_BVH")) p->use_lbvh = atoi(e) != 0;                      /* A/B knob */
     *out = p;
@@ -412,6 +434,8 @@ int gpurt_pipe_destroy(gpurt_pipe* p) {
     cudaStreamSynchronize(p->ctx->stream);
     pipe_free(p);
     pipe_drop_light_accel(p);
+    if(p->h_counts) cudaFreeHost(p->h_counts);
+    if(p->ev_counts) cudaEventDestroy(p->ev_counts);
     delete p;
     return GPURT_OK;
 }
@@ -513,7 +537,28 @@ static int render_core(gpurt_pipe* p, const GpurtPipeParams* prm, const GpurtCam
     GPURT_CUDA(cudaMemsetAsync(p->ray_counts, 0, 16, st));
     k_frame_begin<<<cdivu(n, 256), 256, 0, st>>>(F, restir ? 1 : 0, p->acc, p->pathB, p->gbuf[cur][0],
                                                 p->gbuf[cur][1], p->gbuf[cur][2], p->res[cur]);
-    const uint32_t D = (uint32_t)c.max_depth;
+    /* integrate_direct and the direct-only ReSTIR end every path at its first hit (rt.rgen:393, :548): the queues of
+     * the later bounces are always empty, so they are not launched */
+    const uint32_t D = (c.integrator == 0 || c.integrator == 3) ? std::min(1u, (uint32_t)c.max_depth) : (uint32_t)c.max_depth;
+    /* Queue sizes after the first bounce are only known on the device.  A grid sized for every pixel costs 12-14 us per
+     * launch even when the queue is empty (16,200 CTAs that read the count and exit at 1080p; ncu r01r) — a fifth of a
+     * ReSTIR frame on mis_test —, while a small fixed grid striding over a large queue is slower than one thread per
+     * path (config-2 frame +5 %).  A progressive render traces nearly the same queues frame after frame, so the sizes of
+     * the previous frame's last sample (copied back without a sync at the end of every frame) size these launches,
+     * with 12.5 % + 1024 paths of head room; the kernels stride over the queue, so a low estimate is only slower. */
+    const unsigned full_grid = cdivu(n, 128);
+    if(p->counts_pending) {
+        if(cudaEventQuery(p->ev_counts) == cudaSuccess) {
+            p->est_counts.assign(p->h_counts, p->h_counts + p->max_counts);
+            p->counts_pending = false;
+        } else
+            (void)cudaGetLastError(); /* cudaErrorNotReady is not a failure: keep the older estimate */
+    }
+    auto late_grid = [&](uint32_t d) -> unsigned {
+        if(!p->use_est || d >= p->est_counts.size()) return full_grid;
+        uint64_t est = (uint64_t)p->est_counts[d] + p->est_counts[d] / 8 + 1024;
+        return (unsigned)std::min<uint64_t>(full_grid, std::max<uint64_t>((uint64_t)ctx->sm_count, (est + 127) / 128));
+    };
     for(uint32_t s = 0; s < (uint32_t)c.samples && D > 0; s++) {
         GPURT_CUDA(cudaMemsetAsync(p->counts, 0, (size_t)p->max_counts * 4, st));
         k_gen_camera<<<cdivu(n, 256), 256, 0, st>>>(F, s, p->pathA, p->pathB, p->rays[0], p->queue[0], p->counts + 0);
@@ -524,10 +569,10 @@ static int render_core(gpurt_pipe* p, const GpurtPipeParams* prm, const GpurtCam
         const uint32_t wave = p->wave_depth ? std::min(D, p->wave_depth) : (n > 2500000u ? D : std::min(D, 4u));
         for(uint32_t d = 0; d < wave; d++) {
             int qi = d & 1, qo = qi ^ 1;
-            k_trace_closest_indirect<<<cdivu(n, 128), 128, 0, st>>>(X.nodes, X.tris, p->rays[qi], p->counts + d, p->hits,
-                                                                   X.n_nodes);
+            const unsigned grid = d == 0 ? full_grid : late_grid(d);
+            k_trace_closest_indirect<<<grid, 128, 0, st>>>(X.nodes, X.tris, p->rays[qi], p->counts + d, p->hits, X.n_nodes);
 #define GPURT_SHADE(I)                                                                                                   \
-    k_shade<I><<<cdivu(n, 128), 128, 0, st>>>(F, X, s, d, p->counts + d, p->queue[qi], p->rays[qi], p->hits, p->pathA,  \
+    k_shade<I><<<grid, 128, 0, st>>>(F, X, s, d, p->counts + d, p->queue[qi], p->rays[qi], p->hits, p->pathA,  \
                                               p->pathB, p->acc, p->gbuf[cur][0], p->gbuf[cur][1], p->gbuf[cur][2],      \
                                               p->res[cur], p->counts + d + 1, p->queue[qo], p->rays[qo])
             switch(c.integrator) {
@@ -541,7 +586,7 @@ static int render_core(gpurt_pipe* p, const GpurtPipeParams* prm, const GpurtCam
         }
         if(wave < D) {
 #define GPURT_TAIL(I)                                                                                                    \
-    k_tail<I><<<cdivu(n, 128), 128, 0, st>>>(F, X, s, wave, p->counts + wave, p->queue[wave & 1], p->rays[wave & 1],     \
+    k_tail<I><<<late_grid(wave), 128, 0, st>>>(F, X, s, wave, p->counts + wave, p->queue[wave & 1], p->rays[wave & 1],     \
                                              p->pathA, p->pathB, p->acc, p->gbuf[cur][0], p->gbuf[cur][1],              \
                                              p->gbuf[cur][2], p->res[cur])
             switch(c.integrator) {
@@ -554,6 +599,11 @@ static int render_core(gpurt_pipe* p, const GpurtPipeParams* prm, const GpurtCam
 #undef GPURT_TAIL
         }
         /* closest-hit rays of the wavefront = sum of queue sizes */
+    }
+    if(D > 0 && c.samples > 0 && p->h_counts) { /* this frame's queue sizes -> next frame's launch sizes */
+        GPURT_CUDA(cudaMemcpyAsync(p->h_counts, p->counts, (size_t)p->max_counts * 4, cudaMemcpyDeviceToHost, st));
+        GPURT_CUDA(cudaEventRecord(p->ev_counts, st));
+        p->counts_pending = true;
     }
     k_frame_end<<<cdivu(n, 256), 256, 0, st>>>(F, p->acc, p->image, p->gbuf[cur][0], p->gbuf[cur][1], p->gbuf[prev][0],
                                               p->gbuf[prev][1], p->gbuf[prev][2], mean_out);

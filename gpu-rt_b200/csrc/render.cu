@@ -101,14 +101,27 @@ __global__ void __launch_bounds__(256) k_gen_camera(const __grid_constant__ Fram
     pixel_gen_camera(P, s, shard_pixel(P, li), li, pathA, pathB, rays, queue);
 }
 
+/* STRIDE = false: one ray per thread, the grid covers the queue (first bounce, or no size estimate yet).
+ * STRIDE = true: launches sized from an estimate stride over the queue in case it is larger than estimated; wrapping
+ * the traversal in that loop costs 2-4 % (ncu r01v), hence the two instantiations. */
+template <bool STRIDE>
 __global__ void __launch_bounds__(128) k_trace_closest_indirect(const float4* __restrict__ nodes,
                                                                 const float4* __restrict__ tris,
                                                                 const float4* __restrict__ rays,
                                                                 const uint32_t* __restrict__ count,
                                                                 float4* __restrict__ hits, unsigned n_nodes) {
-    /* grid-stride: queues after the first bounce are launched with a capped grid (see render_core) */
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(!STRIDE) {
+        if(i >= *count) return;
+        float4 a = __ldg(rays + 2ull * i), b = __ldg(rays + 2ull * i + 1);
+        HitRec h;
+        h.t = a.w, h.u = h.v = 0, h.gid = kNoHit;
+        if(n_nodes) traverse8<false, false>(nodes, tris, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), a.w, b.w, h, nullptr);
+        hits[i] = make_float4(h.gid == kNoHit ? GPURT_INF : h.t, h.u, h.v, u2f(h.gid));
+        return;
+    }
     const uint32_t cnt = *count;
-    for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
+    for(; i < cnt; i += gridDim.x * blockDim.x) {
         float4 a = __ldg(rays + 2ull * i), b = __ldg(rays + 2ull * i + 1);
         HitRec h;
         h.t = a.w, h.u = h.v = 0, h.gid = kNoHit;
@@ -217,8 +230,12 @@ __global__ void __launch_bounds__(256) k_accumulate_mean(float4* __restrict__ im
 __global__ void __launch_bounds__(256) k_frame_end(const __grid_constant__ FrameParams P, const float4* acc,
                                                    float4* image, const float4* gpos, const float4* gnorm,
                                                    const float4* ppos, const float4* pnorm, const float4* palb,
-                                                   float4* mean_out) {
+                                                   float4* mean_out, const uint32_t* __restrict__ counts,
+                                                   uint32_t* host_counts, uint32_t n_counts) {
     uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
+    /* this frame's queue sizes, written straight into pinned host memory for the next frame's launch sizes (a D2H copy
+     * in the stream would put a copy-engine hop between the last shading kernel and this one) */
+    if(host_counts && li < n_counts) host_counts[li] = counts[li];
     if(li >= P.n_local) return;
     pixel_end(P, shard_pixel(P, li), acc, image, gpos, gnorm, ppos, pnorm, palb, mean_out);
 }
@@ -557,7 +574,8 @@ static int render_core(gpurt_pipe* p, const GpurtPipeParams* prm, const GpurtCam
     auto late_grid = [&](uint32_t d) -> unsigned {
         if(!p->use_est || d >= p->est_counts.size()) return full_grid;
         uint64_t est = (uint64_t)p->est_counts[d] + p->est_counts[d] / 8 + 1024;
-        return (unsigned)std::min<uint64_t>(full_grid, std::max<uint64_t>((uint64_t)ctx->sm_count, (est + 127) / 128));
+        uint64_t g = std::max<uint64_t>((uint64_t)ctx->sm_count, (est + 127) / 128);
+        return 2 * g > full_grid ? full_grid : (unsigned)g; /* more than half of the pixels alive: the plain full-size launch */
     };
     for(uint32_t s = 0; s < (uint32_t)c.samples && D > 0; s++) {
         GPURT_CUDA(cudaMemsetAsync(p->counts, 0, (size_t)p->max_counts * 4, st));
@@ -570,7 +588,10 @@ static int render_core(gpurt_pipe* p, const GpurtPipeParams* prm, const GpurtCam
         for(uint32_t d = 0; d < wave; d++) {
             int qi = d & 1, qo = qi ^ 1;
             const unsigned grid = d == 0 ? full_grid : late_grid(d);
-            k_trace_closest_indirect<<<grid, 128, 0, st>>>(X.nodes, X.tris, p->rays[qi], p->counts + d, p->hits, X.n_nodes);
+            if(grid == full_grid)
+                k_trace_closest_indirect<false><<<grid, 128, 0, st>>>(X.nodes, X.tris, p->rays[qi], p->counts + d, p->hits, X.n_nodes);
+            else
+                k_trace_closest_indirect<true><<<grid, 128, 0, st>>>(X.nodes, X.tris, p->rays[qi], p->counts + d, p->hits, X.n_nodes);
 #define GPURT_SHADE(I)                                                                                                   \
     k_shade<I><<<grid, 128, 0, st>>>(F, X, s, d, p->counts + d, p->queue[qi], p->rays[qi], p->hits, p->pathA,  \
                                               p->pathB, p->acc, p->gbuf[cur][0], p->gbuf[cur][1], p->gbuf[cur][2],      \
@@ -600,13 +621,14 @@ static int render_core(gpurt_pipe* p, const GpurtPipeParams* prm, const GpurtCam
         }
         /* closest-hit rays of the wavefront = sum of queue sizes */
     }
-    if(D > 0 && c.samples > 0 && p->h_counts) { /* this frame's queue sizes -> next frame's launch sizes */
-        GPURT_CUDA(cudaMemcpyAsync(p->h_counts, p->counts, (size_t)p->max_counts * 4, cudaMemcpyDeviceToHost, st));
+    const bool report = D > 0 && c.samples > 0 && p->h_counts && p->max_counts <= n; /* this frame's queue sizes -> next frame */
+    k_frame_end<<<cdivu(n, 256), 256, 0, st>>>(F, p->acc, p->image, p->gbuf[cur][0], p->gbuf[cur][1], p->gbuf[prev][0],
+                                              p->gbuf[prev][1], p->gbuf[prev][2], mean_out, p->counts,
+                                              report ? p->h_counts : nullptr, p->max_counts);
+    if(report) {
         GPURT_CUDA(cudaEventRecord(p->ev_counts, st));
         p->counts_pending = true;
     }
-    k_frame_end<<<cdivu(n, 256), 256, 0, st>>>(F, p->acc, p->image, p->gbuf[cur][0], p->gbuf[cur][1], p->gbuf[prev][0],
-                                              p->gbuf[prev][1], p->gbuf[prev][2], mean_out);
     GPURT_CUDA(cudaEventRecord(ctx->ev1, st));
     GPURT_CUDA(cudaGetLastError());
     p->parity ^= 1;

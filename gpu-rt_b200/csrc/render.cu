@@ -63,6 +63,13 @@ struct gpurt_pipe {
     uint64_t lgrp_version = ~0ull;
     const float4* lgrp_tris = nullptr;
     bool use_lgrp = true;                             /* GPURT_LIGHT_GROUPS=0: every light triangle, like the GLSL */
+    /* world-space vertices of the light triangles for light_sample (shade.cuh), rebuilt with the light groups */
+    float4* lverts = nullptr;
+    uint32_t* lvert_off = nullptr;
+    size_t lverts_cap = 0, lvert_off_cap = 0;
+    uint64_t lverts_version = ~0ull;
+    const float4* lverts_tris = nullptr;
+    bool use_lverts = true;                           /* GPURT_LIGHT_VERTS=0: light_sample transforms its vertices itself */
     /* light BVH for light_pdf (shade.cuh light_pdf_bvh): a second accel over the lights' triangles only */
     gpurt_scene* lscene = nullptr;
     gpurt_accel* laccel = nullptr;
@@ -90,6 +97,13 @@ __global__ void __launch_bounds__(128) k_light_groups(const float4* __restrict__
     const uint32_t n_tris = lights[l].n_triangles;
     if(r >= light_box_records(n_tris)) return;
     light_box_record(tri_world + 3ull * tri_off[lights[l].index], n_tris, r, pad, out + 2ull * (off[l].x + r));
+}
+
+/* model * v of the three vertices of every light triangle, as light_sample computes them (blockIdx.y = light) */
+__global__ void __launch_bounds__(128) k_light_verts(DeviceScene S, const uint32_t* __restrict__ off, float4* __restrict__ out) {
+    const uint32_t l = blockIdx.y, t = blockIdx.x * blockDim.x + threadIdx.x;
+    if(t >= S.lights[l].n_triangles) return;
+    light_world_tri(S, S.lights[l].index, t, out + 3ull * (off[l] + t));
 }
 
 __global__ void __launch_bounds__(256) k_gen_camera(const __grid_constant__ FrameParams P, uint32_t s,
@@ -271,7 +285,7 @@ __global__ void __launch_bounds__(256) k_tonemap(const float4* __restrict__ img,
 static int pipe_free(gpurt_pipe* p) {
     void* ptrs[] = {p->image, p->res[0], p->res[1], p->gbuf[0][0], p->gbuf[0][1], p->gbuf[0][2], p->gbuf[1][0],
                     p->gbuf[1][1], p->gbuf[1][2], p->acc, p->pathA, p->pathB, p->rays[0], p->rays[1], p->hits,
-                    p->queue[0], p->queue[1], p->counts, p->ray_counts, p->lgrp, p->lgrp_off};
+                    p->queue[0], p->queue[1], p->counts, p->ray_counts, p->lgrp, p->lgrp_off, p->lverts, p->lvert_off};
     for(void* q : ptrs)
         if(q) cudaFree(q);
     return GPURT_OK;
@@ -359,6 +373,39 @@ static int pipe_light_groups(gpurt_pipe* p) {
     return GPURT_OK;
 }
 
+/* (re)build the world-space light vertices when the scene's geometry or poses changed */
+static int pipe_light_verts(gpurt_pipe* p) {
+    const gpurt_accel* A = p->accel;
+    const PackedScene& M = p->scene->packed;
+    const std::vector<SceneLight>& L = M.lights;
+    bool usable = p->use_lverts && !L.empty() && A->tri_gid && L.size() == A->dscene.n_lights;
+    for(const SceneLight& l : L)
+        usable = usable && l.index < M.descs.size() && l.n_triangles == M.tri_off[l.index + 1] - M.tri_off[l.index];
+    if(!usable) {
+        p->lverts_tris = nullptr;
+        return GPURT_OK;
+    }
+    if(p->lverts_tris == A->tri_gid && p->lverts_version == A->dscene.version) return GPURT_OK;
+    cudaStream_t st = p->ctx->stream;
+    std::vector<uint32_t> off(L.size());
+    uint32_t total = 0, most = 0;
+    for(size_t l = 0; l < L.size(); l++) off[l] = total, total += L[l].n_triangles, most = std::max(most, L[l].n_triangles);
+    if(p->lverts_cap < total || p->lvert_off_cap < L.size()) {
+        GPURT_CUDA(cudaStreamSynchronize(st));
+        if(p->lverts) cudaFree(p->lverts);
+        if(p->lvert_off) cudaFree(p->lvert_off);
+        p->lverts = nullptr, p->lvert_off = nullptr, p->lverts_cap = p->lvert_off_cap = 0;
+        GPURT_CUDA(cudaMalloc((void**)&p->lverts, (size_t)std::max(total, 1u) * 48));
+        GPURT_CUDA(cudaMalloc((void**)&p->lvert_off, L.size() * sizeof(uint32_t)));
+        p->lverts_cap = total, p->lvert_off_cap = L.size();
+    }
+    GPURT_CUDA(cudaMemcpyAsync(p->lvert_off, off.data(), L.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    if(most) k_light_verts<<<dim3(cdivu(most, 128), (unsigned)L.size()), 128, 0, st>>>(A->dscene, p->lvert_off, p->lverts);
+    GPURT_CUDA(cudaGetLastError());
+    p->lverts_tris = A->tri_gid, p->lverts_version = A->dscene.version;
+    return GPURT_OK;
+}
+
 static void pipe_drop_light_accel(gpurt_pipe* p) {
     if(p->laccel) gpurt_accel_destroy(p->laccel);
     delete p->lscene;
@@ -372,7 +419,8 @@ static int pipe_light_accel(gpurt_pipe* p) {
     const gpurt_accel* A = p->accel;
     const PackedScene& M = p->scene->packed;
     bool usable = p->use_lbvh && !M.lights.empty() && M.lights.size() == A->dscene.n_lights && A->n > 0;
-    for(const SceneLight& L : M.lights) usable = usable && L.n_triangles > 0 && L.index < M.descs.size();
+    for(const SceneLight& L : M.lights)
+        usable = usable && L.n_triangles > 0 && L.index < M.descs.size() && L.n_triangles == M.tri_off[L.index + 1] - M.tri_off[L.index];
     if(!usable) { /* a light without triangles makes the GLSL's 0/0: leave that to the scan, which reproduces it */
         pipe_drop_light_accel(p);
         return GPURT_OK;
@@ -442,6 +490,7 @@ int gpurt_pipe_create(gpurt_scene* scene, gpurt_accel* accel, gpurt_pipe** out) 
     if(const char* e = getenv("GPURT_WAVE_ESTIMATE")) p->use_est = atoi(e) != 0;                   /* A/B knob */
     if(const char* e = getenv("GPURT_LIGHT_GROUPS")) p->use_lgrp = atoi(e) != 0;                   /* A/B knob */
     if(const char* e = getenv("GPURT_LIGHT_BVH")) p->use_lbvh = atoi(e) != 0;                      /* A/B knob */
+    if(const char* e = getenv("GPURT_LIGHT_VERTS")) p->use_lverts = atoi(e) != 0;                  /* A/B knob */
     *out = p;
     return GPURT_OK;
 }
@@ -541,6 +590,11 @@ static int render_core(gpurt_pipe* p, const GpurtPipeParams* prm, const GpurtCam
     if((rc = pipe_light_groups(p))) return rc;
     X.lgrp = p->lgrp_tris ? p->lgrp : nullptr, X.lgrp_off = p->lgrp_off;
     X.lnodes = nullptr, X.ltris = nullptr, X.ltri_off = nullptr, X.n_lnodes = 0;
+    X.lverts = nullptr, X.lvert_off = nullptr;
+    if(c.integrator != 1 && c.integrator != 2) { /* the integrators that call light_sample */
+        if((rc = pipe_light_verts(p))) return rc;
+        if(p->lverts_tris) X.lverts = p->lverts, X.lvert_off = p->lvert_off;
+    }
     if(c.integrator == 2) { /* only MIS evaluates light_pdf */
         if((rc = pipe_light_accel(p))) return rc;
         if(p->laccel && p->laccel->n_nodes)

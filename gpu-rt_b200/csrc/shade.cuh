@@ -202,12 +202,28 @@ struct ShadeCtx {
     const float4* ltris;
     const uint32_t* ltri_off;
     unsigned n_lnodes;
+    /* world-space vertices of the light triangles (render.cu k_light_verts): 3 float4 per triangle = model * v0, v1, v2
+     * exactly as light_sample computes them, light l starts at triangle lvert_off[l]; NULL: light_sample transforms
+     * the three vertices itself like the GLSL */
+    const float4* lverts;
+    const uint32_t* lvert_off;
     const float4* prev_res;  /* previous frame reservoirs */
     const float4* ppos;      /* previous frame G-buffers */
     const float4* pnorm;
     const float4* palb;
     unsigned long long* ray_counts; /* [0] closest, [1] any */
 };
+
+/* model * vec4(v, 1) of the three vertices of triangle t of object obj (rt.rgen:172-174) */
+SH_D void light_world_tri(const DeviceScene& S, uint32_t obj, uint32_t t, float4* out3) {
+    const uint32_t* ip = S.idx + 3ull * (S.tri_off[obj] + t);
+    const float* m = reinterpret_cast<const float*>(S.descs + obj);
+    for(int k = 0; k < 3; k++) {
+        const float* v = reinterpret_cast<const float*>(S.verts + (S.vert_off[obj] + ip[k]));
+        F3 w = xform_point(m, F3{v[0], v[1], v[2]});
+        out3[k] = make_float4(w.x, w.y, w.z, 0.0f);
+    }
+}
 
 struct Shader {
     const ShadeCtx& X;
@@ -465,18 +481,27 @@ struct Shader {
         uint32_t l_idx = randu(0, (uint32_t)P.c.n_lights);
         uint32_t o_idx = X.S.lights[l_idx].index, n_tris = X.S.lights[l_idx].n_triangles;
         uint32_t t_idx = randu(0, n_tris);
-        uint32_t ind[3];
-        tri_indices(o_idx, t_idx, ind);
-        const float *v0 = vertex(o_idx, ind[0]), *v1 = vertex(o_idx, ind[1]), *v2 = vertex(o_idx, ind[2]);
-        const float* m = model(o_idx);
-        F3 _v0 = xform_point(m, F3{v0[0], v0[1], v0[2]}), _v1 = xform_point(m, F3{v1[0], v1[1], v1[2]}),
-           _v2 = xform_point(m, F3{v2[0], v2[1], v2[2]});
-        F3 bary = triangle_sample();
-        float tc[2] = {v0[3] * bary.x + v1[3] * bary.y + v2[3] * bary.z, v1[7] * bary.x + v1[7] * bary.y + v1[7] * bary.z};
-        s.pos = _v0 * bary.x + _v1 * bary.y + _v2 * bary.z;
         int emissiveIdx = desc_int(o_idx, 45);
         s.emissive = desc_vec(o_idx, 36);
-        if(emissiveIdx >= 0) s.emissive = texture(emissiveIdx, tc);
+        F3 _v0, _v1, _v2, bary;
+        if(X.lverts && emissiveIdx < 0) { /* the three transformed vertices were computed once per build: one 48-byte read */
+            const float4* q = X.lverts + 3ull * (X.lvert_off[l_idx] + t_idx);
+            float4 a = GPURT_LDG(q), b = GPURT_LDG(q + 1), c = GPURT_LDG(q + 2);
+            _v0 = F3{a.x, a.y, a.z}, _v1 = F3{b.x, b.y, b.z}, _v2 = F3{c.x, c.y, c.z};
+            bary = triangle_sample();
+            s.pos = _v0 * bary.x + _v1 * bary.y + _v2 * bary.z;
+        } else {
+            uint32_t ind[3];
+            tri_indices(o_idx, t_idx, ind);
+            const float *v0 = vertex(o_idx, ind[0]), *v1 = vertex(o_idx, ind[1]), *v2 = vertex(o_idx, ind[2]);
+            const float* m = model(o_idx);
+            _v0 = xform_point(m, F3{v0[0], v0[1], v0[2]}), _v1 = xform_point(m, F3{v1[0], v1[1], v1[2]}),
+            _v2 = xform_point(m, F3{v2[0], v2[1], v2[2]});
+            bary = triangle_sample();
+            float tc[2] = {v0[3] * bary.x + v1[3] * bary.y + v2[3] * bary.z, v1[7] * bary.x + v1[7] * bary.y + v1[7] * bary.z};
+            s.pos = _v0 * bary.x + _v1 * bary.y + _v2 * bary.z;
+            if(emissiveIdx >= 0) s.emissive = texture(emissiveIdx, tc);
+        }
         F3 Narea = cross3(_v1 - _v0, _v2 - _v0);
         float a = 2 / length3(Narea);
         F3 dist = s.pos - p;

@@ -200,7 +200,7 @@ struct EmuFrameArgs {
 };
 
 /* pipe_light_groups() + k_light_groups of render.cu */
-static int g_light_groups = 1, g_light_bvh = 1;
+static int g_light_groups = 1, g_light_bvh = 1, g_light_verts = 1;
 static void build_light_groups(const Emu* E, const EmuFrameArgs* A, std::vector<float4>& boxes, std::vector<uint2>& off) {
     const SceneLight* L = (const SceneLight*)A->lights;
     off.resize(A->n_lights);
@@ -254,6 +254,7 @@ static void render_rows(const FrameParams& P, const ShadeCtx& X, uint32_t i0, ui
 extern "C" {
 void emu_set_light_groups(int on) { g_light_groups = on; }
 void emu_set_light_bvh(int on) { g_light_bvh = on; }
+void emu_set_light_verts(int on) { g_light_verts = on; }
 
 /* light_pdf(p, d) for n rays (6 floats each): through the light-run boxes, testing every triangle, through the light
  * BVH -> out3[3 i .. 3 i + 2] */
@@ -305,6 +306,17 @@ void emu_render_frame(void* bvh, const EmuFrameArgs* A, const uint32_t* consts, 
     if(g_light_groups && A->n_lights) {
         build_light_groups(E, A, lboxes, loff);
         X.lgrp = lboxes.data(), X.lgrp_off = loff.data();
+    }
+    std::vector<float4> lverts; /* pipe_light_verts() + k_light_verts of render.cu */
+    std::vector<uint32_t> lvoff(A->n_lights);
+    if(g_light_verts && A->n_lights) {
+        const SceneLight* L = (const SceneLight*)A->lights;
+        uint32_t total = 0;
+        for(uint32_t l = 0; l < A->n_lights; l++) lvoff[l] = total, total += L[l].n_triangles;
+        lverts.resize(3ull * total);
+        for(uint32_t l = 0; l < A->n_lights; l++)
+            for(uint32_t t = 0; t < L[l].n_triangles; t++) light_world_tri(X.S, L[l].index, t, lverts.data() + 3ull * (lvoff[l] + t));
+        X.lverts = lverts.data(), X.lvert_off = lvoff.data();
     }
     X.prev_res = (const float4*)prev_res, X.ppos = (const float4*)ppos, X.pnorm = (const float4*)pnorm, X.palb = (const float4*)palb;
     const uint32_t n = w * h;

@@ -247,3 +247,45 @@ def test_light_groups_do_not_change_light_pdf(emu, orc, gpurt, name):
     assert es.lh and (c == b).all(), f"{(c != b).sum()} of {n} light_pdf values differ (light BVH)"
     assert (out[:, 1] > 0).mean() > 0.2
     es.close()
+
+
+@pytest.mark.parametrize("bvh,groups,verts", [(0, 1, 0), (0, 0, 0), (1, 0, 1)])
+def test_fallback_paths_render_the_same(emu, orc, gpurt, bvh, groups, verts):
+    """the A/B knobs of render.cu (GPURT_LIGHT_BVH / GPURT_LIGHT_GROUPS / GPURT_LIGHT_VERTS) select code paths
+    that must all equal the oracle: light_pdf by scan / by the GLSL's full loop, light_sample with its own transforms"""
+    s = gpurt.Scene(None).load(os.path.join(MEDIA, "mis_test", "mis_test.gltf"))
+    cam = gpurt.camera(1, 64, 36, (0.5, 0.6, 2.6), (0.5, 0.45, 0.0), 50.0)
+    emu.emu_set_light_bvh(bvh), emu.emu_set_light_groups(groups), emu.emu_set_light_verts(verts)
+    try:
+        for integ in (0, 2, 4):
+            _run(emu, orc, gpurt, s, 64, 36, 2, cam=cam, integrator=integ, brdf=1, samples_per_frame=1, max_depth=3,
+                 seed=40 + integ)
+    finally:
+        emu.emu_set_light_bvh(1), emu.emu_set_light_groups(1), emu.emu_set_light_verts(1)
+
+
+def test_more_light_hits_than_the_buffer_holds(emu, orc, gpurt):
+    """a ray through a stack of 12 emissive quads crosses more light triangles than light_pdf_bvh keeps (8):
+    it must fall back to the scan and still equal the full loop"""
+    s = gpurt.Scene(None)
+    e = gpurt.Material()
+    e.albedo[:] = (1, 1, 1)
+    e.emissive[:] = (2, 2, 2)
+    e.albedo_tex = e.emissive_tex = e.metal_rough_tex = e.normal_tex = -1
+    e.metal_rough[:] = (0, 1)
+    for k in range(12):
+        z = 0.1 * k
+        s.add_triangles(np.array([[0, 0, z, 1, 0, z, 1, 1, z], [0, 0, z, 1, 1, z, 0, 1, z]], np.float32), e)
+    es = EmuScene(emu, orc, s)
+    rng = np.random.default_rng(9)
+    n = 20000
+    o = np.concatenate([rng.random((n, 2)) * 0.8 + 0.1, np.full((n, 1), -0.5)], axis=1).astype(np.float32)
+    d = np.concatenate([(rng.random((n, 2)) - 0.5) * 0.2, np.ones((n, 1))], axis=1).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = np.concatenate([o, d], axis=1).astype(np.float32)
+    out = np.zeros((n, 3), np.float32)
+    emu.emu_light_pdf(es.h, C.byref(es.args), _vp(rays), C.c_ulonglong(n), _vp(out))
+    assert (out[:, 2].view(np.uint32) == out[:, 1].view(np.uint32)).all()
+    assert (out[:, 0].view(np.uint32) == out[:, 1].view(np.uint32)).all()
+    assert (out[:, 1] > 0).mean() > 0.9
+    es.close()

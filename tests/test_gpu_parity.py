@@ -238,7 +238,10 @@ def test_pose_edit_update_equals_fresh_build(gpurt, orc, ctx):
     n_nodes_before = accel.info().n_wide_nodes
     cam = gpurt.camera(0, 256, 256)
     params = gpurt.pipe_params(max_frames=1, samples_per_frame=2, max_depth=3, integrator=2, seed=5)
-    pipe.render_frame(params, cam, 256, 256)   # builds the pipe's light-run boxes for the OLD pose of the light
+    params0 = gpurt.pipe_params(max_frames=1, samples_per_frame=2, max_depth=3, integrator=0, seed=6)
+    pipe.render_frame(params, cam, 256, 256)   # builds the pipe's light BVH / light-run boxes for the OLD pose of the light
+    pipe.reset_frame()
+    pipe.render_frame(params0, cam, 256, 256)  # ... and its world-space light vertices (light_sample)
     light = scene.lights()[0].index
 
     def light_model(k):
@@ -272,6 +275,10 @@ def test_pose_edit_update_equals_fresh_build(gpurt, orc, ctx):
     pipe.render_frame(params, cam, 256, 256)
     fresh_pipe = gpurt.RTPipe(fresh_scene, fresh)
     fresh_pipe.render_frame(params, cam, 256, 256)
+    assert same_bits(pipe.read_image(), fresh_pipe.read_image())
+    pipe.reset_frame(), fresh_pipe.reset_frame()
+    pipe.render_frame(params0, cam, 256, 256)
+    fresh_pipe.render_frame(params0, cam, 256, 256)
     assert same_bits(pipe.read_image(), fresh_pipe.read_image())
     for o in (pipe, fresh_pipe, accel, fresh, scene, fresh_scene):
         o.close()

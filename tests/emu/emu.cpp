@@ -252,6 +252,20 @@ static void render_rows(const FrameParams& P, const ShadeCtx& X, uint32_t i0, ui
 }
 
 extern "C" {
+/* shard_pixel() of shade.cuh for every local index of one shard: out[n_local] global pixel indices; returns n_local
+ * computed the way render_core does */
+unsigned emu_shard_pixels(unsigned w, unsigned h, unsigned band_rows, unsigned n_shards, unsigned shard, unsigned* out) {
+    FrameParams P;
+    std::memset(&P, 0, sizeof(P));
+    P.W = w, P.H = h, P.band_rows = band_rows ? band_rows : h, P.n_shards = band_rows ? n_shards : 1, P.shard = band_rows ? shard : 0;
+    unsigned n_local = 0, bands = (h + P.band_rows - 1) / P.band_rows;
+    for(unsigned g = P.shard; g < bands; g += P.n_shards) n_local += std::min(P.band_rows, h - g * P.band_rows) * w;
+    P.n_local = n_local;
+    if(out)
+        for(unsigned i = 0; i < n_local; i++) out[i] = shard_pixel(P, i);
+    return n_local;
+}
+
 void emu_set_light_groups(int on) { g_light_groups = on; }
 void emu_set_light_bvh(int on) { g_light_bvh = on; }
 void emu_set_light_verts(int on) { g_light_verts = on; }

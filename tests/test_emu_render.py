@@ -289,3 +289,26 @@ def test_more_light_hits_than_the_buffer_holds(emu, orc, gpurt):
     assert (out[:, 0].view(np.uint32) == out[:, 1].view(np.uint32)).all()
     assert (out[:, 1] > 0).mean() > 0.9
     es.close()
+
+
+@pytest.mark.parametrize("w,h,band,shards", [(1920, 1080, 0, 1), (1920, 1080, 16, 8), (192, 108, 16, 2), (100, 37, 16, 3),
+                                             (64, 36, 4, 4), (33, 17, 5, 2), (3840, 2160, 16, 8), (16, 8, 8, 1)])
+def test_shard_pixel_enumerates_every_pixel_exactly_once(emu, w, h, band, shards):
+    """the pixel order the frame kernels use (8x4 warp tiles inside 16x8 CTA blocks, interleaved row bands per rank):
+    the shards partition the frame, and a warp's 32 pixels form an 8x4 tile whenever the tiled order applies"""
+    emu.emu_shard_pixels.restype = C.c_uint
+    seen = np.zeros(w * h, np.int32)
+    for r in range(shards):
+        n = emu.emu_shard_pixels(w, h, band, shards, r, None)
+        out = np.zeros(max(n, 1), np.uint32)
+        assert emu.emu_shard_pixels(w, h, band, shards, r, _vp(out)) == n
+        out = out[:n]
+        assert (out < w * h).all()
+        np.add.at(seen, out, 1)
+        rows = out // w
+        band_rows = band if band else h
+        assert ((rows // band_rows) % shards == r).all(), "a rank only renders its own bands"
+        if w % 16 == 0 and band_rows % 8 == 0 and h % 8 == 0 and n >= 32:
+            x, y = (out[:32] % w).astype(int), (out[:32] // w).astype(int)
+            assert x.max() - x.min() == 7 and y.max() - y.min() == 3
+    assert (seen == 1).all()

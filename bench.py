@@ -340,11 +340,12 @@ def main():
 
     # physical DRAM bytes of one launch: dram__bytes_read.sum + dram__bytes_write.sum of k_trace_closest from the
     # committed ncu capture of this same workload, scaled per ray (never measured under the profiler here)
-    traffic, traffic_src = None, None
+    traffic, traffic_src, secondary = None, None, None
     tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
     if os.path.exists(tpath):
         tj = json.load(open(tpath))
         traffic, traffic_src = tj["dram_bytes_per_ray"] * n_rays, tj["source"]
+        secondary = tj.get("secondary_ceilings")   # L2 / issue-slot ceilings of the same ncu capture
     if rank == 0:
         line = {
             "metric": "Mrays/s closest-hit on Sponza", "value": value, "unit": "Mrays/s", "n_gpus": world,
@@ -360,7 +361,8 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel": "k_trace_closest<false>",
                          "bytes_per_ray": bytes_per_ray, "nodes_per_ray": nodes_per_ray, "tris_per_ray": tris_per_ray,
-                         "stream_floor_bytes_per_ray": BYTES_STREAM, "kernel_ms": kernel_ms},
+                         "stream_floor_bytes_per_ray": BYTES_STREAM, "kernel_ms": kernel_ms,
+                         "secondary_ceilings": secondary},
             "cpu_baseline": cpu,
             "primary_only": {"value": n_p / (float(np.median(prim_ms)) * 1e-3) / 1e6, "unit": "Mrays/s", "rays": n_p},
             "cpq": {"value": n_p / (float(np.median(cpq_ms)) * 1e-3) / 1e6, "unit": "Mqueries/s", "queries": n_p,

@@ -312,3 +312,90 @@ def test_shard_pixel_enumerates_every_pixel_exactly_once(emu, w, h, band, shards
             x, y = (out[:32] % w).astype(int), (out[:32] // w).astype(int)
             assert x.max() - x.min() == 7 and y.max() - y.min() == 3
     assert (seen == 1).all()
+
+
+def _random_material_scene(gpurt, seed, n_objs=24, degenerate=True):
+    """small random scene: mirrors (roughness 0), rough and emissive objects, non-unit / zero normals, zero-area
+    triangles (also among the lights), a tiny and a huge object"""
+    rng = np.random.default_rng(seed)
+    s = gpurt.Scene(None)
+    for k in range(n_objs):
+        n_tris = int(rng.integers(1, 12))
+        c = rng.random(3) * 2 - 1
+        size = [0.4, 0.4, 0.4, 0.02, 1.5][k % 5]
+        tris = (c + (rng.random((n_tris, 3, 3)) - 0.5) * size).astype(np.float32)
+        if degenerate and k % 4 == 1:
+            tris[0, 2] = tris[0, 1]                       # zero-area triangle
+        if degenerate and k % 6 == 2 and n_tris > 1:
+            tris[1, 1] = tris[1, 0] + (tris[1, 2] - tris[1, 0]) * 0.5   # collinear
+        verts = np.zeros((3 * n_tris, 12), np.float32)
+        verts[:, 0:3] = tris.reshape(-1, 3)
+        verts[:, 3], verts[:, 7] = rng.random(3 * n_tris), rng.random(3 * n_tris)
+        nrm = rng.standard_normal((3 * n_tris, 3)) * [1.0, 3.0, 0.2][k % 3]
+        if degenerate and k % 5 == 3:
+            nrm[0] = 0                                     # zero normal -> normalize gives NaN, as in the GLSL
+        verts[:, 4:7] = nrm
+        verts[:, 8:11] = rng.standard_normal((3 * n_tris, 3))
+        verts[:, 11] = rng.choice([-1.0, 1.0], 3 * n_tris)
+        m = gpurt.Material()
+        m.albedo[:] = tuple(rng.random(3))
+        m.albedo_tex = m.emissive_tex = m.metal_rough_tex = m.normal_tex = -1
+        kind = k % 4
+        m.metal_rough[:] = (rng.random(), 0.0 if kind == 0 else float(rng.random() * 0.9 + 0.05))
+        if kind == 3:
+            m.emissive[:] = tuple(rng.random(3) * 5 + 0.1)
+        model = np.eye(4, dtype=np.float32)
+        model[:3, :3] += (rng.random((3, 3)).astype(np.float32) - 0.5) * 0.3
+        model[:3, 3] = (rng.random(3) - 0.5) * 0.5
+        s.add_object(verts, np.arange(3 * n_tris, dtype=np.uint32), model.T.reshape(16).copy(), m)
+    return s
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_random_material_scenes_all_integrators(emu, orc, gpurt, seed):
+    """product shading code == oracle on scenes full of edge cases (NaN normals, zero-area lights, mirrors, skewed
+    instances), every integrator and both BRDFs, two frames (temporal reuse), bit for bit incl. NaN payloads"""
+    s = _random_material_scene(gpurt, seed)
+    cam = gpurt.camera(1, 48, 27, (0.2, 0.1, 2.4), (0.0, 0.0, 0.0), 70.0)
+    for integ in range(5):
+        _run(emu, orc, gpurt, s, 48, 27, 2, cam=cam, integrator=integ, brdf=(integ + seed) % 2, samples_per_frame=2,
+             max_depth=4, env_scale=0.3, use_metalness=seed % 2, seed=100 * seed + integ)
+
+
+def test_textured_quads_all_texture_kinds(emu, orc, gpurt):
+    """albedo / emissive / metal-rough / normal textures, sRGB decode, bilinear + REPEAT with negative and > 1
+    coordinates, an emissive-textured light (light_sample's texture path and the Q5 texcoord quirk)"""
+    rng = np.random.default_rng(5)
+    texs = [rng.integers(0, 256, (16, 16, 4), dtype=np.uint8), rng.integers(0, 256, (8, 32, 4), dtype=np.uint8),
+            rng.integers(64, 256, (4, 4, 4), dtype=np.uint8), rng.integers(100, 156, (32, 32, 4), dtype=np.uint8)]
+    texs[3][..., 2] = 250
+    scene = gpurt.Scene(None)
+    for t in texs:
+        scene.add_texture(t)
+
+    def quad(z, size, mat, uvscale=3.0):
+        v = np.zeros((4, 12), np.float32)
+        v[:, 0:3] = [[-size, -size, z], [size, -size, z], [size, size, z], [-size, size, z]]
+        v[:, 3] = np.array([0, 1, 1, 0]) * uvscale - 0.7
+        v[:, 7] = np.array([0, 0, 1, 1]) * uvscale - 0.3
+        v[:, 4:7] = [0, 0, 1]
+        v[:, 8:12] = [1, 0, 0, 1]
+        scene.add_object(v, np.array([0, 1, 2, 0, 2, 3], np.uint32), None, mat)
+
+    m = gpurt.Material()
+    m.albedo[:] = (1, 1, 1)
+    m.albedo_tex, m.emissive_tex, m.metal_rough_tex, m.normal_tex = 0, -1, 2, 3
+    m.metal_rough[:] = (0.5, 0.5)
+    quad(0.0, 2.0, m)
+    e = gpurt.Material()
+    e.albedo[:] = (1, 1, 1)
+    e.emissive[:] = (4, 4, 4)
+    e.albedo_tex, e.emissive_tex, e.metal_rough_tex, e.normal_tex = -1, 1, -1, -1
+    e.metal_rough[:] = (0, 1)
+    quad(3.0, 0.8, e, uvscale=1.0)
+    cam = gpurt.camera(1, 64, 48, (1.5, 1.0, 2.5), (0.0, 0.0, 0.5), 70.0)
+    for integ in (0, 1, 2, 3, 4):
+        img = _run(emu, orc, gpurt, scene, 64, 48, 2, cam=cam, textures=texs, integrator=integ, brdf=1, samples_per_frame=2,
+                   max_depth=3, use_normal_map=1, use_metalness=1, seed=20 + integ)
+        assert np.isfinite(img[..., :3]).mean() > 0.9
+    scene.close()

@@ -7,6 +7,7 @@
 #include <cstring>
 #include <vector>
 
+#include <algorithm>
 #include <cmath>
 #include <thread>
 
@@ -39,7 +40,247 @@ static void fill_ranges(const int* left, const int* right, int node, std::vector
     }
 }
 
+/* ---- experiment support: a top-down binned-SAH binary tree in the layout emu_build() takes (tools/sah_probe.py).
+ * Not a product path: the shipped build is the Morton LBVH; this answers "what would a SAH-split tree buy the same
+ * collapse + traversal" without a GPU. ---- */
+namespace {
+struct SahBuilder {
+    const float* tris;
+    int bins;
+    std::vector<unsigned> perm;
+    std::vector<float> lo, hi, cen; /* per triangle: box and centroid, 3 floats each */
+    unsigned* order;
+    int *left, *right;
+    float* boxes6;
+    int next_node = 0;
+    unsigned next_pos = 0;
+
+    static float area(const float* b) {
+        float ex = b[3] - b[0], ey = b[4] - b[1], ez = b[5] - b[2];
+        return 2.0f * (ex * ey + ey * ez + ez * ex);
+    }
+    static void grow(float* b, const float* l, const float* h) {
+        for(int k = 0; k < 3; k++) b[k] = fminf(b[k], l[k]), b[3 + k] = fmaxf(b[3 + k], h[k]);
+    }
+    /* builds the subtree over perm[a, b); returns its reference (>= 0 internal node, < 0: ~sorted position) */
+    int build(unsigned a, unsigned b) {
+        if(b - a == 1) {
+            order[next_pos] = perm[a];
+            return ~(int)(next_pos++);
+        }
+        const int me = next_node++;
+        float box[6] = {3e38f, 3e38f, 3e38f, -3e38f, -3e38f, -3e38f}, cb[6] = {3e38f, 3e38f, 3e38f, -3e38f, -3e38f, -3e38f};
+        for(unsigned i = a; i < b; i++) {
+            unsigned g = perm[i];
+            grow(box, &lo[3 * g], &hi[3 * g]);
+            grow(cb, &cen[3 * g], &cen[3 * g]);
+        }
+        for(int k = 0; k < 6; k++) boxes6[6 * me + k] = box[k];
+        int best_axis = -1, best_bin = 0;
+        float best_cost = 3e38f;
+        std::vector<float> bb(6 * bins), acc(6);
+        std::vector<unsigned> cnt(bins);
+        std::vector<float> left_area(bins);
+        std::vector<unsigned> left_cnt(bins);
+        for(int ax = 0; ax < 3; ax++) {
+            float ext = cb[3 + ax] - cb[ax];
+            if(!(ext > 0)) continue;
+            for(int i = 0; i < bins; i++) {
+                cnt[i] = 0;
+                for(int k = 0; k < 3; k++) bb[6 * i + k] = 3e38f, bb[6 * i + 3 + k] = -3e38f;
+            }
+            float scale = (float)bins / ext;
+            for(unsigned i = a; i < b; i++) {
+                unsigned g = perm[i];
+                int bi = std::min(bins - 1, (int)((cen[3 * g + ax] - cb[ax]) * scale));
+                cnt[bi]++;
+                grow(&bb[6 * bi], &lo[3 * g], &hi[3 * g]);
+            }
+            float run[6] = {3e38f, 3e38f, 3e38f, -3e38f, -3e38f, -3e38f};
+            unsigned c = 0;
+            for(int i = 0; i < bins - 1; i++) {
+                if(cnt[i]) grow(run, &bb[6 * i], &bb[6 * i + 3]);
+                c += cnt[i];
+                left_cnt[i] = c, left_area[i] = c ? area(run) : 0.0f;
+            }
+            float rrun[6] = {3e38f, 3e38f, 3e38f, -3e38f, -3e38f, -3e38f};
+            c = 0;
+            for(int i = bins - 1; i > 0; i--) {
+                if(cnt[i]) grow(rrun, &bb[6 * i], &bb[6 * i + 3]);
+                c += cnt[i];
+                if(left_cnt[i - 1] == 0 || c == 0) continue;
+                float cost = left_area[i - 1] * (float)left_cnt[i - 1] + area(rrun) * (float)c;
+                if(cost < best_cost) best_cost = cost, best_axis = ax, best_bin = i;
+            }
+        }
+        unsigned mid;
+        if(best_axis >= 0) {
+            float ext = cb[3 + best_axis] - cb[best_axis], scale = (float)bins / ext;
+            auto it = std::partition(perm.begin() + a, perm.begin() + b, [&](unsigned g) {
+                return std::min(bins - 1, (int)((cen[3 * g + best_axis] - cb[best_axis]) * scale)) < best_bin;
+            });
+            mid = (unsigned)(it - perm.begin());
+        } else
+            mid = a + (b - a) / 2; /* all centroids coincide */
+        if(mid == a || mid == b) mid = a + (b - a) / 2;
+        int l = build(a, mid);
+        int r = build(mid, b);
+        left[me] = l, right[me] = r;
+        return me;
+    }
+};
+} // namespace
+
 extern "C" {
+
+/* Hybrid: keep the Morton LBVH below "cluster roots" (maximal subtrees with at most `cluster` triangles) and rebuild
+ * only the tree ABOVE them by binned SAH over the cluster boxes — what a host-side top-level pass over a few thousand
+ * boxes could do after the GPU LBVH.  in_*: the LBVH (oracle conventions); out_*: the re-assembled tree. */
+namespace {
+struct Hybrid {
+    const unsigned* in_order;
+    const int *in_left, *in_right;
+    const float* in_boxes;
+    const float* tris;
+    int bins;
+    unsigned* order;
+    int *left, *right;
+    float* boxes6;
+    int next_node = 0;
+    unsigned next_pos = 0;
+    struct Item { int ref; float box[6]; float cen[3]; };
+    std::vector<Item> items;
+
+    void ref_box(int ref, float* b) const {
+        if(ref >= 0) {
+            for(int k = 0; k < 6; k++) b[k] = in_boxes[6 * ref + k];
+        } else {
+            const float* t = tris + 9ull * in_order[~ref];
+            for(int k = 0; k < 3; k++) b[k] = fminf(fminf(t[k], t[3 + k]), t[6 + k]), b[3 + k] = fmaxf(fmaxf(t[k], t[3 + k]), t[6 + k]);
+        }
+    }
+    unsigned count(int ref, std::vector<unsigned>& memo) const {
+        if(ref < 0) return 1;
+        if(memo[ref]) return memo[ref];
+        return memo[ref] = count(in_left[ref], memo) + count(in_right[ref], memo);
+    }
+    void collect(int ref, unsigned cluster, std::vector<unsigned>& memo) {
+        if(ref < 0 || count(ref, memo) <= cluster) {
+            Item it;
+            it.ref = ref;
+            ref_box(ref, it.box);
+            for(int k = 0; k < 3; k++) it.cen[k] = (it.box[k] + it.box[3 + k]) * 0.5f;
+            items.push_back(it);
+            return;
+        }
+        collect(in_left[ref], cluster, memo);
+        collect(in_right[ref], cluster, memo);
+    }
+    /* copy an LBVH subtree, renumbering nodes and positions in DFS order */
+    int copy(int ref) {
+        if(ref < 0) {
+            order[next_pos] = in_order[~ref];
+            return ~(int)(next_pos++);
+        }
+        const int me = next_node++;
+        for(int k = 0; k < 6; k++) boxes6[6 * me + k] = in_boxes[6 * ref + k];
+        int l = copy(in_left[ref]);
+        int r = copy(in_right[ref]);
+        left[me] = l, right[me] = r;
+        return me;
+    }
+    int build(unsigned a, unsigned b) {
+        if(b - a == 1) return copy(items[a].ref);
+        const int me = next_node++;
+        float box[6] = {3e38f, 3e38f, 3e38f, -3e38f, -3e38f, -3e38f}, cb[6] = {3e38f, 3e38f, 3e38f, -3e38f, -3e38f, -3e38f};
+        for(unsigned i = a; i < b; i++) SahBuilder::grow(box, items[i].box, items[i].box + 3), SahBuilder::grow(cb, items[i].cen, items[i].cen);
+        for(int k = 0; k < 6; k++) boxes6[6 * me + k] = box[k];
+        int best_axis = -1, best_bin = 0;
+        float best_cost = 3e38f;
+        std::vector<float> bb(6 * bins), left_area(bins);
+        std::vector<unsigned> cnt(bins), left_cnt(bins);
+        for(int ax = 0; ax < 3; ax++) {
+            float ext = cb[3 + ax] - cb[ax];
+            if(!(ext > 0)) continue;
+            for(int i = 0; i < bins; i++) {
+                cnt[i] = 0;
+                for(int k = 0; k < 3; k++) bb[6 * i + k] = 3e38f, bb[6 * i + 3 + k] = -3e38f;
+            }
+            float scale = (float)bins / ext;
+            for(unsigned i = a; i < b; i++) {
+                int bi = std::min(bins - 1, (int)((items[i].cen[ax] - cb[ax]) * scale));
+                cnt[bi]++;
+                SahBuilder::grow(&bb[6 * bi], items[i].box, items[i].box + 3);
+            }
+            float run[6] = {3e38f, 3e38f, 3e38f, -3e38f, -3e38f, -3e38f};
+            unsigned c = 0;
+            for(int i = 0; i < bins - 1; i++) {
+                if(cnt[i]) SahBuilder::grow(run, &bb[6 * i], &bb[6 * i + 3]);
+                c += cnt[i];
+                left_cnt[i] = c, left_area[i] = c ? SahBuilder::area(run) : 0.0f;
+            }
+            float rrun[6] = {3e38f, 3e38f, 3e38f, -3e38f, -3e38f, -3e38f};
+            c = 0;
+            for(int i = bins - 1; i > 0; i--) {
+                if(cnt[i]) SahBuilder::grow(rrun, &bb[6 * i], &bb[6 * i + 3]);
+                c += cnt[i];
+                if(left_cnt[i - 1] == 0 || c == 0) continue;
+                /* clusters hold similar triangle counts, so the item count stands in for the triangle count */
+                float cost = left_area[i - 1] * (float)left_cnt[i - 1] + SahBuilder::area(rrun) * (float)c;
+                if(cost < best_cost) best_cost = cost, best_axis = ax, best_bin = i;
+            }
+        }
+        unsigned mid;
+        if(best_axis >= 0) {
+            float ext = cb[3 + best_axis] - cb[best_axis], scale = (float)bins / ext;
+            auto it = std::stable_partition(items.begin() + a, items.begin() + b, [&](const Item& q) {
+                return std::min(bins - 1, (int)((q.cen[best_axis] - cb[best_axis]) * scale)) < best_bin;
+            });
+            mid = (unsigned)(it - items.begin());
+        } else
+            mid = a + (b - a) / 2;
+        if(mid == a || mid == b) mid = a + (b - a) / 2;
+        int l = build(a, mid);
+        int r = build(mid, b);
+        left[me] = l, right[me] = r;
+        return me;
+    }
+};
+} // namespace
+
+unsigned emu_hybrid_bvh2(const float* tris9, unsigned n, const unsigned* in_order, const int* in_left, const int* in_right,
+                         const float* in_boxes6, unsigned cluster, int bins, unsigned* order, int* left, int* right,
+                         float* boxes6) {
+    Hybrid H;
+    H.tris = tris9, H.in_order = in_order, H.in_left = in_left, H.in_right = in_right, H.in_boxes = in_boxes6;
+    H.bins = bins, H.order = order, H.left = left, H.right = right, H.boxes6 = boxes6;
+    if(n < 2) {
+        if(n) order[0] = in_order[0];
+        return n;
+    }
+    std::vector<unsigned> memo(n - 1, 0);
+    H.collect(0, cluster, memo);
+    H.build(0, (unsigned)H.items.size());
+    return (unsigned)H.items.size();
+}
+
+/* order[n], left/right[n-1], boxes6[6 (n-1)]: same conventions as the oracle's orc_bvh_get_bvh2 */
+void emu_sah_bvh2(const float* tris9, unsigned n, int bins, unsigned* order, int* left, int* right, float* boxes6) {
+    SahBuilder S;
+    S.tris = tris9, S.bins = bins, S.order = order, S.left = left, S.right = right, S.boxes6 = boxes6;
+    S.perm.resize(n), S.lo.resize(3ull * n), S.hi.resize(3ull * n), S.cen.resize(3ull * n);
+    for(unsigned g = 0; g < n; g++) {
+        S.perm[g] = g;
+        const float* t = tris9 + 9ull * g;
+        for(int k = 0; k < 3; k++) {
+            S.lo[3 * g + k] = fminf(fminf(t[k], t[3 + k]), t[6 + k]);
+            S.hi[3 * g + k] = fmaxf(fmaxf(t[k], t[3 + k]), t[6 + k]);
+            S.cen[3 * g + k] = (S.lo[3 * g + k] + S.hi[3 * g + k]) * 0.5f;
+        }
+    }
+    if(n == 1) order[0] = 0;
+    if(n > 1) S.build(0, n);
+}
 
 int g_greedy = 1; /* 1: the greedy largest-area collapse (the default); 0: SAH-optimal collapse (GPURT_BUILD_SAH_COLLAPSE) */
 void emu_set_greedy(int g) { g_greedy = g; }

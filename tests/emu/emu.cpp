@@ -264,6 +264,107 @@ unsigned emu_hybrid_bvh2(const float* tris9, unsigned n, const unsigned* in_orde
     return (unsigned)H.items.size();
 }
 
+/* PLOC (parallel locally-ordered clustering, Meister & Bittner 2018) over the Morton order: every round each cluster
+ * looks `radius` neighbours to each side for the partner with the smallest merged surface area, mutual choices merge.
+ * The GPU-friendly bottom-up alternative to a top-down binned-SAH build: rounds of search / merge / compact kernels
+ * over the array the LBVH sort already produces.  The tree is renumbered depth-first at the end so that every node
+ * covers a contiguous range of `order`, as the collapse expects. */
+unsigned emu_ploc_bvh2(const float* tris9, unsigned n, const unsigned* morton_order, int radius, unsigned* order, int* left,
+                       int* right, float* boxes6) {
+    if(n < 2) {
+        if(n) order[0] = morton_order[0];
+        return 0;
+    }
+    struct Cl { int ref; float box[6]; };
+    std::vector<Cl> cur(n), nxt;
+    for(unsigned i = 0; i < n; i++) {
+        unsigned g = morton_order[i];
+        const float* t = tris9 + 9ull * g;
+        cur[i].ref = ~(int)g;
+        for(int k = 0; k < 3; k++)
+            cur[i].box[k] = fminf(fminf(t[k], t[3 + k]), t[6 + k]), cur[i].box[3 + k] = fmaxf(fmaxf(t[k], t[3 + k]), t[6 + k]);
+    }
+    std::vector<int> tl(n - 1), tr(n - 1); /* temporary tree: refs >= 0 internal (creation order), < 0: ~gid */
+    std::vector<float> tb(6ull * (n - 1));
+    int made = 0;
+    unsigned rounds = 0;
+    std::vector<int> nn;
+    while(cur.size() > 1) {
+        const int m = (int)cur.size();
+        nn.assign(m, -1);
+        for(int i = 0; i < m; i++) {
+            float best = 3e38f;
+            for(int j = std::max(0, i - radius); j <= std::min(m - 1, i + radius); j++) {
+                if(j == i) continue;
+                float b[6];
+                for(int k = 0; k < 3; k++) b[k] = fminf(cur[i].box[k], cur[j].box[k]), b[3 + k] = fmaxf(cur[i].box[3 + k], cur[j].box[3 + k]);
+                float a = SahBuilder::area(b);
+                if(a < best) best = a, nn[i] = j;
+            }
+        }
+        nxt.clear();
+        for(int i = 0; i < m; i++) {
+            int j = nn[i];
+            if(nn[j] == i) {
+                if(i < j) {
+                    Cl c;
+                    c.ref = made;
+                    for(int k = 0; k < 3; k++) c.box[k] = fminf(cur[i].box[k], cur[j].box[k]), c.box[3 + k] = fmaxf(cur[i].box[3 + k], cur[j].box[3 + k]);
+                    tl[made] = cur[i].ref, tr[made] = cur[j].ref;
+                    for(int k = 0; k < 6; k++) tb[6ull * made + k] = c.box[k];
+                    made++;
+                    nxt.push_back(c);
+                }
+            } else
+                nxt.push_back(cur[i]);
+        }
+        cur.swap(nxt);
+        rounds++;
+    }
+    /* depth-first renumbering from the root (the last node made) */
+    int next_node = 0;
+    unsigned next_pos = 0;
+    struct Fr { int ref; int me; int phase; };
+    std::vector<Fr> st;
+    std::vector<int> newid(n - 1, -1);
+    /* first pass: assign new ids in preorder, positions to leaves in left-to-right order */
+    std::vector<int> stack{cur[0].ref};
+    std::vector<int> pre;
+    while(!stack.empty()) {
+        int r = stack.back();
+        stack.pop_back();
+        if(r < 0) {
+            order[next_pos++] = (unsigned)~r;
+            continue;
+        }
+        newid[r] = next_node++;
+        stack.push_back(tr[r]);
+        stack.push_back(tl[r]);
+    }
+    /* second pass: leaf refs become positions; walk again in the same order to number them */
+    next_pos = 0;
+    stack.assign(1, cur[0].ref);
+    std::vector<std::pair<int, int>> fix; /* (new node, side) waiting for a leaf position */
+    std::vector<std::pair<int, int>> parent_slot{{-1, 0}};
+    std::vector<std::pair<int, int>> pstack{{-1, 0}};
+    while(!stack.empty()) {
+        int r = stack.back();
+        stack.pop_back();
+        std::pair<int, int> ps = pstack.back();
+        pstack.pop_back();
+        int ref_out;
+        if(r < 0) ref_out = ~(int)(next_pos++);
+        else {
+            ref_out = newid[r];
+            for(int k = 0; k < 6; k++) boxes6[6ull * ref_out + k] = tb[6ull * r + k];
+            stack.push_back(tr[r]), pstack.push_back({ref_out, 1});
+            stack.push_back(tl[r]), pstack.push_back({ref_out, 0});
+        }
+        if(ps.first >= 0) (ps.second ? right : left)[ps.first] = ref_out;
+    }
+    return rounds;
+}
+
 /* order[n], left/right[n-1], boxes6[6 (n-1)]: same conventions as the oracle's orc_bvh_get_bvh2 */
 void emu_sah_bvh2(const float* tris9, unsigned n, int bins, unsigned* order, int* left, int* right, float* boxes6) {
     SahBuilder S;

@@ -43,7 +43,8 @@ def main():
     ap.add_argument("--bins", type=int, default=16)
     ap.add_argument("--rays", type=int, default=200000)
     ap.add_argument("--scenes", nargs="*", default=["cbox", "mis_test", "sponza_standin"])
-    ap.add_argument("--clusters", type=int, nargs="*", default=[8, 64, 512])
+    ap.add_argument("--clusters", type=int, nargs="*", default=[8, 64])
+    ap.add_argument("--ploc", type=int, nargs="*", default=[8, 32])
     args = ap.parse_args()
     emu = C.CDLL(os.path.join(ROOT, "tests", "emu", "libemu.so"))
     emu.emu_build.restype = C.c_void_p
@@ -64,6 +65,13 @@ def main():
         emu.emu_sah_bvh2(vp(tris), n, args.bins, vp(order), vp(sl), vp(sr), vp(sbx))
         assert sorted(order.tolist()) == list(range(n))
         trees["binned_sah"] = (order, sl, sr, sbx)
+        for radius in args.ploc:        # PLOC over the Morton order
+            po = np.zeros(n, np.uint32)
+            pl, pr_, pb = np.zeros(n - 1, np.int32), np.zeros(n - 1, np.int32), np.zeros((n - 1, 6), np.float32)
+            rounds = emu.emu_ploc_bvh2(vp(tris), n, vp(trees["lbvh"][0]), radius, vp(po), vp(pl), vp(pr_), vp(pb))
+            assert sorted(po.tolist()) == list(range(n))
+            trees[f"ploc_r{radius}"] = (po, pl, pr_, pb)
+            print(f"{name}: PLOC radius {radius}: {rounds} rounds", file=sys.stderr)
         for cluster in args.clusters:   # Morton subtrees of <= cluster triangles under a binned-SAH top tree
             ho = np.zeros(n, np.uint32)
             hl, hr, hb = np.zeros(n - 1, np.int32), np.zeros(n - 1, np.int32), np.zeros((n - 1, 6), np.float32)
@@ -89,7 +97,11 @@ def main():
         sets["bounce"] = br
         res = {"tris": n}
         ref = {}
-        for tname, (o, tl, tr, tb) in trees.items():
+        variants = [(t, 1) for t in trees] + [(t, 0) for t in ("lbvh", "binned_sah")]
+        for tname, greedy in variants:
+            o, tl, tr, tb = trees[tname]
+            emu.emu_set_greedy(greedy)   # 0: the SAH-optimal wide collapse (GPURT_BUILD_SAH_COLLAPSE)
+            tname = tname if greedy else tname + "+dp_collapse"
             hnd = C.c_void_p(emu.emu_build(vp(tris), n, vp(o), vp(tl), vp(tr), vp(np.ascontiguousarray(tb)), C.c_float(inflate)))
             assert emu.emu_depth(hnd) < 60, "too deep for the traversal stack"
             e = {"wide_nodes": int(emu.emu_n_nodes(hnd)), "wide_depth": int(emu.emu_depth(hnd))}
@@ -102,6 +114,7 @@ def main():
                     assert (ref[sname] == hits).all(), "the two trees disagree on a hit"
                 ref[sname] = hits
             emu.emu_free(hnd)
+            emu.emu_set_greedy(1)
             res[tname] = e
         out[name] = res
     print(json.dumps(out, indent=1))

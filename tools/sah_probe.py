@@ -113,6 +113,15 @@ def main():
                 if sname in ref:
                     assert (ref[sname] == hits).all(), "the two trees disagree on a hit"
                 ref[sname] = hits
+            q = orc.gen_random_points(min(args.rays, 100000), 0xFACADE, b.scene_box())
+            cres, ccnt = np.zeros((len(q), 8), np.uint32), np.zeros(2, np.uint64)
+            emu.emu_cpq_counts(vp(ccnt))                       # reset
+            emu.emu_cpq(hnd, vp(q), C.c_ulonglong(len(q)), vp(cres))
+            emu.emu_cpq_counts(vp(ccnt))
+            e["closest_point"] = {"queries": len(q), "nodes_per_query": float(ccnt[0]) / len(q), "tris_per_query": float(ccnt[1]) / len(q)}
+            if "cpq" in ref:
+                assert (ref["cpq"][:, 3] == cres[:, 3]).all(), "the two trees disagree on a closest-point distance"
+            ref["cpq"] = cres
             emu.emu_free(hnd)
             emu.emu_set_greedy(1)
             res[tname] = e

@@ -115,3 +115,42 @@ def test_adversarial_inputs(emu, orc):
     assert (cref == cbrute).all(), f"oracle BVH vs brute force: queries {np.nonzero((cref != cbrute).any(1))[0][:10]}"
     assert (res == cref).all(), f"BVH8 vs oracle: queries {np.nonzero((res != cref).any(1))[0][:10]}"
     emu.emu_free(h)
+
+
+def test_experimental_trees_give_the_same_hits(emu, orc):
+    """tools/sah_probe.py's binary trees (binned SAH, PLOC, SAH top over Morton clusters) through the product's
+    collapse + traversal: any valid tree must give the oracle's hits and closest points"""
+    tris = soup(3000, seed=77, ext=0.08)
+    n = len(tris)
+    b = orc.Bvh(tris)
+    l, r, bx = b.bvh2()
+    inflate = np.float32(max(1e-30, np.abs(b.scene_box()).max()) * 2.0 ** -19)
+    rays = orc.gen_random_rays(20000, 0xC0FFEE, b.scene_box())
+    want = b.closest_hit(rays).view(np.uint32).reshape(-1, 4)
+    q = orc.gen_random_points(5000, 0xFACADE, b.scene_box())
+    want_cp = b.closest_point(q).view(np.uint32).reshape(-1, 8)
+
+    def arrays():
+        return np.zeros(n, np.uint32), np.zeros(n - 1, np.int32), np.zeros(n - 1, np.int32), np.zeros((n - 1, 6), np.float32)
+    trees = []
+    o, tl, tr, tb = arrays()
+    emu.emu_sah_bvh2(_vp(tris), n, 16, _vp(o), _vp(tl), _vp(tr), _vp(tb))
+    trees.append((o, tl, tr, tb))
+    o, tl, tr, tb = arrays()
+    emu.emu_ploc_bvh2(_vp(tris), n, _vp(b.prim_order()), 8, _vp(o), _vp(tl), _vp(tr), _vp(tb))
+    trees.append((o, tl, tr, tb))
+    o, tl, tr, tb = arrays()
+    emu.emu_hybrid_bvh2(_vp(tris), n, _vp(b.prim_order()), _vp(l), _vp(r), _vp(np.ascontiguousarray(bx)), 64, 16, _vp(o), _vp(tl),
+                        _vp(tr), _vp(tb))
+    trees.append((o, tl, tr, tb))
+    for o, tl, tr, tb in trees:
+        assert sorted(o.tolist()) == list(range(n))
+        h = C.c_void_p(emu.emu_build(_vp(tris), n, _vp(o), _vp(tl), _vp(tr), _vp(tb), C.c_float(inflate)))
+        assert emu.emu_depth(h) < 60
+        hits, cnt = np.zeros((len(rays), 4), np.uint32), np.zeros(4, np.uint64)
+        emu.emu_trace(h, _vp(rays), C.c_ulonglong(len(rays)), _vp(hits), None, _vp(cnt))
+        assert (hits == want).all()
+        res = np.zeros((len(q), 8), np.uint32)
+        emu.emu_cpq(h, _vp(q), C.c_ulonglong(len(q)), _vp(res))
+        assert (res == want_cp).all()
+        emu.emu_free(h)

@@ -21,6 +21,7 @@
 #include <cstdlib>
 #include <cstring>
 
+#include "../host/sah_split.h"
 #include "device.cuh"
 
 namespace gpurt {
@@ -692,10 +693,35 @@ int build_accel_device(gpurt_accel* A) {
     float ext[3] = {sb[3] - sb[0], sb[4] - sb[1], sb[5] - sb[2]}, inv[3];
     for(int k = 0; k < 3; k++) inv[k] = ext[k] > 0 ? 1.0f / ext[k] : 0.0f;
 
-    /* keys + sort */
-    k_morton<<<cdiv(n, 256), 256, 0, st>>>(A->tri_lo, A->tri_hi, n, sb[0], sb[1], sb[2], inv[0], inv[1],
-                                          inv[2], A->keys, A->order);
-    TRY(radix_sort_u64(st, A->keys, A->order, keys_tmp, vals_tmp, n, 8, ctx->scratch, ctx->sm_count));
+    const bool sah_split = (A->flags & GPURT_BUILD_SAH_SPLIT) != 0;
+    if(!sah_split) {
+        /* keys + sort */
+        k_morton<<<cdiv(n, 256), 256, 0, st>>>(A->tri_lo, A->tri_hi, n, sb[0], sb[1], sb[2], inv[0], inv[1],
+                                              inv[2], A->keys, A->order);
+        TRY(radix_sort_u64(st, A->keys, A->order, keys_tmp, vals_tmp, n, 8, ctx->scratch, ctx->sm_count));
+    } else {
+        /* GPURT_BUILD_SAH_SPLIT: primitive order and binary topology from the host-side binned-SAH definition
+         * (host/sah_split.h) over the boxes k_flatten just wrote; everything after it (refit, collapse, node encoding,
+         * triangle re-layout) is the same device code */
+        std::vector<float> h_lo(4ull * n), h_hi(4ull * n);
+        GPURT_CUDA(cudaMemcpyAsync(h_lo.data(), A->tri_lo, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
+        GPURT_CUDA(cudaMemcpyAsync(h_hi.data(), A->tri_hi, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
+        GPURT_CUDA(cudaStreamSynchronize(st));
+        SahSplitTree T;
+        build_sah_split(h_lo.data(), h_hi.data(), 4, n, T);
+        std::vector<uint64_t> h_keys(n);
+        for(unsigned i = 0; i < n; i++) h_keys[i] = i; /* the "key" of a primitive is its position in the SAH order */
+        GPURT_CUDA(cudaMemcpyAsync(A->order, T.order.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+        GPURT_CUDA(cudaMemcpyAsync(A->keys, h_keys.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st));
+        if(ni) {
+            GPURT_CUDA(cudaMemcpyAsync(A->left, T.left.data(), (size_t)ni * 4, cudaMemcpyHostToDevice, st));
+            GPURT_CUDA(cudaMemcpyAsync(A->right, T.right.data(), (size_t)ni * 4, cudaMemcpyHostToDevice, st));
+            GPURT_CUDA(cudaMemcpyAsync(parent, T.parent.data(), ((size_t)ni + n) * 4, cudaMemcpyHostToDevice, st));
+            GPURT_CUDA(cudaMemcpyAsync(range_first, T.range_first.data(), (size_t)ni * 4, cudaMemcpyHostToDevice, st));
+            GPURT_CUDA(cudaMemcpyAsync(range_last, T.range_last.data(), (size_t)ni * 4, cudaMemcpyHostToDevice, st));
+        }
+        GPURT_CUDA(cudaStreamSynchronize(st)); /* the host vectors go out of scope */
+    }
 
     /* binary tree */
     Bvh2View B;
@@ -706,7 +732,8 @@ int build_accel_device(gpurt_accel* A) {
     unsigned* arrive = (unsigned*)vals_tmp; /* the sort is done with it */
     if(ni) {
         GPURT_CUDA(cudaMemsetAsync(arrive, 0, (size_t)ni * 4, st));
-        k_karras<<<cdiv(ni, 256), 256, 0, st>>>(A->keys, (int)n, A->left, A->right, parent, range_first, range_last);
+        if(!sah_split)
+            k_karras<<<cdiv(ni, 256), 256, 0, st>>>(A->keys, (int)n, A->left, A->right, parent, range_first, range_last);
         if(sah)
             k_refit<true><<<cdiv(n, 256), 256, 0, st>>>((int)n, A->left, A->right, parent, A->order, A->tri_lo, A->tri_hi,
                                                        A->node_lo, A->node_hi, arrive, B, dp_cost, dp_dec);

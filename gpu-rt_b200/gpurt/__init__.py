@@ -18,7 +18,7 @@ LIB_PATH = os.environ.get("GPURT_LIB") or os.path.join(os.path.dirname(_HERE), "
 
 MEM_HOST, MEM_DEVICE = 0, 1
 NO_HIT = 0xFFFFFFFF
-BUILD_DEFAULT, BUILD_KEEP_BVH2, BUILD_SAH_COLLAPSE = 0, 1, 2
+BUILD_DEFAULT, BUILD_KEEP_BVH2, BUILD_SAH_COLLAPSE, BUILD_SAH_SPLIT = 0, 1, 2, 4
 
 RAY_DT = np.dtype([("o", "<f4", 3), ("tmin", "<f4"), ("d", "<f4", 3), ("tmax", "<f4")])
 HIT_DT = np.dtype([("t", "<f4"), ("u", "<f4"), ("v", "<f4"), ("prim", "<u4")])
@@ -322,6 +322,9 @@ class Accel:
         self.scene = scene
         self.ctx = scene.ctx
         self.h = C.c_void_p()
+        # GPURT_BUILD_FLAGS (binding only): OR extra build flags into every Accel of a tool run, for A/B measurements
+        # of GPURT_BUILD_SAH_COLLAPSE (2) / GPURT_BUILD_SAH_SPLIT (4) without editing the tools
+        flags |= int(os.environ.get("GPURT_BUILD_FLAGS", "0"))
         _check(lib.gpurt_accel_build(scene.h, flags, C.byref(self.h)))
 
     def update(self):

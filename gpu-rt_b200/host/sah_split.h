@@ -1,0 +1,153 @@
+/*
+ * sah_split.h — top-down binned-SAH binary tree over triangle boxes (GPURT_BUILD_SAH_SPLIT), host side.
+ *
+ * The default build orders primitives along a Morton curve (contract N6) because that is a sort plus two linear
+ * passes on the GPU.  On real meshes a tree split by the surface-area heuristic is visited about 30 % less per ray
+ * (tools/sah_probe.py), so a static scene — the reference's use case: BLAS built once with
+ * PREFER_FAST_TRACE, src/vk/vulkan.cpp:881-936 — can ask for one.  This header is the *definition* of that tree, written
+ * so that a parallel builder can reproduce it bit for bit: every reduction is a min / max or an integer count (order
+ * independent), every partition is stable, every float expression is written out and compiled without contraction.
+ *
+ *   items      triangles, initially in global primitive id order
+ *   box(t)     the world-space AABB k_flatten wrote (tri_lo / tri_hi), centroid c(t) = (lo + hi) * 0.5f (as in N6)
+ *   node(S)    cb = centroid bounds of S.  For axis = x, y, z with ext = cb.hi - cb.lo > 0:
+ *                bin(t) = min(BINS - 1, (int)((c(t)[axis] - cb.lo[axis]) * ((float)BINS / ext)))
+ *                for each boundary k = 1..BINS-1 with both sides non-empty:
+ *                  cost = area(union of bins < k) * count(bins < k) + area(union of bins >= k) * count(bins >= k)
+ *              area(b) = 2 * (ex * ey + ey * ez + ez * ex);  the lowest cost wins, ties -> lower axis, then lower k.
+ *              S is stably partitioned into bins < k | bins >= k.  No axis with ext > 0: split at the middle.
+ *   leaves     single triangles; nodes are numbered in preorder (root 0), leaf positions in depth-first order.
+ * Output conventions are those of the LBVH stage (build.cu k_karras): child >= 0 inner node, < 0: ~sorted position.
+ */
+#pragma once
+#include <algorithm>
+#include <cstdint>
+#include <vector>
+
+namespace gpurt {
+
+struct SahSplitTree {
+    std::vector<uint32_t> order;                 /* sorted position -> primitive id */
+    std::vector<int> left, right;                /* n - 1 inner nodes */
+    std::vector<int> parent;                     /* [n - 1 inner | n leaf positions], root -1 */
+    std::vector<int> range_first, range_last;    /* sorted positions covered by each inner node */
+    unsigned depth = 0;
+};
+
+namespace sah_detail {
+constexpr int kBins = 16;
+struct Box {
+    float lo[3], hi[3];
+};
+inline Box empty_box() { return Box{{3.0e38f, 3.0e38f, 3.0e38f}, {-3.0e38f, -3.0e38f, -3.0e38f}}; }
+inline void grow(Box& b, const float* lo, const float* hi) {
+    for(int k = 0; k < 3; k++) b.lo[k] = std::min(b.lo[k], lo[k]), b.hi[k] = std::max(b.hi[k], hi[k]);
+}
+inline float area(const Box& b) {
+    float ex = b.hi[0] - b.lo[0], ey = b.hi[1] - b.lo[1], ez = b.hi[2] - b.lo[2];
+    return 2.0f * (ex * ey + ey * ez + ez * ex);
+}
+} // namespace sah_detail
+
+/* tri_lo / tri_hi: n records of `stride` floats, xyz first (the float4 arrays of the accel) */
+inline void build_sah_split(const float* tri_lo, const float* tri_hi, size_t stride, uint32_t n, SahSplitTree& T) {
+    using namespace sah_detail;
+    T = SahSplitTree();
+    T.order.resize(n);
+    if(n == 0) return;
+    if(n == 1) {
+        T.order[0] = 0;
+        T.parent.assign(1, -1);
+        return;
+    }
+    const uint32_t ni = n - 1;
+    T.left.resize(ni), T.right.resize(ni), T.range_first.resize(ni), T.range_last.resize(ni);
+    T.parent.assign((size_t)ni + n, -1);
+    std::vector<uint32_t> items(n), scratch(n);
+    std::vector<float> cen(3ull * n);
+    for(uint32_t g = 0; g < n; g++) {
+        items[g] = g;
+        for(int k = 0; k < 3; k++) cen[3ull * g + k] = (tri_lo[stride * g + k] + tri_hi[stride * g + k]) * 0.5f;
+    }
+    struct Job {
+        uint32_t a, b; /* segment of `items` */
+        int parent;    /* inner node that waits for this subtree, -1 for the root */
+        int side;      /* 0 left, 1 right */
+        unsigned depth;
+    };
+    /* explicit stack, right child pushed first: nodes come out in preorder, leaves left to right */
+    std::vector<Job> stack{{0, n, -1, 0, 1}};
+    int next_node = 0;
+    uint32_t next_pos = 0;
+    while(!stack.empty()) {
+        const Job j = stack.back();
+        stack.pop_back();
+        int ref;
+        if(j.b - j.a == 1) {
+            T.order[next_pos] = items[j.a];
+            T.parent[(size_t)ni + next_pos] = j.parent;
+            ref = ~(int)next_pos;
+            next_pos++;
+        } else {
+            const int me = next_node++;
+            ref = me;
+            T.parent[me] = j.parent;
+            T.depth = std::max(T.depth, j.depth);
+            /* positions are handed out depth-first, so this subtree will cover [next_pos, next_pos + count) */
+            T.range_first[me] = (int)next_pos, T.range_last[me] = (int)(next_pos + (j.b - j.a) - 1);
+            Box cb = empty_box();
+            for(uint32_t i = j.a; i < j.b; i++) grow(cb, &cen[3ull * items[i]], &cen[3ull * items[i]]);
+            int best_axis = -1, best_k = 0;
+            float best_cost = 3.0e38f;
+            for(int ax = 0; ax < 3; ax++) {
+                const float ext = cb.hi[ax] - cb.lo[ax];
+                if(!(ext > 0.0f)) continue;
+                const float scale = (float)kBins / ext;
+                Box bb[kBins];
+                uint32_t cnt[kBins];
+                for(int k = 0; k < kBins; k++) bb[k] = empty_box(), cnt[k] = 0;
+                for(uint32_t i = j.a; i < j.b; i++) {
+                    const uint32_t g = items[i];
+                    const int bi = std::min(kBins - 1, (int)((cen[3ull * g + ax] - cb.lo[ax]) * scale));
+                    cnt[bi]++;
+                    grow(bb[bi], tri_lo + stride * g, tri_hi + stride * g);
+                }
+                float right_area[kBins];
+                uint32_t right_cnt[kBins];
+                Box run = empty_box();
+                uint32_t c = 0;
+                for(int k = kBins - 1; k >= 1; k--) {
+                    if(cnt[k]) grow(run, bb[k].lo, bb[k].hi);
+                    c += cnt[k];
+                    right_cnt[k] = c, right_area[k] = c ? area(run) : 0.0f;
+                }
+                run = empty_box(), c = 0;
+                for(int k = 1; k < kBins; k++) {
+                    if(cnt[k - 1]) grow(run, bb[k - 1].lo, bb[k - 1].hi);
+                    c += cnt[k - 1];
+                    if(c == 0 || right_cnt[k] == 0) continue;
+                    const float cost = area(run) * (float)c + right_area[k] * (float)right_cnt[k];
+                    if(cost < best_cost) best_cost = cost, best_axis = ax, best_k = k;
+                }
+            }
+            uint32_t mid = j.a + (j.b - j.a) / 2;
+            if(best_axis >= 0) {
+                const float lo = cb.lo[best_axis], scale = (float)kBins / (cb.hi[best_axis] - cb.lo[best_axis]);
+                uint32_t nl = 0, nr = 0;
+                for(uint32_t i = j.a; i < j.b; i++) { /* stable partition through the scratch array */
+                    const uint32_t g = items[i];
+                    const int bi = std::min(kBins - 1, (int)((cen[3ull * g + best_axis] - lo) * scale));
+                    if(bi < best_k) items[j.a + nl++] = g;
+                    else scratch[nr++] = g;
+                }
+                for(uint32_t i = 0; i < nr; i++) items[j.a + nl + i] = scratch[i];
+                mid = j.a + nl; /* both sides are non-empty by construction of best_k */
+            }
+            stack.push_back(Job{mid, j.b, me, 1, j.depth + 1});
+            stack.push_back(Job{j.a, mid, me, 0, j.depth + 1});
+        }
+        if(j.parent >= 0) (j.side ? T.right : T.left)[j.parent] = ref;
+    }
+}
+
+} // namespace gpurt

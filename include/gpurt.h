@@ -204,6 +204,13 @@ int gpurt_camera_make(int mode, float width, float height, const float pos[3],
  * greedy largest-area rule.  Same query results.  Measured on the Sponza stand-in: 31 % fewer wide nodes, primary
  * rays +5 %, bounce rays -3 %, closest-point queries -15 %, build +15..40 % — an option for camera-ray-heavy use. */
 #define GPURT_BUILD_SAH_COLLAPSE 2u
+/* EXPERIMENTAL (built and checked on the CPU replay at the end of round 1, not yet run on a GPU): primitive order and
+ * binary topology from a top-down binned-SAH split computed on the host (gpu-rt_b200/host/sah_split.h) instead of the
+ * Morton sort; refit, wide collapse and traversal unchanged, query results unchanged.  For static scenes with real
+ * meshes: about 30 % fewer node visits per ray on media/cbox in the CPU probe (tools/sah_probe.py), nothing on
+ * regular procedural geometry; the host pass costs ~13 ms per 16 k triangles, 270 ms per 262 k.  Composes with
+ * GPURT_BUILD_SAH_COLLAPSE.  gpurt_accel_get_morton_keys returns positions 0..n-1 in this mode. */
+#define GPURT_BUILD_SAH_SPLIT 4u
 int gpurt_accel_build(gpurt_scene* scene, uint32_t flags, gpurt_accel** out);
 /* Rebuild after scene edits (GPURT::build_accel with rebuild_tlas / rebuild_blas, src/gpurt.cpp:220-241).
  * Pose-only edits re-upload the 208-byte Scene_Desc records and rebuild on the device in the buffers

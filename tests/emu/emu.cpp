@@ -12,6 +12,7 @@
 #include <thread>
 
 #include "../../gpu-rt_b200/csrc/shade.cuh"
+#include "../../gpu-rt_b200/host/sah_split.h"
 
 using namespace gpurt;
 
@@ -40,93 +41,16 @@ static void fill_ranges(const int* left, const int* right, int node, std::vector
     }
 }
 
-/* ---- experiment support: a top-down binned-SAH binary tree in the layout emu_build() takes (tools/sah_probe.py).
- * Not a product path: the shipped build is the Morton LBVH; this answers "what would a SAH-split tree buy the same
- * collapse + traversal" without a GPU. ---- */
+/* ---- experiment support for tools/sah_probe.py: alternative binary trees in the layout emu_build() takes, to answer
+ * "what would this tree buy the same collapse + traversal" without a GPU. ---- */
 namespace {
-struct SahBuilder {
-    const float* tris;
-    int bins;
-    std::vector<unsigned> perm;
-    std::vector<float> lo, hi, cen; /* per triangle: box and centroid, 3 floats each */
-    unsigned* order;
-    int *left, *right;
-    float* boxes6;
-    int next_node = 0;
-    unsigned next_pos = 0;
-
+struct SahBuilder { /* box helpers of the experimental builders below */
     static float area(const float* b) {
         float ex = b[3] - b[0], ey = b[4] - b[1], ez = b[5] - b[2];
         return 2.0f * (ex * ey + ey * ez + ez * ex);
     }
     static void grow(float* b, const float* l, const float* h) {
         for(int k = 0; k < 3; k++) b[k] = fminf(b[k], l[k]), b[3 + k] = fmaxf(b[3 + k], h[k]);
-    }
-    /* builds the subtree over perm[a, b); returns its reference (>= 0 internal node, < 0: ~sorted position) */
-    int build(unsigned a, unsigned b) {
-        if(b - a == 1) {
-            order[next_pos] = perm[a];
-            return ~(int)(next_pos++);
-        }
-        const int me = next_node++;
-        float box[6] = {3e38f, 3e38f, 3e38f, -3e38f, -3e38f, -3e38f}, cb[6] = {3e38f, 3e38f, 3e38f, -3e38f, -3e38f, -3e38f};
-        for(unsigned i = a; i < b; i++) {
-            unsigned g = perm[i];
-            grow(box, &lo[3 * g], &hi[3 * g]);
-            grow(cb, &cen[3 * g], &cen[3 * g]);
-        }
-        for(int k = 0; k < 6; k++) boxes6[6 * me + k] = box[k];
-        int best_axis = -1, best_bin = 0;
-        float best_cost = 3e38f;
-        std::vector<float> bb(6 * bins), acc(6);
-        std::vector<unsigned> cnt(bins);
-        std::vector<float> left_area(bins);
-        std::vector<unsigned> left_cnt(bins);
-        for(int ax = 0; ax < 3; ax++) {
-            float ext = cb[3 + ax] - cb[ax];
-            if(!(ext > 0)) continue;
-            for(int i = 0; i < bins; i++) {
-                cnt[i] = 0;
-                for(int k = 0; k < 3; k++) bb[6 * i + k] = 3e38f, bb[6 * i + 3 + k] = -3e38f;
-            }
-            float scale = (float)bins / ext;
-            for(unsigned i = a; i < b; i++) {
-                unsigned g = perm[i];
-                int bi = std::min(bins - 1, (int)((cen[3 * g + ax] - cb[ax]) * scale));
-                cnt[bi]++;
-                grow(&bb[6 * bi], &lo[3 * g], &hi[3 * g]);
-            }
-            float run[6] = {3e38f, 3e38f, 3e38f, -3e38f, -3e38f, -3e38f};
-            unsigned c = 0;
-            for(int i = 0; i < bins - 1; i++) {
-                if(cnt[i]) grow(run, &bb[6 * i], &bb[6 * i + 3]);
-                c += cnt[i];
-                left_cnt[i] = c, left_area[i] = c ? area(run) : 0.0f;
-            }
-            float rrun[6] = {3e38f, 3e38f, 3e38f, -3e38f, -3e38f, -3e38f};
-            c = 0;
-            for(int i = bins - 1; i > 0; i--) {
-                if(cnt[i]) grow(rrun, &bb[6 * i], &bb[6 * i + 3]);
-                c += cnt[i];
-                if(left_cnt[i - 1] == 0 || c == 0) continue;
-                float cost = left_area[i - 1] * (float)left_cnt[i - 1] + area(rrun) * (float)c;
-                if(cost < best_cost) best_cost = cost, best_axis = ax, best_bin = i;
-            }
-        }
-        unsigned mid;
-        if(best_axis >= 0) {
-            float ext = cb[3 + best_axis] - cb[best_axis], scale = (float)bins / ext;
-            auto it = std::partition(perm.begin() + a, perm.begin() + b, [&](unsigned g) {
-                return std::min(bins - 1, (int)((cen[3 * g + best_axis] - cb[best_axis]) * scale)) < best_bin;
-            });
-            mid = (unsigned)(it - perm.begin());
-        } else
-            mid = a + (b - a) / 2; /* all centroids coincide */
-        if(mid == a || mid == b) mid = a + (b - a) / 2;
-        int l = build(a, mid);
-        int r = build(mid, b);
-        left[me] = l, right[me] = r;
-        return me;
     }
 };
 } // namespace
@@ -365,22 +289,76 @@ unsigned emu_ploc_bvh2(const float* tris9, unsigned n, const unsigned* morton_or
     return rounds;
 }
 
-/* order[n], left/right[n-1], boxes6[6 (n-1)]: same conventions as the oracle's orc_bvh_get_bvh2 */
-void emu_sah_bvh2(const float* tris9, unsigned n, int bins, unsigned* order, int* left, int* right, float* boxes6) {
-    SahBuilder S;
-    S.tris = tris9, S.bins = bins, S.order = order, S.left = left, S.right = right, S.boxes6 = boxes6;
-    S.perm.resize(n), S.lo.resize(3ull * n), S.hi.resize(3ull * n), S.cen.resize(3ull * n);
+/* The product's SAH-split tree (host/sah_split.h, GPURT_BUILD_SAH_SPLIT) in the arrays emu_build() takes:
+ * order[n], left/right[n-1], boxes6[6 (n-1)] — same conventions as the oracle's orc_bvh_get_bvh2.  `bins` is ignored
+ * (the definition fixes 16).  Returns the depth of the binary tree. */
+unsigned emu_sah_bvh2(const float* tris9, unsigned n, int bins, unsigned* order, int* left, int* right, float* boxes6) {
+    (void)bins;
+    std::vector<float> lo(4ull * n), hi(4ull * n);
     for(unsigned g = 0; g < n; g++) {
-        S.perm[g] = g;
         const float* t = tris9 + 9ull * g;
         for(int k = 0; k < 3; k++) {
-            S.lo[3 * g + k] = fminf(fminf(t[k], t[3 + k]), t[6 + k]);
-            S.hi[3 * g + k] = fmaxf(fmaxf(t[k], t[3 + k]), t[6 + k]);
-            S.cen[3 * g + k] = (S.lo[3 * g + k] + S.hi[3 * g + k]) * 0.5f;
+            lo[4ull * g + k] = fminf(fminf(t[k], t[3 + k]), t[6 + k]);
+            hi[4ull * g + k] = fmaxf(fmaxf(t[k], t[3 + k]), t[6 + k]);
         }
     }
-    if(n == 1) order[0] = 0;
-    if(n > 1) S.build(0, n);
+    SahSplitTree T;
+    build_sah_split(lo.data(), hi.data(), 4, n, T);
+    for(unsigned i = 0; i < n; i++) order[i] = T.order[i];
+    if(n < 2) return 0;
+    /* node boxes = exact unions, children before parents: preorder numbering means children have larger ids */
+    for(int i = (int)n - 2; i >= 0; i--) {
+        left[i] = T.left[i], right[i] = T.right[i];
+        float* b = boxes6 + 6ull * i;
+        for(int k = 0; k < 3; k++) b[k] = 3e38f, b[3 + k] = -3e38f;
+        for(int c : {T.left[i], T.right[i]}) {
+            const float *cl, *ch;
+            if(c >= 0) cl = boxes6 + 6ull * c, ch = cl + 3;
+            else cl = &lo[4ull * T.order[~c]], ch = &hi[4ull * T.order[~c]];
+            for(int k = 0; k < 3; k++) b[k] = fminf(b[k], cl[k]), b[3 + k] = fmaxf(b[3 + k], ch[k]);
+        }
+    }
+    return T.depth;
+}
+
+/* consistency of every array build_sah_split() hands to the device stages: 0 = fine, else the number of the failed check */
+int emu_sah_split_check(const float* tris9, unsigned n) {
+    std::vector<float> lo(4ull * n), hi(4ull * n);
+    for(unsigned g = 0; g < n; g++)
+        for(int k = 0; k < 3; k++) {
+            const float* t = tris9 + 9ull * g;
+            lo[4ull * g + k] = fminf(fminf(t[k], t[3 + k]), t[6 + k]), hi[4ull * g + k] = fmaxf(fmaxf(t[k], t[3 + k]), t[6 + k]);
+        }
+    SahSplitTree T, U;
+    build_sah_split(lo.data(), hi.data(), 4, n, T);
+    build_sah_split(lo.data(), hi.data(), 4, n, U);
+    if(T.order != U.order || T.left != U.left || T.right != U.right) return 1; /* deterministic */
+    if(T.order.size() != n) return 2;
+    std::vector<char> seen(n, 0);
+    for(unsigned g : T.order) {
+        if(g >= n || seen[g]) return 3;
+        seen[g] = 1;
+    }
+    if(n < 2) return 0;
+    const unsigned ni = n - 1;
+    if(T.left.size() != ni || T.right.size() != ni || T.parent.size() != (size_t)ni + n || T.range_first.size() != ni) return 4;
+    if(T.parent[0] != -1) return 5;
+    std::vector<int> child_count(ni, 0);
+    for(unsigned i = 0; i < ni; i++) {
+        const int L = T.left[i], R = T.right[i];
+        for(int c : {L, R}) {
+            int p = c >= 0 ? T.parent[c] : T.parent[(size_t)ni + (unsigned)~c];
+            if(p != (int)i) return 6;
+            if(c >= 0 && (c <= (int)i || c >= (int)ni)) return 7; /* preorder: children after their parent */
+            if(c < 0 && (unsigned)~c >= n) return 8;
+        }
+        /* the left subtree covers the lower positions, together they tile the node's range */
+        int lf = L >= 0 ? T.range_first[L] : ~L, ll = L >= 0 ? T.range_last[L] : ~L;
+        int rf = R >= 0 ? T.range_first[R] : ~R, rl = R >= 0 ? T.range_last[R] : ~R;
+        if(lf != T.range_first[i] || rl != T.range_last[i] || ll + 1 != rf) return 9;
+    }
+    if(T.range_first[0] != 0 || T.range_last[0] != (int)n - 1) return 10;
+    return 0;
 }
 
 int g_greedy = 1; /* 1: the greedy largest-area collapse (the default); 0: SAH-optimal collapse (GPURT_BUILD_SAH_COLLAPSE) */

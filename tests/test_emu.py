@@ -154,3 +154,28 @@ def test_experimental_trees_give_the_same_hits(emu, orc):
         emu.emu_cpq(h, _vp(q), C.c_ulonglong(len(q)), _vp(res))
         assert (res == want_cp).all()
         emu.emu_free(h)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 17, 1000, 20000])
+def test_sah_split_tree_is_consistent_and_deterministic(emu, orc, n):
+    """host/sah_split.h (GPURT_BUILD_SAH_SPLIT): order is a permutation, parents / ranges are what the refit and
+    collapse kernels expect, duplicates and coincident centroids do not break it, and the wide BVH built from it
+    answers like the oracle"""
+    tris = soup(n, seed=n + 5, ext=0.05)
+    if n >= 17:
+        tris[3:9] = tris[3]                 # duplicates: centroids coincide -> middle split
+        tris[10, 3:] = np.tile(tris[10, :3], 2)   # a point-sized triangle
+    assert emu.emu_sah_split_check(_vp(tris), n) == 0
+    if n < 2:
+        return
+    o, tl, tr, tb = np.zeros(n, np.uint32), np.zeros(n - 1, np.int32), np.zeros(n - 1, np.int32), np.zeros((n - 1, 6), np.float32)
+    emu.emu_sah_bvh2(_vp(tris), n, 16, _vp(o), _vp(tl), _vp(tr), _vp(tb))
+    b = orc.Bvh(tris)
+    inflate = np.float32(max(1e-30, np.abs(b.scene_box()).max()) * 2.0 ** -19)
+    h = C.c_void_p(emu.emu_build(_vp(tris), n, _vp(o), _vp(tl), _vp(tr), _vp(tb), C.c_float(inflate)))
+    assert emu.emu_depth(h) < 60
+    rays = orc.gen_random_rays(5000, 0xC0FFEE, b.scene_box())
+    hits, cnt = np.zeros((len(rays), 4), np.uint32), np.zeros(4, np.uint64)
+    emu.emu_trace(h, _vp(rays), C.c_ulonglong(len(rays)), _vp(hits), None, _vp(cnt))
+    assert (hits == b.closest_hit(rays).view(np.uint32).reshape(-1, 4)).all()
+    emu.emu_free(h)

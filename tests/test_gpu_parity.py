@@ -1,4 +1,6 @@
 """GPU parity tests proper: CUDA path (through the C ABI) vs the CPU oracle, bit-exact."""
+import os
+
 import numpy as np
 import pytest
 
@@ -361,6 +363,48 @@ def test_sah_optimal_collapse_flag(gpurt, orc, ctx):
     sah.update()                                       # the in-place rebuild keeps the flag
     assert sah.info().n_wide_nodes < 0.8 * base.info().n_wide_nodes
     sah.close(), base.close(), scene.close()
+
+
+@pytest.mark.skipif(os.environ.get("GPURT_TEST_EXPERIMENTAL") != "1",
+                    reason="GPURT_BUILD_SAH_SPLIT was written after the round's GPU budget was spent: checked on the CPU replay "
+                           "only (tests/test_emu.py); run with GPURT_TEST_EXPERIMENTAL=1 on a GPU box")
+def test_sah_split_build_flag(gpurt, orc, ctx):
+    """GPURT_BUILD_SAH_SPLIT: host-side binned-SAH order + topology, device refit / collapse / traversal: same query
+    results as the default build and the oracle, also combined with the SAH-optimal collapse and after a pose edit"""
+    scene = load_scene(gpurt, ctx, "cbox")
+    tris = world_tris(orc, scene)
+    ob = orc.Bvh(tris)
+    rays = orc.gen_random_rays(1 << 18, 41, ob.scene_box())
+    q = orc.gen_random_points(1 << 16, 42, ob.scene_box())
+    ref_h, ref_a, ref_c = ob.closest_hit(rays), ob.any_hit(rays), ob.closest_point(q)
+    base = gpurt.Accel(scene)
+    for flags in (gpurt.BUILD_SAH_SPLIT, gpurt.BUILD_SAH_SPLIT | gpurt.BUILD_SAH_COLLAPSE):
+        accel = gpurt.Accel(scene, flags)
+        assert sorted(accel.prim_order().tolist()) == list(range(len(tris)))
+        assert same_bits(accel.trace_closest(rays), ref_h) and (accel.trace_any(rays) == ref_a).all()
+        cp = accel.closest_points(q)
+        assert same_bits(cp["dist"], ref_c["dist"]) and (cp["prim"] == ref_c["gid"]).all()
+        print(f"flags {flags}: {accel.info().n_wide_nodes} wide nodes (default {base.info().n_wide_nodes}), "
+              f"build {accel.info().build_ms:.2f} ms")
+        accel.close()
+    accel = gpurt.Accel(scene, gpurt.BUILD_SAH_SPLIT)
+    m = np.array(list(scene.descs()[3].model), np.float32).reshape(4, 4).T.copy()
+    m[:3, 3] += np.float32(0.2)
+    scene.set_transform(3, m.T.reshape(16).copy())
+    accel.update()
+    ob2 = orc.Bvh(world_tris(orc, scene))
+    assert same_bits(accel.trace_closest(rays), ob2.closest_hit(rays))
+    cam = gpurt.camera(0, 128, 128)
+    prm = gpurt.pipe_params(max_frames=1, samples_per_frame=1, max_depth=3, integrator=2, seed=3)
+    base.update()
+    imgs = []
+    for a in (accel, base):
+        pipe = gpurt.RTPipe(scene, a)
+        pipe.render_frame(prm, cam, 128, 128)
+        imgs.append(pipe.read_image().copy())
+        pipe.close()
+    assert same_bits(imgs[0], imgs[1])
+    accel.close(), base.close(), scene.close()
 
 
 def test_no_device_memory_growth_over_create_destroy_cycles(gpurt, ctx):

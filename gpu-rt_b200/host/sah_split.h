@@ -16,12 +16,15 @@
  *                  cost = area(union of bins < k) * count(bins < k) + area(union of bins >= k) * count(bins >= k)
  *              area(b) = 2 * (ex * ey + ey * ez + ez * ex);  the lowest cost wins, ties -> lower axis, then lower k.
  *              S is stably partitioned into bins < k | bins >= k.  No axis with ext > 0: split at the middle.
- *   leaves     single triangles; nodes are numbered in preorder (root 0), leaf positions in depth-first order.
+ *   leaves     single triangles; nodes are numbered in preorder (root 0), leaf positions in depth-first order
+ *              (= the final order of `items`: a subtree over items[a, b) owns positions a..b-1).
  * Output conventions are those of the LBVH stage (build.cu k_karras): child >= 0 inner node, < 0: ~sorted position.
  */
 #pragma once
 #include <algorithm>
+#include <atomic>
 #include <cstdint>
+#include <thread>
 #include <vector>
 
 namespace gpurt {
@@ -49,8 +52,12 @@ inline float area(const Box& b) {
 }
 } // namespace sah_detail
 
-/* tri_lo / tri_hi: n records of `stride` floats, xyz first (the float4 arrays of the accel) */
-inline void build_sah_split(const float* tri_lo, const float* tri_hi, size_t stride, uint32_t n, SahSplitTree& T) {
+/* tri_lo / tri_hi: n records of `stride` floats, xyz first (the float4 arrays of the accel).
+ * threads: 0 = std::thread::hardware_concurrency().  Node ids and leaf positions follow from subtree sizes alone (a
+ * subtree over m items owns m - 1 consecutive preorder ids and m consecutive positions), so subtrees are independent
+ * work items and the result does not depend on the number of threads. */
+inline void build_sah_split(const float* tri_lo, const float* tri_hi, size_t stride, uint32_t n, SahSplitTree& T,
+                            unsigned threads = 0) {
     using namespace sah_detail;
     T = SahSplitTree();
     T.order.resize(n);
@@ -70,84 +77,119 @@ inline void build_sah_split(const float* tri_lo, const float* tri_hi, size_t str
         for(int k = 0; k < 3; k++) cen[3ull * g + k] = (tri_lo[stride * g + k] + tri_hi[stride * g + k]) * 0.5f;
     }
     struct Job {
-        uint32_t a, b; /* segment of `items` */
-        int parent;    /* inner node that waits for this subtree, -1 for the root */
-        int side;      /* 0 left, 1 right */
+        uint32_t a, b;  /* segment of `items` = the leaf positions this subtree will own */
+        int me;         /* preorder id of the subtree's root if it is an inner node */
+        int parent;     /* inner node that waits for this subtree, -1 for the root */
+        int side;       /* 0 left, 1 right */
         unsigned depth;
     };
-    /* explicit stack, right child pushed first: nodes come out in preorder, leaves left to right */
-    std::vector<Job> stack{{0, n, -1, 0, 1}};
-    int next_node = 0;
-    uint32_t next_pos = 0;
-    while(!stack.empty()) {
-        const Job j = stack.back();
-        stack.pop_back();
-        int ref;
+    /* split one inner node: partitions items[a, b) and returns the boundary */
+    auto split = [&](const Job& j) -> uint32_t {
+        Box cb = empty_box();
+        for(uint32_t i = j.a; i < j.b; i++) grow(cb, &cen[3ull * items[i]], &cen[3ull * items[i]]);
+        int best_axis = -1, best_k = 0;
+        float best_cost = 3.0e38f;
+        for(int ax = 0; ax < 3; ax++) {
+            const float ext = cb.hi[ax] - cb.lo[ax];
+            if(!(ext > 0.0f)) continue;
+            const float scale = (float)kBins / ext;
+            Box bb[kBins];
+            uint32_t cnt[kBins];
+            for(int k = 0; k < kBins; k++) bb[k] = empty_box(), cnt[k] = 0;
+            for(uint32_t i = j.a; i < j.b; i++) {
+                const uint32_t g = items[i];
+                const int bi = std::min(kBins - 1, (int)((cen[3ull * g + ax] - cb.lo[ax]) * scale));
+                cnt[bi]++;
+                grow(bb[bi], tri_lo + stride * g, tri_hi + stride * g);
+            }
+            float right_area[kBins];
+            uint32_t right_cnt[kBins];
+            Box run = empty_box();
+            uint32_t c = 0;
+            for(int k = kBins - 1; k >= 1; k--) {
+                if(cnt[k]) grow(run, bb[k].lo, bb[k].hi);
+                c += cnt[k];
+                right_cnt[k] = c, right_area[k] = c ? area(run) : 0.0f;
+            }
+            run = empty_box(), c = 0;
+            for(int k = 1; k < kBins; k++) {
+                if(cnt[k - 1]) grow(run, bb[k - 1].lo, bb[k - 1].hi);
+                c += cnt[k - 1];
+                if(c == 0 || right_cnt[k] == 0) continue;
+                const float cost = area(run) * (float)c + right_area[k] * (float)right_cnt[k];
+                if(cost < best_cost) best_cost = cost, best_axis = ax, best_k = k;
+            }
+        }
+        if(best_axis < 0) return j.a + (j.b - j.a) / 2;
+        const float lo = cb.lo[best_axis], scale = (float)kBins / (cb.hi[best_axis] - cb.lo[best_axis]);
+        uint32_t nl = 0, nr = 0;
+        for(uint32_t i = j.a; i < j.b; i++) { /* stable partition through this segment's slice of the scratch array */
+            const uint32_t g = items[i];
+            const int bi = std::min(kBins - 1, (int)((cen[3ull * g + best_axis] - lo) * scale));
+            if(bi < best_k) items[j.a + nl++] = g;
+            else scratch[j.a + nr++] = g;
+        }
+        for(uint32_t i = 0; i < nr; i++) items[j.a + nl + i] = scratch[j.a + i];
+        return j.a + nl; /* both sides are non-empty by construction of best_k */
+    };
+    /* emit the node or leaf of job j; inner nodes return their two child jobs */
+    auto emit = [&](const Job& j, Job out[2]) -> int {
+        int ref, n_out = 0;
         if(j.b - j.a == 1) {
-            T.order[next_pos] = items[j.a];
-            T.parent[(size_t)ni + next_pos] = j.parent;
-            ref = ~(int)next_pos;
-            next_pos++;
+            T.order[j.a] = items[j.a];
+            T.parent[(size_t)ni + j.a] = j.parent;
+            ref = ~(int)j.a;
         } else {
-            const int me = next_node++;
-            ref = me;
-            T.parent[me] = j.parent;
-            T.depth = std::max(T.depth, j.depth);
-            /* positions are handed out depth-first, so this subtree will cover [next_pos, next_pos + count) */
-            T.range_first[me] = (int)next_pos, T.range_last[me] = (int)(next_pos + (j.b - j.a) - 1);
-            Box cb = empty_box();
-            for(uint32_t i = j.a; i < j.b; i++) grow(cb, &cen[3ull * items[i]], &cen[3ull * items[i]]);
-            int best_axis = -1, best_k = 0;
-            float best_cost = 3.0e38f;
-            for(int ax = 0; ax < 3; ax++) {
-                const float ext = cb.hi[ax] - cb.lo[ax];
-                if(!(ext > 0.0f)) continue;
-                const float scale = (float)kBins / ext;
-                Box bb[kBins];
-                uint32_t cnt[kBins];
-                for(int k = 0; k < kBins; k++) bb[k] = empty_box(), cnt[k] = 0;
-                for(uint32_t i = j.a; i < j.b; i++) {
-                    const uint32_t g = items[i];
-                    const int bi = std::min(kBins - 1, (int)((cen[3ull * g + ax] - cb.lo[ax]) * scale));
-                    cnt[bi]++;
-                    grow(bb[bi], tri_lo + stride * g, tri_hi + stride * g);
-                }
-                float right_area[kBins];
-                uint32_t right_cnt[kBins];
-                Box run = empty_box();
-                uint32_t c = 0;
-                for(int k = kBins - 1; k >= 1; k--) {
-                    if(cnt[k]) grow(run, bb[k].lo, bb[k].hi);
-                    c += cnt[k];
-                    right_cnt[k] = c, right_area[k] = c ? area(run) : 0.0f;
-                }
-                run = empty_box(), c = 0;
-                for(int k = 1; k < kBins; k++) {
-                    if(cnt[k - 1]) grow(run, bb[k - 1].lo, bb[k - 1].hi);
-                    c += cnt[k - 1];
-                    if(c == 0 || right_cnt[k] == 0) continue;
-                    const float cost = area(run) * (float)c + right_area[k] * (float)right_cnt[k];
-                    if(cost < best_cost) best_cost = cost, best_axis = ax, best_k = k;
-                }
-            }
-            uint32_t mid = j.a + (j.b - j.a) / 2;
-            if(best_axis >= 0) {
-                const float lo = cb.lo[best_axis], scale = (float)kBins / (cb.hi[best_axis] - cb.lo[best_axis]);
-                uint32_t nl = 0, nr = 0;
-                for(uint32_t i = j.a; i < j.b; i++) { /* stable partition through the scratch array */
-                    const uint32_t g = items[i];
-                    const int bi = std::min(kBins - 1, (int)((cen[3ull * g + best_axis] - lo) * scale));
-                    if(bi < best_k) items[j.a + nl++] = g;
-                    else scratch[nr++] = g;
-                }
-                for(uint32_t i = 0; i < nr; i++) items[j.a + nl + i] = scratch[i];
-                mid = j.a + nl; /* both sides are non-empty by construction of best_k */
-            }
-            stack.push_back(Job{mid, j.b, me, 1, j.depth + 1});
-            stack.push_back(Job{j.a, mid, me, 0, j.depth + 1});
+            ref = j.me;
+            T.parent[j.me] = j.parent;
+            T.range_first[j.me] = (int)j.a, T.range_last[j.me] = (int)j.b - 1;
+            const uint32_t mid = split(j);
+            /* preorder: the left subtree takes the ids right after this node, (mid - a) - 1 of them */
+            out[0] = Job{j.a, mid, j.me + 1, j.me, 0, j.depth + 1};
+            out[1] = Job{mid, j.b, j.me + (int)(mid - j.a), j.me, 1, j.depth + 1};
+            n_out = 2;
         }
         if(j.parent >= 0) (j.side ? T.right : T.left)[j.parent] = ref;
+        return n_out;
+    };
+    auto run_subtree = [&](Job root, unsigned& max_depth) {
+        std::vector<Job> stack{root};
+        while(!stack.empty()) {
+            const Job j = stack.back();
+            stack.pop_back();
+            if(j.b - j.a > 1) max_depth = std::max(max_depth, j.depth);
+            Job out[2];
+            if(emit(j, out) == 2) stack.push_back(out[1]), stack.push_back(out[0]);
+        }
+    };
+    if(threads == 0) threads = std::max(1u, std::thread::hardware_concurrency());
+    const uint32_t grain = std::max<uint32_t>(4096, n / (8 * threads));
+    /* top of the tree on this thread until the segments are small enough, then the subtrees in parallel */
+    std::vector<Job> top{Job{0, n, 0, -1, 0, 1}}, tasks;
+    unsigned depth = 0;
+    while(!top.empty()) {
+        const Job j = top.back();
+        top.pop_back();
+        if(threads > 1 && j.b - j.a <= grain) {
+            tasks.push_back(j);
+            continue;
+        }
+        if(j.b - j.a > 1) depth = std::max(depth, j.depth);
+        Job out[2];
+        if(emit(j, out) == 2) top.push_back(out[1]), top.push_back(out[0]);
     }
+    if(!tasks.empty()) {
+        std::atomic<size_t> next{0};
+        std::vector<unsigned> depths(threads, 0);
+        std::vector<std::thread> pool;
+        for(unsigned t = 0; t < std::min<size_t>(threads, tasks.size()); t++)
+            pool.emplace_back([&, t] {
+                for(size_t k; (k = next.fetch_add(1)) < tasks.size();) run_subtree(tasks[k], depths[t]);
+            });
+        for(auto& th : pool) th.join();
+        for(unsigned d : depths) depth = std::max(depth, d);
+    }
+    T.depth = depth;
 }
 
 } // namespace gpurt

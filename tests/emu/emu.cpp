@@ -330,9 +330,11 @@ int emu_sah_split_check(const float* tris9, unsigned n) {
             lo[4ull * g + k] = fminf(fminf(t[k], t[3 + k]), t[6 + k]), hi[4ull * g + k] = fmaxf(fmaxf(t[k], t[3 + k]), t[6 + k]);
         }
     SahSplitTree T, U;
-    build_sah_split(lo.data(), hi.data(), 4, n, T);
-    build_sah_split(lo.data(), hi.data(), 4, n, U);
-    if(T.order != U.order || T.left != U.left || T.right != U.right) return 1; /* deterministic */
+    build_sah_split(lo.data(), hi.data(), 4, n, T, 1);
+    build_sah_split(lo.data(), hi.data(), 4, n, U, 7);
+    if(T.order != U.order || T.left != U.left || T.right != U.right || T.parent != U.parent || T.range_first != U.range_first ||
+       T.range_last != U.range_last || T.depth != U.depth)
+        return 1; /* deterministic, whatever the number of threads */
     if(T.order.size() != n) return 2;
     std::vector<char> seen(n, 0);
     for(unsigned g : T.order) {

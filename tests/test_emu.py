@@ -179,3 +179,16 @@ def test_sah_split_tree_is_consistent_and_deterministic(emu, orc, n):
     emu.emu_trace(h, _vp(rays), C.c_ulonglong(len(rays)), _vp(hits), None, _vp(cnt))
     assert (hits == b.closest_hit(rays).view(np.uint32).reshape(-1, 4)).all()
     emu.emu_free(h)
+
+
+def test_sah_probe_tool_runs(built):
+    """tools/sah_probe.py (the CPU tree-quality experiment DESIGN.md §4 quotes) still runs and its trees agree"""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sah_probe.py"), "--scenes", "mis_test", "--rays", "20000",
+                          "--ploc", "8", "--clusters", "64"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    j = json.loads(out.stdout)["mis_test"]
+    assert {"lbvh", "binned_sah", "ploc_r8", "hybrid_64", "lbvh+dp_collapse"} <= set(j)
+    assert j["binned_sah"]["bounce"]["nodes_per_ray"] <= j["lbvh"]["bounce"]["nodes_per_ray"] * 1.05

@@ -11,7 +11,7 @@
  *   items      triangles, initially in global primitive id order
  *   box(t)     the world-space AABB k_flatten wrote (tri_lo / tri_hi), centroid c(t) = (lo + hi) * 0.5f (as in N6)
  *   node(S)    cb = centroid bounds of S.  For axis = x, y, z with ext = cb.hi - cb.lo > 0:
- *                bin(t) = min(BINS - 1, (int)((c(t)[axis] - cb.lo[axis]) * ((float)BINS / ext)))
+ *                bin(t) = min(BINS - 1, (int)((c(t)[axis] - cb.lo[axis]) * ((float)BINS / ext))), 0 if that is NaN
  *                for each boundary k = 1..BINS-1 with both sides non-empty:
  *                  cost = area(union of bins < k) * count(bins < k) + area(union of bins >= k) * count(bins >= k)
  *              area(b) = 2 * (ex * ey + ey * ez + ez * ex);  the lowest cost wins, ties -> lower axis, then lower k.
@@ -45,6 +45,11 @@ struct Box {
 inline Box empty_box() { return Box{{3.0e38f, 3.0e38f, 3.0e38f}, {-3.0e38f, -3.0e38f, -3.0e38f}}; }
 inline void grow(Box& b, const float* lo, const float* hi) {
     for(int k = 0; k < 3; k++) b.lo[k] = std::min(b.lo[k], lo[k]), b.hi[k] = std::max(b.hi[k], hi[k]);
+}
+/* bin of a centroid coordinate; NaN / negative products (non-finite input) land in bin 0 instead of being undefined */
+inline int bin_of(float c, float lo, float scale) {
+    const float f = (c - lo) * scale;
+    return f >= 0.0f ? (f < (float)kBins ? (int)f : kBins - 1) : 0;
 }
 inline float area(const Box& b) {
     float ex = b.hi[0] - b.lo[0], ey = b.hi[1] - b.lo[1], ez = b.hi[2] - b.lo[2];
@@ -98,7 +103,7 @@ inline void build_sah_split(const float* tri_lo, const float* tri_hi, size_t str
             for(int k = 0; k < kBins; k++) bb[k] = empty_box(), cnt[k] = 0;
             for(uint32_t i = j.a; i < j.b; i++) {
                 const uint32_t g = items[i];
-                const int bi = std::min(kBins - 1, (int)((cen[3ull * g + ax] - cb.lo[ax]) * scale));
+                const int bi = bin_of(cen[3ull * g + ax], cb.lo[ax], scale);
                 cnt[bi]++;
                 grow(bb[bi], tri_lo + stride * g, tri_hi + stride * g);
             }
@@ -125,7 +130,7 @@ inline void build_sah_split(const float* tri_lo, const float* tri_hi, size_t str
         uint32_t nl = 0, nr = 0;
         for(uint32_t i = j.a; i < j.b; i++) { /* stable partition through this segment's slice of the scratch array */
             const uint32_t g = items[i];
-            const int bi = std::min(kBins - 1, (int)((cen[3ull * g + best_axis] - lo) * scale));
+            const int bi = bin_of(cen[3ull * g + best_axis], lo, scale);
             if(bi < best_k) items[j.a + nl++] = g;
             else scratch[j.a + nr++] = g;
         }

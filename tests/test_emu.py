@@ -166,6 +166,13 @@ def test_sah_split_tree_is_consistent_and_deterministic(emu, orc, n):
         tris[3:9] = tris[3]                 # duplicates: centroids coincide -> middle split
         tris[10, 3:] = np.tile(tris[10, :3], 2)   # a point-sized triangle
     assert emu.emu_sah_split_check(_vp(tris), n) == 0
+    if n == 1000:                           # degenerate / huge-offset / non-finite input keeps the tree well-formed
+        from scenes import adversarial_scene
+        adv = adversarial_scene()
+        assert emu.emu_sah_split_check(_vp(adv), len(adv)) == 0
+        bad = tris.copy()
+        bad[5, 0], bad[6, 4], bad[7, :] = np.nan, np.inf, -np.inf
+        assert emu.emu_sah_split_check(_vp(bad), len(bad)) == 0
     if n < 2:
         return
     o, tl, tr, tb = np.zeros(n, np.uint32), np.zeros(n - 1, np.int32), np.zeros(n - 1, np.int32), np.zeros((n - 1, 6), np.float32)

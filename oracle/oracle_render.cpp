@@ -939,6 +939,83 @@ void orc_mat_eval(int brdf, const float* albedo3, float roughness, const float* 
     out3[0] = r.x, out3[1] = r.y, out3[2] = r.z;
 }
 
+/* the oracle's texture unit for the compiled reference shader (oracle/ref_shim/glsl_ref.cpp): texture() is hardware
+ * behaviour (R8G8B8A8_SRGB decode, linear filter, REPEAT), not shader text */
+void orc_texture_fetch(const orc_scene* S, int tex, float u, float v, float* rgb) {
+    Invocation inv;
+    inv.S = S;
+    const float tc[2] = {u, v};
+    vec3 c = inv.texture(tex, tc);
+    rgb[0] = c.x, rgb[1] = c.y, rgb[2] = c.z;
+}
+
+/* One call of one restated rtcommon.glsl / restir.glsl function, by id — the same ids and argument layout as
+ * ref_glsl_unit in oracle/ref_shim/glsl_ref.cpp, which runs the reference's own shader text compiled as C++.
+ * in: floats, u[0]: RNG state (in / out), u[1], u[2]: unsigned arguments / results, out: floats. */
+void orc_glsl_unit(int fn, const float* in, uint32_t* u, float* out) {
+    Consts c;
+    memset(&c, 0, sizeof(c));
+    Invocation inv;
+    inv.S = nullptr, inv.c = &c, inv.cam = nullptr;
+    inv.seed = u[0];
+    auto V = [&](int k) { return vec3{in[k], in[k + 1], in[k + 2]}; };
+    auto put = [&](int k, vec3 v) { out[k] = v.x, out[k + 1] = v.y, out[k + 2] = v.z; };
+    MatInfo mat;
+    ShadeInfo sh;
+    auto shading = [&]() {
+        c.brdf = (int)in[0];
+        mat.roughness = in[1];
+        mat.albedo = V(2), mat.emissive = v3(0), mat.tanspaceNormal = v3(0), mat.use_tanspace = false;
+        sh.wo = V(5), sh.N = V(8);
+        Invocation::make_tanspace(sh.N, sh.T, sh.B);
+    };
+    switch(fn) {
+    case 0: u[0] = orc_tea(u[1], u[2]); return;
+    case 1: out[0] = inv.randf(); break;
+    case 2: u[1] = inv.randu(u[1], u[2]); break;
+    case 3: put(0, inv.cospow_hemisphere(in[0], V(1), V(4), V(7))); break;
+    case 4: put(0, inv.triangle_sample()); break;
+    case 5: {
+        vec3 hitp = v3(0);
+        out[0] = Invocation::triangle_hit(V(0), V(3), V(6), V(9), V(12), hitp) ? 1.0f : 0.0f;
+        put(1, hitp);
+        break;
+    }
+    case 6: out[0] = Invocation::triangle_pdf(V(0), V(3), V(6), V(9), V(12)); break;
+    case 7: {
+        vec3 t, b;
+        Invocation::make_tanspace(V(0), t, b);
+        put(0, t), put(3, b);
+        break;
+    }
+    case 8: out[0] = Invocation::hit_bbox(V(0), V(3), V(6), V(9)) ? 1.0f : 0.0f; break;
+    case 9: shading(), out[0] = inv.MAT_pdf(mat, sh, V(11)); break;
+    case 10: shading(), put(0, inv.MAT_eval(mat, sh, V(11))); break;
+    case 11: {
+        shading();
+        vec3 wi = v3(0);
+        out[0] = inv.MAT_sample(mat, sh, wi) ? 1.0f : 0.0f;
+        put(1, wi);
+        break;
+    }
+    case 12: {
+        Reservoir r;
+        r.pos = V(0), r.normal = V(3), r.emissive = V(6), r.w_sum = in[9], r.w = in[10], r.n_seen = u[1];
+        inv.res_update(r, in[11], V(12), V(15), V(18));
+        put(0, r.pos), put(3, r.normal), put(6, r.emissive), out[9] = r.w_sum, out[10] = r.w;
+        u[1] = r.n_seen;
+        break;
+    }
+    case 13: out[0] = Invocation::power_heuristic(in[0], in[1]); break;
+    case 14: out[0] = Invocation::luma(V(0)); break;
+    case 15: /* hammersley(i, N) as make_camera_ray evaluates it (rtcommon.glsl:128-139) */
+        out[0] = (float)u[1] / (float)u[2], out[1] = orc_radical_inverse(u[1]);
+        break;
+    default: break;
+    }
+    u[0] = inv.seed;
+}
+
 /* tonemap.frag:17-48, then the R8G8B8A8_SRGB framebuffer encode (gpurt.cpp:176, :258-262) */
 void orc_tonemap(const float* rgba, uint64_t n, int op, float exposure, float gamma, uint8_t* out) {
     auto u2 = [](float x) {

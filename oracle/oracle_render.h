@@ -46,6 +46,10 @@ void orc_camera_ray(const uint32_t* consts, const uint32_t* camera, uint32_t w, 
 float orc_mat_pdf(int brdf, float roughness, const float* wo3, const float* n3, const float* wi3);
 void orc_mat_eval(int brdf, const float* albedo3, float roughness, const float* wo3, const float* n3,
                   const float* wi3, float* out3);
+void orc_texture_fetch(const orc_scene* S, int tex, float u, float v, float* rgb);
+/* one restated rtcommon.glsl / restir.glsl function by id (ids and layout: oracle/ref_shim/glsl_ref.cpp, which runs the
+ * reference's own shader text): the hook tests/test_oracle.py pins against tests/golden/glsl_unit_golden.npz */
+void orc_glsl_unit(int fn, const float* in, uint32_t* u, float* out);
 /* tonemap.frag:17-48 on RGBA32F -> RGBA8 (op 0 Uncharted2, 1 exponential, 2 passthrough) */
 void orc_tonemap(const float* rgba, uint64_t n, int op, float exposure, float gamma, uint8_t* out);
 

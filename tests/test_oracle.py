@@ -4,6 +4,7 @@ bit-twiddling, (b) brute force vs its own BVH, (c) size-independent geometric pr
 import ctypes as C
 
 import numpy as np
+import pytest
 
 from scenes import soup
 
@@ -156,3 +157,61 @@ def test_oracle_integrator_is_deterministic_and_accumulates(orc, gpurt):
         d = orc.FrameState(w, h)
         orc.render_frame(rs, d, consts(0, integ), cam, 6)
         assert (d.image != f0).any(), "seed must matter"
+
+
+# ---- the oracle against the reference's own shader text ---------------------------------------------------------
+# oracle/_ref/libglsl_ref.so is the reference's rtcommon.glsl + restir.glsl + rt.rgen compiled as C++ (oracle/
+# make_glsl_ref.py rewrites the text into oracle/_ref/, oracle/ref_shim/glsl_compat.h supplies the GLSL types and — for
+# what GLSL leaves to the implementation: fma contraction, sin / cos / pow — the numeric contract N8 of DESIGN.md §3).
+# tests/golden/make_glsl_golden.py ran it in the build container and committed (a) input / output vectors of 16 shader
+# functions and (b) SHA-256 digests of whole frames.  The oracle's restatement must reproduce both BIT FOR BIT.
+GLSL_FUNCS = {0: "tea", 1: "randf", 2: "randu", 3: "cospow_hemisphere", 4: "triangle_sample", 5: "triangle_hit",
+              6: "triangle_pdf", 7: "make_tanspace", 8: "hit_bbox", 9: "MAT_pdf", 10: "MAT_eval", 11: "MAT_sample",
+              12: "res_update", 13: "power_heuristic", 14: "luma", 15: "hammersley"}
+
+
+def _glsl_unit(fn_ptr, fn, f, u):
+    out = np.zeros((len(f), 12), np.float32)
+    u = u.copy()
+    for i in range(len(f)):
+        fn_ptr(fn, f[i].ctypes.data_as(C.c_void_p), u[i].ctypes.data_as(C.c_void_p), out[i].ctypes.data_as(C.c_void_p))
+    return out, u
+
+
+@pytest.mark.parametrize("fn", sorted(GLSL_FUNCS))
+def test_oracle_functions_match_the_reference_shader_text(orc, fn):
+    import os
+    from conftest import ROOT
+    g = np.load(os.path.join(ROOT, "tests", "golden", "glsl_unit_golden.npz"))
+    f, u, want, uwant = g[f"in_{fn}"], g[f"u_{fn}"], g[f"out_{fn}"], g[f"uout_{fn}"]
+    orc.lib.orc_glsl_unit.restype = None
+    got, ugot = _glsl_unit(orc.lib.orc_glsl_unit, fn, f, u)
+    name = GLSL_FUNCS[fn]
+    assert (ugot == uwant).all(), f"{name}: RNG state / unsigned results differ"
+    assert (got.view(np.uint32) == want.view(np.uint32)).all(), f"{name}: {(got.view(np.uint32) != want.view(np.uint32)).any(axis=1).sum()} of {len(f)} results differ"
+    assert np.abs(want).sum() > 0 or fn in (0, 2)
+    so = os.path.join(ROOT, "oracle", "_ref", "libglsl_ref.so")
+    if os.path.exists(so):   # the compiled reference itself is here: the committed vectors are not stale
+        ref = C.CDLL(so).ref_glsl_unit
+        ref.restype = None
+        live, ulive = _glsl_unit(ref, fn, f, u)
+        assert (live.view(np.uint32) == want.view(np.uint32)).all() and (ulive == uwant).all(), "golden file is stale"
+
+
+def test_oracle_frames_match_the_reference_shader_text(orc, gpurt):
+    """whole frames of rt.rgen `main` (all integrators, both BRDFs, textures, ReSTIR temporal reuse over several frames,
+    QMC, debug views, scenes with NaN normals and zero-area lights): image, G-buffers, reservoirs and ray counts of the
+    oracle == those of the reference's shader text, by SHA-256 of the raw buffers"""
+    import json
+    import os
+    from conftest import ROOT
+    sys_path_golden = os.path.join(ROOT, "tests", "golden")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_glsl_golden", os.path.join(sys_path_golden, "make_glsl_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    want = json.load(open(os.path.join(sys_path_golden, "glsl_frames_golden.json")))
+    got = mg.frame_digests(gpurt, orc, lambda rs, st, consts, cam, seed, n_tex: orc.render_frame(rs, st, consts, cam, seed))
+    assert set(got) == set(want)
+    bad = [k for k in want if got[k] != want[k]]
+    assert not bad, f"{len(bad)} of {len(want)} frame buffers differ from the reference shader's: {bad[:5]}"

@@ -2,7 +2,8 @@
 """Rewrite the reference's shader sources into C++-compilable text under oracle/_ref/ (git-ignored; TEST
 INFRASTRUCTURE — see oracle/ref_shim/glsl_compat.h).  Nothing of the shader text is stored in the repository.
 usage: python oracle/make_glsl_ref.py /root/reference oracle/_ref
-writes rt_glsl_gen.inc (rtcommon.glsl + restir.glsl) and rt_rgen_gen.inc (rt.rgen without its binding declarations)"""
+writes rt_glsl_gen.inc (rtcommon.glsl + restir.glsl), rt_rgen_gen.inc (rt.rgen without its binding declarations)
+and tonemap_gen.inc (tonemap.frag)"""
 import re
 import sys
 
@@ -47,3 +48,4 @@ head = "/* generated from the reference shaders by oracle/make_glsl_ref.py — d
 common = "".join(open(f"{ref}/src/shaders/rt/{n}").read() + "\n" for n in ("rtcommon.glsl", "restir.glsl"))
 open(f"{out_dir}/rt_glsl_gen.inc", "w").write(head + rewrite(common))
 open(f"{out_dir}/rt_rgen_gen.inc", "w").write(head + rewrite(open(f"{ref}/src/shaders/rt/rt.rgen").read()))
+open(f"{out_dir}/tonemap_gen.inc", "w").write(head + rewrite(open(f"{ref}/src/shaders/tonemap.frag").read()))

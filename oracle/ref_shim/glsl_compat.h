@@ -67,8 +67,9 @@ struct vec4 {
     };
     union {
         struct { float x, y, z, w; };
+        struct { float r, g, b, a; };
         SwzXY xy;
-        SwzXYZ xyz;
+        SwzXYZ xyz, rgb;
     };
     vec4() : x(0), y(0), z(0), w(0) {}
     vec4(float a, float b, float c, float d) : x(a), y(b), z(c), w(d) {}
@@ -102,6 +103,7 @@ inline vec3 operator/(vec3 a, float s) { return vec3(a.x / s, a.y / s, a.z / s);
 inline vec3 operator/(float s, vec3 a) { return vec3(s / a.x, s / a.y, s / a.z); }
 inline vec3 operator-(float s, vec3 a) { return vec3(s - a.x, s - a.y, s - a.z); }
 inline vec3 operator-(vec3 a, float s) { return vec3(a.x - s, a.y - s, a.z - s); }
+inline vec3 operator+(vec3 a, float s) { return vec3(a.x + s, a.y + s, a.z + s); }
 inline vec3& operator+=(vec3& a, vec3 b) { return a = a + b; }
 inline vec3& operator*=(vec3& a, vec3 b) { return a = a * b; }
 inline vec3& operator/=(vec3& a, float s) { return a = a / s; }
@@ -125,6 +127,8 @@ inline float sqrt(float x) { return sqrtf(x); }
 inline float cos(float x) { return dm_cos(x); }
 inline float sin(float x) { return dm_sin(x); }
 inline float pow(float x, float y) { return dm_pow(x, y); }
+inline vec3 pow(vec3 x, vec3 y) { return vec3(dm_pow(x.x, y.x), dm_pow(x.y, y.y), dm_pow(x.z, y.z)); }
+inline vec3 exp(vec3 x) { return vec3(dm_exp(x.x), dm_exp(x.y), dm_exp(x.z)); }
 inline float abs(float x) { return fabsf(x); }
 inline float max(float a, float b) { return fmaxf(a, b); }
 inline float min(float a, float b) { return fminf(a, b); }

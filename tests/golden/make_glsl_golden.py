@@ -184,6 +184,31 @@ def frame_digests(gpurt, orc, render):
     return out
 
 
+def tonemap_inputs():
+    rng = np.random.default_rng(3)
+    x = (rng.random((100000, 4), dtype=np.float32) * 4).astype(np.float32)
+    x[:100, 0], x[100:200, 1], x[200:300, 2] = np.nan, np.inf, -1
+    return x
+
+
+def tonemap_digests(fn):
+    """tonemap.frag + the R8G8B8A8_SRGB framebuffer store: RGBA8 digests for the three operators"""
+    import hashlib
+    x, out = tonemap_inputs(), {}
+    for op in (0, 1, 2):
+        for exposure, gamma in ((1.0, 2.2), (0.37, 1.0), (3.0, 2.6)):
+            out[f"tonemap/op{op}/e{exposure}/g{gamma}"] = hashlib.sha256(np.ascontiguousarray(fn(x, op, exposure, gamma)).tobytes()).hexdigest()
+    return out
+
+
+def _ref_tonemap(x, op, exposure, gamma):
+    ref = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libglsl_ref.so"))
+    out = np.zeros(x.shape, np.uint8)
+    ref.ref_glsl_tonemap(C.c_void_p(x.ctypes.data), C.c_ulonglong(len(x)), op, C.c_float(exposure), C.c_float(gamma),
+                         C.c_void_p(out.ctypes.data))
+    return out
+
+
 def main():
     ref_dir = os.path.join(ROOT, "oracle", "_ref")
     subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "_ref/libglsl_ref.so"])
@@ -202,6 +227,9 @@ def main():
     import gpurt
     import orc
     digests = frame_digests(gpurt, orc, ref_renderer(orc))
+    json.dump(digests, open(os.path.join(ROOT, "tests", "golden", "glsl_frames_golden.json"), "w"), indent=0, sort_keys=True)
+    for k, v in tonemap_digests(lambda x, op, e, g: _ref_tonemap(x, op, e, g)).items():
+        digests[k] = v
     json.dump(digests, open(os.path.join(ROOT, "tests", "golden", "glsl_frames_golden.json"), "w"), indent=0, sort_keys=True)
     print("wrote", len(digests), "frame-buffer digests")
 

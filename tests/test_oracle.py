@@ -212,6 +212,7 @@ def test_oracle_frames_match_the_reference_shader_text(orc, gpurt):
     spec.loader.exec_module(mg)
     want = json.load(open(os.path.join(sys_path_golden, "glsl_frames_golden.json")))
     got = mg.frame_digests(gpurt, orc, lambda rs, st, consts, cam, seed, n_tex: orc.render_frame(rs, st, consts, cam, seed))
+    got.update(mg.tonemap_digests(lambda x, op, e, g: orc.tonemap(x, op, e, g)))   # tonemap.frag + framebuffer store
     assert set(got) == set(want)
     bad = [k for k in want if got[k] != want[k]]
     assert not bad, f"{len(bad)} of {len(want)} frame buffers differ from the reference shader's: {bad[:5]}"

@@ -10,9 +10,12 @@
  * (README.md:6-8).  The reference ships no tests or golden vectors.  For those three pieces this
  * oracle is "parity unpinned": it restates the *observable contract* at the reference's own call
  * sites (ray interval, flags, payload, instance transforms) with a documented fp32 numeric
- * contract.  Everything that IS reference source — RNG, sampling, BRDFs, light
- * sampling, integrators, ReSTIR, accumulation, host matrices, scene packing — is restated line by
- * line and pinned against the reference's own host code compiled in oracle/_ref.
+ * contract.  Everything that IS reference source is restated line by line and pinned
+ * against that source compiled in oracle/_ref: host matrices, camera, scene loading / packing and
+ * texture decode against the reference's C++ (libgpurt_ref.so); RNG, sampling, BRDFs, light
+ * sampling, the five integrators, ReSTIR, accumulation, debug views and the tonemap against the
+ * reference's GLSL compiled as C++ (libglsl_ref.so) — bit for bit, whole frames included
+ * (tests/golden/glsl_*_golden.*, tests/test_oracle.py).
  *
  * All functions are extern "C", plain pointers and sizes, so tests drive them with ctypes.
  */

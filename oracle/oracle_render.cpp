@@ -10,6 +10,10 @@
  * sin / cos / pow / exp come from include/gpurt_detmath.h; no other contraction
  * (-ffp-contract=off).  Documented deviations from the GLSL: Q1 seed, Q4 no-light
  * guard.
+ *
+ * PINNED: the reference's own rt.rgen / rtcommon.glsl / restir.glsl / tonemap.frag, compiled as C++ under the same
+ * contract (oracle/_ref/libglsl_ref.so, oracle/ref_shim/glsl_*.{h,cpp}), produce the same bits as this file on 16
+ * functions x 400 vectors and on whole frames of every integrator (tests/test_oracle.py, tests/golden/).
  */
 #include "oracle_render.h"
 

@@ -169,6 +169,7 @@ def frame_digests(gpurt, orc, render):
     out = {}
     for name, scene, texs, w, h, frames, cam, kw in frame_cases(gpurt):
         rs = orc.RenderScene(scene, texs)
+        rs.gscene, rs.textures = scene, texs   # for renderers that build their own structures from the scene
         st = orc.FrameState(w, h)
         cam = cam or gpurt.camera(0, w, h)
         for f in range(frames):

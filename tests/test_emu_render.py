@@ -399,3 +399,29 @@ def test_textured_quads_all_texture_kinds(emu, orc, gpurt):
                    max_depth=3, use_normal_map=1, use_metalness=1, seed=20 + integ)
         assert np.isfinite(img[..., :3]).mean() > 0.9
     scene.close()
+
+
+def test_product_shading_code_equals_the_reference_shader_text(emu, orc, gpurt):
+    """the product's device code (shade.cuh + bvh8 / traverse, replayed on the CPU) against the digests of whole frames
+    rendered by the REFERENCE'S OWN rt.rgen compiled as C++ (tests/golden/glsl_frames_golden.json, see
+    tests/test_oracle.py): image, G-buffers, reservoirs and ray counts of every case, without the oracle's integrator
+    in between (its BVH only served the reference run)"""
+    import importlib.util
+    import json
+    spec = importlib.util.spec_from_file_location("make_glsl_golden", os.path.join(ROOT, "tests", "golden", "make_glsl_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    want = {k: v for k, v in json.load(open(os.path.join(ROOT, "tests", "golden", "glsl_frames_golden.json"))).items()
+            if not k.startswith("tonemap/")}
+    cache = {}
+
+    def render(rs, st, consts, cam, seed, n_tex):
+        if id(rs) not in cache:
+            cache.clear()
+            cache[id(rs)] = EmuScene(emu, orc, rs.gscene, rs.textures)
+        frame = int(np.asarray(consts, np.uint32)[8])
+        return cache[id(rs)].render_frame(st, consts, cam, seed ^ frame)
+    got = mg.frame_digests(gpurt, orc, render)
+    assert set(got) == set(want)
+    bad = [k for k in want if got[k] != want[k]]
+    assert not bad, f"{len(bad)} of {len(want)} frame buffers differ from the reference shader's: {bad[:5]}"

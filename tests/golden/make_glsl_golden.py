@@ -152,6 +152,11 @@ def frame_cases(gpurt):
         yield (f"features_i{integ}", feat, texs, 80, 60, 2, cam,
                dict(integrator=integ, brdf=integ % 2, samples_per_frame=2, max_depth=3, use_normal_map=1, use_metalness=1,
                     env_scale=0.5, seed=77 + integ))
+    quads, qtex = T._textured_quads_scene(gpurt)   # emissive-TEXTURED light: light_sample's texture path, quirk Q5
+    cam = gpurt.camera(1, 64, 48, (1.5, 1.0, 2.5), (0.0, 0.0, 0.5), 70.0)
+    for integ in (0, 2, 3, 4):
+        yield (f"texquads_i{integ}", quads, qtex, 64, 48, 2, cam,
+               dict(integrator=integ, brdf=1, samples_per_frame=2, max_depth=3, use_normal_map=1, use_metalness=1, seed=20 + integ))
     for seed in (1, 2):
         rnd = T._random_material_scene(gpurt, seed)
         cam = gpurt.camera(1, 48, 27, (0.2, 0.1, 2.4), (0.0, 0.0, 0.0), 70.0)

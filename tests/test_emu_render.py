@@ -362,7 +362,7 @@ def test_random_material_scenes_all_integrators(emu, orc, gpurt, seed):
              max_depth=4, env_scale=0.3, use_metalness=seed % 2, seed=100 * seed + integ)
 
 
-def test_textured_quads_all_texture_kinds(emu, orc, gpurt):
+def _textured_quads_scene(gpurt):
     """albedo / emissive / metal-rough / normal textures, sRGB decode, bilinear + REPEAT with negative and > 1
     coordinates, an emissive-textured light (light_sample's texture path and the Q5 texcoord quirk)"""
     rng = np.random.default_rng(5)
@@ -393,6 +393,11 @@ def test_textured_quads_all_texture_kinds(emu, orc, gpurt):
     e.albedo_tex, e.emissive_tex, e.metal_rough_tex, e.normal_tex = -1, 1, -1, -1
     e.metal_rough[:] = (0, 1)
     quad(3.0, 0.8, e, uvscale=1.0)
+    return scene, texs
+
+
+def test_textured_quads_all_texture_kinds(emu, orc, gpurt):
+    scene, texs = _textured_quads_scene(gpurt)
     cam = gpurt.camera(1, 64, 48, (1.5, 1.0, 2.5), (0.0, 0.0, 0.5), 70.0)
     for integ in (0, 1, 2, 3, 4):
         img = _run(emu, orc, gpurt, scene, 64, 48, 2, cam=cam, textures=texs, integrator=integ, brdf=1, samples_per_frame=2,

@@ -88,49 +88,101 @@ inline void build_sah_split(const float* tri_lo, const float* tri_hi, size_t str
         int side;       /* 0 left, 1 right */
         unsigned depth;
     };
-    /* split one inner node: partitions items[a, b) and returns the boundary */
-    auto split = [&](const Job& j) -> uint32_t {
+    /* split one inner node: partitions items[a, b) and returns the boundary.  `par` > 1: the two reductions over the
+     * segment (centroid bounds; per-axis bin counts and boxes) are cut into `par` slices and merged — min / max / integer
+     * sums, so the merged values are the sequential ones */
+    struct Bins {
+        Box bb[3][kBins];
+        uint32_t cnt[3][kBins];
+    };
+    auto split = [&](const Job& j, unsigned par) -> uint32_t {
+        const uint32_t m = j.b - j.a;
+        par = std::max(1u, std::min(par, m / 16384u));
+        auto slice = [&](unsigned t, uint32_t& lo, uint32_t& hi) {
+            lo = j.a + (uint32_t)((uint64_t)m * t / par), hi = j.a + (uint32_t)((uint64_t)m * (t + 1) / par);
+        };
+        auto run = [&](auto&& fn) {
+            if(par == 1) return fn(0u);
+            std::vector<std::thread> pool;
+            for(unsigned t = 0; t < par; t++) pool.emplace_back(fn, t);
+            for(auto& th : pool) th.join();
+        };
+        Box cb_one;
+        Bins bins_one; /* the common case (par == 1) stays on the stack */
+        std::vector<Box> cb_many(par > 1 ? par : 0);
+        std::vector<Bins> bins_many(par > 1 ? par : 0);
+        Box* cbs = par > 1 ? cb_many.data() : &cb_one;
+        Bins* part = par > 1 ? bins_many.data() : &bins_one;
+        run([&](unsigned t) {
+            uint32_t lo, hi;
+            slice(t, lo, hi);
+            Box c = empty_box();
+            for(uint32_t i = lo; i < hi; i++) grow(c, &cen[3ull * items[i]], &cen[3ull * items[i]]);
+            cbs[t] = c;
+        });
         Box cb = empty_box();
-        for(uint32_t i = j.a; i < j.b; i++) grow(cb, &cen[3ull * items[i]], &cen[3ull * items[i]]);
+        for(unsigned t = 0; t < par; t++) grow(cb, cbs[t].lo, cbs[t].hi);
+        float scale[3];
+        bool use[3];
+        for(int ax = 0; ax < 3; ax++) {
+            const float ext = cb.hi[ax] - cb.lo[ax];
+            use[ax] = ext > 0.0f;
+            scale[ax] = use[ax] ? (float)kBins / ext : 0.0f;
+        }
+        run([&](unsigned t) {
+            uint32_t lo, hi;
+            slice(t, lo, hi);
+            Bins& B = part[t];
+            for(int ax = 0; ax < 3; ax++)
+                for(int k = 0; k < kBins; k++) B.bb[ax][k] = empty_box(), B.cnt[ax][k] = 0;
+            for(uint32_t i = lo; i < hi; i++) {
+                const uint32_t g = items[i];
+                for(int ax = 0; ax < 3; ax++) {
+                    if(!use[ax]) continue;
+                    const int bi = bin_of(cen[3ull * g + ax], cb.lo[ax], scale[ax]);
+                    B.cnt[ax][bi]++;
+                    grow(B.bb[ax][bi], tri_lo + stride * g, tri_hi + stride * g);
+                }
+            }
+        });
         int best_axis = -1, best_k = 0;
         float best_cost = 3.0e38f;
         for(int ax = 0; ax < 3; ax++) {
-            const float ext = cb.hi[ax] - cb.lo[ax];
-            if(!(ext > 0.0f)) continue;
-            const float scale = (float)kBins / ext;
+            if(!use[ax]) continue;
             Box bb[kBins];
             uint32_t cnt[kBins];
-            for(int k = 0; k < kBins; k++) bb[k] = empty_box(), cnt[k] = 0;
-            for(uint32_t i = j.a; i < j.b; i++) {
-                const uint32_t g = items[i];
-                const int bi = bin_of(cen[3ull * g + ax], cb.lo[ax], scale);
-                cnt[bi]++;
-                grow(bb[bi], tri_lo + stride * g, tri_hi + stride * g);
+            for(int k = 0; k < kBins; k++) {
+                bb[k] = empty_box(), cnt[k] = 0;
+                for(unsigned t = 0; t < par; t++) {
+                    const Bins& B = part[t];
+                    cnt[k] += B.cnt[ax][k];
+                    if(B.cnt[ax][k]) grow(bb[k], B.bb[ax][k].lo, B.bb[ax][k].hi);
+                }
             }
             float right_area[kBins];
             uint32_t right_cnt[kBins];
-            Box run = empty_box();
+            Box run_box = empty_box();
             uint32_t c = 0;
             for(int k = kBins - 1; k >= 1; k--) {
-                if(cnt[k]) grow(run, bb[k].lo, bb[k].hi);
+                if(cnt[k]) grow(run_box, bb[k].lo, bb[k].hi);
                 c += cnt[k];
-                right_cnt[k] = c, right_area[k] = c ? area(run) : 0.0f;
+                right_cnt[k] = c, right_area[k] = c ? area(run_box) : 0.0f;
             }
-            run = empty_box(), c = 0;
+            run_box = empty_box(), c = 0;
             for(int k = 1; k < kBins; k++) {
-                if(cnt[k - 1]) grow(run, bb[k - 1].lo, bb[k - 1].hi);
+                if(cnt[k - 1]) grow(run_box, bb[k - 1].lo, bb[k - 1].hi);
                 c += cnt[k - 1];
                 if(c == 0 || right_cnt[k] == 0) continue;
-                const float cost = area(run) * (float)c + right_area[k] * (float)right_cnt[k];
+                const float cost = area(run_box) * (float)c + right_area[k] * (float)right_cnt[k];
                 if(cost < best_cost) best_cost = cost, best_axis = ax, best_k = k;
             }
         }
         if(best_axis < 0) return j.a + (j.b - j.a) / 2;
-        const float lo = cb.lo[best_axis], scale = (float)kBins / (cb.hi[best_axis] - cb.lo[best_axis]);
+        const float lo = cb.lo[best_axis], sc = scale[best_axis];
         uint32_t nl = 0, nr = 0;
         for(uint32_t i = j.a; i < j.b; i++) { /* stable partition through this segment's slice of the scratch array */
             const uint32_t g = items[i];
-            const int bi = bin_of(cen[3ull * g + best_axis], lo, scale);
+            const int bi = bin_of(cen[3ull * g + best_axis], lo, sc);
             if(bi < best_k) items[j.a + nl++] = g;
             else scratch[j.a + nr++] = g;
         }
@@ -138,7 +190,7 @@ inline void build_sah_split(const float* tri_lo, const float* tri_hi, size_t str
         return j.a + nl; /* both sides are non-empty by construction of best_k */
     };
     /* emit the node or leaf of job j; inner nodes return their two child jobs */
-    auto emit = [&](const Job& j, Job out[2]) -> int {
+    auto emit = [&](const Job& j, Job out[2], unsigned par) -> int {
         int ref, n_out = 0;
         if(j.b - j.a == 1) {
             T.order[j.a] = items[j.a];
@@ -148,7 +200,7 @@ inline void build_sah_split(const float* tri_lo, const float* tri_hi, size_t str
             ref = j.me;
             T.parent[j.me] = j.parent;
             T.range_first[j.me] = (int)j.a, T.range_last[j.me] = (int)j.b - 1;
-            const uint32_t mid = split(j);
+            const uint32_t mid = split(j, par);
             /* preorder: the left subtree takes the ids right after this node, (mid - a) - 1 of them */
             out[0] = Job{j.a, mid, j.me + 1, j.me, 0, j.depth + 1};
             out[1] = Job{mid, j.b, j.me + (int)(mid - j.a), j.me, 1, j.depth + 1};
@@ -164,7 +216,7 @@ inline void build_sah_split(const float* tri_lo, const float* tri_hi, size_t str
             stack.pop_back();
             if(j.b - j.a > 1) max_depth = std::max(max_depth, j.depth);
             Job out[2];
-            if(emit(j, out) == 2) stack.push_back(out[1]), stack.push_back(out[0]);
+            if(emit(j, out, 1) == 2) stack.push_back(out[1]), stack.push_back(out[0]);
         }
     };
     if(threads == 0) threads = std::max(1u, std::thread::hardware_concurrency());
@@ -181,7 +233,7 @@ inline void build_sah_split(const float* tri_lo, const float* tri_hi, size_t str
         }
         if(j.b - j.a > 1) depth = std::max(depth, j.depth);
         Job out[2];
-        if(emit(j, out) == 2) top.push_back(out[1]), top.push_back(out[0]);
+        if(emit(j, out, threads) == 2) top.push_back(out[1]), top.push_back(out[0]);
     }
     if(!tasks.empty()) {
         std::atomic<size_t> next{0};

@@ -208,7 +208,7 @@ int gpurt_camera_make(int mode, float width, float height, const float pos[3],
  * binary topology from a top-down binned-SAH split computed on the host (gpu-rt_b200/host/sah_split.h) instead of the
  * Morton sort; refit, wide collapse and traversal unchanged, query results unchanged.  For static scenes with real
  * meshes: about 30 % fewer node visits per ray on media/cbox in the CPU probe (tools/sah_probe.py), nothing on
- * regular procedural geometry; the host pass costs ~8 ms per 16 k triangles, ~140 ms per 262 k (8 threads).  Composes with
+ * regular procedural geometry; the host pass costs ~8 ms per 16 k triangles, ~105 ms per 262 k (8 threads).  Composes with
  * GPURT_BUILD_SAH_COLLAPSE.  gpurt_accel_get_morton_keys returns positions 0..n-1 in this mode. */
 #define GPURT_BUILD_SAH_SPLIT 4u
 int gpurt_accel_build(gpurt_scene* scene, uint32_t flags, gpurt_accel** out);

@@ -8,6 +8,7 @@
 #include <vector>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <thread>
 
@@ -319,6 +320,20 @@ unsigned emu_sah_bvh2(const float* tris9, unsigned n, int bins, unsigned* order,
         }
     }
     return T.depth;
+}
+
+/* milliseconds of build_sah_split() alone with a given thread count (0 = all cores) */
+double emu_sah_split_ms(const float* tris9, unsigned n, unsigned threads) {
+    std::vector<float> lo(4ull * n), hi(4ull * n);
+    for(unsigned g = 0; g < n; g++)
+        for(int k = 0; k < 3; k++) {
+            const float* t = tris9 + 9ull * g;
+            lo[4ull * g + k] = fminf(fminf(t[k], t[3 + k]), t[6 + k]), hi[4ull * g + k] = fmaxf(fmaxf(t[k], t[3 + k]), t[6 + k]);
+        }
+    SahSplitTree T;
+    auto t0 = std::chrono::steady_clock::now();
+    build_sah_split(lo.data(), hi.data(), 4, n, T, threads);
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
 }
 
 /* consistency of every array build_sah_split() hands to the device stages: 0 = fine, else the number of the failed check */

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""Rewrite the reference's shader sources into C++-compilable text under oracle/_ref/ (git-ignored; TEST
-INFRASTRUCTURE — see oracle/ref_shim/glsl_compat.h).  Nothing of the shader text is stored in the repository.
+"""Rewrite the reference's shader sources into C++-compilable text under oracle/_ref/ (TEST INFRASTRUCTURE — see
+oracle/ref_shim/glsl_compat.h).  oracle/Makefile deletes the rewritten text again right after compiling it: nothing of
+the shader text is stored in the repository or left in the tree.
 usage: python oracle/make_glsl_ref.py /root/reference oracle/_ref
 writes rt_glsl_gen.inc (rtcommon.glsl + restir.glsl), rt_rgen_gen.inc (rt.rgen without its binding declarations)
 and tonemap_gen.inc (tonemap.frag)"""

@@ -4,7 +4,7 @@
  * (TEST INFRASTRUCTURE, oracle/_ref only).
  *
  * The shader text is not copied into this repository: oracle/make_glsl_ref.py reads it where it lies under
- * /root/reference and writes a lightly rewritten copy into oracle/_ref/ (git-ignored): `inout T x` / `out T x` become
+ * /root/reference and writes a lightly rewritten copy into oracle/_ref/ for the duration of the compile (removed afterwards; only the compiled library stays): `inout T x` / `out T x` become
  * `T& x`, decimal literals get an `f` suffix so that arithmetic stays fp32 as in GLSL, layout / binding declarations
  * are dropped (their storage is declared here), constructor calls with two random draws are brace-initialised
  * (GLSL evaluates arguments left to right, C++ does not promise to).

@@ -22,6 +22,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 #include "../host/camera.h"
 #include "device.cuh"
@@ -461,16 +462,21 @@ static int pipe_light_accel(gpurt_pipe* p) {
     return GPURT_OK;
 }
 
-static void upload_lut_once() {
-    static bool done = false;
-    if(done) return;
+/* __constant__ symbols exist once per device: the table is uploaded once per device ordinal */
+static cudaError_t upload_lut_once(int device) {
+    static std::mutex mu;
+    static bool done[256] = {};
+    std::lock_guard<std::mutex> lock(mu);
+    if(device < 0 || device >= 256) return cudaErrorInvalidDevice;
+    if(done[device]) return cudaSuccess;
     float lut[256];
     for(int i = 0; i < 256; i++) {
         double c = i / 255.0;
         lut[i] = (float)(c <= 0.04045 ? c / 12.92 : std::pow((c + 0.055) / 1.055, 2.4));
     }
-    cudaMemcpyToSymbol(c_srgb_lut, lut, sizeof(lut));
-    done = true;
+    cudaError_t e = cudaMemcpyToSymbol(c_srgb_lut, lut, sizeof(lut));
+    if(e == cudaSuccess) done[device] = true;
+    return e;
 }
 
 } // namespace gpurt
@@ -480,12 +486,12 @@ extern "C" {
 int gpurt_pipe_create(gpurt_scene* scene, gpurt_accel* accel, gpurt_pipe** out) {
     if(!scene || !accel || !out) return set_error("NULL argument"), GPURT_E_INVALID;
     if(accel->scene != scene) return set_error("accel was built from a different scene"), GPURT_E_STATE;
+    GPURT_CUDA(cudaSetDevice(accel->ctx->device));
+    GPURT_CUDA(upload_lut_once(accel->ctx->device));
     gpurt_pipe* p = new gpurt_pipe;
     p->ctx = accel->ctx, p->scene = scene, p->accel = accel;
     std::memset(&p->old_cam, 0, sizeof(p->old_cam));
     std::memset(&p->last, 0, sizeof(p->last));
-    GPURT_CUDA(cudaSetDevice(p->ctx->device));
-    upload_lut_once();
     if(const char* e = getenv("GPURT_WAVE_DEPTH")) p->wave_depth = (uint32_t)std::max(1, atoi(e)); /* tuning knob */
     if(const char* e = getenv("GPURT_WAVE_ESTIMATE")) p->use_est = atoi(e) != 0;                   /* A/B knob */
     if(const char* e = getenv("GPURT_LIGHT_GROUPS")) p->use_lgrp = atoi(e) != 0;                   /* A/B knob */

@@ -19,6 +19,14 @@ bool gpurt_scene::pack() {
     PackedScene& P = packed;
     P = PackedScene();
     scene.build_desc(P.descs, P.lights);
+    /* a material may name a texture that does not exist (a glTF image that failed to load shifts the table; add_object
+     * copies the ids verbatim): the reference would index past its descriptor array, here the slot falls back to the
+     * constant factor (-1) and the last-error string says so */
+    int ntex = (int)scene.textures.size(), dropped = 0;
+    for(SceneDesc& d : P.descs)
+        for(int32_t* t : {&d.albedo_tex, &d.emissive_tex, &d.metal_rough_tex, &d.normal_tex})
+            if(*t >= ntex) *t = -1, dropped++;
+    if(dropped) set_error("warning: " + std::to_string(dropped) + " material texture id(s) beyond the texture table were reset to -1");
     P.tri_off.push_back(0);
     P.vert_off.push_back(0);
     bool ok = true;

@@ -166,27 +166,45 @@ def frame_cases(gpurt):
                         use_metalness=seed % 2, seed=100 * seed + integ))
 
 
-def frame_digests(gpurt, orc, render):
-    """{case/frame/buffer: sha256} of the raw output buffers of `render` (the compiled reference or the oracle)"""
+def buffer_digest(arr):
+    """SHA-256 of a frame buffer's words with every NaN replaced by the canonical quiet NaN 0x7fc00000: which NaN an
+    operation returns (sign, payload) is left open by GLSL and differs between x86 (first operand's payload) and the GPU
+    (0x7fffffff); everything that is a number — or an integer word such as n_seen — is compared bit for bit"""
     import hashlib
+    w = np.ascontiguousarray(arr).view(np.uint32).copy()
+    w[(w & 0x7FFFFFFF) > 0x7F800000] = 0x7FC00000
+    return hashlib.sha256(w.tobytes()).hexdigest()
+
+
+def frame_digests(gpurt, orc, render):
+    """{case/frame/buffer: sha256} of the output buffers of `render` (the compiled reference or the oracle).  Every case
+    is rendered as frames 0, 1, 2, ... (keys case/frameF/...); the ReSTIR cases (integrators 3 / 4, whose frames depend on
+    the previous one) additionally as the sequence a freshly created RTPipe produces — frame 0 twice, both with prev_PV =
+    identity, because `old_cam` is only assigned during the second call (rt.cpp:121-138) — under case/pipeK/... for call K"""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import test_emu_render as T
     out = {}
-    for name, scene, texs, w, h, frames, cam, kw in frame_cases(gpurt):
-        rs = orc.RenderScene(scene, texs)
-        rs.gscene, rs.textures = scene, texs   # for renderers that build their own structures from the scene
+
+    def sequence(name, tag, rs, w, h, cam, texs, kw, plan):
         st = orc.FrameState(w, h)
-        cam = cam or gpurt.camera(0, w, h)
-        for f in range(frames):
-            consts, ubo, seed = T._uniforms(gpurt, rs, cam, f, **kw)
+        for k, (f, ident) in enumerate(plan):
+            consts, ubo, seed = T._uniforms(gpurt, rs, cam, f, prev_identity=ident, **kw)
             counts = render(rs, st, consts, ubo, seed, len(texs))
             cur = st.parity ^ 1
             bufs = {"image": st.image, "pos": st.gb[cur][0], "norm": st.gb[cur][1], "albedo": st.gb[cur][2]}
             if kw.get("integrator", 0) in (3, 4):
                 bufs["reservoirs"] = st.res[cur]
             for b, arr in bufs.items():
-                out[f"{name}/frame{f}/{b}"] = hashlib.sha256(np.ascontiguousarray(arr).tobytes()).hexdigest()
-            out[f"{name}/frame{f}/rays"] = f"{int(counts[0])},{int(counts[1])}"
+                out[f"{name}/{tag}{k}/{b}"] = buffer_digest(arr)
+            out[f"{name}/{tag}{k}/rays"] = f"{int(counts[0])},{int(counts[1])}"
+
+    for name, scene, texs, w, h, frames, cam, kw in frame_cases(gpurt):
+        rs = orc.RenderScene(scene, texs)
+        rs.gscene, rs.textures = scene, texs   # for renderers that build their own structures from the scene
+        cam = cam or gpurt.camera(0, w, h)
+        sequence(name, "frame", rs, w, h, cam, texs, kw, [(f, False) for f in range(frames)])
+        if kw.get("integrator", 0) in (3, 4):
+            sequence(name, "pipe", rs, w, h, cam, texs, kw, [(0, True), (0, True)] + [(f, False) for f in range(1, frames)])
     return out
 
 

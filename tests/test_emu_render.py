@@ -77,7 +77,7 @@ class EmuScene:
             self.emu.emu_free(self.lh)
 
 
-def _uniforms(gpurt, rs, cam, frame, **kw):
+def _uniforms(gpurt, rs, cam, frame, prev_identity=False, **kw):
     """the words RTPipe::trace / update_uniforms would push (rt.cpp:121-138, :355-368) for these tunables"""
     p = gpurt.pipe_params(**kw)
     c = gpurt.Constants()
@@ -92,6 +92,8 @@ def _uniforms(gpurt, rs, cam, frame, **kw):
     V = np.array(cam.V, np.float32).reshape(4, 4).T
     P = np.array(cam.P, np.float32).reshape(4, 4).T
     cam.prev_PV = (C.c_float * 16)(*(P @ V).T.reshape(-1))   # static camera: prev_PV = P * V
+    if prev_identity:                                        # the first two calls of a new RTPipe (old_cam = {})
+        cam.prev_PV = (C.c_float * 16)(*np.eye(4, dtype=np.float32).reshape(-1))
     return np.frombuffer(bytes(c), np.uint32).copy(), np.frombuffer(bytes(cam), np.uint32).copy(), p.seed
 
 

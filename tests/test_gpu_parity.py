@@ -365,9 +365,6 @@ def test_sah_optimal_collapse_flag(gpurt, orc, ctx):
     sah.close(), base.close(), scene.close()
 
 
-@pytest.mark.skipif(os.environ.get("GPURT_TEST_EXPERIMENTAL") != "1",
-                    reason="GPURT_BUILD_SAH_SPLIT was written after the round's GPU budget was spent: checked on the CPU replay "
-                           "only (tests/test_emu.py); run with GPURT_TEST_EXPERIMENTAL=1 on a GPU box")
 def test_sah_split_build_flag(gpurt, orc, ctx):
     """GPURT_BUILD_SAH_SPLIT: host-side binned-SAH order + topology, device refit / collapse / traversal: same query
     results as the default build and the oracle, also combined with the SAH-optimal collapse and after a pose edit"""

@@ -18,6 +18,12 @@ One "step" = one pass of the hot path (closest-hit traversal) over the whole ray
 path: it runs inside the Vulkan driver — see DESIGN.md §6).
 
 Launch: python bench.py --gpus N --steps K --warmup W   (N>1 under torchrun, one rank per GPU).
+
+At N > 1 (one rank per GPU, scene replicated, one view per rank = weak scaling) the timed step includes result
+placement: every rank's trace kernel stores its hits straight into rank 0's result array over NVLink
+(gpurt_shared_alloc / gpurt_shared_open), so a step ends with all N result sets in rank 0's HBM.  The line also carries
+`placement` (the same step with results left local, and an NCCL gather of the same bytes, for comparison) and `strong`
+(BASELINE configs 4 and 5 at the same N: fixed total work sharded over the ranks, results placed on rank 0).
 """
 import argparse
 import json
@@ -141,6 +147,9 @@ def reference_arm(args, rank, world):
     if rank != 0:
         return
     sys.path.insert(0, os.path.join(ROOT, "tests"))
+    # the CPU arm never maps the CUDA library: the scene is constructed by the host half alone (libgpurt_host.so = glTF
+    # loader / stand-in generator / camera, g++ only), everything timed is oracle/
+    os.environ["GPURT_LIB"] = os.path.join(ROOT, "gpu-rt_b200", "libgpurt_host.so")
     import gpurt
     import orc
     scene, label = build_scene(gpurt, None)
@@ -178,6 +187,226 @@ def reference_arm(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def bind_to_gpu_numa(local):
+    """Pin this rank's host threads (and, by first touch, its pinned staging memory) to the NUMA node the GPU hangs
+    off, when the box exposes one (SCALE_r01: e2e scaled 2.4x on 8 GPUs with every rank's staging memory wherever the
+    scheduler put it).  Returns what was found, for the JSON line."""
+    info = {"numa_node": None, "cpus": len(os.sched_getaffinity(0)), "bound": False}
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        dev = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        base = f"/sys/bus/pci/devices/{dev}"
+        node = int(open(f"{base}/numa_node").read())
+        cpus = set()
+        for part in open(f"{base}/local_cpulist").read().strip().split(","):
+            if part:
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        info["numa_node"] = node
+        cpus &= os.sched_getaffinity(0)
+        if node >= 0 and cpus and len(cpus) < info["cpus"]:
+            os.sched_setaffinity(0, cpus)
+            info["cpus"], info["bound"] = len(cpus), True
+    except Exception as e:  # noqa: BLE001 — diagnostics only
+        info["error"] = str(e)[:80]
+    return info
+
+
+def device_max(dist, world, x, dev, op="max"):
+    import torch
+    t = torch.tensor([float(x)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX if op == "max" else dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+def roofline_obj(kernel, n, ms, nodes, tris, stream_bytes, peak, peak_src, ncu=None):
+    """logical bytes = stream + 80 B x nodes visited + 48 B x triangles tested per element, over the
+    kernel's device time; `ncu` adds the physical side of the same kernel from the committed capture"""
+    bpe = stream_bytes + BYTES_NODE * nodes + BYTES_TRI * tris
+    achieved = bpe * n / (ms * 1e-3) / 1e9
+    o = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+         "peak_source": peak_src, "kernel": kernel, "elements": int(n), "kernel_ms": ms, "bytes_per_element": bpe,
+         "nodes_per_element": nodes, "tris_per_element": tris, "stream_floor_bytes_per_element": stream_bytes,
+         "m_elements_s": n / (ms * 1e-3) / 1e6,
+         "frac_is": "LOGICAL bytes (the BVH is L2-resident): read dram_frac and issue_lane_frac for what the hardware sees"}
+    if ncu:
+        o["traffic"] = ncu["dram_bytes_per_element"] * n
+        o["traffic_source"] = ncu["source"]
+        o["dram_frac"] = o["traffic"] / (ms * 1e-3) / 1e9 / peak
+        sc = ncu.get("secondary_ceilings") or {}
+        if "issue_slots_active_pct" in sc and "lanes_per_instruction" in sc:
+            o["issue_lane_frac"] = sc["issue_slots_active_pct"] / 100.0 * sc["lanes_per_instruction"] / 32.0
+        o["secondary_ceilings"] = sc
+    return o
+
+
+def ncu_facts():
+    """physical-side numbers of the committed ncu captures (never measured under the profiler here), newest round first"""
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        p = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(p):
+            tj = json.load(open(p))
+            if "kernels" not in tj:  # round-1 layout: the closest-hit kernel only
+                tj = {"kernels": {"closest": {"dram_bytes_per_element": tj["dram_bytes_per_ray"], "source": tj["source"],
+                                              "secondary_ceilings": tj.get("secondary_ceilings")}}}
+            return tj["kernels"]
+    return {}
+
+
+# ---- strong-scaling sub-benchmarks (BASELINE configs 4 and 5 at the same N) -----------------------------------------
+def strong_config4(gpurt, torch, dist, ctx, rank, world, dev, n_tris, n_queries, check):
+    """config 4: 10 M-triangle soup, 100 M closest-point queries in contiguous ranges per rank, all 3.2 GB of results
+    placed in rank 0's memory inside the timed region: rank 0's kernel writes there directly; the other ranks compute
+    chunk k into a local buffer while chunk k-1 crosses NVLink on a second stream (copy engine, no collective)."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from config4_cpq import make_queries, make_soup
+    from gpurt.dist import shard_range, shared_result_buffer
+    tris_h = make_soup(n_tris, dev).cpu().numpy()
+    scene = gpurt.Scene(ctx)
+    scene.add_triangles(tris_h)
+    accel = gpurt.Accel(scene)
+    info = accel.info()
+    a, b = shard_range(n_queries, rank, world)
+    nq = b - a
+    chunk = max(1 << 20, min(6_250_000, (nq + 3) // 4))
+    q = torch.empty((nq, 4), dtype=torch.float32, device=dev)
+    for c0 in range(0, nq, 12_500_000):
+        c1 = min(nq, c0 + 12_500_000)
+        q[c0:c1] = make_queries(a + c0, a + c1, dev)
+    shared = shared_result_buffer(ctx, n_queries * 32)
+    remote = shared.tensor().view(torch.float32).view(-1, 8)       # rank 0: its own memory; others: NVLink mapping
+    local = [torch.empty((chunk, 8), dtype=torch.float32, device=dev) for _ in range(2)] if rank else None
+    main_s, copy_s = torch.cuda.current_stream(), torch.cuda.Stream()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    free_ev = [None, None]
+
+    def run():
+        e0.record()
+        for k, c0 in enumerate(range(0, nq, chunk)):
+            c1 = min(nq, c0 + chunk)
+            if rank == 0:
+                accel.closest_points(q[c0:c1], shared.at((a + c0) * 32))
+                continue
+            buf = local[k & 1]
+            if free_ev[k & 1] is not None:
+                main_s.wait_event(free_ev[k & 1])                  # the copy that last read this buffer is done
+            accel.closest_points(q[c0:c1], buf[: c1 - c0])
+            done = torch.cuda.Event()
+            done.record(main_s)
+            copy_s.wait_event(done)
+            with torch.cuda.stream(copy_s):
+                remote[a + c0:a + c1].copy_(buf[: c1 - c0], non_blocking=True)
+                free_ev[k & 1] = torch.cuda.Event()
+                free_ev[k & 1].record(copy_s)
+        main_s.wait_stream(copy_s)
+        e1.record()
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    run()                                                          # warm-up (communicators, arenas, sort scratch)
+    sync()
+    t0 = time.time()
+    run()
+    sync()
+    wall = time.time() - t0
+    ms = device_max(dist, world, e0.elapsed_time(e1), dev)
+    # the same queries with the results left on each rank (no placement): what the kernels alone take
+    e0.record()
+    for c0 in range(0, nq, chunk):
+        c1 = min(nq, c0 + chunk)
+        accel.closest_points(q[c0:c1], local[0][: c1 - c0] if rank else shared.at((a + c0) * 32))
+    e1.record()
+    sync()
+    ms_local = device_max(dist, world, e0.elapsed_time(e1), dev)
+    out = {"config": "4: synthetic 10 M-triangle soup, 100 M closest-point queries", "tris": info.n_tris, "queries": n_queries,
+           "n_gpus": world, "mqueries_s": n_queries / (ms * 1e-3) / 1e6, "ms": ms, "wall_ms_barrier_to_barrier": wall * 1e3,
+           "results": "all results in rank 0's memory at the end of the timed region (rank 0: direct; others: chunk k computed "
+                      "while chunk k-1 is copied over NVLink, no collective)",
+           "bytes_into_rank0": int((n_queries - (shard_range(n_queries, 0, world)[1])) * 32), "chunk_queries": chunk,
+           "mqueries_s_results_left_local": n_queries / (ms_local * 1e-3) / 1e6, "bvh_build_ms": info.build_ms}
+    if rank == 0 and check:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import orc
+        c0 = shard_range(n_queries, world - 1, world)[0]           # a slice the LAST rank placed
+        got = remote[c0:c0 + check].cpu().numpy().view(np.uint32)
+        ref = orc.Bvh(tris_h).closest_point(make_queries(c0, c0 + check, dev).cpu().numpy()).view(np.uint32).reshape(-1, 8)
+        out["check"] = {"queries": check, "placed_by_rank": world - 1,
+                        "bit_exact_vs_oracle": bool((got[:, [0, 1, 2, 3, 4, 6, 7]] == ref[:, [0, 1, 2, 3, 4, 6, 7]]).all())}
+    if world > 1:
+        dist.barrier()
+    shared.close()
+    accel.close(), scene.close()
+    return out
+
+
+def strong_config5(gpurt, torch, dist, ctx, scene, accel, rank, world, dev, label, verify=True):
+    """config 5: 3840x2160, 64 spp as 8 samples x 8 progressive frames, integrator 1, depth 8, RR on.  Frame f is rendered
+    at full resolution by rank f mod N; its frame-end kernel stores the per-pixel mean straight into rank 0's buffer over
+    NVLink; rank 0 folds the means in frame order (rt.rgen:640-645) — bit-identical to the sequential loop."""
+    from gpurt.dist import shared_result_buffer
+    w, h, F, spp = 3840, 2160, 8, 8
+    pipe = gpurt.RTPipe(scene, accel)
+    cam = gpurt.camera(1, w, h, CAM_POS, CAM_AT, VFOV)
+    prm = gpurt.pipe_params(integrator=1, brdf=1, max_depth=8, samples_per_frame=spp, max_frames=F - 1, use_rr=1,
+                            env_scale=1.0, seed=7)
+    img_bytes = w * h * 16
+    means = shared_result_buffer(ctx, F * img_bytes)
+    mine = list(range(rank, F, world))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def run():
+        e0.record()
+        for f in mine:
+            pipe.render_frame_mean(prm, cam, w, h, f, means.at(f * img_bytes))
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()                                         # every mean is in rank 0's memory
+        fold = 0.0
+        if rank == 0:
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            for f in range(F):
+                pipe.accumulate_mean(means.at(f * img_bytes), f, w, h)
+            f1.record()
+            torch.cuda.synchronize()
+            fold = f0.elapsed_time(f1)
+        return fold
+
+    run()
+    if world > 1:
+        dist.barrier()
+    t0 = time.time()
+    fold_ms = run()
+    wall = time.time() - t0
+    ms = device_max(dist, world, e0.elapsed_time(e1) if mine else 0.0, dev)
+    total_s = (ms + fold_ms) * 1e-3
+    out = None
+    if rank == 0:
+        identical = None
+        if verify:
+            ref = gpurt.RTPipe(scene, accel)
+            while ref.render_frame(prm, cam, w, h) == 0:
+                pass
+            identical = bool(torch.equal(ref.device_image().view(torch.int32), pipe.device_image().view(torch.int32)))
+            ref.close()
+        out = {"config": "5: Sponza 3840x2160, 64 spp (8 x 8 progressive frames), integrator 1, depth 8, RR", "scene": label,
+               "n_gpus": world, "s_per_image": total_s, "mpaths_s": w * h * spp * F / total_s / 1e6,
+               "render_ms_max_rank": ms, "fold_ms_rank0": fold_ms, "wall_s_incl_barriers": wall,
+               "results": "frame means stored into rank 0's buffer by the frame-end kernel over NVLink, folded there in frame order",
+               "bytes_into_rank0": int(img_bytes * (F - len(range(0, F, world)))), "bit_identical_to_sequential_render": identical}
+    if world > 1:
+        dist.barrier()
+    means.close()
+    pipe.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -185,6 +414,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-strong", action="store_true", help="skip the config-4 / config-5 strong-scaling sub-benchmarks")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -193,13 +423,17 @@ def main():
     if args.impl == "reference":
         return reference_arm(args, rank, world)
 
+    host = bind_to_gpu_numa(local)
     import torch
     import torch.distributed as dist
     import gpurt
+    from gpurt.dist import gather_to_rank0, shared_result_buffer, warmup as dist_warmup
 
     torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.init_process_group("nccl", device_id=dev)
+        dist_warmup(dev)
     ctx = gpurt.Context(local)
     scene, label = build_scene(gpurt, ctx)
     gpurt.Accel(scene).close()      # first build warms the allocation pool
@@ -232,8 +466,19 @@ def main():
     d_hits = torch.empty((n_rays, 4), dtype=torch.float32, device="cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
+    # ---- result placement (N > 1): every rank's hits go into rank 0's array, written by the trace kernel itself ----
+    counts = [n_rays]
+    if world > 1:
+        t = torch.tensor([n_rays], dtype=torch.int64, device=dev)
+        ts = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(ts, t)
+        counts = [int(x.item()) for x in ts]
+    offs = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    shared = shared_result_buffer(ctx, int(offs[-1]) * 16) if world > 1 else None
+    dst = shared.at(int(offs[rank]) * 16) if world > 1 else d_hits
+
     def step():
-        accel.trace_closest(d_rays, d_hits)
+        accel.trace_closest(d_rays, dst)
 
     def barrier():
         torch.cuda.synchronize()
@@ -255,39 +500,78 @@ def main():
         a.record()
         step()
         b.record()
-    barrier()
+    barrier()                  # every rank's stores have landed in rank 0's memory
     wall = time.time() - wall0
     sampler.window[1] = wall0 + wall
     ms = sum(a.elapsed_time(b) for a, b in ev)
     clocks = sampler.summary()
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    tot = torch.tensor([float(n_rays)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    total_rays = float(tot.item())
+    ms_max = device_max(dist, world, ms, dev)
+    total_rays = device_max(dist, world, n_rays, dev, "sum")
     value = total_rays * args.steps / (ms_max * 1e-3) / 1e6
 
-    # ---- roofline of the trace kernel (rank 0's numbers) ---------------------------------------
-    st = accel.trace_stats(d_rays, d_hits)
-    nodes_per_ray = st.nodes_visited / st.rays
-    tris_per_ray = st.tris_tested / st.rays
-    bytes_per_ray = BYTES_STREAM + BYTES_NODE * nodes_per_ray + BYTES_TRI * tris_per_ray
-    kernel_ms = ms / args.steps
-    achieved = bytes_per_ray * n_rays / (kernel_ms * 1e-3) / 1e9
-    peak, peak_src = peaks()
+    # ---- placement: verification + what it costs (results left local; NCCL gather of the same bytes) --------------
+    placement = None
+    accel.trace_closest(d_rays, d_hits)
+    if world > 1:
+        def checksum(x):
+            return int(x.contiguous().view(torch.int32).to(torch.int64).sum().item())
+        mine = torch.tensor([checksum(d_hits)], dtype=torch.int64, device=dev)
+        sums = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(sums, mine)
+        ok = None
+        if rank == 0:
+            full = shared.tensor().view(torch.float32).view(-1, 4)
+            ok = all(checksum(full[offs[r]:offs[r + 1]]) == int(sums[r].item()) for r in range(world))
+            assert ok, "hits placed in rank 0's array differ from the ranks' local results"
+        k_local = max(5, min(args.steps, 30))
+        evl = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(k_local)]
+        for a, b in evl:
+            flush.zero_()
+            a.record()
+            accel.trace_closest(d_rays, d_hits)
+            b.record()
+        barrier()
+        local_ms = device_max(dist, world, sum(a.elapsed_time(b) for a, b in evl) / k_local, dev)
+        gather_to_rank0(d_hits)
+        g = []
+        for _ in range(3):
+            barrier()
+            t0 = time.time()
+            gather_to_rank0(d_hits)
+            torch.cuda.synchronize()
+            g.append(device_max(dist, world, (time.time() - t0) * 1e3, dev))
+        placement = {"how": "k_trace_closest stores its hits into rank 0's array over NVLink (gpurt_shared_*); no collective",
+                     "bytes_into_rank0_per_step": int((offs[-1] - offs[1]) * 16), "verified_on_rank0": ok,
+                     "ms_per_step_with_placement": ms_max / args.steps, "ms_per_step_results_left_local": local_ms,
+                     "collective_ms": 0.0, "nccl_gather_ms_same_bytes": float(np.median(g)),
+                     "note": "compute-then-NCCL-gather would cost results_left_local + nccl_gather per step"}
 
-    # primary-only pass (SURVEY §8d headline) and closest-point queries on the hit points
+    # ---- rooflines (rank 0's numbers): the frame's ray set, primary rays only, closest-point queries ----------------
+    peak, peak_src = peaks()
+    ncu = ncu_facts()
+    st = accel.trace_stats(d_rays, d_hits)
+    kernel_ms = ms / args.steps
+    roof = roofline_obj("k_trace_closest<false,false>", n_rays, kernel_ms, st.nodes_visited / st.rays, st.tris_tested / st.rays,
+                        BYTES_STREAM, peak, peak_src, ncu.get("closest"))
+    roof.update({"bytes_per_ray": roof["bytes_per_element"], "nodes_per_ray": roof["nodes_per_element"],
+                 "tris_per_ray": roof["tris_per_element"]})
     n_p = prim.shape[0]
-    flush.zero_()
-    accel.trace_closest(d_rays[:n_p], d_hits[:n_p])
-    prim_ms = []
-    for _ in range(5):
+
+    def median_ms(fn, reps=7):
+        out = []
         flush.zero_()
-        accel.trace_closest(d_rays[:n_p], d_hits[:n_p])
-        prim_ms.append(ctx.last_kernel_ms())
+        fn()
+        for _ in range(reps):
+            flush.zero_()
+            fn()
+            out.append(ctx.last_kernel_ms())
+        return float(np.median(out))
+
+    prim_ms = median_ms(lambda: accel.trace_closest(d_rays[:n_p], d_hits[:n_p]))
+    stp = accel.trace_stats(d_rays[:n_p], d_hits[:n_p])
+    roof_primary = roofline_obj("k_trace_closest<false,false>", n_p, prim_ms, stp.nodes_visited / stp.rays, stp.tris_tested / stp.rays,
+                                BYTES_STREAM, peak, peak_src, ncu.get("primary"))
+    bounce_ms = median_ms(lambda: accel.trace_closest(d_rays[n_p:], d_hits[n_p:])) if n_rays > n_p else None
     q_np = np.zeros((n_p, 4), np.float32)
     hp = d_hits[:n_p].cpu().numpy().view(gpurt.HIT_DT).reshape(-1)
     tt = np.where(np.isfinite(hp["t"]), hp["t"], 100.0).astype(np.float32)
@@ -296,11 +580,11 @@ def main():
     q_np[:, 3] = np.inf
     d_q = torch.from_numpy(q_np).cuda()
     d_cp = accel.closest_points(d_q)
-    cpq_ms = []
-    for _ in range(5):
-        flush.zero_()
-        accel.closest_points(d_q, d_cp)
-        cpq_ms.append(ctx.last_kernel_ms())
+    cpq_ms = median_ms(lambda: accel.closest_points(d_q, d_cp))
+    stq = accel.closest_points_stats(d_q)
+    roof_cpq = roofline_obj("k_closest_points<64,false>", n_p, cpq_ms, stq.nodes_visited / stq.rays, stq.tris_tested / stq.rays,
+                            CPQ_BYTES_STREAM, peak, peak_src, ncu.get("cpq"))
+    accel.trace_closest(d_rays, d_hits)
 
     # ---- e2e: C ABI with HOST buffers (pinned), copies inside the timed region ------------------
     h_rays = torch.from_numpy(rays_np).pin_memory()
@@ -314,11 +598,25 @@ def main():
     for _ in range(e2e_steps):
         accel.trace_closest(hr, hh)     # H2D + kernel + D2H + sync inside the call
     barrier()
-    e2e_s = torch.tensor([time.time() - t0], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_val = total_rays * e2e_steps / float(e2e_s.item()) / 1e6
+    e2e_val = total_rays * e2e_steps / device_max(dist, world, time.time() - t0, dev) / 1e6
     assert np.array_equal(hh.view(np.uint32), d_hits.cpu().numpy().view(np.uint32)), "host and device paths disagree"
+    # e2e of the reference-facing call of this path (RTPipe::trace -> rt_target read back): camera uniforms in, the frame's
+    # rays generated, traced and shaded on the device, RGBA32F image out to pinned host memory every frame
+    h_img = torch.empty((H, W, 4), dtype=torch.float32).pin_memory()
+    himg = h_img.numpy()
+    for _ in range(2):
+        pipe.reset_frame()
+        pipe.render_frame(prm, cam, W, H)
+        pipe.read_image(himg)
+    barrier()
+    t0 = time.time()
+    for _ in range(e2e_steps):
+        pipe.reset_frame()
+        pipe.render_frame(prm, cam, W, H)
+        pipe.read_image(himg)
+    barrier()
+    e2e_render_s = device_max(dist, world, time.time() - t0, dev)
+    frame_rays_total = device_max(dist, world, frame_rays[0], dev, "sum")
 
     # ---- CPU baseline on this box's host cores (rank 0, N=1 only) -------------------------------
     cpu = None
@@ -338,15 +636,21 @@ def main():
                "sample": f"all {sample.shape[0]} rays of one step ({dt:.1f} s wall on {cores} threads); "
                          "results compared bit-exactly with the GPU's"}
 
-    # physical DRAM bytes of one launch: dram__bytes_read.sum + dram__bytes_write.sum of k_trace_closest from the
-    # committed ncu capture of this same workload, scaled per ray (never measured under the profiler here)
-    traffic, traffic_src, secondary = None, None, None
-    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if os.path.exists(tpath):
-        tj = json.load(open(tpath))
-        traffic, traffic_src = tj["dram_bytes_per_ray"] * n_rays, tj["source"]
-        secondary = tj.get("secondary_ceilings")   # L2 / issue-slot ceilings of the same ncu capture
+    # ---- strong scaling at this N (configs 4 and 5) ---------------------------------------------
+    strong = None
+    if not args.no_strong:
+        pipe.close()
+        strong = {"config5": strong_config5(gpurt, torch, dist, ctx, scene, accel, rank, world, dev, label)}
+        accel.close()
+        del d_rays, d_hits, flush, d_q, d_cp
+        torch.cuda.empty_cache()
+        strong["config4"] = strong_config4(gpurt, torch, dist, ctx, rank, world, dev, 10_000_000, 100_000_000, 100_000)
+        strong["note"] = ("fixed total work sharded over the ranks of this run; divide by the N=1 line's numbers for the "
+                          "strong-scaling factor")
+
     if rank == 0:
+        sharding = ("one view per rank, scene replicated" + (", every rank's hits stored into rank 0's array by the trace kernel "
+                    "inside the timed region (no collective)" if world > 1 else ", no collective in the timed region"))
         line = {
             "metric": "Mrays/s closest-hit on Sponza", "value": value, "unit": "Mrays/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
@@ -355,25 +659,32 @@ def main():
                        "scene": label, "rays_per_gpu": n_rays, "tris": info.n_tris, "wide_nodes": info.n_wide_nodes,
                        "wide_depth": info.wide_depth, "bvh_build_ms": info.build_ms, "bvh_update_ms": update_ms,
                        "bvh_build_mtris_s": info.n_tris / (info.build_ms * 1e-3) / 1e6,
-                       "l2": "flushed between timed steps (256 MiB memset)", "sharding": "rays sharded per rank, scene replicated, no collective in the timed region"},
-            "e2e": {"value": e2e_val, "unit": "Mrays/s", "h2d_bytes_per_step": int(n_rays * 32), "d2h_bytes_per_step": int(n_rays * 16)},
+                       "l2": "flushed between timed steps (256 MiB memset)", "sharding": sharding},
+            "e2e": {"value": e2e_val, "unit": "Mrays/s", "h2d_bytes_per_step": int(n_rays * 32), "d2h_bytes_per_step": int(n_rays * 16),
+                    "what": "gpurt_trace_closest with pinned HOST ray / hit arrays"},
+            "e2e_render": {"value": frame_rays_total * e2e_steps / e2e_render_s / 1e6, "unit": "Mrays/s",
+                           "ms_per_frame": e2e_render_s / e2e_steps * 1e3, "h2d_bytes_per_step": 416, "d2h_bytes_per_step": W * H * 16,
+                           "what": "gpurt_pipe_render_frame + gpurt_pipe_read_image into pinned host memory (the reference-facing "
+                                   "RTPipe::trace call: rays generated, traced and shaded on the device; closest-hit rays of the frame / wall time)"},
             "gpu_launches": args.steps,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel": "k_trace_closest<false>",
-                         "bytes_per_ray": bytes_per_ray, "nodes_per_ray": nodes_per_ray, "tris_per_ray": tris_per_ray,
-                         "stream_floor_bytes_per_ray": BYTES_STREAM, "kernel_ms": kernel_ms,
-                         "secondary_ceilings": secondary},
+            "roofline": roof, "roofline_primary": roof_primary, "roofline_cpq": roof_cpq,
             "cpu_baseline": cpu,
-            "primary_only": {"value": n_p / (float(np.median(prim_ms)) * 1e-3) / 1e6, "unit": "Mrays/s", "rays": n_p},
-            "cpq": {"value": n_p / (float(np.median(cpq_ms)) * 1e-3) / 1e6, "unit": "Mqueries/s", "queries": n_p,
+            "primary_only": {"value": n_p / (prim_ms * 1e-3) / 1e6, "unit": "Mrays/s", "rays": n_p},
+            "bounce_only": {"value": (n_rays - n_p) / (bounce_ms * 1e-3) / 1e6, "unit": "Mrays/s", "rays": n_rays - n_p} if bounce_ms else None,
+            "cpq": {"value": n_p / (cpq_ms * 1e-3) / 1e6, "unit": "Mqueries/s", "queries": n_p,
                     "what": "closest-point queries near the primary hit points"},
             "render": {"what": "whole config-2 frame through gpurt_pipe_render_frame (gen + trace + shade + accumulate)",
                        "ms_per_frame": float(np.median(frame_ms)), "closest_rays": frame_rays[0], "any_rays": frame_rays[1],
                        "mrays_s": frame_rays[0] / (float(np.median(frame_ms)) * 1e-3) / 1e6,
                        "mpaths_s": W * H / (float(np.median(frame_ms)) * 1e-3) / 1e6},
+            "placement": placement, "strong": strong, "host": host,
             "clocks": clocks, "wall_s": wall,
         }
         print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+    if shared is not None:
+        shared.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -266,6 +266,14 @@ int gpurt_accel_update(gpurt_accel* A) {
     if(rc == GPURT_OK && A->depth > 60) rc = (set_error("wide BVH deeper than the traversal stack"), GPURT_E_STATE);
     return rc;
 }
+int gpurt_accel_sync_scene(gpurt_accel* A) {
+    if(!A) return set_error("NULL argument"), GPURT_E_INVALID;
+    GPURT_CUDA(cudaSetDevice(A->ctx->device));
+    if(!A->scene->pack()) return GPURT_E_INVALID;
+    if(A->scene->packed.tri_off.back() != A->n) return set_error("geometry changed: gpurt_accel_update() is needed"), GPURT_E_STATE;
+    if(A->scene->geom_version != A->dscene.geom_version) GPURT_CUDA(cudaStreamSynchronize(A->ctx->stream)); /* buffers are replaced */
+    return upload_scene(A->ctx, A->scene, A->dscene);
+}
 int gpurt_accel_destroy(gpurt_accel* A) {
     if(!A) return GPURT_OK;
     cudaSetDevice(A->ctx->device);
@@ -354,6 +362,21 @@ int gpurt_trace_closest_stats(gpurt_accel* A, const GpurtRay* rays, uint64_t n, 
     rc = run_query(ctx, rays, sizeof(GpurtRay), hits, sizeof(GpurtHit), n, GPURT_MEM_DEVICE,
                    [&](const void* i, void* o, uint64_t c) { return launch_trace_closest_stats(A, (const float4*)i, c, (float4*)o, d); });
     if(rc) return rc;
+    unsigned long long h[4];
+    GPURT_CUDA(cudaMemcpyAsync(h, d, 32, cudaMemcpyDeviceToHost, ctx->stream));
+    GPURT_CUDA(cudaStreamSynchronize(ctx->stream));
+    out->rays = n, out->nodes_visited = h[0], out->tris_tested = h[1], out->hits = h[2];
+    return GPURT_OK;
+}
+int gpurt_closest_points_stats(gpurt_accel* A, const GpurtQuery* q, uint64_t n, GpurtTraceStats* out) {
+    if(!A || !out || (n && !q)) return set_error("NULL argument"), GPURT_E_INVALID;
+    gpurt_ctx* ctx = A->ctx;
+    GPURT_CUDA(cudaSetDevice(ctx->device));
+    int rc = ctx->scratch.reserve(64);
+    if(rc) return rc;
+    unsigned long long* d = ctx->scratch.as<unsigned long long>();
+    GPURT_CUDA(cudaMemsetAsync(d, 0, 32, ctx->stream));
+    if((rc = launch_closest_points_stats(A, (const float4*)q, n, d))) return rc;
     unsigned long long h[4];
     GPURT_CUDA(cudaMemcpyAsync(h, d, 32, cudaMemcpyDeviceToHost, ctx->stream));
     GPURT_CUDA(cudaStreamSynchronize(ctx->stream));

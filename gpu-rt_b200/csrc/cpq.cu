@@ -41,6 +41,30 @@ __global__ void __launch_bounds__(128) k_closest_points(const float4* __restrict
     results[2 * i + 1] = o1;
 }
 
+/* instrumented launch for the roofline (mean nodes visited / triangles tested per query); results unchanged */
+__global__ void __launch_bounds__(128) k_closest_points_stats(const float4* __restrict__ nodes, const float4* __restrict__ tris,
+                                                              const float4* __restrict__ queries, uint64_t n,
+                                                              unsigned n_nodes, unsigned long long* counters) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) return;
+    float4 q = __ldg(queries + i);
+    CpRec best;
+    best.gid = kNoHit;
+    unsigned vc[2] = {0u, 0u};
+    if(n_nodes) closest_point8<512>(nodes, tris, f3(q.x, q.y, q.z), q.w, best, vc);
+    atomicAdd(counters + 0, (unsigned long long)vc[0]);
+    atomicAdd(counters + 1, (unsigned long long)vc[1]);
+    if(best.gid != kNoHit) atomicAdd(counters + 2, 1ull);
+}
+int launch_closest_points_stats(gpurt_accel* A, const float4* queries, uint64_t n, unsigned long long* d_counters) {
+    if(!n) return GPURT_OK;
+    if(7u * A->depth + 1u > 512u) return set_error("wide BVH too deep for the closest-point stack"), GPURT_E_STATE;
+    k_closest_points_stats<<<(unsigned)((n + 127) / 128), 128, 0, A->ctx->stream>>>((const float4*)A->nodes, A->tri_wide, queries, n,
+                                                                                   A->n_nodes, d_counters);
+    GPURT_CUDA(cudaGetLastError());
+    return GPURT_OK;
+}
+
 int launch_closest_points(gpurt_accel* A, const float4* queries, uint64_t n, float4* results) {
     if(!n) return GPURT_OK;
     unsigned nb = (unsigned)((n + 127) / 128);

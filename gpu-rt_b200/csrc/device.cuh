@@ -110,4 +110,5 @@ int launch_trace_closest_bvh2(gpurt_accel* A, const float4* rays, uint64_t n, fl
 int launch_trace_closest_stats(gpurt_accel* A, const float4* rays, uint64_t n, float4* hits,
                                unsigned long long* d_counters);
 int launch_closest_points(gpurt_accel* A, const float4* queries, uint64_t n, float4* results);
+int launch_closest_points_stats(gpurt_accel* A, const float4* queries, uint64_t n, unsigned long long* d_counters);
 } // namespace gpurt

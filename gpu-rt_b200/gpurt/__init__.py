@@ -85,12 +85,13 @@ SYMBOLS = [
     "gpurt_scene_object_sizes", "gpurt_scene_get_object", "gpurt_camera_make", "gpurt_accel_build",
     "gpurt_accel_destroy", "gpurt_accel_info", "gpurt_accel_get_prim_order", "gpurt_accel_get_morton_keys",
     "gpurt_accel_get_bvh2", "gpurt_trace_closest", "gpurt_trace_any", "gpurt_closest_points",
-    "gpurt_trace_closest_bvh2", "gpurt_trace_closest_stats", "gpurt_last_kernel_ms",
+    "gpurt_trace_closest_bvh2", "gpurt_trace_closest_stats", "gpurt_closest_points_stats", "gpurt_last_kernel_ms",
     "gpurt_pipe_params_default", "gpurt_pipe_create", "gpurt_pipe_destroy", "gpurt_pipe_reset_frame",
     "gpurt_pipe_render_frame", "gpurt_pipe_frame_index", "gpurt_pipe_read_image", "gpurt_pipe_read_gbuffer",
     "gpurt_pipe_ray_counts", "gpurt_pipe_device_image", "gpurt_tonemap", "gpurt_pipe_last_uniforms",
     "gpurt_pipe_read_reservoirs", "gpurt_pipe_bounce_rays", "gpurt_pipe_set_shard",
     "gpurt_pipe_render_frame_mean", "gpurt_pipe_accumulate_mean", "gpurt_scene_set_transform", "gpurt_accel_update", "gpurt_scene_get_texture", "gpurt_shared_alloc", "gpurt_shared_free", "gpurt_shared_open", "gpurt_shared_close",
+    "gpurt_scene_set_material", "gpurt_scene_set_ordered", "gpurt_scene_clear_textures", "gpurt_accel_sync_scene",
 ]
 
 
@@ -397,6 +398,12 @@ class Accel:
         self.ctx.use_torch_stream()
         _check(lib.gpurt_trace_closest_stats(self.h, C.c_void_p(rays_dev.data_ptr()), C.c_uint64(rays_dev.shape[0]),
                                              C.c_void_p(hits_dev.data_ptr()), C.byref(st)))
+        return st
+
+    def closest_points_stats(self, queries_dev):
+        st = TraceStats()
+        self.ctx.use_torch_stream()
+        _check(lib.gpurt_closest_points_stats(self.h, C.c_void_p(queries_dev.data_ptr()), C.c_uint64(queries_dev.shape[0]), C.byref(st)))
         return st
 
     def close(self):

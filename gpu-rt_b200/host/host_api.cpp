@@ -49,6 +49,16 @@ bool gpurt_scene::pack() {
     return true;
 }
 
+static void material_from_abi(Material& dst, const GpurtMaterial* m) {
+    dst.albedo = Vec3{m->albedo[0], m->albedo[1], m->albedo[2]};
+    dst.albedo_tex = m->albedo_tex;
+    dst.emissive = Vec3{m->emissive[0], m->emissive[1], m->emissive[2]};
+    dst.emissive_tex = m->emissive_tex;
+    dst.metal_rough = Vec2{m->metal_rough[0], m->metal_rough[1]};
+    dst.metal_rough_tex = m->metal_rough_tex;
+    dst.normal_tex = m->normal_tex;
+}
+
 extern "C" {
 
 const char* gpurt_last_error(void) { return g_error.c_str(); }
@@ -95,15 +105,8 @@ int gpurt_scene_add_object(gpurt_scene* s, const void* verts48, uint32_t nv, con
     o.mesh.set(std::move(v), std::move(ix));
     o.has_model = true;
     std::memcpy(o.model.data(), model, 64);
-    if(m) {
-        o.material.albedo = Vec3{m->albedo[0], m->albedo[1], m->albedo[2]};
-        o.material.albedo_tex = m->albedo_tex;
-        o.material.emissive = Vec3{m->emissive[0], m->emissive[1], m->emissive[2]};
-        o.material.emissive_tex = m->emissive_tex;
-        o.material.metal_rough = Vec2{m->metal_rough[0], m->metal_rough[1]};
-        o.material.metal_rough_tex = m->metal_rough_tex;
-        o.material.normal_tex = m->normal_tex;
-    } else {
+    if(m) material_from_abi(o.material, m);
+    else {
         o.material.albedo = Vec3{1.0f};
         o.material.metal_rough = Vec2{1.0f, 1.0f};
     }
@@ -138,6 +141,31 @@ int gpurt_scene_set_transform(gpurt_scene* s, uint32_t obj, const float model[16
         s->scene.build_desc(s->packed.descs, s->packed.lights);
         s->version++;
     }
+    return GPURT_OK;
+}
+int gpurt_scene_set_material(gpurt_scene* s, uint32_t obj, const GpurtMaterial* m) {
+    if(!s || !m) return set_error("NULL argument"), GPURT_E_INVALID;
+    Object* o = s->scene.at_index(obj);
+    if(!o) return set_error("object index out of range"), GPURT_E_INVALID;
+    material_from_abi(o->material, m);
+    if(!s->dirty) { /* geometry already packed: only Scene_Desc / Scene_Light change (rt.cpp:26-76) */
+        s->scene.build_desc(s->packed.descs, s->packed.lights);
+        int ntex = (int)s->scene.textures.size();
+        for(SceneDesc& d : s->packed.descs)
+            for(int32_t* t : {&d.albedo_tex, &d.emissive_tex, &d.metal_rough_tex, &d.normal_tex})
+                if(*t >= ntex) *t = -1;
+        s->version++;
+    }
+    return GPURT_OK;
+}
+int gpurt_scene_set_ordered(gpurt_scene* s, int ordered) {
+    if(!s) return set_error("NULL argument"), GPURT_E_INVALID;
+    if(s->scene.ordered != (ordered != 0)) s->scene.ordered = ordered != 0, s->dirty = true;
+    return GPURT_OK;
+}
+int gpurt_scene_clear_textures(gpurt_scene* s) {
+    if(!s) return set_error("NULL argument"), GPURT_E_INVALID;
+    if(!s->scene.textures.empty()) s->scene.textures.clear(), s->dirty = true;
     return GPURT_OK;
 }
 int gpurt_scene_add_texture(gpurt_scene* s, const uint8_t* rgba, uint32_t w, uint32_t h, int32_t* out) {

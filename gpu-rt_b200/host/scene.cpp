@@ -27,12 +27,13 @@ void Mesh::set(std::vector<Vertex>&& v, std::vector<uint32_t>&& i) {
 
 void Scene::clear() {
     objs.clear();
+    insertion.clear();
     textures.clear();
 }
 
 unsigned int Scene::add(Object&& obj) {
     unsigned int id = obj.id;
-    objs.emplace(std::make_pair(id, std::move(obj)));
+    if(objs.emplace(std::make_pair(id, std::move(obj))).second) insertion.push_back(id);
     return id;
 }
 

@@ -82,17 +82,25 @@ public:
     unsigned int reserve_id() { return next_id++; }
     size_t size() const { return objs.size(); }
 
-    /* iteration order of std::unordered_map<unsigned, Object> — SURVEY Q2: never sort */
+    /* iteration order of std::unordered_map<unsigned, Object> — SURVEY Q2: never sort.  `ordered` (set by a caller
+     * that passes instances in an order of its own, e.g. the BLAS_T order of GPURT::build_accel) iterates in insertion
+     * order instead, so that instance i is object i. */
     template <typename F> void for_objs(F&& f) const {
+        if(ordered) {
+            for(unsigned int id : insertion) f(objs.at(id));
+            return;
+        }
         for(auto& o : objs) f(o.second);
     }
 
     /* k-th object in for_objs order (the obj_id the shaders see), or nullptr */
     Object* at_index(size_t k) {
+        if(ordered) return k < insertion.size() ? &objs.at(insertion[k]) : nullptr;
         for(auto& o : objs)
             if(k-- == 0) return &o.second;
         return nullptr;
     }
+    bool ordered = false;
 
     /* RTPipe::build_desc, src/vk/rt.cpp:26-76 */
     void build_desc(std::vector<SceneDesc>& descs, std::vector<SceneLight>& lights) const;
@@ -102,6 +110,7 @@ public:
 
 private:
     std::unordered_map<unsigned int, Object> objs; /* scene.h:46 */
+    std::vector<unsigned int> insertion;           /* ids in the order add() saw them */
     unsigned int next_id = 1;
 };
 

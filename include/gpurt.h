@@ -173,6 +173,15 @@ int gpurt_scene_add_object(gpurt_scene* scene, const void* verts48, uint32_t n_v
 /* Pose edit (GPURT::edit_scene -> rebuild_tlas, src/gpurt.cpp:286-289, :378-385): replaces the model
  * matrix of object `obj` (index in Scene::for_objs order).  Follow with gpurt_accel_update(). */
 int gpurt_scene_set_transform(gpurt_scene* scene, uint32_t obj, const float model[16]);
+/* Material edit (the ImGui material editor, src/gpurt.cpp:378-385, followed by rt_pipe.recreate(scene) -> build_desc,
+ * src/vk/rt.cpp:26-76): replaces the material of object `obj`.  Follow with gpurt_accel_sync_scene() — the BVH is unaffected. */
+int gpurt_scene_set_material(gpurt_scene* scene, uint32_t obj, const GpurtMaterial* material);
+/* Object order.  0 (default): the iteration order of the reference's std::unordered_map<id, Object>, i.e. what
+ * Scene::for_objs gives for ids handed out from 1.  1: insertion order — for callers that already iterate the
+ * reference's Scene themselves and pass instance i as the i-th add_object call (GPURT::build_accel's BLAS / BLAS_T). */
+int gpurt_scene_set_ordered(gpurt_scene* scene, int ordered);
+/* RTPipe::build_textures starts from an empty table (rt.cpp:432-434). */
+int gpurt_scene_clear_textures(gpurt_scene* scene);
 /* RTPipe::build_textures (src/vk/rt.cpp:430-455): RGBA8, sampled as sRGB, linear, repeat. */
 int gpurt_scene_add_texture(gpurt_scene* scene, const uint8_t* rgba8, uint32_t w, uint32_t h,
                             int32_t* out_tex_index);
@@ -217,6 +226,9 @@ int gpurt_accel_build(gpurt_scene* scene, uint32_t flags, gpurt_accel** out);
  * the accel already owns (no geometry upload, no allocation); geometry edits fall back to a full build.
  * Pipes created on this accel stay valid (call gpurt_pipe_reset_frame, like GPURT::build_accel does). */
 int gpurt_accel_update(gpurt_accel* accel);
+/* Bring the device copy of Scene_Desc / Scene_Light / textures up to date after material or texture edits WITHOUT
+ * rebuilding the BVH (= rt_pipe.recreate(scene) with an unchanged TLAS).  Geometry or pose edits need gpurt_accel_update. */
+int gpurt_accel_sync_scene(gpurt_accel* accel);
 int gpurt_accel_destroy(gpurt_accel* accel);
 int gpurt_accel_info(const gpurt_accel* accel, GpurtAccelInfo* out);
 /* Canonical primitive order (sorted Morton position -> global prim id), host buffers. */
@@ -243,6 +255,8 @@ int gpurt_trace_closest_bvh2(gpurt_accel* accel, const GpurtRay* rays, uint64_t 
 /* Instrumented closest-hit: same results + visit counters (device buffers only). */
 int gpurt_trace_closest_stats(gpurt_accel* accel, const GpurtRay* rays, uint64_t n, GpurtHit* hits,
                               GpurtTraceStats* out_host_stats);
+/* Instrumented closest-point query: visit counters only (device queries; `rays` = queries, `hits` = queries answered). */
+int gpurt_closest_points_stats(gpurt_accel* accel, const GpurtQuery* queries, uint64_t n, GpurtTraceStats* out_host_stats);
 /* Device time (ms) of the last query / render call on this accel's context (CUDA events). */
 int gpurt_last_kernel_ms(gpurt_ctx* ctx, float* out_ms);
 

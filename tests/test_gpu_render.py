@@ -83,6 +83,26 @@ def test_sponza_standin_config2(gpurt, orc, ctx):
          max_depth=2, use_rr=0, env_scale=1.0, seed=3)
 
 
+def test_config2_full_size_1080p(gpurt, orc, ctx):
+    """BASELINE config 2 at its full size: 1920x1080, integrator 1 (Material), GGX, depth 2, 1 spp, env light,
+    no RR — image, G-buffers and ray counts of the frame against the oracle's rt.rgen restatement (rt.rgen:567-677)"""
+    cam = gpurt.camera(1, 1920, 1080, (-1000.0, 200.0, 0.0), (0.0, 200.0, 0.0), 90.0)
+    _run(gpurt, orc, ctx, "sponza_standin", 1920, 1080, 2, cam=cam, integrator=1, brdf=1, samples_per_frame=1,
+         max_depth=2, use_rr=0, env_scale=1.0, seed=3)
+
+
+def test_config3_full_size_1080p(gpurt, orc, ctx):
+    """BASELINE config 3 at its full size: mis_test at 1920x1080, depth 4, 1 spp — MIS (integrator 2), then 8 frames of
+    ReSTIR direct (3) and 4 of ReSTIR (4) with temporal reuse (res_samples 4, temporal_scale 16); image, G-buffers,
+    reservoirs and ray counts of every frame against the oracle"""
+    cam = gpurt.camera(1, 1920, 1080, (0.5, 0.6, 2.6), (0.5, 0.45, 0.0), 50.0)
+    _run(gpurt, orc, ctx, "mis_test", 1920, 1080, 2, cam=cam, integrator=2, brdf=1, samples_per_frame=1, max_depth=4, seed=7)
+    _run(gpurt, orc, ctx, "mis_test", 1920, 1080, 9, cam=cam, integrator=3, brdf=1, samples_per_frame=1, max_depth=4,
+         res_samples=4, use_temporal=1, temporal_scale=16, seed=8)
+    _run(gpurt, orc, ctx, "mis_test", 1920, 1080, 5, cam=cam, integrator=4, brdf=1, samples_per_frame=1, max_depth=4,
+         res_samples=4, use_temporal=1, temporal_scale=16, seed=9)
+
+
 def test_options_qmc_metalness_rr_off_depth1(gpurt, orc, ctx):
     _run(gpurt, orc, ctx, "cbox", 128, 72, 3, integrator=1, brdf=1, samples_per_frame=3, max_depth=5, use_qmc=1,
          use_metalness=1, seed=11)

@@ -172,6 +172,7 @@ int gpurt_ctx_destroy(gpurt_ctx* c) {
     cudaSetDevice(c->device);
     if(c->stream) cudaStreamSynchronize(c->stream);
     c->d_in.release(), c->d_out.release(), c->scratch.release(), c->build_arena.release();
+    if(c->pinned_word) cudaFreeHost(c->pinned_word);
     for(cudaEvent_t ev : {c->ev0, c->ev1, c->ev_copy, c->ev_kernel})
         if(ev) cudaEventDestroy(ev);
     for(cudaStream_t st : {c->s_h2d, c->s_d2h, c->own_stream})

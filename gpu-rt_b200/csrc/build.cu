@@ -645,7 +645,12 @@ int build_accel_device(gpurt_accel* A) {
     static const bool env_sah = getenv("GPURT_COLLAPSE") && !strcmp(getenv("GPURT_COLLAPSE"), "sah");
     const bool sah = env_sah || (A->flags & GPURT_BUILD_SAH_COLLAPSE);
     size_t fixed = 4 * pad + 2 * ((size_t)ni * 4 + pad) + (sah ? (size_t)ni * 8 : 0);
-    size_t phase1 = (size_t)n * 8 + (size_t)n * 4 + ((size_t)ni + n) * 4 + (sah ? (size_t)ni * 28 : 0) + 5 * pad;
+    /* GPURT_BUILD_SAH_SPLIT: the binned-SAH tree is built on the device (sah_build.cu); GPURT_SAH_HOST=1 keeps the host
+     * builder of host/sah_split.h (the definition both follow) for A/B runs and the device == host test */
+    const bool sah_split = (A->flags & GPURT_BUILD_SAH_SPLIT) != 0;
+    const bool sah_host = getenv("GPURT_SAH_HOST") && atoi(getenv("GPURT_SAH_HOST")) != 0; /* read per build */
+    const size_t sah_tmp = sah_split && !sah_host && n > 1 ? sah_split_tmp_bytes(n, ctx->sm_count) : 0;
+    size_t phase1 = (size_t)n * 8 + (size_t)n * 4 + ((size_t)ni + n) * 4 + (sah ? (size_t)ni * 28 : 0) + sah_tmp + 6 * pad;
     size_t phase2 = 2 * max_nodes * 4 + 8 * max_nodes * 4 + (max_nodes + 1) * 8 + scan_tmp_bytes(max_nodes + 1) +
                     (size_t)n * 4 + 8 * pad;
     TRY(ctx->build_arena.reserve(fixed + std::max(phase1, phase2)));
@@ -660,7 +665,8 @@ int build_accel_device(gpurt_accel* A) {
     uint32_t* vals_tmp = ar.take<uint32_t>(n);
     int* parent = ar.take<int>((size_t)ni + n);
     float* dp_cost = ar.take<float>(sah ? (size_t)ni * 7 : 1);
-    if(!dp_cost) return set_error("build arena layout"), GPURT_E_STATE;
+    char* sah_buf = ar.take<char>(sah_tmp);
+    if(!dp_cost || !sah_buf) return set_error("build arena layout"), GPURT_E_STATE;
 
     struct EventPair { /* destroyed on every return path */
         cudaEvent_t a = nullptr, b = nullptr;
@@ -693,14 +699,16 @@ int build_accel_device(gpurt_accel* A) {
     float ext[3] = {sb[3] - sb[0], sb[4] - sb[1], sb[5] - sb[2]}, inv[3];
     for(int k = 0; k < 3; k++) inv[k] = ext[k] > 0 ? 1.0f / ext[k] : 0.0f;
 
-    const bool sah_split = (A->flags & GPURT_BUILD_SAH_SPLIT) != 0;
     if(!sah_split) {
         /* keys + sort */
         k_morton<<<cdiv(n, 256), 256, 0, st>>>(A->tri_lo, A->tri_hi, n, sb[0], sb[1], sb[2], inv[0], inv[1],
                                               inv[2], A->keys, A->order);
         TRY(radix_sort_u64(st, A->keys, A->order, keys_tmp, vals_tmp, n, 8, ctx->scratch, ctx->sm_count));
+    } else if(!sah_host && n > 1) {
+        TRY(build_sah_split_device(ctx, A->tri_lo, A->tri_hi, n, A->order, A->keys, A->left, A->right, parent, range_first,
+                                   range_last, sah_buf, sah_tmp, nullptr));
     } else {
-        /* GPURT_BUILD_SAH_SPLIT: primitive order and binary topology from the host-side binned-SAH definition
+        /* GPURT_SAH_HOST=1: primitive order and binary topology from the host-side binned-SAH definition
          * (host/sah_split.h) over the boxes k_flatten just wrote; everything after it (refit, collapse, node encoding,
          * triangle re-layout) is the same device code */
         std::vector<float> h_lo(4ull * n), h_hi(4ull * n);

@@ -46,6 +46,7 @@ struct gpurt_ctx {
     gpurt::DevBuf d_in, d_out;
     gpurt::DevBuf scratch;
     gpurt::DevBuf build_arena; /* temporaries of gpurt_accel_build / gpurt_accel_update */
+    unsigned* pinned_word = nullptr; /* mapped host memory for single-word read-backs (sah_build.cu) */
 };
 
 namespace gpurt {
@@ -89,6 +90,11 @@ struct gpurt_accel {
 
 namespace gpurt {
 int build_accel_device(gpurt_accel* A);
+/* sah_build.cu: the binned-SAH tree of host/sah_split.h on the device */
+size_t sah_split_tmp_bytes(size_t n, int sm_count);
+int build_sah_split_device(gpurt_ctx* ctx, const float4* tri_lo, const float4* tri_hi, unsigned n, uint32_t* order, uint64_t* keys,
+                           int* left, int* right, int* parent, int* range_first, int* range_last, void* tmp, size_t tmp_bytes,
+                           unsigned* levels_out);
 void free_accel_device(gpurt_accel* A);
 
 /* order.cu: processing order for large incoherent device batches.  `order` (may be NULL) maps processing slot ->

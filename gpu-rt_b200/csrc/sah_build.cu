@@ -1,0 +1,722 @@
+/*
+ * sah_build.cu — the binned-SAH binary tree of host/sah_split.h, built on the device.
+ *
+ * The reference asks its driver for a PREFER_FAST_TRACE acceleration structure (src/vk/vulkan.cpp:780, :884); here that is
+ * a top-down 16-bin SAH split of the triangle boxes k_flatten wrote, and this file reproduces the tree DEFINED in
+ * host/sah_split.h bit for bit (same centroid bounds, bins, costs, tie rules, stable partitions, preorder node ids):
+ * every reduction is a min / max / integer count, so the order in which a parallel machine performs it does not matter.
+ *
+ * Two regimes:
+ *
+ *   segments of more than 1024 items ("big"), level by level over the whole grid, fixed tiles of 1024 positions:
+ *     k_sah_bins     per warp, lane L owns bin L&15 of axis L>>4 (third axis in a second register set): the 32 items of a
+ *                    step are broadcast by shuffle and each lane folds the ones that fall into its bin — no atomics, no
+ *                    conflicts; one flush of 48 x 7 words per warp and segment into the segment's global bins.  The last
+ *                    tile to finish a segment evaluates the 45 split candidates.
+ *     k_sah_count    left-going items per tile and segment
+ *     k_sah_level    ONE block: exclusive scan of the tile counts, then per segment: boundary, node record, children
+ *                    (leaf / small job / next level's big segment), bins and centroid bounds of the new big segments
+ *     k_sah_scatter  stable partition into the other record array, centroid bounds of big children (match_any +
+ *                    redux), primitive ids of single-item children
+ *   segments of at most 1024 items: k_sah_small, persistent warps over a ticket queue.  A warp owns one segment: bounds by
+ *     warp reduction, the same transposed binning, split, stable partition by ballot, then it keeps the left child and
+ *     queues the right one.
+ *
+ * Item records (box + primitive id, 32 bytes) are physically partitioned between two arrays, so every pass reads
+ * contiguous memory.
+ */
+#include <cstdlib>
+
+#include "device.cuh"
+
+namespace gpurt {
+
+namespace {
+
+constexpr unsigned SAH_TILE = 1024;
+constexpr int SAH_BINS = 16;
+constexpr float SAH_BIG = 3.0e38f;
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int SAH_BIN_WORDS = 3 * SAH_BINS * 7; /* per segment: [axis][bin]{count, lo xyz, hi xyz} */
+
+struct SahRec {
+    float4 lo; /* w: primitive id */
+    float4 hi;
+};
+struct SahSeg {
+    unsigned a, b;
+    int me, parent;
+};
+struct SahSplit {
+    unsigned a, b;
+    int axis, k; /* axis < 0: split at the middle */
+    float lo, scale;
+    unsigned nl, base;
+    int child[2]; /* >= 0: big segment of the next level, -1: small job, -2: single item */
+};
+struct SahJob {
+    unsigned a, b;
+    int me, parent;
+    unsigned src;
+};
+struct SahState {
+    unsigned n_seg, n_seg_next, q_tail, q_head, small_total, leaves_done;
+};
+
+/* order-preserving float <-> int for atomicMin / atomicMax */
+__device__ __forceinline__ int enc(float f) {
+    int i = __float_as_int(f);
+    return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float dec(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+/* sah_split.h bin_of */
+__device__ __forceinline__ int sah_bin(float c, float lo, float scale) {
+    const float f = (c - lo) * scale;
+    return f >= 0.0f ? (f < (float)SAH_BINS ? (int)f : SAH_BINS - 1) : 0;
+}
+__device__ __forceinline__ float sah_area(const float lo[3], const float hi[3]) {
+    float ex = hi[0] - lo[0], ey = hi[1] - lo[1], ez = hi[2] - lo[2];
+    return 2.0f * (ex * ey + ey * ez + ez * ex);
+}
+__device__ __forceinline__ float axis_of(float4 v, int ax) { return ax == 0 ? v.x : (ax == 1 ? v.y : v.z); }
+
+/* bins of a segment spread over a warp: set A = (axis lane>>4, bin lane&15), set B = (axis 2, bin lane&15; lanes < 16) */
+struct LaneBins {
+    unsigned cnt[2];
+    float lo[2][3], hi[2][3];
+    __device__ __forceinline__ void reset() {
+#pragma unroll
+        for(int s = 0; s < 2; s++) {
+            cnt[s] = 0;
+#pragma unroll
+            for(int k = 0; k < 3; k++) lo[s][k] = SAH_BIG, hi[s][k] = -SAH_BIG;
+        }
+    }
+};
+struct SegFrame { /* centroid bounds of a segment and what follows from them */
+    float lo[3], scale[3];
+    bool use[3];
+    __device__ __forceinline__ void set(const float cl[3], const float ch[3]) {
+#pragma unroll
+        for(int k = 0; k < 3; k++) {
+            const float ext = ch[k] - cl[k];
+            use[k] = ext > 0.0f;
+            lo[k] = cl[k];
+            scale[k] = use[k] ? (float)SAH_BINS / ext : 0.0f;
+        }
+    }
+    /* the three bins of an item, one byte each; 0xff = axis not used */
+    __device__ __forceinline__ unsigned bins(float4 l, float4 h) const {
+        unsigned p = 0;
+#pragma unroll
+        for(int k = 0; k < 3; k++) {
+            const float c = (axis_of(l, k) + axis_of(h, k)) * 0.5f;
+            p |= (use[k] ? (unsigned)sah_bin(c, lo[k], scale[k]) : 0xffu) << (8 * k);
+        }
+        return p;
+    }
+};
+
+/* fold the items of the lanes in `group` into the lane-owned bins (every lane of the warp calls this) */
+__device__ __forceinline__ void bins_add(LaneBins& B, unsigned group, float4 l, float4 h, unsigned packed, int lane) {
+    const unsigned sh = 8u * (unsigned)(lane >> 4), mine = (unsigned)(lane & 15);
+    for(unsigned m = group; m; m &= m - 1) {
+        const int j = __ffs((int)m) - 1;
+        const float lx = __shfl_sync(FULL, l.x, j), ly = __shfl_sync(FULL, l.y, j), lz = __shfl_sync(FULL, l.z, j);
+        const float hx = __shfl_sync(FULL, h.x, j), hy = __shfl_sync(FULL, h.y, j), hz = __shfl_sync(FULL, h.z, j);
+        const unsigned pk = __shfl_sync(FULL, packed, j);
+        if(((pk >> sh) & 0xffu) == mine) {
+            B.cnt[0]++;
+            B.lo[0][0] = fminf(B.lo[0][0], lx), B.lo[0][1] = fminf(B.lo[0][1], ly), B.lo[0][2] = fminf(B.lo[0][2], lz);
+            B.hi[0][0] = fmaxf(B.hi[0][0], hx), B.hi[0][1] = fmaxf(B.hi[0][1], hy), B.hi[0][2] = fmaxf(B.hi[0][2], hz);
+        }
+        if(((pk >> 16) & 0xffu) == mine) { /* lanes >= 16 keep a redundant copy */
+            B.cnt[1]++;
+            B.lo[1][0] = fminf(B.lo[1][0], lx), B.lo[1][1] = fminf(B.lo[1][1], ly), B.lo[1][2] = fminf(B.lo[1][2], lz);
+            B.hi[1][0] = fmaxf(B.hi[1][0], hx), B.hi[1][1] = fmaxf(B.hi[1][1], hy), B.hi[1][2] = fmaxf(B.hi[1][2], hz);
+        }
+    }
+}
+
+/* The split of a segment from its bins (sah_split.h: lowest cost, ties to the lower axis, then the lower boundary;
+ * candidates need both sides non-empty and a cost below 3.0e38).  Returns axis (-1: none), boundary k and the left count,
+ * the same in every lane. */
+__device__ __forceinline__ void eval_split(const LaneBins& B, int lane, int& axis, int& k, unsigned& nl) {
+    const int b = lane & 15;
+    float best_cost = 0.0f;
+    int best_idx = 0x7fffffff;
+    unsigned nl_set[2];
+#pragma unroll
+    for(int s = 0; s < 2; s++) {
+        /* inclusive prefix (bins 0..b) and suffix (bins b..15) unions inside each half-warp */
+        unsigned pc = B.cnt[s], sc = B.cnt[s];
+        float pl[3], ph[3], sl[3], shh[3];
+#pragma unroll
+        for(int q = 0; q < 3; q++) pl[q] = sl[q] = B.lo[s][q], ph[q] = shh[q] = B.hi[s][q];
+#pragma unroll
+        for(int d = 1; d < 16; d <<= 1) {
+            unsigned c2 = __shfl_up_sync(FULL, pc, d, 16);
+            float l2[3], h2[3];
+#pragma unroll
+            for(int q = 0; q < 3; q++) l2[q] = __shfl_up_sync(FULL, pl[q], d, 16), h2[q] = __shfl_up_sync(FULL, ph[q], d, 16);
+            if(b >= d) {
+                pc += c2;
+#pragma unroll
+                for(int q = 0; q < 3; q++) pl[q] = fminf(pl[q], l2[q]), ph[q] = fmaxf(ph[q], h2[q]);
+            }
+            c2 = __shfl_down_sync(FULL, sc, d, 16);
+#pragma unroll
+            for(int q = 0; q < 3; q++) l2[q] = __shfl_down_sync(FULL, sl[q], d, 16), h2[q] = __shfl_down_sync(FULL, shh[q], d, 16);
+            if(b + d < 16) {
+                sc += c2;
+#pragma unroll
+                for(int q = 0; q < 3; q++) sl[q] = fminf(sl[q], l2[q]), shh[q] = fmaxf(shh[q], h2[q]);
+            }
+        }
+        /* lane b evaluates the boundary k = b + 1: left = bins 0..b (its prefix), right = bins b+1..15 (the next lane's suffix) */
+        const unsigned rc = __shfl_down_sync(FULL, sc, 1, 16);
+        float rl[3], rh[3];
+#pragma unroll
+        for(int q = 0; q < 3; q++) rl[q] = __shfl_down_sync(FULL, sl[q], 1, 16), rh[q] = __shfl_down_sync(FULL, shh[q], 1, 16);
+        nl_set[s] = pc;
+        const int ax = s == 0 ? (lane >> 4) : 2;
+        if(b < 15 && pc != 0 && rc != 0 && (s == 0 || lane < 16)) {
+            const float cost = sah_area(pl, ph) * (float)pc + sah_area(rl, rh) * (float)rc;
+            const int idx = ax * 16 + b + 1;
+            if(cost < SAH_BIG && (best_idx == 0x7fffffff || cost < best_cost || (cost == best_cost && idx < best_idx)))
+                best_cost = cost, best_idx = idx;
+        }
+    }
+#pragma unroll
+    for(int d = 16; d >= 1; d >>= 1) {
+        const float c2 = __shfl_xor_sync(FULL, best_cost, d);
+        const int i2 = __shfl_xor_sync(FULL, best_idx, d);
+        if(i2 != 0x7fffffff && (best_idx == 0x7fffffff || c2 < best_cost || (c2 == best_cost && i2 < best_idx)))
+            best_cost = c2, best_idx = i2;
+    }
+    if(best_idx == 0x7fffffff) {
+        axis = -1, k = 0, nl = 0;
+        return;
+    }
+    axis = best_idx >> 4, k = best_idx & 15;
+    const int src = (axis < 2 ? axis * 16 : 0) + (k - 1);
+    const unsigned n0 = __shfl_sync(FULL, nl_set[0], src), n1 = __shfl_sync(FULL, nl_set[1], src);
+    nl = axis < 2 ? n0 : n1;
+}
+
+/* ---- big segments ------------------------------------------------------------------------------------------------- */
+/* root: either the first big segment (with empty bins / bounds) or the first small job */
+__global__ void k_sah_setup(unsigned n, SahState* st, SahSeg* segs, SahJob* jobs, unsigned* ready, int* cb, int* bins,
+                            unsigned* tiles_done) {
+    const bool big_root = n > SAH_TILE;
+    for(int i = threadIdx.x; i < SAH_BIN_WORDS; i += blockDim.x) bins[i] = (i % 7) == 0 ? 0 : ((i % 7) < 4 ? enc(SAH_BIG) : enc(-SAH_BIG));
+    if(threadIdx.x < 6) cb[threadIdx.x] = threadIdx.x < 3 ? enc(SAH_BIG) : enc(-SAH_BIG);
+    if(threadIdx.x == 0) {
+        tiles_done[0] = 0;
+        *st = SahState{big_root ? 1u : 0u, 0u, big_root ? 0u : 1u, 0u, big_root ? 0u : n, 0u};
+        if(big_root) segs[0] = SahSeg{0u, n, 0, -1};
+        else jobs[0] = SahJob{0u, n, 0, -1, 0u}, ready[0] = 1u;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_sah_init(const float4* __restrict__ tri_lo, const float4* __restrict__ tri_hi, unsigned n,
+                                                   SahRec* rec, int* seg_of, int seg_value, uint64_t* keys, int* cb) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    /* identities and clamps are those of sah_split.h's empty_box(): +-3.0e38 */
+    int e[6] = {enc(SAH_BIG), enc(SAH_BIG), enc(SAH_BIG), enc(-SAH_BIG), enc(-SAH_BIG), enc(-SAH_BIG)};
+    if(i < n) {
+        float4 l = tri_lo[i], h = tri_hi[i];
+        l.w = __uint_as_float(i);
+        rec[i].lo = l, rec[i].hi = h;
+        seg_of[i] = seg_value;
+        keys[i] = i; /* the "key" of a primitive in this build is its position in the SAH order */
+        const float c[3] = {(l.x + h.x) * 0.5f, (l.y + h.y) * 0.5f, (l.z + h.z) * 0.5f};
+#pragma unroll
+        for(int q = 0; q < 3; q++)
+            if(c[q] == c[q]) e[q] = enc(fminf(c[q], SAH_BIG)), e[3 + q] = enc(fmaxf(c[q], -SAH_BIG));
+    }
+    if(seg_value < 0) return;
+#pragma unroll
+    for(int q = 0; q < 3; q++) {
+        const int mn = __reduce_min_sync(FULL, e[q]), mx = __reduce_max_sync(FULL, e[3 + q]);
+        if((threadIdx.x & 31) == 0) atomicMin(cb + q, mn), atomicMax(cb + 3 + q, mx);
+    }
+}
+
+__device__ __forceinline__ void flush_bins(const LaneBins& B, int* bins, int seg, int lane) {
+    int* base = bins + (size_t)seg * SAH_BIN_WORDS;
+#pragma unroll
+    for(int s = 0; s < 2; s++) {
+        if(s == 1 && lane >= 16) break;
+        if(B.cnt[s] == 0) continue;
+        const int ax = s == 0 ? (lane >> 4) : 2;
+        int* w = base + (ax * SAH_BINS + (lane & 15)) * 7;
+        atomicAdd((unsigned*)w, B.cnt[s]);
+#pragma unroll
+        for(int q = 0; q < 3; q++) atomicMin(w + 1 + q, enc(B.lo[s][q])), atomicMax(w + 4 + q, enc(B.hi[s][q]));
+    }
+}
+
+__global__ void __launch_bounds__(256) k_sah_bins(const SahRec* __restrict__ rec, const int* __restrict__ seg_of, unsigned n,
+                                                   const SahSeg* __restrict__ segs, const int* __restrict__ cb, int* bins,
+                                                   unsigned* tiles_done, SahSplit* split) {
+    __shared__ int s_slot[2];
+    const unsigned tile0 = blockIdx.x * SAH_TILE;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if(threadIdx.x < 2) s_slot[threadIdx.x] = -1;
+    __syncthreads();
+    LaneBins B;
+    SegFrame F;
+    int cur = -1;
+    for(int it = 0; it < 4; it++) {
+        const unsigned pos = tile0 + warp * 128 + it * 32 + lane;
+        const int s = pos < n ? seg_of[pos] : -1;
+        float4 l = make_float4(0, 0, 0, 0), h = l;
+        if(s >= 0) {
+            l = rec[pos].lo, h = rec[pos].hi;
+            const unsigned a = segs[s].a;
+            if(pos == tile0) s_slot[0] = s;                 /* the segment that covers the tile's first position */
+            else if(pos == a) s_slot[1] = s;                /* a segment that starts inside the tile (at most one is big) */
+        }
+        unsigned todo = __ballot_sync(FULL, s >= 0);
+        while(todo) {
+            const int sj = __shfl_sync(FULL, s, __ffs((int)todo) - 1);
+            const unsigned group = __ballot_sync(FULL, s == sj);
+            if(sj != cur) {
+                if(cur >= 0) flush_bins(B, bins, cur, lane);
+                B.reset();
+                cur = sj;
+                float cl[3], ch[3];
+#pragma unroll
+                for(int q = 0; q < 3; q++) cl[q] = dec(cb[6 * sj + q]), ch[q] = dec(cb[6 * sj + 3 + q]);
+                F.set(cl, ch);
+            }
+            bins_add(B, group, l, h, s == sj ? F.bins(l, h) : 0xffffffffu, lane);
+            todo &= ~group;
+        }
+    }
+    if(cur >= 0) flush_bins(B, bins, cur, lane);
+    /* the last tile of a segment to get here evaluates its split (warp 0: slot 0, warp 1: slot 1) */
+    __threadfence();
+    __syncthreads();
+    if(warp >= 2) return;
+    const int s = s_slot[warp];
+    if(s < 0) return;
+    const SahSeg sg = segs[s];
+    const unsigned ntiles = (sg.b - 1) / SAH_TILE - sg.a / SAH_TILE + 1;
+    unsigned old = 0;
+    if(lane == 0) old = atomicAdd(tiles_done + s, 1u);
+    old = __shfl_sync(FULL, old, 0);
+    if(old != ntiles - 1) return;
+    __threadfence();
+    const int* base = bins + (size_t)s * SAH_BIN_WORDS;
+#pragma unroll
+    for(int q = 0; q < 2; q++) {
+        const int ax = q == 0 ? (lane >> 4) : 2;
+        const int* w = base + (ax * SAH_BINS + (lane & 15)) * 7;
+        B.cnt[q] = (unsigned)__ldcg(w);
+#pragma unroll
+        for(int c = 0; c < 3; c++) B.lo[q][c] = dec(__ldcg(w + 1 + c)), B.hi[q][c] = dec(__ldcg(w + 4 + c));
+    }
+    int axis, k;
+    unsigned nl;
+    eval_split(B, lane, axis, k, nl);
+    if(lane == 0) {
+        float cl[3], ch[3];
+#pragma unroll
+        for(int q = 0; q < 3; q++) cl[q] = dec(cb[6 * s + q]), ch[q] = dec(cb[6 * s + 3 + q]);
+        F.set(cl, ch);
+        SahSplit sp;
+        sp.a = sg.a, sp.b = sg.b, sp.axis = axis, sp.k = k;
+        sp.lo = axis >= 0 ? F.lo[axis] : 0.0f, sp.scale = axis >= 0 ? F.scale[axis] : 0.0f;
+        sp.nl = axis >= 0 ? nl : (sg.b - sg.a) / 2, sp.base = 0, sp.child[0] = sp.child[1] = -1;
+        split[s] = sp;
+    }
+}
+
+__device__ __forceinline__ bool goes_left(const SahSplit& sp, float4 l, float4 h, unsigned pos) {
+    if(sp.axis < 0) return pos < sp.a + (sp.b - sp.a) / 2;
+    const float c = (axis_of(l, sp.axis) + axis_of(h, sp.axis)) * 0.5f;
+    return sah_bin(c, sp.lo, sp.scale) < sp.k;
+}
+
+/* per thread 4 consecutive positions; returns the left flags (bit r) and slots (bit 4 + r) of its items */
+__device__ __forceinline__ unsigned tile_flags(const SahRec* __restrict__ rec, const int* __restrict__ seg_of, unsigned n,
+                                               const SahSplit* __restrict__ split, unsigned tile0, unsigned p0, int seg[4]) {
+    unsigned f = 0;
+#pragma unroll
+    for(int r = 0; r < 4; r++) {
+        const unsigned pos = p0 + r;
+        seg[r] = pos < n ? seg_of[pos] : -1;
+        if(seg[r] < 0) continue;
+        const SahSplit sp = split[seg[r]];
+        if(goes_left(sp, rec[pos].lo, rec[pos].hi, pos)) f |= 1u << r;
+        if(sp.a > tile0) f |= 16u << r;
+    }
+    return f;
+}
+
+__global__ void __launch_bounds__(256) k_sah_count(const SahRec* __restrict__ rec, const int* __restrict__ seg_of, unsigned n,
+                                                    const SahSplit* __restrict__ split, unsigned* tile_left) {
+    __shared__ unsigned s_sum[8];
+    const unsigned tile0 = blockIdx.x * SAH_TILE;
+    int seg[4];
+    const unsigned f = tile_flags(rec, seg_of, n, split, tile0, tile0 + 4 * threadIdx.x, seg);
+    unsigned c = 0; /* slot 0 lefts in the low half, slot 1 lefts in the high half */
+#pragma unroll
+    for(int r = 0; r < 4; r++)
+        if(f & (1u << r)) c += (f & (16u << r)) ? 0x10000u : 1u;
+    c = __reduce_add_sync(FULL, c);
+    if((threadIdx.x & 31) == 0) s_sum[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if(threadIdx.x == 0) {
+        unsigned t = 0;
+        for(int w = 0; w < 8; w++) t += s_sum[w];
+        tile_left[2 * blockIdx.x] = t & 0xffffu, tile_left[2 * blockIdx.x + 1] = t >> 16;
+    }
+}
+
+/* one block: scan of the tile counts (in place, exclusive, total at [2 * ntiles]) and the bookkeeping of the level */
+__global__ void __launch_bounds__(1024) k_sah_level(unsigned* tile_left, unsigned n_entries, const SahSeg* __restrict__ segs,
+                                                     SahSeg* segs_next, SahSplit* split, SahState* st, int* cb, int* bins,
+                                                     unsigned* tiles_done, SahJob* jobs, int* ready, unsigned dst_parity,
+                                                     int* left, int* right, int* parent, int* range_first, int* range_last,
+                                                     unsigned ni, unsigned* host_flag) {
+    __shared__ unsigned s_w[32];
+    __shared__ unsigned s_carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if(threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for(unsigned base = 0; base < n_entries; base += 1024) {
+        const unsigned i = base + threadIdx.x;
+        const unsigned v = i < n_entries ? tile_left[i] : 0;
+        unsigned inc = v;
+#pragma unroll
+        for(int d = 1; d < 32; d <<= 1) {
+            const unsigned t = __shfl_up_sync(FULL, inc, d);
+            if(lane >= d) inc += t;
+        }
+        if(lane == 31) s_w[warp] = inc;
+        __syncthreads();
+        if(warp == 0) {
+            unsigned w = s_w[lane], winc = w;
+#pragma unroll
+            for(int d = 1; d < 32; d <<= 1) {
+                const unsigned t = __shfl_up_sync(FULL, winc, d);
+                if(lane >= d) winc += t;
+            }
+            s_w[lane] = winc - w;
+        }
+        __syncthreads();
+        const unsigned carry = s_carry;
+        if(i < n_entries) tile_left[i] = carry + s_w[warp] + inc - v;
+        __syncthreads();
+        if(threadIdx.x == 1023) s_carry = carry + s_w[31] + inc;
+        __syncthreads();
+    }
+    if(threadIdx.x == 0) tile_left[n_entries] = s_carry;
+    __syncthreads();
+    const unsigned n_seg = st->n_seg;
+    for(unsigned s = threadIdx.x; s < n_seg; s += 1024) {
+        const SahSeg sg = segs[s];
+        SahSplit sp = split[s];
+        const unsigned first = 2 * (sg.a / SAH_TILE) + ((sg.a % SAH_TILE) ? 1u : 0u);
+        const unsigned last = 2 * ((sg.b - 1) / SAH_TILE);
+        const unsigned nl = tile_left[last + 1] - tile_left[first];
+        sp.nl = nl, sp.base = tile_left[first];
+        const unsigned m = sg.b - sg.a, mid = sg.a + nl;
+        const unsigned ca[2] = {sg.a, mid}, cbnd[2] = {mid, sg.b};
+        const int cme[2] = {sg.me + 1, sg.me + (int)nl};
+        int ref[2];
+        for(int side = 0; side < 2; side++) {
+            const unsigned c = cbnd[side] - ca[side];
+            if(c == 1) {
+                ref[side] = ~(int)ca[side];
+                parent[(size_t)ni + ca[side]] = sg.me;
+                sp.child[side] = -2;
+            } else if(c <= SAH_TILE) {
+                ref[side] = cme[side];
+                const unsigned idx = atomicAdd(&st->q_tail, 1u);
+                jobs[idx] = SahJob{ca[side], cbnd[side], cme[side], sg.me, dst_parity};
+                ready[idx] = 1;
+                atomicAdd(&st->small_total, c);
+                sp.child[side] = -1;
+            } else {
+                ref[side] = cme[side];
+                const unsigned idx = atomicAdd(&st->n_seg_next, 1u);
+                segs_next[idx] = SahSeg{ca[side], cbnd[side], cme[side], sg.me};
+                sp.child[side] = (int)idx;
+            }
+        }
+        (void)m;
+        left[sg.me] = ref[0], right[sg.me] = ref[1], parent[sg.me] = sg.parent;
+        range_first[sg.me] = (int)sg.a, range_last[sg.me] = (int)sg.b - 1;
+        split[s] = sp;
+    }
+    __syncthreads();
+    /* working state of the next level's big segments (this level's bins / bounds / arrival counters are dead by now) */
+    const unsigned nb = st->n_seg_next;
+    for(unsigned i = threadIdx.x; i < nb * (unsigned)SAH_BIN_WORDS; i += 1024) {
+        const unsigned w = i % 7;
+        bins[i] = w == 0 ? 0 : (w < 4 ? enc(SAH_BIG) : enc(-SAH_BIG));
+    }
+    for(unsigned i = threadIdx.x; i < nb * 6; i += 1024) cb[i] = (i % 6) < 3 ? enc(SAH_BIG) : enc(-SAH_BIG);
+    for(unsigned i = threadIdx.x; i < nb; i += 1024) tiles_done[i] = 0;
+    __syncthreads();
+    if(threadIdx.x == 0) {
+        st->n_seg = nb, st->n_seg_next = 0;
+        *host_flag = nb;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_sah_scatter(const SahRec* __restrict__ rec, const int* __restrict__ seg_of, unsigned n,
+                                                      const SahSplit* __restrict__ split, const unsigned* __restrict__ scan,
+                                                      SahRec* rec_out, int* seg_out, int* cb, uint32_t* order) {
+    __shared__ unsigned s_w[8];
+    const unsigned tile0 = blockIdx.x * SAH_TILE, p0 = tile0 + 4 * threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int seg[4];
+    const unsigned f = tile_flags(rec, seg_of, n, split, tile0, p0, seg);
+    unsigned c = 0;
+#pragma unroll
+    for(int r = 0; r < 4; r++)
+        if(f & (1u << r)) c += (f & (16u << r)) ? 0x10000u : 1u;
+    unsigned inc = c;
+#pragma unroll
+    for(int d = 1; d < 32; d <<= 1) {
+        const unsigned t = __shfl_up_sync(FULL, inc, d);
+        if(lane >= d) inc += t;
+    }
+    if(lane == 31) s_w[warp] = inc;
+    __syncthreads();
+    unsigned before = inc - c; /* lefts of both slots in this tile before this thread's items */
+    for(int w = 0; w < warp; w++) before += s_w[w];
+#pragma unroll
+    for(int r = 0; r < 4; r++) {
+        const unsigned pos = p0 + r;
+        const bool valid = pos < n;
+        const int s = seg[r];
+        int child = -1;
+        unsigned dest = pos;
+        float4 l = make_float4(0, 0, 0, 0), h = l;
+        if(valid && s >= 0) {
+            const SahSplit sp = split[s];
+            const unsigned slot = (f >> (4 + r)) & 1u;
+            const bool is_left = (f >> r) & 1u;
+            const unsigned in_tile = slot ? (before >> 16) : (before & 0xffffu);
+            const unsigned lefts_before = scan[2 * blockIdx.x + slot] - sp.base + in_tile;
+            dest = is_left ? sp.a + lefts_before : sp.a + sp.nl + (pos - sp.a) - lefts_before;
+            child = sp.child[is_left ? 0 : 1];
+            l = rec[pos].lo, h = rec[pos].hi;
+            rec_out[dest].lo = l, rec_out[dest].hi = h;
+            if(is_left) before += slot ? 0x10000u : 1u;
+            if(child == -2) order[dest] = __float_as_uint(l.w);
+        }
+        if(valid) seg_out[dest] = child >= 0 ? child : -1;
+        /* centroid bounds of big children: one atomic set per warp and child (every lane takes part in the match) */
+        const unsigned grp = __match_any_sync(FULL, child);
+        if(child >= 0) {
+            const float cen[3] = {(l.x + h.x) * 0.5f, (l.y + h.y) * 0.5f, (l.z + h.z) * 0.5f};
+#pragma unroll
+            for(int q = 0; q < 3; q++) {
+                const bool ok = cen[q] == cen[q];
+                const int mn = __reduce_min_sync(grp, enc(ok ? fminf(cen[q], SAH_BIG) : SAH_BIG));
+                const int mx = __reduce_max_sync(grp, enc(ok ? fmaxf(cen[q], -SAH_BIG) : -SAH_BIG));
+                if(lane == __ffs((int)grp) - 1) atomicMin(cb + 6 * child + q, mn), atomicMax(cb + 6 * child + 3 + q, mx);
+            }
+        }
+    }
+}
+
+/* ---- small segments: persistent warps over a ticket queue ---------------------------------------------------------- */
+__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(128) k_sah_small(SahRec* rec0, SahRec* rec1, SahJob* jobs, unsigned* ready, SahState* st,
+                                                    unsigned cap, uint32_t* order, int* left, int* right, int* parent,
+                                                    int* range_first, int* range_last, unsigned ni) {
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    const unsigned total = st->small_total;
+    for(;;) {
+        unsigned ticket = 0;
+        if(lane == 0) ticket = atomicAdd(&st->q_head, 1u);
+        ticket = __shfl_sync(FULL, ticket, 0);
+        int got = 0;
+        if(lane == 0) {
+            for(;;) {
+                if(ticket < cap && ld_acquire(ready + ticket)) {
+                    got = 1;
+                    break;
+                }
+                if(ld_acquire(&st->leaves_done) >= total) break;
+                __nanosleep(64);
+            }
+        }
+        got = __shfl_sync(FULL, got, 0);
+        if(!got) return;
+        __syncwarp();
+        const unsigned* jw = (const unsigned*)(jobs + ticket);
+        unsigned a = __ldcg(jw), b = __ldcg(jw + 1), src = __ldcg(jw + 4);
+        int me = (int)__ldcg(jw + 2), par = (int)__ldcg(jw + 3);
+        for(;;) { /* one inner node per iteration: [a, b), at least two items */
+            const SahRec* in = src ? rec1 : rec0;
+            SahRec* out = src ? rec0 : rec1;
+            const unsigned m = b - a;
+            float cl[3] = {SAH_BIG, SAH_BIG, SAH_BIG}, ch[3] = {-SAH_BIG, -SAH_BIG, -SAH_BIG};
+            for(unsigned i = a + lane; i < b; i += 32) {
+                const float4 l = __ldcg(&in[i].lo), h = __ldcg(&in[i].hi);
+                const float c[3] = {(l.x + h.x) * 0.5f, (l.y + h.y) * 0.5f, (l.z + h.z) * 0.5f};
+#pragma unroll
+                for(int q = 0; q < 3; q++) cl[q] = fminf(cl[q], c[q]), ch[q] = fmaxf(ch[q], c[q]);
+            }
+#pragma unroll
+            for(int d = 16; d >= 1; d >>= 1)
+#pragma unroll
+                for(int q = 0; q < 3; q++)
+                    cl[q] = fminf(cl[q], __shfl_xor_sync(FULL, cl[q], d)), ch[q] = fmaxf(ch[q], __shfl_xor_sync(FULL, ch[q], d));
+            SegFrame F;
+            F.set(cl, ch);
+            LaneBins B;
+            B.reset();
+            for(unsigned base = a; base < b; base += 32) {
+                const unsigned i = base + lane;
+                const bool valid = i < b;
+                float4 l = make_float4(0, 0, 0, 0), h = l;
+                if(valid) l = __ldcg(&in[i].lo), h = __ldcg(&in[i].hi);
+                bins_add(B, __ballot_sync(FULL, valid), l, h, valid ? F.bins(l, h) : 0xffffffffu, lane);
+            }
+            int axis, k;
+            unsigned nl;
+            eval_split(B, lane, axis, k, nl);
+            if(axis < 0) nl = m / 2;
+            const float s_lo = axis >= 0 ? F.lo[axis] : 0.0f, s_scale = axis >= 0 ? F.scale[axis] : 0.0f;
+            const unsigned nr = m - nl;
+            unsigned run_l = 0, run_r = 0;
+            for(unsigned base = a; base < b; base += 32) {
+                const unsigned i = base + lane;
+                const bool valid = i < b;
+                float4 l = make_float4(0, 0, 0, 0), h = l;
+                bool is_left = false;
+                if(valid) {
+                    l = __ldcg(&in[i].lo), h = __ldcg(&in[i].hi);
+                    is_left = axis < 0 ? i < a + nl : sah_bin((axis_of(l, axis) + axis_of(h, axis)) * 0.5f, s_lo, s_scale) < k;
+                }
+                const unsigned ml = __ballot_sync(FULL, valid && is_left), mr = __ballot_sync(FULL, valid && !is_left);
+                if(valid) {
+                    const unsigned dest = is_left ? a + run_l + __popc(ml & lt) : a + nl + run_r + __popc(mr & lt);
+                    out[dest].lo = l, out[dest].hi = h;
+                    if((is_left && nl == 1) || (!is_left && nr == 1)) order[dest] = __float_as_uint(l.w);
+                }
+                run_l += __popc(ml), run_r += __popc(mr);
+            }
+            if(lane == 0) {
+                left[me] = nl == 1 ? ~(int)a : me + 1;
+                right[me] = nr == 1 ? ~(int)(a + nl) : me + (int)nl;
+                parent[me] = par;
+                range_first[me] = (int)a, range_last[me] = (int)b - 1;
+                if(nl == 1) parent[(size_t)ni + a] = me;
+                if(nr == 1) parent[(size_t)ni + a + nl] = me;
+            }
+            const unsigned leaves = (nl == 1 ? 1u : 0u) + (nr == 1 ? 1u : 0u);
+            const bool go_l = nl >= 2, go_r = nr >= 2;
+            if(go_l && go_r) { /* queue the right child, keep the left one */
+                __threadfence();
+                __syncwarp();
+                if(lane == 0) {
+                    const unsigned idx = atomicAdd(&st->q_tail, 1u);
+                    jobs[idx] = SahJob{a + nl, b, me + (int)nl, me, src ^ 1u};
+                    __threadfence();
+                    st_release(ready + idx, 1u);
+                }
+            }
+            if(leaves && lane == 0) {
+                __threadfence();
+                atomicAdd(&st->leaves_done, leaves);
+            }
+            __syncwarp(); /* the next node reads what the other lanes just wrote */
+            if(go_l) par = me, b = a + nl, me = me + 1, src ^= 1u;
+            else if(go_r) par = me, a = a + nl, me = me + (int)nl, src ^= 1u;
+            else break;
+        }
+    }
+}
+
+} // namespace
+
+/* bytes of temporaries build_sah_split_device() needs for n triangles */
+size_t sah_split_tmp_bytes(size_t n, int sm_count) {
+    const size_t ntiles = (n + SAH_TILE - 1) / SAH_TILE, max_big = n / SAH_TILE + 2, cap = n + (size_t)sm_count * 64 + 64;
+    return 2 * n * sizeof(SahRec) + 2 * n * 4 + cap * (sizeof(SahJob) + 4) + (2 * ntiles + 2) * 4 +
+           max_big * (2 * sizeof(SahSeg) + sizeof(SahSplit) + 24 + SAH_BIN_WORDS * 4 + 4) + sizeof(SahState) + 16 * 256;
+}
+
+/* order / keys / left / right / parent / range_first / range_last of the SAH-split tree over tri_lo / tri_hi (n >= 2).
+ * `tmp` = sah_split_tmp_bytes(n) bytes of device memory.  Synchronises the stream once per level of big segments. */
+int build_sah_split_device(gpurt_ctx* ctx, const float4* tri_lo, const float4* tri_hi, unsigned n, uint32_t* order, uint64_t* keys,
+                           int* left, int* right, int* parent, int* range_first, int* range_last, void* tmp, size_t tmp_bytes,
+                           unsigned* levels_out) {
+    cudaStream_t st = ctx->stream;
+    const unsigned ni = n - 1;
+    const unsigned ntiles = (n + SAH_TILE - 1) / SAH_TILE, max_big = n / SAH_TILE + 2;
+    int occ = 0;
+    GPURT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sah_small, 128, 0));
+    occ = std::max(1, std::min(occ, 16));
+    const unsigned grid_small = (unsigned)ctx->sm_count * (unsigned)occ;
+    const size_t cap = (size_t)n + (size_t)grid_small * 4 + 64;
+    char* p = (char*)tmp;
+    auto take = [&](size_t bytes) {
+        char* q = p;
+        p += (bytes + 255) & ~(size_t)255;
+        return (void*)q;
+    };
+    SahRec* rec[2] = {(SahRec*)take((size_t)n * sizeof(SahRec)), (SahRec*)take((size_t)n * sizeof(SahRec))};
+    int* seg_of[2] = {(int*)take((size_t)n * 4), (int*)take((size_t)n * 4)};
+    SahJob* jobs = (SahJob*)take(cap * sizeof(SahJob));
+    unsigned* ready = (unsigned*)take(cap * 4);
+    unsigned* tile_left = (unsigned*)take(((size_t)2 * ntiles + 2) * 4);
+    SahSeg* segs[2] = {(SahSeg*)take(max_big * sizeof(SahSeg)), (SahSeg*)take(max_big * sizeof(SahSeg))};
+    SahSplit* split = (SahSplit*)take(max_big * sizeof(SahSplit));
+    int* cb = (int*)take(max_big * 24);
+    int* bins = (int*)take(max_big * SAH_BIN_WORDS * 4);
+    unsigned* tiles_done = (unsigned*)take(max_big * 4);
+    SahState* state = (SahState*)take(sizeof(SahState));
+    if((size_t)(p - (char*)tmp) > tmp_bytes) return set_error("SAH build: temporary buffer too small"), GPURT_E_STATE;
+
+    if(!ctx->pinned_word) GPURT_CUDA(cudaHostAlloc((void**)&ctx->pinned_word, 64, cudaHostAllocMapped));
+    volatile unsigned* h_flag = ctx->pinned_word; /* next level's big-segment count, written by k_sah_level */
+    unsigned* d_flag = nullptr;
+    GPURT_CUDA(cudaHostGetDevicePointer((void**)&d_flag, ctx->pinned_word, 0));
+
+    const bool big_root = n > SAH_TILE;
+    GPURT_CUDA(cudaMemsetAsync(ready, 0, cap * 4, st));
+    k_sah_setup<<<1, 128, 0, st>>>(n, state, segs[0], jobs, ready, cb, bins, tiles_done);
+    k_sah_init<<<(n + 255) / 256, 256, 0, st>>>(tri_lo, tri_hi, n, rec[0], seg_of[0], big_root ? 0 : -1, keys, cb);
+    unsigned n_big = big_root ? 1u : 0u, par = 0, levels = 0;
+    while(n_big) {
+        if(++levels > 512) return set_error("SAH build: more than 512 levels of big segments"), GPURT_E_STATE;
+        k_sah_bins<<<ntiles, 256, 0, st>>>(rec[par], seg_of[par], n, segs[par], cb, bins, tiles_done, split);
+        k_sah_count<<<ntiles, 256, 0, st>>>(rec[par], seg_of[par], n, split, tile_left);
+        k_sah_level<<<1, 1024, 0, st>>>(tile_left, 2 * ntiles, segs[par], segs[par ^ 1], split, state, cb, bins, tiles_done, jobs,
+                                        (int*)ready, par ^ 1u, left, right, parent, range_first, range_last, ni, d_flag);
+        k_sah_scatter<<<ntiles, 256, 0, st>>>(rec[par], seg_of[par], n, split, tile_left, rec[par ^ 1], seg_of[par ^ 1], cb, order);
+        GPURT_CUDA(cudaStreamSynchronize(st));
+        n_big = *h_flag;
+        if(n_big > max_big) return set_error("SAH build: segment bound exceeded"), GPURT_E_STATE;
+        par ^= 1;
+    }
+    k_sah_small<<<grid_small, 128, 0, st>>>(rec[0], rec[1], jobs, ready, state, (unsigned)cap, order, left, right, parent, range_first,
+                                            range_last, ni);
+    GPURT_CUDA(cudaGetLastError());
+    if(levels_out) *levels_out = levels;
+    return GPURT_OK;
+}
+
+} // namespace gpurt

@@ -404,6 +404,55 @@ def test_sah_split_build_flag(gpurt, orc, ctx):
     accel.close(), base.close(), scene.close()
 
 
+def _soup(n, seed, ext):
+    rng = np.random.default_rng(seed)
+    c = rng.random((n, 1, 3), dtype=np.float32)
+    return (c + (rng.random((n, 3, 3), dtype=np.float32) - 0.5) * np.float32(ext)).reshape(n, 9).astype(np.float32)
+
+
+def test_sah_split_device_build_equals_the_host_definition(gpurt, orc, ctx, monkeypatch):
+    """sah_build.cu against host/sah_split.h (the definition): primitive order and binary topology bit for bit — sizes around
+    the 1024-item regime boundary, duplicates (middle splits), clustered input (deep, unbalanced splits), the
+    adversarial scene, the shipped scenes — and the queries on the device-built tree against the oracle"""
+    from scenes import adversarial_scene
+    cases = {f"soup{n}": _soup(n, n + 1, 0.05) for n in (2, 3, 5, 33, 1000, 1024, 1025, 2049, 5000, 70000)}
+    dup = _soup(4000, 9, 0.02)
+    dup[100:1500] = dup[100]                                    # 1400 coincident triangles: middle splits across regimes
+    cases["duplicates"] = dup
+    cl = _soup(30000, 3, 0.001)
+    cl[:, :] = (cl.reshape(-1, 3, 3) ** 3).reshape(-1, 9)        # strongly clustered towards the origin
+    cases["clustered"] = cl
+    cases["adversarial"] = np.ascontiguousarray(adversarial_scene(), np.float32)
+    for name in ("cbox", "mis_test", "sponza_standin"):
+        cases[name] = None
+    for name, tris in cases.items():
+        if tris is None:
+            scene = load_scene(gpurt, ctx, name)
+        else:
+            scene = gpurt.Scene(ctx)
+            scene.add_triangles(tris)
+        monkeypatch.setenv("GPURT_SAH_HOST", "1")
+        host = gpurt.Accel(scene, gpurt.BUILD_SAH_SPLIT | gpurt.BUILD_KEEP_BVH2)
+        monkeypatch.setenv("GPURT_SAH_HOST", "0")
+        dev = gpurt.Accel(scene, gpurt.BUILD_SAH_SPLIT | gpurt.BUILD_KEEP_BVH2)
+        assert (dev.prim_order() == host.prim_order()).all(), f"{name}: primitive order differs from host/sah_split.h"
+        hl, hr, hb = host.bvh2()
+        dl, dr, db = dev.bvh2()
+        assert (dl == hl).all() and (dr == hr).all(), f"{name}: binary topology differs from host/sah_split.h"
+        assert same_bits(db, hb), f"{name}: node boxes differ"
+        assert dev.info().n_wide_nodes == host.info().n_wide_nodes and dev.info().wide_depth == host.info().wide_depth
+        if name in ("cbox", "soup5000", "duplicates"):
+            t = world_tris(orc, scene)
+            ob = orc.Bvh(t)
+            rays = orc.gen_random_rays(1 << 16, 5, ob.scene_box())
+            assert same_bits(dev.trace_closest(rays), ob.closest_hit(rays))
+            q = orc.gen_random_points(1 << 14, 6, ob.scene_box())
+            cp, ref = dev.closest_points(q), ob.closest_point(q)
+            assert same_bits(cp["dist"], ref["dist"]) and (cp["prim"] == ref["gid"]).all()
+        print(f"{name}: {dev.info().n_tris} triangles, device SAH build {dev.info().build_ms:.3f} ms, host-side {host.info().build_ms:.3f} ms")
+        dev.close(), host.close(), scene.close()
+
+
 def test_no_device_memory_growth_over_create_destroy_cycles(gpurt, ctx):
     """scene / accel / pipe / update cycles return their device memory (cudaMemGetInfo stays flat)"""
     import torch

@@ -133,6 +133,85 @@ def build_scene(gpurt, ctx):
     return scene, "sponza_standin (Sponza.bin missing from the reference snapshot)"
 
 
+def build_irregular_scene(gpurt, ctx, copies=16):
+    """A Sponza-sized scene of REAL meshes (the stand-in is a regular procedural grid, on which a Morton order is as good as
+    any tree): `copies` instances of every object of media/cbox (16,732 triangles: the bunny / dragon-class meshes the
+    reference ships; the side walls, the ceiling and the back wall are left out so that the instances see each other) under
+    rotations, scales and offsets drawn from the reference RNG -> 96 objects, 266,944 triangles."""
+    src = gpurt.Scene(None).load(os.path.join(ROOT, "tests", "data", "media", "cbox", "cbox.gltf"))
+    descs = src.descs()
+    keep = [i for i in range(len(descs)) if i not in (5, 6, 7, 9)]
+    objs = [src.object(i) for i in keep]
+    descs = [descs[i] for i in keep]
+    scene = gpurt.Scene(ctx).set_ordered()
+    side = int(np.ceil(np.sqrt(copies)))
+    for k in range(copies):
+        st = tea(np.array([k], np.uint32), np.uint32(0x5EED))
+        r = [float(lcg_randf(st)[0]) for _ in range(6)]
+        ang, tilt, sc = 2 * np.pi * r[0], 0.5 * (r[1] - 0.5), 0.7 + 0.6 * r[2]
+        cy, sy, cx, sx = np.cos(ang), np.sin(ang), np.cos(tilt), np.sin(tilt)
+        R = np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]]) @ np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]])
+        T = np.eye(4)
+        T[:3, :3] = R * sc
+        T[:3, 3] = [13.0 * (k % side) + 3.0 * (r[3] - 0.5), 4.0 * (r[4] - 0.5), 13.0 * (k // side) + 3.0 * (r[5] - 0.5)]
+        for (v, idx), d in zip(objs, descs):
+            m = gpurt.Material()
+            m.albedo[:], m.emissive[:], m.metal_rough[:] = d.albedo[:3], d.emissive[:3], d.metal_rough[:2]
+            m.albedo_tex = m.emissive_tex = m.metal_rough_tex = m.normal_tex = -1
+            model = T @ np.array(list(d.model), np.float64).reshape(4, 4).T
+            scene.add_object(v, idx, np.ascontiguousarray(model.T, np.float32).reshape(16), m)
+    ext = 13.0 * (side - 1)
+    cam = dict(pos=(-9.0, 9.0, -9.0), at=(ext * 0.5, -1.0, ext * 0.5), vfov=70.0)
+    return scene, f"cbox_instances ({copies} x media/cbox under random transforms)", cam
+
+
+def tree_report(gpurt, torch, ctx, scene, cam_args, flush):
+    """closest-hit / closest-point throughput of one scene under the default (binned-SAH) build and the Morton LBVH:
+    the frame's config-2 ray set (primary + 1 bounce at 1080p) is recorded once and traced through both trees"""
+    out = {}
+    cam = gpurt.camera(1, W, H, cam_args["pos"], cam_args["at"], cam_args["vfov"])
+    prm = gpurt.pipe_params(integrator=1, brdf=1, max_depth=2, samples_per_frame=1, max_frames=1, use_rr=0, env_scale=1.0, seed=0)
+    rays = None
+    for name, flags in (("default_sah", 0), ("lbvh", gpurt.BUILD_LBVH)):
+        gpurt.Accel(scene, flags).close()
+        accel = gpurt.Accel(scene, flags)
+        if rays is None:
+            pipe = gpurt.RTPipe(scene, accel)
+            ctx.use_torch_stream()
+            pipe.render_frame(prm, cam, W, H)
+            rays = torch.cat([pipe.bounce_rays(0), pipe.bounce_rays(1)]).clone()
+            pipe.close()
+        n, n_p = rays.shape[0], W * H
+        hits = torch.empty((n, 4), dtype=torch.float32, device=rays.device)
+
+        def med(fn, reps=7):
+            ms = []
+            flush.zero_()
+            fn()
+            for _ in range(reps):
+                flush.zero_()
+                fn()
+                ms.append(ctx.last_kernel_ms())
+            return float(np.median(ms))
+        all_ms = med(lambda: accel.trace_closest(rays, hits))
+        prim_ms = med(lambda: accel.trace_closest(rays[:n_p], hits[:n_p]))
+        st = accel.trace_stats(rays, hits)
+        t = hits[:n_p, 0]
+        q = torch.empty((n_p, 4), dtype=torch.float32, device=rays.device)
+        q[:, :3] = rays[:n_p, 0:3] + (0.8 * torch.where(torch.isfinite(t), t, torch.full_like(t, 10.0)))[:, None] * rays[:n_p, 4:7]
+        q[:, 3] = float("inf")
+        cp = accel.closest_points(q)
+        cpq_ms = med(lambda: accel.closest_points(q, cp))
+        info = accel.info()
+        out[name] = {"mrays_s": n / (all_ms * 1e-3) / 1e6, "primary_mrays_s": n_p / (prim_ms * 1e-3) / 1e6,
+                     "bounce_mrays_s": (n - n_p) / max(1e-9, (all_ms - prim_ms) * 1e-3) / 1e6 if n > n_p else None,
+                     "cpq_mqueries_s": n_p / (cpq_ms * 1e-3) / 1e6, "rays": n, "nodes_per_ray": st.nodes_visited / st.rays,
+                     "tris_per_ray": st.tris_tested / st.rays, "build_ms": info.build_ms, "wide_nodes": info.n_wide_nodes}
+        accel.close()
+    out["tris"] = scene.counts()["tris"]
+    return out
+
+
 def scene_world_tris(scene, orc):
     """world-space triangles for the CPU arm (the oracle's own flattening, contract N1)"""
     return np.concatenate([orc.flatten(*scene.object(i), np.array(d.model, np.float32))
@@ -270,7 +349,7 @@ def strong_config4(gpurt, torch, dist, ctx, rank, world, dev, n_tris, n_queries,
     info = accel.info()
     a, b = shard_range(n_queries, rank, world)
     nq = b - a
-    chunk = max(1 << 20, min(6_250_000, (nq + 3) // 4))
+    chunk = max(1 << 20, min(12_500_000, (nq + 3) // 4))
     q = torch.empty((nq, 4), dtype=torch.float32, device=dev)
     for c0 in range(0, nq, 12_500_000):
         c1 = min(nq, c0 + 12_500_000)
@@ -636,6 +715,15 @@ def main():
                "sample": f"all {sample.shape[0]} rays of one step ({dt:.1f} s wall on {cores} threads); "
                          "results compared bit-exactly with the GPU's"}
 
+    # ---- tree quality: default (binned SAH) vs Morton LBVH, on the headline scene and on real meshes (N = 1) -------
+    tree = None
+    if world == 1:
+        irr, irr_label, irr_cam = build_irregular_scene(gpurt, ctx)
+        tree = {"headline_scene": tree_report(gpurt, torch, ctx, scene, dict(pos=CAM_POS, at=CAM_AT, vfov=VFOV), flush),
+                "irregular_scene": dict(tree_report(gpurt, torch, ctx, irr, irr_cam, flush), scene=irr_label),
+                "note": "the headline `value` uses the default build; `lbvh` = GPURT_BUILD_LBVH (round 1's only build)"}
+        irr.close()
+
     # ---- strong scaling at this N (configs 4 and 5) ---------------------------------------------
     strong = None
     if not args.no_strong:
@@ -677,7 +765,7 @@ def main():
                        "ms_per_frame": float(np.median(frame_ms)), "closest_rays": frame_rays[0], "any_rays": frame_rays[1],
                        "mrays_s": frame_rays[0] / (float(np.median(frame_ms)) * 1e-3) / 1e6,
                        "mpaths_s": W * H / (float(np.median(frame_ms)) * 1e-3) / 1e6},
-            "placement": placement, "strong": strong, "host": host,
+            "tree": tree, "placement": placement, "strong": strong, "host": host,
             "clocks": clocks, "wall_s": wall,
         }
         print(json.dumps(line), flush=True)

@@ -647,7 +647,7 @@ int build_accel_device(gpurt_accel* A) {
     size_t fixed = 4 * pad + 2 * ((size_t)ni * 4 + pad) + (sah ? (size_t)ni * 8 : 0);
     /* GPURT_BUILD_SAH_SPLIT: the binned-SAH tree is built on the device (sah_build.cu); GPURT_SAH_HOST=1 keeps the host
      * builder of host/sah_split.h (the definition both follow) for A/B runs and the device == host test */
-    const bool sah_split = (A->flags & GPURT_BUILD_SAH_SPLIT) != 0;
+    const bool sah_split = (A->flags & GPURT_BUILD_LBVH) == 0; /* the default build */
     const bool sah_host = getenv("GPURT_SAH_HOST") && atoi(getenv("GPURT_SAH_HOST")) != 0; /* read per build */
     const size_t sah_tmp = sah_split && !sah_host && n > 1 ? sah_split_tmp_bytes(n, ctx->sm_count) : 0;
     size_t phase1 = (size_t)n * 8 + (size_t)n * 4 + ((size_t)ni + n) * 4 + (sah ? (size_t)ni * 28 : 0) + sah_tmp + 6 * pad;

@@ -446,7 +446,7 @@ static int pipe_light_accel(gpurt_pipe* p) {
         p->lscene->dirty = false; /* `packed` is authoritative: there is no host Scene behind it */
         p->lscene->version = p->lscene->geom_version = 1;
         p->laccel = new gpurt_accel;
-        p->laccel->ctx = p->ctx, p->laccel->scene = p->lscene, p->laccel->flags = 0;
+        p->laccel->ctx = p->ctx, p->laccel->scene = p->lscene, p->laccel->flags = GPURT_BUILD_LBVH; /* rebuilt on every pose edit */
     } else { /* pose edit: same geometry, new model matrices */
         for(size_t l = 0; l < M.lights.size(); l++) p->lscene->packed.descs[l] = M.descs[M.lights[l].index];
         p->lscene->version++;

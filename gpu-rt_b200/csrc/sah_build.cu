@@ -33,7 +33,8 @@ namespace gpurt {
 
 namespace {
 
-constexpr unsigned SAH_TILE = 1024;
+constexpr unsigned SAH_TILE = 1024;      /* positions per tile of the grid-wide kernels */
+constexpr unsigned SAH_SMALL_MAX = 1024; /* default: segments up to this size are built by one warp of k_sah_small (>= SAH_TILE) */
 constexpr int SAH_BINS = 16;
 constexpr float SAH_BIG = 3.0e38f;
 constexpr unsigned FULL = 0xffffffffu;
@@ -59,8 +60,12 @@ struct SahJob {
     int me, parent;
     unsigned src;
 };
-struct SahState {
-    unsigned n_seg, n_seg_next, q_tail, q_head, small_total, leaves_done;
+struct SahState { /* the hot counters of k_sah_small live on cache lines of their own */
+    unsigned n_seg, n_seg_next, small_total, pad0[29];
+    unsigned q_tail, pad1[31];
+    unsigned q_head, pad2[31];
+    unsigned leaves_done, pad3[31];
+    unsigned finished, stalled, pad4[30];
 };
 
 /* order-preserving float <-> int for atomicMin / atomicMax */
@@ -139,6 +144,72 @@ __device__ __forceinline__ void bins_add(LaneBins& B, unsigned group, float4 l, 
     }
 }
 
+
+/* The same, two items per step: the lower half-warp folds item j, the upper half item j + 1, and every lane owns bin
+ * lane & 15 of all three axes (17 instead of 28 warp instructions per item).  `group` must be a contiguous lane range;
+ * lanes outside it pass packed = 0xffffffff.  merge() leaves the union of the two halves in every lane. */
+struct LaneBins3 {
+    unsigned cnt[3];
+    float lo[3][3], hi[3][3];
+    __device__ __forceinline__ void reset() {
+#pragma unroll
+        for(int s = 0; s < 3; s++) {
+            cnt[s] = 0;
+#pragma unroll
+            for(int k = 0; k < 3; k++) lo[s][k] = SAH_BIG, hi[s][k] = -SAH_BIG;
+        }
+    }
+    __device__ __forceinline__ void merge() {
+#pragma unroll
+        for(int s = 0; s < 3; s++) {
+            cnt[s] += __shfl_xor_sync(FULL, cnt[s], 16);
+#pragma unroll
+            for(int k = 0; k < 3; k++)
+                lo[s][k] = fminf(lo[s][k], __shfl_xor_sync(FULL, lo[s][k], 16)), hi[s][k] = fmaxf(hi[s][k], __shfl_xor_sync(FULL, hi[s][k], 16));
+        }
+    }
+    /* after merge(): the layout eval_split works on */
+    __device__ __forceinline__ LaneBins split_layout(int lane) const {
+        LaneBins B;
+        const int a = lane >> 4;
+        B.cnt[0] = a ? cnt[1] : cnt[0], B.cnt[1] = cnt[2];
+#pragma unroll
+        for(int k = 0; k < 3; k++)
+            B.lo[0][k] = a ? lo[1][k] : lo[0][k], B.hi[0][k] = a ? hi[1][k] : hi[0][k], B.lo[1][k] = lo[2][k], B.hi[1][k] = hi[2][k];
+        return B;
+    }
+};
+__device__ __forceinline__ void bins_add2(LaneBins3& B, unsigned group, float4 l, float4 h, unsigned packed, int lane) {
+    if(!group) return;
+    const int first = __ffs((int)group) - 1, last = 31 - __clz((int)group), half = lane >> 4;
+    const unsigned mine = (unsigned)(lane & 15);
+    /* four items per trip (two per half-warp): both shuffle batches are issued before either is consumed */
+    for(int j = first; j <= last; j += 4) {
+        const int s0 = j + half, s1 = j + 2 + half;
+        const float ax0 = __shfl_sync(FULL, l.x, s0), ay0 = __shfl_sync(FULL, l.y, s0), az0 = __shfl_sync(FULL, l.z, s0);
+        const float bx0 = __shfl_sync(FULL, h.x, s0), by0 = __shfl_sync(FULL, h.y, s0), bz0 = __shfl_sync(FULL, h.z, s0);
+        unsigned p0 = __shfl_sync(FULL, packed, s0);
+        const float ax1 = __shfl_sync(FULL, l.x, s1), ay1 = __shfl_sync(FULL, l.y, s1), az1 = __shfl_sync(FULL, l.z, s1);
+        const float bx1 = __shfl_sync(FULL, h.x, s1), by1 = __shfl_sync(FULL, h.y, s1), bz1 = __shfl_sync(FULL, h.z, s1);
+        unsigned p1 = __shfl_sync(FULL, packed, s1);
+        if(s0 > last) p0 = 0xffffffffu;
+        if(s1 > last) p1 = 0xffffffffu;
+#pragma unroll
+        for(int ax = 0; ax < 3; ax++) {
+            if(((p0 >> (8 * ax)) & 0xffu) == mine) {
+                B.cnt[ax]++;
+                B.lo[ax][0] = fminf(B.lo[ax][0], ax0), B.lo[ax][1] = fminf(B.lo[ax][1], ay0), B.lo[ax][2] = fminf(B.lo[ax][2], az0);
+                B.hi[ax][0] = fmaxf(B.hi[ax][0], bx0), B.hi[ax][1] = fmaxf(B.hi[ax][1], by0), B.hi[ax][2] = fmaxf(B.hi[ax][2], bz0);
+            }
+            if(((p1 >> (8 * ax)) & 0xffu) == mine) {
+                B.cnt[ax]++;
+                B.lo[ax][0] = fminf(B.lo[ax][0], ax1), B.lo[ax][1] = fminf(B.lo[ax][1], ay1), B.lo[ax][2] = fminf(B.lo[ax][2], az1);
+                B.hi[ax][0] = fmaxf(B.hi[ax][0], bx1), B.hi[ax][1] = fmaxf(B.hi[ax][1], by1), B.hi[ax][2] = fmaxf(B.hi[ax][2], bz1);
+            }
+        }
+    }
+}
+
 /* The split of a segment from its bins (sah_split.h: lowest cost, ties to the lower axis, then the lower boundary;
  * candidates need both sides non-empty and a cost below 3.0e38).  Returns axis (-1: none), boundary k and the left count,
  * the same in every lane. */
@@ -207,14 +278,15 @@ __device__ __forceinline__ void eval_split(const LaneBins& B, int lane, int& axi
 
 /* ---- big segments ------------------------------------------------------------------------------------------------- */
 /* root: either the first big segment (with empty bins / bounds) or the first small job */
-__global__ void k_sah_setup(unsigned n, SahState* st, SahSeg* segs, SahJob* jobs, unsigned* ready, int* cb, int* bins,
+__global__ void k_sah_setup(unsigned n, unsigned small_max, SahState* st, SahSeg* segs, SahJob* jobs, unsigned* ready, int* cb, int* bins,
                             unsigned* tiles_done) {
-    const bool big_root = n > SAH_TILE;
+    const bool big_root = n > small_max;
     for(int i = threadIdx.x; i < SAH_BIN_WORDS; i += blockDim.x) bins[i] = (i % 7) == 0 ? 0 : ((i % 7) < 4 ? enc(SAH_BIG) : enc(-SAH_BIG));
     if(threadIdx.x < 6) cb[threadIdx.x] = threadIdx.x < 3 ? enc(SAH_BIG) : enc(-SAH_BIG);
     if(threadIdx.x == 0) {
         tiles_done[0] = 0;
-        *st = SahState{big_root ? 1u : 0u, 0u, big_root ? 0u : 1u, 0u, big_root ? 0u : n, 0u};
+        st->n_seg = big_root ? 1u : 0u, st->n_seg_next = 0u, st->small_total = big_root ? 0u : n;
+        st->q_tail = big_root ? 0u : 1u, st->q_head = 0u, st->leaves_done = 0u, st->finished = 0u, st->stalled = 0u;
         if(big_root) segs[0] = SahSeg{0u, n, 0, -1};
         else jobs[0] = SahJob{0u, n, 0, -1, 0u}, ready[0] = 1u;
     }
@@ -244,31 +316,32 @@ __global__ void __launch_bounds__(256) k_sah_init(const float4* __restrict__ tri
     }
 }
 
-__device__ __forceinline__ void flush_bins(const LaneBins& B, int* bins, int seg, int lane) {
-    int* base = bins + (size_t)seg * SAH_BIN_WORDS;
-#pragma unroll
-    for(int s = 0; s < 2; s++) {
-        if(s == 1 && lane >= 16) break;
-        if(B.cnt[s] == 0) continue;
-        const int ax = s == 0 ? (lane >> 4) : 2;
-        int* w = base + (ax * SAH_BINS + (lane & 15)) * 7;
-        atomicAdd((unsigned*)w, B.cnt[s]);
-#pragma unroll
-        for(int q = 0; q < 3; q++) atomicMin(w + 1 + q, enc(B.lo[s][q])), atomicMax(w + 4 + q, enc(B.hi[s][q]));
-    }
-}
-
 __global__ void __launch_bounds__(256) k_sah_bins(const SahRec* __restrict__ rec, const int* __restrict__ seg_of, unsigned n,
                                                    const SahSeg* __restrict__ segs, const int* __restrict__ cb, int* bins,
                                                    unsigned* tiles_done, SahSplit* split) {
     __shared__ int s_slot[2];
+    __shared__ int s_bins[2][SAH_BIN_WORDS]; /* the tile's share of the (at most two) segments it touches */
     const unsigned tile0 = blockIdx.x * SAH_TILE;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if(threadIdx.x < 2) s_slot[threadIdx.x] = -1;
+    for(int i = threadIdx.x; i < 2 * SAH_BIN_WORDS; i += blockDim.x)
+        (&s_bins[0][0])[i] = (i % 7) == 0 ? 0 : ((i % 7) < 4 ? enc(SAH_BIG) : enc(-SAH_BIG));
     __syncthreads();
     LaneBins B;
+    LaneBins3 B3;
     SegFrame F;
-    int cur = -1;
+    int cur = -1, cur_slot = 0;
+    auto flush = [&]() { /* this warp's share of segment `cur` into the tile's bins */
+        int* base = s_bins[cur_slot];
+#pragma unroll
+        for(int ax = 0; ax < 3; ax++) {
+            if(B3.cnt[ax] == 0) continue;
+            int* w = base + (ax * SAH_BINS + (lane & 15)) * 7;
+            atomicAdd((unsigned*)w, B3.cnt[ax]);
+#pragma unroll
+            for(int q = 0; q < 3; q++) atomicMin(w + 1 + q, enc(B3.lo[ax][q])), atomicMax(w + 4 + q, enc(B3.hi[ax][q]));
+        }
+    };
     for(int it = 0; it < 4; it++) {
         const unsigned pos = tile0 + warp * 128 + it * 32 + lane;
         const int s = pos < n ? seg_of[pos] : -1;
@@ -280,23 +353,32 @@ __global__ void __launch_bounds__(256) k_sah_bins(const SahRec* __restrict__ rec
             else if(pos == a) s_slot[1] = s;                /* a segment that starts inside the tile (at most one is big) */
         }
         unsigned todo = __ballot_sync(FULL, s >= 0);
-        while(todo) {
+        while(todo) { /* at most two big segments meet in a warp's 32 positions */
             const int sj = __shfl_sync(FULL, s, __ffs((int)todo) - 1);
             const unsigned group = __ballot_sync(FULL, s == sj);
             if(sj != cur) {
-                if(cur >= 0) flush_bins(B, bins, cur, lane);
-                B.reset();
-                cur = sj;
+                if(cur >= 0) flush();
+                B3.reset();
+                cur = sj, cur_slot = segs[sj].a > tile0 ? 1 : 0;
                 float cl[3], ch[3];
 #pragma unroll
                 for(int q = 0; q < 3; q++) cl[q] = dec(cb[6 * sj + q]), ch[q] = dec(cb[6 * sj + 3 + q]);
                 F.set(cl, ch);
             }
-            bins_add(B, group, l, h, s == sj ? F.bins(l, h) : 0xffffffffu, lane);
+            bins_add2(B3, group, l, h, s == sj ? F.bins(l, h) : 0xffffffffu, lane);
             todo &= ~group;
         }
     }
-    if(cur >= 0) flush_bins(B, bins, cur, lane);
+    if(cur >= 0) flush();
+    __syncthreads();
+    for(int i = threadIdx.x; i < 2 * SAH_BIN_WORDS; i += blockDim.x) { /* one global update per tile, segment and non-empty bin */
+        const int slot = i / SAH_BIN_WORDS, w = i % SAH_BIN_WORDS, sg = s_slot[slot];
+        if(sg < 0 || s_bins[slot][w - w % 7] == 0) continue;
+        int* g = bins + (size_t)sg * SAH_BIN_WORDS + w;
+        if(w % 7 == 0) atomicAdd((unsigned*)g, (unsigned)s_bins[slot][w]);
+        else if(w % 7 < 4) atomicMin(g, s_bins[slot][w]);
+        else atomicMax(g, s_bins[slot][w]);
+    }
     /* the last tile of a segment to get here evaluates its split (warp 0: slot 0, warp 1: slot 1) */
     __threadfence();
     __syncthreads();
@@ -310,14 +392,15 @@ __global__ void __launch_bounds__(256) k_sah_bins(const SahRec* __restrict__ rec
     old = __shfl_sync(FULL, old, 0);
     if(old != ntiles - 1) return;
     __threadfence();
-    const int* base = bins + (size_t)s * SAH_BIN_WORDS;
+    {
+        const int* base = bins + (size_t)s * SAH_BIN_WORDS;
 #pragma unroll
-    for(int q = 0; q < 2; q++) {
-        const int ax = q == 0 ? (lane >> 4) : 2;
-        const int* w = base + (ax * SAH_BINS + (lane & 15)) * 7;
-        B.cnt[q] = (unsigned)__ldcg(w);
+        for(int q = 0; q < 2; q++) {
+            const int* w = base + ((q == 0 ? (lane >> 4) : 2) * SAH_BINS + (lane & 15)) * 7;
+            B.cnt[q] = (unsigned)__ldcg(w);
 #pragma unroll
-        for(int c = 0; c < 3; c++) B.lo[q][c] = dec(__ldcg(w + 1 + c)), B.hi[q][c] = dec(__ldcg(w + 4 + c));
+            for(int c = 0; c < 3; c++) B.lo[q][c] = dec(__ldcg(w + 1 + c)), B.hi[q][c] = dec(__ldcg(w + 4 + c));
+        }
     }
     int axis, k;
     unsigned nl;
@@ -382,7 +465,7 @@ __global__ void __launch_bounds__(1024) k_sah_level(unsigned* tile_left, unsigne
                                                      SahSeg* segs_next, SahSplit* split, SahState* st, int* cb, int* bins,
                                                      unsigned* tiles_done, SahJob* jobs, int* ready, unsigned dst_parity,
                                                      int* left, int* right, int* parent, int* range_first, int* range_last,
-                                                     unsigned ni, unsigned* host_flag) {
+                                                     unsigned ni, unsigned* host_flag, unsigned small_max) {
     __shared__ unsigned s_w[32];
     __shared__ unsigned s_carry;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -435,7 +518,7 @@ __global__ void __launch_bounds__(1024) k_sah_level(unsigned* tile_left, unsigne
                 ref[side] = ~(int)ca[side];
                 parent[(size_t)ni + ca[side]] = sg.me;
                 sp.child[side] = -2;
-            } else if(c <= SAH_TILE) {
+            } else if(c <= small_max) {
                 ref[side] = cme[side];
                 const unsigned idx = atomicAdd(&st->q_tail, 1u);
                 jobs[idx] = SahJob{ca[side], cbnd[side], cme[side], sg.me, dst_parity};
@@ -474,8 +557,11 @@ __global__ void __launch_bounds__(256) k_sah_scatter(const SahRec* __restrict__ 
                                                       const SahSplit* __restrict__ split, const unsigned* __restrict__ scan,
                                                       SahRec* rec_out, int* seg_out, int* cb, uint32_t* order) {
     __shared__ unsigned s_w[8];
+    __shared__ int s_cb[4][6], s_child[4]; /* centroid bounds of the (slot, side) children that are big segments */
     const unsigned tile0 = blockIdx.x * SAH_TILE, p0 = tile0 + 4 * threadIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if(threadIdx.x < 24) s_cb[threadIdx.x / 6][threadIdx.x % 6] = (threadIdx.x % 6) < 3 ? enc(SAH_BIG) : enc(-SAH_BIG);
+    if(threadIdx.x < 4) s_child[threadIdx.x] = -1;
     int seg[4];
     const unsigned f = tile_flags(rec, seg_of, n, split, tile0, p0, seg);
     unsigned c = 0;
@@ -497,7 +583,7 @@ __global__ void __launch_bounds__(256) k_sah_scatter(const SahRec* __restrict__ 
         const unsigned pos = p0 + r;
         const bool valid = pos < n;
         const int s = seg[r];
-        int child = -1;
+        int child = -1, cidx = 0;
         unsigned dest = pos;
         float4 l = make_float4(0, 0, 0, 0), h = l;
         if(valid && s >= 0) {
@@ -507,14 +593,15 @@ __global__ void __launch_bounds__(256) k_sah_scatter(const SahRec* __restrict__ 
             const unsigned in_tile = slot ? (before >> 16) : (before & 0xffffu);
             const unsigned lefts_before = scan[2 * blockIdx.x + slot] - sp.base + in_tile;
             dest = is_left ? sp.a + lefts_before : sp.a + sp.nl + (pos - sp.a) - lefts_before;
-            child = sp.child[is_left ? 0 : 1];
+            child = sp.child[is_left ? 0 : 1], cidx = (int)slot * 2 + (is_left ? 0 : 1);
             l = rec[pos].lo, h = rec[pos].hi;
             rec_out[dest].lo = l, rec_out[dest].hi = h;
             if(is_left) before += slot ? 0x10000u : 1u;
             if(child == -2) order[dest] = __float_as_uint(l.w);
         }
         if(valid) seg_out[dest] = child >= 0 ? child : -1;
-        /* centroid bounds of big children: one atomic set per warp and child (every lane takes part in the match) */
+        /* centroid bounds of big children: reduced per warp and child (every lane takes part in the match), merged per
+         * tile in shared memory, one global update per tile and child */
         const unsigned grp = __match_any_sync(FULL, child);
         if(child >= 0) {
             const float cen[3] = {(l.x + h.x) * 0.5f, (l.y + h.y) * 0.5f, (l.z + h.z) * 0.5f};
@@ -523,9 +610,16 @@ __global__ void __launch_bounds__(256) k_sah_scatter(const SahRec* __restrict__ 
                 const bool ok = cen[q] == cen[q];
                 const int mn = __reduce_min_sync(grp, enc(ok ? fminf(cen[q], SAH_BIG) : SAH_BIG));
                 const int mx = __reduce_max_sync(grp, enc(ok ? fmaxf(cen[q], -SAH_BIG) : -SAH_BIG));
-                if(lane == __ffs((int)grp) - 1) atomicMin(cb + 6 * child + q, mn), atomicMax(cb + 6 * child + 3 + q, mx);
+                if(lane == __ffs((int)grp) - 1) atomicMin(&s_cb[cidx][q], mn), atomicMax(&s_cb[cidx][3 + q], mx);
             }
+            if(lane == __ffs((int)grp) - 1) s_child[cidx] = child;
         }
+    }
+    __syncthreads();
+    if(threadIdx.x < 24 && s_child[threadIdx.x / 6] >= 0) {
+        int* g = cb + 6 * s_child[threadIdx.x / 6] + threadIdx.x % 6;
+        if(threadIdx.x % 6 < 3) atomicMin(g, s_cb[threadIdx.x / 6][threadIdx.x % 6]);
+        else atomicMax(g, s_cb[threadIdx.x / 6][threadIdx.x % 6]);
     }
 }
 
@@ -539,10 +633,133 @@ __device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+/* leaves finished: the warp that completes the last one raises `finished` for the waiting warps */
+__device__ __forceinline__ void leaves_add(SahState* st, unsigned k, unsigned total) {
+    __threadfence();
+    if(atomicAdd(&st->leaves_done, k) + k >= total) st_release(&st->finished, 1u);
+}
+
+struct SmallOut {
+    uint32_t* order;
+    int *left, *right, *parent, *range_first, *range_last;
+    unsigned ni;
+};
+
+/* A subtree of at most 32 items, entirely in registers: lane i holds the item at position a + i.  Nodes are taken from
+ * a warp-private stack; a partition permutes the lanes through shared memory; only the node records and, at the end,
+ * the primitive ids of the final lane order go to global memory. */
+__device__ __forceinline__ void subtree32(unsigned a, unsigned m, int me0, int par0, float4 l, float4 h, float4* stage, uint4* stack,
+                                          const SmallOut& O, int lane) {
+    const unsigned lt = (1u << lane) - 1u;
+    int sp = 0;
+    if(lane == 0) stack[0] = make_uint4(0u, m, (unsigned)me0, (unsigned)par0);
+    sp = 1;
+    __syncwarp();
+    while(sp) {
+        const uint4 nd = stack[--sp];
+        __syncwarp();
+        const unsigned off = nd.x, cnt = nd.y;
+        const int me = (int)nd.z, par = (int)nd.w;
+        const bool in = (unsigned)lane - off < cnt;
+        if(cnt == 2) {
+            /* Two items.  With finite centroids the definition reduces to: the first axis on which the centroids differ, the
+             * boundary k = 1 (bins 0 and >= 1), cost = area(first) + area(second); a cost of 3.0e38 or more, or no such axis,
+             * means the middle split — which is the same node, possibly without the swap. */
+            const float c[3] = {(l.x + h.x) * 0.5f, (l.y + h.y) * 0.5f, (l.z + h.z) * 0.5f};
+            float o[3];
+#pragma unroll
+            for(int q = 0; q < 3; q++) o[q] = __shfl_sync(FULL, c[q], (int)off + 1 - (lane - (int)off)); /* the partner's */
+            bool fin = true;
+            int ax = -1;
+#pragma unroll
+            for(int q = 2; q >= 0; q--) {
+                fin = fin && fabsf(c[q]) < SAH_BIG && fabsf(o[q]) < SAH_BIG && fabsf(c[q] - o[q]) < SAH_BIG;
+                if(c[q] != o[q]) ax = q;
+            }
+            const float lo3[3] = {l.x, l.y, l.z}, hi3[3] = {h.x, h.y, h.z};
+            const float my_area = sah_area(lo3, hi3);
+            const float a0 = __shfl_sync(FULL, my_area, (int)off), a1 = __shfl_sync(FULL, my_area, (int)off + 1);
+            fin = __shfl_sync(FULL, fin, (int)off) && __shfl_sync(FULL, fin, (int)off + 1);
+            ax = __shfl_sync(FULL, ax, (int)off);
+            if(fin) {
+                /* first item (lane off) goes right iff a valid candidate exists and its centroid is the larger one */
+                const float c_first = __shfl_sync(FULL, ax >= 0 ? c[ax] : 0.0f, (int)off);
+                const float c_second = __shfl_sync(FULL, ax >= 0 ? c[ax] : 0.0f, (int)off + 1);
+                const bool first_is_low = c_first < c_second;
+                const float cost = first_is_low ? a0 * 1.0f + a1 * 1.0f : a1 * 1.0f + a0 * 1.0f;
+                const bool swap = ax >= 0 && cost < SAH_BIG && !first_is_low;
+                if(swap) {
+                    const int partner = (int)off + 1 - (lane - (int)off);
+                    const float4 l2 = make_float4(__shfl_sync(FULL, l.x, partner & 31), __shfl_sync(FULL, l.y, partner & 31),
+                                                  __shfl_sync(FULL, l.z, partner & 31), __shfl_sync(FULL, l.w, partner & 31));
+                    const float4 h2 = make_float4(__shfl_sync(FULL, h.x, partner & 31), __shfl_sync(FULL, h.y, partner & 31),
+                                                  __shfl_sync(FULL, h.z, partner & 31), __shfl_sync(FULL, h.w, partner & 31));
+                    if(in) l = l2, h = h2;
+                }
+                if(lane == 0) {
+                    const unsigned p0 = a + off;
+                    O.left[me] = ~(int)p0, O.right[me] = ~(int)(p0 + 1), O.parent[me] = par;
+                    O.range_first[me] = (int)p0, O.range_last[me] = (int)p0 + 1;
+                    O.parent[(size_t)O.ni + p0] = me, O.parent[(size_t)O.ni + p0 + 1] = me;
+                }
+                continue;
+            }
+        }
+        float cl[3], ch[3];
+        {
+            const float c[3] = {(l.x + h.x) * 0.5f, (l.y + h.y) * 0.5f, (l.z + h.z) * 0.5f};
+#pragma unroll
+            for(int q = 0; q < 3; q++) cl[q] = in ? fminf(SAH_BIG, c[q]) : SAH_BIG, ch[q] = in ? fmaxf(-SAH_BIG, c[q]) : -SAH_BIG;
+        }
+#pragma unroll
+        for(int d = 16; d >= 1; d >>= 1)
+#pragma unroll
+            for(int q = 0; q < 3; q++)
+                cl[q] = fminf(cl[q], __shfl_xor_sync(FULL, cl[q], d)), ch[q] = fmaxf(ch[q], __shfl_xor_sync(FULL, ch[q], d));
+        SegFrame F;
+        F.set(cl, ch);
+        LaneBins B;
+        B.reset();
+        const unsigned group = __ballot_sync(FULL, in);
+        bins_add(B, group, l, h, in ? F.bins(l, h) : 0xffffffffu, lane);
+        int axis, k;
+        unsigned nl;
+        eval_split(B, lane, axis, k, nl);
+        if(axis < 0) nl = cnt / 2;
+        const unsigned nr = cnt - nl;
+        bool is_left = false;
+        if(in) is_left = axis < 0 ? (unsigned)lane < off + nl : sah_bin((axis_of(l, axis) + axis_of(h, axis)) * 0.5f, F.lo[axis], F.scale[axis]) < k;
+        const unsigned ml = __ballot_sync(FULL, in && is_left), mr = __ballot_sync(FULL, in && !is_left);
+        if(in) {
+            const unsigned dest = is_left ? off + __popc(ml & lt) : off + nl + __popc(mr & lt);
+            stage[2 * dest] = l, stage[2 * dest + 1] = h;
+        }
+        __syncwarp();
+        if(in) l = stage[2 * lane], h = stage[2 * lane + 1];
+        if(lane == 0) {
+            const unsigned p0 = a + off;
+            O.left[me] = nl == 1 ? ~(int)p0 : me + 1;
+            O.right[me] = nr == 1 ? ~(int)(p0 + nl) : me + (int)nl;
+            O.parent[me] = par;
+            O.range_first[me] = (int)p0, O.range_last[me] = (int)(p0 + cnt) - 1;
+            if(nl == 1) O.parent[(size_t)O.ni + p0] = me;
+            if(nr == 1) O.parent[(size_t)O.ni + p0 + nl] = me;
+            if(nr >= 2) stack[sp] = make_uint4(off + nl, nr, (unsigned)(me + (int)nl), (unsigned)me);
+            if(nl >= 2) stack[sp + (nr >= 2 ? 1 : 0)] = make_uint4(off, nl, (unsigned)(me + 1), (unsigned)me);
+        }
+        sp += (nr >= 2 ? 1 : 0) + (nl >= 2 ? 1 : 0);
+        __syncwarp();
+    }
+    if((unsigned)lane < m) O.order[a + lane] = __float_as_uint(l.w);
+}
+
 __global__ void __launch_bounds__(128) k_sah_small(SahRec* rec0, SahRec* rec1, SahJob* jobs, unsigned* ready, SahState* st,
-                                                    unsigned cap, uint32_t* order, int* left, int* right, int* parent,
-                                                    int* range_first, int* range_last, unsigned ni) {
-    const int lane = threadIdx.x & 31;
+                                                    unsigned cap, SmallOut O) {
+    __shared__ float4 s_stage[4][64];
+    __shared__ uint4 s_stack[4][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float4* stage = s_stage[warp];
+    uint4* stack = s_stack[warp];
     const unsigned lt = (1u << lane) - 1u;
     const unsigned total = st->small_total;
     for(;;) {
@@ -551,13 +768,22 @@ __global__ void __launch_bounds__(128) k_sah_small(SahRec* rec0, SahRec* rec1, S
         ticket = __shfl_sync(FULL, ticket, 0);
         int got = 0;
         if(lane == 0) {
-            for(;;) {
+            /* a ticket is served as soon as some warp queues its job; the warp that finishes the last leaf raises
+             * `finished`.  A warp gives up after ~2 s without either (cannot happen unless a job was lost: the host then
+             * reports the build as failed instead of hanging the device) */
+            unsigned ns = 32;
+            for(unsigned spins = 0;; spins++) {
                 if(ticket < cap && ld_acquire(ready + ticket)) {
                     got = 1;
                     break;
                 }
-                if(ld_acquire(&st->leaves_done) >= total) break;
-                __nanosleep(64);
+                if((spins & 3u) == 3u && (ld_acquire(&st->finished) || ld_acquire(&st->stalled))) break;
+                if(spins > (1u << 21)) {
+                    atomicExch(&st->stalled, 1u);
+                    break;
+                }
+                __nanosleep(ns);
+                if(ns < 1024) ns += ns;
             }
         }
         got = __shfl_sync(FULL, got, 0);
@@ -566,33 +792,53 @@ __global__ void __launch_bounds__(128) k_sah_small(SahRec* rec0, SahRec* rec1, S
         const unsigned* jw = (const unsigned*)(jobs + ticket);
         unsigned a = __ldcg(jw), b = __ldcg(jw + 1), src = __ldcg(jw + 4);
         int me = (int)__ldcg(jw + 2), par = (int)__ldcg(jw + 3);
+        bool have_bounds = false; /* a child continued by this warp inherits the bounds its parent's partition reduced */
+        float cl[3], ch[3];
         for(;;) { /* one inner node per iteration: [a, b), at least two items */
             const SahRec* in = src ? rec1 : rec0;
             SahRec* out = src ? rec0 : rec1;
             const unsigned m = b - a;
-            float cl[3] = {SAH_BIG, SAH_BIG, SAH_BIG}, ch[3] = {-SAH_BIG, -SAH_BIG, -SAH_BIG};
-            for(unsigned i = a + lane; i < b; i += 32) {
-                const float4 l = __ldcg(&in[i].lo), h = __ldcg(&in[i].hi);
-                const float c[3] = {(l.x + h.x) * 0.5f, (l.y + h.y) * 0.5f, (l.z + h.z) * 0.5f};
-#pragma unroll
-                for(int q = 0; q < 3; q++) cl[q] = fminf(cl[q], c[q]), ch[q] = fmaxf(ch[q], c[q]);
+            if(m <= 32) {
+                float4 l = make_float4(0, 0, 0, 0), h = l;
+                if((unsigned)lane < m) l = __ldcg(&in[a + lane].lo), h = __ldcg(&in[a + lane].hi);
+                subtree32(a, m, me, par, l, h, stage, stack, O, lane);
+                if(lane == 0) leaves_add(st, m, total);
+                break;
             }
+            if(!have_bounds) {
 #pragma unroll
-            for(int d = 16; d >= 1; d >>= 1)
+                for(int q = 0; q < 3; q++) cl[q] = SAH_BIG, ch[q] = -SAH_BIG;
+                for(unsigned i = a + lane; i < b; i += 32) {
+                    const float4 l = __ldcg(&in[i].lo), h = __ldcg(&in[i].hi);
+                    const float c[3] = {(l.x + h.x) * 0.5f, (l.y + h.y) * 0.5f, (l.z + h.z) * 0.5f};
 #pragma unroll
-                for(int q = 0; q < 3; q++)
-                    cl[q] = fminf(cl[q], __shfl_xor_sync(FULL, cl[q], d)), ch[q] = fmaxf(ch[q], __shfl_xor_sync(FULL, ch[q], d));
+                    for(int q = 0; q < 3; q++) cl[q] = fminf(cl[q], c[q]), ch[q] = fmaxf(ch[q], c[q]);
+                }
+#pragma unroll
+                for(int d = 16; d >= 1; d >>= 1)
+#pragma unroll
+                    for(int q = 0; q < 3; q++)
+                        cl[q] = fminf(cl[q], __shfl_xor_sync(FULL, cl[q], d)), ch[q] = fmaxf(ch[q], __shfl_xor_sync(FULL, ch[q], d));
+            }
             SegFrame F;
             F.set(cl, ch);
-            LaneBins B;
-            B.reset();
-            for(unsigned base = a; base < b; base += 32) {
-                const unsigned i = base + lane;
-                const bool valid = i < b;
+            LaneBins3 B3;
+            B3.reset();
+            {
+                /* the next step's records are in flight while this step's 32 items are binned */
+                unsigned i = a + lane;
                 float4 l = make_float4(0, 0, 0, 0), h = l;
-                if(valid) l = __ldcg(&in[i].lo), h = __ldcg(&in[i].hi);
-                bins_add(B, __ballot_sync(FULL, valid), l, h, valid ? F.bins(l, h) : 0xffffffffu, lane);
+                if(i < b) l = __ldcg(&in[i].lo), h = __ldcg(&in[i].hi);
+                for(unsigned base = a; base < b; base += 32) {
+                    const bool valid = base + lane < b;
+                    const float4 l0 = l, h0 = h;
+                    i = base + 32 + lane;
+                    if(i < b) l = __ldcg(&in[i].lo), h = __ldcg(&in[i].hi);
+                    bins_add2(B3, __ballot_sync(FULL, valid), l0, h0, valid ? F.bins(l0, h0) : 0xffffffffu, lane);
+                }
             }
+            B3.merge();
+            const LaneBins B = B3.split_layout(lane);
             int axis, k;
             unsigned nl;
             eval_split(B, lane, axis, k, nl);
@@ -600,51 +846,77 @@ __global__ void __launch_bounds__(128) k_sah_small(SahRec* rec0, SahRec* rec1, S
             const float s_lo = axis >= 0 ? F.lo[axis] : 0.0f, s_scale = axis >= 0 ? F.scale[axis] : 0.0f;
             const unsigned nr = m - nl;
             unsigned run_l = 0, run_r = 0;
-            for(unsigned base = a; base < b; base += 32) {
-                const unsigned i = base + lane;
-                const bool valid = i < b;
+            int eb[2][6]; /* centroid bounds of the two children, reduced while their items pass by */
+#pragma unroll
+            for(int q = 0; q < 6; q++) eb[0][q] = eb[1][q] = q < 3 ? enc(SAH_BIG) : enc(-SAH_BIG);
+            {
+                unsigned i = a + lane;
                 float4 l = make_float4(0, 0, 0, 0), h = l;
-                bool is_left = false;
-                if(valid) {
-                    l = __ldcg(&in[i].lo), h = __ldcg(&in[i].hi);
-                    is_left = axis < 0 ? i < a + nl : sah_bin((axis_of(l, axis) + axis_of(h, axis)) * 0.5f, s_lo, s_scale) < k;
+                if(i < b) l = __ldcg(&in[i].lo), h = __ldcg(&in[i].hi);
+                for(unsigned base = a; base < b; base += 32) {
+                    const unsigned pos = base + lane;
+                    const bool valid = pos < b;
+                    const float4 l0 = l, h0 = h;
+                    i = base + 32 + lane;
+                    if(i < b) l = __ldcg(&in[i].lo), h = __ldcg(&in[i].hi);
+                    const float c[3] = {(l0.x + h0.x) * 0.5f, (l0.y + h0.y) * 0.5f, (l0.z + h0.z) * 0.5f};
+                    bool is_left = false;
+                    if(valid) is_left = axis < 0 ? pos < a + nl : sah_bin(axis == 0 ? c[0] : (axis == 1 ? c[1] : c[2]), s_lo, s_scale) < k;
+                    const unsigned ml = __ballot_sync(FULL, valid && is_left), mr = __ballot_sync(FULL, valid && !is_left);
+                    if(valid) {
+                        const unsigned dest = is_left ? a + run_l + __popc(ml & lt) : a + nl + run_r + __popc(mr & lt);
+                        out[dest].lo = l0, out[dest].hi = h0;
+                        if((is_left && nl == 1) || (!is_left && nr == 1)) O.order[dest] = __float_as_uint(l0.w);
+                    }
+                    run_l += __popc(ml), run_r += __popc(mr);
+#pragma unroll
+                    for(int q = 0; q < 3; q++) {
+                        const bool ok = valid && c[q] == c[q];
+                        const int lo_e = enc(ok ? fminf(c[q], SAH_BIG) : SAH_BIG), hi_e = enc(ok ? fmaxf(c[q], -SAH_BIG) : -SAH_BIG);
+                        eb[0][q] = min(eb[0][q], __reduce_min_sync(FULL, is_left ? lo_e : enc(SAH_BIG)));
+                        eb[0][3 + q] = max(eb[0][3 + q], __reduce_max_sync(FULL, is_left ? hi_e : enc(-SAH_BIG)));
+                        eb[1][q] = min(eb[1][q], __reduce_min_sync(FULL, valid && !is_left ? lo_e : enc(SAH_BIG)));
+                        eb[1][3 + q] = max(eb[1][3 + q], __reduce_max_sync(FULL, valid && !is_left ? hi_e : enc(-SAH_BIG)));
+                    }
                 }
-                const unsigned ml = __ballot_sync(FULL, valid && is_left), mr = __ballot_sync(FULL, valid && !is_left);
-                if(valid) {
-                    const unsigned dest = is_left ? a + run_l + __popc(ml & lt) : a + nl + run_r + __popc(mr & lt);
-                    out[dest].lo = l, out[dest].hi = h;
-                    if((is_left && nl == 1) || (!is_left && nr == 1)) order[dest] = __float_as_uint(l.w);
-                }
-                run_l += __popc(ml), run_r += __popc(mr);
             }
             if(lane == 0) {
-                left[me] = nl == 1 ? ~(int)a : me + 1;
-                right[me] = nr == 1 ? ~(int)(a + nl) : me + (int)nl;
-                parent[me] = par;
-                range_first[me] = (int)a, range_last[me] = (int)b - 1;
-                if(nl == 1) parent[(size_t)ni + a] = me;
-                if(nr == 1) parent[(size_t)ni + a + nl] = me;
+                O.left[me] = nl == 1 ? ~(int)a : me + 1;
+                O.right[me] = nr == 1 ? ~(int)(a + nl) : me + (int)nl;
+                O.parent[me] = par;
+                O.range_first[me] = (int)a, O.range_last[me] = (int)b - 1;
+                if(nl == 1) O.parent[(size_t)O.ni + a] = me;
+                if(nr == 1) O.parent[(size_t)O.ni + a + nl] = me;
             }
             const unsigned leaves = (nl == 1 ? 1u : 0u) + (nr == 1 ? 1u : 0u);
-            const bool go_l = nl >= 2, go_r = nr >= 2;
-            if(go_l && go_r) { /* queue the right child, keep the left one */
-                __threadfence();
-                __syncwarp();
-                if(lane == 0) {
-                    const unsigned idx = atomicAdd(&st->q_tail, 1u);
-                    jobs[idx] = SahJob{a + nl, b, me + (int)nl, me, src ^ 1u};
-                    __threadfence();
-                    st_release(ready + idx, 1u);
-                }
+            __threadfence();
+            __syncwarp(); /* the children read what the lanes of this warp just wrote */
+            /* children of at most 32 items are finished here and now, without a trip through the queue */
+            unsigned done_now = leaves;
+#pragma unroll
+            for(int side = 0; side < 2; side++) {
+                const unsigned ca = side ? a + nl : a, cm = side ? nr : nl;
+                if(cm < 2 || cm > 32) continue;
+                float4 l = make_float4(0, 0, 0, 0), h = l;
+                if((unsigned)lane < cm) l = __ldcg(&out[ca + lane].lo), h = __ldcg(&out[ca + lane].hi);
+                subtree32(ca, cm, side ? me + (int)nl : me + 1, me, l, h, stage, stack, O, lane);
+                done_now += cm;
             }
-            if(leaves && lane == 0) {
+            const bool go_l = nl > 32, go_r = nr > 32;
+            if(go_l && go_r && lane == 0) { /* queue the right child, keep the left one */
+                const unsigned idx = atomicAdd(&st->q_tail, 1u);
+                jobs[idx] = SahJob{a + nl, b, me + (int)nl, me, src ^ 1u};
                 __threadfence();
-                atomicAdd(&st->leaves_done, leaves);
+                st_release(ready + idx, 1u);
             }
-            __syncwarp(); /* the next node reads what the other lanes just wrote */
+            if(done_now && lane == 0) leaves_add(st, done_now, total);
+            if(!go_l && !go_r) break;
+            const int side = go_l ? 0 : 1;
+#pragma unroll
+            for(int q = 0; q < 3; q++) cl[q] = dec(eb[side][q]), ch[q] = dec(eb[side][3 + q]);
+            have_bounds = true;
             if(go_l) par = me, b = a + nl, me = me + 1, src ^= 1u;
-            else if(go_r) par = me, a = a + nl, me = me + (int)nl, src ^= 1u;
-            else break;
+            else par = me, a = a + nl, me = me + (int)nl, src ^= 1u;
         }
     }
 }
@@ -690,31 +962,53 @@ int build_sah_split_device(gpurt_ctx* ctx, const float4* tri_lo, const float4* t
     SahState* state = (SahState*)take(sizeof(SahState));
     if((size_t)(p - (char*)tmp) > tmp_bytes) return set_error("SAH build: temporary buffer too small"), GPURT_E_STATE;
 
-    if(!ctx->pinned_word) GPURT_CUDA(cudaHostAlloc((void**)&ctx->pinned_word, 64, cudaHostAllocMapped));
+    if(!ctx->pinned_word) GPURT_CUDA(cudaHostAlloc((void**)&ctx->pinned_word, 1024, cudaHostAllocMapped));
     volatile unsigned* h_flag = ctx->pinned_word; /* next level's big-segment count, written by k_sah_level */
     unsigned* d_flag = nullptr;
     GPURT_CUDA(cudaHostGetDevicePointer((void**)&d_flag, ctx->pinned_word, 0));
 
-    const bool big_root = n > SAH_TILE;
+    unsigned small_max = SAH_SMALL_MAX; /* GPURT_SAH_SMALL_MAX: A/B knob, the tree does not depend on it */
+    if(const char* e = getenv("GPURT_SAH_SMALL_MAX")) small_max = std::max<unsigned>(SAH_TILE, (unsigned)atoi(e));
+    const bool big_root = n > small_max;
     GPURT_CUDA(cudaMemsetAsync(ready, 0, cap * 4, st));
-    k_sah_setup<<<1, 128, 0, st>>>(n, state, segs[0], jobs, ready, cb, bins, tiles_done);
+    k_sah_setup<<<1, 128, 0, st>>>(n, small_max, state, segs[0], jobs, ready, cb, bins, tiles_done);
     k_sah_init<<<(n + 255) / 256, 256, 0, st>>>(tri_lo, tri_hi, n, rec[0], seg_of[0], big_root ? 0 : -1, keys, cb);
-    unsigned n_big = big_root ? 1u : 0u, par = 0, levels = 0;
-    while(n_big) {
-        if(++levels > 512) return set_error("SAH build: more than 512 levels of big segments"), GPURT_E_STATE;
-        k_sah_bins<<<ntiles, 256, 0, st>>>(rec[par], seg_of[par], n, segs[par], cb, bins, tiles_done, split);
-        k_sah_count<<<ntiles, 256, 0, st>>>(rec[par], seg_of[par], n, split, tile_left);
-        k_sah_level<<<1, 1024, 0, st>>>(tile_left, 2 * ntiles, segs[par], segs[par ^ 1], split, state, cb, bins, tiles_done, jobs,
-                                        (int*)ready, par ^ 1u, left, right, parent, range_first, range_last, ni, d_flag);
-        k_sah_scatter<<<ntiles, 256, 0, st>>>(rec[par], seg_of[par], n, split, tile_left, rec[par ^ 1], seg_of[par ^ 1], cb, order);
-        GPURT_CUDA(cudaStreamSynchronize(st));
-        n_big = *h_flag;
-        if(n_big > max_big) return set_error("SAH build: segment bound exceeded"), GPURT_E_STATE;
-        par ^= 1;
+    /* Levels of big segments.  The host learns from k_sah_level whether another level follows; so that this read-back does
+     * not leave the device idle, level L + 1 is already queued when the host waits for level L's count (a level without
+     * big segments touches nothing: its kernels find seg_of == -1 everywhere).  Word 0 / 1 of the pinned block alternate. */
+    unsigned par = 0, levels = 0;
+    if(big_root) {
+        cudaEvent_t ev[2] = {ctx->ev_copy, ctx->ev_kernel}; /* free between host-buffer calls */
+        auto launch_level = [&](unsigned which) {
+            k_sah_bins<<<ntiles, 256, 0, st>>>(rec[par], seg_of[par], n, segs[par], cb, bins, tiles_done, split);
+            k_sah_count<<<ntiles, 256, 0, st>>>(rec[par], seg_of[par], n, split, tile_left);
+            k_sah_level<<<1, 1024, 0, st>>>(tile_left, 2 * ntiles, segs[par], segs[par ^ 1], split, state, cb, bins, tiles_done, jobs,
+                                            (int*)ready, par ^ 1u, left, right, parent, range_first, range_last, ni, d_flag + which,
+                                            small_max);
+            cudaEventRecord(ev[which], st);
+            k_sah_scatter<<<ntiles, 256, 0, st>>>(rec[par], seg_of[par], n, split, tile_left, rec[par ^ 1], seg_of[par ^ 1], cb, order);
+            par ^= 1;
+            levels++;
+        };
+        launch_level(0);
+        for(unsigned which = 0;; which ^= 1) {
+            if(levels > 512) return set_error("SAH build: more than 512 levels of big segments"), GPURT_E_STATE;
+            launch_level(which ^ 1);                       /* speculative */
+            GPURT_CUDA(cudaEventSynchronize(ev[which]));
+            const unsigned n_big = h_flag[which];
+            if(n_big > max_big) return set_error("SAH build: segment bound exceeded"), GPURT_E_STATE;
+            if(n_big == 0) break;                          /* the level just queued is the empty one */
+        }
     }
-    k_sah_small<<<grid_small, 128, 0, st>>>(rec[0], rec[1], jobs, ready, state, (unsigned)cap, order, left, right, parent, range_first,
-                                            range_last, ni);
+    k_sah_small<<<grid_small, 128, 0, st>>>(rec[0], rec[1], jobs, ready, state, (unsigned)cap,
+                                            SmallOut{order, left, right, parent, range_first, range_last, ni});
     GPURT_CUDA(cudaGetLastError());
+    GPURT_CUDA(cudaMemcpyAsync(ctx->pinned_word + 16, state, sizeof(SahState), cudaMemcpyDeviceToHost, st));
+    GPURT_CUDA(cudaStreamSynchronize(st));
+    const SahState* hs = (const SahState*)(ctx->pinned_word + 16);
+    if(hs->stalled || hs->leaves_done != hs->small_total)
+        return set_error("SAH build: the small-segment queue stalled (" + std::to_string(hs->leaves_done) + " of " +
+                         std::to_string(hs->small_total) + " leaves)"), GPURT_E_STATE;
     if(levels_out) *levels_out = levels;
     return GPURT_OK;
 }

@@ -18,7 +18,7 @@ LIB_PATH = os.environ.get("GPURT_LIB") or os.path.join(os.path.dirname(_HERE), "
 
 MEM_HOST, MEM_DEVICE = 0, 1
 NO_HIT = 0xFFFFFFFF
-BUILD_DEFAULT, BUILD_KEEP_BVH2, BUILD_SAH_COLLAPSE, BUILD_SAH_SPLIT = 0, 1, 2, 4
+BUILD_DEFAULT, BUILD_KEEP_BVH2, BUILD_SAH_COLLAPSE, BUILD_SAH_SPLIT, BUILD_LBVH = 0, 1, 2, 4, 8
 
 RAY_DT = np.dtype([("o", "<f4", 3), ("tmin", "<f4"), ("d", "<f4", 3), ("tmax", "<f4")])
 HIT_DT = np.dtype([("t", "<f4"), ("u", "<f4"), ("v", "<f4"), ("prim", "<u4")])
@@ -245,6 +245,17 @@ class Scene:
         v[:, :3] = tris9.reshape(-1, 3)
         return self.add_object(v, np.arange(v.shape[0], dtype=np.uint32), None, material)
 
+    def set_ordered(self, ordered=True):
+        """objects in insertion order instead of the reference container's iteration order (gpurt_scene_set_ordered)"""
+        _check(lib.gpurt_scene_set_ordered(self.h, 1 if ordered else 0))
+        return self
+
+    def set_material(self, obj, material):
+        _check(lib.gpurt_scene_set_material(self.h, int(obj), C.byref(material)))
+
+    def clear_textures(self):
+        _check(lib.gpurt_scene_clear_textures(self.h))
+
     def add_texture(self, rgba8):
         rgba8 = np.ascontiguousarray(rgba8, np.uint8)
         h, w = rgba8.shape[:2]
@@ -324,8 +335,9 @@ class Accel:
         self.ctx = scene.ctx
         self.h = C.c_void_p()
         # GPURT_BUILD_FLAGS (binding only): OR extra build flags into every Accel of a tool run, for A/B measurements
-        # of GPURT_BUILD_SAH_COLLAPSE (2) / GPURT_BUILD_SAH_SPLIT (4) without editing the tools
+        # of GPURT_BUILD_SAH_COLLAPSE (2) / GPURT_BUILD_LBVH (8) without editing the tools
         flags |= int(os.environ.get("GPURT_BUILD_FLAGS", "0"))
+        self.flags = flags
         _check(lib.gpurt_accel_build(scene.h, flags, C.byref(self.h)))
 
     def update(self):
@@ -399,6 +411,10 @@ class Accel:
         _check(lib.gpurt_trace_closest_stats(self.h, C.c_void_p(rays_dev.data_ptr()), C.c_uint64(rays_dev.shape[0]),
                                              C.c_void_p(hits_dev.data_ptr()), C.byref(st)))
         return st
+
+    def sync_scene(self):
+        """materials / textures changed, geometry did not: refresh the device copy without rebuilding the BVH"""
+        _check(lib.gpurt_accel_sync_scene(self.h))
 
     def closest_points_stats(self, queries_dev):
         st = TraceStats()

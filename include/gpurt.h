@@ -204,22 +204,26 @@ int gpurt_camera_make(int mode, float width, float height, const float pos[3],
                       const float center[3], float vfov_deg, GpurtCamera* out);
 
 /* ---- acceleration structure: replaces VK::Accel (src/vk/vulkan.h:256-284) ---------------------- */
-/* = every BLAS build (src/vk/vulkan.cpp:881-936) + the TLAS build (:777-856) of
- * GPURT::build_accel (src/gpurt.cpp:220-241): LBVH over the world-space triangles of all
- * instances, collapsed to 80-byte 8-wide compressed nodes. */
+/* = every BLAS build (src/vk/vulkan.cpp:881-936) + the TLAS build (:777-856) of GPURT::build_accel (src/gpurt.cpp:220-241)
+ * in one call: a binary BVH over the world-space triangles of all instances, collapsed to 80-byte 8-wide compressed nodes.
+ *
+ * GPURT_BUILD_DEFAULT — what the reference asks its driver for (PREFER_FAST_TRACE, vulkan.cpp:780, :884): primitive order
+ * and binary topology from a top-down 16-bin surface-area-heuristic split of the triangle boxes, built on the device
+ * (csrc/sah_build.cu; the tree is defined in gpu-rt_b200/host/sah_split.h and restated in oracle/oracle.cpp).  Measured on
+ * media/cbox against the Morton build: 36 % fewer node visits per random ray, random rays +30 %, shadow rays +36 %,
+ * camera rays +18 %, closest points +14 %; build 1.8x (16.7 k triangles: 1.06 vs 0.60 ms; 262 k: 1.84 vs 0.81 ms).
+ * gpurt_accel_get_morton_keys returns positions 0..n-1 for this build. */
 #define GPURT_BUILD_DEFAULT 0u
-#define GPURT_BUILD_KEEP_BVH2 1u /* accepted; the binary LBVH is always kept (gpurt_accel_update rebuilds into it) */
+#define GPURT_BUILD_KEEP_BVH2 1u /* accepted; the binary tree is always kept (gpurt_accel_update rebuilds into it) */
 /* SAH-optimal wide collapse (dynamic programming over the binary tree, Ylitie-Karras-Laine 2017) instead of the
  * greedy largest-area rule.  Same query results.  Measured on the Sponza stand-in: 31 % fewer wide nodes, primary
  * rays +5 %, bounce rays -3 %, closest-point queries -15 %, build +15..40 % — an option for camera-ray-heavy use. */
 #define GPURT_BUILD_SAH_COLLAPSE 2u
-/* EXPERIMENTAL (built and checked on the CPU replay at the end of round 1, not yet run on a GPU): primitive order and
- * binary topology from a top-down binned-SAH split computed on the host (gpu-rt_b200/host/sah_split.h) instead of the
- * Morton sort; refit, wide collapse and traversal unchanged, query results unchanged.  For static scenes with real
- * meshes: about 30 % fewer node visits per ray on media/cbox in the CPU probe (tools/sah_probe.py), nothing on
- * regular procedural geometry; the host pass costs ~8 ms per 16 k triangles, ~105 ms per 262 k (8 threads).  Composes with
- * GPURT_BUILD_SAH_COLLAPSE.  gpurt_accel_get_morton_keys returns positions 0..n-1 in this mode. */
-#define GPURT_BUILD_SAH_SPLIT 4u
+#define GPURT_BUILD_SAH_SPLIT 4u /* accepted: the SAH split is the default build (round 1 had it behind this flag) */
+/* Morton-order LBVH instead of the SAH split (63-bit keys of the AABB centroids, radix sort, Karras 2012): the fastest
+ * build (PREFER_FAST_BUILD), for scenes rebuilt every frame and for regular procedural geometry, where the Morton order
+ * is as good (Sponza stand-in: rays +6 % with this flag, closest points -20 %).  Same query results. */
+#define GPURT_BUILD_LBVH 8u
 int gpurt_accel_build(gpurt_scene* scene, uint32_t flags, gpurt_accel** out);
 /* Rebuild after scene edits (GPURT::build_accel with rebuild_tlas / rebuild_blas, src/gpurt.cpp:220-241).
  * Pose-only edits re-upload the 208-byte Scene_Desc records and rebuild on the device in the buffers

@@ -439,6 +439,142 @@ orc_bvh* orc_bvh_build(const float* tris9, uint32_t n) {
     return B;
 }
 
+/* N6' — the order and topology of the default ("fast trace") build: a top-down 16-bin surface-area-heuristic split of
+ * the triangle boxes, restated here from its written definition (the comment at the top of gpu-rt_b200/host/sah_split.h)
+ * as a plain sequential recursion:
+ *   segment S of items (initially all triangles in id order); centroid c = (lo + hi) * 0.5 of the triangle's AABB;
+ *   cb = bounds of the centroids (starting from +-3.0e38); for each axis with ext = cb.hi - cb.lo > 0:
+ *   bin = min(15, (int)((c - cb.lo) * (16 / ext))), 0 if that product is negative or NaN; for k = 1..15 with both sides
+ *   non-empty: cost = area(union of boxes in bins < k) * count + area(union in bins >= k) * count, area(b) = 2 (ex ey + ey ez + ez ex);
+ *   lowest cost below 3.0e38 wins, ties to the lower axis then the lower k; stable partition; no candidate: split in the
+ *   middle.  Inner nodes are numbered in preorder, leaves are single triangles at their final position. */
+orc_bvh* orc_bvh_build_sah(const float* tris9, uint32_t n) {
+    orc_bvh* B = orc_bvh_build(tris9, n); /* boxes, scene box, inflation; order / topology are replaced below */
+    if(n < 2) {
+        for(uint32_t i = 0; i < n; i++) B->keys[i] = i;
+        return B;
+    }
+    const float BIG = 3.0e38f;
+    std::vector<uint32_t> items(n);
+    for(uint32_t g = 0; g < n; g++) items[g] = g;
+    auto cen = [&](uint32_t g, int ax) {
+        const Box& b = B->tri_box[g];
+        return ax == 0 ? (b.lo.x + b.hi.x) * 0.5f : ax == 1 ? (b.lo.y + b.hi.y) * 0.5f : (b.lo.z + b.hi.z) * 0.5f;
+    };
+    struct B6 {
+        float lo[3], hi[3];
+    };
+    auto empty = [&]() { return B6{{BIG, BIG, BIG}, {-BIG, -BIG, -BIG}}; };
+    auto add = [&](B6& acc, const Box& b) {
+        const float l[3] = {b.lo.x, b.lo.y, b.lo.z}, h[3] = {b.hi.x, b.hi.y, b.hi.z};
+        for(int q = 0; q < 3; q++) {
+            if(l[q] < acc.lo[q]) acc.lo[q] = l[q];
+            if(h[q] > acc.hi[q]) acc.hi[q] = h[q];
+        }
+    };
+    auto merge = [&](B6& acc, const B6& b) {
+        for(int q = 0; q < 3; q++) {
+            if(b.lo[q] < acc.lo[q]) acc.lo[q] = b.lo[q];
+            if(b.hi[q] > acc.hi[q]) acc.hi[q] = b.hi[q];
+        }
+    };
+    auto area = [](const B6& b) {
+        float ex = b.hi[0] - b.lo[0], ey = b.hi[1] - b.lo[1], ez = b.hi[2] - b.lo[2];
+        return 2.0f * (ex * ey + ey * ez + ez * ex);
+    };
+    auto bin_of = [](float c, float lo, float scale) {
+        float f = (c - lo) * scale;
+        if(!(f >= 0.0f)) return 0;
+        return f < 16.0f ? (int)f : 15;
+    };
+    std::vector<int32_t> parent_of_internal(n - 1, -1), parent_of_leaf(n, -1);
+    struct Frame {
+        uint32_t a, b;
+        int32_t me, parent;
+        int side;
+    };
+    std::vector<Frame> todo{{0, n, 0, -1, 0}};
+    while(!todo.empty()) {
+        Frame f = todo.back();
+        todo.pop_back();
+        int32_t ref;
+        if(f.b - f.a == 1) {
+            ref = ~(int32_t)f.a;
+            B->order[f.a] = items[f.a];
+            parent_of_leaf[f.a] = f.parent;
+        } else {
+            ref = f.me;
+            parent_of_internal[f.me] = f.parent;
+            float clo[3] = {BIG, BIG, BIG}, chi[3] = {-BIG, -BIG, -BIG};
+            for(uint32_t i = f.a; i < f.b; i++)
+                for(int ax = 0; ax < 3; ax++) {
+                    float c = cen(items[i], ax);
+                    if(c < clo[ax]) clo[ax] = c;
+                    if(c > chi[ax]) chi[ax] = c;
+                }
+            int best_ax = -1, best_k = 0;
+            float best = BIG;
+            float scale[3] = {0, 0, 0};
+            for(int ax = 0; ax < 3; ax++) {
+                float ext = chi[ax] - clo[ax];
+                if(!(ext > 0.0f)) continue;
+                scale[ax] = 16.0f / ext;
+                B6 bb[16];
+                uint32_t cnt[16] = {0};
+                for(int k = 0; k < 16; k++) bb[k] = empty();
+                for(uint32_t i = f.a; i < f.b; i++) {
+                    int k = bin_of(cen(items[i], ax), clo[ax], scale[ax]);
+                    cnt[k]++;
+                    add(bb[k], B->tri_box[items[i]]);
+                }
+                for(int k = 1; k < 16; k++) {
+                    B6 L = empty(), R = empty();
+                    uint32_t cl = 0, cr = 0;
+                    for(int j = 0; j < k; j++)
+                        if(cnt[j]) merge(L, bb[j]), cl += cnt[j];
+                    for(int j = k; j < 16; j++)
+                        if(cnt[j]) merge(R, bb[j]), cr += cnt[j];
+                    if(!cl || !cr) continue;
+                    float cost = area(L) * (float)cl + area(R) * (float)cr;
+                    if(cost < best) best = cost, best_ax = ax, best_k = k;
+                }
+            }
+            uint32_t mid;
+            if(best_ax < 0) mid = f.a + (f.b - f.a) / 2;
+            else {
+                auto it = std::stable_partition(items.begin() + f.a, items.begin() + f.b, [&](uint32_t g) {
+                    return bin_of(cen(g, best_ax), clo[best_ax], scale[best_ax]) < best_k;
+                });
+                mid = (uint32_t)(it - items.begin());
+            }
+            todo.push_back({mid, f.b, f.me + (int32_t)(mid - f.a), f.me, 1});
+            todo.push_back({f.a, mid, f.me + 1, f.me, 0});
+        }
+        if(f.parent >= 0) (f.side ? B->right : B->left)[f.parent] = ref;
+    }
+    for(uint32_t i = 0; i < n; i++) B->keys[i] = i; /* the key of a primitive in this build is its position */
+    /* exact boxes: preorder numbering puts children after their parent */
+    auto child_box = [&](int32_t c) -> Box { return c < 0 ? B->tri_box[B->order[~c]] : B->node_box[c]; };
+    for(int64_t i = (int64_t)n - 2; i >= 0; i--) {
+        Box b = child_box(B->left[i]);
+        b.grow(child_box(B->right[i]));
+        B->node_box[i] = b;
+    }
+    float e = B->inflate;
+    auto inflated = [&](Box b) {
+        b.lo = {b.lo.x - e, b.lo.y - e, b.lo.z - e};
+        b.hi = {b.hi.x + e, b.hi.y + e, b.hi.z + e};
+        return b;
+    };
+    for(uint32_t i = 0; i + 1 < n; i++) {
+        B->tnodes[i].c[0] = B->left[i];
+        B->tnodes[i].c[1] = B->right[i];
+        B->tnodes[i].cb[0] = inflated(child_box(B->left[i]));
+        B->tnodes[i].cb[1] = inflated(child_box(B->right[i]));
+    }
+    return B;
+}
+
 void orc_bvh_free(orc_bvh* b) { delete b; }
 uint32_t orc_bvh_n_tris(const orc_bvh* b) { return b->n; }
 float orc_bvh_inflation(const orc_bvh* b) { return b->inflate; }

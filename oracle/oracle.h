@@ -62,6 +62,9 @@ void orc_closest_point_brute(const float* tris9, uint32_t n_tris, const float* q
 /* N6: canonical primitive order: 63-bit Morton of AABB centroid, stable sort (ties by gid). */
 typedef struct orc_bvh orc_bvh;
 orc_bvh* orc_bvh_build(const float* tris9, uint32_t n_tris);
+/* N6': the default ("fast trace") build's order and topology: top-down 16-bin SAH split (definition restated in oracle.cpp);
+ * morton_keys then returns positions 0..n-1.  The same query functions work on either tree. */
+orc_bvh* orc_bvh_build_sah(const float* tris9, uint32_t n_tris);
 void orc_bvh_free(orc_bvh*);
 uint32_t orc_bvh_n_tris(const orc_bvh*);
 void orc_bvh_scene_box(const orc_bvh*, float out6[6]);

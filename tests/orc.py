@@ -37,6 +37,7 @@ def _load():
         "orc_any_hit_brute": (None, [_f32p, C.c_uint32, _f32p, C.c_uint64, _u8p, C.c_int]),
         "orc_closest_point_brute": (None, [_f32p, C.c_uint32, _f32p, C.c_uint64, _u32p, C.c_int]),
         "orc_bvh_build": (C.c_void_p, [_f32p, C.c_uint32]),
+        "orc_bvh_build_sah": (C.c_void_p, [_f32p, C.c_uint32]),
         "orc_bvh_free": (None, [C.c_void_p]),
         "orc_bvh_n_tris": (C.c_uint32, [C.c_void_p]),
         "orc_bvh_scene_box": (None, [C.c_void_p, _f32p]),
@@ -97,10 +98,12 @@ def closest_point_brute(tris9, queries, threads=0):
 
 
 class Bvh:
-    def __init__(self, tris9):
+    """sah=False: the Morton LBVH (contract N6, GPURT_BUILD_LBVH); sah=True: the binned-SAH split of the default build (N6')"""
+
+    def __init__(self, tris9, sah=False):
         self.tris9 = np.ascontiguousarray(tris9, np.float32).reshape(-1, 9)
         self.n = self.tris9.shape[0]
-        self.h = lib.orc_bvh_build(self.tris9, self.n)
+        self.h = (lib.orc_bvh_build_sah if sah else lib.orc_bvh_build)(self.tris9, self.n)
 
     def __del__(self):
         if getattr(self, "h", None):

@@ -341,8 +341,8 @@ def test_cuda_frames_equal_the_reference_shader_digests(gpurt, orc, ctx):
     checked, bad = 0, []
     for name, scene0, texs, w, h, frames, cam, kw in mg.frame_cases(gpurt):
         restir = kw.get("integrator", 0) in (3, 4)
-        # the golden scenes were built without a context; rebuild the same scene on the device
-        scene = gpurt.Scene(ctx)
+        # the golden scenes were built without a context; rebuild the same scene on the device, object i = object i
+        scene = gpurt.Scene(ctx).set_ordered()
         for t in texs:
             scene.add_texture(t)
         for i, d in enumerate(scene0.descs()):
@@ -351,21 +351,6 @@ def test_cuda_frames_equal_the_reference_shader_digests(gpurt, orc, ctx):
             m.albedo[:], m.emissive[:], m.metal_rough[:] = d.albedo[:3], d.emissive[:3], d.metal_rough[:2]
             m.albedo_tex, m.emissive_tex, m.metal_rough_tex, m.normal_tex = d.albedo_tex, d.emissive_tex, d.metal_rough_tex, d.normal_tex
             scene.add_object(v, idx, np.array(list(d.model), np.float32), m)
-        # add_object stores objects in the reference's container order (descending id): adding them in packed order
-        # reverses them, so compare per-object content order before trusting the digests
-        if [bytes(a) for a in scene.descs()] != [bytes(a) for a in scene0.descs()]:
-            scene.close()
-            scene = gpurt.Scene(ctx)
-            for t in texs:
-                scene.add_texture(t)
-            descs = scene0.descs()
-            for i in reversed(range(len(descs))):
-                d = descs[i]
-                v, idx = scene0.object(i)
-                m = gpurt.Material()
-                m.albedo[:], m.emissive[:], m.metal_rough[:] = d.albedo[:3], d.emissive[:3], d.metal_rough[:2]
-                m.albedo_tex, m.emissive_tex, m.metal_rough_tex, m.normal_tex = d.albedo_tex, d.emissive_tex, d.metal_rough_tex, d.normal_tex
-                scene.add_object(v, idx, np.array(list(d.model), np.float32), m)
         assert [bytes(a)[:192] for a in scene.descs()] == [bytes(a)[:192] for a in scene0.descs()]
         accel = gpurt.Accel(scene)
         pipe = gpurt.RTPipe(scene, accel)

@@ -163,7 +163,7 @@ def main():
         q = make_queries(chk0, chk0 + n_chk, dev).cpu().numpy()
         got = results[0][:n_chk].cpu().numpy().view(np.uint32)
         t1 = time.time()
-        ob = orc.Bvh(tris_h)
+        ob = orc.Bvh(tris_h, sah=not (accel.flags & gpurt.BUILD_LBVH))
         ref = ob.closest_point(q).view(np.uint32).reshape(-1, 8)
         same = bool((got[:, [0, 1, 2, 3, 4, 6, 7]] == ref[:, [0, 1, 2, 3, 4, 6, 7]]).all())
         order_same = bool((accel.prim_order() == ob.prim_order()).all())

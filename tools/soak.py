@@ -27,7 +27,7 @@ for name in ("sponza_standin", "cbox", "soup1m"):
         scene = load_scene(gpurt, ctx, name)
         tris = world_tris(orc, scene)
     accel = gpurt.Accel(scene)
-    ob = orc.Bvh(tris)
+    ob = orc.Bvh(tris, sah=True)
     assert (accel.prim_order() == ob.prim_order()).all()
     box = ob.scene_box()
     for seed in (1, 2):

@@ -267,6 +267,29 @@ int gpurt_accel_update(gpurt_accel* A) {
     if(rc == GPURT_OK && A->depth > 60) rc = (set_error("wide BVH deeper than the traversal stack"), GPURT_E_STATE);
     return rc;
 }
+/* pose-only edit, keep order and topology */
+int gpurt_accel_refit(gpurt_accel* A) {
+    if(!A) return set_error("NULL argument"), GPURT_E_INVALID;
+    GPURT_CUDA(cudaSetDevice(A->ctx->device));
+    if(!A->scene->pack()) return GPURT_E_INVALID;
+    if(A->scene->geom_version != A->dscene.geom_version || A->scene->packed.tri_off.back() != A->n || !A->parent)
+        return set_error("geometry changed since the last build: gpurt_accel_update() is needed"), GPURT_E_STATE;
+    if(A->n < 2) return gpurt_accel_update(A);
+    int rc = build_accel_device(A, true);
+    if(rc == GPURT_OK && A->depth > 60) rc = (set_error("wide BVH deeper than the traversal stack"), GPURT_E_STATE);
+    return rc;
+}
+int gpurt_accel_update_auto(gpurt_accel* A, float max_cost_growth) {
+    if(!A) return set_error("NULL argument"), GPURT_E_INVALID;
+    if(!A->scene->pack()) return GPURT_E_INVALID;
+    const bool pose_only = A->scene->geom_version == A->dscene.geom_version && A->scene->packed.tri_off.back() == A->n && A->parent && A->n >= 2;
+    if(!pose_only) return gpurt_accel_update(A);
+    int rc = gpurt_accel_refit(A);
+    if(rc) return rc;
+    if(!(max_cost_growth > 0.0f)) max_cost_growth = 1.25f;
+    if(A->tree_cost > max_cost_growth * A->tree_cost_at_build) return gpurt_accel_update(A); /* the old topology no longer fits */
+    return GPURT_OK;
+}
 int gpurt_accel_sync_scene(gpurt_accel* A) {
     if(!A) return set_error("NULL argument"), GPURT_E_INVALID;
     GPURT_CUDA(cudaSetDevice(A->ctx->device));
@@ -296,6 +319,7 @@ int gpurt_accel_info(const gpurt_accel* A, GpurtAccelInfo* o) {
     o->build_ms = A->build_ms;
     o->node_bytes = (uint64_t)A->n_nodes * sizeof(Node8);
     o->tri_bytes = (uint64_t)A->n * 48;
+    o->tree_cost = A->tree_cost, o->tree_cost_at_build = A->tree_cost_at_build, o->refits = A->refits;
     return GPURT_OK;
 }
 static int d2h(const gpurt_accel* A, void* dst, const void* src, size_t bytes) {

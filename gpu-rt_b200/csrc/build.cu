@@ -605,16 +605,43 @@ struct Arena {
 
 void free_accel_device(gpurt_accel* A) {
     void* ptrs[] = {A->tri_gid, A->tri_lo, A->tri_hi, A->keys, A->order, A->left, A->right,
-                    A->node_lo, A->node_hi, A->nodes, A->tri_wide};
+                    A->node_lo, A->node_hi, A->nodes, A->tri_wide, A->parent, A->range_first, A->range_last, A->tree_cost_dev};
     for(void* p : ptrs)
         if(p) cudaFree(p);
     A->tri_gid = A->tri_lo = A->tri_hi = A->node_lo = A->node_hi = A->tri_wide = nullptr;
     A->keys = nullptr, A->order = nullptr, A->nodes = nullptr;
-    A->left = A->right = nullptr;
+    A->left = A->right = A->parent = A->range_first = A->range_last = nullptr;
+    A->tree_cost_dev = nullptr;
     free_scene(A->dscene);
 }
 
-int build_accel_device(gpurt_accel* A) {
+/* sum over the inner nodes of 2 (ex ey + ey ez + ez ex): the surface-area-heuristic cost of the binary tree up to constant
+ * factors; gpurt_accel_update_auto compares it with the value at the last full build to decide whether a refit still serves */
+__global__ void __launch_bounds__(256) k_tree_cost(const float4* __restrict__ lo, const float4* __restrict__ hi, unsigned ni, float* out) {
+    __shared__ float s[8];
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    float a = 0.0f;
+    if(i < ni) {
+        float4 l = lo[i], h = hi[i];
+        float ex = h.x - l.x, ey = h.y - l.y, ez = h.z - l.z;
+        a = 2.0f * (ex * ey + ey * ez + ez * ex);
+        if(!(a == a) || a > 3.0e38f) a = 0.0f;
+    }
+#pragma unroll
+    for(int d = 16; d >= 1; d >>= 1) a += __shfl_xor_sync(0xffffffffu, a, d);
+    if((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = a;
+    __syncthreads();
+    if(threadIdx.x == 0) {
+        float t = 0.0f;
+        for(int w = 0; w < 8; w++) t += s[w];
+        atomicAdd(out, t);
+    }
+}
+
+/* refit_only: poses changed, geometry did not, and the caller accepts the existing primitive order and topology: triangles
+ * are flattened again, node boxes refitted, the wide tree collapsed and encoded again — the order / topology stage (the
+ * SAH split or the Morton sort, most of a build) is skipped.  Any valid tree gives the same query results. */
+int build_accel_device(gpurt_accel* A, bool refit_only) {
     gpurt_ctx* ctx = A->ctx;
     cudaStream_t st = ctx->stream;
     GPURT_CUDA(cudaSetDevice(ctx->device));
@@ -636,6 +663,10 @@ int build_accel_device(gpurt_accel* A) {
     TRY(dkeep(A->node_lo, ni));
     TRY(dkeep(A->node_hi, ni));
     TRY(dkeep(A->nodes, max_nodes));
+    TRY(dkeep(A->parent, (size_t)ni + n));
+    TRY(dkeep(A->range_first, ni));
+    TRY(dkeep(A->range_last, ni));
+    TRY(dkeep(A->tree_cost_dev, 1));
 
     /* temporaries: [box | range_first | range_last] live through the whole build; behind them phase 1
      * (sort + tree: keys_tmp, vals_tmp / arrival counters, parent) and phase 2 (collapse: item lists,
@@ -657,13 +688,13 @@ int build_accel_device(gpurt_accel* A) {
     Arena ar;
     ar.base = (char*)ctx->build_arena.p, ar.cap = ctx->build_arena.cap;
     float* d_box = ar.take<float>(8);
-    int* range_first = ar.take<int>(ni);
-    int* range_last = ar.take<int>(ni);
+    int* range_first = A->range_first;
+    int* range_last = A->range_last;
     unsigned char* dp_dec = ar.take<unsigned char>(sah ? (size_t)ni * 8 : 1);
     const size_t phase_mark = ar.used;
     uint64_t* keys_tmp = ar.take<uint64_t>(n);
     uint32_t* vals_tmp = ar.take<uint32_t>(n);
-    int* parent = ar.take<int>((size_t)ni + n);
+    int* parent = A->parent;
     float* dp_cost = ar.take<float>(sah ? (size_t)ni * 7 : 1);
     char* sah_buf = ar.take<char>(sah_tmp);
     if(!dp_cost || !sah_buf) return set_error("build arena layout"), GPURT_E_STATE;
@@ -699,7 +730,9 @@ int build_accel_device(gpurt_accel* A) {
     float ext[3] = {sb[3] - sb[0], sb[4] - sb[1], sb[5] - sb[2]}, inv[3];
     for(int k = 0; k < 3; k++) inv[k] = ext[k] > 0 ? 1.0f / ext[k] : 0.0f;
 
-    if(!sah_split) {
+    if(refit_only) {
+        /* order, keys and topology stay */
+    } else if(!sah_split) {
         /* keys + sort */
         k_morton<<<cdiv(n, 256), 256, 0, st>>>(A->tri_lo, A->tri_hi, n, sb[0], sb[1], sb[2], inv[0], inv[1],
                                               inv[2], A->keys, A->order);
@@ -740,7 +773,7 @@ int build_accel_device(gpurt_accel* A) {
     unsigned* arrive = (unsigned*)vals_tmp; /* the sort is done with it */
     if(ni) {
         GPURT_CUDA(cudaMemsetAsync(arrive, 0, (size_t)ni * 4, st));
-        if(!sah_split)
+        if(!sah_split && !refit_only)
             k_karras<<<cdiv(ni, 256), 256, 0, st>>>(A->keys, (int)n, A->left, A->right, parent, range_first, range_last);
         if(sah)
             k_refit<true><<<cdiv(n, 256), 256, 0, st>>>((int)n, A->left, A->right, parent, A->order, A->tri_lo, A->tri_hi,
@@ -749,6 +782,8 @@ int build_accel_device(gpurt_accel* A) {
             k_refit<false><<<cdiv(n, 256), 256, 0, st>>>((int)n, A->left, A->right, parent, A->order, A->tri_lo, A->tri_hi,
                                                         A->node_lo, A->node_hi, arrive, B, dp_cost, dp_dec);
     }
+    GPURT_CUDA(cudaMemsetAsync(A->tree_cost_dev, 0, 4, st));
+    if(ni) k_tree_cost<<<cdiv(ni, 256), 256, 0, st>>>(A->node_lo, A->node_hi, ni, A->tree_cost_dev);
     GPURT_CUDA(cudaGetLastError());
     if(sah) B.dp_dec = dp_dec; /* the collapse follows the SAH-optimal decisions */
 
@@ -808,7 +843,10 @@ int build_accel_device(gpurt_accel* A) {
         k_tri_reorder<<<cdiv(3ull * n, 256), 256, 0, st>>>(wide_order, n, A->tri_gid, A->tri_wide);
     }
     GPURT_CUDA(cudaEventRecord(e1, st));
+    GPURT_CUDA(cudaMemcpyAsync(&A->tree_cost, A->tree_cost_dev, 4, cudaMemcpyDeviceToHost, st));
     GPURT_CUDA(cudaStreamSynchronize(st));
+    if(refit_only) A->refits++;
+    else A->tree_cost_at_build = A->tree_cost, A->refits = 0;
     cudaEventElapsedTime(&A->build_ms, e0, e1);
     GPURT_CUDA(cudaGetLastError());
     return GPURT_OK;

@@ -75,8 +75,12 @@ struct gpurt_accel {
     /* canonical order */
     uint64_t* keys = nullptr;
     uint32_t* order = nullptr;
-    /* binary LBVH */
+    /* binary tree (kept for gpurt_accel_refit: parents and leaf ranges too) */
     int *left = nullptr, *right = nullptr;
+    int *parent = nullptr, *range_first = nullptr, *range_last = nullptr;
+    float* tree_cost_dev = nullptr; /* sum of the inner nodes' box areas (the SAH cost up to constants), one float */
+    float tree_cost = 0, tree_cost_at_build = 0;
+    uint32_t refits = 0; /* since the last full build */
     float4 *node_lo = nullptr, *node_hi = nullptr;
     /* wide BVH */
     gpurt::Node8* nodes = nullptr;
@@ -89,7 +93,7 @@ struct gpurt_accel {
 };
 
 namespace gpurt {
-int build_accel_device(gpurt_accel* A);
+int build_accel_device(gpurt_accel* A, bool refit_only = false);
 /* sah_build.cu: the binned-SAH tree of host/sah_split.h on the device */
 size_t sah_split_tmp_bytes(size_t n, int sm_count);
 int build_sah_split_device(gpurt_ctx* ctx, const float4* tri_lo, const float4* tri_hi, unsigned n, uint32_t* order, uint64_t* keys,

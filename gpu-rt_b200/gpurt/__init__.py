@@ -68,7 +68,8 @@ class AccelInfo(C.Structure):
     _fields_ = [("n_tris", C.c_uint32), ("n_objs", C.c_uint32), ("n_bvh2_nodes", C.c_uint32),
                 ("n_wide_nodes", C.c_uint32), ("wide_depth", C.c_uint32), ("scene_min", C.c_float * 3),
                 ("scene_max", C.c_float * 3), ("inflation", C.c_float), ("build_ms", C.c_float),
-                ("node_bytes", C.c_uint64), ("tri_bytes", C.c_uint64)]
+                ("node_bytes", C.c_uint64), ("tri_bytes", C.c_uint64), ("tree_cost", C.c_float), ("tree_cost_at_build", C.c_float),
+                ("refits", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class TraceStats(C.Structure):
@@ -91,7 +92,7 @@ SYMBOLS = [
     "gpurt_pipe_ray_counts", "gpurt_pipe_device_image", "gpurt_tonemap", "gpurt_pipe_last_uniforms",
     "gpurt_pipe_read_reservoirs", "gpurt_pipe_bounce_rays", "gpurt_pipe_set_shard",
     "gpurt_pipe_render_frame_mean", "gpurt_pipe_accumulate_mean", "gpurt_scene_set_transform", "gpurt_accel_update", "gpurt_scene_get_texture", "gpurt_shared_alloc", "gpurt_shared_free", "gpurt_shared_open", "gpurt_shared_close",
-    "gpurt_scene_set_material", "gpurt_scene_set_ordered", "gpurt_scene_clear_textures", "gpurt_accel_sync_scene",
+    "gpurt_scene_set_material", "gpurt_scene_set_ordered", "gpurt_scene_clear_textures", "gpurt_accel_sync_scene", "gpurt_accel_refit", "gpurt_accel_update_auto",
 ]
 
 
@@ -411,6 +412,13 @@ class Accel:
         _check(lib.gpurt_trace_closest_stats(self.h, C.c_void_p(rays_dev.data_ptr()), C.c_uint64(rays_dev.shape[0]),
                                              C.c_void_p(hits_dev.data_ptr()), C.byref(st)))
         return st
+
+    def refit(self):
+        """pose-only edit: keep order and topology, refit boxes and wide nodes (gpurt_accel_refit)"""
+        _check(lib.gpurt_accel_refit(self.h))
+
+    def update_auto(self, max_cost_growth=0.0):
+        _check(lib.gpurt_accel_update_auto(self.h, C.c_float(max_cost_growth)))
 
     def sync_scene(self):
         """materials / textures changed, geometry did not: refresh the device copy without rebuilding the BVH"""

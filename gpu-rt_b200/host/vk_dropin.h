@@ -28,8 +28,8 @@
  *                             vulkan.cpp:785-805) + gpurt_accel_build.  The reference's Drop<T>::drop() defers destruction
  *                             to an erase queue (vulkan.h:562-564); the same deferral here parks the dropped TLAS until
  *                             the next one is built, and a TLAS over the SAME BLAS objects adopts it: only the instance
- *                             matrices are rewritten and the BVH is updated in place (gpurt_scene_set_transform +
- *                             gpurt_accel_update) — the reference's rebuild_tlas-without-rebuild_blas case (gpurt.cpp:228-237).
+ *                             matrices are rewritten and the BVH is refitted in place (gpurt_scene_set_transform +
+ *                             gpurt_accel_update_auto) — the reference's rebuild_tlas-without-rebuild_blas case (gpurt.cpp:228-237).
  *   RTPipe::recreate(scene)   build_textures + build_desc (rt.cpp:16-24, :26-76, :430-455): materials and textures are
  *                             captured here and applied to the TLAS's scene in use_accel (gpurt_scene_set_material,
  *                             gpurt_accel_sync_scene); reset_frame()
@@ -155,7 +155,7 @@ struct Accel {
                     dropin_check(gpurt_scene_set_transform(top->scene, (uint32_t)i, reinterpret_cast<const float*>(&inst[i])));
                     top->inst[i] = inst[i];
                 }
-            dropin_check(gpurt_accel_update(top->accel));
+            dropin_check(gpurt_accel_update_auto(top->accel, 0.0f)); /* refit while the old topology still fits */
             top->generation = next_generation();
             return;
         }

@@ -408,6 +408,59 @@ def test_sah_split_build_flag(gpurt, orc, ctx):
     accel.close(), base.close(), scene.close()
 
 
+def test_refit_keeps_order_and_topology_and_answers_like_a_fresh_build(gpurt, orc, ctx):
+    """gpurt_accel_refit / gpurt_accel_update_auto (the reference's rebuild_tlas-only case, src/gpurt.cpp:228-237): after a
+    pose edit the primitive order and binary topology stay, boxes and wide nodes follow the new poses, and every query
+    answers like the oracle on the moved geometry; a far move makes update_auto rebuild; geometry edits are refused"""
+    scene = load_scene(gpurt, ctx, "cbox")
+    accel = gpurt.Accel(scene, gpurt.BUILD_KEEP_BVH2)
+    order0 = accel.prim_order().copy()
+    l0, r0, _ = accel.bvh2()
+    full_ms = accel.info().build_ms
+
+    def moved(obj, d):
+        m = np.array(list(scene.descs()[obj].model), np.float32)
+        m[12:15] += np.asarray(d, np.float32)
+        return m
+    scene.set_transform(3, moved(3, (0.2, 0.0, -0.1)))
+    scene.set_transform(0, moved(0, (-0.1, 0.15, 0.0)))
+    accel.refit()
+    info = accel.info()
+    assert info.refits == 1 and info.tree_cost > 0 and info.tree_cost_at_build > 0
+    assert (accel.prim_order() == order0).all()
+    l1, r1, b1 = accel.bvh2()
+    assert (l1 == l0).all() and (r1 == r0).all()
+    tris = world_tris(orc, scene)
+    ob = orc.Bvh(tris, sah=True)                     # a fresh tree over the moved geometry: different order, same answers
+    assert not (ob.prim_order() == order0).all()
+    _check_queries(gpurt, orc, accel, ob, tris, 1 << 17, 1 << 10)
+    pipe = gpurt.RTPipe(scene, accel)
+    cam, prm = gpurt.camera(0, 128, 72), gpurt.pipe_params(integrator=2, brdf=1, samples_per_frame=2, max_depth=3, seed=4)
+    pipe.render_frame(prm, cam, 128, 72)
+    fresh = gpurt.Accel(scene)
+    fpipe = gpurt.RTPipe(scene, fresh)
+    fpipe.render_frame(prm, cam, 128, 72)
+    assert same_bits(pipe.read_image(), fpipe.read_image())
+    print(f"cbox: full build {full_ms:.3f} ms, refit {info.build_ms:.3f} ms, cost x{info.tree_cost / info.tree_cost_at_build:.3f}")
+    # update_auto: a small move refits, a far one (the tree's cost grows) rebuilds
+    scene.set_transform(3, moved(3, (0.05, 0.0, 0.0)))
+    accel.update_auto()
+    assert accel.info().refits == 2 and (accel.prim_order() == order0).all()
+    scene.set_transform(0, moved(0, (40.0, 25.0, -30.0)))
+    accel.update_auto()
+    assert accel.info().refits == 0 and accel.info().tree_cost == accel.info().tree_cost_at_build
+    tris = world_tris(orc, scene)
+    _check_build(gpurt, orc, accel, tris)
+    # geometry edits need a full update
+    scene.add_triangles(_soup(10, 1, 0.1))
+    with pytest.raises(gpurt.GpurtError):
+        accel.refit()
+    accel.update_auto()
+    assert accel.info().n_tris == len(tris) + 10
+    for o in (fpipe, pipe, fresh, accel, scene):
+        o.close()
+
+
 def _soup(n, seed, ext):
     rng = np.random.default_rng(seed)
     c = rng.random((n, 1, 3), dtype=np.float32)

@@ -159,6 +159,7 @@ int gpurt_ctx_create(int device, gpurt_ctx** out) {
     if(e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking);
     if(e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming);
     if(e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_kernel, cudaEventDisableTiming);
+    if(e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_switch, cudaEventDisableTiming);
     if(e != cudaSuccess) { /* release whatever was created before the failure */
         set_error(std::string("gpurt_ctx_create: ") + cudaGetErrorString(e));
         gpurt_ctx_destroy(c);
@@ -173,7 +174,7 @@ int gpurt_ctx_destroy(gpurt_ctx* c) {
     if(c->stream) cudaStreamSynchronize(c->stream);
     c->d_in.release(), c->d_out.release(), c->scratch.release(), c->build_arena.release();
     if(c->pinned_word) cudaFreeHost(c->pinned_word);
-    for(cudaEvent_t ev : {c->ev0, c->ev1, c->ev_copy, c->ev_kernel})
+    for(cudaEvent_t ev : {c->ev0, c->ev1, c->ev_copy, c->ev_kernel, c->ev_switch})
         if(ev) cudaEventDestroy(ev);
     for(cudaStream_t st : {c->s_h2d, c->s_d2h, c->own_stream})
         if(st) cudaStreamDestroy(st);
@@ -182,7 +183,14 @@ int gpurt_ctx_destroy(gpurt_ctx* c) {
 }
 int gpurt_ctx_set_stream(gpurt_ctx* c, void* stream) {
     if(!c) return set_error("NULL context"), GPURT_E_INVALID;
-    c->stream = stream == GPURT_STREAM_OWN ? c->own_stream : (cudaStream_t)stream;
+    cudaStream_t next = stream == GPURT_STREAM_OWN ? c->own_stream : (cudaStream_t)stream;
+    if(next != c->stream) {
+        /* work queued on the old stream may still use the context's arenas / staging buffers: the new stream starts after it */
+        GPURT_CUDA(cudaSetDevice(c->device));
+        GPURT_CUDA(cudaEventRecord(c->ev_switch, c->stream));
+        GPURT_CUDA(cudaStreamWaitEvent(next, c->ev_switch, 0));
+        c->stream = next;
+    }
     return GPURT_OK;
 }
 int gpurt_ctx_synchronize(gpurt_ctx* c) {

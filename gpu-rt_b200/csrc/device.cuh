@@ -42,6 +42,7 @@ struct gpurt_ctx {
     /* host-buffer calls: copy streams and hand-over events of the H2D -> kernel -> D2H pipeline */
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
     cudaEvent_t ev_copy = nullptr, ev_kernel = nullptr;
+    cudaEvent_t ev_switch = nullptr; /* orders a newly selected stream after the old one (gpurt_ctx_set_stream) */
     /* staging for GPURT_MEM_HOST calls */
     gpurt::DevBuf d_in, d_out;
     gpurt::DevBuf scratch;

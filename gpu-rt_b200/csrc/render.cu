@@ -293,7 +293,13 @@ static int pipe_free(gpurt_pipe* p) {
 }
 
 /* RTPipe::resize_temporal_stuff (rt.cpp:178-220) + rt_target (gpurt.cpp:189-193) */
+static int pipe_resize_impl(gpurt_pipe* p, uint32_t w, uint32_t h, uint32_t max_depth);
 static int pipe_resize(gpurt_pipe* p, uint32_t w, uint32_t h, uint32_t max_depth) {
+    int rc = pipe_resize_impl(p, w, h, max_depth);
+    if(rc) p->w = p->h = 0, p->max_counts = 0; /* some buffers have the new size, some are gone: the next call starts over */
+    return rc;
+}
+static int pipe_resize_impl(gpurt_pipe* p, uint32_t w, uint32_t h, uint32_t max_depth) {
     uint32_t need_counts = 2 * (max_depth + 2);
     if(p->w == w && p->h == h && p->max_counts >= need_counts) return GPURT_OK;
     bool dims = !(p->w == w && p->h == h);

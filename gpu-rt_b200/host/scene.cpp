@@ -171,14 +171,20 @@ struct Gltf {
         if(b >= buffers.size()) return false;
         a.ctype = acc["componentType"].integer(0);
         a.ncomp = type_comps(acc["type"].string());
-        a.count = (size_t)acc["count"].number(0);
         int cs = comp_size(a.ctype);
         if(cs < 0 || a.ncomp < 0) return false;
-        size_t bs = (size_t)bv["byteStride"].number(0);
+        /* untrusted numbers: finite, non-negative and no larger than the buffer before anything is multiplied */
+        const double size = (double)buffers[b].size();
+        auto sane = [&](double v) { return v == v && v >= 0.0 && v <= size; };
+        const double d_count = acc["count"].number(0), d_stride = bv["byteStride"].number(0);
+        const double d_off0 = bv["byteOffset"].number(0), d_off1 = acc["byteOffset"].number(0);
+        if(!sane(d_count) || !sane(d_stride) || !sane(d_off0) || !sane(d_off1) || !sane(d_off0 + d_off1)) return false;
+        a.count = (size_t)d_count;
+        size_t bs = (size_t)d_stride;
         a.stride = bs ? bs : (size_t)cs * a.ncomp;
-        size_t off = (size_t)bv["byteOffset"].number(0) + (size_t)acc["byteOffset"].number(0);
-        if(a.count && off + (a.count - 1) * a.stride + (size_t)cs * a.ncomp > buffers[b].size())
-            return false;
+        size_t off = (size_t)d_off0 + (size_t)d_off1;
+        const size_t elem = (size_t)cs * a.ncomp, avail = buffers[b].size() - off; /* off <= size */
+        if(a.count && (elem > avail || (a.count - 1) > (avail - elem) / a.stride)) return false;
         a.ptr = buffers[b].data() + off;
         return true;
     }
@@ -440,7 +446,18 @@ bool Scene::load(const std::string& file, std::string& err) {
     /* scene.cpp:347-371 */
     const Json& nodes = g.root["nodes"];
     bool ok = true;
+    int node_depth = 0; /* a cyclic or absurdly deep node graph must not overflow the stack */
     std::function<void(int, Mat4)> load_node = [&](int n, Mat4 T) {
+        struct Depth {
+            int& d;
+            explicit Depth(int& d) : d(d) { d++; }
+            ~Depth() { d--; }
+        } guard(node_depth);
+        if(node_depth > 256) {
+            ok = false;
+            err = "node graph deeper than 256 levels (cycle?)";
+            return;
+        }
         const Json& node = nodes[(size_t)n];
         Mat4 M;
         const Json& m = node["matrix"];
@@ -477,8 +494,11 @@ bool Scene::load(const std::string& file, std::string& err) {
             const Json& bv = g.root["bufferViews"][(size_t)im["bufferView"].integer(-1)];
             size_t b = (size_t)bv["buffer"].integer(0);
             if(b < g.buffers.size()) {
-                size_t off = (size_t)bv["byteOffset"].number(0), len = (size_t)bv["byteLength"].number(0);
-                if(off + len <= g.buffers[b].size())
+                const double d_off = bv["byteOffset"].number(0), d_len = bv["byteLength"].number(0), size = (double)g.buffers[b].size();
+                size_t off = 0, len = 0;
+                if(d_off == d_off && d_len == d_len && d_off >= 0 && d_len >= 0 && d_off <= size && d_len <= size)
+                    off = (size_t)d_off, len = (size_t)d_len;
+                if(len && off <= g.buffers[b].size() - len)
                     bytes.assign(g.buffers[b].begin() + off, g.buffers[b].begin() + off + len);
             }
         }

@@ -102,6 +102,54 @@ def test_errors_are_codes_not_exits(gpurt, tmp_path):
         assert e.value.code == -2 and "no CPU fallback" in str(e.value)
 
 
+def test_hostile_gltf_numbers_are_rejected_not_followed(gpurt, tmp_path):
+    """untrusted files: a cyclic node graph, accessor counts / offsets that overflow when multiplied, negative and
+    non-finite numbers — the loader answers with an error code (or loads nothing), it does not read out of bounds or recurse
+    until the stack ends; a material that names a missing texture falls back to its constant factor"""
+    import base64
+    import json
+    buf = np.zeros(36, np.float32).tobytes() + np.arange(3, dtype=np.uint32).tobytes()
+    uri = "data:application/octet-stream;base64," + base64.b64encode(buf).decode()
+
+    def doc(**over):
+        d = {"asset": {"version": "2.0"}, "buffers": [{"byteLength": len(buf), "uri": uri}],
+             "bufferViews": [{"buffer": 0, "byteOffset": 0, "byteLength": 144}, {"buffer": 0, "byteOffset": 144, "byteLength": 12}],
+             "accessors": [{"bufferView": 0, "componentType": 5126, "count": 3, "type": "VEC3"},
+                           {"bufferView": 1, "componentType": 5125, "count": 3, "type": "SCALAR"}],
+             "meshes": [{"primitives": [{"attributes": {"POSITION": 0}, "indices": 1}]}],
+             "nodes": [{"mesh": 0}], "scenes": [{"nodes": [0]}]}
+        d.update(over)
+        return d
+
+    def load(d):
+        p = tmp_path / "x.gltf"
+        p.write_text(json.dumps(d))
+        return gpurt.Scene(None).load(str(p))
+    assert load(doc()).counts()["tris"] == 1
+    with pytest.raises(gpurt.GpurtError):                                     # node 0 -> node 1 -> node 0 -> ...
+        load(doc(nodes=[{"mesh": 0, "children": [1]}, {"children": [0]}]))
+    for acc in ({"count": 1e30}, {"count": 2 ** 61}, {"byteOffset": -16}, {"byteOffset": 1e300}, {"count": -3}):
+        d = doc()
+        d["accessors"][0].update(acc)
+        try:
+            assert load(d).counts()["tris"] <= 1
+        except gpurt.GpurtError:
+            pass
+    d = doc()
+    d["bufferViews"][0]["byteStride"] = 2 ** 62
+    try:
+        load(d)
+    except gpurt.GpurtError:
+        pass
+    s = gpurt.Scene(None)
+    m = gpurt.Material()
+    m.albedo[:] = (1, 1, 1)
+    m.albedo_tex, m.emissive_tex, m.metal_rough_tex, m.normal_tex = 3, -1, 0, -1       # no textures in this scene
+    s.add_object(np.zeros((3, 12), np.float32), np.arange(3, dtype=np.uint32), None, m)
+    d0 = s.descs()[0]
+    assert (d0.albedo_tex, d0.metal_rough_tex) == (-1, -1) and "texture" in gpurt.last_error()
+
+
 def test_library_exports_every_declared_symbol(gpurt):
     header = open(os.path.join(ROOT, "include", "gpurt.h")).read()
     declared = set(re.findall(r"\b(gpurt_[a-z0-9_]+)\s*\(", header))

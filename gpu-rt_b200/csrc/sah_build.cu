@@ -891,23 +891,19 @@ __global__ void __launch_bounds__(128) k_sah_small(SahRec* rec0, SahRec* rec1, S
             const unsigned leaves = (nl == 1 ? 1u : 0u) + (nr == 1 ? 1u : 0u);
             __threadfence();
             __syncwarp(); /* the children read what the lanes of this warp just wrote */
-            /* children of at most 32 items are finished here and now, without a trip through the queue */
-            unsigned done_now = leaves;
-#pragma unroll
-            for(int side = 0; side < 2; side++) {
-                const unsigned ca = side ? a + nl : a, cm = side ? nr : nl;
-                if(cm < 2 || cm > 32) continue;
-                float4 l = make_float4(0, 0, 0, 0), h = l;
-                if((unsigned)lane < cm) l = __ldcg(&out[ca + lane].lo), h = __ldcg(&out[ca + lane].hi);
-                subtree32(ca, cm, side ? me + (int)nl : me + 1, me, l, h, stage, stack, O, lane);
-                done_now += cm;
-            }
-            const bool go_l = nl > 32, go_r = nr > 32;
-            if(go_l && go_r && lane == 0) { /* queue the right child, keep the left one */
-                const unsigned idx = atomicAdd(&st->q_tail, 1u);
-                jobs[idx] = SahJob{a + nl, b, me + (int)nl, me, src ^ 1u};
-                __threadfence();
-                st_release(ready + idx, 1u);
+            /* two children to build: the smaller one goes to the queue (thousands of warps are waiting for tickets; finishing
+             * a <= 32-item subtree here would put ~40 us of single-warp work on this chain), the larger one stays */
+            const unsigned done_now = leaves;
+            bool go_l = nl >= 2, go_r = nr >= 2;
+            if(go_l && go_r) {
+                const bool keep_left = nl >= nr;
+                if(lane == 0) {
+                    const unsigned idx = atomicAdd(&st->q_tail, 1u);
+                    jobs[idx] = keep_left ? SahJob{a + nl, b, me + (int)nl, me, src ^ 1u} : SahJob{a, a + nl, me + 1, me, src ^ 1u};
+                    __threadfence();
+                    st_release(ready + idx, 1u);
+                }
+                go_l = keep_left, go_r = !keep_left;
             }
             if(done_now && lane == 0) leaves_add(st, done_now, total);
             if(!go_l && !go_r) break;

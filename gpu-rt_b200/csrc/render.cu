@@ -71,6 +71,8 @@ struct gpurt_pipe {
     uint64_t lverts_version = ~0ull;
     const float4* lverts_tris = nullptr;
     bool use_lverts = true;                           /* GPURT_LIGHT_VERTS=0: light_sample transforms its vertices itself */
+    bool use_shadow_queue = false;                    /* GPURT_SHADOW_QUEUE=1: integrator 0 queues its shadow rays for k_shadow_resolve
+                                                       * (measured: 10 % slower than the inline trace; bit-identical) */
     /* light BVH for light_pdf (shade.cuh light_pdf_bvh): a second accel over the lights' triangles only */
     gpurt_scene* lscene = nullptr;
     gpurt_accel* laccel = nullptr;
@@ -145,7 +147,10 @@ __global__ void __launch_bounds__(128) k_trace_closest_indirect(const float4* __
     }
 }
 
-template <int INTEG>
+/* DEFER (integrator 0 only): the shadow ray of integrate_direct is not traced here — the pixel's segment goes to the
+ * (otherwise unused) next-bounce queue together with the term it gates, and k_shadow_resolve traces it and finishes
+ * the pixel.  Paths of integrator 0 end at their first hit, so nothing else competes for that queue. */
+template <int INTEG, bool DEFER = false>
 __global__ void __launch_bounds__(128, INTEG == 2 ? 5 : 0) k_shade(const __grid_constant__ FrameParams P,
                                                const __grid_constant__ ShadeCtx X, uint32_t s, uint32_t depth,
                                                const uint32_t* __restrict__ count_in, const uint32_t* __restrict__ queue_in,
@@ -164,6 +169,7 @@ __global__ void __launch_bounds__(128, INTEG == 2 ? 5 : 0) k_shade(const __grid_
         uint32_t pix = 0;
         TraceInfo trace;
         Shader sh(X, P);
+        sh.defer_shadow = DEFER;
         if(live) {
             pix = queue_in[k];
             float4 r0 = rays_in[2ull * k], r1 = rays_in[2ull * k + 1], h = hits[k];
@@ -174,7 +180,10 @@ __global__ void __launch_bounds__(128, INTEG == 2 ? 5 : 0) k_shade(const __grid_
             sh.seed = f2u(B.w);
             bool broke = shade_step<INTEG>(P, sh, trace, s, depth, pix, h, gpos, gnorm, galb, res_cur);
             cont = !broke && trace.depth + 1 < (uint32_t)P.c.max_depth;
-            if(cont) {
+            if(DEFER && sh.shadow_pending) { /* finished by k_shadow_resolve: radiance so far | term, RNG state */
+                pathA[pix] = make_float4(trace.acc.x, trace.acc.y, trace.acc.z, 0.0f);
+                pathB[pix] = make_float4(sh.shadow_term.x, sh.shadow_term.y, sh.shadow_term.z, u2f(sh.seed));
+            } else if(cont) {
                 pathA[pix] = make_float4(trace.acc.x, trace.acc.y, trace.acc.z, trace.mis);
                 pathB[pix] = make_float4(trace.throughput.x, trace.throughput.y, trace.throughput.z, u2f(sh.seed));
             } else { /* rt.rgen:630: acc += trace.acc; the RNG stream continues into the next sample */
@@ -184,7 +193,8 @@ __global__ void __launch_bounds__(128, INTEG == 2 ? 5 : 0) k_shade(const __grid_
             }
             nc += 1u + sh.n_closest, na += sh.n_any; /* this thread's wavefront ray + its inline rays */
         }
-        /* warp-aggregated compaction of the surviving paths */
+        /* warp-aggregated compaction of the surviving paths (DEFER: of the pixels with a shadow ray to trace) */
+        if(DEFER) cont = live && sh.shadow_pending;
         unsigned m = __ballot_sync(0xffffffffu, cont);
         uint32_t slot0 = 0;
         if(m) {
@@ -194,8 +204,16 @@ __global__ void __launch_bounds__(128, INTEG == 2 ? 5 : 0) k_shade(const __grid_
         if(cont) {
             uint32_t slot = slot0 + __popc(m & ((1u << lane) - 1u));
             queue_out[slot] = pix;
-            rays_out[2ull * slot] = make_float4(trace.o.x, trace.o.y, trace.o.z, kEps);
-            rays_out[2ull * slot + 1] = make_float4(trace.d.x, trace.d.y, trace.d.z, kLargeDist);
+            if(DEFER) { /* the segment of `visibility` (rt.rgen:272-291): direction (b - a) / |b - a|, (EPS, |b - a| - EPS) */
+                F3 dir = sh.shadow_b - sh.shadow_a;
+                float dl = length3(dir);
+                dir = dir / dl;
+                rays_out[2ull * slot] = make_float4(sh.shadow_a.x, sh.shadow_a.y, sh.shadow_a.z, kEps);
+                rays_out[2ull * slot + 1] = make_float4(dir.x, dir.y, dir.z, dl - kEps);
+            } else {
+                rays_out[2ull * slot] = make_float4(trace.o.x, trace.o.y, trace.o.z, kEps);
+                rays_out[2ull * slot + 1] = make_float4(trace.d.x, trace.d.y, trace.d.z, kLargeDist);
+            }
         }
     }
     /* ray accounting, one atomic per warp */
@@ -204,6 +222,26 @@ __global__ void __launch_bounds__(128, INTEG == 2 ? 5 : 0) k_shade(const __grid_
     if(lane == 0) {
         if(nc) atomicAdd(X.ray_counts + 0, (unsigned long long)nc);
         if(na) atomicAdd(X.ray_counts + 1, (unsigned long long)na);
+    }
+}
+
+/* Shadow stage of integrator 0: any-hit trace of the queued segments, then the last line of integrate_direct and the
+ * end-of-path accumulation k_shade left undone (rt.rgen:630).  One thread per queued pixel. */
+__global__ void __launch_bounds__(128) k_shadow_resolve(const float4* __restrict__ nodes, const float4* __restrict__ tris,
+                                                        unsigned n_nodes, const uint32_t* __restrict__ count,
+                                                        const uint32_t* __restrict__ queue, const float4* __restrict__ rays,
+                                                        float4* pathA, float4* pathB, float4* acc) {
+    const uint32_t cnt = *count;
+    for(uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < cnt; k += gridDim.x * blockDim.x) {
+        const uint32_t pix = queue[k];
+        const float4 a = __ldg(rays + 2ull * k), b = __ldg(rays + 2ull * k + 1);
+        HitRec h;
+        const bool occluded = n_nodes && traverse8<true, false>(nodes, tris, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), a.w, b.w, h, nullptr);
+        const float4 A = pathA[pix], B = pathB[pix];
+        const F3 t = Shader::shadow_finish(F3{A.x, A.y, A.z}, F3{B.x, B.y, B.z}, occluded);
+        const float4 o = acc[pix];
+        acc[pix] = make_float4(o.x + t.x, o.y + t.y, o.z + t.z, 0.0f);
+        pathB[pix] = make_float4(1.0f, 1.0f, 1.0f, B.w);
     }
 }
 
@@ -503,6 +541,7 @@ int gpurt_pipe_create(gpurt_scene* scene, gpurt_accel* accel, gpurt_pipe** out) 
     if(const char* e = getenv("GPURT_LIGHT_GROUPS")) p->use_lgrp = atoi(e) != 0;                   /* A/B knob */
     if(const char* e = getenv("GPURT_LIGHT_BVH")) p->use_lbvh = atoi(e) != 0;                      /* A/B knob */
     if(const char* e = getenv("GPURT_LIGHT_VERTS")) p->use_lverts = atoi(e) != 0;                  /* A/B knob */
+    if(const char* e = getenv("GPURT_SHADOW_QUEUE")) p->use_shadow_queue = atoi(e) != 0;           /* A/B knob */
     *out = p;
     return GPURT_OK;
 }
@@ -663,7 +702,16 @@ static int render_core(gpurt_pipe* p, const GpurtPipeParams* prm, const GpurtCam
                                               p->pathB, p->acc, p->gbuf[cur][0], p->gbuf[cur][1], p->gbuf[cur][2],      \
                                               p->res[cur], p->counts + d + 1, p->queue[qo], p->rays[qo])
             switch(c.integrator) {
-            case 0: GPURT_SHADE(0); break;
+            case 0:
+                if(p->use_shadow_queue) {
+                    k_shade<0, true><<<grid, 128, 0, st>>>(F, X, s, d, p->counts + d, p->queue[qi], p->rays[qi], p->hits, p->pathA,
+                                                           p->pathB, p->acc, p->gbuf[cur][0], p->gbuf[cur][1], p->gbuf[cur][2],
+                                                           p->res[cur], p->counts + d + 1, p->queue[qo], p->rays[qo]);
+                    k_shadow_resolve<<<grid, 128, 0, st>>>(X.nodes, X.tris, X.n_nodes, p->counts + d + 1, p->queue[qo], p->rays[qo],
+                                                           p->pathA, p->pathB, p->acc);
+                } else
+                    GPURT_SHADE(0);
+                break;
             case 1: GPURT_SHADE(1); break;
             case 2: GPURT_SHADE(2); break;
             case 3: GPURT_SHADE(3); break;

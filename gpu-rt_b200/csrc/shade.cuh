@@ -231,6 +231,10 @@ struct Shader {
     uint32_t seed;
     Reservoir prev_res;
     unsigned n_closest, n_any;
+    /* deferred shadow ray of integrate_direct (render.cu's shadow stage): instead of tracing `visibility` inline the
+     * segment and the term it gates are handed back, and k_shadow_resolve finishes the pixel */
+    bool defer_shadow = false, shadow_pending = false;
+    F3 shadow_a, shadow_b, shadow_term;
 
     SH_D Shader(const ShadeCtx& x, const FrameParams& p) : X(x), P(p), seed(0), n_closest(0), n_any(0) {}
 
@@ -815,11 +819,19 @@ struct Shader {
             F3 wi = normalize3(light.pos - hit.pos);
             F3 light_atten = MAT_eval(mat, shade, wi);
             if(light.pdf != 0) {
+                if(defer_shadow) { /* same arithmetic, finished by shadow_finish() once the segment has been traced */
+                    shadow_pending = true, n_any++;
+                    shadow_a = hit.pos, shadow_b = light.pos, shadow_term = light_atten / light.pdf * light.emissive;
+                    return;
+                }
                 float shadow = visibility(hit.pos, light.pos) ? 0.0f : 1.0f;
                 trace.acc = trace.acc + light_atten / light.pdf * light.emissive * shadow;
             }
         }
     }
+
+    /* the last line of integrate_direct for a deferred shadow ray */
+    SH_D static F3 shadow_finish(F3 acc, F3 term, bool occluded) { return acc + term * (occluded ? 0.0f : 1.0f); }
 
     /* restir.glsl:17-35 */
     SH_D void res_update(Reservoir& res, float weight, F3 pos, F3 normal, F3 emissive) {

@@ -83,6 +83,15 @@ def test_sponza_standin_config2(gpurt, orc, ctx):
          max_depth=2, use_rr=0, env_scale=1.0, seed=3)
 
 
+def test_shadow_queue_stage_is_bit_identical(gpurt, orc, ctx, monkeypatch):
+    """GPURT_SHADOW_QUEUE=1 (opt-in; measured slower than the inline trace): integrator 0 hands its shadow segments to a
+    queue, k_shadow_resolve traces them and finishes the pixels — same frames, same ray counts"""
+    monkeypatch.setenv("GPURT_SHADOW_QUEUE", "1")
+    for brdf in (0, 1):
+        _run(gpurt, orc, ctx, "cbox", 192, 108, 3, integrator=0, brdf=brdf, samples_per_frame=3, max_depth=4, seed=77)
+    _run(gpurt, orc, ctx, "cbox", 128, 72, 2, integrator=0, brdf=0, samples_per_frame=1, max_depth=1, use_rr=0, seed=12)
+
+
 def test_config2_full_size_1080p(gpurt, orc, ctx):
     """BASELINE config 2 at its full size: 1920x1080, integrator 1 (Material), GGX, depth 2, 1 spp, env light,
     no RR — image, G-buffers and ray counts of the frame against the oracle's rt.rgen restatement (rt.rgen:567-677)"""

@@ -76,7 +76,7 @@ int upload_scene(gpurt_ctx* ctx, gpurt_scene* s, DeviceScene& d) {
  * max(H2D, kernel, D2H) instead of their sum.  ev0/ev1 bracket the device work for gpurt_last_kernel_ms. */
 template <typename F>
 static int run_query(gpurt_ctx* ctx, const void* in, size_t in_stride, void* out, size_t out_stride, uint64_t n,
-                     int mem, F launch) {
+                     int mem, F launch, bool single_pass = false) {
     GPURT_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     if(mem == GPURT_MEM_DEVICE) {
@@ -88,6 +88,32 @@ static int run_query(gpurt_ctx* ctx, const void* in, size_t in_stride, void* out
     }
     if(mem != GPURT_MEM_HOST) return set_error("mem must be GPURT_MEM_HOST or GPURT_MEM_DEVICE"), GPURT_E_INVALID;
     int rc;
+    /* Pinned (page-locked, hence device-mapped) caller buffers and a launch that reads every element once: the kernel
+     * streams its input over PCIe itself and stores its results straight into the caller's array — one launch, no
+     * staging copies, no chunk pipeline with its un-overlapped first copy in and last copy out.  Every ray still crosses
+     * PCIe once in and its hit once out.  GPURT_ZERO_COPY=0 keeps the staged pipeline (pageable memory always uses it). */
+    static const int zc_mode = getenv("GPURT_ZERO_COPY") ? atoi(getenv("GPURT_ZERO_COPY")) : 1;
+    const bool zero_copy = zc_mode == 1;
+    char* mapped_out = nullptr; /* GPURT_ZERO_COPY=2 (A/B): copy engine in, results stored straight into the caller's array */
+    if(zc_mode == 2 && single_pass && n) {
+        cudaPointerAttributes ao;
+        if(cudaPointerGetAttributes(&ao, out) == cudaSuccess && ao.type == cudaMemoryTypeHost && ao.devicePointer)
+            mapped_out = (char*)ao.devicePointer;
+        (void)cudaGetLastError();
+    }
+    if(zero_copy && single_pass && n) {
+        cudaPointerAttributes ai, ao;
+        const bool ok = cudaPointerGetAttributes(&ai, in) == cudaSuccess && ai.type == cudaMemoryTypeHost && ai.devicePointer &&
+                        cudaPointerGetAttributes(&ao, out) == cudaSuccess && ao.type == cudaMemoryTypeHost && ao.devicePointer;
+        (void)cudaGetLastError(); /* pageable memory answers with an error on older drivers: not a failure */
+        if(ok) {
+            GPURT_CUDA(cudaEventRecord(ctx->ev0, st));
+            if((rc = launch(ai.devicePointer, ao.devicePointer, n))) return rc;
+            GPURT_CUDA(cudaEventRecord(ctx->ev1, st));
+            GPURT_CUDA(cudaStreamSynchronize(st));
+            return GPURT_OK;
+        }
+    }
     if((rc = ctx->d_in.reserve(n * in_stride))) return rc;
     if((rc = ctx->d_out.reserve(n * out_stride))) return rc;
     /* chunk = a quarter of the batch, between 64 Ki and 512 Ki elements (16 MB of rays per copy): each chunk costs
@@ -112,11 +138,12 @@ static int run_query(gpurt_ctx* ctx, const void* in, size_t in_stride, void* out
             if(taper && rem <= 2 * chunk) cnt = std::min<uint64_t>(rem, std::max<uint64_t>(min_chunk, (rem / 2 + 1023) & ~1023ull));
             if(rem - cnt < min_chunk / 2) cnt = rem;
             char* di = (char*)ctx->d_in.p + off * in_stride;
-            char* dout = (char*)ctx->d_out.p + off * out_stride;
+            char* dout = mapped_out ? mapped_out + off * out_stride : (char*)ctx->d_out.p + off * out_stride;
             GPURT_CUDA(cudaMemcpyAsync(di, (const char*)in + off * in_stride, cnt * in_stride, cudaMemcpyHostToDevice, ctx->s_h2d));
             GPURT_CUDA(cudaEventRecord(ctx->ev_copy, ctx->s_h2d));
             GPURT_CUDA(cudaStreamWaitEvent(st, ctx->ev_copy, 0));
             if(int lrc = launch(di, dout, cnt)) return lrc;
+            if(mapped_out) continue;
             GPURT_CUDA(cudaEventRecord(ctx->ev_kernel, st));
             GPURT_CUDA(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_kernel, 0));
             GPURT_CUDA(cudaMemcpyAsync((char*)out + off * out_stride, dout, cnt * out_stride, cudaMemcpyDeviceToHost, ctx->s_d2h));
@@ -371,10 +398,16 @@ int gpurt_accel_get_bvh2(const gpurt_accel* A, int32_t* left, int32_t* right, fl
 }
 
 /* ---- queries ---------------------------------------------------------------------------------- */
+/* true when a batch of n elements is answered by one pass over its input (order.cu does not re-order it) */
+static bool single_pass(const gpurt_accel* A, uint64_t n) {
+    const size_t bvh_bytes = (size_t)A->n_nodes * sizeof(Node8) + (size_t)A->n * 48;
+    return n < (1u << 20) || bvh_bytes <= (64u << 20);
+}
 int gpurt_trace_closest(gpurt_accel* A, const GpurtRay* rays, uint64_t n, GpurtHit* hits, int mem) {
     if(!A || (n && (!rays || !hits))) return set_error("NULL argument"), GPURT_E_INVALID;
     return run_query(A->ctx, rays, sizeof(GpurtRay), hits, sizeof(GpurtHit), n, mem,
-                     [&](const void* i, void* o, uint64_t c) { return launch_trace_closest(A, (const float4*)i, c, (float4*)o); });
+                     [&](const void* i, void* o, uint64_t c) { return launch_trace_closest(A, (const float4*)i, c, (float4*)o); },
+                     single_pass(A, n));
 }
 int gpurt_trace_closest_bvh2(gpurt_accel* A, const GpurtRay* rays, uint64_t n, GpurtHit* hits, int mem) {
     if(!A || (n && (!rays || !hits))) return set_error("NULL argument"), GPURT_E_INVALID;
@@ -384,12 +417,14 @@ int gpurt_trace_closest_bvh2(gpurt_accel* A, const GpurtRay* rays, uint64_t n, G
 int gpurt_trace_any(gpurt_accel* A, const GpurtRay* rays, uint64_t n, uint8_t* occ, int mem) {
     if(!A || (n && (!rays || !occ))) return set_error("NULL argument"), GPURT_E_INVALID;
     return run_query(A->ctx, rays, sizeof(GpurtRay), occ, 1, n, mem,
-                     [&](const void* i, void* o, uint64_t c) { return launch_trace_any(A, (const float4*)i, c, (uint8_t*)o); });
+                     [&](const void* i, void* o, uint64_t c) { return launch_trace_any(A, (const float4*)i, c, (uint8_t*)o); },
+                     single_pass(A, n));
 }
 int gpurt_closest_points(gpurt_accel* A, const GpurtQuery* q, uint64_t n, GpurtClosestPoint* res, int mem) {
     if(!A || (n && (!q || !res))) return set_error("NULL argument"), GPURT_E_INVALID;
     return run_query(A->ctx, q, sizeof(GpurtQuery), res, sizeof(GpurtClosestPoint), n, mem,
-                     [&](const void* i, void* o, uint64_t c) { return launch_closest_points(A, (const float4*)i, c, (float4*)o); });
+                     [&](const void* i, void* o, uint64_t c) { return launch_closest_points(A, (const float4*)i, c, (float4*)o); },
+                     single_pass(A, n));
 }
 int gpurt_trace_closest_stats(gpurt_accel* A, const GpurtRay* rays, uint64_t n, GpurtHit* hits,
                               GpurtTraceStats* out) {

@@ -127,6 +127,19 @@ def test_device_buffers_match_host_buffers(gpurt, orc, ctx):
     d_hits = accel.trace_closest(d_rays)
     torch.cuda.synchronize()
     assert same_bits(d_hits.cpu().numpy(), host)
+    # pinned host arrays: the kernels read / write them in place over PCIe (zero-copy path of the GPURT_MEM_HOST calls)
+    p_rays = torch.from_numpy(rays).pin_memory()
+    p_hits = torch.empty((len(rays), 4), dtype=torch.float32).pin_memory()
+    accel.trace_closest(p_rays.numpy(), p_hits.numpy())
+    assert same_bits(p_hits.numpy(), host)
+    p_occ = torch.empty(len(rays), dtype=torch.uint8).pin_memory()
+    accel.trace_any(p_rays.numpy(), p_occ.numpy())
+    assert (p_occ.numpy() == accel.trace_any(rays)).all()
+    q = orc.gen_random_points(100000, 9, box)
+    p_q = torch.from_numpy(q).pin_memory()
+    p_cp = torch.empty((len(q), 8), dtype=torch.float32).pin_memory()
+    accel.closest_points(p_q.numpy(), p_cp.numpy())
+    assert same_bits(p_cp.numpy(), accel.closest_points(q))
     st = accel.trace_stats(d_rays, d_hits)
     assert st.rays == 200000 and st.hits == int((host["prim"] != gpurt.NO_HIT).sum())
     assert st.nodes_visited > st.rays

@@ -764,7 +764,8 @@ def main():
                        "bvh_build_mtris_s": info.n_tris / (info.build_ms * 1e-3) / 1e6,
                        "l2": "flushed between timed steps (256 MiB memset)", "sharding": sharding},
             "e2e": {"value": e2e_val, "unit": "Mrays/s", "h2d_bytes_per_step": int(n_rays * 32), "d2h_bytes_per_step": int(n_rays * 16),
-                    "what": f"gpurt_trace_closest with HOST ray ({ray_mem}) / hit (pinned) arrays"},
+                    "what": f"gpurt_trace_closest with HOST ray ({ray_mem}) / hit (pinned) arrays: the kernel reads the rays and "
+                            "stores the hits in place over PCIe (32 B in + 16 B out per ray inside the timed call)"},
             "e2e_render": {"value": frame_rays_total * e2e_steps / e2e_render_s / 1e6, "unit": "Mrays/s",
                            "ms_per_frame": e2e_render_s / e2e_steps * 1e3, "h2d_bytes_per_step": 416, "d2h_bytes_per_step": W * H * 16,
                            "what": "gpurt_pipe_render_frame + gpurt_pipe_read_image into pinned host memory (the reference-facing "

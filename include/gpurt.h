@@ -10,9 +10,10 @@
  * Conventions: every function returns 0 on success and a negative GPURT_E_* code on failure, never
  * exits (the reference's VK_CHECK -> die() -> exit(), src/vk/vulkan.h:26-33, is replaced by error
  * codes + gpurt_last_error()).  Handles are opaque.  One gpurt_ctx per GPU, used from one host
- * thread at a time.  `mem` says where ray/query/result buffers live: GPURT_MEM_HOST buffers are
- * staged through pinned memory inside the call; GPURT_MEM_DEVICE buffers are used in place and the
- * call is asynchronous on the context's stream.  There is NO CPU fallback: compute entry points fail
+ * thread at a time.  `mem` says where ray/query/result buffers live.  GPURT_MEM_HOST: the call returns when the results
+ * are in the caller's array; page-locked arrays (cudaHostAlloc / cudaHostRegister) are read and written in place by
+ * the kernels over PCIe (one launch, no staging), pageable ones go through a chunked copy pipeline.
+ * GPURT_MEM_DEVICE buffers are used in place and the call is asynchronous on the context's stream.  There is NO CPU fallback: compute entry points fail
  * with GPURT_E_NO_DEVICE when no B200 is present.
  */
 #ifndef GPURT_H

@@ -145,68 +145,57 @@ __device__ __forceinline__ void bins_add(LaneBins& B, unsigned group, float4 l, 
 }
 
 
-/* The same, two items per step: the lower half-warp folds item j, the upper half item j + 1, and every lane owns bin
- * lane & 15 of all three axes (17 instead of 28 warp instructions per item).  `group` must be a contiguous lane range;
- * lanes outside it pass packed = 0xffffffff.  merge() leaves the union of the two halves in every lane. */
-struct LaneBins3 {
-    unsigned cnt[3];
-    float lo[3][3], hi[3][3];
-    __device__ __forceinline__ void reset() {
+/* One step of 32 items (lane = item) into bins in shared memory (phase A: the tile's bins, shared by its warps; small
+ * segments: the warp's own).  Per axis: when every item of the step falls into the same bin — the usual case near the top
+ * of a spatially coherent mesh — the warp reduces the boxes with six full-mask redux.sync and one lane updates the bin;
+ * otherwise every lane updates its bin with shared-memory atomics (conflicts only between lanes that share a bin).  About
+ * 1-3 warp instructions per item instead of the 17-28 of the register-transposed loop, which remains for <= 32-item
+ * subtrees.  packed: the item's three bins, 0xff = none (lane beyond the segment, axis not used). */
+__device__ __forceinline__ void bins_step(int* sb, unsigned packed, float4 l, float4 h, int lane) {
+    const float lv[3] = {l.x, l.y, l.z}, hv[3] = {h.x, h.y, h.z};
+    int el[3], eh[3];
 #pragma unroll
-        for(int s = 0; s < 3; s++) {
-            cnt[s] = 0;
+    for(int q = 0; q < 3; q++) el[q] = enc(lv[q] == lv[q] ? lv[q] : SAH_BIG), eh[q] = enc(hv[q] == hv[q] ? hv[q] : -SAH_BIG);
 #pragma unroll
-            for(int k = 0; k < 3; k++) lo[s][k] = SAH_BIG, hi[s][k] = -SAH_BIG;
-        }
-    }
-    __device__ __forceinline__ void merge() {
+    for(int ax = 0; ax < 3; ax++) {
+        const unsigned b = (packed >> (8 * ax)) & 0xffu;
+        const unsigned valid = __ballot_sync(FULL, b != 0xffu);
+        if(!valid) continue;
+        const unsigned bref = __shfl_sync(FULL, b, __ffs((int)valid) - 1);
+        if(__all_sync(FULL, b == 0xffu || b == bref)) {
+            int mn[3], mx[3];
 #pragma unroll
-        for(int s = 0; s < 3; s++) {
-            cnt[s] += __shfl_xor_sync(FULL, cnt[s], 16);
-#pragma unroll
-            for(int k = 0; k < 3; k++)
-                lo[s][k] = fminf(lo[s][k], __shfl_xor_sync(FULL, lo[s][k], 16)), hi[s][k] = fmaxf(hi[s][k], __shfl_xor_sync(FULL, hi[s][k], 16));
-        }
-    }
-    /* after merge(): the layout eval_split works on */
-    __device__ __forceinline__ LaneBins split_layout(int lane) const {
-        LaneBins B;
-        const int a = lane >> 4;
-        B.cnt[0] = a ? cnt[1] : cnt[0], B.cnt[1] = cnt[2];
-#pragma unroll
-        for(int k = 0; k < 3; k++)
-            B.lo[0][k] = a ? lo[1][k] : lo[0][k], B.hi[0][k] = a ? hi[1][k] : hi[0][k], B.lo[1][k] = lo[2][k], B.hi[1][k] = hi[2][k];
-        return B;
-    }
-};
-__device__ __forceinline__ void bins_add2(LaneBins3& B, unsigned group, float4 l, float4 h, unsigned packed, int lane) {
-    if(!group) return;
-    const int first = __ffs((int)group) - 1, last = 31 - __clz((int)group), half = lane >> 4;
-    const unsigned mine = (unsigned)(lane & 15);
-    /* four items per trip (two per half-warp): both shuffle batches are issued before either is consumed */
-    for(int j = first; j <= last; j += 4) {
-        const int s0 = j + half, s1 = j + 2 + half;
-        const float ax0 = __shfl_sync(FULL, l.x, s0), ay0 = __shfl_sync(FULL, l.y, s0), az0 = __shfl_sync(FULL, l.z, s0);
-        const float bx0 = __shfl_sync(FULL, h.x, s0), by0 = __shfl_sync(FULL, h.y, s0), bz0 = __shfl_sync(FULL, h.z, s0);
-        unsigned p0 = __shfl_sync(FULL, packed, s0);
-        const float ax1 = __shfl_sync(FULL, l.x, s1), ay1 = __shfl_sync(FULL, l.y, s1), az1 = __shfl_sync(FULL, l.z, s1);
-        const float bx1 = __shfl_sync(FULL, h.x, s1), by1 = __shfl_sync(FULL, h.y, s1), bz1 = __shfl_sync(FULL, h.z, s1);
-        unsigned p1 = __shfl_sync(FULL, packed, s1);
-        if(s0 > last) p0 = 0xffffffffu;
-        if(s1 > last) p1 = 0xffffffffu;
-#pragma unroll
-        for(int ax = 0; ax < 3; ax++) {
-            if(((p0 >> (8 * ax)) & 0xffu) == mine) {
-                B.cnt[ax]++;
-                B.lo[ax][0] = fminf(B.lo[ax][0], ax0), B.lo[ax][1] = fminf(B.lo[ax][1], ay0), B.lo[ax][2] = fminf(B.lo[ax][2], az0);
-                B.hi[ax][0] = fmaxf(B.hi[ax][0], bx0), B.hi[ax][1] = fmaxf(B.hi[ax][1], by0), B.hi[ax][2] = fmaxf(B.hi[ax][2], bz0);
+            for(int q = 0; q < 3; q++) {
+                mn[q] = __reduce_min_sync(FULL, b != 0xffu ? el[q] : enc(SAH_BIG));
+                mx[q] = __reduce_max_sync(FULL, b != 0xffu ? eh[q] : enc(-SAH_BIG));
             }
-            if(((p1 >> (8 * ax)) & 0xffu) == mine) {
-                B.cnt[ax]++;
-                B.lo[ax][0] = fminf(B.lo[ax][0], ax1), B.lo[ax][1] = fminf(B.lo[ax][1], ay1), B.lo[ax][2] = fminf(B.lo[ax][2], az1);
-                B.hi[ax][0] = fmaxf(B.hi[ax][0], bx1), B.hi[ax][1] = fmaxf(B.hi[ax][1], by1), B.hi[ax][2] = fmaxf(B.hi[ax][2], bz1);
+            if(lane == 0) {
+                int* w = sb + (ax * SAH_BINS + (int)bref) * 7;
+                atomicAdd((unsigned*)w, (unsigned)__popc(valid));
+#pragma unroll
+                for(int q = 0; q < 3; q++) atomicMin(w + 1 + q, mn[q]), atomicMax(w + 4 + q, mx[q]);
             }
+        } else if(b != 0xffu) {
+            int* w = sb + (ax * SAH_BINS + (int)b) * 7;
+            atomicAdd((unsigned*)w, 1u);
+#pragma unroll
+            for(int q = 0; q < 3; q++) atomicMin(w + 1 + q, el[q]), atomicMax(w + 4 + q, eh[q]);
         }
+    }
+}
+__device__ __forceinline__ void bins_clear(int* sb, int lane) {
+    for(int i = lane; i < SAH_BIN_WORDS; i += 32) sb[i] = (i % 7) == 0 ? 0 : ((i % 7) < 4 ? enc(SAH_BIG) : enc(-SAH_BIG));
+    __syncwarp();
+}
+/* shared bins -> the lane-owned layout eval_split works on */
+__device__ __forceinline__ void bins_load(LaneBins& B, const int* sb, int lane) {
+    __syncwarp();
+#pragma unroll
+    for(int q = 0; q < 2; q++) {
+        const int* w = sb + ((q == 0 ? (lane >> 4) : 2) * SAH_BINS + (lane & 15)) * 7;
+        B.cnt[q] = (unsigned)w[0];
+#pragma unroll
+        for(int c = 0; c < 3; c++) B.lo[q][c] = dec(w[1 + c]), B.hi[q][c] = dec(w[4 + c]);
     }
 }
 
@@ -294,10 +283,12 @@ __global__ void k_sah_setup(unsigned n, unsigned small_max, SahState* st, SahSeg
 
 __global__ void __launch_bounds__(256) k_sah_init(const float4* __restrict__ tri_lo, const float4* __restrict__ tri_hi, unsigned n,
                                                    SahRec* rec, int* seg_of, int seg_value, uint64_t* keys, int* cb) {
-    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ int s_e[6];
     /* identities and clamps are those of sah_split.h's empty_box(): +-3.0e38 */
     int e[6] = {enc(SAH_BIG), enc(SAH_BIG), enc(SAH_BIG), enc(-SAH_BIG), enc(-SAH_BIG), enc(-SAH_BIG)};
-    if(i < n) {
+    if(threadIdx.x < 6) s_e[threadIdx.x] = e[threadIdx.x];
+    __syncthreads();
+    for(unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         float4 l = tri_lo[i], h = tri_hi[i];
         l.w = __uint_as_float(i);
         rec[i].lo = l, rec[i].hi = h;
@@ -306,14 +297,18 @@ __global__ void __launch_bounds__(256) k_sah_init(const float4* __restrict__ tri
         const float c[3] = {(l.x + h.x) * 0.5f, (l.y + h.y) * 0.5f, (l.z + h.z) * 0.5f};
 #pragma unroll
         for(int q = 0; q < 3; q++)
-            if(c[q] == c[q]) e[q] = enc(fminf(c[q], SAH_BIG)), e[3 + q] = enc(fmaxf(c[q], -SAH_BIG));
+            if(c[q] == c[q]) e[q] = min(e[q], enc(fminf(c[q], SAH_BIG))), e[3 + q] = max(e[3 + q], enc(fmaxf(c[q], -SAH_BIG)));
     }
     if(seg_value < 0) return;
+    /* centroid bounds of the root: warp, block, then one global update per block */
 #pragma unroll
     for(int q = 0; q < 3; q++) {
         const int mn = __reduce_min_sync(FULL, e[q]), mx = __reduce_max_sync(FULL, e[3 + q]);
-        if((threadIdx.x & 31) == 0) atomicMin(cb + q, mn), atomicMax(cb + 3 + q, mx);
+        if((threadIdx.x & 31) == 0) atomicMin(s_e + q, mn), atomicMax(s_e + 3 + q, mx);
     }
+    __syncthreads();
+    if(threadIdx.x < 3) atomicMin(cb + threadIdx.x, s_e[threadIdx.x]);
+    else if(threadIdx.x < 6) atomicMax(cb + threadIdx.x, s_e[threadIdx.x]);
 }
 
 __global__ void __launch_bounds__(256) k_sah_bins(const SahRec* __restrict__ rec, const int* __restrict__ seg_of, unsigned n,
@@ -328,20 +323,8 @@ __global__ void __launch_bounds__(256) k_sah_bins(const SahRec* __restrict__ rec
         (&s_bins[0][0])[i] = (i % 7) == 0 ? 0 : ((i % 7) < 4 ? enc(SAH_BIG) : enc(-SAH_BIG));
     __syncthreads();
     LaneBins B;
-    LaneBins3 B3;
     SegFrame F;
     int cur = -1, cur_slot = 0;
-    auto flush = [&]() { /* this warp's share of segment `cur` into the tile's bins */
-        int* base = s_bins[cur_slot];
-#pragma unroll
-        for(int ax = 0; ax < 3; ax++) {
-            if(B3.cnt[ax] == 0) continue;
-            int* w = base + (ax * SAH_BINS + (lane & 15)) * 7;
-            atomicAdd((unsigned*)w, B3.cnt[ax]);
-#pragma unroll
-            for(int q = 0; q < 3; q++) atomicMin(w + 1 + q, enc(B3.lo[ax][q])), atomicMax(w + 4 + q, enc(B3.hi[ax][q]));
-        }
-    };
     for(int it = 0; it < 4; it++) {
         const unsigned pos = tile0 + warp * 128 + it * 32 + lane;
         const int s = pos < n ? seg_of[pos] : -1;
@@ -357,19 +340,16 @@ __global__ void __launch_bounds__(256) k_sah_bins(const SahRec* __restrict__ rec
             const int sj = __shfl_sync(FULL, s, __ffs((int)todo) - 1);
             const unsigned group = __ballot_sync(FULL, s == sj);
             if(sj != cur) {
-                if(cur >= 0) flush();
-                B3.reset();
                 cur = sj, cur_slot = segs[sj].a > tile0 ? 1 : 0;
                 float cl[3], ch[3];
 #pragma unroll
                 for(int q = 0; q < 3; q++) cl[q] = dec(cb[6 * sj + q]), ch[q] = dec(cb[6 * sj + 3 + q]);
                 F.set(cl, ch);
             }
-            bins_add2(B3, group, l, h, s == sj ? F.bins(l, h) : 0xffffffffu, lane);
+            bins_step(s_bins[cur_slot], s == sj ? F.bins(l, h) : 0xffffffffu, l, h, lane);
             todo &= ~group;
         }
     }
-    if(cur >= 0) flush();
     __syncthreads();
     for(int i = threadIdx.x; i < 2 * SAH_BIN_WORDS; i += blockDim.x) { /* one global update per tile, segment and non-empty bin */
         const int slot = i / SAH_BIN_WORDS, w = i % SAH_BIN_WORDS, sg = s_slot[slot];
@@ -424,18 +404,33 @@ __device__ __forceinline__ bool goes_left(const SahSplit& sp, float4 l, float4 h
     return sah_bin(c, sp.lo, sp.scale) < sp.k;
 }
 
-/* per thread 4 consecutive positions; returns the left flags (bit r) and slots (bit 4 + r) of its items */
+/* per thread 4 consecutive positions; returns the left flags (bit r) and slots (bit 4 + r) of its items.  The splits of
+ * the (at most two) big segments that meet in the tile are staged in shared memory first (block-wide: contains barriers);
+ * s_sp[slot] is left valid for the caller. */
 __device__ __forceinline__ unsigned tile_flags(const SahRec* __restrict__ rec, const int* __restrict__ seg_of, unsigned n,
-                                               const SahSplit* __restrict__ split, unsigned tile0, unsigned p0, int seg[4]) {
+                                               const SahSplit* __restrict__ split, unsigned tile0, unsigned p0, int seg[4],
+                                               SahSplit* s_sp, int* s_seg) {
+    if(threadIdx.x == 0) s_seg[0] = tile0 < n ? seg_of[tile0] : -1, s_seg[1] = -1;
+#pragma unroll
+    for(int r = 0; r < 4; r++) seg[r] = p0 + r < n ? seg_of[p0 + r] : -1;
+    __syncthreads();
+    const int s0 = s_seg[0];
+#pragma unroll
+    for(int r = 0; r < 4; r++)
+        if(seg[r] >= 0 && seg[r] != s0) s_seg[1] = seg[r]; /* every writer stores the same value */
+    __syncthreads();
+    if(threadIdx.x < 2 * (sizeof(SahSplit) / 4)) {
+        const int slot = threadIdx.x / (sizeof(SahSplit) / 4), w = threadIdx.x % (sizeof(SahSplit) / 4);
+        if(s_seg[slot] >= 0) ((unsigned*)(s_sp + slot))[w] = ((const unsigned*)(split + s_seg[slot]))[w];
+    }
+    __syncthreads();
     unsigned f = 0;
 #pragma unroll
     for(int r = 0; r < 4; r++) {
-        const unsigned pos = p0 + r;
-        seg[r] = pos < n ? seg_of[pos] : -1;
         if(seg[r] < 0) continue;
-        const SahSplit sp = split[seg[r]];
-        if(goes_left(sp, rec[pos].lo, rec[pos].hi, pos)) f |= 1u << r;
-        if(sp.a > tile0) f |= 16u << r;
+        const unsigned pos = p0 + r, slot = seg[r] == s0 ? 0u : 1u;
+        if(goes_left(s_sp[slot], rec[pos].lo, rec[pos].hi, pos)) f |= 1u << r;
+        f |= (16u * slot) << r;
     }
     return f;
 }
@@ -443,9 +438,11 @@ __device__ __forceinline__ unsigned tile_flags(const SahRec* __restrict__ rec, c
 __global__ void __launch_bounds__(256) k_sah_count(const SahRec* __restrict__ rec, const int* __restrict__ seg_of, unsigned n,
                                                     const SahSplit* __restrict__ split, unsigned* tile_left) {
     __shared__ unsigned s_sum[8];
+    __shared__ SahSplit s_sp[2];
+    __shared__ int s_seg[2];
     const unsigned tile0 = blockIdx.x * SAH_TILE;
     int seg[4];
-    const unsigned f = tile_flags(rec, seg_of, n, split, tile0, tile0 + 4 * threadIdx.x, seg);
+    const unsigned f = tile_flags(rec, seg_of, n, split, tile0, tile0 + 4 * threadIdx.x, seg, s_sp, s_seg);
     unsigned c = 0; /* slot 0 lefts in the low half, slot 1 lefts in the high half */
 #pragma unroll
     for(int r = 0; r < 4; r++)
@@ -562,8 +559,10 @@ __global__ void __launch_bounds__(256) k_sah_scatter(const SahRec* __restrict__ 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if(threadIdx.x < 24) s_cb[threadIdx.x / 6][threadIdx.x % 6] = (threadIdx.x % 6) < 3 ? enc(SAH_BIG) : enc(-SAH_BIG);
     if(threadIdx.x < 4) s_child[threadIdx.x] = -1;
+    __shared__ SahSplit s_sp[2];
+    __shared__ int s_seg[2];
     int seg[4];
-    const unsigned f = tile_flags(rec, seg_of, n, split, tile0, p0, seg);
+    const unsigned f = tile_flags(rec, seg_of, n, split, tile0, p0, seg, s_sp, s_seg);
     unsigned c = 0;
 #pragma unroll
     for(int r = 0; r < 4; r++)
@@ -587,8 +586,8 @@ __global__ void __launch_bounds__(256) k_sah_scatter(const SahRec* __restrict__ 
         unsigned dest = pos;
         float4 l = make_float4(0, 0, 0, 0), h = l;
         if(valid && s >= 0) {
-            const SahSplit sp = split[s];
             const unsigned slot = (f >> (4 + r)) & 1u;
+            const SahSplit& sp = s_sp[slot];
             const bool is_left = (f >> r) & 1u;
             const unsigned in_tile = slot ? (before >> 16) : (before & 0xffffu);
             const unsigned lefts_before = scan[2 * blockIdx.x + slot] - sp.base + in_tile;
@@ -757,9 +756,11 @@ __global__ void __launch_bounds__(128) k_sah_small(SahRec* rec0, SahRec* rec1, S
                                                     unsigned cap, SmallOut O) {
     __shared__ float4 s_stage[4][64];
     __shared__ uint4 s_stack[4][32];
+    __shared__ int s_bins[4][SAH_BIN_WORDS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float4* stage = s_stage[warp];
     uint4* stack = s_stack[warp];
+    int* sb = s_bins[warp];
     const unsigned lt = (1u << lane) - 1u;
     const unsigned total = st->small_total;
     for(;;) {
@@ -822,8 +823,7 @@ __global__ void __launch_bounds__(128) k_sah_small(SahRec* rec0, SahRec* rec1, S
             }
             SegFrame F;
             F.set(cl, ch);
-            LaneBins3 B3;
-            B3.reset();
+            bins_clear(sb, lane);
             {
                 /* the next step's records are in flight while this step's 32 items are binned */
                 unsigned i = a + lane;
@@ -834,11 +834,11 @@ __global__ void __launch_bounds__(128) k_sah_small(SahRec* rec0, SahRec* rec1, S
                     const float4 l0 = l, h0 = h;
                     i = base + 32 + lane;
                     if(i < b) l = __ldcg(&in[i].lo), h = __ldcg(&in[i].hi);
-                    bins_add2(B3, __ballot_sync(FULL, valid), l0, h0, valid ? F.bins(l0, h0) : 0xffffffffu, lane);
+                    bins_step(sb, valid ? F.bins(l0, h0) : 0xffffffffu, l0, h0, lane);
                 }
             }
-            B3.merge();
-            const LaneBins B = B3.split_layout(lane);
+            LaneBins B;
+            bins_load(B, sb, lane);
             int axis, k;
             unsigned nl;
             eval_split(B, lane, axis, k, nl);
@@ -968,7 +968,8 @@ int build_sah_split_device(gpurt_ctx* ctx, const float4* tri_lo, const float4* t
     const bool big_root = n > small_max;
     GPURT_CUDA(cudaMemsetAsync(ready, 0, cap * 4, st));
     k_sah_setup<<<1, 128, 0, st>>>(n, small_max, state, segs[0], jobs, ready, cb, bins, tiles_done);
-    k_sah_init<<<(n + 255) / 256, 256, 0, st>>>(tri_lo, tri_hi, n, rec[0], seg_of[0], big_root ? 0 : -1, keys, cb);
+    k_sah_init<<<std::min((n + 255) / 256, (unsigned)ctx->sm_count * 8u), 256, 0, st>>>(tri_lo, tri_hi, n, rec[0], seg_of[0],
+                                                                                   big_root ? 0 : -1, keys, cb);
     /* Levels of big segments.  The host learns from k_sah_level whether another level follows; so that this read-back does
      * not leave the device idle, level L + 1 is already queued when the host waits for level L's count (a level without
      * big segments touches nothing: its kernels find seg_of == -1 everywhere).  Word 0 / 1 of the pinned block alternate. */

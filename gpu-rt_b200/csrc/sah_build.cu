@@ -24,7 +24,14 @@
  *
  * Item records (box + primitive id, 32 bytes) are physically partitioned between two arrays, so every pass reads
  * contiguous memory.
+ *
+ * Measured and not kept: binning by match.any + group-masked redux.sync (group-masked redux serialises per group: 2.7x
+ * slower than the register-transposed loop); <= 32-item subtrees level by level with every lane walking the members of
+ * its segment (bit-identical, 3-8 % slower than node by node: ~70 warp instructions per member and axis).
+ * -DSAH_PROFILE prints where k_sah_small's cycles go: on 262 k triangles 79 % in <= 32-item subtrees (~10 k warp
+ * instructions each), which is also the tail of the build's critical path.
  */
+#include <cstdio>
 #include <cstdlib>
 
 #include "device.cuh"
@@ -66,6 +73,7 @@ struct SahState { /* the hot counters of k_sah_small live on cache lines of thei
     unsigned q_head, pad2[31];
     unsigned leaves_done, pad3[31];
     unsigned finished, stalled, pad4[30];
+    unsigned long long prof[4]; /* -DSAH_PROFILE: cycles in <= 32-item subtrees, in larger nodes, waiting for tickets; subtrees */
 };
 
 /* order-preserving float <-> int for atomicMin / atomicMax */
@@ -276,6 +284,7 @@ __global__ void k_sah_setup(unsigned n, unsigned small_max, SahState* st, SahSeg
         tiles_done[0] = 0;
         st->n_seg = big_root ? 1u : 0u, st->n_seg_next = 0u, st->small_total = big_root ? 0u : n;
         st->q_tail = big_root ? 0u : 1u, st->q_head = 0u, st->leaves_done = 0u, st->finished = 0u, st->stalled = 0u;
+        st->prof[0] = st->prof[1] = st->prof[2] = st->prof[3] = 0ull;
         if(big_root) segs[0] = SahSeg{0u, n, 0, -1};
         else jobs[0] = SahJob{0u, n, 0, -1, 0u}, ready[0] = 1u;
     }
@@ -767,6 +776,9 @@ __global__ void __launch_bounds__(128) k_sah_small(SahRec* rec0, SahRec* rec1, S
         unsigned ticket = 0;
         if(lane == 0) ticket = atomicAdd(&st->q_head, 1u);
         ticket = __shfl_sync(FULL, ticket, 0);
+#ifdef SAH_PROFILE
+        const long long tw0 = clock64();
+#endif
         int got = 0;
         if(lane == 0) {
             /* a ticket is served as soon as some warp queues its job; the warp that finishes the last leaf raises
@@ -787,6 +799,9 @@ __global__ void __launch_bounds__(128) k_sah_small(SahRec* rec0, SahRec* rec1, S
                 if(ns < 1024) ns += ns;
             }
         }
+#ifdef SAH_PROFILE
+        if(lane == 0 && got) atomicAdd(&st->prof[2], (unsigned long long)(clock64() - tw0));
+#endif
         got = __shfl_sync(FULL, got, 0);
         if(!got) return;
         __syncwarp();
@@ -802,10 +817,19 @@ __global__ void __launch_bounds__(128) k_sah_small(SahRec* rec0, SahRec* rec1, S
             if(m <= 32) {
                 float4 l = make_float4(0, 0, 0, 0), h = l;
                 if((unsigned)lane < m) l = __ldcg(&in[a + lane].lo), h = __ldcg(&in[a + lane].hi);
+#ifdef SAH_PROFILE
+                const long long t0 = clock64();
+#endif
                 subtree32(a, m, me, par, l, h, stage, stack, O, lane);
+#ifdef SAH_PROFILE
+                if(lane == 0) atomicAdd(&st->prof[0], (unsigned long long)(clock64() - t0)), atomicAdd(&st->prof[3], 1ull);
+#endif
                 if(lane == 0) leaves_add(st, m, total);
                 break;
             }
+#ifdef SAH_PROFILE
+            const long long tn0 = clock64();
+#endif
             if(!have_bounds) {
 #pragma unroll
                 for(int q = 0; q < 3; q++) cl[q] = SAH_BIG, ch[q] = -SAH_BIG;
@@ -906,6 +930,9 @@ __global__ void __launch_bounds__(128) k_sah_small(SahRec* rec0, SahRec* rec1, S
                 go_l = keep_left, go_r = !keep_left;
             }
             if(done_now && lane == 0) leaves_add(st, done_now, total);
+#ifdef SAH_PROFILE
+            if(lane == 0) atomicAdd(&st->prof[1], (unsigned long long)(clock64() - tn0));
+#endif
             if(!go_l && !go_r) break;
             const int side = go_l ? 0 : 1;
 #pragma unroll
@@ -1006,6 +1033,10 @@ int build_sah_split_device(gpurt_ctx* ctx, const float4* tri_lo, const float4* t
     if(hs->stalled || hs->leaves_done != hs->small_total)
         return set_error("SAH build: the small-segment queue stalled (" + std::to_string(hs->leaves_done) + " of " +
                          std::to_string(hs->small_total) + " leaves)"), GPURT_E_STATE;
+#ifdef SAH_PROFILE
+    fprintf(stderr, "[sah profile] n %u: <=32 subtrees %llu (%.1f Mcycles), larger nodes %.1f Mcycles, ticket waits of served warps %.1f Mcycles\n", n,
+            hs->prof[3], hs->prof[0] * 1e-6, hs->prof[1] * 1e-6, hs->prof[2] * 1e-6);
+#endif
     if(levels_out) *levels_out = levels;
     return GPURT_OK;
 }

@@ -242,9 +242,15 @@ def reference_arm(args, rank, world):
     c.frame, c.samples, c.max_frame, c.max_depth, c.integrator, c.brdf, c.use_rr = 0, 1, 1, 2, 1, 1, 0
     c.use_temporal, c.n_lights, c.n_objs = 1, scene.counts()["lights"], scene.counts()["objs"]
     rays = orc.frame_rays(rs, W, H, np.frombuffer(bytes(c), np.uint32), np.frombuffer(bytes(cam), np.uint32), 0, 2 * W * H)
-    stride = 8
-    sample = rays[::stride].copy()
     cores = orc.lib.orc_hw_threads()
+    # every ray of the step (the same config as the GPU arm) unless the whole run would then pass ~2 minutes: a probe on
+    # 1/16 of the rays sizes the sample
+    probe = rays[::16].copy()
+    t0 = time.time()
+    rs.bvh.closest_hit(probe, threads=cores)
+    est_full = (time.time() - t0) * 16.0
+    stride = max(1, int(np.ceil(est_full * (args.warmup + args.steps) / 120.0)))
+    sample = rays[::stride].copy()
     times = []
     for i in range(args.warmup + args.steps):
         t0 = time.time()
@@ -253,12 +259,13 @@ def reference_arm(args, rank, world):
             times.append(time.time() - t0)
     dt = float(np.mean(times))
     val = sample.shape[0] / dt / 1e6
-    what = f"every {stride}th of the {rays.shape[0]} closest-hit rays of the frame ({sample.shape[0]} rays per step)"
+    what = (f"all {rays.shape[0]} closest-hit rays of the frame per step" if stride == 1 else
+            f"every {stride}th of the {rays.shape[0]} closest-hit rays of the frame ({sample.shape[0]} rays per step)")
     line = {"impl": "reference", "metric": "Mrays/s closest-hit on Sponza", "value": val, "unit": "Mrays/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "sponza 1080p config-2 ray set (2,073,600 primary + 1-bounce rays), closest-hit",
-                       "scene": label, "sample": what},
+                       "scene": label, "rays_per_gpu": int(sample.shape[0]), "sample": what},
             "cpu_baseline": {"value": val, "unit": "Mrays/s", "cores": cores, "kind": "port",
                              "sample": what + f"; CPU LBVH build {build_s:.2f} s not included"},
             "e2e": {"value": val, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -739,6 +746,13 @@ def main():
                 "note": "the headline `value` uses the default build; `lbvh` = GPURT_BUILD_LBVH (round 1's only build)"}
         irr.close()
 
+    # ---- BASELINE configs 1 (cbox: random / coherent / shadow rays, closest points) and 3 (mis_test 1080p: MIS, ReSTIR) ---
+    configs13 = None
+    if world == 1:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import config13
+        configs13 = config13.run(ctx, flush, local)
+
     # ---- strong scaling at this N (configs 4 and 5) ---------------------------------------------
     strong = None
     if not args.no_strong:
@@ -781,7 +795,7 @@ def main():
                        "ms_per_frame": float(np.median(frame_ms)), "closest_rays": frame_rays[0], "any_rays": frame_rays[1],
                        "mrays_s": frame_rays[0] / (float(np.median(frame_ms)) * 1e-3) / 1e6,
                        "mpaths_s": W * H / (float(np.median(frame_ms)) * 1e-3) / 1e6},
-            "tree": tree, "placement": placement, "strong": strong, "host": host,
+            "tree": tree, "configs_1_and_3": configs13, "placement": placement, "strong": strong, "host": host,
             "clocks": clocks, "wall_s": wall,
         }
         print(json.dumps(line), flush=True)

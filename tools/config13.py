@@ -73,11 +73,13 @@ def median_ms(fn, ctx, flush, reps=10, warm=3):
     return float(np.median(ms)), float(min(ms))
 
 
-def main():
-    dev = torch.device("cuda", 0)
-    ctx = gpurt.Context(0)
+def run(ctx=None, flush=None, device=0):
+    """both configs on `ctx` (a fresh context on `device` if None); returns the result dict"""
+    dev = torch.device("cuda", device)
+    ctx = ctx or gpurt.Context(device)
     ctx.use_torch_stream()
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    if flush is None:
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     out = {}
 
     # ---- config 1 ------------------------------------------------------------------------------
@@ -130,7 +132,12 @@ def main():
                     "ms_first_frame": per_frame[0], "mpaths_s": W * H / (float(np.median(per_frame)) * 1e-3) / 1e6,
                     "closest_rays_last_frame": closest, "any_rays_last_frame": anyr}
     out["config3_mis_test_1080p"] = c3
-    print(json.dumps(out))
+    pipe.close(), accel.close(), scene.close()
+    return out
+
+
+def main():
+    print(json.dumps(run()))
 
 
 if __name__ == "__main__":

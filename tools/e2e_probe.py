@@ -26,13 +26,22 @@ if len(sys.argv) > 1:
     rays = torch.cat([pipe.bounce_rays(0), pipe.bounce_rays(1)]).cpu().pin_memory()
     hits = torch.empty((rays.shape[0], 4), dtype=torch.float32).pin_memory()
     hr, hh = rays.numpy(), hits.numpy().view(gpurt.HIT_DT).reshape(-1)
+    if os.environ.get("E2E_WC") == "1":   # rays in write-combined pinned memory
+        import ctypes as C
+        rt = C.CDLL("libcudart.so.12")
+        p = C.c_void_p()
+        assert rt.cudaHostAlloc(C.byref(p), C.c_size_t(hr.nbytes), C.c_uint(4)) == 0
+        wc = np.frombuffer((C.c_uint8 * hr.nbytes).from_address(p.value), np.float32).reshape(hr.shape)
+        wc[:] = hr
+        hr = wc
     for _ in range(3):
         accel.trace_closest(hr, hh)
     t0 = time.time()
     for _ in range(10):
         accel.trace_closest(hr, hh)
     dt = (time.time() - t0) / 10
-    print(f"chunk {os.environ.get('GPURT_HOST_CHUNK', 'default'):>8s}: {dt * 1e3:6.3f} ms  {rays.shape[0] / dt / 1e6:7.1f} Mrays/s")
+    print(f"chunk {os.environ.get('GPURT_HOST_CHUNK', 'default'):>8s} zero_copy {os.environ.get('GPURT_ZERO_COPY', '1')} wc {os.environ.get('E2E_WC', '0')}: "
+          f"{dt * 1e3:6.3f} ms  {rays.shape[0] / dt / 1e6:7.1f} Mrays/s")
 else:
     n = 112 << 20
     h = torch.empty(n, dtype=torch.uint8).pin_memory()

@@ -619,6 +619,7 @@ static int render_core(gpurt_pipe* p, const GpurtPipeParams* prm, const GpurtCam
     c.frame = forced_frame < 0 ? ++p->frame : forced_frame;
     F.W = w, F.H = h;
     F.seed_val = prm->seed ^ (uint32_t)c.frame;
+    F.spatial_samples = prm->spatial_samples > 0 ? (uint32_t)prm->spatial_samples : 0u, F.spatial_radius = prm->spatial_radius;
 
     F.band_rows = p->band_rows ? p->band_rows : h, F.n_shards = p->band_rows ? p->n_shards : 1, F.shard = p->band_rows ? p->shard : 0;
     {

@@ -74,6 +74,9 @@ struct FrameParams {
     /* multi-GPU sharding of the frame: this pipe renders the bands of `band_rows` rows whose
      * band index is congruent to `shard` modulo `n_shards`; (H, 1, 0) = the whole frame */
     uint32_t band_rows, n_shards, shard, n_local;
+    /* extension (GpurtPipeParams): ReSTIR spatial reuse; 0 samples = the reference's estimator */
+    uint32_t spatial_samples;
+    float spatial_radius;
 };
 
 /* i-th locally rendered pixel -> global pixel index y*W + x (RNG, image and G-buffers are indexed by
@@ -233,6 +236,7 @@ struct Shader {
     unsigned n_closest, n_any;
     /* deferred shadow ray of integrate_direct (render.cu's shadow stage): instead of tracing `visibility` inline the
      * segment and the term it gates are handed back, and k_shadow_resolve finishes the pixel */
+    uint32_t pix_x = 0, pix_y = 0; /* the pixel being shaded (spatial reuse looks around it) */
     bool defer_shadow = false, shadow_pending = false;
     F3 shadow_a, shadow_b, shadow_term;
 
@@ -919,6 +923,7 @@ struct Shader {
             new_res = temporal_res;
             break;
         }
+        if(first && P.spatial_samples > 0) spatial_reuse(new_res, hit, mat, shade);
         if(new_res.w != 0) {
             F3 dir = new_res.pos - hit.pos;
             F3 wi = normalize3(dir);
@@ -928,6 +933,39 @@ struct Shader {
             trace.acc = trace.acc + new_res.w * contrib * g;
         }
         prev_res = new_res;
+    }
+    /* Extension (include/gpurt.h GpurtPipeParams::spatial_samples; no reference counterpart): combine the pixel's reservoir
+     * with reservoirs of the previous frame from a disc around the pixel.  Neighbours are treated the way the temporal
+     * step treats prev_res (rt.rgen:489-497): their weight is re-derived at this shading point by update_weight, their
+     * history is capped at temporal_multiplier x the new samples, and they enter with pHat * W * M.  The survivor is
+     * tested for visibility once. */
+    SH_D void spatial_reuse(Reservoir& cur, const HitInfo& hit, const MatInfo& mat, const ShadeInfo& shade) {
+        Reservoir comb = res_new();
+        float cur_pHat = update_weight(cur, hit, mat, shade);
+        res_update(comb, cur_pHat * cur.w * (float)cur.n_seen, cur.pos, cur.normal, cur.emissive);
+        uint32_t total = cur.n_seen;
+        const uint32_t cap = P.cam.temporal_multiplier * P.cam.new_samples;
+        for(uint32_t i = 0; i < P.spatial_samples; i++) {
+            float r = P.spatial_radius * sqrtf(randf());
+            float phi = 2.0f * kPiGlsl * randf();
+            int qx = (int)pix_x + (int)floorf(r * dm_cos(phi) + 0.5f), qy = (int)pix_y + (int)floorf(r * dm_sin(phi) + 0.5f);
+            if(qx < 0 || qy < 0 || qx >= (int)P.W || qy >= (int)P.H) continue;
+            size_t q = (size_t)qy * P.W + (size_t)qx;
+            float4 np = X.ppos[q], nn = X.pnorm[q];
+            F3 d = F3{np.x, np.y, np.z} - hit.pos;
+            if(!(dot3(F3{nn.x, nn.y, nn.z}, shade.N) >= 0.9f)) continue;                    /* same orientation */
+            if(!(fabsf(dot3(d, shade.N)) <= 0.05f * sqrtf(dot3(d, d)) + 1.0e-3f)) continue; /* same plane */
+            Reservoir nb = res_load(X.prev_res + 3ull * q);
+            if(nb.n_seen == 0) continue;
+            float nb_pHat = update_weight(nb, hit, mat, shade);
+            nb.n_seen = cap < nb.n_seen ? cap : nb.n_seen;
+            res_update(comb, nb_pHat * nb.w * (float)nb.n_seen, nb.pos, nb.normal, nb.emissive);
+            total += nb.n_seen;
+        }
+        comb.n_seen = total;
+        float pHat = update_weight(comb, hit, mat, shade);
+        if(pHat != 0 && comb.w != 0 && visibility(hit.pos, comb.pos)) comb.w = 0;
+        cur = comb;
     }
     /* rt.rgen:507-549 */
     SH_D void integrate_restir(TraceInfo& trace, const HitInfo& hit, const MatInfo& mat, const ShadeInfo& shade, bool d_only, bool first) {
@@ -1052,7 +1090,7 @@ SH_D bool shade_step(const FrameParams& P, Shader& sh, TraceInfo& trace, uint32_
         gnorm[pix] = make_float4(shade.N.x, shade.N.y, shade.N.z, 1.0f);
         galb[pix] = make_float4(mat.albedo.x, mat.albedo.y, mat.albedo.z, 1.0f);
     }
-    if(restir && depth == 0) sh.prev_res = Shader::res_load(res_cur + 3ull * pix);
+    if(restir && depth == 0) sh.prev_res = Shader::res_load(res_cur + 3ull * pix), sh.pix_x = pix % P.W, sh.pix_y = pix / P.W;
     if(INTEG == 0) sh.integrate_direct(trace, hit, mat, shade);
     else if(INTEG == 1) sh.integrate_mats(trace, hit, mat, shade);
     else if(INTEG == 2) sh.integrate_mis(trace, hit, mat, shade);

@@ -269,6 +269,7 @@ int gpurt_pipe_params_default(GpurtPipeParams* p) { /* rt.h:38-53 */
     p->use_normal_map = 0, p->use_rr = 1, p->use_metalness = 0, p->use_qmc = 0, p->use_temporal = 1;
     p->integrator = 0, p->temporal_scale = 16, p->brdf = 0, p->debug_view = 0, p->res_samples = 4;
     p->seed = 0;
+    p->spatial_samples = 0, p->spatial_radius = 16.0f;
     return GPURT_OK;
 }
 

@@ -125,6 +125,13 @@ typedef struct GpurtPipeParams {
     int32_t use_normal_map, use_rr, use_metalness, use_qmc, use_temporal, integrator,
         temporal_scale, brdf, debug_view, res_samples;
     uint32_t seed; /* SURVEY Q1 */
+    /* Extension, off by default (no reference counterpart: todo.txt:10-12 "work on ReSTIR"): ReSTIR
+     * spatial reuse.  After the temporal combination of the frame's first sample the pixel's reservoir is combined with
+     * `spatial_samples` reservoirs of the PREVIOUS frame taken from a disc of `spatial_radius` pixels around it (neighbours
+     * whose previous-frame normal / plane disagree are skipped), and the surviving sample gets one visibility ray.  Changes
+     * the estimator (less noise per frame, slightly biased like any unshadowed-neighbour reuse), hence a flag. */
+    int32_t spatial_samples;
+    float spatial_radius;
 } GpurtPipeParams;
 
 typedef struct GpurtAccelInfo {

@@ -173,6 +173,8 @@ struct Invocation {
     Reservoir prev_res;
     const uint32_t* prev_res_buf;
     const float *ppos, *pnorm, *palb;
+    uint32_t spatial_samples = 0; /* extension, see orc_render_set_spatial */
+    float spatial_radius = 16.0f;
     uint64_t n_closest = 0, n_any = 0;
 
     /* rtcommon.glsl:111-124 */
@@ -699,6 +701,40 @@ struct Invocation {
             new_res = temporal_res;
             break;
         }
+        if(first && spatial_samples > 0) { /* extension, see orc_render_set_spatial */
+            /* the pixel's reservoir and `spatial_samples` reservoirs of the previous frame from a disc of `spatial_radius`
+             * pixels: each enters the way prev_res enters the temporal step (weight re-derived here, history capped) */
+            Reservoir comb = res_new();
+            float cur_pHat = update_weight(new_res, hit, mat, shade);
+            res_update(comb, cur_pHat * new_res.w * (float)new_res.n_seen, new_res.pos, new_res.normal, new_res.emissive);
+            uint32_t total = new_res.n_seen;
+            const uint32_t cap = cam->temporal_multiplier * cam->new_samples;
+            for(uint32_t i = 0; i < spatial_samples; i++) {
+                float r = spatial_radius * sqrtf(randf());
+                float phi = 2.0f * M_PI_F * randf();
+                int qx = (int)px + (int)floorf(r * dm_cos(phi) + 0.5f), qy = (int)py + (int)floorf(r * dm_sin(phi) + 0.5f);
+                if(qx < 0 || qy < 0 || qx >= (int)W || qy >= (int)H) continue;
+                size_t q = (size_t)qy * W + (size_t)qx;
+                vec3 npos = {ppos[4 * q], ppos[4 * q + 1], ppos[4 * q + 2]}, nnorm = {pnorm[4 * q], pnorm[4 * q + 1], pnorm[4 * q + 2]};
+                vec3 d = npos - hit.pos;
+                if(!(dot(nnorm, shade.N) >= 0.9f)) continue;
+                if(!(fabsf(dot(d, shade.N)) <= 0.05f * sqrtf(dot(d, d)) + 1.0e-3f)) continue;
+                const uint32_t* rr = prev_res_buf + 12ull * q;
+                Reservoir nb;
+                nb.pos = {u2f(rr[0]), u2f(rr[1]), u2f(rr[2])}, nb.w_sum = u2f(rr[3]);
+                nb.normal = {u2f(rr[4]), u2f(rr[5]), u2f(rr[6])}, nb.w = u2f(rr[7]);
+                nb.emissive = {u2f(rr[8]), u2f(rr[9]), u2f(rr[10])}, nb.n_seen = rr[11];
+                if(nb.n_seen == 0) continue;
+                float nb_pHat = update_weight(nb, hit, mat, shade);
+                nb.n_seen = cap < nb.n_seen ? cap : nb.n_seen;
+                res_update(comb, nb_pHat * nb.w * (float)nb.n_seen, nb.pos, nb.normal, nb.emissive);
+                total += nb.n_seen;
+            }
+            comb.n_seen = total;
+            float pHat = update_weight(comb, hit, mat, shade);
+            if(pHat != 0 && comb.w != 0 && visibility(hit.pos, comb.pos)) comb.w = 0;
+            new_res = comb;
+        }
         if(new_res.w != 0) {
             vec3 dir = new_res.pos - hit.pos;
             vec3 wi = normalize(dir);
@@ -864,6 +900,12 @@ void orc_record_rays(float* rays8, uint64_t capacity) {
 }
 uint64_t orc_recorded_rays(void) { return std::min<uint64_t>(g_rec_count.load(), g_rec_cap); }
 
+/* Extension shared with the product (include/gpurt.h GpurtPipeParams::spatial_samples / spatial_radius; NOT part of the
+ * reference): ReSTIR spatial reuse.  0 samples = rt.rgen as written.  Set before orc_render_frame. */
+static uint32_t g_spatial_samples = 0;
+static float g_spatial_radius = 16.0f;
+void orc_render_set_spatial(uint32_t samples, float radius) { g_spatial_samples = samples, g_spatial_radius = radius; }
+
 void orc_render_frame(const orc_scene* S, const uint32_t* consts, const uint32_t* camera, uint32_t w,
                       uint32_t h, uint32_t seed, float* image, const uint32_t* prev_res,
                       uint32_t* out_res, const float* ppos, const float* pnorm, const float* palb,
@@ -883,6 +925,7 @@ void orc_render_frame(const orc_scene* S, const uint32_t* consts, const uint32_t
                     Invocation inv;
                     inv.S = S, inv.c = &c, inv.cam = &cam, inv.W = w, inv.H = h, inv.px = x, inv.py = y;
                     inv.prev_res_buf = prev_res, inv.ppos = ppos, inv.pnorm = pnorm, inv.palb = palb;
+                    inv.spatial_samples = g_spatial_samples, inv.spatial_radius = g_spatial_radius;
                     inv.main_(seed_val, image, out_res, pos, norm, alb);
                     nc[t] += inv.n_closest, na[t] += inv.n_any;
                 }

@@ -30,6 +30,9 @@ void orc_scene_free(orc_scene*);
  * image: RGBA32F in/out (progressive accumulation, rt.rgen:638-645).
  * reservoirs: 12 words each {pos.xyz,w_sum, normal.xyz,w, emissive.xyz,n_seen}; prev_* are the
  * previous frame's buffers (read), out_* this frame's (written). G-buffers RGBA32F. */
+/* Extension shared with the product (GpurtPipeParams::spatial_samples / spatial_radius, NOT in the reference): ReSTIR spatial
+ * reuse for the following orc_render_frame calls; 0 samples (the default) = rt.rgen as written. */
+void orc_render_set_spatial(uint32_t samples, float radius);
 void orc_render_frame(const orc_scene* S, const uint32_t* consts, const uint32_t* camera, uint32_t w,
                       uint32_t h, uint32_t seed, float* image, const uint32_t* prev_res,
                       uint32_t* out_res, const float* ppos, const float* pnorm, const float* palb,

@@ -631,6 +631,11 @@ void emu_light_pdf(void* bvh, const EmuFrameArgs* A, const float* rays6, unsigne
     }
 }
 
+/* ReSTIR spatial-reuse extension of the following emu_render_frame calls (GpurtPipeParams::spatial_samples / spatial_radius) */
+static uint32_t g_spatial_samples = 0;
+static float g_spatial_radius = 16.0f;
+void emu_set_spatial(uint32_t samples, float radius) { g_spatial_samples = samples, g_spatial_radius = radius; }
+
 void emu_render_frame(void* bvh, const EmuFrameArgs* A, const uint32_t* consts, const uint32_t* camera, uint32_t w, uint32_t h,
                       uint32_t seed_val, float* image, const uint32_t* prev_res, uint32_t* out_res, const float* ppos,
                       const float* pnorm, const float* palb, float* pos, float* norm, float* alb,
@@ -650,6 +655,7 @@ void emu_render_frame(void* bvh, const EmuFrameArgs* A, const uint32_t* consts, 
     std::memcpy(&P.cam, camera, sizeof(P.cam));
     P.W = w, P.H = h, P.seed_val = seed_val;
     P.band_rows = h, P.n_shards = 1, P.shard = 0, P.n_local = w * h;
+    P.spatial_samples = g_spatial_samples, P.spatial_radius = g_spatial_radius;
     ShadeCtx X{};
     fill_ctx(E, A, X);
     std::vector<float4> lboxes;

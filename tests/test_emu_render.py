@@ -126,6 +126,34 @@ def test_cbox_all_integrators(emu, orc, gpurt, integrator):
         assert img[..., :3].mean() > 0.01
 
 
+def test_restir_spatial_reuse_extension(emu, orc, gpurt):
+    """GpurtPipeParams::spatial_samples (no reference counterpart, off by default): the product's code and the oracle's
+    restatement of the extension agree bit for bit over frames with temporal + spatial reuse, and 0 samples is the
+    reference's estimator"""
+    s = gpurt.Scene(None).load(os.path.join(MEDIA, "cbox", "cbox.gltf"))
+    es = EmuScene(emu, orc, s, ())
+    emu.emu_set_spatial.argtypes = [C.c_uint32, C.c_float]
+    images = {}
+    for spatial in ((0, 16.0), (3, 6.0)):
+        a, b = orc.FrameState(64, 36), orc.FrameState(64, 36)
+        cam = gpurt.camera(0, 64, 36)
+        for integ in (3, 4):
+            for f in range(4):
+                consts, ubo, seed = _uniforms(gpurt, es.rs, cam, f, integrator=integ, brdf=1, samples_per_frame=2, max_depth=3,
+                                              res_samples=4, use_temporal=1, temporal_scale=16, seed=90 + integ)
+                emu.emu_set_spatial(*spatial)
+                ce = es.render_frame(a, consts, ubo, seed ^ f)
+                co = orc.render_frame(es.rs, b, consts, ubo, seed, spatial=spatial)
+                assert (a.image.view(np.uint32) == b.image.view(np.uint32)).all(), f"spatial {spatial} integrator {integ} frame {f}: image"
+                assert (a.res[a.parity ^ 1] == b.res[b.parity ^ 1]).all()
+                assert tuple(int(x) for x in ce) == tuple(int(x) for x in co)
+        images[spatial[0]] = a.image.copy()
+    emu.emu_set_spatial(0, 16.0)
+    orc.lib.orc_render_set_spatial(0, 16.0)
+    assert not (images[0].view(np.uint32) == images[3].view(np.uint32)).all()    # the extension does something
+    es.close()
+
+
 def test_mis_test_scene(emu, orc, gpurt):
     s = gpurt.Scene(None).load(os.path.join(MEDIA, "mis_test", "mis_test.gltf"))
     cam = gpurt.camera(1, 80, 45, (0.5, 0.6, 2.6), (0.5, 0.45, 0.0), 50.0)

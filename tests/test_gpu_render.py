@@ -38,6 +38,7 @@ def _run(gpurt, orc, ctx, scene_name, w, h, frames, cam=None, textures=(), scene
     rs = orc.RenderScene(scene, textures)
     st = orc.FrameState(w, h)
     prm = gpurt.pipe_params(**params)
+    spatial = (params.get("spatial_samples", 0), params.get("spatial_radius", 16.0))
     cam = cam or gpurt.camera(0, w, h)
     worst = 0.0
     for f in range(frames):
@@ -45,7 +46,7 @@ def _run(gpurt, orc, ctx, scene_name, w, h, frames, cam=None, textures=(), scene
         consts, ubo, seed_word = pipe.last_uniforms()
         # frame counter: 0, 0, 1, 2, ... (the second call resets: old_cam was never assigned, rt.cpp:132-135)
         assert consts[8] == max(0, f - 1)
-        counts = orc.render_frame(rs, st, consts, ubo, seed_word ^ int(consts[8]))  # oracle xors the frame itself
+        counts = orc.render_frame(rs, st, consts, ubo, seed_word ^ int(consts[8]), spatial=spatial)  # oracle xors the frame itself
         worst = max(worst, _compare(f"{scene_name} frame {f} image", pipe.read_image(), st.image))
         for g in range(3):
             _compare(f"{scene_name} frame {f} gbuffer {g}", pipe.read_gbuffer(g), st.gb[st.parity ^ 1][g])
@@ -110,6 +111,43 @@ def test_config3_full_size_1080p(gpurt, orc, ctx):
          res_samples=4, use_temporal=1, temporal_scale=16, seed=8)
     _run(gpurt, orc, ctx, "mis_test", 1920, 1080, 5, cam=cam, integrator=4, brdf=1, samples_per_frame=1, max_depth=4,
          res_samples=4, use_temporal=1, temporal_scale=16, seed=9)
+
+
+def test_restir_spatial_reuse_extension(gpurt, orc, ctx):
+    """GpurtPipeParams::spatial_samples / spatial_radius (extension, off by default, SURVEY §8f rank 4): CUDA frames ==
+    the oracle's restatement of the extension over frames with temporal + spatial reuse (image, G-buffers, reservoirs,
+    ray counts); and the estimator it changes stays an estimator of the same image: against a converged render of the
+    reference's estimator (MIS, 256 spp) the mean of 8 frames with spatial reuse is not further away than the
+    reference's ReSTIR mean by more than 10 % RMSE, and its mean radiance agrees within 3 %"""
+    for integ in (3, 4):
+        _run(gpurt, orc, ctx, "cbox", 160, 90, 5, integrator=integ, brdf=1, samples_per_frame=2, max_depth=3, res_samples=4,
+             use_temporal=1, temporal_scale=16, seed=40 + integ, spatial_samples=4, spatial_radius=8.0)
+    cam = gpurt.camera(1, 160, 90, (0.5, 0.6, 2.6), (0.5, 0.45, 0.0), 50.0)
+    _run(gpurt, orc, ctx, "mis_test", 160, 90, 4, cam=cam, integrator=3, brdf=0, samples_per_frame=1, max_depth=4,
+         res_samples=4, use_temporal=1, temporal_scale=16, seed=8, spatial_samples=3, spatial_radius=20.0)
+
+    scene = load_scene(gpurt, ctx, "cbox")
+    accel = gpurt.Accel(scene)
+    w, h = 160, 90
+
+    def mean_image(frames, **params):
+        pipe = gpurt.RTPipe(scene, accel)
+        prm = gpurt.pipe_params(**params)
+        for _ in range(frames + 1):   # the pipe's start-up renders frame 0 twice (rt.cpp:132-135): accumulation restarts
+            assert pipe.render_frame(prm, gpurt.camera(0, w, h), w, h) == 0
+        img = pipe.read_image()[..., :3].astype(np.float64)
+        pipe.close()
+        return img
+
+    ref = mean_image(32, integrator=2, brdf=0, samples_per_frame=8, max_depth=1, seed=5)
+    base = mean_image(8, integrator=3, brdf=0, samples_per_frame=1, max_depth=1, res_samples=4, use_temporal=1, temporal_scale=16, seed=6)
+    spat = mean_image(8, integrator=3, brdf=0, samples_per_frame=1, max_depth=1, res_samples=4, use_temporal=1, temporal_scale=16, seed=6,
+                      spatial_samples=4, spatial_radius=8.0)
+    accel.close()
+    rm = lambda a: float(np.sqrt(((a - ref) ** 2).mean()))
+    assert np.isfinite(spat).all() and not np.array_equal(base, spat)
+    assert abs(spat.mean() - ref.mean()) <= 0.03 * ref.mean(), (spat.mean(), base.mean(), ref.mean())
+    assert rm(spat) <= 1.10 * rm(base), (rm(spat), rm(base))
 
 
 def test_options_qmc_metalness_rr_off_depth1(gpurt, orc, ctx):

@@ -50,6 +50,12 @@ struct gpurt_pipe {
     uint64_t last_counts[2] = {0, 0};
     uint32_t max_counts = 0;
     uint32_t band_rows = 0, n_shards = 1, shard = 0; /* gpurt_pipe_set_shard; 0 = whole frame */
+    /* res[] and gbuf[][] live in one block (exportable as a whole, gpurt_pipe_history_export):
+     * [kHistHeader: flag of shard s at byte 128*s, time-out counter at byte 8192][parity 0: res 48n, pos, normal, albedo 16n each][parity 1] */
+    char* hist = nullptr;
+    char** d_peers = nullptr;                         /* device array [64]: history blocks of all shards (own entry = hist) */
+    uint32_t n_peers = 0, halo_rows = 0xFFFFFFFFu;    /* gpurt_pipe_history_peers; 0 peers = no exchange */
+    uint32_t hist_seq = 0;                            /* frames pushed so far (= the flag value peers wait for) */
     uint32_t wave_depth = 0;                          /* bounces run as wavefronts before k_tail; 0 = by size */
     /* queue sizes of the previous frame, copied back without a sync and used to size this frame's launches */
     uint32_t* h_counts = nullptr;                     /* pinned */
@@ -293,6 +299,65 @@ __global__ void __launch_bounds__(256) k_frame_end(const __grid_constant__ Frame
     pixel_end(P, shard_pixel(P, li), acc, image, gpos, gnorm, ppos, pnorm, palb, mean_out);
 }
 
+/* ---- ReSTIR on a sharded frame: the previous frame travels between the shards' history blocks over peer memory ---- */
+constexpr size_t kHistHeader = 16384;
+constexpr uint32_t kHistMaxShards = 64;
+
+/* One float4 per thread of the rows this shard rendered (reservoirs, position, normal, albedo of the frame just
+ * finished), stored to the same offset of every shard that will read the row next frame.  Row-major over the local rows,
+ * so loads and remote stores are fully coalesced. */
+__global__ void __launch_bounds__(256) k_history_push(const __grid_constant__ FrameParams P, uint32_t halo, const char* own,
+                                                      char* const* __restrict__ peers, size_t parity_off, uint32_t local_rows) {
+    const size_t per_row = 6ull * P.W;
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if(idx >= per_row * local_rows) return;
+    uint32_t j = (uint32_t)(idx / per_row), o = (uint32_t)(idx - (size_t)j * per_row);
+    uint32_t y = shard_row(P, j);
+    if(y >= P.H) return;
+    unsigned long long readers = history_row_readers(P, y, halo) & ~(1ull << P.shard);
+    if(!readers) return;
+    const size_t n = (size_t)P.W * P.H;
+    size_t off;
+    if(o < 3u * P.W) off = 3ull * y * P.W + o;
+    else {
+        uint32_t g = o / P.W - 3u, x = o - (g + 3u) * P.W;
+        off = (3ull + g) * n + (size_t)y * P.W + x;
+    }
+    float4 v = ((const float4*)(own + parity_off))[off];
+    while(readers) {
+        int s = __ffsll((long long)readers) - 1;
+        readers &= readers - 1;
+        ((float4*)(peers[s] + parity_off))[off] = v;
+    }
+    __threadfence_system();
+}
+/* "this shard's rows of frame number `seq` are in your block" — after k_history_push in stream order */
+__global__ void k_history_signal(char* const* __restrict__ peers, uint32_t n_shards, uint32_t shard, uint32_t seq) {
+    uint32_t s = threadIdx.x;
+    if(s >= n_shards || !peers[s]) return;
+    __threadfence_system();
+    *(volatile uint32_t*)(peers[s] + 128ull * shard) = seq;
+}
+/* wait until every shard has delivered `seq` frames (also means: every shard is done reading the buffers this frame is
+ * about to overwrite).  Gives up after 20 s and counts the time-out instead of hanging the device. */
+__global__ void k_history_wait(char* own, uint32_t n_shards, uint32_t seq) {
+    uint32_t s = threadIdx.x;
+    if(s >= n_shards) return;
+    const volatile uint32_t* f = (const volatile uint32_t*)(own + 128ull * s);
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while((int32_t)(*f - seq) < 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if(t - t0 > 20000000000ull) {
+            atomicAdd((uint32_t*)(own + 8192), 1u);
+            break;
+        }
+        __nanosleep(100);
+    }
+    __threadfence_system();
+}
+
 /* tonemap.frag:17-48 followed by the R8G8B8A8_SRGB framebuffer encode (gpurt.cpp:176) */
 __global__ void __launch_bounds__(256) k_tonemap(const float4* __restrict__ img, uint32_t n, int op, float exposure,
                                                  float gamma, uchar4* __restrict__ out) {
@@ -322,8 +387,7 @@ __global__ void __launch_bounds__(256) k_tonemap(const float4* __restrict__ img,
 }
 
 static int pipe_free(gpurt_pipe* p) {
-    void* ptrs[] = {p->image, p->res[0], p->res[1], p->gbuf[0][0], p->gbuf[0][1], p->gbuf[0][2], p->gbuf[1][0],
-                    p->gbuf[1][1], p->gbuf[1][2], p->acc, p->pathA, p->pathB, p->rays[0], p->rays[1], p->hits,
+    void* ptrs[] = {p->image, p->hist, p->d_peers, p->acc, p->pathA, p->pathB, p->rays[0], p->rays[1], p->hits,
                     p->queue[0], p->queue[1], p->counts, p->ray_counts, p->lgrp, p->lgrp_off, p->lverts, p->lvert_off};
     for(void* q : ptrs)
         if(q) cudaFree(q);
@@ -353,10 +417,16 @@ static int pipe_resize_impl(gpurt_pipe* p, uint32_t w, uint32_t h, uint32_t max_
     int rc;
     if(dims) {
         if((rc = alloc(p->image, n * 16))) return rc;
+        p->n_peers = 0, p->hist_seq = 0; /* a new block: the shards exchange handles again (gpurt_pipe_history_export) */
         for(int k = 0; k < 2; k++) {
-            if((rc = alloc(p->res[k], n * 48))) return rc;
-            for(int g = 0; g < 3; g++)
-                if((rc = alloc(p->gbuf[k][g], n * 16))) return rc;
+            p->res[k] = nullptr;
+            for(int g = 0; g < 3; g++) p->gbuf[k][g] = nullptr;
+        }
+        if((rc = alloc(p->hist, kHistHeader + 2 * n * 96))) return rc;
+        for(int k = 0; k < 2; k++) {
+            char* base = p->hist + kHistHeader + (size_t)k * n * 96;
+            p->res[k] = (float4*)base;
+            for(int g = 0; g < 3; g++) p->gbuf[k][g] = (float4*)(base + n * 48 + (size_t)g * n * 16);
             if((rc = alloc(p->rays[k], n * 32))) return rc;
             if((rc = alloc(p->queue[k], n * 4))) return rc;
         }
@@ -567,6 +637,58 @@ int gpurt_pipe_set_shard(gpurt_pipe* p, uint32_t band_rows, uint32_t n_shards, u
     p->band_rows = band_rows, p->n_shards = band_rows ? n_shards : 1, p->shard = band_rows ? shard : 0;
     return GPURT_OK;
 }
+/* ReSTIR on a sharded frame: every shard keeps the whole previous frame (G-buffers + reservoirs) because the temporal
+ * pass reprojects into it (rt.rgen:454-472); each shard stores the rows it rendered into the other shards' blocks. */
+int gpurt_pipe_history_export(gpurt_pipe* p, uint32_t w, uint32_t h, void** out_ptr, uint8_t* handle, uint64_t* out_bytes) {
+    if(!p || !w || !h) return set_error("bad argument"), GPURT_E_INVALID;
+    GPURT_CUDA(cudaSetDevice(p->ctx->device));
+    int rc = pipe_resize(p, w, h, 0);
+    if(rc) return rc;
+    if(out_ptr) *out_ptr = p->hist;
+    if(out_bytes) *out_bytes = kHistHeader + 2ull * w * h * 96;
+    if(handle) {
+        cudaIpcMemHandle_t hd;
+        cudaError_t e = cudaIpcGetMemHandle(&hd, p->hist);
+        if(e != cudaSuccess) return set_error(std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e)), GPURT_E_CUDA;
+        memcpy(handle, &hd, sizeof hd);
+    }
+    return GPURT_OK;
+}
+int gpurt_pipe_history_peers(gpurt_pipe* p, uint32_t n, void* const* blocks, uint32_t halo_rows) {
+    if(!p) return set_error("NULL argument"), GPURT_E_INVALID;
+    if(n == 0) {
+        p->n_peers = 0;
+        return GPURT_OK;
+    }
+    if(!blocks || !p->band_rows || n != p->n_shards || n > kHistMaxShards)
+        return set_error("history_peers: one block per shard of gpurt_pipe_set_shard (at most 64)"), GPURT_E_INVALID;
+    if(!p->hist) return set_error("history_peers: call gpurt_pipe_history_export first"), GPURT_E_STATE;
+    GPURT_CUDA(cudaSetDevice(p->ctx->device));
+    cudaStream_t st = p->ctx->stream;
+    if(!p->d_peers) GPURT_CUDA(cudaMalloc((void**)&p->d_peers, kHistMaxShards * sizeof(char*)));
+    char* host[kHistMaxShards] = {};
+    for(uint32_t s = 0; s < n; s++) {
+        host[s] = s == p->shard ? p->hist : (char*)blocks[s];
+        if(!host[s]) return set_error("history_peers: NULL block"), GPURT_E_INVALID;
+    }
+    GPURT_CUDA(cudaMemcpyAsync(p->d_peers, host, sizeof host, cudaMemcpyHostToDevice, st));
+    GPURT_CUDA(cudaStreamSynchronize(st)); /* `host` leaves scope */
+    p->n_peers = n, p->halo_rows = halo_rows;
+    return GPURT_OK;
+}
+int gpurt_pipe_history_status(gpurt_pipe* p, uint32_t* out_frames_pushed, uint32_t* out_timeouts) {
+    if(!p) return set_error("NULL argument"), GPURT_E_INVALID;
+    if(out_frames_pushed) *out_frames_pushed = p->hist_seq;
+    if(out_timeouts) {
+        *out_timeouts = 0;
+        if(p->hist) {
+            GPURT_CUDA(cudaSetDevice(p->ctx->device));
+            GPURT_CUDA(cudaStreamSynchronize(p->ctx->stream));
+            GPURT_CUDA(cudaMemcpy(out_timeouts, p->hist + 8192, 4, cudaMemcpyDeviceToHost));
+        }
+    }
+    return GPURT_OK;
+}
 int gpurt_pipe_frame_index(const gpurt_pipe* p, int32_t* f) {
     if(!p || !f) return set_error("NULL argument"), GPURT_E_INVALID;
     *f = p->frame;
@@ -628,13 +750,29 @@ static int render_core(gpurt_pipe* p, const GpurtPipeParams* prm, const GpurtCam
         F.n_local = n_local;
     }
     const uint32_t n = F.n_local; /* pixels rendered by this pipe */
+    const int cur = p->parity, prev = cur ^ 1; /* bind_temporal_stuff ping-pong (rt.cpp:222-344) */
+    const bool restir = c.integrator == 3 || c.integrator == 4;
+    /* ReSTIR on a sharded frame: wait for the other shards' rows of the previous frame before reading them, and hand
+     * this frame's rows over at the end (gpurt_pipe_history_peers) */
+    const bool exchange = restir && p->band_rows && p->n_peers && !mean_out;
+    auto history_wait = [&] {
+        if(exchange && p->hist_seq > 0) k_history_wait<<<1, kHistMaxShards, 0, st>>>(p->hist, F.n_shards, p->hist_seq);
+    };
+    auto history_push = [&] {
+        if(!exchange) return;
+        const uint32_t local_rows = n / w;
+        const size_t parity_off = kHistHeader + (size_t)cur * w * h * 96;
+        if(local_rows)
+            k_history_push<<<cdivu((size_t)local_rows * 6 * w, 256), 256, 0, st>>>(F, p->halo_rows, p->hist, p->d_peers, parity_off, local_rows);
+        k_history_signal<<<1, kHistMaxShards, 0, st>>>(p->d_peers, F.n_shards, F.shard, ++p->hist_seq);
+    };
     if(n == 0) { /* more shards than bands: nothing to do on this rank */
+        history_wait(), history_push();
+        GPURT_CUDA(cudaGetLastError());
         p->parity ^= 1;
         p->last = F;
         return GPURT_OK;
     }
-    const int cur = p->parity, prev = cur ^ 1; /* bind_temporal_stuff ping-pong (rt.cpp:222-344) */
-    const bool restir = c.integrator == 3 || c.integrator == 4;
     ShadeCtx X;
     X.S = p->accel->dscene;
     X.nodes = (const float4*)p->accel->nodes, X.tris = p->accel->tri_wide, X.n_nodes = p->accel->n_nodes;
@@ -658,6 +796,7 @@ static int render_core(gpurt_pipe* p, const GpurtPipeParams* prm, const GpurtCam
 
     GPURT_CUDA(cudaEventRecord(ctx->ev0, st));
     GPURT_CUDA(cudaMemsetAsync(p->ray_counts, 0, 16, st));
+    history_wait();
     k_frame_begin<<<cdivu(n, 256), 256, 0, st>>>(F, restir ? 1 : 0, p->acc, p->pathB, p->gbuf[cur][0],
                                                 p->gbuf[cur][1], p->gbuf[cur][2], p->res[cur]);
     /* integrate_direct and the direct-only ReSTIR end every path at its first hit (rt.rgen:393, :548): the queues of
@@ -744,6 +883,7 @@ static int render_core(gpurt_pipe* p, const GpurtPipeParams* prm, const GpurtCam
         GPURT_CUDA(cudaEventRecord(p->ev_counts, st));
         p->counts_pending = true;
     }
+    history_push();
     GPURT_CUDA(cudaEventRecord(ctx->ev1, st));
     GPURT_CUDA(cudaGetLastError());
     p->parity ^= 1;

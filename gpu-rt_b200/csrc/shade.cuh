@@ -103,6 +103,26 @@ SH_D uint32_t shard_pixel(const FrameParams& P, uint32_t i) {
     return (band * P.n_shards + P.shard) * per_band + in_band;
 }
 
+/* j-th locally rendered row (bands in ascending order, rows inside a band in ascending order) -> image row */
+SH_D uint32_t shard_row(const FrameParams& P, uint32_t j) {
+    uint32_t band = j / P.band_rows;
+    return (band * P.n_shards + P.shard) * P.band_rows + (j - band * P.band_rows);
+}
+/* ReSTIR on a sharded frame (gpurt_pipe_history_peers): which shards read row y of the previous frame's G-buffers and
+ * reservoirs when their temporal / spatial look-ups stay within `halo` rows of the pixel being shaded — every shard that
+ * owns a row of [y - halo, y + halo].  Bit s of the result = shard s; the owner's own bit is included.
+ * halo = 0xFFFFFFFF: every shard (any camera motion).  n_shards <= 64. */
+SH_D unsigned long long history_row_readers(const FrameParams& P, uint32_t y, uint32_t halo) {
+    const unsigned long long all = P.n_shards >= 64u ? ~0ull : ((1ull << P.n_shards) - 1ull);
+    if(halo == 0xFFFFFFFFu) return all;
+    uint32_t y0 = y > halo ? y - halo : 0u, y1 = y + halo < P.H - 1u ? y + halo : P.H - 1u;
+    uint32_t b0 = y0 / P.band_rows, b1 = y1 / P.band_rows;
+    if(b1 - b0 + 1u >= P.n_shards) return all;
+    unsigned long long m = 0;
+    for(uint32_t b = b0; b <= b1; b++) m |= 1ull << (b % P.n_shards);
+    return m;
+}
+
 struct Reservoir { /* restir.glsl:2-9; stored as 3 float4: pos|w_sum, normal|w, emissive|n_seen */
     F3 pos, normal, emissive;
     float w_sum, w;

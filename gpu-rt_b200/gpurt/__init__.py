@@ -18,6 +18,7 @@ LIB_PATH = os.environ.get("GPURT_LIB") or os.path.join(os.path.dirname(_HERE), "
 
 MEM_HOST, MEM_DEVICE = 0, 1
 NO_HIT = 0xFFFFFFFF
+HISTORY_ALL_ROWS = 0xFFFFFFFF
 BUILD_DEFAULT, BUILD_KEEP_BVH2, BUILD_SAH_COLLAPSE, BUILD_SAH_SPLIT, BUILD_LBVH = 0, 1, 2, 4, 8
 
 RAY_DT = np.dtype([("o", "<f4", 3), ("tmin", "<f4"), ("d", "<f4", 3), ("tmax", "<f4")])
@@ -91,6 +92,7 @@ SYMBOLS = [
     "gpurt_pipe_render_frame", "gpurt_pipe_frame_index", "gpurt_pipe_read_image", "gpurt_pipe_read_gbuffer",
     "gpurt_pipe_ray_counts", "gpurt_pipe_device_image", "gpurt_tonemap", "gpurt_pipe_last_uniforms",
     "gpurt_pipe_read_reservoirs", "gpurt_pipe_bounce_rays", "gpurt_pipe_set_shard",
+    "gpurt_pipe_history_export", "gpurt_pipe_history_peers", "gpurt_pipe_history_status",
     "gpurt_pipe_render_frame_mean", "gpurt_pipe_accumulate_mean", "gpurt_scene_set_transform", "gpurt_accel_update", "gpurt_scene_get_texture", "gpurt_shared_alloc", "gpurt_shared_free", "gpurt_shared_open", "gpurt_shared_close",
     "gpurt_scene_set_material", "gpurt_scene_set_ordered", "gpurt_scene_clear_textures", "gpurt_accel_sync_scene", "gpurt_accel_refit", "gpurt_accel_update_auto",
 ]
@@ -451,6 +453,24 @@ class RTPipe:
     def set_shard(self, band_rows, n_shards, shard):
         """render only row bands with (band index % n_shards) == shard; band_rows=0: whole frame"""
         _check(lib.gpurt_pipe_set_shard(self.h, band_rows, n_shards, shard))
+
+    def history_export(self, w, h):
+        """(device pointer, 64-byte handle, bytes) of this shard's previous-frame block (gpurt_pipe_history_export)"""
+        p, hd, nb = C.c_void_p(), (C.c_uint8 * 64)(), C.c_uint64()
+        _check(lib.gpurt_pipe_history_export(self.h, w, h, C.byref(p), hd, C.byref(nb)))
+        return p.value, bytes(hd), nb.value
+
+    def history_peers(self, blocks, halo_rows=HISTORY_ALL_ROWS):
+        """blocks[s] = device pointer of shard s's history block as mapped in this process (own entry ignored);
+        [] switches the exchange off"""
+        arr = (C.c_void_p * max(1, len(blocks)))(*[C.c_void_p(b or 0) for b in blocks])
+        _check(lib.gpurt_pipe_history_peers(self.h, len(blocks), arr, C.c_uint32(halo_rows)))
+
+    def history_status(self):
+        """(frames pushed to the peers, flag waits that timed out)"""
+        a, b = C.c_uint32(), C.c_uint32()
+        _check(lib.gpurt_pipe_history_status(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def device_image(self):
         """torch view (H,W,4) of rt_target in device memory (no copy)"""

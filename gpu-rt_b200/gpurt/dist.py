@@ -62,3 +62,22 @@ def gather_to_rank0(local, counts=None):
     if local.shape[0]:
         dist.send(local.contiguous(), dst=0)
     return None
+
+
+def share_history(pipe, ctx, w, h, halo_rows=0xFFFFFFFF):
+    """ReSTIR on a frame sharded over the ranks (include/gpurt.h, gpurt_pipe_history_peers): every rank exports the block
+    holding its previous-frame G-buffers + reservoirs, maps the other ranks' blocks over NVLink and hands the mappings to
+    its pipe; from then on each rendered frame ends with the rank's rows stored into the peers' blocks and a flag, and
+    begins by waiting for the peers' flags — no host synchronisation or collective per frame.  Call after
+    pipe.set_shard(...) and again whenever the frame size changes.  Returns the mappings (keep them alive; close them
+    after the pipe)."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return []
+    world, rank = dist.get_world_size(), dist.get_rank()
+    _, handle, nbytes = pipe.history_export(w, h)
+    handles = [None] * world
+    dist.all_gather_object(handles, handle)
+    maps = [None if r == rank else ctx.shared_open(handles[r], nbytes) for r in range(world)]
+    pipe.history_peers([0 if m is None else m.ptr for m in maps], halo_rows)
+    dist.barrier()   # nobody renders into a block that is not mapped everywhere yet
+    return [m for m in maps if m is not None]

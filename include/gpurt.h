@@ -318,8 +318,30 @@ int gpurt_pipe_frame_index(const gpurt_pipe* pipe, int32_t* out_frame);
  * bands of `band_rows` rows whose band index is congruent to `shard` modulo `n_shards`.  RNG streams,
  * image and G-buffers stay indexed by the global pixel, so the union of all shards is bit-identical to
  * an unsharded frame (integrators 0-2; ReSTIR's temporal pass reads neighbouring pixels of the previous
- * frame and needs the whole previous frame on the rank).  band_rows = 0 restores whole-frame rendering. */
+ * frame and needs the whole previous frame on the rank: gpurt_pipe_history_peers below).  band_rows = 0 restores
+ * whole-frame rendering. */
 int gpurt_pipe_set_shard(gpurt_pipe* pipe, uint32_t band_rows, uint32_t n_shards, uint32_t shard);
+/* ReSTIR (integrators 3, 4) on a sharded frame (SURVEY §8e "halo exchange or all-gather of the previous frame"; the temporal
+ * pass reprojects the hit point into the previous frame, rt.rgen:454-472, and reads G-buffers + reservoir there): every
+ * shard keeps buffers for the whole frame and, at the end of a frame, stores the rows it rendered straight into the other
+ * shards' buffers over peer memory (NVLink), then raises a per-shard flag there; the next frame's first kernel waits for the
+ * flags.  No host synchronisation and no collective library call per frame; frames stay asynchronous on the context's stream.
+ *   1. every shard: gpurt_pipe_set_shard, then gpurt_pipe_history_export(w, h) -> its history block (device pointer, 64-byte
+ *      IPC handle to ship to the other processes, size).  The block is re-allocated when the frame size changes: export again.
+ *   2. every shard: gpurt_pipe_history_peers(n_shards, blocks[shard index], halo_rows) with the other shards' blocks mapped
+ *      by gpurt_shared_open (or plain device pointers inside one process); the own entry is ignored.
+ *      halo_rows = GPURT_HISTORY_ALL_ROWS: every shard receives every row — bit-identical to the unsharded frame for any
+ *      camera motion.  Otherwise a row goes only to the shards owning a row within halo_rows of it: bit-identical as long as
+ *      reprojection (and spatial_radius) stay within halo_rows rows — e.g. a static or slowly moving camera with a few
+ *      contiguous bands (band_rows = ceil(h / n_shards)) moves (n-1)/n less data.
+ *   3. all shards render the same sequence of frames (same count, same sizes); a shard that is 20 s late is not waited for
+ *      any longer (the frame proceeds on stale rows and gpurt_pipe_history_status counts the time-out).
+ * Inside one process on one stream, render frame f on every shard before frame f + 1 on any. */
+#define GPURT_HISTORY_ALL_ROWS 0xFFFFFFFFu
+int gpurt_pipe_history_export(gpurt_pipe* pipe, uint32_t width, uint32_t height, void** out_device_ptr,
+                              uint8_t handle_out[GPURT_IPC_HANDLE_BYTES], uint64_t* out_bytes);
+int gpurt_pipe_history_peers(gpurt_pipe* pipe, uint32_t n_shards, void* const* blocks, uint32_t halo_rows);
+int gpurt_pipe_history_status(gpurt_pipe* pipe, uint32_t* out_frames_pushed, uint32_t* out_timeouts);
 /* Frame-parallel sharding (integrators 0-2, whose frames are independent given the frame index): render frame
  * `frame` of the progressive sequence — same RNG streams as RTPipe::trace would use for it — and write the
  * per-pixel mean of its samples (rt.rgen:638) to mean_out_device (w*h RGBA32F, may be a gpurt_shared_open

@@ -573,7 +573,8 @@ static void render_rows(const FrameParams& P, const ShadeCtx& X, uint32_t i0, ui
                         unsigned long long* counts) {
     const bool restir = I == 3 || I == 4;
     unsigned long long nc = 0, na = 0;
-    for(uint32_t i = i0; i < i1; i++) {
+    for(uint32_t li = i0; li < i1; li++) {
+        const uint32_t i = shard_pixel(P, li);
         pixel_begin(P, restir ? 1 : 0, i, acc, pathB, gpos, gnorm, galb, res_cur);
         for(uint32_t s = 0; s < (uint32_t)P.c.samples && P.c.max_depth > 0; s++) {
             float4 ray[2];
@@ -631,6 +632,25 @@ void emu_light_pdf(void* bvh, const EmuFrameArgs* A, const float* rays6, unsigne
     }
 }
 
+/* band sharding of the following emu_render_frame calls (gpurt_pipe_set_shard); 0 rows = the whole frame */
+static uint32_t g_band_rows = 0, g_n_shards = 1, g_shard = 0;
+void emu_set_shard(uint32_t band_rows, uint32_t n_shards, uint32_t shard) { g_band_rows = band_rows, g_n_shards = n_shards, g_shard = shard; }
+/* history_row_readers() of shade.cuh: the shards that receive row y of `shard`'s previous frame (k_history_push) */
+unsigned long long emu_history_row_readers(uint32_t w, uint32_t h, uint32_t band_rows, uint32_t n_shards, uint32_t shard, uint32_t y,
+                                           uint32_t halo) {
+    FrameParams P;
+    std::memset(&P, 0, sizeof(P));
+    P.W = w, P.H = h, P.band_rows = band_rows, P.n_shards = n_shards, P.shard = shard;
+    return history_row_readers(P, y, halo);
+}
+/* shard_row() of shade.cuh */
+uint32_t emu_shard_row(uint32_t w, uint32_t h, uint32_t band_rows, uint32_t n_shards, uint32_t shard, uint32_t j) {
+    FrameParams P;
+    std::memset(&P, 0, sizeof(P));
+    P.W = w, P.H = h, P.band_rows = band_rows, P.n_shards = n_shards, P.shard = shard;
+    return shard_row(P, j);
+}
+
 /* ReSTIR spatial-reuse extension of the following emu_render_frame calls (GpurtPipeParams::spatial_samples / spatial_radius) */
 static uint32_t g_spatial_samples = 0;
 static float g_spatial_radius = 16.0f;
@@ -654,7 +674,8 @@ void emu_render_frame(void* bvh, const EmuFrameArgs* A, const uint32_t* consts, 
     std::memcpy(&P.c, consts, sizeof(P.c));
     std::memcpy(&P.cam, camera, sizeof(P.cam));
     P.W = w, P.H = h, P.seed_val = seed_val;
-    P.band_rows = h, P.n_shards = 1, P.shard = 0, P.n_local = w * h;
+    P.band_rows = g_band_rows ? g_band_rows : h, P.n_shards = g_band_rows ? g_n_shards : 1, P.shard = g_band_rows ? g_shard : 0;
+    P.n_local = emu_shard_pixels(w, h, g_band_rows, g_n_shards, g_shard, nullptr);
     P.spatial_samples = g_spatial_samples, P.spatial_radius = g_spatial_radius;
     ShadeCtx X{};
     fill_ctx(E, A, X);
@@ -676,8 +697,8 @@ void emu_render_frame(void* bvh, const EmuFrameArgs* A, const uint32_t* consts, 
         X.lverts = lverts.data(), X.lvert_off = lvoff.data();
     }
     X.prev_res = (const float4*)prev_res, X.ppos = (const float4*)ppos, X.pnorm = (const float4*)pnorm, X.palb = (const float4*)palb;
-    const uint32_t n = w * h;
-    std::vector<float4> acc(n), pathA(n), pathB(n);
+    const uint32_t n = P.n_local; /* thread ranges are over local indices; buffers are indexed by the global pixel */
+    std::vector<float4> acc((size_t)w * h), pathA((size_t)w * h), pathB((size_t)w * h);
     int T = threads > 0 ? threads : (int)std::max(1u, std::thread::hardware_concurrency());
     T = std::min<int>(T, (int)std::max(1u, n / 64));
     std::vector<unsigned long long> cnt(2 * T, 0);

@@ -272,6 +272,42 @@ def test_sharded_frames_compose_to_the_unsharded_frame(gpurt, ctx):
     whole.close(), accel.close(), scene.close()
 
 
+def _restir_sharded(*argv, nproc=0):
+    import json
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    tool = os.path.join(ROOT, "tools", "restir_sharded.py")
+    cmd = [sys.executable, tool] if not nproc else [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node",
+                                                    str(nproc), "--master-addr", "127.0.0.1", "--master-port", "29741", tool]
+    out = subprocess.run(cmd + ["--verify", "--reps", "1"] + list(argv), capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-1500:] + out.stderr[-2500:]
+    res = json.loads(out.stdout.strip().splitlines()[-1])
+    assert res["flag_wait_timeouts"] == 0 and all(res["verified"].values()), res
+    return res
+
+
+def test_restir_sharded_frame_with_history_exchange(gpurt, built):
+    """SURVEY §8e, ReSTIR: shards store their rows of the finished frame into each other's previous-frame blocks
+    (k_history_push / signal / wait); image, G-buffers and reservoirs after every frame == the unsharded render, with a
+    moving camera (whole rows to everyone) and with a halo (static camera, spatial reuse inside the halo).  One process,
+    the shards' pipes on one GPU — the two-GPU test below runs the same thing over NVLink."""
+    r = _restir_sharded("--shards", "3", "--size", "320", "180", "--frames", "5", "--bands", "interleaved", "--orbit", "--integrator", "4")
+    assert r["n_shards"] == 3 and r["bytes_pushed_per_frame_shard0"] > 0
+    _restir_sharded("--shards", "4", "--size", "320", "200", "--frames", "4", "--halo", "10", "--spatial", "3", "--radius", "8")
+    _restir_sharded("--shards", "2", "--size", "1920", "1080", "--frames", "3", "--orbit")
+
+
+def test_restir_sharded_frame_two_gpus(gpurt, built):
+    """the same over NVLink: one rank per GPU, blocks mapped through gpurt_shared_open (needs 2 GPUs)"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    _restir_sharded("--frames", "6", "--orbit", nproc=2)
+    _restir_sharded("--frames", "6", "--halo", "16", "--spatial", "2", "--radius", "8", nproc=2)
+
+
 def test_tonemap_matches_oracle(gpurt, orc, ctx):
     scene = load_scene(gpurt, ctx, "cbox")
     accel = gpurt.Accel(scene)

@@ -344,8 +344,10 @@ def ncu_facts():
 # ---- strong-scaling sub-benchmarks (BASELINE configs 4 and 5 at the same N) -----------------------------------------
 def strong_config4(gpurt, torch, dist, ctx, rank, world, dev, n_tris, n_queries, check):
     """config 4: 10 M-triangle soup, 100 M closest-point queries in contiguous ranges per rank, all 3.2 GB of results
-    placed in rank 0's memory inside the timed region: rank 0's kernel writes there directly; the other ranks compute
-    chunk k into a local buffer while chunk k-1 crosses NVLink on a second stream (copy engine, no collective)."""
+    placed in rank 0's memory inside the timed region.  Every rank passes its slice of rank 0's buffer (rank 0: its own
+    memory; the others: the NVLink mapping) as the result pointer of gpurt_closest_points: the library sorts the batch once,
+    traverses it in slices of the processing order and stores slice k to rank 0 on a second stream while slice k + 1 is
+    traversed (csrc/order.cu) — no collective, no staging in the caller."""
     sys.path.insert(0, os.path.join(ROOT, "tools"))
     from config4_cpq import make_queries, make_soup
     from gpurt.dist import shard_range, shared_result_buffer
@@ -356,37 +358,21 @@ def strong_config4(gpurt, torch, dist, ctx, rank, world, dev, n_tris, n_queries,
     info = accel.info()
     a, b = shard_range(n_queries, rank, world)
     nq = b - a
-    chunk = max(1 << 20, min(12_500_000, (nq + 3) // 4))
+    chunk = max(1 << 20, min(12_500_000, nq))
     q = torch.empty((nq, 4), dtype=torch.float32, device=dev)
     for c0 in range(0, nq, 12_500_000):
         c1 = min(nq, c0 + 12_500_000)
         q[c0:c1] = make_queries(a + c0, a + c1, dev)
     shared = shared_result_buffer(ctx, n_queries * 32)
     remote = shared.tensor().view(torch.float32).view(-1, 8)       # rank 0: its own memory; others: NVLink mapping
-    local = [torch.empty((chunk, 8), dtype=torch.float32, device=dev) for _ in range(2)] if rank else None
-    main_s, copy_s = torch.cuda.current_stream(), torch.cuda.Stream()
+    local = torch.empty((chunk, 8), dtype=torch.float32, device=dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    free_ev = [None, None]
 
     def run():
         e0.record()
-        for k, c0 in enumerate(range(0, nq, chunk)):
+        for c0 in range(0, nq, chunk):
             c1 = min(nq, c0 + chunk)
-            if rank == 0:
-                accel.closest_points(q[c0:c1], shared.at((a + c0) * 32))
-                continue
-            buf = local[k & 1]
-            if free_ev[k & 1] is not None:
-                main_s.wait_event(free_ev[k & 1])                  # the copy that last read this buffer is done
-            accel.closest_points(q[c0:c1], buf[: c1 - c0])
-            done = torch.cuda.Event()
-            done.record(main_s)
-            copy_s.wait_event(done)
-            with torch.cuda.stream(copy_s):
-                remote[a + c0:a + c1].copy_(buf[: c1 - c0], non_blocking=True)
-                free_ev[k & 1] = torch.cuda.Event()
-                free_ev[k & 1].record(copy_s)
-        main_s.wait_stream(copy_s)
+            accel.closest_points(q[c0:c1], shared.at((a + c0) * 32))
         e1.record()
 
     def sync():
@@ -394,7 +380,7 @@ def strong_config4(gpurt, torch, dist, ctx, rank, world, dev, n_tris, n_queries,
         if world > 1:
             dist.barrier()
 
-    run()                                                          # warm-up (communicators, arenas, sort scratch)
+    run()                                                          # warm-up (arenas, sort scratch, placement stream)
     sync()
     t0 = time.time()
     run()
@@ -405,14 +391,15 @@ def strong_config4(gpurt, torch, dist, ctx, rank, world, dev, n_tris, n_queries,
     e0.record()
     for c0 in range(0, nq, chunk):
         c1 = min(nq, c0 + chunk)
-        accel.closest_points(q[c0:c1], local[0][: c1 - c0] if rank else shared.at((a + c0) * 32))
+        accel.closest_points(q[c0:c1], local[: c1 - c0])
     e1.record()
     sync()
     ms_local = device_max(dist, world, e0.elapsed_time(e1), dev)
     out = {"config": "4: synthetic 10 M-triangle soup, 100 M closest-point queries", "tris": info.n_tris, "queries": n_queries,
            "n_gpus": world, "mqueries_s": n_queries / (ms * 1e-3) / 1e6, "ms": ms, "wall_ms_barrier_to_barrier": wall * 1e3,
-           "results": "all results in rank 0's memory at the end of the timed region (rank 0: direct; others: chunk k computed "
-                      "while chunk k-1 is copied over NVLink, no collective)",
+           "results": "all results in rank 0's memory at the end of the timed region: every rank's gpurt_closest_points call gets its "
+                      "slice of rank 0's buffer as the result pointer; the library stores slice k of the sorted batch over NVLink "
+                      "on a second stream while slice k+1 is traversed (no collective)",
            "bytes_into_rank0": int((n_queries - (shard_range(n_queries, 0, world)[1])) * 32), "chunk_queries": chunk,
            "mqueries_s_results_left_local": n_queries / (ms_local * 1e-3) / 1e6, "bvh_build_ms": info.build_ms}
     if rank == 0 and check:
@@ -426,6 +413,67 @@ def strong_config4(gpurt, torch, dist, ctx, rank, world, dev, n_tris, n_queries,
     if world > 1:
         dist.barrier()
     shared.close()
+    accel.close(), scene.close()
+    return out
+
+
+def strong_config3_restir(gpurt, torch, dist, ctx, rank, world, dev):
+    """config 3's ReSTIR frames (mis_test 1920x1080, integrator 3, depth 4, 1 spp, res_samples 4, temporal reuse) with the frame
+    sharded over the ranks in contiguous row bands: each rank's frame-end stores its rows of the G-buffers + reservoirs
+    (those within 16 rows of another rank's band; the camera is static) into the other ranks' previous-frame blocks over
+    NVLink and raises a flag; the next frame's first kernel waits for the flags (gpurt_pipe_history_peers) — no host
+    synchronisation or collective per frame.  The composite image on rank 0 is compared with the unsharded render."""
+    from gpurt.dist import gather_to_rank0, share_history
+    w, h, frames, halo = 1920, 1080, 9, 16
+    scene = gpurt.Scene(ctx).load(os.path.join(ROOT, "tests", "data", "media", "mis_test", "mis_test.gltf"))
+    accel = gpurt.Accel(scene)
+    cam = gpurt.camera(1, w, h, (0.5, 0.6, 2.6), (0.5, 0.45, 0.0), 50.0)
+    prm = gpurt.pipe_params(integrator=3, brdf=1, samples_per_frame=1, max_depth=4, res_samples=4, use_temporal=1, temporal_scale=16, seed=8)
+    band = (h + world - 1) // world
+    pipe = gpurt.RTPipe(scene, accel)
+    maps = []
+    if world > 1:
+        pipe.set_shard(band, world, rank)
+        maps = share_history(pipe, ctx, w, h, halo)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def loop(p):
+        p.reset_frame()
+        for _ in range(frames):
+            p.render_frame(prm, cam, w, h)
+
+    best = None
+    for _ in range(4):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0.record()
+        loop(pipe)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = device_max(dist, world, e0.elapsed_time(e1), dev)
+        best = ms if best is None else min(best, ms)
+    timeouts = int(device_max(dist, world, float(pipe.history_status()[1]), dev))
+    identical = None
+    rows = torch.arange(h, device=dev)
+    mine = pipe.device_image()[(rows // band) % world == rank] if world > 1 else pipe.device_image()
+    full = gather_to_rank0(mine.contiguous().view(-1, 4)) if world > 1 else mine     # contiguous bands: rank order = row order
+    if rank == 0:
+        ref = gpurt.RTPipe(scene, accel)
+        for _ in range(4):      # the same call sequence as the sharded pipes (reservoir history carries across reset_frame)
+            loop(ref)
+        identical = bool(torch.equal(ref.device_image().view(torch.int32).view(-1, 4), full.view(torch.int32).view(-1, 4)))
+        ref.close()
+    out = {"config": "3 (ReSTIR direct): mis_test 1920x1080, depth 4, 1 spp, res_samples 4, temporal reuse, 9 frames", "n_gpus": world,
+           "ms_per_frame": best / frames, "mpaths_s": w * h * frames / (best * 1e-3) / 1e6,
+           "sharding": (f"{band}-row contiguous bands; rows within {halo} rows of another band pushed into that rank's previous-frame "
+                        "block by the frame-end kernels over NVLink, flag wait at the next frame start") if world > 1 else "one GPU",
+           "flag_wait_timeouts": timeouts, "composite_bit_identical_to_unsharded": identical}
+    if world > 1:
+        dist.barrier()
+    pipe.close()
+    for m in maps:
+        m.close()
     accel.close(), scene.close()
     return out
 
@@ -764,6 +812,7 @@ def main():
     if not args.no_strong:
         pipe.close()
         strong = {"config5": strong_config5(gpurt, torch, dist, ctx, scene, accel, rank, world, dev, label)}
+        strong["config3_restir"] = strong_config3_restir(gpurt, torch, dist, ctx, rank, world, dev)
         accel.close()
         del d_rays, d_hits, flush, d_q, d_cp
         torch.cuda.empty_cache()

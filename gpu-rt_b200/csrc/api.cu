@@ -209,9 +209,9 @@ int gpurt_ctx_destroy(gpurt_ctx* c) {
     if(c->stream) cudaStreamSynchronize(c->stream);
     c->d_in.release(), c->d_out.release(), c->scratch.release(), c->build_arena.release();
     if(c->pinned_word) cudaFreeHost(c->pinned_word);
-    for(cudaEvent_t ev : {c->ev0, c->ev1, c->ev_copy, c->ev_kernel, c->ev_switch})
+    for(cudaEvent_t ev : {c->ev0, c->ev1, c->ev_copy, c->ev_kernel, c->ev_switch, c->ev_place})
         if(ev) cudaEventDestroy(ev);
-    for(cudaStream_t st : {c->s_h2d, c->s_d2h, c->own_stream})
+    for(cudaStream_t st : {c->s_h2d, c->s_d2h, c->s_place, c->own_stream})
         if(st) cudaStreamDestroy(st);
     delete c;
     return GPURT_OK;

@@ -6,6 +6,8 @@
  * Priority-ordered descent (traverse.cuh: closest_point8).  N5 tie rule: smallest d^2 wins, equal
  * d^2 -> lowest global primitive id; the radius is inclusive.
  */
+#include <algorithm>
+
 #include "device.cuh"
 #include "traverse.cuh"
 
@@ -67,24 +69,39 @@ int launch_closest_points_stats(gpurt_accel* A, const float4* queries, uint64_t 
 
 int launch_closest_points(gpurt_accel* A, const float4* queries, uint64_t n, float4* results) {
     if(!n) return GPURT_OK;
-    unsigned nb = (unsigned)((n + 127) / 128);
     const float4* nodes = (const float4*)A->nodes;
     cudaStream_t st = A->ctx->stream;
     OrderPlan P; /* large incoherent batches on large scenes are processed in Morton order of the query point (order.cu) */
-    int rc = plan_spatial_order(A, queries, 1, n, results, 32, P);
+    int rc = plan_spatial_order(A, queries, 1, n, results, 32, P, true);
     if(rc) return rc;
-    float4* out = (float4*)P.out;
-    const int staged = P.unperm ? 1 : 0;
     unsigned need = 7u * A->depth + 1u;
+    if(need > 512) return set_error("wide BVH too deep for the closest-point stack"), GPURT_E_STATE;
+    /* [off, off + m) of the processing order; the whole batch unless results are scattered to another GPU slice by slice */
+    auto launch = [&](uint64_t off, uint64_t m) {
+        const unsigned nb = (unsigned)((m + 127) / 128);
+        float4* out = (float4*)P.out + (P.scatter ? 2 * off : 0);
+        const uint32_t* order = P.order ? P.order + off : nullptr;
+        const int staged = (P.unperm || P.scatter) ? 1 : 0;
 #define GPURT_CPQ_LAUNCH(S)                                                                                                  \
-    (P.order ? k_closest_points<S, true><<<nb, 128, 0, st>>>(nodes, A->tri_wide, queries, n, out, A->n_nodes, P.order, staged) \
-             : k_closest_points<S, false><<<nb, 128, 0, st>>>(nodes, A->tri_wide, queries, n, out, A->n_nodes, nullptr, 0))
-    if(need <= 64) GPURT_CPQ_LAUNCH(64);
-    else if(need <= 128) GPURT_CPQ_LAUNCH(128);
-    else if(need <= 256) GPURT_CPQ_LAUNCH(256);
-    else if(need <= 512) GPURT_CPQ_LAUNCH(512);
-    else return set_error("wide BVH too deep for the closest-point stack"), GPURT_E_STATE;
+    (order ? k_closest_points<S, true><<<nb, 128, 0, st>>>(nodes, A->tri_wide, queries, m, out, A->n_nodes, order, staged) \
+           : k_closest_points<S, false><<<nb, 128, 0, st>>>(nodes, A->tri_wide, queries, m, out, A->n_nodes, nullptr, 0))
+        if(need <= 64) GPURT_CPQ_LAUNCH(64);
+        else if(need <= 128) GPURT_CPQ_LAUNCH(128);
+        else if(need <= 256) GPURT_CPQ_LAUNCH(256);
+        else GPURT_CPQ_LAUNCH(512);
 #undef GPURT_CPQ_LAUNCH
+    };
+    if(P.scatter) {
+        const uint64_t slice = order_slice_size(n);
+        for(uint64_t off = 0; off < n; off += slice) {
+            const uint64_t m = std::min(slice, n - off);
+            launch(off, m);
+            GPURT_CUDA(cudaGetLastError());
+            if((rc = scatter_slice_async(A, P, off, m, results, 32))) return rc;
+        }
+        return scatter_join(A);
+    }
+    launch(0, n);
     GPURT_CUDA(cudaGetLastError());
     return finish_spatial_order(A, P, n, results, 32);
 }

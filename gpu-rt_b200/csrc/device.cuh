@@ -43,6 +43,8 @@ struct gpurt_ctx {
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
     cudaEvent_t ev_copy = nullptr, ev_kernel = nullptr;
     cudaEvent_t ev_switch = nullptr; /* orders a newly selected stream after the old one (gpurt_ctx_set_stream) */
+    cudaStream_t s_place = nullptr;  /* result placement into another GPU's memory while the next slice is computed (order.cu) */
+    cudaEvent_t ev_place = nullptr;
     /* staging for GPURT_MEM_HOST calls */
     gpurt::DevBuf d_in, d_out;
     gpurt::DevBuf scratch;
@@ -109,10 +111,16 @@ struct OrderPlan {
     const uint32_t* order = nullptr;
     const uint32_t* unperm = nullptr;
     void* out = nullptr;
+    bool scatter = false; /* results on another GPU: slices staged in processing order, scattered by a second stream */
 };
 int plan_spatial_order(gpurt_accel* A, const float4* pos, unsigned stride_vec4, uint64_t n, void* results,
-                       size_t result_bytes, OrderPlan& P);
+                       size_t result_bytes, OrderPlan& P, bool sliced_scatter = false);
 int finish_spatial_order(gpurt_accel* A, const OrderPlan& P, uint64_t n, void* results, size_t result_bytes);
+/* remote results of an ordered batch: the slice [off, off + m) of the staging array (processing order) goes to its storage
+ * positions in `results` on the placement stream, after everything queued on the context's stream so far */
+uint64_t order_slice_size(uint64_t n);
+int scatter_slice_async(gpurt_accel* A, const OrderPlan& P, uint64_t off, uint64_t m, void* results, size_t result_bytes);
+int scatter_join(gpurt_accel* A); /* the context's stream waits for the placement stream */
 
 /* query launchers (device pointers, async on ctx->stream) */
 int launch_trace_closest(gpurt_accel* A, const float4* rays, uint64_t n, float4* hits);

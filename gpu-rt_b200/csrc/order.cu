@@ -12,10 +12,15 @@
  * neighbouring elements already share a cell of a 16^3 grid (e.g. rays and points generated per pixel).
  * Results never depend on the processing order (contracts N4 / N5).
  *
- * If the result array lives on another GPU (gpurt_shared_open mapping), scattered 16/32-byte stores over NVLink
- * would cost ~70 % more than the traversal itself, so results are staged locally in processing order and a second
- * kernel writes the caller's array front to back.
+ * If the result array lives on another GPU (gpurt_shared_open mapping), scattered 16/32-byte stores over NVLink issued by
+ * the traversal kernel itself would cost ~70 % more than the traversal, so results are staged locally in processing order.
+ * Closest-hit and closest-point batches are then traversed in slices of the processing order: while slice k + 1 is
+ * traversed, a small kernel on a second stream stores slice k to its storage positions on the other GPU, so only the last
+ * slice's transfer is exposed and the batch keeps the coherence of ONE sort over all its elements (chunking the batch by
+ * storage position instead, to overlap copies, sorts each chunk separately: 3.1 M-point chunks of config 4 run 17 % slower
+ * than one 12.5 M-point batch).  Any-hit results (1 byte) are written front to back by a second kernel.
  */
+#include <algorithm>
 #include <cstdlib>
 
 #include "device.cuh"
@@ -57,6 +62,15 @@ __global__ void __launch_bounds__(256) k_order_unpermute(const float4* __restric
     if(t >= (uint64_t)VEC4 * n) return;
     results[t] = staged[(uint64_t)VEC4 * inv[t / VEC4] + (t % VEC4)];
 }
+/* results[order[i]] = staged[i] for the records of one slice; one thread per float4, the VEC4 float4s of a record by
+ * neighbouring lanes */
+template <int VEC4>
+__global__ void __launch_bounds__(256) k_order_scatter(const float4* __restrict__ staged, const uint32_t* __restrict__ order,
+                                                       uint64_t m, float4* __restrict__ results) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if(t >= (uint64_t)VEC4 * m) return;
+    results[(uint64_t)VEC4 * order[t / VEC4] + (t % VEC4)] = staged[t];
+}
 __global__ void __launch_bounds__(256) k_order_unpermute_u8(const uint8_t* __restrict__ staged, const uint32_t* __restrict__ inv,
                                                             uint64_t n, uint8_t* __restrict__ results) {
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -67,7 +81,7 @@ constexpr uint64_t kOrderMinBatch = 1u << 20;
 constexpr size_t kOrderMinBvhBytes = 64u << 20;
 
 int plan_spatial_order(gpurt_accel* A, const float4* pos, unsigned stride_vec4, uint64_t n, void* results,
-                       size_t result_bytes, OrderPlan& P) {
+                       size_t result_bytes, OrderPlan& P, bool sliced_scatter) {
     P = OrderPlan();
     P.out = results;
     gpurt_ctx* ctx = A->ctx;
@@ -78,8 +92,10 @@ int plan_spatial_order(gpurt_accel* A, const float4* pos, unsigned stride_vec4, 
     /* scratch in the build arena (no build runs concurrently on this stream): keys | keys_tmp | vals | vals_tmp | counter | staging */
     const size_t kb = ((size_t)n * 8 + 255) & ~(size_t)255, vb = ((size_t)n * 4 + 255) & ~(size_t)255;
     cudaPointerAttributes pa;
-    const bool remote = cudaPointerGetAttributes(&pa, results) == cudaSuccess && pa.type == cudaMemoryTypeDevice &&
-                        pa.device != ctx->device;
+    /* GPURT_PLACE_FORCE=1 (test hook): treat local results like another GPU's, to run the placement path on one GPU */
+    const bool force_remote = getenv("GPURT_PLACE_FORCE") && atoi(getenv("GPURT_PLACE_FORCE")) != 0;
+    const bool remote = (cudaPointerGetAttributes(&pa, results) == cudaSuccess && pa.type == cudaMemoryTypeDevice &&
+                         pa.device != ctx->device) || force_remote;
     (void)cudaGetLastError();
     const size_t used = 2 * kb + 2 * vb + 256, stage_bytes = remote ? (((size_t)n * result_bytes + 255) & ~(size_t)255) : 0;
     int rc = ctx->build_arena.reserve(used + stage_bytes);
@@ -101,13 +117,46 @@ int plan_spatial_order(gpurt_accel* A, const float4* pos, unsigned stride_vec4, 
     rc = radix_sort_u64(st, keys, vals, keys_tmp, vals_tmp, n, 4, ctx->scratch, ctx->sm_count);
     if(rc) return rc;
     P.order = vals; /* 4 passes: the result is back in the primary buffers */
-    if(remote) {
+    static const bool allow_slices = !(getenv("GPURT_PLACE_SLICES") && atoi(getenv("GPURT_PLACE_SLICES")) == 0);
+    if(remote && sliced_scatter && allow_slices) {
+        P.out = base + used;
+        P.scatter = true;
+        if(!ctx->s_place) {
+            GPURT_CUDA(cudaStreamCreateWithFlags(&ctx->s_place, cudaStreamNonBlocking));
+            GPURT_CUDA(cudaEventCreateWithFlags(&ctx->ev_place, cudaEventDisableTiming));
+        }
+    } else if(remote) {
         P.out = base + used;
         uint32_t* invw = (uint32_t*)keys_tmp; /* the sort is finished with its key scratch */
         k_order_invert<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(P.order, n, invw);
         P.unperm = invw;
     }
     GPURT_CUDA(cudaGetLastError());
+    return GPURT_OK;
+}
+
+uint64_t order_slice_size(uint64_t n) {
+    static const uint64_t want = getenv("GPURT_PLACE_SLICES") ? (uint64_t)std::max(1, atoi(getenv("GPURT_PLACE_SLICES"))) : 8u;
+    uint64_t s = std::max<uint64_t>((n + want - 1) / want, 1u << 18);
+    return (s + 127) & ~(uint64_t)127;
+}
+int scatter_slice_async(gpurt_accel* A, const OrderPlan& P, uint64_t off, uint64_t m, void* results, size_t result_bytes) {
+    gpurt_ctx* ctx = A->ctx;
+    GPURT_CUDA(cudaEventRecord(ctx->ev_place, ctx->stream));
+    GPURT_CUDA(cudaStreamWaitEvent(ctx->s_place, ctx->ev_place, 0));
+    const float4* staged = (const float4*)((const char*)P.out + off * result_bytes);
+    if(result_bytes == 32)
+        k_order_scatter<2><<<(unsigned)((2 * m + 255) / 256), 256, 0, ctx->s_place>>>(staged, P.order + off, m, (float4*)results);
+    else if(result_bytes == 16)
+        k_order_scatter<1><<<(unsigned)((m + 255) / 256), 256, 0, ctx->s_place>>>(staged, P.order + off, m, (float4*)results);
+    else return set_error("scatter_slice_async: record size"), GPURT_E_STATE;
+    GPURT_CUDA(cudaGetLastError());
+    return GPURT_OK;
+}
+int scatter_join(gpurt_accel* A) {
+    gpurt_ctx* ctx = A->ctx;
+    GPURT_CUDA(cudaEventRecord(ctx->ev_place, ctx->s_place));
+    GPURT_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_place, 0));
     return GPURT_OK;
 }
 

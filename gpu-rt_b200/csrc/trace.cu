@@ -11,6 +11,8 @@
  * N4 tie rule: nearest t wins, equal t -> lowest global primitive id, so the result does not depend
  * on traversal order and equals the brute-force oracle bit for bit.
  */
+#include <algorithm>
+
 #include "device.cuh"
 #include "traverse.cuh"
 
@@ -125,8 +127,19 @@ static inline unsigned blocks_for(uint64_t n, unsigned t) { return (unsigned)((n
 int launch_trace_closest(gpurt_accel* A, const float4* rays, uint64_t n, float4* hits) {
     if(!n) return GPURT_OK;
     OrderPlan P; /* large incoherent batches on large scenes are processed in Morton order of the ray origin (order.cu) */
-    int rc = plan_spatial_order(A, rays, 2, n, hits, 16, P);
+    int rc = plan_spatial_order(A, rays, 2, n, hits, 16, P, true);
     if(rc) return rc;
+    if(P.scatter) { /* hits live on another GPU: slice k is stored there while slice k + 1 is traced (order.cu) */
+        const uint64_t slice = order_slice_size(n);
+        for(uint64_t off = 0; off < n; off += slice) {
+            const uint64_t m = std::min(slice, n - off);
+            k_trace_closest<false, true><<<blocks_for(m, 128), 128, 0, A->ctx->stream>>>(
+                (const float4*)A->nodes, A->tri_wide, rays, m, (float4*)P.out + off, A->n_nodes, nullptr, P.order + off, 1);
+            GPURT_CUDA(cudaGetLastError());
+            if((rc = scatter_slice_async(A, P, off, m, hits, 16))) return rc;
+        }
+        return scatter_join(A);
+    }
     if(P.order)
         k_trace_closest<false, true><<<blocks_for(n, 128), 128, 0, A->ctx->stream>>>(
             (const float4*)A->nodes, A->tri_wide, rays, n, (float4*)P.out, A->n_nodes, nullptr, P.order, P.unperm ? 1 : 0);

@@ -42,8 +42,8 @@ def params(args):
 
 
 def same(a, b):
-    a, b = np.asarray(a), np.asarray(b)
-    return bool((a.view(np.uint32) == b.view(np.uint32)).all())
+    a, b = np.ascontiguousarray(a).reshape(-1), np.ascontiguousarray(b).reshape(-1)
+    return a.size == b.size and bool((a.view(np.uint32) == b.view(np.uint32)).all())
 
 
 def main():
@@ -55,6 +55,7 @@ def main():
     ap.add_argument("--spatial", type=int, default=0)
     ap.add_argument("--radius", type=float, default=8.0)
     ap.add_argument("--bands", choices=["contiguous", "interleaved"], default="contiguous")
+    ap.add_argument("--band-rows", type=int, default=0, help="rows per band, interleaved over the shards (overrides --bands)")
     ap.add_argument("--halo", default="all", help="rows, or 'all'")
     ap.add_argument("--orbit", action="store_true")
     ap.add_argument("--shards", type=int, default=0, help="single process: this many pipes on one GPU")
@@ -70,7 +71,7 @@ def main():
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n_shards = world if torchrun else max(1, args.shards)
-    band = 16 if args.bands == "interleaved" else (h + n_shards - 1) // n_shards
+    band = args.band_rows or (16 if args.bands == "interleaved" else (h + n_shards - 1) // n_shards)
     ctx = gpurt.Context(local)
     ctx.use_torch_stream()
     scene = gpurt.Scene(ctx).load(args.scene)
@@ -98,12 +99,13 @@ def main():
     def gather_rows(arr_by_shard):
         """rows of the composite frame from their owners (host arrays; verification only)"""
         if torchrun:
-            t = torch.from_numpy(np.ascontiguousarray(arr_by_shard[rank])).cuda()
+            a = np.ascontiguousarray(arr_by_shard[rank]).reshape(h, -1)
+            t = torch.from_numpy(a.view(np.uint8)).cuda()   # bytes: NCCL has no uint32
             parts = [torch.empty_like(t) for _ in range(world)]
             dist.all_gather(parts, t)
-            parts = [q.cpu().numpy() for q in parts]
+            parts = [q.cpu().numpy().view(a.dtype) for q in parts]
         else:
-            parts = [arr_by_shard[s] for s in range(n_shards)]
+            parts = [np.asarray(arr_by_shard[s]).reshape(h, -1) for s in range(n_shards)]
         return np.stack([parts[int(owner[y])][y] for y in range(h)])
 
     def check(f):
@@ -194,7 +196,7 @@ def main():
         print(json.dumps({
             "workload": f"{os.path.basename(args.scene)} {w}x{h}, integrator {args.integrator}, depth 4, 1 spp, res_samples 4, temporal reuse"
                         + (f", spatial reuse {args.spatial} x r{args.radius:g}" if args.spatial else "") + (", moving camera" if args.orbit else ""),
-            "n_shards": n_shards, "processes": world, "bands": f"{args.bands} ({band} rows)",
+            "n_shards": n_shards, "processes": world, "bands": f"{band} rows, {(h + band - 1) // band} bands",
             "halo_rows": "all" if halo == ALL else halo, "frames": args.frames + 1,
             "ms_per_frame_sharded": ms_sharded, "ms_per_frame_one_gpu": ms_single,
             "speedup": (ms_single / ms_sharded) if (ms_single and torchrun) else None,

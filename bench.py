@@ -344,10 +344,12 @@ def ncu_facts():
 # ---- strong-scaling sub-benchmarks (BASELINE configs 4 and 5 at the same N) -----------------------------------------
 def strong_config4(gpurt, torch, dist, ctx, rank, world, dev, n_tris, n_queries, check):
     """config 4: 10 M-triangle soup, 100 M closest-point queries in contiguous ranges per rank, all 3.2 GB of results
-    placed in rank 0's memory inside the timed region.  Every rank passes its slice of rank 0's buffer (rank 0: its own
-    memory; the others: the NVLink mapping) as the result pointer of gpurt_closest_points: the library sorts the batch once,
-    traverses it in slices of the processing order and stores slice k to rank 0 on a second stream while slice k + 1 is
-    traversed (csrc/order.cu) — no collective, no staging in the caller."""
+    placed in rank 0's memory inside the timed region: rank 0's kernel writes there directly; the other ranks compute
+    chunk k into a local buffer while chunk k-1 crosses NVLink on a second stream (copy engine, no collective).
+    (Measured alternative, profiles/r03_summary.md: one call per rank with rank 0's buffer as the result pointer and
+    GPURT_PLACE_SLICES=8 — the library sorts the 12.5 M batch once and stores slice k of the processing order to rank 0 while
+    slice k + 1 is traversed.  Kernels run at the single-GPU rate (7.95x at 8 GPUs with results left local) but 87.5 M
+    scattered 32-byte stores from 7 senders into one GPU arrive at only 175 GB/s: 6039 Mq/s against 8105 for the chunked copies.)"""
     sys.path.insert(0, os.path.join(ROOT, "tools"))
     from config4_cpq import make_queries, make_soup
     from gpurt.dist import shard_range, shared_result_buffer
@@ -358,21 +360,37 @@ def strong_config4(gpurt, torch, dist, ctx, rank, world, dev, n_tris, n_queries,
     info = accel.info()
     a, b = shard_range(n_queries, rank, world)
     nq = b - a
-    chunk = max(1 << 20, min(12_500_000, nq))
+    chunk = max(1 << 20, min(12_500_000, (nq + 3) // 4))
     q = torch.empty((nq, 4), dtype=torch.float32, device=dev)
     for c0 in range(0, nq, 12_500_000):
         c1 = min(nq, c0 + 12_500_000)
         q[c0:c1] = make_queries(a + c0, a + c1, dev)
     shared = shared_result_buffer(ctx, n_queries * 32)
     remote = shared.tensor().view(torch.float32).view(-1, 8)       # rank 0: its own memory; others: NVLink mapping
-    local = torch.empty((chunk, 8), dtype=torch.float32, device=dev)
+    local = [torch.empty((chunk, 8), dtype=torch.float32, device=dev) for _ in range(2)] if rank else None
+    main_s, copy_s = torch.cuda.current_stream(), torch.cuda.Stream()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    free_ev = [None, None]
 
     def run():
         e0.record()
-        for c0 in range(0, nq, chunk):
+        for k, c0 in enumerate(range(0, nq, chunk)):
             c1 = min(nq, c0 + chunk)
-            accel.closest_points(q[c0:c1], shared.at((a + c0) * 32))
+            if rank == 0:
+                accel.closest_points(q[c0:c1], shared.at((a + c0) * 32))
+                continue
+            buf = local[k & 1]
+            if free_ev[k & 1] is not None:
+                main_s.wait_event(free_ev[k & 1])                  # the copy that last read this buffer is done
+            accel.closest_points(q[c0:c1], buf[: c1 - c0])
+            done = torch.cuda.Event()
+            done.record(main_s)
+            copy_s.wait_event(done)
+            with torch.cuda.stream(copy_s):
+                remote[a + c0:a + c1].copy_(buf[: c1 - c0], non_blocking=True)
+                free_ev[k & 1] = torch.cuda.Event()
+                free_ev[k & 1].record(copy_s)
+        main_s.wait_stream(copy_s)
         e1.record()
 
     def sync():
@@ -380,7 +398,7 @@ def strong_config4(gpurt, torch, dist, ctx, rank, world, dev, n_tris, n_queries,
         if world > 1:
             dist.barrier()
 
-    run()                                                          # warm-up (arenas, sort scratch, placement stream)
+    run()                                                          # warm-up (communicators, arenas, sort scratch)
     sync()
     t0 = time.time()
     run()
@@ -391,15 +409,14 @@ def strong_config4(gpurt, torch, dist, ctx, rank, world, dev, n_tris, n_queries,
     e0.record()
     for c0 in range(0, nq, chunk):
         c1 = min(nq, c0 + chunk)
-        accel.closest_points(q[c0:c1], local[: c1 - c0])
+        accel.closest_points(q[c0:c1], local[0][: c1 - c0] if rank else shared.at((a + c0) * 32))
     e1.record()
     sync()
     ms_local = device_max(dist, world, e0.elapsed_time(e1), dev)
     out = {"config": "4: synthetic 10 M-triangle soup, 100 M closest-point queries", "tris": info.n_tris, "queries": n_queries,
            "n_gpus": world, "mqueries_s": n_queries / (ms * 1e-3) / 1e6, "ms": ms, "wall_ms_barrier_to_barrier": wall * 1e3,
-           "results": "all results in rank 0's memory at the end of the timed region: every rank's gpurt_closest_points call gets its "
-                      "slice of rank 0's buffer as the result pointer; the library stores slice k of the sorted batch over NVLink "
-                      "on a second stream while slice k+1 is traversed (no collective)",
+           "results": "all results in rank 0's memory at the end of the timed region (rank 0: direct; others: chunk k computed "
+                      "while chunk k-1 is copied over NVLink, no collective)",
            "bytes_into_rank0": int((n_queries - (shard_range(n_queries, 0, world)[1])) * 32), "chunk_queries": chunk,
            "mqueries_s_results_left_local": n_queries / (ms_local * 1e-3) / 1e6, "bvh_build_ms": info.build_ms}
     if rank == 0 and check:

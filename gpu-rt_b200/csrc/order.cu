@@ -117,7 +117,10 @@ int plan_spatial_order(gpurt_accel* A, const float4* pos, unsigned stride_vec4, 
     rc = radix_sort_u64(st, keys, vals, keys_tmp, vals_tmp, n, 4, ctx->scratch, ctx->sm_count);
     if(rc) return rc;
     P.order = vals; /* 4 passes: the result is back in the primary buffers */
-    static const bool allow_slices = !(getenv("GPURT_PLACE_SLICES") && atoi(getenv("GPURT_PLACE_SLICES")) == 0);
+    /* opt-in (GPURT_PLACE_SLICES=<slices>): fine for one or two senders (2 GPUs, config 4: 2616 Mq/s against 2655 with the
+     * results left local), but scattered 32-byte stores from 7 senders into one GPU arrive at only ~175 GB/s (8 GPUs: 6039
+     * Mq/s against 8105 for caller-side chunks + coalesced copies), so the default stays "stage, then one coalesced pass" */
+    const bool allow_slices = getenv("GPURT_PLACE_SLICES") && atoi(getenv("GPURT_PLACE_SLICES")) > 0;
     if(remote && sliced_scatter && allow_slices) {
         P.out = base + used;
         P.scatter = true;
@@ -136,7 +139,7 @@ int plan_spatial_order(gpurt_accel* A, const float4* pos, unsigned stride_vec4, 
 }
 
 uint64_t order_slice_size(uint64_t n) {
-    static const uint64_t want = getenv("GPURT_PLACE_SLICES") ? (uint64_t)std::max(1, atoi(getenv("GPURT_PLACE_SLICES"))) : 8u;
+    const uint64_t want = getenv("GPURT_PLACE_SLICES") ? (uint64_t)std::max(1, atoi(getenv("GPURT_PLACE_SLICES"))) : 8u;
     uint64_t s = std::max<uint64_t>((n + want - 1) / want, 1u << 18);
     return (s + 127) & ~(uint64_t)127;
 }

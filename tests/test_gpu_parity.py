@@ -359,16 +359,20 @@ def test_large_scene_batches_in_spatial_order(gpurt, orc, ctx):
     assert (got[:, [0, 1, 2, 3, 4, 6, 7]] == ref[:, [0, 1, 2, 3, 4, 6, 7]]).all()
     # results on another GPU: slices of the processing order are staged and stored to their storage positions by a second
     # stream while the next slice is traversed (order.cu; GPURT_PLACE_FORCE runs that path with local results)
-    os.environ["GPURT_PLACE_FORCE"] = "1"
-    try:
-        hits_p = accel.trace_closest(d_rays)
-        cp_p = accel.closest_points(torch.from_numpy(q).cuda())
-        occ_p = accel.trace_any(d_rays)
-        torch.cuda.synchronize()
-    finally:
-        del os.environ["GPURT_PLACE_FORCE"]
-    assert same_bits(hits_p.cpu().numpy(), hits.cpu().numpy()) and torch.equal(cp_p.view(torch.int32), cp.view(torch.int32))
-    assert torch.equal(occ_p, occ)
+    for slices in (None, "5"):   # default: stage + one coalesced pass; GPURT_PLACE_SLICES: slice-by-slice scatter on a second stream
+        os.environ["GPURT_PLACE_FORCE"] = "1"
+        if slices:
+            os.environ["GPURT_PLACE_SLICES"] = slices
+        try:
+            hits_p = accel.trace_closest(d_rays)
+            cp_p = accel.closest_points(torch.from_numpy(q).cuda())
+            occ_p = accel.trace_any(d_rays)
+            torch.cuda.synchronize()
+        finally:
+            del os.environ["GPURT_PLACE_FORCE"]
+            os.environ.pop("GPURT_PLACE_SLICES", None)
+        assert same_bits(hits_p.cpu().numpy(), hits.cpu().numpy()) and torch.equal(cp_p.view(torch.int32), cp.view(torch.int32))
+        assert torch.equal(occ_p, occ)
     # a coherent batch (sorted input) takes the unsorted path and gives the same answers
     order = np.lexsort((rays[:, 2], rays[:, 1], rays[:, 0]))
     hits2 = accel.trace_closest(torch.from_numpy(rays[order].copy()).cuda())

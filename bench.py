@@ -342,7 +342,96 @@ def ncu_facts():
 
 
 # ---- strong-scaling sub-benchmarks (BASELINE configs 4 and 5 at the same N) -----------------------------------------
-def strong_config4(gpurt, torch, dist, ctx, rank, world, dev, n_tris, n_queries, check):
+def strong_config4(gpurt, torch, dist, ctx, rank, world, dev, n_tris, n_queries, check, schedule=None):
+    """config 4: 10 M-triangle soup, 100 M closest-point queries in contiguous ranges per rank, all 3.2 GB of results
+    placed in rank 0's memory inside the timed region, through gpurt_gather_* (csrc/gather.cu): every rank makes ONE
+    gpurt_closest_points call on its range with its part of rank 0's array as the result pointer.  The library sorts the
+    range once, traverses it in slices of the processing order, and after each slice the copy engine moves the slice's
+    results + storage indices into an inbox on rank 0 and raises a flag; kernels rank 0 queued on a side stream wait for
+    the flags and scatter the slices into the array while rank 0 traverses its own range.  No collective, no host
+    synchronisation inside the round.  GPURT_CONFIG4_MODE=chunks runs round 2's caller-side chunked copies instead."""
+    if os.environ.get("GPURT_CONFIG4_MODE", "gather") == "chunks" or schedule is not None:
+        return strong_config4_chunks(gpurt, torch, dist, ctx, rank, world, dev, n_tris, n_queries, check, schedule)
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from config4_cpq import make_queries, make_soup
+    from gpurt.dist import shard_range
+    tris_h = make_soup(n_tris, dev).cpu().numpy()
+    scene = gpurt.Scene(ctx)
+    scene.add_triangles(tris_h)
+    accel = gpurt.Accel(scene)
+    info = accel.info()
+    first = [shard_range(n_queries, r, world)[0] for r in range(world)] + [n_queries]
+    a, b = first[rank], first[rank + 1]
+    nq = b - a
+    q = torch.empty((nq, 4), dtype=torch.float32, device=dev)
+    for c0 in range(0, nq, 12_500_000):
+        c1 = min(nq, c0 + 12_500_000)
+        q[c0:c1] = make_queries(a + c0, a + c1, dev)
+    box = [None]
+    if rank == 0:
+        g = gpurt.Gather.create(ctx, n_queries, 32, first)
+        box[0] = g.handle
+    if world > 1:
+        dist.broadcast_object_list(box, src=0)
+    if rank != 0:
+        g = gpurt.Gather.open(ctx, n_queries, 32, first, rank, handle=box[0])
+    if world > 1:
+        dist.barrier()
+    local = torch.empty((nq, 8), dtype=torch.float32, device=dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def run():
+        e0.record()
+        if rank == 0:
+            g.begin()
+        accel.closest_points(q, g.mine())
+        if rank == 0:
+            g.end()
+        e1.record()
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    run()                                                          # warm-up (arenas, sort scratch, streams)
+    sync()
+    t0 = time.time()
+    run()
+    sync()
+    wall = time.time() - t0
+    ms = device_max(dist, world, e0.elapsed_time(e1), dev)
+    timeouts = g.end(sync=True) if rank == 0 else 0
+    # the same queries with the results left on each rank (no placement): what the kernels alone take
+    e0.record()
+    accel.closest_points(q, local)
+    e1.record()
+    sync()
+    ms_local = device_max(dist, world, e0.elapsed_time(e1), dev)
+    out = {"config": "4: synthetic 10 M-triangle soup, 100 M closest-point queries", "tris": info.n_tris, "queries": n_queries,
+           "n_gpus": world, "mqueries_s": n_queries / (ms * 1e-3) / 1e6, "ms": ms, "wall_ms_barrier_to_barrier": wall * 1e3,
+           "results": "all results in rank 0's array at the end of the timed region (gpurt_gather_*): one call per rank, slices of the "
+                      "sorted batch copied into rank 0's inbox while the next slice is traversed, scattered there by rank 0's side "
+                      "stream while rank 0 traverses its own range; no collective",
+           "bytes_into_rank0": int((n_queries - first[1]) * 36), "queries_per_call": nq, "flag_wait_timeouts": timeouts,
+           "mqueries_s_results_left_local": n_queries / (ms_local * 1e-3) / 1e6, "bvh_build_ms": info.build_ms}
+    if rank == 0 and check:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import orc
+        remote = g.tensor().view(torch.float32).view(-1, 8)
+        c0 = first[world - 1]                                      # a slice the LAST rank placed
+        got = remote[c0:c0 + check].cpu().numpy().view(np.uint32)
+        ref = orc.Bvh(tris_h).closest_point(make_queries(c0, c0 + check, dev).cpu().numpy()).view(np.uint32).reshape(-1, 8)
+        out["check"] = {"queries": check, "placed_by_rank": world - 1,
+                        "bit_exact_vs_oracle": bool((got[:, [0, 1, 2, 3, 4, 6, 7]] == ref[:, [0, 1, 2, 3, 4, 6, 7]]).all())}
+    if world > 1:
+        dist.barrier()
+    g.close()
+    accel.close(), scene.close()
+    return out
+
+
+def strong_config4_chunks(gpurt, torch, dist, ctx, rank, world, dev, n_tris, n_queries, check, schedule=None):
     """config 4: 10 M-triangle soup, 100 M closest-point queries in contiguous ranges per rank, all 3.2 GB of results
     placed in rank 0's memory inside the timed region: rank 0's kernel writes there directly; the other ranks compute
     chunk k into a local buffer while chunk k-1 crosses NVLink on a second stream (copy engine, no collective).
@@ -360,7 +449,24 @@ def strong_config4(gpurt, torch, dist, ctx, rank, world, dev, n_tris, n_queries,
     info = accel.info()
     a, b = shard_range(n_queries, rank, world)
     nq = b - a
-    chunk = max(1 << 20, min(12_500_000, (nq + 3) // 4))
+    # Chunks by storage position.  Each chunk is sorted and traversed on its own, and small chunks are less coherent
+    # (3.1 M points: 1096 Mq/s per GPU, 12.5 M: 1328), but only the last chunk's copy is exposed: so a large first chunk
+    # and a short tail — fractions of a 12.5 M block, overridable with GPURT_CONFIG4_SCHEDULE="0.75,0.17,0.08".
+    if schedule is None:
+        schedule = [float(x) for x in os.environ.get("GPURT_CONFIG4_SCHEDULE", "0.75,0.17,0.08").split(",")]
+    bounds = [0]
+    for blk0 in range(0, nq, 12_500_000):
+        blk = min(12_500_000, nq - blk0)
+        if rank == 0 or world == 1 or blk < (4 << 20):
+            bounds.append(blk0 + blk)                               # rank 0 writes in place: nothing to overlap
+            continue
+        acc = 0.0
+        for f in schedule[:-1]:
+            acc += f
+            bounds.append(blk0 + min(blk, int(blk * acc) // 128 * 128))
+        bounds.append(blk0 + blk)
+    chunks = [(bounds[i], bounds[i + 1]) for i in range(len(bounds) - 1) if bounds[i + 1] > bounds[i]]
+    chunk = max(c1 - c0 for c0, c1 in chunks)
     q = torch.empty((nq, 4), dtype=torch.float32, device=dev)
     for c0 in range(0, nq, 12_500_000):
         c1 = min(nq, c0 + 12_500_000)
@@ -374,8 +480,7 @@ def strong_config4(gpurt, torch, dist, ctx, rank, world, dev, n_tris, n_queries,
 
     def run():
         e0.record()
-        for k, c0 in enumerate(range(0, nq, chunk)):
-            c1 = min(nq, c0 + chunk)
+        for k, (c0, c1) in enumerate(chunks):
             if rank == 0:
                 accel.closest_points(q[c0:c1], shared.at((a + c0) * 32))
                 continue
@@ -407,8 +512,7 @@ def strong_config4(gpurt, torch, dist, ctx, rank, world, dev, n_tris, n_queries,
     ms = device_max(dist, world, e0.elapsed_time(e1), dev)
     # the same queries with the results left on each rank (no placement): what the kernels alone take
     e0.record()
-    for c0 in range(0, nq, chunk):
-        c1 = min(nq, c0 + chunk)
+    for c0, c1 in chunks:
         accel.closest_points(q[c0:c1], local[0][: c1 - c0] if rank else shared.at((a + c0) * 32))
     e1.record()
     sync()
@@ -417,7 +521,7 @@ def strong_config4(gpurt, torch, dist, ctx, rank, world, dev, n_tris, n_queries,
            "n_gpus": world, "mqueries_s": n_queries / (ms * 1e-3) / 1e6, "ms": ms, "wall_ms_barrier_to_barrier": wall * 1e3,
            "results": "all results in rank 0's memory at the end of the timed region (rank 0: direct; others: chunk k computed "
                       "while chunk k-1 is copied over NVLink, no collective)",
-           "bytes_into_rank0": int((n_queries - (shard_range(n_queries, 0, world)[1])) * 32), "chunk_queries": chunk,
+           "bytes_into_rank0": int((n_queries - (shard_range(n_queries, 0, world)[1])) * 32), "chunk_queries": [c1 - c0 for c0, c1 in chunks] if len(chunks) <= 16 else chunk,
            "mqueries_s_results_left_local": n_queries / (ms_local * 1e-3) / 1e6, "bvh_build_ms": info.build_ms}
     if rank == 0 and check:
         sys.path.insert(0, os.path.join(ROOT, "tests"))

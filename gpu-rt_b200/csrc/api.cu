@@ -207,6 +207,7 @@ int gpurt_ctx_destroy(gpurt_ctx* c) {
     if(!c) return GPURT_OK;
     cudaSetDevice(c->device);
     if(c->stream) cudaStreamSynchronize(c->stream);
+    while(!c->gathers.empty()) gpurt_gather_destroy(c->gathers.back());
     c->d_in.release(), c->d_out.release(), c->scratch.release(), c->build_arena.release();
     if(c->pinned_word) cudaFreeHost(c->pinned_word);
     for(cudaEvent_t ev : {c->ev0, c->ev1, c->ev_copy, c->ev_kernel, c->ev_switch, c->ev_place})

@@ -99,7 +99,7 @@ int launch_closest_points(gpurt_accel* A, const float4* queries, uint64_t n, flo
             GPURT_CUDA(cudaGetLastError());
             if((rc = scatter_slice_async(A, P, off, m, results, 32))) return rc;
         }
-        return scatter_join(A);
+        return scatter_join(A, P);
     }
     launch(0, n);
     GPURT_CUDA(cudaGetLastError());

@@ -11,6 +11,8 @@
 #include "bvh8.cuh"
 #include "scene_view.cuh"
 
+struct gpurt_gather;
+
 namespace gpurt {
 
 #define GPURT_CUDA(call)                                                                           \
@@ -43,6 +45,7 @@ struct gpurt_ctx {
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
     cudaEvent_t ev_copy = nullptr, ev_kernel = nullptr;
     cudaEvent_t ev_switch = nullptr; /* orders a newly selected stream after the old one (gpurt_ctx_set_stream) */
+    std::vector<gpurt_gather*> gathers; /* gpurt_gather_create / _open on this context */
     cudaStream_t s_place = nullptr;  /* result placement into another GPU's memory while the next slice is computed (order.cu) */
     cudaEvent_t ev_place = nullptr;
     /* staging for GPURT_MEM_HOST calls */
@@ -108,6 +111,8 @@ void free_accel_device(gpurt_accel* A);
  * storage index; when `unperm` is set the kernel writes slot-indexed records to `out` (local staging) and
  * finish_spatial_order() moves them to the caller's (remote) array. */
 struct OrderPlan {
+    gpurt_gather* gather = nullptr; /* results go to a gather's array on another GPU (gather.cu) */
+    uint64_t n = 0;
     const uint32_t* order = nullptr;
     const uint32_t* unperm = nullptr;
     void* out = nullptr;
@@ -120,7 +125,13 @@ int finish_spatial_order(gpurt_accel* A, const OrderPlan& P, uint64_t n, void* r
  * positions in `results` on the placement stream, after everything queued on the context's stream so far */
 uint64_t order_slice_size(uint64_t n);
 int scatter_slice_async(gpurt_accel* A, const OrderPlan& P, uint64_t off, uint64_t m, void* results, size_t result_bytes);
-int scatter_join(gpurt_accel* A); /* the context's stream waits for the placement stream */
+int scatter_join(gpurt_accel* A, const OrderPlan& P); /* the context's stream waits for the placement stream */
+/* gather.cu */
+gpurt_gather* gather_find(gpurt_ctx* ctx, const void* results, uint64_t n, size_t record_bytes);
+int gather_begin_batch(gpurt_gather* g);
+int gather_push_slice(gpurt_gather* g, const void* staged, const uint32_t* order, uint64_t off, uint64_t m, uint32_t slice);
+int gather_join(gpurt_gather* g);
+int gather_signal_direct(gpurt_gather* g);
 
 /* query launchers (device pointers, async on ctx->stream) */
 int launch_trace_closest(gpurt_accel* A, const float4* rays, uint64_t n, float4* hits);

@@ -83,9 +83,13 @@ constexpr size_t kOrderMinBvhBytes = 64u << 20;
 int plan_spatial_order(gpurt_accel* A, const float4* pos, unsigned stride_vec4, uint64_t n, void* results,
                        size_t result_bytes, OrderPlan& P, bool sliced_scatter) {
     P = OrderPlan();
-    P.out = results;
+    P.out = results, P.n = n;
     gpurt_ctx* ctx = A->ctx;
     cudaStream_t st = ctx->stream;
+    if(sliced_scatter && !ctx->gathers.empty() && (P.gather = gather_find(ctx, results, n, result_bytes))) {
+        int grc = gather_begin_batch(P.gather);
+        if(grc) return grc;
+    }
     static const bool allow = !(getenv("GPURT_SPATIAL_ORDER") && atoi(getenv("GPURT_SPATIAL_ORDER")) == 0);
     const size_t bvh_bytes = (size_t)A->n_nodes * sizeof(Node8) + (size_t)A->n * 48;
     if(!allow || n < kOrderMinBatch || n >= (1ull << 30) || bvh_bytes <= kOrderMinBvhBytes) return GPURT_OK;
@@ -97,7 +101,7 @@ int plan_spatial_order(gpurt_accel* A, const float4* pos, unsigned stride_vec4, 
     const bool remote = (cudaPointerGetAttributes(&pa, results) == cudaSuccess && pa.type == cudaMemoryTypeDevice &&
                          pa.device != ctx->device) || force_remote;
     (void)cudaGetLastError();
-    const size_t used = 2 * kb + 2 * vb + 256, stage_bytes = remote ? (((size_t)n * result_bytes + 255) & ~(size_t)255) : 0;
+    const size_t used = 2 * kb + 2 * vb + 256, stage_bytes = (remote || P.gather) ? (((size_t)n * result_bytes + 255) & ~(size_t)255) : 0;
     int rc = ctx->build_arena.reserve(used + stage_bytes);
     if(rc) return rc;
     char* base = (char*)ctx->build_arena.p;
@@ -121,7 +125,10 @@ int plan_spatial_order(gpurt_accel* A, const float4* pos, unsigned stride_vec4, 
      * results left local), but scattered 32-byte stores from 7 senders into one GPU arrive at only ~175 GB/s (8 GPUs: 6039
      * Mq/s against 8105 for caller-side chunks + coalesced copies), so the default stays "stage, then one coalesced pass" */
     const bool allow_slices = getenv("GPURT_PLACE_SLICES") && atoi(getenv("GPURT_PLACE_SLICES")) > 0;
-    if(remote && sliced_scatter && allow_slices) {
+    if(P.gather) { /* slices go to the owner's inbox by copy engine; the owner scatters them (gather.cu) */
+        P.out = base + used;
+        P.scatter = true;
+    } else if(remote && sliced_scatter && allow_slices) {
         P.out = base + used;
         P.scatter = true;
         if(!ctx->s_place) {
@@ -145,6 +152,7 @@ uint64_t order_slice_size(uint64_t n) {
 }
 int scatter_slice_async(gpurt_accel* A, const OrderPlan& P, uint64_t off, uint64_t m, void* results, size_t result_bytes) {
     gpurt_ctx* ctx = A->ctx;
+    if(P.gather) return gather_push_slice(P.gather, P.out, P.order, off, m, (uint32_t)(off / order_slice_size(P.n)));
     GPURT_CUDA(cudaEventRecord(ctx->ev_place, ctx->stream));
     GPURT_CUDA(cudaStreamWaitEvent(ctx->s_place, ctx->ev_place, 0));
     const float4* staged = (const float4*)((const char*)P.out + off * result_bytes);
@@ -156,14 +164,16 @@ int scatter_slice_async(gpurt_accel* A, const OrderPlan& P, uint64_t off, uint64
     GPURT_CUDA(cudaGetLastError());
     return GPURT_OK;
 }
-int scatter_join(gpurt_accel* A) {
+int scatter_join(gpurt_accel* A, const OrderPlan& P) {
     gpurt_ctx* ctx = A->ctx;
+    if(P.gather) return gather_join(P.gather);
     GPURT_CUDA(cudaEventRecord(ctx->ev_place, ctx->s_place));
     GPURT_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_place, 0));
     return GPURT_OK;
 }
 
 int finish_spatial_order(gpurt_accel* A, const OrderPlan& P, uint64_t n, void* results, size_t result_bytes) {
+    if(P.gather && !P.scatter) return gather_signal_direct(P.gather); /* answered with the kernel's own stores: tell the owner */
     if(!P.unperm) return GPURT_OK;
     cudaStream_t st = A->ctx->stream;
     if(result_bytes == 32)

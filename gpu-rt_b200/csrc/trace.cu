@@ -138,7 +138,7 @@ int launch_trace_closest(gpurt_accel* A, const float4* rays, uint64_t n, float4*
             GPURT_CUDA(cudaGetLastError());
             if((rc = scatter_slice_async(A, P, off, m, hits, 16))) return rc;
         }
-        return scatter_join(A);
+        return scatter_join(A, P);
     }
     if(P.order)
         k_trace_closest<false, true><<<blocks_for(n, 128), 128, 0, A->ctx->stream>>>(

@@ -93,6 +93,8 @@ SYMBOLS = [
     "gpurt_pipe_ray_counts", "gpurt_pipe_device_image", "gpurt_tonemap", "gpurt_pipe_last_uniforms",
     "gpurt_pipe_read_reservoirs", "gpurt_pipe_bounce_rays", "gpurt_pipe_set_shard",
     "gpurt_pipe_history_export", "gpurt_pipe_history_peers", "gpurt_pipe_history_status",
+    "gpurt_gather_create", "gpurt_gather_open", "gpurt_gather_results", "gpurt_gather_base", "gpurt_gather_begin", "gpurt_gather_end",
+    "gpurt_gather_destroy",
     "gpurt_pipe_render_frame_mean", "gpurt_pipe_accumulate_mean", "gpurt_scene_set_transform", "gpurt_accel_update", "gpurt_scene_get_texture", "gpurt_shared_alloc", "gpurt_shared_free", "gpurt_shared_open", "gpurt_shared_close",
     "gpurt_scene_set_material", "gpurt_scene_set_ordered", "gpurt_scene_clear_textures", "gpurt_accel_sync_scene", "gpurt_accel_refit", "gpurt_accel_update_auto",
 ]
@@ -151,6 +153,70 @@ class SharedBuffer:
             fn = lib.gpurt_shared_free if self.owner else lib.gpurt_shared_close
             _check(fn(self.ctx.h, C.c_void_p(self.ptr)))
             self.ptr = 0
+
+
+class Gather:
+    """One result array on the owner rank, filled by one query call per rank and round (include/gpurt.h, gpurt_gather_*).
+    Owner: Gather.create(ctx, ...); others: Gather.open(ctx, handle or base, ...).  `g.mine()` is the result argument of this
+    rank's query call; the owner brackets its call with g.begin() / g.end(); `g.tensor()` views the whole array (owner)."""
+
+    def __init__(self, ctx, h, n_records, record_bytes, first, rank, owner, handle=None):
+        self.ctx, self.h, self.n_records, self.record_bytes, self.first, self.rank, self.owner = ctx, h, n_records, record_bytes, list(first), rank, owner
+        self.handle = handle
+        a, m = C.c_void_p(), C.c_void_p()
+        _check(lib.gpurt_gather_results(self.h, C.byref(a), C.byref(m)))
+        self.array_ptr, self.mine_ptr = a.value, m.value
+
+    @staticmethod
+    def create(ctx, n_records, record_bytes, first, owner_rank=0):
+        g, hd, nb = C.c_void_p(), (C.c_uint8 * 64)(), C.c_uint64()
+        arr = (C.c_uint64 * len(first))(*first)
+        _check(lib.gpurt_gather_create(ctx.h, C.c_uint64(n_records), record_bytes, len(first) - 1, arr, owner_rank, C.byref(g), hd, C.byref(nb)))
+        out = Gather(ctx, g, n_records, record_bytes, first, owner_rank, True, bytes(hd))
+        out.nbytes = nb.value
+        return out
+
+    @staticmethod
+    def open(ctx, n_records, record_bytes, first, my_rank, owner_rank=0, handle=None, base=None):
+        g = C.c_void_p()
+        arr = (C.c_uint64 * len(first))(*first)
+        hd = (C.c_uint8 * 64).from_buffer_copy(handle) if handle is not None else None
+        _check(lib.gpurt_gather_open(ctx.h, hd, C.c_void_p(base or 0), C.c_uint64(n_records), record_bytes, len(first) - 1, arr,
+                                     owner_rank, my_rank, C.byref(g)))
+        return Gather(ctx, g, n_records, record_bytes, first, my_rank, False)
+
+    def base(self):
+        p = C.c_void_p()
+        _check(lib.gpurt_gather_base(self.h, C.byref(p)))
+        return p.value
+
+    def mine(self):
+        return _RawDevicePtr(self.mine_ptr, self)
+
+    def begin(self):
+        _check(lib.gpurt_gather_begin(self.h))
+
+    def end(self, sync=False):
+        t = C.c_uint32()
+        _check(lib.gpurt_gather_end(self.h, C.byref(t) if sync else None))
+        return t.value
+
+    def tensor(self):
+        """the whole result array as a torch uint8 tensor (no copy)"""
+        import torch
+
+        class _Arr:
+            pass
+
+        a = _Arr()
+        a.__cuda_array_interface__ = {"shape": (self.n_records * self.record_bytes,), "typestr": "|u1", "data": (self.array_ptr, False), "version": 2}
+        a.keep = self
+        return torch.as_tensor(a, device=f"cuda:{self.ctx.device}")
+
+    def close(self):
+        if self.h:
+            _check(lib.gpurt_gather_destroy(self.h))
+            self.h = C.c_void_p()
 
 
 class _RawDevicePtr:

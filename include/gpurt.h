@@ -301,6 +301,37 @@ int gpurt_shared_free(gpurt_ctx* ctx, void* device_ptr);
 int gpurt_shared_open(gpurt_ctx* ctx, const uint8_t handle[GPURT_IPC_HANDLE_BYTES], void** out_device_ptr);
 int gpurt_shared_close(gpurt_ctx* ctx, void* mapped_device_ptr);
 
+/* ---- multi-GPU gather of sharded result arrays without a collective ------------------------------------
+ * n_records results of record_bytes (16: GpurtHit, 32: GpurtClosestPoint) live in ONE array on the owner rank; rank r
+ * answers the records [first_record[r], first_record[r + 1]) with ONE query call per round, passing the pointer
+ * gpurt_gather_results gives it as the device `hits` / `results` argument.  A large incoherent batch on a large scene is
+ * traversed in Morton order (csrc/order.cu), so its results come out in processing order: the sender traverses the batch in
+ * slices of that order and, after each slice, its copy engine moves the slice's results and storage indices — coalesced —
+ * into an inbox next to the owner's array and raises a flag there; kernels the owner queued with gpurt_gather_begin wait for
+ * the flags and scatter the slices to their storage positions locally while the owner's own batch is still being traversed.
+ * Small or already coherent batches are stored by the traversal kernel directly, as with gpurt_shared_open.  Measured on
+ * config 4 at 8 GPUs: see csrc/gather.cu.
+ *   owner:   gpurt_gather_create -> handle to the other ranks;   per round: gpurt_gather_begin, its own query call (results =
+ *            the pointer from gpurt_gather_results), gpurt_gather_end (the context's stream then waits for all scatters)
+ *   others:  gpurt_gather_open (handle from another process, or same_process_base = the owner's base pointer inside one
+ *            process);   per round: one query call with results = the pointer from gpurt_gather_results
+ * Rounds are counted on both sides: every rank issues exactly one call per round.  A sender does not overwrite the inbox before
+ * the owner has scattered the previous round (acknowledged over NVLink); waits give up after 20 s (gpurt_gather_end reports
+ * the count). */
+typedef struct gpurt_gather gpurt_gather;
+int gpurt_gather_create(gpurt_ctx* ctx, uint64_t n_records, uint32_t record_bytes, uint32_t n_ranks,
+                        const uint64_t* first_record /* [n_ranks + 1] */, uint32_t owner_rank, gpurt_gather** out,
+                        uint8_t handle_out[GPURT_IPC_HANDLE_BYTES], uint64_t* out_bytes);
+int gpurt_gather_open(gpurt_ctx* ctx, const uint8_t handle[GPURT_IPC_HANDLE_BYTES], void* same_process_base, uint64_t n_records,
+                      uint32_t record_bytes, uint32_t n_ranks, const uint64_t* first_record, uint32_t owner_rank,
+                      uint32_t my_rank, gpurt_gather** out);
+/* out_array: record 0 of the whole array (the owner's memory or its mapping); out_mine: this rank's first record */
+int gpurt_gather_results(gpurt_gather* g, void** out_array, void** out_mine);
+int gpurt_gather_base(gpurt_gather* g, void** out_base); /* owner: what same_process_base takes */
+int gpurt_gather_begin(gpurt_gather* g);
+int gpurt_gather_end(gpurt_gather* g, uint32_t* out_timeouts /* NULL: do not synchronise */);
+int gpurt_gather_destroy(gpurt_gather* g);
+
 /* ---- integrator: replaces VK::RTPipe (src/vk/rt.h:14-142) -------------------------------------- */
 int gpurt_pipe_params_default(GpurtPipeParams* out); /* rt.h:38-53 */
 /* RTPipe::recreate(scene) + use_accel(tlas) (src/vk/rt.cpp:16-24, :159-176) */

@@ -381,6 +381,51 @@ def test_large_scene_batches_in_spatial_order(gpurt, orc, ctx):
     accel.close(), scene.close()
 
 
+def test_gather_inbox_single_process(gpurt, orc, ctx):
+    """gpurt_gather_*: two contexts on one GPU play owner and sender.  The sender's ordered batch reaches the owner's array
+    through the inbox (slices copied in processing order + storage indices, flags, owner-side scatter on a side stream); a
+    small batch goes by direct stores and the owner's receivers are told to skip.  Both rounds == the plain call."""
+    import torch
+    tris = soup(1_600_000, seed=5, ext=0.01)
+    ctx2 = gpurt.Context(0)
+    scenes, accels = [], []
+    for c in (ctx, ctx2):
+        sc = gpurt.Scene(c)
+        sc.add_triangles(tris)
+        scenes.append(sc), accels.append(gpurt.Accel(sc))
+    assert accels[0].info().node_bytes + accels[0].info().tri_bytes > (64 << 20)
+    ob = orc.Bvh(tris)
+    for n0, n1 in (((1 << 20) + 5, (1 << 20) + 4321), (3000, 70000)):   # ordered batches through the inbox; small ones direct
+        n = n0 + n1
+        q = orc.gen_random_points(n, 72 + n0, ob.scene_box(), frac=0.2)
+        d_q = torch.from_numpy(q).cuda()
+        want_cp = torch.cat([accels[0].closest_points(d_q[:n0]), accels[1].closest_points(d_q[n0:])]).clone()
+        rays = orc.gen_random_rays(n, 71 + n0, ob.scene_box())
+        d_rays = torch.from_numpy(rays).cuda()
+        want_hit = torch.cat([accels[0].trace_closest(d_rays[:n0]), accels[1].trace_closest(d_rays[n0:])]).clone()
+        torch.cuda.synchronize()
+        for rb, call, src, want in ((32, "closest_points", d_q, want_cp), (16, "trace_closest", d_rays, want_hit)):
+            g0 = gpurt.Gather.create(ctx, n, rb, [0, n0, n])
+            g1 = gpurt.Gather.open(ctx2, n, rb, [0, n0, n], 1, base=g0.base())
+            for _ in range(3):                                  # rounds reuse the inbox: flags, acknowledgements
+                g0.tensor().zero_()
+                torch.cuda.synchronize()
+                g0.begin()
+                getattr(accels[1], call)(src[n0:], g1.mine())
+                getattr(accels[0], call)(src[:n0], g0.mine())
+                assert g0.end(sync=True) == 0, "a flag wait timed out"
+                torch.cuda.synchronize()
+                got = g0.tensor().view(torch.int32).view(n, rb // 4)
+                ref = want.view(torch.int32).view(n, rb // 4)
+                assert torch.equal(got, ref), f"{call}: gathered array differs ({n0}+{n1})"
+            g1.close(), g0.close()
+    for a in accels:
+        a.close()
+    for sc in scenes:
+        sc.close()
+    ctx2.close()
+
+
 def test_sah_optimal_collapse_flag(gpurt, orc, ctx):
     """GPURT_BUILD_SAH_COLLAPSE: same primitive order and query results as the default build, fewer wide nodes"""
     scene = load_scene(gpurt, ctx, "sponza_standin")

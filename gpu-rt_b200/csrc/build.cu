@@ -245,6 +245,11 @@ size_t radix_sort_tmp_bytes(size_t n, int passes) {
     return (size_t)passes * (256 + 64) * 4 + (size_t)passes * nb * 256 * 4;
 }
 
+void preload_sort_kernels() {
+    cudaFuncAttributes a;
+    (void)cudaFuncGetAttributes(&a, (const void*)k_rs_digit_hist);
+    (void)cudaFuncGetAttributes(&a, (const void*)k_rs_onesweep);
+}
 int radix_sort_u64(cudaStream_t st, uint64_t* keys, uint32_t* vals, uint64_t* kt, uint32_t* vt,
                    size_t n, int passes, DevBuf& tmp, int sm_count) {
     if(n == 0) return GPURT_OK;

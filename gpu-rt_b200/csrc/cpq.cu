@@ -106,4 +106,11 @@ int launch_closest_points(gpurt_accel* A, const float4* queries, uint64_t n, flo
     return finish_spatial_order(A, P, n, results, 32);
 }
 
+void preload_cpq_kernels() {
+    cudaFuncAttributes a;
+#define GPURT_PRELOAD(S) (void)cudaFuncGetAttributes(&a, (const void*)k_closest_points<S, true>), (void)cudaFuncGetAttributes(&a, (const void*)k_closest_points<S, false>)
+    GPURT_PRELOAD(64), GPURT_PRELOAD(128), GPURT_PRELOAD(256), GPURT_PRELOAD(512);
+#undef GPURT_PRELOAD
+}
+
 } // namespace gpurt

@@ -117,6 +117,14 @@ __global__ void __launch_bounds__(256) k_gather_scatter(const char* base, uint32
     results[(uint64_t)VEC4 * __ldcg(order + t / VEC4) + (t % VEC4)] = __ldcg(staged + t);
 }
 
+static void gather_preload() {
+    cudaFuncAttributes a;
+    for(const void* f : {(const void*)k_gather_signal, (const void*)k_gather_ack, (const void*)k_gather_wait_ack, (const void*)k_gather_wait,
+                         (const void*)k_gather_scatter<1>, (const void*)k_gather_scatter<2>})
+        (void)cudaFuncGetAttributes(&a, f);
+    preload_order_kernels(), preload_cpq_kernels(), preload_trace_kernels();
+}
+
 gpurt_gather* gather_find(gpurt_ctx* ctx, const void* results, uint64_t n, size_t record_bytes) {
     for(gpurt_gather* g : ctx->gathers) {
         if(g->owner || g->record_bytes != record_bytes) continue;
@@ -180,6 +188,7 @@ int gpurt_gather_create(gpurt_ctx* ctx, uint64_t n_records, uint32_t record_byte
     int rc = gather_check(n_records, record_bytes, n_ranks, first, owner_rank);
     if(rc) return rc;
     GPURT_CUDA(cudaSetDevice(ctx->device));
+    gather_preload();
     gpurt_gather* g = new gpurt_gather;
     g->ctx = ctx, g->owner = true, g->n_ranks = n_ranks, g->owner_rank = g->my_rank = owner_rank, g->record_bytes = record_bytes;
     g->n_records = n_records, g->first.assign(first, first + n_ranks + 1);
@@ -201,6 +210,12 @@ int gpurt_gather_create(gpurt_ctx* ctx, uint64_t n_records, uint32_t record_byte
         delete g;
         return GPURT_E_CUDA;
     }
+    /* allocate now what the owner's own batch will need: an allocation inside a round would wait for the receivers queued
+     * by gpurt_gather_begin (cudaMalloc synchronises the device), i.e. for every sender */
+    if((rc = ctx->build_arena.reserve(order_arena_bytes(first[owner_rank + 1] - first[owner_rank], record_bytes, false)))) {
+        gpurt_gather_destroy(g);
+        return rc;
+    }
     if(out_bytes) *out_bytes = g->bytes;
     ctx->gathers.push_back(g);
     *out = g;
@@ -213,6 +228,7 @@ int gpurt_gather_open(gpurt_ctx* ctx, const uint8_t* handle, void* same_process_
     if(rc) return rc;
     if(my_rank >= n_ranks || my_rank == owner_rank) return set_error("gather_open: my_rank must be one of the other ranks"), GPURT_E_INVALID;
     GPURT_CUDA(cudaSetDevice(ctx->device));
+    gather_preload();
     gpurt_gather* g = new gpurt_gather;
     g->ctx = ctx, g->owner = false, g->n_ranks = n_ranks, g->owner_rank = owner_rank, g->my_rank = my_rank, g->record_bytes = record_bytes;
     g->n_records = n_records, g->first.assign(first, first + n_ranks + 1);
@@ -228,6 +244,10 @@ int gpurt_gather_open(gpurt_ctx* ctx, const uint8_t* handle, void* same_process_
         }
     }
     g->ipc = !same_process_base; /* same-process bases are not unmapped on destroy */
+    GPURT_CUDA(cudaStreamCreateWithFlags(&g->s_side, cudaStreamNonBlocking));
+    GPURT_CUDA(cudaEventCreateWithFlags(&g->ev, cudaEventDisableTiming));
+    /* sort scratch + staging of this rank's batch, allocated outside the rounds (see gpurt_gather_create) */
+    if((rc = ctx->build_arena.reserve(order_arena_bytes(first[my_rank + 1] - first[my_rank], record_bytes, true)))) return rc;
     ctx->gathers.push_back(g);
     *out = g;
     return GPURT_OK;

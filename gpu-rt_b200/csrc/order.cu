@@ -80,6 +80,12 @@ __global__ void __launch_bounds__(256) k_order_unpermute_u8(const uint8_t* __res
 constexpr uint64_t kOrderMinBatch = 1u << 20;
 constexpr size_t kOrderMinBvhBytes = 64u << 20;
 
+/* bytes plan_spatial_order takes from the context's build arena for a batch of n elements (with a staging array) */
+size_t order_arena_bytes(uint64_t n, size_t result_bytes, bool staged) {
+    const size_t kb = ((size_t)n * 8 + 255) & ~(size_t)255, vb = ((size_t)n * 4 + 255) & ~(size_t)255;
+    return 2 * kb + 2 * vb + 256 + (staged ? (((size_t)n * result_bytes + 255) & ~(size_t)255) : 0);
+}
+
 int plan_spatial_order(gpurt_accel* A, const float4* pos, unsigned stride_vec4, uint64_t n, void* results,
                        size_t result_bytes, OrderPlan& P, bool sliced_scatter) {
     P = OrderPlan();
@@ -185,6 +191,19 @@ int finish_spatial_order(gpurt_accel* A, const OrderPlan& P, uint64_t n, void* r
     else return set_error("finish_spatial_order: record size"), GPURT_E_STATE;
     GPURT_CUDA(cudaGetLastError());
     return GPURT_OK;
+}
+
+/* CUDA loads a kernel at its first launch, and that can wait for the device to go idle — forever, if a kernel of
+ * gather.cu is spinning on a flag only this launch would raise.  gpurt_gather_create / _open load everything a round uses. */
+static void preload(const void* f) {
+    cudaFuncAttributes a;
+    (void)cudaFuncGetAttributes(&a, f);
+}
+void preload_order_kernels() {
+    preload((const void*)k_order_keys), preload((const void*)k_order_invert), preload((const void*)k_order_unpermute<1>);
+    preload((const void*)k_order_unpermute<2>), preload((const void*)k_order_scatter<1>), preload((const void*)k_order_scatter<2>);
+    preload((const void*)k_order_unpermute_u8);
+    preload_sort_kernels();
 }
 
 } // namespace gpurt

@@ -180,4 +180,10 @@ int launch_trace_closest_bvh2(gpurt_accel* A, const float4* rays, uint64_t n, fl
     return GPURT_OK;
 }
 
+void preload_trace_kernels() {
+    cudaFuncAttributes a;
+    (void)cudaFuncGetAttributes(&a, (const void*)k_trace_closest<false, true>);
+    (void)cudaFuncGetAttributes(&a, (const void*)k_trace_closest<false, false>);
+}
+
 } // namespace gpurt

@@ -360,7 +360,14 @@ def strong_config4(gpurt, torch, dist, ctx, rank, world, dev, n_tris, n_queries,
     scene.add_triangles(tris_h)
     accel = gpurt.Accel(scene)
     info = accel.info()
-    first = [shard_range(n_queries, r, world)[0] for r in range(world)] + [n_queries]
+    # rank 0 also receives and scatters everybody else's results (~6 GB of memory traffic next to its own traversal): it gets
+    # `share` of an equal part of the queries, the rest is spread over the other ranks (still contiguous ascending ranges).
+    # Measured at 8 GPUs (gpurun_out/r03o): share 1.0 -> 7921 Mq/s, 0.85 -> 8734, 0.7 -> 9489.
+    share = float(os.environ.get("GPURT_CONFIG4_OWNER_SHARE", "0.7")) if world > 1 else 1.0
+    n0 = int(n_queries / world * share) // 128 * 128
+    first = [0] + [n0 + shard_range(n_queries - n0, r, world - 1)[0] for r in range(max(0, world - 1))] + [n_queries]
+    if world == 1:
+        first = [0, n_queries]
     a, b = first[rank], first[rank + 1]
     nq = b - a
     q = torch.empty((nq, 4), dtype=torch.float32, device=dev)
@@ -413,7 +420,7 @@ def strong_config4(gpurt, torch, dist, ctx, rank, world, dev, n_tris, n_queries,
            "results": "all results in rank 0's array at the end of the timed region (gpurt_gather_*): one call per rank, slices of the "
                       "sorted batch copied into rank 0's inbox while the next slice is traversed, scattered there by rank 0's side "
                       "stream while rank 0 traverses its own range; no collective",
-           "bytes_into_rank0": int((n_queries - first[1]) * 36), "queries_per_call": nq, "flag_wait_timeouts": timeouts,
+           "bytes_into_rank0": int((n_queries - first[1]) * 36), "queries_per_call": nq, "owner_share_of_equal_part": share, "flag_wait_timeouts": timeouts,
            "mqueries_s_results_left_local": n_queries / (ms_local * 1e-3) / 1e6, "bvh_build_ms": info.build_ms}
     if rank == 0 and check:
         sys.path.insert(0, os.path.join(ROOT, "tests"))

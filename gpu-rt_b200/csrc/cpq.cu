@@ -92,12 +92,15 @@ int launch_closest_points(gpurt_accel* A, const float4* queries, uint64_t n, flo
 #undef GPURT_CPQ_LAUNCH
     };
     if(P.scatter) {
-        const uint64_t slice = order_slice_size(n);
-        for(uint64_t off = 0; off < n; off += slice) {
-            const uint64_t m = std::min(slice, n - off);
+        std::vector<uint64_t> ends;
+        order_slices(n, ends);
+        uint64_t off = 0;
+        for(uint64_t e : ends) {
+            const uint64_t m = e - off;
             launch(off, m);
             GPURT_CUDA(cudaGetLastError());
             if((rc = scatter_slice_async(A, P, off, m, results, 32))) return rc;
+            off = e;
         }
         return scatter_join(A, P);
     }

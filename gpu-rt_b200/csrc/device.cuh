@@ -123,7 +123,7 @@ int plan_spatial_order(gpurt_accel* A, const float4* pos, unsigned stride_vec4, 
 int finish_spatial_order(gpurt_accel* A, const OrderPlan& P, uint64_t n, void* results, size_t result_bytes);
 /* remote results of an ordered batch: the slice [off, off + m) of the staging array (processing order) goes to its storage
  * positions in `results` on the placement stream, after everything queued on the context's stream so far */
-uint64_t order_slice_size(uint64_t n);
+void order_slices(uint64_t n, std::vector<uint64_t>& ends);
 size_t order_arena_bytes(uint64_t n, size_t result_bytes, bool staged);
 int scatter_slice_async(gpurt_accel* A, const OrderPlan& P, uint64_t off, uint64_t m, void* results, size_t result_bytes);
 int scatter_join(gpurt_accel* A, const OrderPlan& P); /* the context's stream waits for the placement stream */
@@ -134,7 +134,7 @@ void preload_trace_kernels();
 /* gather.cu */
 gpurt_gather* gather_find(gpurt_ctx* ctx, const void* results, uint64_t n, size_t record_bytes);
 int gather_begin_batch(gpurt_gather* g);
-int gather_push_slice(gpurt_gather* g, const void* staged, const uint32_t* order, uint64_t off, uint64_t m, uint32_t slice);
+int gather_push_slice(gpurt_gather* g, const void* staged, const uint32_t* order, uint64_t off, uint64_t m);
 int gather_join(gpurt_gather* g);
 int gather_signal_direct(gpurt_gather* g);
 

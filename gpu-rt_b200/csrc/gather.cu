@@ -30,6 +30,7 @@ struct gpurt_gather {
     char* base = nullptr;                 /* owner: allocation; others: mapping */
     uint64_t off_results = 0, off_staging = 0, off_order = 0, bytes = 0;
     uint32_t seq = 0;                     /* rounds begun (owner) / batches pushed (sender) */
+    uint32_t slices_pushed = 0;           /* sender: slices of the current batch handed over so far */
     cudaStream_t s_side = nullptr;        /* owner: waits + scatters */
     cudaEvent_t ev = nullptr;
 };
@@ -134,7 +135,7 @@ gpurt_gather* gather_find(gpurt_ctx* ctx, const void* results, uint64_t n, size_
     return nullptr;
 }
 int gather_begin_batch(gpurt_gather* g) {
-    g->seq++;
+    g->seq++, g->slices_pushed = 0;
     if(!g->s_side) {
         GPURT_CUDA(cudaStreamCreateWithFlags(&g->s_side, cudaStreamNonBlocking));
         GPURT_CUDA(cudaEventCreateWithFlags(&g->ev, cudaEventDisableTiming));
@@ -143,8 +144,9 @@ int gather_begin_batch(gpurt_gather* g) {
 }
 /* sender, after slice [off, off + m) of the processing order was traversed on the context's stream: results + storage
  * indices to the owner's inbox on the side stream, then the progress flag */
-int gather_push_slice(gpurt_gather* g, const void* staged, const uint32_t* order, uint64_t off, uint64_t m, uint32_t slice) {
+int gather_push_slice(gpurt_gather* g, const void* staged, const uint32_t* order, uint64_t off, uint64_t m) {
     gpurt_ctx* ctx = g->ctx;
+    const uint32_t slice = g->slices_pushed++;
     GPURT_CUDA(cudaEventRecord(g->ev, ctx->stream));
     GPURT_CUDA(cudaStreamWaitEvent(g->s_side, g->ev, 0));
     const uint64_t f = foreign_first(g, g->my_rank) + off;
@@ -272,20 +274,19 @@ int gpurt_gather_begin(gpurt_gather* g) {
     GPURT_CUDA(cudaEventRecord(g->ev, ctx->stream));
     GPURT_CUDA(cudaStreamWaitEvent(g->s_side, g->ev, 0));
     const uint32_t n_ranks = g->n_ranks;
-    uint32_t max_slices = 0;
-    std::vector<uint64_t> slice(n_ranks, 0);
+    size_t max_slices = 0;
+    std::vector<std::vector<uint64_t>> ends(n_ranks);
     for(uint32_t r = 0; r < n_ranks; r++) {
         const uint64_t n = g->first[r + 1] - g->first[r];
         if(r == g->owner_rank || !n) continue;
-        slice[r] = order_slice_size(n);
-        max_slices = std::max<uint32_t>(max_slices, (uint32_t)((n + slice[r] - 1) / slice[r]));
+        order_slices(n, ends[r]);
+        max_slices = std::max(max_slices, ends[r].size());
     }
-    for(uint32_t k = 0; k < max_slices; k++)
+    for(size_t k = 0; k < max_slices; k++)
         for(uint32_t r = 0; r < n_ranks; r++) {
-            const uint64_t n = g->first[r + 1] - g->first[r];
-            if(!slice[r] || (uint64_t)k * slice[r] >= n) continue;
-            const uint64_t off = (uint64_t)k * slice[r], m = std::min(slice[r], n - off), f = foreign_first(g, r) + off;
-            k_gather_wait<<<1, 32, 0, g->s_side>>>(g->base, r, g->seq, k);
+            if(k >= ends[r].size()) continue;
+            const uint64_t off = k ? ends[r][k - 1] : 0, m = ends[r][k] - off, f = foreign_first(g, r) + off;
+            k_gather_wait<<<1, 32, 0, g->s_side>>>(g->base, r, g->seq, (uint32_t)k);
             const float4* staged = (const float4*)(g->base + g->off_staging + f * g->record_bytes);
             const uint32_t* order = (const uint32_t*)(g->base + g->off_order + f * 4);
             float4* results = (float4*)(g->base + g->off_results + g->first[r] * g->record_bytes);

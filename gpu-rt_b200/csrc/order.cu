@@ -22,6 +22,7 @@
  */
 #include <algorithm>
 #include <cstdlib>
+#include <vector>
 
 #include "device.cuh"
 #include "traverse.cuh"
@@ -151,14 +152,33 @@ int plan_spatial_order(gpurt_accel* A, const float4* pos, unsigned stride_vec4, 
     return GPURT_OK;
 }
 
-uint64_t order_slice_size(uint64_t n) {
-    const uint64_t want = getenv("GPURT_PLACE_SLICES") ? (uint64_t)std::max(1, atoi(getenv("GPURT_PLACE_SLICES"))) : 8u;
-    uint64_t s = std::max<uint64_t>((n + want - 1) / want, 1u << 18);
-    return (s + 127) & ~(uint64_t)127;
+/* Slices of the processing order, as ascending end positions.  The transfer of slice k overlaps the traversal of slice
+ * k + 1, so only the last slice's transfer is exposed, and every slice boundary costs a drain of the traversal kernel: a few
+ * large slices first, small ones at the end (GPURT_PLACE_SLICES=<k>: k equal slices instead). */
+void order_slices(uint64_t n, std::vector<uint64_t>& ends) {
+    ends.clear();
+    const char* env = getenv("GPURT_PLACE_SLICES");
+    const uint64_t min_slice = 1u << 18;
+    if(env && atoi(env) > 0) {
+        const uint64_t k = (uint64_t)atoi(env);
+        uint64_t s = std::max<uint64_t>((n + k - 1) / k, min_slice);
+        s = (s + 127) & ~(uint64_t)127;
+        for(uint64_t e = s; e < n; e += s) ends.push_back(e);
+    } else {
+        static const double cum[] = {0.30, 0.55, 0.74, 0.87, 0.95};
+        uint64_t prev = 0;
+        for(double c : cum) {
+            uint64_t e = ((uint64_t)((double)n * c) + 127) & ~(uint64_t)127;
+            if(e >= n || n - e < min_slice) break;
+            if(e - prev < min_slice) continue;
+            ends.push_back(e), prev = e;
+        }
+    }
+    ends.push_back(n);
 }
 int scatter_slice_async(gpurt_accel* A, const OrderPlan& P, uint64_t off, uint64_t m, void* results, size_t result_bytes) {
     gpurt_ctx* ctx = A->ctx;
-    if(P.gather) return gather_push_slice(P.gather, P.out, P.order, off, m, (uint32_t)(off / order_slice_size(P.n)));
+    if(P.gather) return gather_push_slice(P.gather, P.out, P.order, off, m);
     GPURT_CUDA(cudaEventRecord(ctx->ev_place, ctx->stream));
     GPURT_CUDA(cudaStreamWaitEvent(ctx->s_place, ctx->ev_place, 0));
     const float4* staged = (const float4*)((const char*)P.out + off * result_bytes);

@@ -130,13 +130,16 @@ int launch_trace_closest(gpurt_accel* A, const float4* rays, uint64_t n, float4*
     int rc = plan_spatial_order(A, rays, 2, n, hits, 16, P, true);
     if(rc) return rc;
     if(P.scatter) { /* hits live on another GPU: slice k is stored there while slice k + 1 is traced (order.cu) */
-        const uint64_t slice = order_slice_size(n);
-        for(uint64_t off = 0; off < n; off += slice) {
-            const uint64_t m = std::min(slice, n - off);
+        std::vector<uint64_t> ends;
+        order_slices(n, ends);
+        uint64_t off = 0;
+        for(uint64_t e : ends) {
+            const uint64_t m = e - off;
             k_trace_closest<false, true><<<blocks_for(m, 128), 128, 0, A->ctx->stream>>>(
                 (const float4*)A->nodes, A->tri_wide, rays, m, (float4*)P.out + off, A->n_nodes, nullptr, P.order + off, 1);
             GPURT_CUDA(cudaGetLastError());
             if((rc = scatter_slice_async(A, P, off, m, hits, 16))) return rc;
+            off = e;
         }
         return scatter_join(A, P);
     }

@@ -415,8 +415,20 @@ def strong_config4(gpurt, torch, dist, ctx, rank, world, dev, n_tris, n_queries,
     e1.record()
     sync()
     ms_local = device_max(dist, world, e0.elapsed_time(e1), dev)
+    # throughput depends on how dense a batch is (the batch is traversed in Morton order of its points: the more points per
+    # triangle, the more the lanes of a warp share): the same range in calls of 12.5 M points — what one rank of 8 gets
+    ms_small = None
+    if nq > 12_500_000:
+        e0.record()
+        for c0 in range(0, nq, 12_500_000):
+            c1 = min(nq, c0 + 12_500_000)
+            accel.closest_points(q[c0:c1], local[c0:c1])
+        e1.record()
+        sync()
+        ms_small = device_max(dist, world, e0.elapsed_time(e1), dev)
     out = {"config": "4: synthetic 10 M-triangle soup, 100 M closest-point queries", "tris": info.n_tris, "queries": n_queries,
            "n_gpus": world, "mqueries_s": n_queries / (ms * 1e-3) / 1e6, "ms": ms, "wall_ms_barrier_to_barrier": wall * 1e3,
+           "mqueries_s_in_calls_of_12_5M_results_left_local": (n_queries / (ms_small * 1e-3) / 1e6) if ms_small else None,
            "results": "all results in rank 0's array at the end of the timed region (gpurt_gather_*): one call per rank, slices of the "
                       "sorted batch copied into rank 0's inbox while the next slice is traversed, scattered there by rank 0's side "
                       "stream while rank 0 traverses its own range; no collective",

@@ -206,7 +206,8 @@ def tree_report(gpurt, torch, ctx, scene, cam_args, flush):
         out[name] = {"mrays_s": n / (all_ms * 1e-3) / 1e6, "primary_mrays_s": n_p / (prim_ms * 1e-3) / 1e6,
                      "bounce_mrays_s": (n - n_p) / max(1e-9, (all_ms - prim_ms) * 1e-3) / 1e6 if n > n_p else None,
                      "cpq_mqueries_s": n_p / (cpq_ms * 1e-3) / 1e6, "rays": n, "nodes_per_ray": st.nodes_visited / st.rays,
-                     "tris_per_ray": st.tris_tested / st.rays, "build_ms": info.build_ms, "wide_nodes": info.n_wide_nodes}
+                     "tris_per_ray": st.tris_tested / st.rays, "build_ms": info.build_ms, "wide_nodes": info.n_wide_nodes,
+                     "binary_tree_sah_cost": info.tree_cost}
         accel.close()
     out["tris"] = scene.counts()["tris"]
     return out
@@ -363,7 +364,11 @@ def strong_config4(gpurt, torch, dist, ctx, rank, world, dev, n_tris, n_queries,
     # rank 0 also receives and scatters everybody else's results (~6 GB of memory traffic next to its own traversal): it gets
     # `share` of an equal part of the queries, the rest is spread over the other ranks (still contiguous ascending ranges).
     # Measured at 8 GPUs (gpurun_out/r03o): share 1.0 -> 7921 Mq/s, 0.85 -> 8734, 0.7 -> 9489.
-    share = float(os.environ.get("GPURT_CONFIG4_OWNER_SHARE", "0.7")) if world > 1 else 1.0
+    # With k = cost of scattering one foreign record in units of one query (0.049, fitted at 8 GPUs) the two finish together
+    # when rank 0 answers s0 = (1/(N-1) - k) / (1 - k + 1/(N-1)) of the queries: 0.975 / 0.886 / 0.69 of an equal part at 2 / 4 / 8.
+    k_scatter = 0.049
+    model = world * (1.0 / (world - 1) - k_scatter) / (1.0 - k_scatter + 1.0 / (world - 1)) if world > 1 else 1.0
+    share = float(os.environ.get("GPURT_CONFIG4_OWNER_SHARE", model)) if world > 1 else 1.0
     n0 = int(n_queries / world * share) // 128 * 128
     first = [0] + [n0 + shard_range(n_queries - n0, r, world - 1)[0] for r in range(max(0, world - 1))] + [n_queries]
     if world == 1:
@@ -418,7 +423,7 @@ def strong_config4(gpurt, torch, dist, ctx, rank, world, dev, n_tris, n_queries,
     # throughput depends on how dense a batch is (the batch is traversed in Morton order of its points: the more points per
     # triangle, the more the lanes of a warp share): the same range in calls of 12.5 M points — what one rank of 8 gets
     ms_small = None
-    if nq > 12_500_000:
+    if world == 1 and nq > 12_500_000:
         e0.record()
         for c0 in range(0, nq, 12_500_000):
             c1 = min(nq, c0 + 12_500_000)

@@ -77,6 +77,13 @@ struct gpurt_pipe {
     uint64_t lverts_version = ~0ull;
     const float4* lverts_tris = nullptr;
     bool use_lverts = true;                           /* GPURT_LIGHT_VERTS=0: light_sample transforms its vertices itself */
+    /* power-proportional light sampling (GpurtPipeParams::light_sampling): running sums over the light triangles */
+    float* lcdf = nullptr;
+    uint32_t* lcdf_off = nullptr;
+    size_t lcdf_cap = 0, lcdf_off_cap = 0;
+    uint32_t n_ltris = 0;
+    uint64_t lcdf_version = ~0ull;
+    const float4* lcdf_tris = nullptr;
     bool use_shadow_queue = false;                    /* GPURT_SHADOW_QUEUE=1: integrator 0 queues its shadow rays for k_shadow_resolve
                                                        * (measured: 10 % slower than the inline trace; bit-identical) */
     /* light BVH for light_pdf (shade.cuh light_pdf_bvh): a second accel over the lights' triangles only */
@@ -307,20 +314,21 @@ constexpr uint32_t kHistMaxShards = 64;
  * finished), stored to the same offset of every shard that will read the row next frame.  Row-major over the local rows,
  * so loads and remote stores are fully coalesced. */
 __global__ void __launch_bounds__(256) k_history_push(const __grid_constant__ FrameParams P, uint32_t halo, const char* own,
-                                                      char* const* __restrict__ peers, size_t parity_off, uint32_t local_rows) {
-    const size_t per_row = 6ull * P.W;
-    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if(idx >= per_row * local_rows) return;
-    uint32_t j = (uint32_t)(idx / per_row), o = (uint32_t)(idx - (size_t)j * per_row);
-    uint32_t y = shard_row(P, j);
-    if(y >= P.H) return;
-    unsigned long long readers = history_row_readers(P, y, halo) & ~(1ull << P.shard);
-    if(!readers) return;
+                                                      char* const* __restrict__ peers, size_t parity_off) {
+    /* blockIdx.y = local row, blockIdx.x * 256 + threadIdx.x = float4 within the row's 6 W float4s: no index division, and
+     * the row's readers are worked out once per block (rows nobody reads leave at once) */
+    __shared__ unsigned long long s_readers;
+    const uint32_t y = shard_row(P, blockIdx.y);
+    if(threadIdx.x == 0) s_readers = y < P.H ? (history_row_readers(P, y, halo) & ~(1ull << P.shard)) : 0ull;
+    __syncthreads();
+    unsigned long long readers = s_readers;
+    const uint32_t o = blockIdx.x * blockDim.x + threadIdx.x;
+    if(!readers || o >= 6u * P.W) return;
     const size_t n = (size_t)P.W * P.H;
     size_t off;
     if(o < 3u * P.W) off = 3ull * y * P.W + o;
     else {
-        uint32_t g = o / P.W - 3u, x = o - (g + 3u) * P.W;
+        const uint32_t g = o >= 5u * P.W ? 2u : o >= 4u * P.W ? 1u : 0u, x = o - (g + 3u) * P.W;
         off = (3ull + g) * n + (size_t)y * P.W + x;
     }
     float4 v = ((const float4*)(own + parity_off))[off];
@@ -388,7 +396,7 @@ __global__ void __launch_bounds__(256) k_tonemap(const float4* __restrict__ img,
 
 static int pipe_free(gpurt_pipe* p) {
     void* ptrs[] = {p->image, p->hist, p->d_peers, p->acc, p->pathA, p->pathB, p->rays[0], p->rays[1], p->hits,
-                    p->queue[0], p->queue[1], p->counts, p->ray_counts, p->lgrp, p->lgrp_off, p->lverts, p->lvert_off};
+                    p->queue[0], p->queue[1], p->counts, p->ray_counts, p->lgrp, p->lgrp_off, p->lverts, p->lvert_off, p->lcdf, p->lcdf_off};
     for(void* q : ptrs)
         if(q) cudaFree(q);
     return GPURT_OK;
@@ -518,6 +526,50 @@ static int pipe_light_verts(gpurt_pipe* p) {
     if(most) k_light_verts<<<dim3(cdivu(most, 128), (unsigned)L.size()), 128, 0, st>>>(A->dscene, p->lvert_off, p->lverts);
     GPURT_CUDA(cudaGetLastError());
     p->lverts_tris = A->tri_gid, p->lverts_version = A->dscene.version;
+    return GPURT_OK;
+}
+
+/* Running sums of light_tri_power over the light triangles, in (light, triangle) order, for light_sampling = 1.  The
+ * weights come from the world-space vertices of the light vertex table (read back: a few thousand triangles) and the
+ * objects' emissive factors; the sum is taken on the host in index order, as the oracle takes it.  Rebuilt with the table. */
+static int pipe_light_cdf(gpurt_pipe* p) {
+    int rc = pipe_light_verts(p);
+    if(rc) return rc;
+    if(!p->lverts_tris) return set_error("light_sampling = 1 needs the light vertex table (GPURT_LIGHT_VERTS=0, or lights that are not whole objects)"), GPURT_E_STATE;
+    if(p->lcdf_tris == p->lverts_tris && p->lcdf_version == p->lverts_version) return GPURT_OK;
+    const PackedScene& M = p->scene->packed;
+    const std::vector<SceneLight>& L = M.lights;
+    cudaStream_t st = p->ctx->stream;
+    std::vector<uint32_t> off(L.size() + 1, 0);
+    for(size_t l = 0; l < L.size(); l++) off[l + 1] = off[l] + L[l].n_triangles;
+    const uint32_t total = off.back();
+    std::vector<float4> v(3ull * std::max(total, 1u));
+    if(total) GPURT_CUDA(cudaMemcpyAsync(v.data(), p->lverts, (size_t)total * 48, cudaMemcpyDeviceToHost, st));
+    GPURT_CUDA(cudaStreamSynchronize(st));
+    std::vector<float> cdf(std::max(total, 1u), 0.0f);
+    float run = 0.0f;
+    for(size_t l = 0; l < L.size(); l++) {
+        const float* e = reinterpret_cast<const float*>(&M.descs[L[l].index]) + 36; /* Scene_Desc::emissive (rt.h:68-77) */
+        for(uint32_t t = 0; t < L[l].n_triangles; t++) {
+            const float4 *q = &v[3ull * (off[l] + t)];
+            float w = light_tri_power(F3{q[0].x, q[0].y, q[0].z}, F3{q[1].x, q[1].y, q[1].z}, F3{q[2].x, q[2].y, q[2].z}, F3{e[0], e[1], e[2]});
+            if(!(w > 0.0f) || w > 3.0e38f) w = 0.0f; /* NaN / negative / infinite weights never get chosen */
+            run += w;
+            cdf[off[l] + t] = run;
+        }
+    }
+    if(p->lcdf_cap < total || p->lcdf_off_cap < L.size() + 1) {
+        if(p->lcdf) cudaFree(p->lcdf);
+        if(p->lcdf_off) cudaFree(p->lcdf_off);
+        p->lcdf = nullptr, p->lcdf_off = nullptr, p->lcdf_cap = p->lcdf_off_cap = 0;
+        GPURT_CUDA(cudaMalloc((void**)&p->lcdf, (size_t)std::max(total, 1u) * 4));
+        GPURT_CUDA(cudaMalloc((void**)&p->lcdf_off, (L.size() + 1) * 4));
+        p->lcdf_cap = total, p->lcdf_off_cap = L.size() + 1;
+    }
+    GPURT_CUDA(cudaMemcpyAsync(p->lcdf, cdf.data(), (size_t)std::max(total, 1u) * 4, cudaMemcpyHostToDevice, st));
+    GPURT_CUDA(cudaMemcpyAsync(p->lcdf_off, off.data(), (L.size() + 1) * 4, cudaMemcpyHostToDevice, st));
+    GPURT_CUDA(cudaStreamSynchronize(st)); /* the host vectors leave scope */
+    p->n_ltris = total, p->lcdf_tris = p->lverts_tris, p->lcdf_version = p->lverts_version;
     return GPURT_OK;
 }
 
@@ -742,6 +794,7 @@ static int render_core(gpurt_pipe* p, const GpurtPipeParams* prm, const GpurtCam
     F.W = w, F.H = h;
     F.seed_val = prm->seed ^ (uint32_t)c.frame;
     F.spatial_samples = prm->spatial_samples > 0 ? (uint32_t)prm->spatial_samples : 0u, F.spatial_radius = prm->spatial_radius;
+    F.light_sampling = prm->light_sampling == 1 ? 1u : 0u;
 
     F.band_rows = p->band_rows ? p->band_rows : h, F.n_shards = p->band_rows ? p->n_shards : 1, F.shard = p->band_rows ? p->shard : 0;
     {
@@ -763,7 +816,7 @@ static int render_core(gpurt_pipe* p, const GpurtPipeParams* prm, const GpurtCam
         const uint32_t local_rows = n / w;
         const size_t parity_off = kHistHeader + (size_t)cur * w * h * 96;
         if(local_rows)
-            k_history_push<<<cdivu((size_t)local_rows * 6 * w, 256), 256, 0, st>>>(F, p->halo_rows, p->hist, p->d_peers, parity_off, local_rows);
+            k_history_push<<<dim3(cdivu(6 * (size_t)w, 256), local_rows), 256, 0, st>>>(F, p->halo_rows, p->hist, p->d_peers, parity_off);
         k_history_signal<<<1, kHistMaxShards, 0, st>>>(p->d_peers, F.n_shards, F.shard, ++p->hist_seq);
     };
     if(n == 0) { /* more shards than bands: nothing to do on this rank */
@@ -790,6 +843,11 @@ static int render_core(gpurt_pipe* p, const GpurtPipeParams* prm, const GpurtCam
         if(p->laccel && p->laccel->n_nodes)
             X.lnodes = (const float4*)p->laccel->nodes, X.ltris = p->laccel->tri_wide, X.ltri_off = p->laccel->dscene.tri_off,
             X.n_lnodes = p->laccel->n_nodes;
+    }
+    X.lcdf = nullptr, X.lcdf_off = nullptr, X.n_ltris = 0;
+    if(F.light_sampling && c.n_lights > 0 && c.integrator != 1) { /* every integrator that samples or evaluates lights */
+        if((rc = pipe_light_cdf(p))) return rc;
+        X.lcdf = p->lcdf, X.lcdf_off = p->lcdf_off, X.n_ltris = p->n_ltris;
     }
     X.prev_res = p->res[prev], X.ppos = p->gbuf[prev][0], X.pnorm = p->gbuf[prev][1], X.palb = p->gbuf[prev][2];
     X.ray_counts = p->ray_counts;

@@ -77,6 +77,9 @@ struct FrameParams {
     /* extension (GpurtPipeParams): ReSTIR spatial reuse; 0 samples = the reference's estimator */
     uint32_t spatial_samples;
     float spatial_radius;
+    /* extension (GpurtPipeParams::light_sampling): 0 = the reference's uniform light, uniform triangle; 1 = a light triangle
+     * with probability proportional to area x luma(emissive), light_pdf weighted to match */
+    uint32_t light_sampling;
 };
 
 /* i-th locally rendered pixel -> global pixel index y*W + x (RNG, image and G-buffers are indexed by
@@ -230,12 +233,24 @@ struct ShadeCtx {
      * the three vertices itself like the GLSL */
     const float4* lverts;
     const uint32_t* lvert_off;
+    /* power-proportional light sampling (GpurtPipeParams::light_sampling = 1): running sums of light_tri_power over the
+     * light triangles in (light, triangle) order, light l starting at lcdf_off[l] (n_lights + 1 entries); NULL: off */
+    const float* lcdf;
+    const uint32_t* lcdf_off;
+    unsigned n_ltris;
     const float4* prev_res;  /* previous frame reservoirs */
     const float4* ppos;      /* previous frame G-buffers */
     const float4* pnorm;
     const float4* palb;
     unsigned long long* ray_counts; /* [0] closest, [1] any */
 };
+
+/* weight of a light triangle for power-proportional sampling: area x luma of the object's emissive factor (an emissive
+ * texture is not looked at: any positive weights give an unbiased estimator, the pdf carries them) */
+GPURT_HD float light_tri_power(F3 v0, F3 v1, F3 v2, F3 emissive) { /* host + device: the pipe evaluates it on the host */
+    F3 c = cross3(v1 - v0, v2 - v0);
+    return 0.5f * sqrtf(dot3(c, c)) * (0.299f * emissive.x + 0.587f * emissive.y + 0.114f * emissive.z);
+}
 
 /* model * vec4(v, 1) of the three vertices of triangle t of object obj (rt.rgen:172-174) */
 SH_D void light_world_tri(const DeviceScene& S, uint32_t obj, uint32_t t, float4* out3) {
@@ -506,9 +521,13 @@ struct Shader {
             s.pdf = 0;
             return s;
         }
-        uint32_t l_idx = randu(0, (uint32_t)P.c.n_lights);
+        uint32_t l_idx, t_idx;
+        float prob = 0;
+        const bool by_power = power_sampling();
+        if(by_power) light_pick(l_idx, t_idx, prob);
+        else l_idx = randu(0, (uint32_t)P.c.n_lights);
         uint32_t o_idx = X.S.lights[l_idx].index, n_tris = X.S.lights[l_idx].n_triangles;
-        uint32_t t_idx = randu(0, n_tris);
+        if(!by_power) t_idx = randu(0, n_tris);
         int emissiveIdx = desc_int(o_idx, 45);
         s.emissive = desc_vec(o_idx, 36);
         F3 _v0, _v1, _v2, bary;
@@ -537,14 +556,41 @@ struct Shader {
         F3 d = normalize3(dist);
         float g = dot3(dist, dist) / fabsf(dot3(N, d));
         s.normal = N;
-        s.pdf = a * g / (float)(n_tris * (uint32_t)P.c.n_lights);
+        s.pdf = by_power ? a * g * prob : a * g / (float)(n_tris * (uint32_t)P.c.n_lights);
         return s;
+    }
+    /* ---- extension: power-proportional choice of the light triangle (GpurtPipeParams::light_sampling = 1) ---- */
+    SH_D bool power_sampling() const { return P.light_sampling == 1u && X.lcdf && X.n_ltris && X.lcdf[X.n_ltris - 1u] > 0; }
+    /* probability of light triangle j (index in (light, triangle) order) */
+    SH_D float light_tri_prob(uint32_t j) const {
+        float prev = j ? X.lcdf[j - 1u] : 0.0f;
+        return (X.lcdf[j] - prev) / X.lcdf[X.n_ltris - 1u];
+    }
+    /* one randf(): the first triangle whose running sum exceeds u x total (triangles of zero weight are never chosen) */
+    SH_D void light_pick(uint32_t& l_idx, uint32_t& t_idx, float& prob) {
+        float u = randf() * X.lcdf[X.n_ltris - 1u];
+        uint32_t lo = 0, hi = X.n_ltris - 1u;
+        while(lo < hi) {
+            uint32_t mid = (lo + hi) >> 1;
+            if(X.lcdf[mid] > u) hi = mid;
+            else lo = mid + 1u;
+        }
+        prob = light_tri_prob(lo);
+        l_idx = 0;
+        while(l_idx + 1u < (uint32_t)P.c.n_lights && X.lcdf_off[l_idx + 1u] <= lo) l_idx++;
+        t_idx = lo - X.lcdf_off[l_idx];
     }
     /* rt.rgen:200-220 */
     SH_D F3 light_sample_dir(F3 p) {
-        uint32_t l_idx = randu(0, (uint32_t)P.c.n_lights);
-        uint32_t o_idx = X.S.lights[l_idx].index, n_tris = X.S.lights[l_idx].n_triangles;
-        uint32_t t_idx = randu(0, n_tris);
+        uint32_t l_idx, t_idx;
+        if(power_sampling()) {
+            float prob;
+            light_pick(l_idx, t_idx, prob);
+        } else {
+            l_idx = randu(0, (uint32_t)P.c.n_lights);
+            t_idx = randu(0, X.S.lights[l_idx].n_triangles);
+        }
+        uint32_t o_idx = X.S.lights[l_idx].index;
         uint32_t ind[3];
         tri_indices(o_idx, t_idx, ind);
         const float *v0 = vertex(o_idx, ind[0]), *v1 = vertex(o_idx, ind[1]), *v2 = vertex(o_idx, ind[2]);
@@ -626,6 +672,7 @@ struct Shader {
         if(n_lights == 0) return 0;
         const F3 inv = f3s(1.0f) / d;
         const bool boxes = X.lgrp != nullptr;
+        const bool by_power = power_sampling(); /* every term weighted by its triangle's probability instead of 1 / (n_tris n_lights) */
         float oacc = 0, tacc = 0;
         uint32_t l = 0, t = 0, n_tris = 0;
         bool in_light = false;
@@ -646,7 +693,7 @@ struct Shader {
                 } else
                     l++;
             } else if(t >= n_tris) { /* end of the triangle loop: `oacc += tacc / float(n_tris)` */
-                oacc += tacc / (float)n_tris;
+                oacc += by_power ? tacc : tacc / (float)n_tris;
                 in_light = false, l++;
             } else {
                 bool test = true;
@@ -661,12 +708,14 @@ struct Shader {
                 if(test) {
                     const float4* q = tp + 3ull * t;
                     float4 r0 = GPURT_LDG(q), r1 = GPURT_LDG(q + 1), r2 = GPURT_LDG(q + 2);
-                    tacc += triangle_pdf_flat(p, d, F3{r0.x, r0.y, r0.z}, F3{r1.x, r1.y, r1.z}, F3{r2.x, r2.y, r2.z});
+                    float term = triangle_pdf_flat(p, d, F3{r0.x, r0.y, r0.z}, F3{r1.x, r1.y, r1.z}, F3{r2.x, r2.y, r2.z});
+                    if(by_power && term != 0) term = term * light_tri_prob(X.lcdf_off[l] + t);
+                    tacc += term;
                     t++;
                 }
             }
         }
-        return oacc / (float)n_lights;
+        return by_power ? oacc : oacc / (float)n_lights;
     }
     /* light_pdf through the light BVH.  Only the triangles the ray actually crosses contribute a non-zero term to the
      * GLSL's sums, and index-order runs make poor boxes (64 consecutive triangles of a sphere are one latitude ring: its
@@ -728,6 +777,7 @@ struct Shader {
                 }
             }
         }
+        const bool by_power = power_sampling(); /* hg = index in (light, triangle) order = index into lcdf */
         float oacc = 0;
         uint32_t l = 0;
         for(int i = 0; i < nh;) {
@@ -735,11 +785,11 @@ struct Shader {
             const SceneLight& L = X.S.lights[l];
             const uint32_t end = X.ltri_off[l + 1];
             float tacc = 0;
-            for(; i < nh && hg[i] < end; i++) tacc += hp[i];
+            for(; i < nh && hg[i] < end; i++) tacc += by_power ? hp[i] * light_tri_prob(hg[i]) : hp[i];
             if(hit_bbox(p, d, F3{L.bmin[0], L.bmin[1], L.bmin[2]}, F3{L.bmax[0], L.bmax[1], L.bmax[2]}))
-                oacc += tacc / (float)L.n_triangles;
+                oacc += by_power ? tacc : tacc / (float)L.n_triangles;
         }
-        return oacc / (float)P.c.n_lights;
+        return by_power ? oacc : oacc / (float)P.c.n_lights;
     }
 #if defined(GPURT_LIGHT_PDF_INLINE) /* A/B build: both call sites of integrate_mis get their own copy */
     SH_D

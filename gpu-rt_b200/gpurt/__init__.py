@@ -62,7 +62,8 @@ class PipeParams(C.Structure):
                 ("use_normal_map", C.c_int32), ("use_rr", C.c_int32), ("use_metalness", C.c_int32),
                 ("use_qmc", C.c_int32), ("use_temporal", C.c_int32), ("integrator", C.c_int32),
                 ("temporal_scale", C.c_int32), ("brdf", C.c_int32), ("debug_view", C.c_int32),
-                ("res_samples", C.c_int32), ("seed", C.c_uint32), ("spatial_samples", C.c_int32), ("spatial_radius", C.c_float)]
+                ("res_samples", C.c_int32), ("seed", C.c_uint32), ("spatial_samples", C.c_int32), ("spatial_radius", C.c_float),
+                ("light_sampling", C.c_int32)]
 
 
 class AccelInfo(C.Structure):

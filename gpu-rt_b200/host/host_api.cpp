@@ -270,6 +270,7 @@ int gpurt_pipe_params_default(GpurtPipeParams* p) { /* rt.h:38-53 */
     p->integrator = 0, p->temporal_scale = 16, p->brdf = 0, p->debug_view = 0, p->res_samples = 4;
     p->seed = 0;
     p->spatial_samples = 0, p->spatial_radius = 16.0f;
+    p->light_sampling = 0;
     return GPURT_OK;
 }
 

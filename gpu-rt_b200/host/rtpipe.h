@@ -97,6 +97,7 @@ public:
     unsigned seed = 0; /* replaces clockARB() (rt.rgen:569) */
     int spatial_samples = 0;     /* extension: ReSTIR spatial reuse (include/gpurt.h), off by default */
     float spatial_radius = 16.0f;
+    int light_sampling = 0;      /* extension: 1 = light triangles chosen in proportion to their power (include/gpurt.h) */
 
     void reset_frame() { check(gpurt_pipe_reset_frame(h)); }
 
@@ -109,7 +110,7 @@ public:
         p.use_normal_map = use_normal_map, p.use_rr = use_rr, p.use_metalness = use_metalness, p.use_qmc = use_qmc;
         p.use_temporal = use_temporal, p.integrator = integrator, p.temporal_scale = temporal_scale, p.brdf = brdf;
         p.debug_view = debug_view, p.res_samples = res_samples, p.seed = seed;
-        p.spatial_samples = spatial_samples, p.spatial_radius = spatial_radius;
+        p.spatial_samples = spatial_samples, p.spatial_radius = spatial_radius, p.light_sampling = light_sampling;
         return p;
     }
     /* multi-GPU, frame-parallel: render frame f into a device buffer / fold a frame mean (include/gpurt.h) */

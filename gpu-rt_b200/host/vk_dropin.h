@@ -255,7 +255,7 @@ struct RTPipe {
             clear = src.clear, env = src.env, env_scale = src.env_scale, use_normal_map = src.use_normal_map;
             use_rr = src.use_rr, use_metalness = src.use_metalness, use_qmc = src.use_qmc, use_temporal = src.use_temporal;
             integrator = src.integrator, temporal_scale = src.temporal_scale, brdf = src.brdf, debug_view = src.debug_view;
-            res_samples = src.res_samples, seed = src.seed, spatial_samples = src.spatial_samples, spatial_radius = src.spatial_radius;
+            res_samples = src.res_samples, seed = src.seed, spatial_samples = src.spatial_samples, spatial_radius = src.spatial_radius, light_sampling = src.light_sampling;
             mats = std::move(src.mats), texs = std::move(src.texs), mats_version = src.mats_version;
             pipe = src.pipe, src.pipe = nullptr;
             bound = std::move(src.bound), bound_generation = src.bound_generation, applied_version = src.applied_version;
@@ -359,6 +359,7 @@ struct RTPipe {
     unsigned seed = 0; /* stands in for clockARB() in the per-pixel seed (rt.rgen:569), see DESIGN.md Q1 */
     int spatial_samples = 0;     /* extension: ReSTIR spatial reuse (include/gpurt.h), off by default */
     float spatial_radius = 16.0f;
+    int light_sampling = 0;      /* extension: 1 = light triangles chosen in proportion to their power (include/gpurt.h) */
 
     /* ---- results (the reference samples rt_target in EffectPipe::tonemap and reads the framebuffer in save_rt) ---- */
     std::vector<float> read_image() const { /* RGBA32F, w*h*4 */
@@ -394,7 +395,7 @@ struct RTPipe {
         p.use_normal_map = use_normal_map, p.use_rr = use_rr, p.use_metalness = use_metalness, p.use_qmc = use_qmc;
         p.use_temporal = use_temporal, p.integrator = integrator, p.temporal_scale = temporal_scale, p.brdf = brdf;
         p.debug_view = debug_view, p.res_samples = res_samples, p.seed = seed;
-        p.spatial_samples = spatial_samples, p.spatial_radius = spatial_radius;
+        p.spatial_samples = spatial_samples, p.spatial_radius = spatial_radius, p.light_sampling = light_sampling;
         return p;
     }
 

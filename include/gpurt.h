@@ -132,6 +132,12 @@ typedef struct GpurtPipeParams {
      * the estimator (less noise per frame, slightly biased like any unshadowed-neighbour reuse), hence a flag. */
     int32_t spatial_samples;
     float spatial_radius;
+    /* Extension, off by default (SURVEY §8f rank 4 "light-sampling acceleration ... only behind a flag"): 0 = the reference's
+     * light_sample / light_sample_dir (uniform light, uniform triangle, rt.rgen:151-220); 1 = one light triangle chosen with
+     * probability proportional to area x luma(emissive factor) from a table of running sums (one random number, binary
+     * search), with light_pdf (rt.rgen:222-255) weighting every triangle's term by the same probability, so direct, MIS and
+     * ReSTIR estimators stay unbiased and small or dim emitters stop getting as many samples as large bright ones. */
+    int32_t light_sampling;
 } GpurtPipeParams;
 
 typedef struct GpurtAccelInfo {

@@ -175,6 +175,25 @@ struct Invocation {
     const float *ppos, *pnorm, *palb;
     uint32_t spatial_samples = 0; /* extension, see orc_render_set_spatial */
     float spatial_radius = 16.0f;
+    /* extension, see orc_render_set_light_sampling: running sums of the light triangles' weights in (light, triangle)
+     * order and the first index of every light; NULL = rt.rgen as written */
+    const float* lcdf = nullptr;
+    const uint32_t* lcdf_off = nullptr;
+    uint32_t n_ltris = 0;
+    bool power_sampling() const { return lcdf && n_ltris && lcdf[n_ltris - 1] > 0; }
+    float light_tri_prob(uint32_t j) const {
+        float prev = j ? lcdf[j - 1] : 0.0f;
+        return (lcdf[j] - prev) / lcdf[n_ltris - 1];
+    }
+    void light_pick(uint32_t& l_idx, uint32_t& t_idx, float& prob) {
+        float u = randf() * lcdf[n_ltris - 1];
+        uint32_t j = 0; /* the first triangle whose running sum exceeds u (linear here, a binary search in the product) */
+        while(j + 1 < n_ltris && !(lcdf[j] > u)) j++;
+        prob = light_tri_prob(j);
+        l_idx = 0;
+        while(l_idx + 1 < (uint32_t)c->n_lights && lcdf_off[l_idx + 1] <= j) l_idx++;
+        t_idx = j - lcdf_off[l_idx];
+    }
     uint64_t n_closest = 0, n_any = 0;
 
     /* rtcommon.glsl:111-124 */
@@ -426,10 +445,13 @@ struct Invocation {
             s.pdf = 0;
             return s;
         }
-        s.l_idx = randu(0, (uint32_t)c->n_lights);
+        float prob = 0;
+        const bool by_power = power_sampling();
+        if(by_power) light_pick(s.l_idx, s.t_idx, prob);
+        else s.l_idx = randu(0, (uint32_t)c->n_lights);
         s.o_idx = light(s.l_idx)[8];
         uint32_t n_tris = light(s.l_idx)[9];
-        s.t_idx = randu(0, n_tris);
+        if(!by_power) s.t_idx = randu(0, n_tris);
         uint32_t ind[3];
         tri_indices(s.o_idx, s.t_idx, ind);
         const float *v0 = vertex(s.o_idx, ind[0]), *v1 = vertex(s.o_idx, ind[1]), *v2 = vertex(s.o_idx, ind[2]);
@@ -450,14 +472,20 @@ struct Invocation {
         vec3 d = normalize(dist);
         float g = dot(dist, dist) / fabsf(dot(N, d));
         s.normal = N;
-        s.pdf = a * g / (float)(n_tris * (uint32_t)c->n_lights);
+        s.pdf = by_power ? a * g * prob : a * g / (float)(n_tris * (uint32_t)c->n_lights);
         return s;
     }
     /* rt.rgen:200-220 */
     vec3 light_sample_dir(vec3 p) {
-        uint32_t l_idx = randu(0, (uint32_t)c->n_lights);
-        uint32_t o_idx = light(l_idx)[8], n_tris = light(l_idx)[9];
-        uint32_t t_idx = randu(0, n_tris);
+        uint32_t l_idx, t_idx;
+        if(power_sampling()) {
+            float prob;
+            light_pick(l_idx, t_idx, prob);
+        } else {
+            l_idx = randu(0, (uint32_t)c->n_lights);
+            t_idx = randu(0, light(l_idx)[9]);
+        }
+        uint32_t o_idx = light(l_idx)[8];
         uint32_t ind[3];
         tri_indices(o_idx, t_idx, ind);
         const float *v0 = vertex(o_idx, ind[0]), *v1 = vertex(o_idx, ind[1]), *v2 = vertex(o_idx, ind[2]);
@@ -507,6 +535,7 @@ struct Invocation {
     /* rt.rgen:222-255 */
     float light_pdf(vec3 p, vec3 d) const {
         if(c->n_lights <= 0) return 0; /* Q4 */
+        const bool by_power = power_sampling(); /* extension: every term weighted by its triangle's probability */
         float oacc = 0;
         for(uint32_t l = 0; l < (uint32_t)c->n_lights; l++) {
             float tacc = 0;
@@ -521,11 +550,13 @@ struct Invocation {
                 const float *a = vertex(o_idx, ind[0]), *b = vertex(o_idx, ind[1]), *cc = vertex(o_idx, ind[2]);
                 vec3 v0 = xform_point(m, {a[0], a[1], a[2]}), v1 = xform_point(m, {b[0], b[1], b[2]}),
                      v2 = xform_point(m, {cc[0], cc[1], cc[2]});
-                tacc += triangle_pdf(p, d, v0, v1, v2);
+                float term = triangle_pdf(p, d, v0, v1, v2);
+                if(by_power) term = term * light_tri_prob(lcdf_off[l] + t);
+                tacc += term;
             }
-            oacc += tacc / (float)n_tris;
+            oacc += by_power ? tacc : tacc / (float)n_tris;
         }
-        return oacc / (float)c->n_lights;
+        return by_power ? oacc : oacc / (float)c->n_lights;
     }
     /* rt.rgen:293-301 */
     vec3 direct_light(vec3 o, vec3 d) {
@@ -906,6 +937,39 @@ static uint32_t g_spatial_samples = 0;
 static float g_spatial_radius = 16.0f;
 void orc_render_set_spatial(uint32_t samples, float radius) { g_spatial_samples = samples, g_spatial_radius = radius; }
 
+/* Extension shared with the product (GpurtPipeParams::light_sampling, NOT in the reference): 1 = light_sample /
+ * light_sample_dir choose a light triangle with probability proportional to area x luma(emissive factor) and light_pdf
+ * weights every triangle's term by that probability; 0 (default) = rt.rgen as written. */
+static uint32_t g_light_sampling = 0;
+void orc_render_set_light_sampling(uint32_t mode) { g_light_sampling = mode; }
+/* the table: weight of triangle t of light l = 0.5 |(v1 - v0) x (v2 - v0)| * luma(emissive) on the world-space vertices
+ * light_sample computes, summed in (light, triangle) order */
+static void light_power_table(const orc_scene* S, const Consts& c, std::vector<float>& cdf, std::vector<uint32_t>& off) {
+    Invocation inv;
+    inv.S = S, inv.c = &c;
+    const uint32_t nl = c.n_lights > 0 ? (uint32_t)c.n_lights : 0u;
+    off.assign(nl + 1, 0);
+    for(uint32_t l = 0; l < nl; l++) off[l + 1] = off[l] + inv.light(l)[9];
+    cdf.assign(std::max<uint32_t>(off[nl], 1u), 0.0f);
+    float run = 0.0f;
+    for(uint32_t l = 0; l < nl; l++) {
+        const uint32_t o_idx = inv.light(l)[8], n_tris = inv.light(l)[9];
+        const float* m = inv.model(o_idx);
+        const vec3 e = inv.desc_vec(o_idx, 36);
+        for(uint32_t t = 0; t < n_tris; t++) {
+            uint32_t ind[3];
+            inv.tri_indices(o_idx, t, ind);
+            const float *a = inv.vertex(o_idx, ind[0]), *b = inv.vertex(o_idx, ind[1]), *cc = inv.vertex(o_idx, ind[2]);
+            vec3 v0 = xform_point(m, {a[0], a[1], a[2]}), v1 = xform_point(m, {b[0], b[1], b[2]}),
+                 v2 = xform_point(m, {cc[0], cc[1], cc[2]});
+            float w = 0.5f * length(cross(v1 - v0, v2 - v0)) * Invocation::luma(e);
+            if(!(w > 0.0f) || w > 3.0e38f) w = 0.0f;
+            run += w;
+            cdf[off[l] + t] = run;
+        }
+    }
+}
+
 void orc_render_frame(const orc_scene* S, const uint32_t* consts, const uint32_t* camera, uint32_t w,
                       uint32_t h, uint32_t seed, float* image, const uint32_t* prev_res,
                       uint32_t* out_res, const float* ppos, const float* pnorm, const float* palb,
@@ -916,6 +980,9 @@ void orc_render_frame(const orc_scene* S, const uint32_t* consts, const uint32_t
     memcpy(&cam, camera, sizeof(cam));
     if(threads <= 0) threads = orc_hw_threads();
     uint32_t seed_val = seed ^ (uint32_t)c.frame;
+    std::vector<float> lcdf;
+    std::vector<uint32_t> lcdf_off;
+    if(g_light_sampling == 1 && c.n_lights > 0) light_power_table(S, c, lcdf, lcdf_off);
     std::vector<std::thread> pool;
     std::vector<uint64_t> nc(threads, 0), na(threads, 0);
     for(int t = 0; t < threads; t++)
@@ -926,6 +993,7 @@ void orc_render_frame(const orc_scene* S, const uint32_t* consts, const uint32_t
                     inv.S = S, inv.c = &c, inv.cam = &cam, inv.W = w, inv.H = h, inv.px = x, inv.py = y;
                     inv.prev_res_buf = prev_res, inv.ppos = ppos, inv.pnorm = pnorm, inv.palb = palb;
                     inv.spatial_samples = g_spatial_samples, inv.spatial_radius = g_spatial_radius;
+                    if(!lcdf_off.empty()) inv.lcdf = lcdf.data(), inv.lcdf_off = lcdf_off.data(), inv.n_ltris = lcdf_off.back();
                     inv.main_(seed_val, image, out_res, pos, norm, alb);
                     nc[t] += inv.n_closest, na[t] += inv.n_any;
                 }

@@ -33,6 +33,9 @@ void orc_scene_free(orc_scene*);
 /* Extension shared with the product (GpurtPipeParams::spatial_samples / spatial_radius, NOT in the reference): ReSTIR spatial
  * reuse for the following orc_render_frame calls; 0 samples (the default) = rt.rgen as written. */
 void orc_render_set_spatial(uint32_t samples, float radius);
+/* Extension shared with the product (GpurtPipeParams::light_sampling, NOT in the reference): 1 = light triangles chosen in
+ * proportion to area x luma(emissive), light_pdf weighted to match; 0 (default) = rt.rgen as written. */
+void orc_render_set_light_sampling(uint32_t mode);
 void orc_render_frame(const orc_scene* S, const uint32_t* consts, const uint32_t* camera, uint32_t w,
                       uint32_t h, uint32_t seed, float* image, const uint32_t* prev_res,
                       uint32_t* out_res, const float* ppos, const float* pnorm, const float* palb,

@@ -632,6 +632,10 @@ void emu_light_pdf(void* bvh, const EmuFrameArgs* A, const float* rays6, unsigne
     }
 }
 
+/* GpurtPipeParams::light_sampling of the following emu_render_frame calls (render.cu pipe_light_cdf builds the table) */
+static uint32_t g_light_sampling = 0;
+void emu_set_light_sampling(uint32_t mode) { g_light_sampling = mode; }
+
 /* band sharding of the following emu_render_frame calls (gpurt_pipe_set_shard); 0 rows = the whole frame */
 static uint32_t g_band_rows = 0, g_n_shards = 1, g_shard = 0;
 void emu_set_shard(uint32_t band_rows, uint32_t n_shards, uint32_t shard) { g_band_rows = band_rows, g_n_shards = n_shards, g_shard = shard; }
@@ -695,6 +699,27 @@ void emu_render_frame(void* bvh, const EmuFrameArgs* A, const uint32_t* consts, 
         for(uint32_t l = 0; l < A->n_lights; l++)
             for(uint32_t t = 0; t < L[l].n_triangles; t++) light_world_tri(X.S, L[l].index, t, lverts.data() + 3ull * (lvoff[l] + t));
         X.lverts = lverts.data(), X.lvert_off = lvoff.data();
+    }
+    std::vector<float> lcdf; /* pipe_light_cdf() of render.cu */
+    std::vector<uint32_t> lcdf_off(A->n_lights + 1, 0);
+    P.light_sampling = g_light_sampling == 1 ? 1u : 0u;
+    if(P.light_sampling && A->n_lights && P.c.integrator != 1) {
+        const SceneLight* L = (const SceneLight*)A->lights;
+        for(uint32_t l = 0; l < A->n_lights; l++) lcdf_off[l + 1] = lcdf_off[l] + L[l].n_triangles;
+        lcdf.assign(std::max(lcdf_off[A->n_lights], 1u), 0.0f);
+        float run = 0.0f;
+        for(uint32_t l = 0; l < A->n_lights; l++) {
+            const float* e = reinterpret_cast<const float*>(X.S.descs + L[l].index) + 36;
+            for(uint32_t t = 0; t < L[l].n_triangles; t++) {
+                float4 q[3];
+                light_world_tri(X.S, L[l].index, t, q);
+                float w = light_tri_power(F3{q[0].x, q[0].y, q[0].z}, F3{q[1].x, q[1].y, q[1].z}, F3{q[2].x, q[2].y, q[2].z}, F3{e[0], e[1], e[2]});
+                if(!(w > 0.0f) || w > 3.0e38f) w = 0.0f;
+                run += w;
+                lcdf[lcdf_off[l] + t] = run;
+            }
+        }
+        X.lcdf = lcdf.data(), X.lcdf_off = lcdf_off.data(), X.n_ltris = lcdf_off[A->n_lights];
     }
     X.prev_res = (const float4*)prev_res, X.ppos = (const float4*)ppos, X.pnorm = (const float4*)pnorm, X.palb = (const float4*)palb;
     const uint32_t n = P.n_local; /* thread ranges are over local indices; buffers are indexed by the global pixel */

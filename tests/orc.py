@@ -170,6 +170,8 @@ lib.orc_scene_create.restype = _vp
 lib.orc_scene_create.argtypes = [C.c_uint32, _vp, _vp, _vp, _vp, _vp, C.c_uint32, _vp, C.c_uint32, _vp, _vp, _vp]
 lib.orc_scene_free.argtypes = [_vp]
 lib.orc_render_frame.restype = None
+lib.orc_render_set_light_sampling.restype = None
+lib.orc_render_set_light_sampling.argtypes = [C.c_uint32]
 lib.orc_render_set_spatial.restype = None
 lib.orc_render_set_spatial.argtypes = [C.c_uint32, C.c_float]
 lib.orc_render_frame.argtypes = [_vp, _vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32, _vp, _vp, _vp, _vp, _vp, _vp,
@@ -241,10 +243,11 @@ class FrameState:
         self.parity = 0
 
 
-def render_frame(rs, st, consts_words, camera_words, seed, threads=0, spatial=(0, 16.0)):
+def render_frame(rs, st, consts_words, camera_words, seed, threads=0, spatial=(0, 16.0), light_sampling=0):
     """one rt.rgen dispatch; consts/camera are the exact words the product used for the frame; spatial = (samples, radius)
     of the ReSTIR spatial-reuse extension (0 samples: the reference's estimator)"""
     lib.orc_render_set_spatial(int(spatial[0]), float(spatial[1]))
+    lib.orc_render_set_light_sampling(int(light_sampling))   # extension: power-proportional light triangles
     cur, prev = st.parity, st.parity ^ 1
     counts = np.zeros(2, np.uint64)
     consts_words = np.ascontiguousarray(consts_words, np.uint32)

@@ -154,6 +154,39 @@ def test_restir_spatial_reuse_extension(emu, orc, gpurt):
     es.close()
 
 
+def test_light_sampling_extension(emu, orc, gpurt):
+    """GpurtPipeParams::light_sampling = 1 (no reference counterpart, off by default): the product's code and the oracle's
+    restatement agree bit for bit for every integrator that samples or evaluates lights (direct, MIS with its weighted
+    light_pdf through the light BVH and through the scan, both ReSTIR variants), and the flag changes the frames"""
+    s = gpurt.Scene(None).load(os.path.join(MEDIA, "mis_test", "mis_test.gltf"))
+    es = EmuScene(emu, orc, s, ())
+    emu.emu_set_light_sampling.argtypes = [C.c_uint32]
+    cam = gpurt.camera(1, 64, 36, (0.5, 0.6, 2.6), (0.5, 0.45, 0.0), 50.0)
+    try:
+        for integ in (0, 2, 3, 4):
+            frames = {}
+            for mode in (0, 1):
+                for bvh in ((1, 0) if integ == 2 else (1,)):
+                    emu.emu_set_light_bvh(bvh)
+                    a, b = orc.FrameState(64, 36), orc.FrameState(64, 36)
+                    for f in range(3):
+                        consts, ubo, seed = _uniforms(gpurt, es.rs, cam, f, integrator=integ, brdf=1, samples_per_frame=2, max_depth=3,
+                                                      res_samples=4, use_temporal=1, temporal_scale=16, seed=300 + integ)
+                        emu.emu_set_light_sampling(mode)
+                        ce = es.render_frame(a, consts, ubo, seed ^ f)
+                        co = orc.render_frame(es.rs, b, consts, ubo, seed, light_sampling=mode)
+                        assert (a.image.view(np.uint32) == b.image.view(np.uint32)).all(), f"light_sampling {mode} integrator {integ} bvh {bvh} frame {f}"
+                        assert (a.res[a.parity ^ 1] == b.res[b.parity ^ 1]).all()
+                        assert tuple(int(x) for x in ce) == tuple(int(x) for x in co)
+                    frames[mode] = a.image.copy()
+            assert not (frames[0].view(np.uint32) == frames[1].view(np.uint32)).all()
+    finally:
+        emu.emu_set_light_sampling(0)
+        emu.emu_set_light_bvh(1)
+        orc.lib.orc_render_set_light_sampling(0)
+    es.close()
+
+
 def test_mis_test_scene(emu, orc, gpurt):
     s = gpurt.Scene(None).load(os.path.join(MEDIA, "mis_test", "mis_test.gltf"))
     cam = gpurt.camera(1, 80, 45, (0.5, 0.6, 2.6), (0.5, 0.45, 0.0), 50.0)

@@ -131,6 +131,15 @@ __global__ void __launch_bounds__(256) k_gen_camera(const __grid_constant__ Fram
     pixel_gen_camera(P, s, shard_pixel(P, li), li, pathA, pathB, rays, queue);
 }
 
+__global__ void __launch_bounds__(256) k_begin_camera(const __grid_constant__ FrameParams P, int restir, int clear_gbuf, float4* acc,
+                                                      float4* pathA, float4* pathB, float4* gpos, float4* gnorm, float4* galb,
+                                                      float4* res_out, float4* rays, uint32_t* queue, uint32_t* count) {
+    uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
+    if(li == 0) *count = P.n_local;
+    if(li >= P.n_local) return;
+    pixel_begin_camera(P, restir, clear_gbuf, shard_pixel(P, li), li, acc, pathA, pathB, gpos, gnorm, galb, res_out, rays, queue);
+}
+
 /* STRIDE = false: one ray per thread, the grid covers the queue (first bounce, or no size estimate yet).
  * STRIDE = true: launches sized from an estimate stride over the queue in case it is larger than estimated; wrapping
  * the traversal in that loop costs 2-4 % (ncu r01v), hence the two instantiations. */
@@ -855,8 +864,14 @@ static int render_core(gpurt_pipe* p, const GpurtPipeParams* prm, const GpurtCam
     GPURT_CUDA(cudaEventRecord(ctx->ev0, st));
     GPURT_CUDA(cudaMemsetAsync(p->ray_counts, 0, 16, st));
     history_wait();
-    k_frame_begin<<<cdivu(n, 256), 256, 0, st>>>(F, restir ? 1 : 0, p->acc, p->pathB, p->gbuf[cur][0],
-                                                p->gbuf[cur][1], p->gbuf[cur][2], p->res[cur]);
+    /* the first sample's camera rays are generated by the same kernel that starts the frame (k_begin_camera) unless nothing
+     * will be shaded (then k_frame_begin clears the G-buffers itself); GPURT_FUSED_BEGIN=0 keeps the two kernels */
+    static const bool fused_begin_ok = !(getenv("GPURT_FUSED_BEGIN") && atoi(getenv("GPURT_FUSED_BEGIN")) == 0);
+    const bool shades = c.samples > 0 && c.max_depth > 0;
+    const bool fused_begin = fused_begin_ok && shades;
+    if(!fused_begin)
+        k_frame_begin<<<cdivu(n, 256), 256, 0, st>>>(F, restir ? 1 : 0, p->acc, p->pathB, p->gbuf[cur][0],
+                                                    p->gbuf[cur][1], p->gbuf[cur][2], p->res[cur]);
     /* integrate_direct and the direct-only ReSTIR end every path at its first hit (rt.rgen:393, :548): the queues of
      * the later bounces are always empty, so they are not launched */
     const uint32_t D = (c.integrator == 0 || c.integrator == 3) ? std::min(1u, (uint32_t)c.max_depth) : (uint32_t)c.max_depth;
@@ -882,7 +897,11 @@ static int render_core(gpurt_pipe* p, const GpurtPipeParams* prm, const GpurtCam
     };
     for(uint32_t s = 0; s < (uint32_t)c.samples && D > 0; s++) {
         GPURT_CUDA(cudaMemsetAsync(p->counts, 0, (size_t)p->max_counts * 4, st));
-        k_gen_camera<<<cdivu(n, 256), 256, 0, st>>>(F, s, p->pathA, p->pathB, p->rays[0], p->queue[0], p->counts + 0);
+        if(s == 0 && fused_begin)
+            k_begin_camera<<<cdivu(n, 256), 256, 0, st>>>(F, restir ? 1 : 0, 0, p->acc, p->pathA, p->pathB, p->gbuf[cur][0], p->gbuf[cur][1],
+                                                          p->gbuf[cur][2], p->res[cur], p->rays[0], p->queue[0], p->counts + 0);
+        else
+            k_gen_camera<<<cdivu(n, 256), 256, 0, st>>>(F, s, p->pathA, p->pathB, p->rays[0], p->queue[0], p->counts + 0);
         /* wavefront for the first `wave` bounces, then one tail kernel for whatever is still alive */
         /* measured (profiles/r01_tuning.md): with >= ~2.5 M paths per launch the full wavefront is fastest
          * (tail after 3 bounces: -9 %, mega-kernel: -73 %); for small shards (4K frame over 8 GPUs) every

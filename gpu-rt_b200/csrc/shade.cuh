@@ -1118,6 +1118,37 @@ SH_D void pixel_begin(const FrameParams& P, int restir, uint32_t i, float4* acc,
     }
 }
 
+/* k_begin_camera: pixel_begin + pixel_gen_camera(s = 0) in one pass — the seed goes from tea() straight into the camera
+ * ray instead of through pathB, and when every pixel is shaded at (s = 0, depth = 0) the G-buffer clear is left to
+ * shade_step (a hit overwrites it anyway; a miss writes the cleared values there): ~96 bytes per pixel less than the two
+ * kernels.  clear_gbuf: nothing will be shaded (max_depth 0), clear here. */
+SH_D void pixel_begin_camera(const FrameParams& P, int restir, int clear_gbuf, uint32_t i, uint32_t li, float4* acc,
+                             float4* pathA, float4* pathB, float4* gpos, float4* gnorm, float4* galb, float4* res_out,
+                             float4* rays, uint32_t* queue) {
+    uint32_t v0 = i, v1 = P.seed_val, s0 = 0;
+    for(uint32_t k = 0; k < 16; k++) {
+        s0 += 0x9e3779b9u;
+        v0 += ((v1 << 4) + 0xa341316cu) ^ (v1 + s0) ^ ((v1 >> 5) + 0xc8013ea4u);
+        v1 += ((v0 << 4) + 0xad90777du) ^ (v0 + s0) ^ ((v0 >> 5) + 0x7e95761eu);
+    }
+    acc[i] = make_float4(0, 0, 0, 0);
+    if(clear_gbuf) gpos[i] = gnorm[i] = galb[i] = make_float4(0, 0, 0, 1);
+    if(restir) {
+        res_out[3ull * i] = res_out[3ull * i + 1] = make_float4(0, 0, 0, 0);
+        res_out[3ull * i + 2] = make_float4(0, 0, 0, u2f(0u));
+    }
+    ShadeCtx dummy{};
+    Shader sh(dummy, P);
+    sh.seed = v0;
+    F3 d = sh.make_camera_ray(0, i % P.W, i / P.W);
+    F4 co = mul4(P.cam.iV, 0.0f, 0.0f, 0.0f, 1.0f); /* rt.rgen:572 */
+    rays[2ull * li] = make_float4(co.x, co.y, co.z, kEps);
+    rays[2ull * li + 1] = make_float4(d.x, d.y, d.z, kLargeDist);
+    queue[li] = i;
+    pathA[i] = make_float4(0, 0, 0, 1.0f);
+    pathB[i] = make_float4(1.0f, 1.0f, 1.0f, u2f(sh.seed));
+}
+
 /* k_gen_camera: sample s of pixel i -> ray slot li of queue 0 (rt.rgen:551-565, :572, :579-585) */
 SH_D void pixel_gen_camera(const FrameParams& P, uint32_t s, uint32_t i, uint32_t li, float4* pathA, float4* pathB,
                            float4* rays, uint32_t* queue) {
@@ -1146,6 +1177,9 @@ SH_D bool shade_step(const FrameParams& P, Shader& sh, TraceInfo& trace, uint32_
     bool broke = false;
     uint32_t gid = f2u(h.w);
     if(gid == kNoHit) { /* rt.rgen:591-598 */
+        /* the G-buffer of a pixel whose first ray misses keeps its cleared value (rt.rgen:573); written here because
+         * k_begin_camera leaves the clear to the first shading pass */
+        if(s == 0 && depth == 0) gpos[pix] = gnorm[pix] = galb[pix] = make_float4(0, 0, 0, 1);
         if(depth == 0) trace.acc = F3{P.c.clear_col[0], P.c.clear_col[1], P.c.clear_col[2]};
         else trace.acc = trace.acc + F3{P.c.env_light[0], P.c.env_light[1], P.c.env_light[2]} * trace.throughput;
         return true;

@@ -133,9 +133,14 @@ __global__ void __launch_bounds__(256) k_gen_camera(const __grid_constant__ Fram
 
 __global__ void __launch_bounds__(256) k_begin_camera(const __grid_constant__ FrameParams P, int restir, int clear_gbuf, float4* acc,
                                                       float4* pathA, float4* pathB, float4* gpos, float4* gnorm, float4* galb,
-                                                      float4* res_out, float4* rays, uint32_t* queue, uint32_t* count) {
+                                                      float4* res_out, float4* rays, uint32_t* queue, uint32_t* counts,
+                                                      uint32_t n_counts, unsigned long long* ray_counts) {
     uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
-    if(li == 0) *count = P.n_local;
+    /* the frame's counters start here too (n_counts = 0: the host cleared them): queue 0 holds every local pixel, the
+     * later queues are empty, no rays counted yet */
+    if(li == 0) counts[0] = P.n_local;
+    else if(li < n_counts) counts[li] = 0u;
+    if(ray_counts && li < 2u) ray_counts[li] = 0ull;
     if(li >= P.n_local) return;
     pixel_begin_camera(P, restir, clear_gbuf, shard_pixel(P, li), li, acc, pathA, pathB, gpos, gnorm, galb, res_out, rays, queue);
 }
@@ -862,13 +867,15 @@ static int render_core(gpurt_pipe* p, const GpurtPipeParams* prm, const GpurtCam
     X.ray_counts = p->ray_counts;
 
     GPURT_CUDA(cudaEventRecord(ctx->ev0, st));
-    GPURT_CUDA(cudaMemsetAsync(p->ray_counts, 0, 16, st));
-    history_wait();
     /* the first sample's camera rays are generated by the same kernel that starts the frame (k_begin_camera) unless nothing
-     * will be shaded (then k_frame_begin clears the G-buffers itself); GPURT_FUSED_BEGIN=0 keeps the two kernels */
+     * will be shaded (then k_frame_begin clears the G-buffers itself); GPURT_FUSED_BEGIN=0 keeps the separate kernels.  That
+     * kernel also zeroes the ray counters and the queue sizes when its grid covers them (two memset launches less). */
     static const bool fused_begin_ok = !(getenv("GPURT_FUSED_BEGIN") && atoi(getenv("GPURT_FUSED_BEGIN")) == 0);
     const bool shades = c.samples > 0 && c.max_depth > 0;
     const bool fused_begin = fused_begin_ok && shades;
+    const bool fused_clear = fused_begin && p->max_counts <= n;
+    if(!fused_clear) GPURT_CUDA(cudaMemsetAsync(p->ray_counts, 0, 16, st));
+    history_wait();
     if(!fused_begin)
         k_frame_begin<<<cdivu(n, 256), 256, 0, st>>>(F, restir ? 1 : 0, p->acc, p->pathB, p->gbuf[cur][0],
                                                     p->gbuf[cur][1], p->gbuf[cur][2], p->res[cur]);
@@ -896,10 +903,11 @@ static int render_core(gpurt_pipe* p, const GpurtPipeParams* prm, const GpurtCam
         return 2 * g > full_grid ? full_grid : (unsigned)g; /* more than half of the pixels alive: the plain full-size launch */
     };
     for(uint32_t s = 0; s < (uint32_t)c.samples && D > 0; s++) {
-        GPURT_CUDA(cudaMemsetAsync(p->counts, 0, (size_t)p->max_counts * 4, st));
+        if(!(s == 0 && fused_clear)) GPURT_CUDA(cudaMemsetAsync(p->counts, 0, (size_t)p->max_counts * 4, st));
         if(s == 0 && fused_begin)
             k_begin_camera<<<cdivu(n, 256), 256, 0, st>>>(F, restir ? 1 : 0, 0, p->acc, p->pathA, p->pathB, p->gbuf[cur][0], p->gbuf[cur][1],
-                                                          p->gbuf[cur][2], p->res[cur], p->rays[0], p->queue[0], p->counts + 0);
+                                                          p->gbuf[cur][2], p->res[cur], p->rays[0], p->queue[0], p->counts,
+                                                          fused_clear ? p->max_counts : 0u, fused_clear ? p->ray_counts : nullptr);
         else
             k_gen_camera<<<cdivu(n, 256), 256, 0, st>>>(F, s, p->pathA, p->pathB, p->rays[0], p->queue[0], p->counts + 0);
         /* wavefront for the first `wave` bounces, then one tail kernel for whatever is still alive */

@@ -96,6 +96,10 @@ GPURT_HD int collapse_assign(const Bvh2View& B, const int cand[8], const Box3 bo
     }
     F3 nc = (nb.lo + nb.hi) * 0.5f;
     for(int s = 0; s < 8; s++) out_child[s] = kEmptyChild;
+#ifndef GPURT_ASSIGN_VARIANT
+#define GPURT_ASSIGN_VARIANT 0
+#endif
+#if GPURT_ASSIGN_VARIANT == 0
     unsigned used_child = 0, used_slot = 0;
     for(int round = 0; round < n; round++) {
         float best = -3.0e38f;
@@ -117,6 +121,74 @@ GPURT_HD int collapse_assign(const Bvh2View& B, const int cand[8], const Box3 bo
         else if((as_leaf >> bc) & 1u) out_child[bs] = encode_leaf_range((unsigned)B.range_first[c], (unsigned)bvh2_count(B, c));
         else out_child[bs] = c;
     }
+#else
+    /* experiment (tools/assign_probe.py): the assignment that maximises the SUM of the projections, by dynamic programming
+     * over slot subsets (child i takes one of the slots not used by children 0..i-1); variant 2 / 3 divide the offsets by the
+     * node's extent first */
+    float cost[8][8];
+    F3 ext = nb.hi - nb.lo;
+    for(int i = 0; i < n; i++) {
+        F3 dlt = cen[i] - nc;
+#if GPURT_ASSIGN_VARIANT >= 2
+        dlt = F3{ext.x > 0 ? dlt.x / ext.x : 0.0f, ext.y > 0 ? dlt.y / ext.y : 0.0f, ext.z > 0 ? dlt.z / ext.z : 0.0f};
+#endif
+        for(int s = 0; s < 8; s++) cost[i][s] = ((s & 1) ? dlt.x : -dlt.x) + ((s & 2) ? dlt.y : -dlt.y) + ((s & 4) ? dlt.z : -dlt.z);
+    }
+    (void)ext;
+    int slot_of[8];
+#if GPURT_ASSIGN_VARIANT == 2
+    { /* greedy as variant 0, on the normalised offsets */
+        unsigned used_child = 0, used_slot = 0;
+        for(int round = 0; round < n; round++) {
+            float best = -3.0e38f;
+            int bc = -1, bs = -1;
+            for(int i = 0; i < n; i++) {
+                if(used_child & (1u << i)) continue;
+                for(int s = 0; s < 8; s++)
+                    if(!(used_slot & (1u << s)) && cost[i][s] > best) best = cost[i][s], bc = i, bs = s;
+            }
+            used_child |= 1u << bc, used_slot |= 1u << bs;
+            slot_of[bc] = bs;
+        }
+    }
+#else
+    {
+        float dp[256];
+        signed char choice[8][256];
+        for(int m = 0; m < 256; m++) dp[m] = -3.0e38f;
+        dp[0] = 0.0f;
+        for(int m = 0; m < 256; m++) {
+            int i = 0;
+            for(int b = m; b; b &= b - 1) i++;
+            if(i >= n || dp[m] < -1.0e38f) continue;
+            for(int s = 0; s < 8; s++) {
+                if(m & (1 << s)) continue;
+                float v = dp[m] + cost[i][s];
+                int m2 = m | (1 << s);
+                if(v > dp[m2]) dp[m2] = v, choice[i][m2] = (signed char)s;
+            }
+        }
+        int bestm = -1;
+        float bestv = -3.0e38f;
+        for(int m = 0; m < 256; m++) {
+            int i = 0;
+            for(int b = m; b; b &= b - 1) i++;
+            if(i == n && dp[m] > bestv) bestv = dp[m], bestm = m;
+        }
+        for(int i = n - 1, m = bestm; i >= 0; i--) {
+            int sl = choice[i][m];
+            slot_of[i] = sl;
+            m &= ~(1 << sl);
+        }
+    }
+#endif
+    for(int i = 0; i < n; i++) {
+        int c = cand[i], bs = slot_of[i];
+        if(c < 0) out_child[bs] = encode_leaf_range((unsigned)~c, 1);
+        else if((as_leaf >> i) & 1u) out_child[bs] = encode_leaf_range((unsigned)B.range_first[c], (unsigned)bvh2_count(B, c));
+        else out_child[bs] = c;
+    }
+#endif
     int n_inner = 0;
     n_leaf_tris = 0;
     for(int s = 0; s < 8; s++) {

@@ -99,7 +99,11 @@ int plan_spatial_order(gpurt_accel* A, const float4* pos, unsigned stride_vec4, 
     }
     static const bool allow = !(getenv("GPURT_SPATIAL_ORDER") && atoi(getenv("GPURT_SPATIAL_ORDER")) == 0);
     const size_t bvh_bytes = (size_t)A->n_nodes * sizeof(Node8) + (size_t)A->n * 48;
-    if(!allow || n < kOrderMinBatch || n >= (1ull << 30) || bvh_bytes <= kOrderMinBvhBytes) return GPURT_OK;
+    /* test hooks (sanitizer runs, small-scene tests of the ordered paths): GPURT_ORDER_MIN_BATCH / GPURT_ORDER_MIN_BVH_BYTES */
+    const char *eb = getenv("GPURT_ORDER_MIN_BATCH"), *ev = getenv("GPURT_ORDER_MIN_BVH_BYTES");
+    const uint64_t min_batch = eb ? (uint64_t)atoll(eb) : kOrderMinBatch;
+    const size_t min_bvh = ev ? (size_t)atoll(ev) : kOrderMinBvhBytes;
+    if(!allow || n < min_batch || n >= (1ull << 30) || bvh_bytes <= min_bvh) return GPURT_OK;
     /* scratch in the build arena (no build runs concurrently on this stream): keys | keys_tmp | vals | vals_tmp | counter | staging */
     const size_t kb = ((size_t)n * 8 + 255) & ~(size_t)255, vb = ((size_t)n * 4 + 255) & ~(size_t)255;
     cudaPointerAttributes pa;
@@ -158,7 +162,7 @@ int plan_spatial_order(gpurt_accel* A, const float4* pos, unsigned stride_vec4, 
 void order_slices(uint64_t n, std::vector<uint64_t>& ends) {
     ends.clear();
     const char* env = getenv("GPURT_PLACE_SLICES");
-    const uint64_t min_slice = 1u << 18;
+    const uint64_t min_slice = getenv("GPURT_ORDER_MIN_BATCH") ? 256u : 1u << 18; /* small slices only under the test hook */
     if(env && atoi(env) > 0) {
         const uint64_t k = (uint64_t)atoi(env);
         uint64_t s = std::max<uint64_t>((n + k - 1) / k, min_slice);

@@ -994,6 +994,7 @@ int build_sah_split_device(gpurt_ctx* ctx, const float4* tri_lo, const float4* t
     if(const char* e = getenv("GPURT_SAH_SMALL_MAX")) small_max = std::max<unsigned>(SAH_TILE, (unsigned)atoi(e));
     const bool big_root = n > small_max;
     GPURT_CUDA(cudaMemsetAsync(ready, 0, cap * 4, st));
+    GPURT_CUDA(cudaMemsetAsync(state, 0, sizeof(SahState), st)); /* the padding words travel to the host with the rest */
     k_sah_setup<<<1, 128, 0, st>>>(n, small_max, state, segs[0], jobs, ready, cb, bins, tiles_done);
     k_sah_init<<<std::min((n + 255) / 256, (unsigned)ctx->sm_count * 8u), 256, 0, st>>>(tri_lo, tri_hi, n, rec[0], seg_of[0],
                                                                                    big_root ? 0 : -1, keys, cb);

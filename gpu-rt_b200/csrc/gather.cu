@@ -246,10 +246,18 @@ int gpurt_gather_open(gpurt_ctx* ctx, const uint8_t* handle, void* same_process_
         }
     }
     g->ipc = !same_process_base; /* same-process bases are not unmapped on destroy */
-    GPURT_CUDA(cudaStreamCreateWithFlags(&g->s_side, cudaStreamNonBlocking));
-    GPURT_CUDA(cudaEventCreateWithFlags(&g->ev, cudaEventDisableTiming));
+    cudaError_t e = cudaStreamCreateWithFlags(&g->s_side, cudaStreamNonBlocking);
+    if(e == cudaSuccess) e = cudaEventCreateWithFlags(&g->ev, cudaEventDisableTiming);
+    if(e != cudaSuccess) {
+        set_error(std::string("gpurt_gather_open: ") + cudaGetErrorString(e));
+        gpurt_gather_destroy(g);
+        return GPURT_E_CUDA;
+    }
     /* sort scratch + staging of this rank's batch, allocated outside the rounds (see gpurt_gather_create) */
-    if((rc = ctx->build_arena.reserve(order_arena_bytes(first[my_rank + 1] - first[my_rank], record_bytes, true)))) return rc;
+    if((rc = ctx->build_arena.reserve(order_arena_bytes(first[my_rank + 1] - first[my_rank], record_bytes, true)))) {
+        gpurt_gather_destroy(g);
+        return rc;
+    }
     ctx->gathers.push_back(g);
     *out = g;
     return GPURT_OK;

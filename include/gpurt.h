@@ -373,7 +373,9 @@ int gpurt_pipe_set_shard(gpurt_pipe* pipe, uint32_t band_rows, uint32_t n_shards
  *      contiguous bands (band_rows = ceil(h / n_shards)) moves (n-1)/n less data.
  *   3. all shards render the same sequence of frames (same count, same sizes); a shard that is 20 s late is not waited for
  *      any longer (the frame proceeds on stale rows and gpurt_pipe_history_status counts the time-out).
- * Inside one process on one stream, render frame f on every shard before frame f + 1 on any. */
+ * Inside one process on one stream, render frame f on every shard before frame f + 1 on any.
+ * Lifetime: a shard's block is freed by gpurt_pipe_destroy and re-allocated when the frame size changes — the other shards
+ * call gpurt_pipe_history_peers(pipe, 0, NULL, 0) and unmap it (gpurt_shared_close) first. */
 #define GPURT_HISTORY_ALL_ROWS 0xFFFFFFFFu
 int gpurt_pipe_history_export(gpurt_pipe* pipe, uint32_t width, uint32_t height, void** out_device_ptr,
                               uint8_t handle_out[GPURT_IPC_HANDLE_BYTES], uint64_t* out_bytes);

@@ -30,6 +30,25 @@
 
 using namespace gpurt;
 
+/* Minimum CTAs per SM asked of the shade / tail kernels of each integrator (ptxas caps the registers accordingly).  Measured
+ * on mis_test 1080p (tools/ab_restir.sh, variants built side by side): MIS 5 -> 6 CTAs (96 -> 80 registers, 40 B of spills)
+ * 0.434 -> 0.386 ms per frame, 7: 0.395, 4: 0.446; ReSTIR 4 -> 7 CTAs (128 -> 72 registers, 504 B of spills) 0.283 -> 0.265 and
+ * 0.331 -> 0.308 ms, 6: 0.270 / 0.316, 8: 0.262 / 0.311; direct 5 -> 8 CTAs (96 -> 64 registers, 60 B of spills): the reference's
+ * default workload (cbox 1280x720, 8 spp, depth 8) 1.873 -> 1.720 ms per frame, 7 CTAs: 1.742; material (64 registers as it
+ * is) 9 / 10 CTAs: -1 % / +0.5 %, left alone.  These kernels wait on dependent gathers; more resident warps beat fewer spills. */
+#ifndef GPURT_MIS_MINB
+#define GPURT_MIS_MINB 6
+#endif
+#ifndef GPURT_RESTIR_MINB
+#define GPURT_RESTIR_MINB 7
+#endif
+#ifndef GPURT_MAT_MINB
+#define GPURT_MAT_MINB 0
+#endif
+#ifndef GPURT_DIRECT_MINB
+#define GPURT_DIRECT_MINB 8
+#endif
+
 struct gpurt_pipe {
     gpurt_ctx* ctx = nullptr;
     gpurt_scene* scene = nullptr;
@@ -178,7 +197,7 @@ __global__ void __launch_bounds__(128) k_trace_closest_indirect(const float4* __
  * (otherwise unused) next-bounce queue together with the term it gates, and k_shadow_resolve traces it and finishes
  * the pixel.  Paths of integrator 0 end at their first hit, so nothing else competes for that queue. */
 template <int INTEG, bool DEFER = false>
-__global__ void __launch_bounds__(128, INTEG == 2 ? 5 : 0) k_shade(const __grid_constant__ FrameParams P,
+__global__ void __launch_bounds__(128, INTEG == 2 ? GPURT_MIS_MINB : (INTEG >= 3 ? GPURT_RESTIR_MINB : (INTEG == 1 ? GPURT_MAT_MINB : GPURT_DIRECT_MINB))) k_shade(const __grid_constant__ FrameParams P,
                                                const __grid_constant__ ShadeCtx X, uint32_t s, uint32_t depth,
                                                const uint32_t* __restrict__ count_in, const uint32_t* __restrict__ queue_in,
                                                const float4* __restrict__ rays_in, const float4* __restrict__ hits,
@@ -277,7 +296,7 @@ __global__ void __launch_bounds__(128) k_shadow_resolve(const float4* __restrict
  * Here every remaining path runs its bounce loop to the end in one thread: same shade_step, same
  * traverse8, same per-pixel RNG stream, so the image does not change — only the launch count does. */
 template <int INTEG>
-__global__ void __launch_bounds__(128, INTEG == 2 ? 5 : 0) k_tail(const __grid_constant__ FrameParams P, const __grid_constant__ ShadeCtx X,
+__global__ void __launch_bounds__(128, INTEG == 2 ? GPURT_MIS_MINB : (INTEG >= 3 ? GPURT_RESTIR_MINB : (INTEG == 1 ? GPURT_MAT_MINB : GPURT_DIRECT_MINB))) k_tail(const __grid_constant__ FrameParams P, const __grid_constant__ ShadeCtx X,
                                               uint32_t s, uint32_t depth0, const uint32_t* __restrict__ count_in,
                                               const uint32_t* __restrict__ queue_in, const float4* __restrict__ rays_in,
                                               float4* pathA, float4* pathB, float4* acc, float4* gpos, float4* gnorm,

@@ -13,8 +13,13 @@
 
 namespace gpurt {
 
+#ifndef GPURT_CPQ_MINB
+#define GPURT_CPQ_MINB 10 /* minimum CTAs per SM asked of k_closest_points: 48 registers instead of 54 (8 B of spills); bench
+                            queries 1388 -> 1430 Mq/s; 8 CTAs (58 registers) 1315, 12 CTAs (40 registers, 140 B spills) 1350
+                            (tools/ab_cpq.sh, variants built side by side, interleaved x 3) */
+#endif
 template <int STACK, bool ORDERED>
-__global__ void __launch_bounds__(128) k_closest_points(const float4* __restrict__ nodes,
+__global__ void __launch_bounds__(128, GPURT_CPQ_MINB) k_closest_points(const float4* __restrict__ nodes,
                                                         const float4* __restrict__ tris,
                                                         const float4* __restrict__ queries, uint64_t n,
                                                         float4* __restrict__ results, unsigned n_nodes,

@@ -761,7 +761,11 @@ __device__ __forceinline__ void subtree32(unsigned a, unsigned m, int me0, int p
     if((unsigned)lane < m) O.order[a + lane] = __float_as_uint(l.w);
 }
 
-__global__ void __launch_bounds__(128) k_sah_small(SahRec* rec0, SahRec* rec1, SahJob* jobs, unsigned* ready, SahState* st,
+#ifndef GPURT_SAH_SMALL_MINB
+#define GPURT_SAH_SMALL_MINB 0 /* minimum CTAs per SM asked of k_sah_small (A/B builds, tools/ab_build.sh): 72 registers as compiled;
+                                  8 / 10 / 12 CTAs (64 / 48 / 40 registers, spills) make the stand-in build 1.40 -> 1.43 / 1.53 / 1.60 ms */
+#endif
+__global__ void __launch_bounds__(128, GPURT_SAH_SMALL_MINB) k_sah_small(SahRec* rec0, SahRec* rec1, SahJob* jobs, unsigned* ready, SahState* st,
                                                     unsigned cap, SmallOut O) {
     __shared__ float4 s_stage[4][64];
     __shared__ uint4 s_stack[4][32];

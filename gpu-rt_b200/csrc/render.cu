@@ -110,6 +110,11 @@ struct gpurt_pipe {
     gpurt_accel* laccel = nullptr;
     uint64_t laccel_version = ~0ull, laccel_geom = ~0ull;
     bool use_lbvh = true;                             /* GPURT_LIGHT_BVH=0: light-run boxes only */
+    /* gpurt_pipe_read_image_async: the image crosses PCIe on a second stream while the next frame traces and shades;
+     * the next writer of `image` (k_frame_end, k_accumulate_mean) waits for ev_copy */
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_frame = nullptr, ev_copy = nullptr;
+    bool copy_pending = false;
 };
 
 namespace gpurt {
@@ -708,6 +713,12 @@ int gpurt_pipe_destroy(gpurt_pipe* p) {
     pipe_drop_light_accel(p);
     if(p->h_counts) cudaFreeHost(p->h_counts);
     if(p->ev_counts) cudaEventDestroy(p->ev_counts);
+    if(p->copy_stream) {
+        cudaStreamSynchronize(p->copy_stream);
+        cudaStreamDestroy(p->copy_stream);
+        cudaEventDestroy(p->ev_frame);
+        cudaEventDestroy(p->ev_copy);
+    }
     delete p;
     return GPURT_OK;
 }
@@ -980,6 +991,7 @@ static int render_core(gpurt_pipe* p, const GpurtPipeParams* prm, const GpurtCam
         /* closest-hit rays of the wavefront = sum of queue sizes */
     }
     const bool report = D > 0 && c.samples > 0 && p->h_counts && p->max_counts <= n; /* this frame's queue sizes -> next frame */
+    if(p->copy_pending) GPURT_CUDA(cudaStreamWaitEvent(st, p->ev_copy, 0)); /* an asynchronous read-back still reads the image */
     k_frame_end<<<cdivu(n, 256), 256, 0, st>>>(F, p->acc, p->image, p->gbuf[cur][0], p->gbuf[cur][1], p->gbuf[prev][0],
                                               p->gbuf[prev][1], p->gbuf[prev][2], mean_out, p->counts,
                                               report ? p->h_counts : nullptr, p->max_counts);
@@ -1009,6 +1021,7 @@ int gpurt_pipe_accumulate_mean(gpurt_pipe* p, const void* mean_device, int32_t f
     GPURT_CUDA(cudaSetDevice(p->ctx->device));
     if(!p->image || p->w != w || p->h != h) return set_error("accumulate: the pipe has no image of this size (render or resize first)"), GPURT_E_STATE;
     cudaStream_t st = p->ctx->stream;
+    if(p->copy_pending) GPURT_CUDA(cudaStreamWaitEvent(st, p->ev_copy, 0));
     GPURT_CUDA(cudaEventRecord(p->ctx->ev0, st));
     k_accumulate_mean<<<cdivu(w * h, 256), 256, 0, st>>>(p->image, (const float4*)mean_device, w * h, frame);
     GPURT_CUDA(cudaEventRecord(p->ctx->ev1, st));
@@ -1039,6 +1052,32 @@ static int copy_out(gpurt_pipe* p, const void* src, size_t bytes, void* dst, int
 int gpurt_pipe_read_image(gpurt_pipe* p, float* out, int mem) {
     if(!p || !out || !p->image) return set_error("no image"), GPURT_E_STATE;
     return copy_out(p, p->image, (size_t)p->w * p->h * 16, out, mem);
+}
+/* Progressive display without a stall (the reference hands rt_target to the tonemap pass on the GPU, src/gpurt.cpp:60-66;
+ * a headless consumer wants it in host memory): the copy is ordered after the frames rendered so far, runs on the pipe's
+ * own copy stream and overlaps the tracing / shading of the following frames; only their accumulation kernel waits for it. */
+int gpurt_pipe_read_image_async(gpurt_pipe* p, float* out_host) {
+    if(!p || !out_host || !p->image) return set_error("no image"), GPURT_E_STATE;
+    GPURT_CUDA(cudaSetDevice(p->ctx->device));
+    if(!p->copy_stream) {
+        GPURT_CUDA(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
+        GPURT_CUDA(cudaEventCreateWithFlags(&p->ev_frame, cudaEventDisableTiming));
+        GPURT_CUDA(cudaEventCreateWithFlags(&p->ev_copy, cudaEventDisableTiming));
+    }
+    GPURT_CUDA(cudaEventRecord(p->ev_frame, p->ctx->stream));
+    GPURT_CUDA(cudaStreamWaitEvent(p->copy_stream, p->ev_frame, 0));
+    GPURT_CUDA(cudaMemcpyAsync(out_host, p->image, (size_t)p->w * p->h * 16, cudaMemcpyDeviceToHost, p->copy_stream));
+    GPURT_CUDA(cudaEventRecord(p->ev_copy, p->copy_stream));
+    p->copy_pending = true;
+    return GPURT_OK;
+}
+int gpurt_pipe_read_image_wait(gpurt_pipe* p) {
+    if(!p) return set_error("NULL argument"), GPURT_E_INVALID;
+    if(!p->copy_pending) return GPURT_OK;
+    GPURT_CUDA(cudaSetDevice(p->ctx->device));
+    GPURT_CUDA(cudaEventSynchronize(p->ev_copy));
+    p->copy_pending = false;
+    return GPURT_OK;
 }
 int gpurt_pipe_read_gbuffer(gpurt_pipe* p, int which, float* out, int mem) {
     if(!p || !out || !p->image || which < 0 || which > 2) return set_error("bad g-buffer request"), GPURT_E_STATE;

@@ -91,6 +91,7 @@ SYMBOLS = [
     "gpurt_trace_closest_bvh2", "gpurt_trace_closest_stats", "gpurt_closest_points_stats", "gpurt_last_kernel_ms",
     "gpurt_pipe_params_default", "gpurt_pipe_create", "gpurt_pipe_destroy", "gpurt_pipe_reset_frame",
     "gpurt_pipe_render_frame", "gpurt_pipe_frame_index", "gpurt_pipe_read_image", "gpurt_pipe_read_gbuffer",
+    "gpurt_pipe_read_image_async", "gpurt_pipe_read_image_wait", "gpurt_write_exr",
     "gpurt_pipe_ray_counts", "gpurt_pipe_device_image", "gpurt_tonemap", "gpurt_pipe_last_uniforms",
     "gpurt_pipe_read_reservoirs", "gpurt_pipe_bounce_rays", "gpurt_pipe_set_shard",
     "gpurt_pipe_history_export", "gpurt_pipe_history_peers", "gpurt_pipe_history_status",
@@ -386,6 +387,13 @@ def camera(mode=0, width=1280, height=720, pos=None, center=None, vfov=90.0):
     return cam
 
 
+def write_exr(path, rgba):
+    """rgba: (h, w, 4) float32 in host memory -> OpenEXR file (uncompressed scanlines, 32-bit float A B G R)"""
+    rgba = np.ascontiguousarray(rgba, np.float32)
+    assert rgba.ndim == 3 and rgba.shape[2] == 4
+    _check(lib.gpurt_write_exr(os.fsencode(path), rgba.ctypes.data_as(C.c_void_p), rgba.shape[1], rgba.shape[0]))
+
+
 def pipe_params(**kw):
     p = PipeParams()
     _check(lib.gpurt_pipe_params_default(C.byref(p)))
@@ -582,6 +590,18 @@ class RTPipe:
         p, m, _k = _ptr(out)
         _check(lib.gpurt_pipe_read_image(self.h, p, m))
         return out
+
+    def read_image_async(self, out):
+        """Queue a copy of the image (as of the frames rendered so far) into page-locked host memory `out`; it
+        overlaps the following frames.  read_image_wait() returns when it has landed."""
+        p, m, _k = _ptr(out)
+        if m != MEM_HOST:
+            raise ValueError("read_image_async copies to host memory")
+        _check(lib.gpurt_pipe_read_image_async(self.h, p))
+        return out
+
+    def read_image_wait(self):
+        _check(lib.gpurt_pipe_read_image_wait(self.h))
 
     def read_gbuffer(self, which, out=None):
         if out is None:

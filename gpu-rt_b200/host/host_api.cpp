@@ -2,7 +2,9 @@
  * host_api.cpp — host-only half of the C ABI: error state, scene loading / packing, camera.
  * Needs no GPU; the CUDA half lives in csrc/api.cu.
  */
+#include <cstdio>
 #include <cstring>
+#include <vector>
 
 #include "camera.h"
 #include "internal.h"
@@ -275,3 +277,70 @@ int gpurt_pipe_params_default(GpurtPipeParams* p) { /* rt.h:38-53 */
 }
 
 } /* extern "C" */
+
+/* ---- OpenEXR output (no reference code: the reference links tinyexr) ------------------------------------------------
+ * File layout (OpenEXR file-layout document): magic 20000630, version 2 (no flag bits: single part, scanlines, short
+ * names), header = attributes (name\0 type\0 size value) ended by \0, offset table (one u64 per scanline block; without
+ * compression a block is one scanline), blocks (y, byte count, then the row channel by channel in header order). */
+namespace {
+struct ExrOut {
+    std::vector<uint8_t> b;
+    void u8(uint8_t v) { b.push_back(v); }
+    void i32(int32_t v) {
+        for(int k = 0; k < 4; k++) b.push_back((uint8_t)((uint32_t)v >> (8 * k)));
+    }
+    void u64(uint64_t v) {
+        for(int k = 0; k < 8; k++) b.push_back((uint8_t)(v >> (8 * k)));
+    }
+    void f32(float v) {
+        uint32_t u;
+        std::memcpy(&u, &v, 4);
+        i32((int32_t)u);
+    }
+    void str(const char* s) {
+        while(*s) b.push_back((uint8_t)*s++);
+        b.push_back(0);
+    }
+    void attr(const char* name, const char* type, int32_t size) { str(name), str(type), i32(size); }
+};
+} // namespace
+int gpurt_write_exr(const char* path, const float* rgba, uint32_t w, uint32_t h) {
+    if(!path || !rgba || !w || !h || w > (1u << 24) || h > (1u << 24)) return set_error("write_exr: bad argument"), GPURT_E_INVALID;
+    ExrOut o;
+    o.i32(20000630), o.i32(2);
+    static const char* const names[4] = {"A", "B", "G", "R"};   /* channels are stored in alphabetical order */
+    static const int source[4] = {3, 2, 1, 0};                   /* index into the RGBA pixel */
+    o.attr("channels", "chlist", 4 * (2 + 16) + 1);
+    for(int c = 0; c < 4; c++) {
+        o.str(names[c]);
+        o.i32(2);                                               /* FLOAT */
+        o.u8(0), o.u8(0), o.u8(0), o.u8(0);                     /* pLinear + reserved */
+        o.i32(1), o.i32(1);                                     /* x / y sampling */
+    }
+    o.u8(0);
+    o.attr("compression", "compression", 1), o.u8(0);
+    o.attr("dataWindow", "box2i", 16), o.i32(0), o.i32(0), o.i32((int32_t)w - 1), o.i32((int32_t)h - 1);
+    o.attr("displayWindow", "box2i", 16), o.i32(0), o.i32(0), o.i32((int32_t)w - 1), o.i32((int32_t)h - 1);
+    o.attr("lineOrder", "lineOrder", 1), o.u8(0);               /* increasing y */
+    o.attr("pixelAspectRatio", "float", 4), o.f32(1.0f);
+    o.attr("screenWindowCenter", "v2f", 8), o.f32(0.0f), o.f32(0.0f);
+    o.attr("screenWindowWidth", "float", 4), o.f32(1.0f);
+    o.u8(0);
+    const uint64_t row_bytes = (uint64_t)w * 16, block = 8 + row_bytes, first = o.b.size() + 8ull * h;
+    for(uint32_t y = 0; y < h; y++) o.u64(first + block * y);
+    FILE* f = fopen(path, "wb");
+    if(!f) return set_error(std::string("write_exr: cannot open ") + path), GPURT_E_IO;
+    bool ok = fwrite(o.b.data(), 1, o.b.size(), f) == o.b.size();
+    std::vector<float> row((size_t)w * 4);
+    for(uint32_t y = 0; y < h && ok; y++) {
+        ExrOut hd;
+        hd.i32((int32_t)y), hd.i32((int32_t)row_bytes);
+        const float* src = rgba + (size_t)y * w * 4;
+        for(int c = 0; c < 4; c++)
+            for(uint32_t x = 0; x < w; x++) row[(size_t)c * w + x] = src[4ull * x + source[c]];
+        ok = fwrite(hd.b.data(), 1, 8, f) == 8 && fwrite(row.data(), 4, row.size(), f) == row.size(); /* little-endian host */
+    }
+    ok = fclose(f) == 0 && ok;
+    if(!ok) return set_error(std::string("write_exr: short write to ") + path), GPURT_E_IO;
+    return GPURT_OK;
+}

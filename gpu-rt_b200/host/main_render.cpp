@@ -102,7 +102,7 @@ int main(int argc, char** argv) {
         }
     }
     if(scene_file.empty() && !standin) {
-        fprintf(stderr, "usage: gpurt_render -s scene.gltf|--sponza-standin [-o out.png] [--size W H] [--frames N] [--spp N] "
+        fprintf(stderr, "usage: gpurt_render -s scene.gltf|--sponza-standin [-o out.png|out.exr] [--size W H] [--frames N] [--spp N] "
                         "[--depth N] [--integrator 0..4] [--brdf 0|1] [--camera px py pz ax ay az vfov] ...\n");
         return 2;
     }
@@ -126,9 +126,16 @@ int main(int argc, char** argv) {
         auto t1 = std::chrono::steady_clock::now();
         int frames = 0;
         while(pipe.trace(cam, w, h)) frames++; /* GPURT::render until converged (rt.cpp:353) */
-        auto img = pipe.tonemap(tonemap_op, exposure, gamma);
         auto t2 = std::chrono::steady_clock::now();
-        if(!write_png(out, img, w, h)) throw std::runtime_error("cannot write " + out);
+        if(out.size() > 4 && out.compare(out.size() - 4, 4, ".exr") == 0) { /* linear radiance, untouched by the tonemap pass */
+            auto lin = pipe.read_image();
+            t2 = std::chrono::steady_clock::now();
+            gpurt::check(gpurt_write_exr(out.c_str(), lin.data(), w, h));
+        } else {
+            auto img = pipe.tonemap(tonemap_op, exposure, gamma);
+            t2 = std::chrono::steady_clock::now();
+            if(!write_png(out, img, w, h)) throw std::runtime_error("cannot write " + out);
+        }
         printf("%u tris, %u wide nodes (depth %u), build %.2f ms; %d frames x %d spp at %ux%u in %.1f ms -> %s\n", info.n_tris,
                info.n_wide_nodes, info.wide_depth, info.build_ms, frames, o.spp, w, h,
                std::chrono::duration<double, std::milli>(t2 - t1).count(), out.c_str());

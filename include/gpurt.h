@@ -393,6 +393,13 @@ int gpurt_pipe_accumulate_mean(gpurt_pipe* pipe, const void* mean_device, int32_
                                uint32_t height);
 /* rt_target (RGBA32F, src/gpurt.cpp:189-193) -> caller buffer of width*height*4 floats. */
 int gpurt_pipe_read_image(gpurt_pipe* pipe, float* out_rgba, int mem);
+/* The same copy without stalling the render loop (GPURT::render hands rt_target to the next pass on the GPU,
+ * src/gpurt.cpp:60-66; a headless consumer wants it in host memory): snapshot of the image as of the frames queued so
+ * far, copied to page-locked host memory by the pipe's own copy stream while the following frames trace and shade — only
+ * their accumulation into rt_target waits for the copy.  gpurt_pipe_read_image_wait returns once the last requested copy
+ * has landed (earlier ones have, too: they are ordered).  Pageable memory works but makes the call itself synchronous. */
+int gpurt_pipe_read_image_async(gpurt_pipe* pipe, float* out_rgba_host);
+int gpurt_pipe_read_image_wait(gpurt_pipe* pipe);
 /* which: 0 position, 1 normal, 2 albedo (rt.rgen:674-676) */
 int gpurt_pipe_read_gbuffer(gpurt_pipe* pipe, int which, float* out_rgba, int mem);
 /* rays traced by the last frame: [0] closest-hit, [1] any-hit */
@@ -412,6 +419,11 @@ int gpurt_pipe_bounce_rays(gpurt_pipe* pipe, uint32_t bounce, void** out_dev_ray
 
 /* tonemap.frag:17-48 (exposure/Uncharted2 + gamma) -> RGBA8, host or device output */
 int gpurt_tonemap(gpurt_pipe* pipe, int op, float exposure, float gamma, uint8_t* out_rgba8, int mem);
+
+/* rt_target as a file in linear radiance (the reference vendors tinyexr next to stb_image_write,
+ * deps/sf_libs, and GPURT::save_rt, src/gpurt.cpp:258-262, writes the tonemapped PNG): OpenEXR 2, one part, scanlines,
+ * no compression, channels A B G R as 32-bit float.  rgba = width*height*4 floats in HOST memory, row 0 on top. */
+int gpurt_write_exr(const char* path, const float* rgba, uint32_t width, uint32_t height);
 
 #ifdef __cplusplus
 }

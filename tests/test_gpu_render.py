@@ -413,6 +413,17 @@ def test_headless_cli_writes_the_same_image_as_the_api(gpurt, orc, ctx, tmp_path
     api = pipe.tonemap(1, 1.5, 2.2)
     assert cli.shape == api.shape and (cli == api).all()
     assert (api == orc.tonemap(st.image, 1, 1.5, 2.2)).all()
+    # -o *.exr: the same frames as linear radiance, bit for bit the oracle's rt_target
+    from test_host import _read_exr
+    out_exr = str(tmp_path / "cli.exr")
+    r = subprocess.run([exe, "-s", os.path.join(MEDIA, "cbox", "cbox.gltf"), "-o", out_exr, "--size", str(w), str(h), "--frames", str(frames),
+                        "--spp", str(spp), "--depth", "4", "--integrator", "2", "--brdf", "1", "--seed", "9"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    _, ch = _read_exr(out_exr)
+    lin = np.stack([ch[c] for c in "RGBA"], axis=-1)
+    assert (lin.view(np.uint32) == pipe.read_image().view(np.uint32)).all()
+    _compare("cli exr vs oracle", lin, st.image)
     pipe.close(), accel.close(), scene.close()
 
 
@@ -445,6 +456,34 @@ def test_frame_parallel_equals_sequential(gpurt, ctx):
     with pytest.raises(gpurt.GpurtError):       # ReSTIR frames depend on the previous frame
         par.render_frame_mean(gpurt.pipe_params(integrator=3), cam, w, h, 0, means[0])
     for o in (seq, par, other, accel, scene):
+        o.close()
+
+
+def test_async_image_read_back_is_a_snapshot_of_its_frame(gpurt, ctx):
+    """gpurt_pipe_read_image_async / _wait: every queued copy holds the image as of the frames rendered before the call,
+    although the following frames were queued (and trace / shade) while it crossed PCIe"""
+    import torch
+    w, h, frames = 640, 360, 6
+    scene = load_scene(gpurt, ctx, "cbox")
+    accel = gpurt.Accel(scene)
+    prm = gpurt.pipe_params(max_frames=64, samples_per_frame=2, max_depth=4, integrator=2, brdf=1, seed=5)
+    cam = gpurt.camera(0, w, h)
+    seq = gpurt.RTPipe(scene, accel)
+    want = []
+    for _ in range(frames):
+        assert seq.render_frame(prm, cam, w, h) == 0
+        want.append(seq.read_image().copy())
+    pipe = gpurt.RTPipe(scene, accel)
+    pinned = [torch.empty((h, w, 4), dtype=torch.float32).pin_memory() for _ in range(frames)]
+    for f in range(frames):                     # no host synchronisation inside this loop
+        assert pipe.render_frame(prm, cam, w, h) == 0
+        pipe.read_image_async(pinned[f])
+    pipe.read_image_wait()
+    for f in range(frames):
+        assert (pinned[f].numpy().view(np.uint32) == want[f].view(np.uint32)).all(), f"snapshot of frame {f}"
+    assert (pipe.read_image().view(np.uint32) == want[-1].view(np.uint32)).all()
+    pipe.read_image_wait()                      # nothing pending: returns at once
+    for o in (seq, pipe, accel, scene):
         o.close()
 
 

@@ -414,7 +414,7 @@ def test_headless_cli_writes_the_same_image_as_the_api(gpurt, orc, ctx, tmp_path
     assert cli.shape == api.shape and (cli == api).all()
     assert (api == orc.tonemap(st.image, 1, 1.5, 2.2)).all()
     # -o *.exr: the same frames as linear radiance, bit for bit the oracle's rt_target
-    from test_host import _read_exr
+    from exr_reader import read_exr as _read_exr
     out_exr = str(tmp_path / "cli.exr")
     r = subprocess.run([exe, "-s", os.path.join(MEDIA, "cbox", "cbox.gltf"), "-o", out_exr, "--size", str(w), str(h), "--frames", str(frames),
                         "--spp", str(spp), "--depth", "4", "--integrator", "2", "--brdf", "1", "--seed", "9"],

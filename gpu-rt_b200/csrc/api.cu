@@ -400,9 +400,9 @@ int gpurt_accel_get_bvh2(const gpurt_accel* A, int32_t* left, int32_t* right, fl
 
 /* ---- queries ---------------------------------------------------------------------------------- */
 /* true when a batch of n elements is answered by one pass over its input (order.cu does not re-order it) */
-static bool single_pass(const gpurt_accel* A, uint64_t n) {
+static bool single_pass(const gpurt_accel* A, uint64_t n, bool any_bvh_size = false) {
     const size_t bvh_bytes = (size_t)A->n_nodes * sizeof(Node8) + (size_t)A->n * 48;
-    return n < (1u << 20) || bvh_bytes <= (64u << 20);
+    return n < (1u << 20) || bvh_bytes <= (any_bvh_size ? (4u << 20) : (64u << 20)); /* order.cu kOrderMinBvhBytes[Points] */
 }
 int gpurt_trace_closest(gpurt_accel* A, const GpurtRay* rays, uint64_t n, GpurtHit* hits, int mem) {
     if(!A || (n && (!rays || !hits))) return set_error("NULL argument"), GPURT_E_INVALID;
@@ -425,7 +425,7 @@ int gpurt_closest_points(gpurt_accel* A, const GpurtQuery* q, uint64_t n, GpurtC
     if(!A || (n && (!q || !res))) return set_error("NULL argument"), GPURT_E_INVALID;
     return run_query(A->ctx, q, sizeof(GpurtQuery), res, sizeof(GpurtClosestPoint), n, mem,
                      [&](const void* i, void* o, uint64_t c) { return launch_closest_points(A, (const float4*)i, c, (float4*)o); },
-                     single_pass(A, n));
+                     single_pass(A, n, true)); /* point batches may be re-ordered on scenes > 4 MB (cpq.cu) */
 }
 int gpurt_trace_closest_stats(gpurt_accel* A, const GpurtRay* rays, uint64_t n, GpurtHit* hits,
                               GpurtTraceStats* out) {

@@ -76,8 +76,11 @@ int launch_closest_points(gpurt_accel* A, const float4* queries, uint64_t n, flo
     if(!n) return GPURT_OK;
     const float4* nodes = (const float4*)A->nodes;
     cudaStream_t st = A->ctx->stream;
-    OrderPlan P; /* large incoherent batches on large scenes are processed in Morton order of the query point (order.cu) */
-    int rc = plan_spatial_order(A, queries, 1, n, results, 32, P, true);
+    /* large incoherent batches are processed in Morton order of the query point (order.cu) — on every scene larger than
+     * the L1s: the descent diverges with the spread of a warp's points even when the whole tree sits in L2 (stand-in, 2 M
+     * points jittered by +-200 units: 738 -> 1101 Mq/s including the sort; profiles/r04c_cpq_order.log) */
+    OrderPlan P;
+    int rc = plan_spatial_order(A, queries, 1, n, results, 32, P, true, true);
     if(rc) return rc;
     unsigned need = 7u * A->depth + 1u;
     if(need > 512) return set_error("wide BVH too deep for the closest-point stack"), GPURT_E_STATE;

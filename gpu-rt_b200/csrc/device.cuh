@@ -119,7 +119,7 @@ struct OrderPlan {
     bool scatter = false; /* results on another GPU: slices staged in processing order, scattered by a second stream */
 };
 int plan_spatial_order(gpurt_accel* A, const float4* pos, unsigned stride_vec4, uint64_t n, void* results,
-                       size_t result_bytes, OrderPlan& P, bool sliced_scatter = false);
+                       size_t result_bytes, OrderPlan& P, bool sliced_scatter = false, bool any_bvh_size = false);
 int finish_spatial_order(gpurt_accel* A, const OrderPlan& P, uint64_t n, void* results, size_t result_bytes);
 /* remote results of an ordered batch: the slice [off, off + m) of the staging array (processing order) goes to its storage
  * positions in `results` on the placement stream, after everything queued on the context's stream so far */

@@ -7,9 +7,15 @@
  * 10 M-triangle config-4 soup (tools/cpq_sort_probe.py, tools/ray_sort_probe.py): uniform random points
  * 807 -> 1355 Mq/s and uniform random rays 676 -> 970 Mrays/s when processed in Morton order of the position.
  * So such batches get a 30-bit Morton key per element, a 4-pass radix sort of (key, index) pairs, and the
- * traversal kernel reads its element and writes its result through the sorted index.  Skipped when the scene is
- * small (BVH < 64 MB: order hardly matters once the tree sits in L2), when the batch is small (< 2^20), or when
- * neighbouring elements already share a cell of a 16^3 grid (e.g. rays and points generated per pixel).
+ * traversal kernel reads its element and writes its result through the sorted index.  Skipped when the batch is small
+ * (< 2^20), when a probe on 1 / 16 of the batch finds that neighbouring elements already share a cell of a 16^3 grid
+ * (32^3 on small scenes; e.g. rays and points generated per pixel), and — for rays — when the scene is small (BVH < 64 MB:
+ * ray order hardly matters once the tree sits in L2; stand-in bounce rays gain 10-18 % BEFORE paying for the sort).
+ * Closest-point batches are re-ordered on every scene larger than the L1s (4 MB) since the end of round 2: the descent
+ * diverges with the spread of a warp's points even when the tree sits in L2 (stand-in, 2 M points near the visible
+ * surfaces, kernel + sort:
+ * jittered by +-30 units 1431 Mq/s either way -> left alone by the probe; +-200 units 738 -> 1090 Mq/s; points in pixel
+ * order without jitter lose 8 % when sorted -> left alone; profiles/r04b_cpq_order.log).
  * Results never depend on the processing order (contracts N4 / N5).
  *
  * If the result array lives on another GPU (gpurt_shared_open mapping), scattered 16/32-byte stores over NVLink issued by
@@ -29,26 +35,37 @@
 
 namespace gpurt {
 
+GPURT_HD unsigned order_key30(float4 q, float lx, float ly, float lz, float ix, float iy, float iz) {
+    unsigned x = (unsigned)fminf(fmaxf((q.x - lx) * ix * 1024.0f, 0.0f), 1023.0f);
+    unsigned y = (unsigned)fminf(fmaxf((q.y - ly) * iy * 1024.0f, 0.0f), 1023.0f);
+    unsigned z = (unsigned)fminf(fmaxf((q.z - lz) * iz * 1024.0f, 0.0f), 1023.0f);
+    return (unsigned)((expand21(x) << 2) | (expand21(y) << 1) | expand21(z));
+}
 __global__ void __launch_bounds__(256) k_order_keys(const float4* __restrict__ pos, unsigned stride, uint64_t n, float lx,
                                                     float ly, float lz, float ix, float iy, float iz,
-                                                    uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
-                                                    unsigned* __restrict__ same_cell) {
+                                                    uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) return;
+    keys[i] = order_key30(__ldg(pos + (size_t)stride * i), lx, ly, lz, ix, iy, iz);
+    vals[i] = (uint32_t)i;
+}
+/* Coherence probe on a sample of the batch (every block_stride-th run of 256 elements; nothing is written but two
+ * counters): does the next element fall into the same cell of a 2^bits-per-axis grid (the top 3 * bits key bits)?
+ * counters[0] += pairs that do, counters[1] += pairs looked at. */
+__global__ void __launch_bounds__(256) k_order_probe(const float4* __restrict__ pos, unsigned stride, uint64_t n, float lx,
+                                                     float ly, float lz, float ix, float iy, float iz, unsigned block_stride,
+                                                     unsigned probe_shift, unsigned* __restrict__ counters) {
+    uint64_t i = (uint64_t)blockIdx.x * block_stride * blockDim.x + threadIdx.x;
     unsigned key = 0xffffffffu;
-    if(i < n) {
-        float4 q = __ldg(pos + (size_t)stride * i);
-        unsigned x = (unsigned)fminf(fmaxf((q.x - lx) * ix * 1024.0f, 0.0f), 1023.0f);
-        unsigned y = (unsigned)fminf(fmaxf((q.y - ly) * iy * 1024.0f, 0.0f), 1023.0f);
-        unsigned z = (unsigned)fminf(fmaxf((q.z - lz) * iz * 1024.0f, 0.0f), 1023.0f);
-        key = (unsigned)((expand21(x) << 2) | (expand21(y) << 1) | expand21(z));
-        keys[i] = key;
-        vals[i] = (uint32_t)i;
-    }
-    /* coherence probe: does the next element fall into the same cell of a 16^3 grid (top 12 key bits)? */
+    if(i < n) key = order_key30(__ldg(pos + (size_t)stride * i), lx, ly, lz, ix, iy, iz);
     unsigned next = __shfl_down_sync(0xffffffffu, key, 1);
-    bool same = (threadIdx.x & 31) != 31 && i + 1 < n && (key >> 18) == (next >> 18);
-    unsigned cnt = __popc(__ballot_sync(0xffffffffu, same));
-    if((threadIdx.x & 31) == 0 && cnt) atomicAdd(same_cell, cnt);
+    bool pair = (threadIdx.x & 31) != 31 && i + 1 < n;
+    bool same = pair && (key >> probe_shift) == (next >> probe_shift);
+    unsigned cs = __popc(__ballot_sync(0xffffffffu, same)), cp = __popc(__ballot_sync(0xffffffffu, pair));
+    if((threadIdx.x & 31) == 0 && cp) {
+        if(cs) atomicAdd(counters, cs);
+        atomicAdd(counters + 1, cp);
+    }
 }
 
 __global__ void __launch_bounds__(256) k_order_invert(const uint32_t* __restrict__ order, uint64_t n, uint32_t* __restrict__ inv) {
@@ -80,6 +97,10 @@ __global__ void __launch_bounds__(256) k_order_unpermute_u8(const uint8_t* __res
 
 constexpr uint64_t kOrderMinBatch = 1u << 20;
 constexpr size_t kOrderMinBvhBytes = 64u << 20;
+/* closest-point batches: re-ordered whenever the tree does not fit the L1s.  Measured with 2^20 uniform random points: on
+ * the stand-in (16 MB of nodes + triangles, L2-resident) 738 -> 1101 Mq/s including the sort; on cbox (1 MB: served by
+ * L1 whatever the order) 677 -> 563 Mq/s — the kernel gains nothing there and the sort is a sixth of the call. */
+constexpr size_t kOrderMinBvhBytesPoints = 4u << 20;
 
 /* bytes plan_spatial_order takes from the context's build arena for a batch of n elements (with a staging array) */
 size_t order_arena_bytes(uint64_t n, size_t result_bytes, bool staged) {
@@ -88,7 +109,7 @@ size_t order_arena_bytes(uint64_t n, size_t result_bytes, bool staged) {
 }
 
 int plan_spatial_order(gpurt_accel* A, const float4* pos, unsigned stride_vec4, uint64_t n, void* results,
-                       size_t result_bytes, OrderPlan& P, bool sliced_scatter) {
+                       size_t result_bytes, OrderPlan& P, bool sliced_scatter, bool any_bvh_size) {
     P = OrderPlan();
     P.out = results, P.n = n;
     gpurt_ctx* ctx = A->ctx;
@@ -102,8 +123,8 @@ int plan_spatial_order(gpurt_accel* A, const float4* pos, unsigned stride_vec4, 
     /* test hooks (sanitizer runs, small-scene tests of the ordered paths): GPURT_ORDER_MIN_BATCH / GPURT_ORDER_MIN_BVH_BYTES */
     const char *eb = getenv("GPURT_ORDER_MIN_BATCH"), *ev = getenv("GPURT_ORDER_MIN_BVH_BYTES");
     const uint64_t min_batch = eb ? (uint64_t)atoll(eb) : kOrderMinBatch;
-    const size_t min_bvh = ev ? (size_t)atoll(ev) : kOrderMinBvhBytes;
-    if(!allow || n < min_batch || n >= (1ull << 30) || bvh_bytes <= min_bvh) return GPURT_OK;
+    const size_t min_bvh = ev ? (size_t)atoll(ev) : (any_bvh_size ? kOrderMinBvhBytesPoints : kOrderMinBvhBytes);
+    if(!allow || n < min_batch || n >= (1ull << 30) || bvh_bytes <= min_bvh || !A->n_nodes) return GPURT_OK;
     /* scratch in the build arena (no build runs concurrently on this stream): keys | keys_tmp | vals | vals_tmp | counter | staging */
     const size_t kb = ((size_t)n * 8 + 255) & ~(size_t)255, vb = ((size_t)n * 4 + 255) & ~(size_t)255;
     cudaPointerAttributes pa;
@@ -122,13 +143,19 @@ int plan_spatial_order(gpurt_accel* A, const float4* pos, unsigned stride_vec4, 
     const float* sb = A->scene_box;
     float inv[3];
     for(int k = 0; k < 3; k++) inv[k] = sb[3 + k] > sb[k] ? 1.0f / (sb[3 + k] - sb[k]) : 0.0f;
-    GPURT_CUDA(cudaMemsetAsync(counter, 0, 4, st));
-    k_order_keys<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(pos, stride_vec4, n, sb[0], sb[1], sb[2], inv[0], inv[1], inv[2],
-                                                               keys, vals, counter);
-    unsigned same = 0;
-    GPURT_CUDA(cudaMemcpyAsync(&same, counter, 4, cudaMemcpyDeviceToHost, st));
+    /* the probe reads 1 / 16 of the batch (every 16th run of 256 elements) and costs a few microseconds plus one 8-byte
+     * read-back; only batches it finds incoherent pay for keys and sort */
+    const char* epb = getenv("GPURT_ORDER_PROBE_BITS"); /* experiment hook: bits per axis of the probe grid */
+    const unsigned probe_bits = epb ? (unsigned)std::min(10, std::max(1, atoi(epb))) : (bvh_bytes > kOrderMinBvhBytes ? 4u : 5u);
+    const unsigned nb = (unsigned)((n + 255) / 256), probe_stride = 16;
+    GPURT_CUDA(cudaMemsetAsync(counter, 0, 8, st));
+    k_order_probe<<<(nb + probe_stride - 1) / probe_stride, 256, 0, st>>>(pos, stride_vec4, n, sb[0], sb[1], sb[2], inv[0], inv[1], inv[2],
+                                                                          probe_stride, 30u - 3u * probe_bits, counter);
+    unsigned same[2] = {0, 0};
+    GPURT_CUDA(cudaMemcpyAsync(same, counter, 8, cudaMemcpyDeviceToHost, st));
     GPURT_CUDA(cudaStreamSynchronize(st));
-    if((double)same >= 0.5 * (double)n) return GPURT_OK; /* already coherent */
+    if((double)same[0] >= 0.5 * (double)same[1]) return GPURT_OK; /* already coherent */
+    k_order_keys<<<nb, 256, 0, st>>>(pos, stride_vec4, n, sb[0], sb[1], sb[2], inv[0], inv[1], inv[2], keys, vals);
     rc = radix_sort_u64(st, keys, vals, keys_tmp, vals_tmp, n, 4, ctx->scratch, ctx->sm_count);
     if(rc) return rc;
     P.order = vals; /* 4 passes: the result is back in the primary buffers */

@@ -218,6 +218,38 @@ def test_shared_result_buffer_single_process(gpurt, orc, ctx):
     buf.close(), accel.close(), scene.close()
 
 
+def test_large_incoherent_point_batch_on_a_small_scene_is_ordered_and_unchanged(gpurt, orc, ctx):
+    """closest-point batches of >= 2^20 points are processed in Morton order when a sampled probe finds them incoherent —
+    on every scene above 4 MB since round 2 (order.cu; it used to take a BVH > 64 MB); the results are those of the plain path (the same points in calls
+    below the batch threshold) and of the oracle, bit for bit, for device and host arrays; a coherent batch is left alone"""
+    import torch
+    scene = gpurt.Scene(ctx).make_sponza_standin()       # 16 MB of nodes + triangles: above the 4 MB gate, far below L2
+    accel = gpurt.Accel(scene)
+    ob = orc.Bvh(world_tris(orc, scene), sah=True)
+    n = (1 << 20) + 777
+    q = orc.gen_random_points(n, 77, ob.scene_box())
+    dq = torch.from_numpy(q).cuda()
+    whole = accel.closest_points(dq).cpu().numpy()
+    parts = np.concatenate([accel.closest_points(dq[a:a + 300_000].contiguous()).cpu().numpy() for a in range(0, n, 300_000)])
+    assert (whole.view(np.uint32) == parts.view(np.uint32)).all()
+    host = accel.closest_points(q)                       # numpy in / out: the staged host pipeline answers in chunks
+    assert (np.ascontiguousarray(host).view(np.uint32).reshape(-1) == whole.view(np.uint32).reshape(-1)).all()
+    sub = np.arange(0, n, 97)
+    ref = ob.closest_point(q[sub])
+    got = whole.view(gpurt.CPQ_DT).reshape(-1)[sub]
+    assert same_bits(got["dist"], ref["dist"]) and (got["prim"] == ref["gid"]).all()
+    # a coherent batch (points along a scan of the floor): same answers as in small calls, too
+    box = ob.scene_box()
+    g = np.stack(np.meshgrid(np.linspace(box[0], box[3], 1100), np.linspace(box[2], box[5], 1000), indexing="ij"), -1).reshape(-1, 2).astype(np.float32)
+    qc = np.zeros((g.shape[0], 4), np.float32)
+    qc[:, 0], qc[:, 2], qc[:, 1], qc[:, 3] = g[:, 0], g[:, 1], 0.5 * (box[1] + box[4]), np.inf
+    dqc = torch.from_numpy(qc).cuda()
+    a = accel.closest_points(dqc).cpu().numpy()
+    b = np.concatenate([accel.closest_points(dqc[k:k + 250_000].contiguous()).cpu().numpy() for k in range(0, qc.shape[0], 250_000)])
+    assert (a.view(np.uint32) == b.view(np.uint32)).all()
+    accel.close(), scene.close()
+
+
 def test_p2p_result_placement_two_gpus(gpurt, built):
     """config 4 on two ranks with the kernels storing into rank 0's buffer over NVLink; rank 0 checks
     the half written by rank 1 against the oracle (needs 2 GPUs)"""

@@ -251,7 +251,7 @@ static void preload(const void* f) {
     (void)cudaFuncGetAttributes(&a, f);
 }
 void preload_order_kernels() {
-    preload((const void*)k_order_keys), preload((const void*)k_order_invert), preload((const void*)k_order_unpermute<1>);
+    preload((const void*)k_order_probe), preload((const void*)k_order_keys), preload((const void*)k_order_invert), preload((const void*)k_order_unpermute<1>);
     preload((const void*)k_order_unpermute<2>), preload((const void*)k_order_scatter<1>), preload((const void*)k_order_scatter<2>);
     preload((const void*)k_order_unpermute_u8);
     preload_sort_kernels();

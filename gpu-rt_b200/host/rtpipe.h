@@ -134,6 +134,8 @@ public:
         check(gpurt_pipe_read_image(h, img.data(), GPURT_MEM_HOST));
         return img;
     }
+    void read_image_async(float* out_pinned) { check(gpurt_pipe_read_image_async(h, out_pinned)); }
+    void read_image_wait() { check(gpurt_pipe_read_image_wait(h)); }
     /* EffectPipe::tonemap (src/vk/effect.cpp:32-61) + save_rt's framebuffer read (gpurt.cpp:258-262) */
     std::vector<uint8_t> tonemap(int op = 1, float exposure = 1.0f, float gamma = 2.2f) {
         std::vector<uint8_t> out((size_t)w_ * h_ * 4);

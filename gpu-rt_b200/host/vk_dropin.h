@@ -367,6 +367,9 @@ struct RTPipe {
         dropin_check(gpurt_pipe_read_image(pipe, img.data(), GPURT_MEM_HOST));
         return img;
     }
+    /* the same copy queued behind the frames traced so far; it overlaps the following trace() calls (page-locked `out`) */
+    void read_image_async(float* out) const { dropin_check(gpurt_pipe_read_image_async(pipe, out)); }
+    void read_image_wait() const { dropin_check(gpurt_pipe_read_image_wait(pipe)); }
     const float* device_image() const {
         void* p = nullptr;
         dropin_check(gpurt_pipe_device_image(pipe, &p));

@@ -861,7 +861,9 @@ def main():
     d_cp = accel.closest_points(d_q)
     cpq_ms = median_ms(lambda: accel.closest_points(d_q, d_cp))
     stq = accel.closest_points_stats(d_q)
-    roof_cpq = roofline_obj("k_closest_points<64,false>", n_p, cpq_ms, stq.nodes_visited / stq.rays, stq.tris_tested / stq.rays,
+    # the timed span is the whole call: probe + Morton keys + 4 sort passes + k_closest_points<64,true> through the sorted index
+    # when the probe finds the batch incoherent (these queries: it does), k_closest_points<64,false> alone otherwise
+    roof_cpq = roofline_obj("k_closest_points<64,ordered> incl. probe / keys / sort of the call", n_p, cpq_ms, stq.nodes_visited / stq.rays, stq.tris_tested / stq.rays,
                             CPQ_BYTES_STREAM, peak, peak_src, ncu.get("cpq"))
     accel.trace_closest(d_rays, d_hits)
 

@@ -14,8 +14,9 @@
  * Closest-point batches are re-ordered on every scene larger than the L1s (4 MB) since the end of round 2: the descent
  * diverges with the spread of a warp's points even when the tree sits in L2 (stand-in, 2 M points near the visible
  * surfaces, kernel + sort:
- * jittered by +-30 units 1431 Mq/s either way -> left alone by the probe; +-200 units 738 -> 1090 Mq/s; points in pixel
- * order without jitter lose 8 % when sorted -> left alone; profiles/r04b_cpq_order.log).
+ * jittered by +-30 units 1431 -> 1453 Mq/s: the probe orders them and the sort takes back what the kernel gains (1.41 ->
+ * 1.19 ms); +-200 units 738 -> 1090 Mq/s; points in pixel order without jitter lose 8 % when sorted -> left alone by the
+ * probe; profiles/r04b_cpq_order.log, r04c_cpq_order.log).
  * Results never depend on the processing order (contracts N4 / N5).
  *
  * If the result array lives on another GPU (gpurt_shared_open mapping), scattered 16/32-byte stores over NVLink issued by

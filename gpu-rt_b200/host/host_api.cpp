@@ -4,6 +4,8 @@
  */
 #include <cstdio>
 #include <cstring>
+#include <exception>
+#include <string>
 #include <vector>
 
 #include "camera.h"
@@ -16,7 +18,7 @@ void set_error(const std::string& msg) { g_error = msg; }
 
 using namespace gpurt;
 
-bool gpurt_scene::pack() {
+bool gpurt_scene::pack() try {
     if(!dirty) return true;
     PackedScene& P = packed;
     P = PackedScene();
@@ -49,6 +51,11 @@ bool gpurt_scene::pack() {
     version++;
     geom_version++;
     return true;
+} catch(const std::exception& e) { /* packing a scene copies it: out of host memory is an error code, not a terminate */
+    packed = PackedScene();
+    dirty = true;
+    set_error(std::string("scene could not be packed: ") + e.what());
+    return false;
 }
 
 static void material_from_abi(Material& dst, const GpurtMaterial* m) {
@@ -81,10 +88,17 @@ int gpurt_scene_load_gltf(gpurt_scene* s, const char* path, float scale) {
     std::string err;
     s->dirty = true;
     s->scene.scale = scale;
-    if(!s->scene.load(path, err)) return set_error(err), GPURT_E_IO;
-    if(!err.empty()) set_error(err); /* warnings */
-    s->label = path;
-    return s->pack() ? GPURT_OK : GPURT_E_INVALID;
+    /* no exception leaves the C ABI: a file that asks for more memory than there is (or than a vector may hold) is an
+     * unreadable file, not a reason to terminate the caller */
+    try {
+        if(!s->scene.load(path, err)) return set_error(err), GPURT_E_IO;
+        if(!err.empty()) set_error(err); /* warnings */
+        s->label = path;
+        return s->pack() ? GPURT_OK : GPURT_E_INVALID;
+    } catch(const std::exception& e) {
+        s->scene.clear();
+        return set_error(std::string("scene file rejected: ") + e.what()), GPURT_E_IO;
+    }
 }
 int gpurt_scene_make_sponza_standin(gpurt_scene* s) {
     if(!s) return set_error("NULL argument"), GPURT_E_INVALID;
@@ -99,6 +113,7 @@ int gpurt_scene_add_object(gpurt_scene* s, const void* verts48, uint32_t nv, con
     if(!s || (!verts48 && nv) || (!idx && ni) || !model) return set_error("NULL argument"), GPURT_E_INVALID;
     for(uint32_t i = 0; i < ni; i++)
         if(idx[i] >= nv) return set_error("index out of range"), GPURT_E_INVALID;
+    try {
     Object o;
     o.id = s->scene.reserve_id();
     std::vector<Vertex> v(nv);
@@ -124,6 +139,9 @@ int gpurt_scene_add_object(gpurt_scene* s, const void* verts48, uint32_t nv, con
         *out = found;
     }
     return GPURT_OK;
+    } catch(const std::exception& e) {
+        return set_error(std::string("object not added: ") + e.what()), GPURT_E_INVALID;
+    }
 }
 int gpurt_scene_get_texture(const gpurt_scene* s, uint32_t tex, uint32_t* w, uint32_t* h, uint8_t* out) {
     if(!s || tex >= s->scene.textures.size()) return set_error("texture index out of range"), GPURT_E_INVALID;
@@ -174,8 +192,12 @@ int gpurt_scene_add_texture(gpurt_scene* s, const uint8_t* rgba, uint32_t w, uin
     if(!s || !rgba || !w || !h) return set_error("bad texture"), GPURT_E_INVALID;
     Texture t;
     t.w = w, t.h = h;
-    t.rgba.assign(rgba, rgba + (size_t)w * h * 4);
-    s->scene.textures.push_back(std::move(t));
+    try {
+        t.rgba.assign(rgba, rgba + (size_t)w * h * 4);
+        s->scene.textures.push_back(std::move(t));
+    } catch(const std::exception& e) {
+        return set_error(std::string("texture not added: ") + e.what()), GPURT_E_INVALID;
+    }
     s->dirty = true;
     if(out) *out = (int32_t)s->scene.textures.size() - 1;
     return GPURT_OK;
@@ -217,7 +239,7 @@ int gpurt_scene_object_sizes(const gpurt_scene* cs, uint32_t obj, uint32_t* nv, 
     gpurt_scene* s = const_cast<gpurt_scene*>(cs);
     if(!s) return set_error("NULL argument"), GPURT_E_INVALID;
     if(!s->pack()) return GPURT_E_INVALID;
-    if(obj + 1 >= s->packed.tri_off.size()) return set_error("object index out of range"), GPURT_E_INVALID;
+    if((size_t)obj + 1 >= s->packed.tri_off.size()) return set_error("object index out of range"), GPURT_E_INVALID;
     if(nv) *nv = s->packed.vert_off[obj + 1] - s->packed.vert_off[obj];
     if(ni) *ni = 3 * (s->packed.tri_off[obj + 1] - s->packed.tri_off[obj]);
     return GPURT_OK;
@@ -226,7 +248,7 @@ int gpurt_scene_get_object(const gpurt_scene* cs, uint32_t obj, void* verts, uin
     gpurt_scene* s = const_cast<gpurt_scene*>(cs);
     if(!s) return set_error("NULL argument"), GPURT_E_INVALID;
     if(!s->pack()) return GPURT_E_INVALID;
-    if(obj + 1 >= s->packed.tri_off.size()) return set_error("object index out of range"), GPURT_E_INVALID;
+    if((size_t)obj + 1 >= s->packed.tri_off.size()) return set_error("object index out of range"), GPURT_E_INVALID;
     const PackedScene& P = s->packed;
     if(verts)
         std::memcpy(verts, P.verts.data() + P.vert_off[obj],

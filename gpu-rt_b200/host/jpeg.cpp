@@ -120,23 +120,28 @@ inline int fix(float c) { return (int)(c * 4096 + 0.5); } /* float constant, sca
 struct Pass {
     int x0, x1, x2, x3, t0, t1, t2, t3;
 };
+/* 32-bit arithmetic that wraps: a valid stream never overflows here and decodes as before; a corrupt one (coefficients far
+ * outside the 11-bit range) gets wrapped garbage pixels instead of undefined behaviour */
+inline int wadd(int a, int b) { return (int)((unsigned)a + (unsigned)b); }
+inline int wsub(int a, int b) { return (int)((unsigned)a - (unsigned)b); }
+inline int wmul(int a, int b) { return (int)((unsigned)a * (unsigned)b); }
 inline Pass idct8(int s0, int s1, int s2, int s3, int s4, int s5, int s6, int s7) {
     static const int c0541 = fix(0.5411961f), c1847 = fix(-1.847759065f), c0765 = fix(0.765366865f),
                      c1175 = fix(1.175875602f), c0298 = fix(0.298631336f), c2053 = fix(2.053119869f),
                      c3072 = fix(3.072711026f), c1501 = fix(1.501321110f), c0899 = fix(-0.899976223f),
                      c2562 = fix(-2.562915447f), c1961 = fix(-1.961570560f), c0390 = fix(-0.390180644f);
     Pass r;
-    int p1 = (s2 + s6) * c0541;
-    int e2 = p1 + s6 * c1847, e3 = p1 + s2 * c0765;
-    int e0 = (s0 + s4) * 4096, e1 = (s0 - s4) * 4096;
-    r.x0 = e0 + e3, r.x3 = e0 - e3, r.x1 = e1 + e2, r.x2 = e1 - e2;
+    int p1 = wmul(wadd(s2, s6), c0541);
+    int e2 = wadd(p1, wmul(s6, c1847)), e3 = wadd(p1, wmul(s2, c0765));
+    int e0 = wmul(wadd(s0, s4), 4096), e1 = wmul(wsub(s0, s4), 4096);
+    r.x0 = wadd(e0, e3), r.x3 = wsub(e0, e3), r.x1 = wadd(e1, e2), r.x2 = wsub(e1, e2);
     int o0 = s7, o1 = s5, o2 = s3, o3 = s1;
-    int q3 = o0 + o2, q4 = o1 + o3, q1 = o0 + o3, q2 = o1 + o2;
-    int q5 = (q3 + q4) * c1175;
-    o0 *= c0298, o1 *= c2053, o2 *= c3072, o3 *= c1501;
-    q1 = q5 + q1 * c0899, q2 = q5 + q2 * c2562;
-    q3 *= c1961, q4 *= c0390;
-    r.t3 = o3 + q1 + q4, r.t2 = o2 + q2 + q3, r.t1 = o1 + q2 + q4, r.t0 = o0 + q1 + q3;
+    int q3 = wadd(o0, o2), q4 = wadd(o1, o3), q1 = wadd(o0, o3), q2 = wadd(o1, o2);
+    int q5 = wmul(wadd(q3, q4), c1175);
+    o0 = wmul(o0, c0298), o1 = wmul(o1, c2053), o2 = wmul(o2, c3072), o3 = wmul(o3, c1501);
+    q1 = wadd(q5, wmul(q1, c0899)), q2 = wadd(q5, wmul(q2, c2562));
+    q3 = wmul(q3, c1961), q4 = wmul(q4, c0390);
+    r.t3 = wadd(wadd(o3, q1), q4), r.t2 = wadd(wadd(o2, q2), q3), r.t1 = wadd(wadd(o1, q2), q4), r.t0 = wadd(wadd(o0, q1), q3);
     return r;
 }
 
@@ -150,22 +155,22 @@ void idct_block(uint8_t* out, int stride, const short d[64]) {
             continue;
         }
         Pass p = idct8(s[0], s[8], s[16], s[24], s[32], s[40], s[48], s[56]);
-        p.x0 += 512, p.x1 += 512, p.x2 += 512, p.x3 += 512;
-        v[0 * 8 + c] = (p.x0 + p.t3) >> 10, v[7 * 8 + c] = (p.x0 - p.t3) >> 10;
-        v[1 * 8 + c] = (p.x1 + p.t2) >> 10, v[6 * 8 + c] = (p.x1 - p.t2) >> 10;
-        v[2 * 8 + c] = (p.x2 + p.t1) >> 10, v[5 * 8 + c] = (p.x2 - p.t1) >> 10;
-        v[3 * 8 + c] = (p.x3 + p.t0) >> 10, v[4 * 8 + c] = (p.x3 - p.t0) >> 10;
+        p.x0 = wadd(p.x0, 512), p.x1 = wadd(p.x1, 512), p.x2 = wadd(p.x2, 512), p.x3 = wadd(p.x3, 512);
+        v[0 * 8 + c] = wadd(p.x0, p.t3) >> 10, v[7 * 8 + c] = wsub(p.x0, p.t3) >> 10;
+        v[1 * 8 + c] = wadd(p.x1, p.t2) >> 10, v[6 * 8 + c] = wsub(p.x1, p.t2) >> 10;
+        v[2 * 8 + c] = wadd(p.x2, p.t1) >> 10, v[5 * 8 + c] = wsub(p.x2, p.t1) >> 10;
+        v[3 * 8 + c] = wadd(p.x3, p.t0) >> 10, v[4 * 8 + c] = wsub(p.x3, p.t0) >> 10;
     }
     for(int r = 0; r < 8; r++) { /* rows: remove 2^17, round, level shift by 128 */
         const int* s = v + r * 8;
         uint8_t* o = out + (size_t)r * stride;
         Pass p = idct8(s[0], s[1], s[2], s[3], s[4], s[5], s[6], s[7]);
         const int bias = 65536 + (128 << 17);
-        p.x0 += bias, p.x1 += bias, p.x2 += bias, p.x3 += bias;
-        o[0] = clamp8((p.x0 + p.t3) >> 17), o[7] = clamp8((p.x0 - p.t3) >> 17);
-        o[1] = clamp8((p.x1 + p.t2) >> 17), o[6] = clamp8((p.x1 - p.t2) >> 17);
-        o[2] = clamp8((p.x2 + p.t1) >> 17), o[5] = clamp8((p.x2 - p.t1) >> 17);
-        o[3] = clamp8((p.x3 + p.t0) >> 17), o[4] = clamp8((p.x3 - p.t0) >> 17);
+        p.x0 = wadd(p.x0, bias), p.x1 = wadd(p.x1, bias), p.x2 = wadd(p.x2, bias), p.x3 = wadd(p.x3, bias);
+        o[0] = clamp8(wadd(p.x0, p.t3) >> 17), o[7] = clamp8(wsub(p.x0, p.t3) >> 17);
+        o[1] = clamp8(wadd(p.x1, p.t2) >> 17), o[6] = clamp8(wsub(p.x1, p.t2) >> 17);
+        o[2] = clamp8(wadd(p.x2, p.t1) >> 17), o[5] = clamp8(wsub(p.x2, p.t1) >> 17);
+        o[3] = clamp8(wadd(p.x3, p.t0) >> 17), o[4] = clamp8(wsub(p.x3, p.t0) >> 17);
     }
 }
 

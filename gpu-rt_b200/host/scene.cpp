@@ -230,6 +230,7 @@ bool decode_image(const std::vector<uint8_t>& f, Texture& out, std::string& err)
         if(o + 12 + len > f.size()) break;
         const uint8_t* d = &f[o + 8];
         if(tag == "IHDR") {
+            if(len < 13) break;
             w = be32(o + 8), h = be32(o + 12);
             depth = d[8], ctype = d[9], interlace = d[12];
         } else if(tag == "IDAT") idat.insert(idat.end(), d, d + len);
@@ -248,6 +249,12 @@ bool decode_image(const std::vector<uint8_t>& f, Texture& out, std::string& err)
         return false;
     }
     size_t row = (size_t)w * ch;
+    /* untrusted dimensions: deflate expands by at most 1032 : 1, so a header that asks for more than the IDAT bytes can
+     * inflate to is wrong before anything is allocated (row, h < 2^34 and 2^32: the product fits 64 bits) */
+    if((row + 1) * h > (idat.size() + 16) * 1032) {
+        err = "PNG inflate failed";
+        return false;
+    }
     std::vector<uint8_t> raw((row + 1) * h);
     uLongf rawlen = (uLongf)raw.size();
     if(uncompress(raw.data(), &rawlen, idat.data(), (uLong)idat.size()) != Z_OK || rawlen != raw.size()) {

@@ -321,6 +321,53 @@ def test_corrupt_images_fall_back_to_a_placeholder_with_a_warning(gpurt, tmp_pat
             assert t.shape in ((1, 1, 4), (23, 37, 4)), f
 
 
+def test_png_header_that_promises_more_than_its_data_is_refused_before_allocating(gpurt, tmp_path):
+    """a PNG whose IHDR names 60000 x 60000 pixels over a few hundred IDAT bytes (found by tools/fuzz_loader.sh under
+    AddressSanitizer: a 24 GB allocation) decodes to the placeholder; a short IHDR chunk is not read past its end; an object
+    index of 2^32 - 1 is out of range, not index 0 after a wrap"""
+    import struct
+    import zlib
+    good = open(os.path.join(ROOT, "tests", "data", "synth", "p_rgba.png"), "rb").read()
+
+    def chunks(b):
+        o = 8
+        while o + 12 <= len(b):
+            n = struct.unpack(">I", b[o:o + 4])[0]
+            yield b[o + 4:o + 8], b[o + 8:o + 8 + n]
+            o += 12 + n
+
+    def png(parts):
+        out = good[:8]
+        for tag, data in parts:
+            out += struct.pack(">I", len(data)) + tag + data + struct.pack(">I", zlib.crc32(tag + data))
+        return out
+    parts = list(chunks(good))
+    huge = [(t, struct.pack(">II", 60000, 60000) + d[8:]) if t == b"IHDR" else (t, d) for t, d in parts]
+    short = [(t, d[:6]) if t == b"IHDR" else (t, d) for t, d in parts]
+    files = {"good.png": good, "huge.png": png(huge), "short.png": png(short)[:8 + 12 + 6]}
+    for f, b in files.items():
+        (tmp_path / f).write_bytes(b)
+    names = sorted(files)
+    pos = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32)
+    blob = pos.tobytes() + np.array([0, 1, 2], np.uint32).tobytes()
+    g = {"asset": {"version": "2.0"}, "scene": 0, "scenes": [{"nodes": [0]}], "nodes": [{"mesh": 0}],
+         "meshes": [{"primitives": [{"attributes": {"POSITION": 0}, "indices": 1}]}],
+         "textures": [{"source": i} for i in range(len(names))], "images": [{"uri": f} for f in names],
+         "buffers": [{"byteLength": len(blob), "uri": "data:application/octet-stream;base64," + base64.b64encode(blob).decode()}],
+         "bufferViews": [{"buffer": 0, "byteOffset": 0, "byteLength": 36}, {"buffer": 0, "byteOffset": 36, "byteLength": 12}],
+         "accessors": [{"bufferView": 0, "componentType": 5126, "count": 3, "type": "VEC3"},
+                       {"bufferView": 1, "componentType": 5125, "count": 3, "type": "SCALAR"}]}
+    (tmp_path / "t.gltf").write_text(json.dumps(g))
+    s = gpurt.Scene(None).load(str(tmp_path / "t.gltf"))
+    shapes = {f: s.texture(i).shape for i, f in enumerate(names)}
+    assert shapes["huge.png"] == (1, 1, 4) and shapes["short.png"] == (1, 1, 4) and shapes["good.png"] != (1, 1, 4), shapes
+    import ctypes as C
+    nv, ni = C.c_uint32(), C.c_uint32()
+    assert gpurt.lib.gpurt_scene_object_sizes(s.h, 0, C.byref(nv), C.byref(ni)) == 0 and (nv.value, ni.value) == (3, 3)
+    assert gpurt.lib.gpurt_scene_object_sizes(s.h, 0xFFFFFFFF, C.byref(nv), C.byref(ni)) == -1
+    assert gpurt.lib.gpurt_scene_get_object(s.h, 0xFFFFFFFF, None, None) == -1
+
+
 def test_header_is_plain_c_and_links(gpurt, tmp_path):
     """include/gpurt.h compiles as C99 with -pedantic, and a C program linked against libgpurt.so can call the
     host-only entry points (what a cgo / JNI / ctypes binding of the reference's maintainers would do)"""

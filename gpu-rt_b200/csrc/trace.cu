@@ -18,9 +18,19 @@
 
 namespace gpurt {
 
+/* experiment hooks (tools/build_variant.sh): threads per CTA and minimum CTAs per SM of k_trace_closest */
+#ifndef GPURT_TRACE_BLOCK
+#define GPURT_TRACE_BLOCK 128
+#endif
+#ifdef GPURT_TRACE_MINB
+#define GPURT_TRACE_BOUNDS __launch_bounds__(GPURT_TRACE_BLOCK, GPURT_TRACE_MINB)
+#else
+#define GPURT_TRACE_BOUNDS __launch_bounds__(GPURT_TRACE_BLOCK)
+#endif
+
 /* ORDERED: the batch is processed through a sorted index (order.cu); the plain instantiation is the headline kernel */
 template <bool STATS, bool ORDERED>
-__global__ void __launch_bounds__(128) k_trace_closest(const float4* __restrict__ nodes,
+__global__ void GPURT_TRACE_BOUNDS k_trace_closest(const float4* __restrict__ nodes,
                                                        const float4* __restrict__ tris,
                                                        const float4* __restrict__ rays, uint64_t n,
                                                        float4* __restrict__ hits, unsigned n_nodes,
@@ -135,7 +145,7 @@ int launch_trace_closest(gpurt_accel* A, const float4* rays, uint64_t n, float4*
         uint64_t off = 0;
         for(uint64_t e : ends) {
             const uint64_t m = e - off;
-            k_trace_closest<false, true><<<blocks_for(m, 128), 128, 0, A->ctx->stream>>>(
+            k_trace_closest<false, true><<<blocks_for(m, GPURT_TRACE_BLOCK), GPURT_TRACE_BLOCK, 0, A->ctx->stream>>>(
                 (const float4*)A->nodes, A->tri_wide, rays, m, (float4*)P.out + off, A->n_nodes, nullptr, P.order + off, 1);
             GPURT_CUDA(cudaGetLastError());
             if((rc = scatter_slice_async(A, P, off, m, hits, 16))) return rc;
@@ -144,10 +154,10 @@ int launch_trace_closest(gpurt_accel* A, const float4* rays, uint64_t n, float4*
         return scatter_join(A, P);
     }
     if(P.order)
-        k_trace_closest<false, true><<<blocks_for(n, 128), 128, 0, A->ctx->stream>>>(
+        k_trace_closest<false, true><<<blocks_for(n, GPURT_TRACE_BLOCK), GPURT_TRACE_BLOCK, 0, A->ctx->stream>>>(
             (const float4*)A->nodes, A->tri_wide, rays, n, (float4*)P.out, A->n_nodes, nullptr, P.order, P.unperm ? 1 : 0);
     else
-        k_trace_closest<false, false><<<blocks_for(n, 128), 128, 0, A->ctx->stream>>>(
+        k_trace_closest<false, false><<<blocks_for(n, GPURT_TRACE_BLOCK), GPURT_TRACE_BLOCK, 0, A->ctx->stream>>>(
             (const float4*)A->nodes, A->tri_wide, rays, n, hits, A->n_nodes, nullptr, nullptr, 0);
     GPURT_CUDA(cudaGetLastError());
     return finish_spatial_order(A, P, n, hits, 16);
@@ -155,7 +165,7 @@ int launch_trace_closest(gpurt_accel* A, const float4* rays, uint64_t n, float4*
 int launch_trace_closest_stats(gpurt_accel* A, const float4* rays, uint64_t n, float4* hits,
                                unsigned long long* d_counters) {
     if(!n) return GPURT_OK;
-    k_trace_closest<true, false><<<blocks_for(n, 128), 128, 0, A->ctx->stream>>>(
+    k_trace_closest<true, false><<<blocks_for(n, GPURT_TRACE_BLOCK), GPURT_TRACE_BLOCK, 0, A->ctx->stream>>>(
         (const float4*)A->nodes, A->tri_wide, rays, n, hits, A->n_nodes, d_counters, nullptr, 0);
     GPURT_CUDA(cudaGetLastError());
     return GPURT_OK;

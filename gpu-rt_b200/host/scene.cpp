@@ -6,6 +6,7 @@
  * only node.matrix honoured (TRS ignored), pose recovered through
  * Mat4::decompose -> Euler -> Pose::transform, textures as RGBA8.
  */
+#include <sys/stat.h>
 #include "scene.h"
 
 #include <cstdio>
@@ -81,6 +82,11 @@ namespace {
 bool read_file(const std::string& path, std::vector<uint8_t>& out) {
     FILE* f = fopen(path.c_str(), "rb");
     if(!f) return false;
+    struct stat st; /* a uri may name a directory (fopen succeeds, ftell answers LONG_MAX) or a device */
+    if(fstat(fileno(f), &st) != 0 || !S_ISREG(st.st_mode)) {
+        fclose(f);
+        return false;
+    }
     fseek(f, 0, SEEK_END);
     long n = ftell(f);
     fseek(f, 0, SEEK_SET);

@@ -47,6 +47,13 @@ for integ in (0, 2, 3):
     pipe.reset_frame()
     pipe.render_frame(gpurt.pipe_params(integrator=integ, samples_per_frame=1, max_depth=3), gpurt.camera(0, 96, 54), 96, 54)
     pipe.read_image()
+# asynchronous read-back (copy stream + event) overlapping the next frames
+host_img = torch.empty((54, 96, 4), dtype=torch.float32).pin_memory()
+for _ in range(3):
+    pipe.render_frame(gpurt.pipe_params(integrator=1, samples_per_frame=1, max_depth=3), gpurt.camera(0, 96, 54), 96, 54)
+    pipe.read_image_async(host_img.numpy())
+pipe.read_image_wait()
+assert np.array_equal(host_img.numpy(), pipe.read_image())
 pipe.close()
 # round 2, late: ReSTIR extensions, the frame sharded over two pipes with the history exchange, the gather inbox and the sliced
 # placement of ordered batches (thresholds lowered by the test hooks so that a 6000-triangle scene takes the ordered paths)

@@ -6,7 +6,7 @@
  * descents the lanes also shrink their radius at different paces (9 of 32 lanes busy).  Measured on the
  * 10 M-triangle config-4 soup (tools/cpq_sort_probe.py, tools/ray_sort_probe.py): uniform random points
  * 807 -> 1355 Mq/s and uniform random rays 676 -> 970 Mrays/s when processed in Morton order of the position.
- * So such batches get a 30-bit Morton key per element, a 4-pass radix sort of (key, index) pairs, and the
+ * So such batches get a 30-bit Morton key per element, a 3- or 4-pass radix sort of (key, index) pairs, and the
  * traversal kernel reads its element and writes its result through the sorted index.  Skipped when the batch is small
  * (< 2^20), when a probe on 1 / 16 of the batch finds that neighbouring elements already share a cell of a 16^3 grid
  * (32^3 on small scenes; e.g. rays and points generated per pixel), and — for rays — when the scene is small (BVH < 64 MB:
@@ -44,10 +44,11 @@ GPURT_HD unsigned order_key30(float4 q, float lx, float ly, float lz, float ix, 
 }
 __global__ void __launch_bounds__(256) k_order_keys(const float4* __restrict__ pos, unsigned stride, uint64_t n, float lx,
                                                     float ly, float lz, float ix, float iy, float iz,
-                                                    uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+                                                    unsigned key_shift, uint64_t* __restrict__ keys,
+                                                    uint32_t* __restrict__ vals) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if(i >= n) return;
-    keys[i] = order_key30(__ldg(pos + (size_t)stride * i), lx, ly, lz, ix, iy, iz);
+    keys[i] = order_key30(__ldg(pos + (size_t)stride * i), lx, ly, lz, ix, iy, iz) >> key_shift;
     vals[i] = (uint32_t)i;
 }
 /* Coherence probe on a sample of the batch (every block_stride-th run of 256 elements; nothing is written but two
@@ -97,6 +98,11 @@ __global__ void __launch_bounds__(256) k_order_unpermute_u8(const uint8_t* __res
 }
 
 constexpr uint64_t kOrderMinBatch = 1u << 20;
+/* 8-bit radix passes over the 30-bit Morton key: the top 24 bits (2^24 cells) order a batch of up to 2^24 elements as well as
+ * all 30 do and save a pass — stand-in, 2 M points: 1428 -> 1485 Mq/s; config 4 in calls of 12.5 M: 1378 -> 1392; one call of
+ * 100 M points (6 per cell) loses 5 % with 3 passes and 35 % with 2, so dense batches keep 4
+ * (tools/order_passes_probe.py, profiles/r05c_order_passes.log) */
+constexpr uint64_t kOrderCoarseBatch = 1u << 24;
 constexpr size_t kOrderMinBvhBytes = 64u << 20;
 /* closest-point batches: re-ordered whenever the tree does not fit the L1s.  Measured with 2^20 uniform random points: on
  * the stand-in (16 MB of nodes + triangles, L2-resident) 738 -> 1101 Mq/s including the sort; on cbox (1 MB: served by
@@ -156,10 +162,18 @@ int plan_spatial_order(gpurt_accel* A, const float4* pos, unsigned stride_vec4, 
     GPURT_CUDA(cudaMemcpyAsync(same, counter, 8, cudaMemcpyDeviceToHost, st));
     GPURT_CUDA(cudaStreamSynchronize(st));
     if((double)same[0] >= 0.5 * (double)same[1]) return GPURT_OK; /* already coherent */
-    k_order_keys<<<nb, 256, 0, st>>>(pos, stride_vec4, n, sb[0], sb[1], sb[2], inv[0], inv[1], inv[2], keys, vals);
-    rc = radix_sort_u64(st, keys, vals, keys_tmp, vals_tmp, n, 4, ctx->scratch, ctx->sm_count);
+    /* the sort looks at the top 8 * passes bits of the 30-bit key (GPURT_ORDER_PASSES, experiment hook: 2..4) */
+    const char* eps = getenv("GPURT_ORDER_PASSES");
+    const int passes = eps ? std::min(4, std::max(2, atoi(eps))) : (n <= kOrderCoarseBatch ? 3 : 4);
+    k_order_keys<<<nb, 256, 0, st>>>(pos, stride_vec4, n, sb[0], sb[1], sb[2], inv[0], inv[1], inv[2], passes >= 4 ? 0u : 30u - 8u * passes,
+                                     keys, vals);
+    rc = radix_sort_u64(st, keys, vals, keys_tmp, vals_tmp, n, passes, ctx->scratch, ctx->sm_count);
     if(rc) return rc;
-    P.order = vals; /* 4 passes: the result is back in the primary buffers */
+    if(passes & 1) { /* an odd number of passes leaves the result in the secondary buffers; the roles swap */
+        std::swap(keys, keys_tmp);
+        std::swap(vals, vals_tmp);
+    }
+    P.order = vals;
     /* opt-in (GPURT_PLACE_SLICES=<slices>): fine for one or two senders (2 GPUs, config 4: 2616 Mq/s against 2655 with the
      * results left local), but scattered 32-byte stores from 7 senders into one GPU arrive at only ~175 GB/s (8 GPUs: 6039
      * Mq/s against 8105 for caller-side chunks + coalesced copies), so the default stays "stage, then one coalesced pass" */

@@ -331,7 +331,7 @@ def roofline_obj(kernel, n, ms, nodes, tris, stream_bytes, peak, peak_src, ncu=N
 
 def ncu_facts():
     """physical-side numbers of the committed ncu captures (never measured under the profiler here), newest round first"""
-    for name in ("r04_traffic.json", "r03_traffic.json", "r02_traffic.json", "r01_traffic.json"):
+    for name in ("r05_traffic.json", "r04_traffic.json", "r03_traffic.json", "r02_traffic.json", "r01_traffic.json"):
         p = os.path.join(ROOT, "profiles", name)
         if os.path.exists(p):
             tj = json.load(open(p))

@@ -35,6 +35,8 @@ def _run(gpurt, orc, ctx, scene_name, w, h, frames, cam=None, textures=(), scene
     scene = scene or load_scene(gpurt, ctx, scene_name)
     accel = gpurt.Accel(scene)
     pipe = gpurt.RTPipe(scene, accel)
+    if not len(textures):   # a loaded scene brings its own (media/sponza through GPURT_SPONZA_GLTF)
+        textures = [scene.texture(i) for i in range(scene.counts()["textures"])]
     rs = orc.RenderScene(scene, textures)
     st = orc.FrameState(w, h)
     prm = gpurt.pipe_params(**params)
@@ -81,7 +83,7 @@ def test_mis_test_scene_mis_and_restir(gpurt, orc, ctx):
 def test_sponza_standin_config2(gpurt, orc, ctx):
     """BASELINE config 2 at reduced resolution: integrator 1, GGX, depth 2, 1 spp, env light, no RR"""
     cam = gpurt.camera(1, 320, 180, (-1000.0, 200.0, 0.0), (0.0, 200.0, 0.0), 90.0)
-    _run(gpurt, orc, ctx, "sponza_standin", 320, 180, 2, cam=cam, integrator=1, brdf=1, samples_per_frame=1,
+    _run(gpurt, orc, ctx, "sponza", 320, 180, 2, cam=cam, integrator=1, brdf=1, samples_per_frame=1,
          max_depth=2, use_rr=0, env_scale=1.0, seed=3)
 
 
@@ -98,7 +100,7 @@ def test_config2_full_size_1080p(gpurt, orc, ctx):
     """BASELINE config 2 at its full size: 1920x1080, integrator 1 (Material), GGX, depth 2, 1 spp, env light,
     no RR — image, G-buffers and ray counts of the frame against the oracle's rt.rgen restatement (rt.rgen:567-677)"""
     cam = gpurt.camera(1, 1920, 1080, (-1000.0, 200.0, 0.0), (0.0, 200.0, 0.0), 90.0)
-    _run(gpurt, orc, ctx, "sponza_standin", 1920, 1080, 2, cam=cam, integrator=1, brdf=1, samples_per_frame=1,
+    _run(gpurt, orc, ctx, "sponza", 1920, 1080, 2, cam=cam, integrator=1, brdf=1, samples_per_frame=1,
          max_depth=2, use_rr=0, env_scale=1.0, seed=3)
 
 

@@ -18,8 +18,11 @@ namespace gpurt {
                             queries 1388 -> 1430 Mq/s; 8 CTAs (58 registers) 1315, 12 CTAs (40 registers, 140 B spills) 1350
                             (tools/ab_cpq.sh, variants built side by side, interleaved x 3) */
 #endif
+#ifndef GPURT_CPQ_BLOCK
+#define GPURT_CPQ_BLOCK 128 /* threads per CTA (experiment hook, with GPURT_CPQ_MINB: tools/build_variant.sh) */
+#endif
 template <int STACK, bool ORDERED>
-__global__ void __launch_bounds__(128, GPURT_CPQ_MINB) k_closest_points(const float4* __restrict__ nodes,
+__global__ void __launch_bounds__(GPURT_CPQ_BLOCK, GPURT_CPQ_MINB) k_closest_points(const float4* __restrict__ nodes,
                                                         const float4* __restrict__ tris,
                                                         const float4* __restrict__ queries, uint64_t n,
                                                         float4* __restrict__ results, unsigned n_nodes,
@@ -86,13 +89,13 @@ int launch_closest_points(gpurt_accel* A, const float4* queries, uint64_t n, flo
     if(need > 512) return set_error("wide BVH too deep for the closest-point stack"), GPURT_E_STATE;
     /* [off, off + m) of the processing order; the whole batch unless results are scattered to another GPU slice by slice */
     auto launch = [&](uint64_t off, uint64_t m) {
-        const unsigned nb = (unsigned)((m + 127) / 128);
+        const unsigned nb = (unsigned)((m + GPURT_CPQ_BLOCK - 1) / GPURT_CPQ_BLOCK);
         float4* out = (float4*)P.out + (P.scatter ? 2 * off : 0);
         const uint32_t* order = P.order ? P.order + off : nullptr;
         const int staged = (P.unperm || P.scatter) ? 1 : 0;
 #define GPURT_CPQ_LAUNCH(S)                                                                                                  \
-    (order ? k_closest_points<S, true><<<nb, 128, 0, st>>>(nodes, A->tri_wide, queries, m, out, A->n_nodes, order, staged) \
-           : k_closest_points<S, false><<<nb, 128, 0, st>>>(nodes, A->tri_wide, queries, m, out, A->n_nodes, nullptr, 0))
+    (order ? k_closest_points<S, true><<<nb, GPURT_CPQ_BLOCK, 0, st>>>(nodes, A->tri_wide, queries, m, out, A->n_nodes, order, staged) \
+           : k_closest_points<S, false><<<nb, GPURT_CPQ_BLOCK, 0, st>>>(nodes, A->tri_wide, queries, m, out, A->n_nodes, nullptr, 0))
         if(need <= 64) GPURT_CPQ_LAUNCH(64);
         else if(need <= 128) GPURT_CPQ_LAUNCH(128);
         else if(need <= 256) GPURT_CPQ_LAUNCH(256);

@@ -28,7 +28,8 @@ struct Json {
     }
     size_t size() const { return type == Arr ? arr.size() : 0; }
     double number(double def) const { return type == Num ? num : def; }
-    int integer(int def) const { return type == Num ? (int)num : def; }
+    /* a number outside int's range (1e30, NaN) is not an index: the default, not an undefined conversion */
+    int integer(int def) const { return type == Num && num >= -2147483648.0 && num <= 2147483647.0 ? (int)num : def; }
     std::string string(const std::string& def = "") const { return type == Str ? str : def; }
 
     static bool parse(const std::string& text, Json& out, std::string& err) {
@@ -44,6 +45,9 @@ private:
     struct Parser {
         const char* cur;
         const char* end;
+        int depth = 0; /* nesting of the value being read: glTF needs about ten levels; a file of 100,000 '[' must not
+                          recurse until the stack ends */
+        static constexpr int kMaxDepth = 200;
         void ws() {
             while(cur < end && (*cur == ' ' || *cur == '\n' || *cur == '\t' || *cur == '\r')) cur++;
         }
@@ -92,6 +96,13 @@ private:
             return true;
         }
         bool value(Json& v) {
+            if(depth >= kMaxDepth) return false;
+            depth++;
+            bool ok = value_body(v);
+            depth--;
+            return ok;
+        }
+        bool value_body(Json& v) {
             ws();
             if(cur >= end) return false;
             char c = *cur;

@@ -148,6 +148,18 @@ def test_hostile_gltf_numbers_are_rejected_not_followed(gpurt, tmp_path):
     s.add_object(np.zeros((3, 12), np.float32), np.arange(3, dtype=np.uint32), None, m)
     d0 = s.descs()[0]
     assert (d0.albedo_tex, d0.metal_rough_tex) == (-1, -1) and "texture" in gpurt.last_error()
+    # nesting without end: the reader gives up at a fixed depth instead of recursing until the stack ends
+    for text in ('{"asset":{"version":"2.0"},"x":' + "[" * 200000 + "]" * 200000 + "}", '{"a":' * 100000 + "1" + "}" * 100000):
+        p = tmp_path / "deep.gltf"
+        p.write_text(text)
+        with pytest.raises(gpurt.GpurtError) as e:
+            gpurt.Scene(None).load(str(p))
+        assert e.value.code == -4
+    # an index that is no int (1e30, -1e30) reads as "absent", not through an undefined float -> int conversion
+    d = doc(materials=[{"pbrMetallicRoughness": {"baseColorTexture": {"index": 1e30}}, "normalTexture": {"index": -1e30}}])
+    d["meshes"][0]["primitives"][0]["material"] = 0
+    d0 = load(d).descs()[0]
+    assert (d0.albedo_tex, d0.normal_tex) == (-1, -1)
 
 
 def test_library_exports_every_declared_symbol(gpurt):

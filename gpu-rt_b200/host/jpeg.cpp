@@ -290,6 +290,9 @@ bool decode_jpeg(const std::vector<uint8_t>& f, Texture& out, std::string& err) 
             img_h = (s[1] << 8) | s[2], img_w = (s[3] << 8) | s[4], n_comp = s[5];
             if(!img_w || !img_h) return fail("empty image");
             if((uint64_t)img_w * img_h > (1ull << 28)) return fail("image larger than 2^28 pixels");
+            /* untrusted dimensions: a coded 8 x 8 block takes at least one bit, so a file of n bytes holds at most 8 n blocks =
+             * 512 n pixels — a header that promises more is refused before planes of that size are allocated */
+            if((uint64_t)img_w * img_h > 512ull * f.size()) return fail("image dimensions exceed what the file can encode");
             if(n_comp != 1 && n_comp != 3) return fail("only 1- and 3-component files are supported");
             if(sl < (size_t)(6 + 3 * n_comp)) return fail("bad SOF");
             static const char rgb[3] = {'R', 'G', 'B'};

@@ -86,6 +86,25 @@ static void mutate_text(std::vector<uint8_t>& d) {
             mutate_binary(d);
             continue;
         }
+        if(rnd_below(4) == 0) { /* type confusion: a whole [...] / {...} / "..." value becomes something else */
+            size_t b = rnd_below(d.size());
+            while(b < d.size() && d[b] != '[' && d[b] != '{' && d[b] != '"') b++;
+            if(b >= d.size()) continue;
+            size_t e = b + 1;
+            if(d[b] == '"') {
+                while(e < d.size() && d[e] != '"') e += d[e] == '\\' ? 2 : 1;
+                e = e < d.size() ? e + 1 : d.size();
+            } else {
+                int level = 1;
+                for(; e < d.size() && level; e++) level += (d[e] == '[' || d[e] == '{') - (d[e] == ']' || d[e] == '}');
+            }
+            if(e > d.size()) e = d.size();
+            static const char* repl[] = {"null", "0", "-1", "[]", "{}", "\"x\"", "[[]]", "{\"a\":{}}", "1e30", "true"};
+            const char* h = repl[rnd_below(sizeof(repl) / sizeof(repl[0]))];
+            d.erase(d.begin() + (long)b, d.begin() + (long)e);
+            d.insert(d.begin() + (long)b, (const uint8_t*)h, (const uint8_t*)h + strlen(h));
+            continue;
+        }
         /* find a numeric token starting at a random position and replace it */
         size_t start = rnd_below(d.size()), i = start;
         auto is_num = [](uint8_t c) { return (c >= '0' && c <= '9') || c == '-' || c == '.' || c == 'e' || c == 'E' || c == '+'; };
